@@ -1,0 +1,743 @@
+/*
+ * maxi_oracle.c -- TEST INFRASTRUCTURE ONLY. CPU restatement ("port") of the reference's
+ * per-sample DSP hot path in plain C, behind oracle_api.h.
+ *
+ * Parity status: PINNED. tests/test_oracle_vs_reference.py compares every function below
+ * bit-for-bit (fp64 and fp32 alike, integer state exactly) with the unmodified reference
+ * compiled from /root/reference (oracle/_ref/libmaxiref.so), and tests/test_golden.py
+ * compares it with the fixtures under tests/golden/ that were generated from that same
+ * compiled reference by tests/golden/make_golden.py. The reference's own tests hold no
+ * numeric expectations for this path, so the compiled reference
+ * is the only pin there is.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+ * legs may load this library; the product (maximilian_b200/) never does.
+ *
+ * Every function cites the reference lines it restates (paths relative to /root/reference).
+ * Build with -ffp-contract=off: the reference's evaluation order, without fused
+ * multiply-adds, is part of the contract (float FFT differs by 4e-6 of frame max otherwise).
+ * Uninitialised reference members (maxiDelayline::phase, all of maxiEnv, maxiOsc::output,
+ * mel filter column 0) are defined as zero, the value they have in zero-filled storage.
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "oracle_api.h"
+
+/* src/maximilian.h:55-58 */
+#define MAXI_PI 3.1415926535897932384626433832795
+#define MAXI_TWOPI 6.283185307179586476925286766559
+/* src/libs/fft.h:36-38 (glibc's M_PI has the same value) */
+#define FFT_M_PI 3.14159265358979323846
+
+const char* mxo_kind(void) { return "port"; }
+
+/* ================================================================= voices */
+
+typedef struct {
+    mxo_chain chain;
+    int V;
+    double* p[16];          /* parameter arrays, index = MXO_P_* */
+    /* oscillator state: src/maximilian.h:172-177 (phase, output) */
+    double* osc_out;        /* maxiOsc::output, read by square()/pulse() when no branch fires */
+    /* filter state */
+    double *f0, *f1, *f2;   /* lores/hires x,y | svf v0z,v1,v2 | biquad v[1],v[2] */
+    double *cf[5];          /* svf g1,g2,g3,g4,k | biquad a0,a1,a2,b1,b2 */
+    /* maxiEnv state: src/maximilian.h:895-917 */
+    double *env_amp, *env_output;
+    int64_t* env_holdcount;
+    int32_t* env_flags;     /* attack | decay<<1 | sustain<<2 | hold<<3 | release<<4 */
+    /* maxiDelayline state: src/maximilian.h:269,273 */
+    int32_t* dl_phase;
+    double* ring;           /* [V][delay_capacity] */
+} bank_t;
+
+static double* dalloc(size_t n, double fill) {
+    double* a = (double*)malloc(sizeof(double) * (n ? n : 1));
+    if (a) for (size_t i = 0; i < n; ++i) a[i] = fill;
+    return a;
+}
+
+/* maxiSVF::setParams, src/maximilian.h:1322-1334 (sampleRate is a size_t there) */
+static void svf_set_params(const bank_t* b, int v) {
+    const double sr = (double)(size_t)b->chain.sample_rate;
+    const double freq = b->p[MXO_P_CUTOFF][v], res = b->p[MXO_P_RESONANCE][v];
+    const double g = tan(MAXI_PI * freq / sr);
+    const double damping = res == 0 ? 0 : 1.0 / res;
+    const double k = damping;
+    const double ginv = g / (1.0 + g * (g + k));
+    b->cf[0][v] = ginv;                    /* g1 */
+    b->cf[1][v] = 2.0 * (g + k) * ginv;    /* g2 */
+    b->cf[2][v] = g * ginv;                /* g3 */
+    b->cf[3][v] = 2.0 * ginv;              /* g4 */
+    b->cf[4][v] = k;
+}
+
+/* maxiBiquad::set, src/maximilian.h:1375-1479. abs() there resolves to the double overload. */
+static void biquad_set(const bank_t* b, int v) {
+    const double sr = (double)(size_t)b->chain.sample_rate;
+    const double cutoff = b->p[MXO_P_CUTOFF][v], Q = b->p[MXO_P_RESONANCE][v], peakGain = b->p[MXO_P_GAIN][v];
+    const double SQRT2 = sqrt(2.0);                      /* src/maximilian.h:1484 */
+    double norm = 0, a0 = 0, a1 = 0, a2 = 0, b1 = 0, b2 = 0;
+    const double Vg = pow(10.0, fabs(peakGain) / 20.0);
+    const double K = tan(MAXI_PI * cutoff / sr);
+    switch (b->chain.biquad_type) {
+        case 0: /* LOWPASS :1381-1388 */
+            norm = 1.0 / (1.0 + K / Q + K * K);
+            a0 = K * K * norm; a1 = 2.0 * a0; a2 = a0;
+            b1 = 2.0 * (K * K - 1.0) * norm; b2 = (1.0 - K / Q + K * K) * norm; break;
+        case 1: /* HIGHPASS :1390-1397 */
+            norm = 1. / (1. + K / Q + K * K);
+            a0 = 1 * norm; a1 = -2 * a0; a2 = a0;
+            b1 = 2 * (K * K - 1) * norm; b2 = (1 - K / Q + K * K) * norm; break;
+        case 2: /* BANDPASS :1399-1406 */
+            norm = 1. / (1. + K / Q + K * K);
+            a0 = K / Q * norm; a1 = 0.; a2 = -a0;
+            b1 = 2. * (K * K - 1.) * norm; b2 = (1. - K / Q + K * K) * norm; break;
+        case 3: /* NOTCH :1408-1415 */
+            norm = 1. / (1. + K / Q + K * K);
+            a0 = (1. + K * K) * norm; a1 = 2. * (K * K - 1.) * norm; a2 = a0;
+            b1 = a1; b2 = (1. - K / Q + K * K) * norm; break;
+        case 4: /* PEAK :1417-1436 */
+            if (peakGain >= 0.0) {
+                norm = 1. / (1. + 1. / Q * K + K * K);
+                a0 = (1. + Vg / Q * K + K * K) * norm; a1 = 2. * (K * K - 1.) * norm;
+                a2 = (1. - Vg / Q * K + K * K) * norm; b1 = a1; b2 = (1. - 1. / Q * K + K * K) * norm;
+            } else {
+                norm = 1. / (1. + Vg / Q * K + K * K);
+                a0 = (1. + 1 / Q * K + K * K) * norm; a1 = 2. * (K * K - 1) * norm;
+                a2 = (1. - 1. / Q * K + K * K) * norm; b1 = a1; b2 = (1. - Vg / Q * K + K * K) * norm;
+            }
+            break;
+        case 5: /* LOWSHELF :1437-1456 */
+            if (peakGain >= 0.) {
+                norm = 1. / (1. + SQRT2 * K + K * K);
+                a0 = (1. + sqrt(2. * Vg) * K + Vg * K * K) * norm; a1 = 2. * (Vg * K * K - 1.) * norm;
+                a2 = (1. - sqrt(2. * Vg) * K + Vg * K * K) * norm;
+                b1 = 2. * (K * K - 1.) * norm; b2 = (1. - SQRT2 * K + K * K) * norm;
+            } else {
+                norm = 1. / (1. + sqrt(2. * Vg) * K + Vg * K * K);
+                a0 = (1. + SQRT2 * K + K * K) * norm; a1 = 2. * (K * K - 1.) * norm;
+                a2 = (1. - SQRT2 * K + K * K) * norm;
+                b1 = 2. * (Vg * K * K - 1.) * norm; b2 = (1. - sqrt(2. * Vg) * K + Vg * K * K) * norm;
+            }
+            break;
+        case 6: /* HIGHSHELF :1457-1476 */
+            if (peakGain >= 0.) {
+                norm = 1. / (1. + SQRT2 * K + K * K);
+                a0 = (Vg + sqrt(2. * Vg) * K + K * K) * norm; a1 = 2. * (K * K - Vg) * norm;
+                a2 = (Vg - sqrt(2. * Vg) * K + K * K) * norm;
+                b1 = 2. * (K * K - 1) * norm; b2 = (1. - SQRT2 * K + K * K) * norm;
+            } else {
+                norm = 1. / (Vg + sqrt(2. * Vg) * K + K * K);
+                a0 = (1. + SQRT2 * K + K * K) * norm; a1 = 2. * (K * K - 1.) * norm;
+                a2 = (1. - SQRT2 * K + K * K) * norm;
+                b1 = 2. * (K * K - Vg) * norm; b2 = (Vg - sqrt(2. * Vg) * K + K * K) * norm;
+            }
+            break;
+        default: break;
+    }
+    b->cf[0][v] = a0; b->cf[1][v] = a1; b->cf[2][v] = a2; b->cf[3][v] = b1; b->cf[4][v] = b2;
+}
+
+void* mxo_bank_create(const mxo_chain* chain, int32_t voices) {
+    if (!chain || voices <= 0) return NULL;
+    bank_t* b = (bank_t*)calloc(1, sizeof(bank_t));
+    if (!b) return NULL;
+    const size_t V = (size_t)voices;
+    b->chain = *chain;
+    b->V = voices;
+    for (int i = 0; i <= MXO_P_PAN; ++i) b->p[i] = dalloc(V, 0.0);
+    for (size_t v = 0; v < V; ++v) {
+        b->p[MXO_P_DUTY][v] = 0.5; b->p[MXO_P_DELAY_SIZE][v] = 1.0; b->p[MXO_P_PAN][v] = 0.5;
+        b->p[MXO_P_ENV_HOLDTIME][v] = 1.0;          /* src/maximilian.h:913 */
+        b->p[MXO_P_CUTOFF][v] = 1000.0; b->p[MXO_P_RESONANCE][v] = 1.0;   /* maxiSVF ctor, src/maximilian.h:1284 */
+    }
+    b->osc_out = dalloc(V, 0.0);
+    b->f0 = dalloc(V, 0.0); b->f1 = dalloc(V, 0.0); b->f2 = dalloc(V, 0.0);
+    for (int i = 0; i < 5; ++i) b->cf[i] = dalloc(V, 0.0);   /* maxiBiquad coefficients default to 0, src/maximilian.h:1482 */
+    b->env_amp = dalloc(V, 0.0); b->env_output = dalloc(V, 0.0);
+    b->env_holdcount = (int64_t*)calloc(V, sizeof(int64_t));
+    b->env_flags = (int32_t*)calloc(V, sizeof(int32_t));
+    b->dl_phase = (int32_t*)calloc(V, sizeof(int32_t));
+    if (chain->filt_kind == MXO_FILT_SVF) for (int v = 0; v < voices; ++v) svf_set_params(b, v);
+    if (chain->delay_on) {
+        if (chain->delay_capacity <= 0) { free(b); return NULL; }
+        b->ring = (double*)calloc(V * (size_t)chain->delay_capacity, sizeof(double));  /* ctor memset, src/maximilian.cpp:415-417 */
+        if (!b->ring) { free(b); return NULL; }
+    }
+    return b;
+}
+
+void mxo_bank_destroy(void* h) {
+    bank_t* b = (bank_t*)h;
+    if (!b) return;
+    for (int i = 0; i < 16; ++i) free(b->p[i]);
+    free(b->osc_out); free(b->f0); free(b->f1); free(b->f2);
+    for (int i = 0; i < 5; ++i) free(b->cf[i]);
+    free(b->env_amp); free(b->env_output); free(b->env_holdcount); free(b->env_flags);
+    free(b->dl_phase); free(b->ring); free(b);
+}
+
+int32_t mxo_bank_set(void* h, int32_t id, const double* x) {
+    bank_t* b = (bank_t*)h;
+    if (!b || !x || id < 0 || id > MXO_P_PAN) return -1;
+    memcpy(b->p[id], x, sizeof(double) * (size_t)b->V);
+    if (id == MXO_P_CUTOFF || id == MXO_P_RESONANCE || id == MXO_P_GAIN) {
+        if (b->chain.filt_kind == MXO_FILT_SVF) for (int v = 0; v < b->V; ++v) svf_set_params(b, v);
+        if (b->chain.filt_kind == MXO_FILT_BIQUAD) for (int v = 0; v < b->V; ++v) biquad_set(b, v);
+    }
+    return 0;
+}
+
+int32_t mxo_bank_get(void* h, int32_t id, double* x) {
+    bank_t* b = (bank_t*)h;
+    if (!b || !x) return -1;
+    for (int v = 0; v < b->V; ++v) {
+        switch (id) {
+            case MXO_S_FILT_0: x[v] = b->f0[v]; break;
+            case MXO_S_FILT_1: x[v] = b->f1[v]; break;
+            case MXO_S_FILT_2: x[v] = b->chain.filt_kind == MXO_FILT_SVF ? b->f2[v] : 0.0; break;
+            case MXO_S_ENV_AMPLITUDE: x[v] = b->env_amp[v]; break;
+            case MXO_S_ENV_OUTPUT: x[v] = b->env_output[v]; break;
+            case MXO_S_ENV_HOLDCOUNT: x[v] = (double)b->env_holdcount[v]; break;
+            case MXO_S_ENV_FLAGS: x[v] = (double)b->env_flags[v]; break;
+            case MXO_S_DELAY_PHASE: x[v] = (double)b->dl_phase[v]; break;
+            default: if (id >= 0 && id <= MXO_P_PAN) x[v] = b->p[id][v]; else return -1;
+        }
+    }
+    return 0;
+}
+
+int32_t mxo_bank_get_ring(void* h, int32_t v, double* dst, int32_t n) {
+    bank_t* b = (bank_t*)h;
+    if (!b || !b->ring || v < 0 || v >= b->V || n < 0 || n > b->chain.delay_capacity) return -1;
+    memcpy(dst, b->ring + (size_t)v * (size_t)b->chain.delay_capacity, sizeof(double) * (size_t)n);
+    return 0;
+}
+
+/* maxiOsc::*, src/maximilian.cpp:228-235 (sinewave), 276-283 (coswave), 285-291 (phasor),
+ * 293-300 (square), 302-311 (pulse), 312-319 (impulse), 333-340 (saw), 362-373 (triangle).
+ * The increment is 1./(sampleRate/frequency) with sampleRate a size_t: two divides, kept. */
+static inline double osc_tick(int kind, double* phase_p, double* output_p, double frequency, double duty, double sr) {
+    double phase = *phase_p, output = *output_p;
+    switch (kind) {
+        case MXO_OSC_SINEWAVE:
+            output = sin(phase * (MAXI_TWOPI));
+            if (phase >= 1.0) phase -= 1.0;
+            phase += (1. / (sr / (frequency)));
+            break;
+        case MXO_OSC_COSWAVE:
+            output = cos(phase * (MAXI_TWOPI));
+            if (phase >= 1.0) phase -= 1.0;
+            phase += (1. / (sr / (frequency)));
+            break;
+        case MXO_OSC_PHASOR:
+            output = phase;
+            if (phase >= 1.0) phase -= 1.0;
+            phase += (1. / (sr / (frequency)));
+            break;
+        case MXO_OSC_SAW:
+            output = phase;
+            if (phase >= 1.0) phase -= 2.0;
+            phase += (1. / (sr / (frequency))) * 2.0;
+            break;
+        case MXO_OSC_SQUARE:
+            if (phase < 0.5) output = -1;
+            if (phase > 0.5) output = 1;
+            if (phase >= 1.0) phase -= 1.0;
+            phase += (1. / (sr / (frequency)));
+            break;
+        case MXO_OSC_PULSE:
+            if (duty < 0.) duty = 0;
+            if (duty > 1.) duty = 1;
+            if (phase >= 1.0) phase -= 1.0;
+            phase += (1. / (sr / (frequency)));
+            if (phase < duty) output = -1.;
+            if (phase > duty) output = 1.;
+            break;
+        case MXO_OSC_IMPULSE: {
+            if (phase >= 1.0) phase -= 1.0;
+            double phaseInc = (1. / (sr / (frequency)));
+            double o = phase < phaseInc ? 1.0 : 0.0;     /* a local in the reference: the member is untouched */
+            phase += phaseInc;
+            *phase_p = phase;
+            return o;
+        }
+        case MXO_OSC_TRIANGLE:
+            if (phase >= 1.0) phase -= 1.0;
+            phase += (1. / (sr / (frequency)));
+            if (phase <= 0.5) output = (phase - 0.25) * 4;
+            else output = ((1.0 - phase) - 0.25) * 4;
+            break;
+        default: break;
+    }
+    *phase_p = phase; *output_p = output;
+    return output;
+}
+
+/* maxiEnv::adsr(double input, int trigger), src/maximilian.cpp:1415-1466 */
+static inline double env_adsr(bank_t* b, int v, double input, int trigger) {
+    int fl = b->env_flags[v];
+    int attackphase = fl & 1, decayphase = (fl >> 1) & 1, sustainphase = (fl >> 2) & 1,
+        holdphase = (fl >> 3) & 1, releasephase = (fl >> 4) & 1;
+    double amplitude = b->env_amp[v], output = b->env_output[v];
+    int64_t holdcount = b->env_holdcount[v];
+    const double attack = b->p[MXO_P_ENV_ATTACK][v], decay = b->p[MXO_P_ENV_DECAY][v],
+                 sustain = b->p[MXO_P_ENV_SUSTAIN][v], release = b->p[MXO_P_ENV_RELEASE][v];
+    const int64_t holdtime = (int64_t)b->p[MXO_P_ENV_HOLDTIME][v];
+
+    if (trigger == 1 && attackphase != 1 && holdphase != 1 && decayphase != 1) {
+        holdcount = 0; decayphase = 0; sustainphase = 0; releasephase = 0; attackphase = 1;
+    }
+    if (attackphase == 1) {
+        releasephase = 0;
+        amplitude += (1 * attack);
+        output = input * amplitude;
+        if (amplitude >= 1) { amplitude = 1; attackphase = 0; decayphase = 1; }
+    }
+    if (decayphase == 1) {
+        output = input * (amplitude *= decay);
+        if (amplitude <= sustain) { decayphase = 0; holdphase = 1; }
+    }
+    if (holdcount < holdtime && holdphase == 1) { output = input * amplitude; holdcount++; }
+    if (holdcount >= holdtime && trigger == 1) { output = input * amplitude; }
+    if (holdcount >= holdtime && trigger != 1) { holdphase = 0; releasephase = 1; }
+    if (releasephase == 1 && amplitude > 0.) { output = input * (amplitude *= release); }
+
+    b->env_flags[v] = attackphase | decayphase << 1 | sustainphase << 2 | holdphase << 3 | releasephase << 4;
+    b->env_amp[v] = amplitude; b->env_output[v] = output; b->env_holdcount[v] = holdcount;
+    return output;
+}
+
+int32_t mxo_bank_process(void* h, int32_t nframes, const int32_t* trig_on, const int32_t* trig_off,
+                         double* out, double* mix, int32_t first, int32_t count) {
+    bank_t* b = (bank_t*)h;
+    if (!b || nframes < 0 || first < 0 || count < 0 || first + count > b->V) return -1;
+    const mxo_chain* c = &b->chain;
+    const int V = b->V;
+    const double sr = (double)(size_t)c->sample_rate;     /* maxiSettings::sampleRate is a size_t, src/maximilian.h:124 */
+    for (int t = 0; t < nframes; ++t) {
+        double m0 = 0.0, m1 = 0.0;
+        for (int v = first; v < first + count; ++v) {
+            double x = osc_tick(c->osc_kind, &b->p[MXO_P_PHASE][v], &b->osc_out[v], b->p[MXO_P_FREQ][v], b->p[MXO_P_DUTY][v], sr);
+            if (c->env_kind == MXO_ENV_ADSR) {
+                int trig = (trig_on && trig_off && t >= trig_on[v] && t < trig_off[v]) ? 1 : 0;
+                x = env_adsr(b, v, x, trig);
+            }
+            switch (c->filt_kind) {
+                case MXO_FILT_LORES:
+                case MXO_FILT_HIRES: {
+                    /* maxiFilter::lores / hires, src/maximilian.cpp:455-468 / 471-484 */
+                    double input = x, cutoff = b->p[MXO_P_CUTOFF][v], resonance = b->p[MXO_P_RESONANCE][v];
+                    double fx = b->f0[v], fy = b->f1[v];
+                    if (cutoff < 10) cutoff = 10;
+                    if (cutoff > sr) cutoff = sr;
+                    if (resonance < 1.) resonance = 1.;
+                    double z = cos(MAXI_TWOPI * cutoff / sr);
+                    double cc = 2 - 2 * z;
+                    double r = (sqrt(2.0) * sqrt(-pow((z - 1.0), 3.0)) + resonance * (z - 1)) / (resonance * (z - 1));
+                    fx = fx + (input - fy) * cc;
+                    fy = fy + fx;
+                    fx = fx * r;
+                    b->f0[v] = fx; b->f1[v] = fy;
+                    x = (c->filt_kind == MXO_FILT_LORES) ? fy : input - fy;
+                    break;
+                }
+                case MXO_FILT_SVF: {
+                    /* maxiSVF::play, src/maximilian.h:1305-1319 */
+                    const double g1 = b->cf[0][v], g2 = b->cf[1][v], g3 = b->cf[2][v], g4 = b->cf[3][v], k = b->cf[4][v];
+                    double w = x, v0z = b->f0[v], v1 = b->f1[v], v2 = b->f2[v];
+                    double low, band, high, notch;
+                    double v1z = v1;
+                    double v2z = v2;
+                    double v3 = w + v0z - 2.0 * v2z;
+                    v1 += g1 * v3 - g2 * v1z;
+                    v2 += g3 * v3 + g4 * v1z;
+                    v0z = w;
+                    low = v2;
+                    band = v1;
+                    high = w - k * v1 - v2;
+                    notch = w - k * v1;
+                    b->f0[v] = v0z; b->f1[v] = v1; b->f2[v] = v2;
+                    x = (low * c->svf_mix[0]) + (band * c->svf_mix[1]) + (high * c->svf_mix[2]) + (notch * c->svf_mix[3]);
+                    break;
+                }
+                case MXO_FILT_BIQUAD: {
+                    /* maxiBiquad::play, src/maximilian.h:1360-1367 */
+                    const double a0 = b->cf[0][v], a1 = b->cf[1][v], a2 = b->cf[2][v], b1 = b->cf[3][v], b2 = b->cf[4][v];
+                    double v1 = b->f0[v], v2 = b->f1[v];
+                    double v0 = x - (b1 * v1) - (b2 * v2);
+                    double y = (a0 * v0) + (a1 * v1) + (a2 * v2);
+                    b->f1[v] = v1; b->f0[v] = v0;
+                    x = y;
+                    break;
+                }
+                default: break;
+            }
+            if (c->delay_on) {
+                /* maxiDelayline::dl, src/maximilian.cpp:420-429 */
+                const int size = (int)b->p[MXO_P_DELAY_SIZE][v];
+                const double feedback = b->p[MXO_P_DELAY_FEEDBACK][v];
+                double* memory = b->ring + (size_t)v * (size_t)c->delay_capacity;
+                int phase = b->dl_phase[v];
+                if (phase >= size) phase = 0;
+                if (phase < 0 || phase >= c->delay_capacity) return -4;   /* the reference would index out of its 705600 slots */
+                double output = memory[phase];
+                memory[phase] = (memory[phase] * feedback) + (x * feedback) * 0.5;
+                phase += 1;
+                b->dl_phase[v] = phase;
+                x = output;
+            }
+            if (out) out[(size_t)t * (size_t)V + (size_t)v] = x;
+            if (mix) {
+                /* maxiMix::stereo, src/maximilian.cpp:503-509 */
+                double px = b->p[MXO_P_PAN][v];
+                if (px > 1) px = 1;
+                if (px < 0) px = 0;
+                m0 += x * sqrt(1.0 - px);
+                m1 += x * sqrt(px);
+            }
+        }
+        if (mix) { mix[2 * t] = m0; mix[2 * t + 1] = m1; }
+    }
+    return 0;
+}
+
+/* maxiEnv::setAttack / setAttackMS / setDecay (= setRelease), src/maximilian.cpp:1469-1486 */
+double mxo_env_attack_coeff(double attackMS, int32_t sr) { return 1 - pow(0.01, 1.0 / (attackMS * (double)(size_t)sr * 0.001)); }
+double mxo_env_attack_ms_coeff(double attackMS, int32_t sr) { return 1.0 / (attackMS / 1000.0 * (double)(size_t)sr); }
+double mxo_env_decay_coeff(double ms, int32_t sr) { return pow(0.01, 1.0 / (ms * (double)(size_t)sr * 0.001)); }
+
+/* ==================================================================== FFT */
+
+/* ReverseBits, src/libs/fft.cpp:75-85 (the lazily built gFFTBitTable, :87-112, holds the same values) */
+static int reverse_bits(int index, int NumBits) {
+    int i, rev;
+    for (i = rev = 0; i < NumBits; i++) { rev = (rev << 1) | (index & 1); index >>= 1; }
+    return rev;
+}
+static int bits_needed(int PowerOfTwo) { int i; for (i = 0;; i++) if (PowerOfTwo & (1 << i)) return i; }
+
+/* FFT(), src/libs/fft.cpp:118-211: radix-2 decimation in time, float data, float twiddle recurrence
+ * restarted for every block, /N on the inverse. */
+static void ref_FFT(int NumSamples, int InverseTransform, const float* RealIn, const float* ImagIn,
+                    float* RealOut, float* ImagOut) {
+    int NumBits, i, j, k, n, BlockSize, BlockEnd;
+    double angle_numerator = 2.0 * FFT_M_PI;
+    float tr, ti;
+    if (InverseTransform) angle_numerator = -angle_numerator;
+    NumBits = bits_needed(NumSamples);
+    for (i = 0; i < NumSamples; i++) {
+        j = reverse_bits(i, NumBits);
+        RealOut[j] = RealIn[i];
+        ImagOut[j] = (ImagIn == NULL) ? 0.0 : ImagIn[i];
+    }
+    BlockEnd = 1;
+    for (BlockSize = 2; BlockSize <= NumSamples; BlockSize <<= 1) {
+        double delta_angle = angle_numerator / (double)BlockSize;
+        float sm2 = sin(-2 * delta_angle);
+        float sm1 = sin(-delta_angle);
+        float cm2 = cos(-2 * delta_angle);
+        float cm1 = cos(-delta_angle);
+        float w = 2 * cm1;
+        float ar0, ar1, ar2, ai0, ai1, ai2;
+        for (i = 0; i < NumSamples; i += BlockSize) {
+            ar2 = cm2; ar1 = cm1;
+            ai2 = sm2; ai1 = sm1;
+            for (j = i, n = 0; n < BlockEnd; j++, n++) {
+                ar0 = w * ar1 - ar2; ar2 = ar1; ar1 = ar0;
+                ai0 = w * ai1 - ai2; ai2 = ai1; ai1 = ai0;
+                k = j + BlockEnd;
+                tr = ar0 * RealOut[k] - ai0 * ImagOut[k];
+                ti = ar0 * ImagOut[k] + ai0 * RealOut[k];
+                RealOut[k] = RealOut[j] - tr;
+                ImagOut[k] = ImagOut[j] - ti;
+                RealOut[j] += tr;
+                ImagOut[j] += ti;
+            }
+        }
+        BlockEnd = BlockSize;
+    }
+    if (InverseTransform) {
+        float denom = (float)NumSamples;
+        for (i = 0; i < NumSamples; i++) { RealOut[i] /= denom; ImagOut[i] /= denom; }
+    }
+}
+
+/* RealFFT(), src/libs/fft.cpp:228-282. The double literals (0.5, -2.0, 1.0) promote their
+ * sub-expressions to double before the result narrows back to float; kept as written. */
+static void ref_RealFFT(int NumSamples, const float* RealIn, float* RealOut, float* ImagOut, float* tmpReal, float* tmpImag) {
+    int Half = NumSamples / 2;
+    int i;
+    float theta = FFT_M_PI / Half;
+    for (i = 0; i < Half; i++) { tmpReal[i] = RealIn[2 * i]; tmpImag[i] = RealIn[2 * i + 1]; }
+    ref_FFT(Half, 0, tmpReal, tmpImag, RealOut, ImagOut);
+    float wtemp = (float)(sin(0.5 * theta));
+    float wpr = -2.0 * wtemp * wtemp;
+    float wpi = (float)(sin(theta));
+    float wr = 1.0 + wpr;
+    float wi = wpi;
+    int i3;
+    float h1r, h1i, h2r, h2i;
+    for (i = 1; i < Half / 2; i++) {
+        i3 = Half - i;
+        h1r = 0.5 * (RealOut[i] + RealOut[i3]);
+        h1i = 0.5 * (ImagOut[i] - ImagOut[i3]);
+        h2r = 0.5 * (ImagOut[i] + ImagOut[i3]);
+        h2i = -0.5 * (RealOut[i] - RealOut[i3]);
+        RealOut[i] = h1r + wr * h2r - wi * h2i;
+        ImagOut[i] = h1i + wr * h2i + wi * h2r;
+        RealOut[i3] = h1r - wr * h2r + wi * h2i;
+        ImagOut[i3] = -h1i + wr * h2i + wi * h2r;
+        wtemp = wr;
+        wr = wtemp * wpr - wi * wpi + wr;
+        wi = wi * wpr + wtemp * wpi + wi;
+    }
+    h1r = RealOut[0];
+    RealOut[0] = h1r + ImagOut[0];
+    ImagOut[0] = h1r - ImagOut[0];
+}
+
+/* fft::genWindow(3, ...), src/libs/fft.cpp:409-413 (Hann, computed in double, stored as float) */
+static void gen_hann(int NumSamples, float* window) {
+    for (int i = 0; i < NumSamples; i++) window[i] = 0.50 - 0.50 * cos(2 * FFT_M_PI * i / (NumSamples - 1));
+}
+
+typedef struct {
+    int C, n, hop, bins;
+    int* pos;                       /* maxiFFT::pos per channel */
+    float* buffer;                  /* [C][n]   maxiFFT::buffer */
+    float* window;                  /* [n] */
+    float *in_real, *out_real, *out_img, *tmpR, *tmpI;   /* fft::in_real ... (scratch, one channel at a time) */
+} stft_t;
+
+/* maxiFFT::setup, src/libs/maxiFFT.cpp:45-60 (windowSize == fftSize) */
+void* mxo_stft_create(int32_t channels, int32_t fft_size, int32_t hop_size) {
+    if (channels <= 0 || fft_size < 4 || (fft_size & (fft_size - 1)) || hop_size <= 0 || hop_size > fft_size) return NULL;
+    stft_t* s = (stft_t*)calloc(1, sizeof(stft_t));
+    s->C = channels; s->n = fft_size; s->hop = hop_size; s->bins = fft_size / 2;
+    s->pos = (int*)malloc(sizeof(int) * (size_t)channels);
+    for (int c = 0; c < channels; ++c) s->pos[c] = fft_size - hop_size;
+    s->buffer = (float*)calloc((size_t)channels * (size_t)fft_size, sizeof(float));
+    s->window = (float*)calloc((size_t)fft_size, sizeof(float));
+    gen_hann(fft_size, s->window);
+    s->in_real = (float*)calloc((size_t)fft_size, sizeof(float));
+    s->out_real = (float*)calloc((size_t)fft_size, sizeof(float));
+    s->out_img = (float*)calloc((size_t)fft_size, sizeof(float));
+    s->tmpR = (float*)calloc((size_t)fft_size, sizeof(float));
+    s->tmpI = (float*)calloc((size_t)fft_size, sizeof(float));
+    return s;
+}
+void mxo_stft_destroy(void* h) {
+    stft_t* s = (stft_t*)h; if (!s) return;
+    free(s->pos); free(s->buffer); free(s->window); free(s->in_real); free(s->out_real); free(s->out_img);
+    free(s->tmpR); free(s->tmpI); free(s);
+}
+int32_t mxo_stft_window(void* h, float* w) {
+    stft_t* s = (stft_t*)h; if (!s || !w) return -1;
+    memcpy(w, s->window, sizeof(float) * (size_t)s->n); return 0;
+}
+
+/* maxiFFT::process, src/libs/maxiFFT.cpp:65-91 -> fft::powerSpectrum, src/libs/fft.cpp:519-524
+ * = calcFFT :499-505 + cartToPol :507-515 (sqrt/atan2 on floats are the float overloads) */
+int32_t mxo_stft_process(void* h, const float* in, int32_t n, int32_t max_frames,
+                         float* mags, float* phases, float* re, float* im) {
+    stft_t* s = (stft_t*)h;
+    if (!s || !in || n < 0) return -1;
+    int frames = 0;
+    for (int c = 0; c < s->C; ++c) {
+        float* buffer = s->buffer + (size_t)c * (size_t)s->n;
+        int pos = s->pos[c];
+        int k = 0;
+        for (int t = 0; t < n; ++t) {
+            buffer[pos++] = in[(size_t)c * (size_t)n + (size_t)t];
+            if (pos == s->n) {
+                if (k >= max_frames) return -3;
+                for (int i = 0; i < s->n; i++) s->in_real[i] = buffer[i] * s->window[i];
+                ref_RealFFT(s->n, s->in_real, s->out_real, s->out_img, s->tmpR, s->tmpI);
+                size_t o = ((size_t)c * (size_t)max_frames + (size_t)k) * (size_t)s->bins;
+                for (int i = 0; i < s->bins; i++) {
+                    float power = s->out_real[i] * s->out_real[i] + s->out_img[i] * s->out_img[i];
+                    if (mags) mags[o + i] = sqrtf(power);
+                    if (phases) phases[o + i] = atan2f(s->out_img[i], s->out_real[i]);
+                    if (re) re[o + i] = s->out_real[i];
+                    if (im) im[o + i] = s->out_img[i];
+                }
+                memmove(buffer, buffer + s->hop, sizeof(float) * (size_t)(s->n - s->hop));
+                pos = s->n - s->hop;
+                ++k;
+            }
+        }
+        s->pos[c] = pos;
+        frames = k;
+    }
+    return frames;
+}
+
+/* =================================================================== MFCC */
+
+typedef struct {
+    unsigned numBins, numFilters, numCoeffs;
+    double* melFilters;   /* idx = filter + bin*numFilters, src/libs/maxiMFCC.h:157 */
+    double* dctMatrix;    /* idx = i + j*numCoeffs,        src/libs/maxiMFCC.h:194 */
+    double* melBands;
+} mfcc_t;
+
+static double hzToMel(double hz) { return 2595.0 * (log10(hz / 700.0 + 1.0)); }        /* maxiMFCC.h:30-32 */
+static double melToHz(double mel) { return 700.0 * (pow(10, mel / 2595.0) - 1.0); }    /* maxiMFCC.h:36-38 */
+
+/* maxiMFCCAnalyser<double>::setup :56-75, calcMelFilterBank :118-182, createDCTCoeffs :183-203 */
+void* mxo_mfcc_create(int32_t num_bins, int32_t num_filters, int32_t num_coeffs,
+                      double minFreq, double maxFreq, int32_t sample_rate) {
+    if (num_bins <= 0 || num_filters <= 0 || num_coeffs <= 0) return NULL;
+    mfcc_t* m = (mfcc_t*)calloc(1, sizeof(mfcc_t));
+    const unsigned numBins = (unsigned)num_bins, numFilters = (unsigned)num_filters, numCoeffs = (unsigned)num_coeffs;
+    m->numBins = numBins; m->numFilters = numFilters; m->numCoeffs = numCoeffs;
+    m->melBands = (double*)calloc(numFilters, sizeof(double));
+    m->dctMatrix = (double*)calloc((size_t)numCoeffs * numFilters, sizeof(double));
+    /* column 0 (filter 0) is never written by the reference (loop starts at 1, :149): zero */
+    m->melFilters = (double*)calloc((size_t)numFilters * numBins, sizeof(double));
+    {
+        const double sampleRate = (double)(unsigned)sample_rate;
+        double mel, dMel, maxMel, minMel, nyquist, binFreq, start, thisF, nextF, prevF;
+        nyquist = sampleRate / 2;
+        if (maxFreq > nyquist) maxFreq = nyquist;
+        maxMel = hzToMel(maxFreq);
+        minMel = hzToMel(minFreq);
+        dMel = (maxMel - minMel) / (numFilters + 2 - 1);
+        double* filtPos = (double*)malloc(sizeof(double) * (numFilters + 2));
+        mel = minMel;
+        for (unsigned i = 0; i < numFilters + 2; i++) { filtPos[i] = melToHz(mel); mel += dMel; }
+        for (unsigned filter = 1; filter < numFilters; filter++) {
+            for (unsigned bin = 0; bin < numBins; bin++) {
+                binFreq = (double)sampleRate / (double)(int)numBins * (double)(int)bin;   /* sr/numBins, not sr/fftSize: SURVEY.md A13 */
+                thisF = filtPos[filter]; nextF = filtPos[filter + 1]; prevF = filtPos[filter - 1];
+                size_t idx = filter + ((size_t)bin * numFilters);
+                if (binFreq > nextF || binFreq < prevF) {
+                    m->melFilters[idx] = 0;
+                } else {
+                    double height = 2.0 / (nextF - prevF);
+                    if (binFreq < thisF) {
+                        start = prevF;
+                        m->melFilters[idx] = (binFreq - start) * (height / (thisF - start));
+                    } else {
+                        m->melFilters[idx] = height + ((binFreq - thisF) * (-height / (nextF - thisF)));
+                    }
+                }
+            }
+        }
+        free(filtPos);
+    }
+    {
+        double k = 3.14159265358979323846 / numFilters;
+        double w1 = 1.0 / (sqrt((double)numFilters));
+        double w2 = sqrt(2.0 / numFilters);
+        for (unsigned i = 0; i < numCoeffs; i++) {
+            for (unsigned j = 0; j < numFilters; j++) {
+                size_t idx = i + ((size_t)j * numCoeffs);
+                if (i == 0) m->dctMatrix[idx] = w1 * cos(k * (int)(i + 1) * ((int)j + 0.5));
+                else m->dctMatrix[idx] = w2 * cos(k * (int)(i + 1) * ((int)j + 0.5));
+            }
+        }
+    }
+    return m;
+}
+void mxo_mfcc_destroy(void* h) { mfcc_t* m = (mfcc_t*)h; if (!m) return; free(m->melFilters); free(m->dctMatrix); free(m->melBands); free(m); }
+
+/* maxiMFCC::mfcc :77-81 = melFilterAndLogSq_Part2 (src/libs/maxiMFCC.cpp:48-66) + dct (maxiMFCC.h:98-111) */
+int32_t mxo_mfcc_process(void* h, const float* mags, int32_t n, double* coeffs, double* melbands) {
+    mfcc_t* m = (mfcc_t*)h;
+    if (!m || !mags || !coeffs) return -1;
+    for (int f = 0; f < n; ++f) {
+        const float* powerSpectrum = mags + (size_t)f * m->numBins;
+        double* mfccs = coeffs + (size_t)f * m->numCoeffs;
+        for (unsigned filter = 0; filter < m->numFilters; filter++) {
+            m->melBands[filter] = 0.0;
+            for (unsigned bin = 0; bin < m->numBins; bin++) {
+                size_t idx = filter + ((size_t)bin * m->numFilters);
+                m->melBands[filter] += (m->melFilters[idx] * powerSpectrum[bin]);
+            }
+        }
+        for (unsigned filter = 0; filter < m->numFilters; filter++)
+            m->melBands[filter] = m->melBands[filter] > 0.000001 ? log(m->melBands[filter] * m->melBands[filter]) : 0.0;
+        for (unsigned i = 0; i < m->numCoeffs; i++) mfccs[i] = 0.0;
+        for (unsigned i = 0; i < m->numCoeffs; i++)
+            for (unsigned j = 0; j < m->numFilters; j++) {
+                size_t idx = i + ((size_t)j * m->numCoeffs);
+                mfccs[i] += (m->dctMatrix[idx] * m->melBands[j]);
+            }
+        for (unsigned i = 0; i < m->numCoeffs; i++) mfccs[i] /= m->numCoeffs;
+        if (melbands) memcpy(melbands + (size_t)f * m->numFilters, m->melBands, sizeof(double) * m->numFilters);
+    }
+    return 0;
+}
+
+/* ================================================================== ISTFT */
+
+typedef struct {
+    int C, n, hop, bins;
+    int* pos;
+    float* buffer;        /* [C][n] maxiIFFT::buffer */
+    float* window;
+    float *ifftOut, *in_real, *in_img, *out_real, *out_img;
+} istft_t;
+
+/* maxiIFFT::setup, src/libs/maxiFFT.cpp:141-152 */
+void* mxo_istft_create(int32_t channels, int32_t fft_size, int32_t hop_size) {
+    if (channels <= 0 || fft_size < 4 || (fft_size & (fft_size - 1)) || hop_size <= 0 || hop_size > fft_size) return NULL;
+    istft_t* s = (istft_t*)calloc(1, sizeof(istft_t));
+    s->C = channels; s->n = fft_size; s->hop = hop_size; s->bins = fft_size / 2;
+    s->pos = (int*)calloc((size_t)channels, sizeof(int));
+    s->buffer = (float*)calloc((size_t)channels * (size_t)fft_size, sizeof(float));
+    s->window = (float*)calloc((size_t)fft_size, sizeof(float));
+    gen_hann(fft_size, s->window);
+    s->ifftOut = (float*)calloc((size_t)fft_size, sizeof(float));
+    s->in_real = (float*)calloc((size_t)fft_size, sizeof(float));
+    s->in_img = (float*)calloc((size_t)fft_size, sizeof(float));
+    s->out_real = (float*)calloc((size_t)fft_size, sizeof(float));
+    s->out_img = (float*)calloc((size_t)fft_size, sizeof(float));
+    return s;
+}
+void mxo_istft_destroy(void* h) {
+    istft_t* s = (istft_t*)h; if (!s) return;
+    free(s->pos); free(s->buffer); free(s->window); free(s->ifftOut); free(s->in_real); free(s->in_img);
+    free(s->out_real); free(s->out_img); free(s);
+}
+
+/* maxiIFFT::process (SPECTRUM), src/libs/maxiFFT.cpp:154-192 -> fft::inversePowerSpectrum :621-624
+ * = polToCart :590-603 (cosf/sinf) + calcIFFT :605-610 */
+int32_t mxo_istft_process(void* h, const float* mags, const float* phases, int32_t frames, float* out) {
+    istft_t* s = (istft_t*)h;
+    if (!s || !mags || !phases || !out || frames < 0) return -1;
+    for (int c = 0; c < s->C; ++c) {
+        float* buffer = s->buffer + (size_t)c * (size_t)s->n;
+        int pos = s->pos[c];
+        for (int f = 0; f < frames; ++f) {
+            const float* magnitude = mags + ((size_t)c * (size_t)frames + (size_t)f) * (size_t)s->bins;
+            const float* phase = phases + ((size_t)c * (size_t)frames + (size_t)f) * (size_t)s->bins;
+            for (int t = 0; t < s->hop; ++t) {
+                if (0 == pos) {
+                    for (int i = 0; i < s->n; i++) s->ifftOut[i] = 0;
+                    for (int i = 0; i < s->bins; i++) {
+                        s->in_real[i] = magnitude[i] * cosf(phase[i]);
+                        s->in_img[i] = magnitude[i] * sinf(phase[i]);
+                    }
+                    memset(s->in_real + s->bins, 0, sizeof(float) * (size_t)s->bins);
+                    memset(s->in_img + s->bins, 0, sizeof(float) * (size_t)s->bins);
+                    ref_FFT(s->n, 1, s->in_real, s->in_img, s->out_real, s->out_img);
+                    for (int i = 0; i < s->n; i++) s->ifftOut[i] += s->out_real[i] * s->window[i];
+                    memmove(buffer, buffer + s->hop, sizeof(float) * (size_t)(s->n - s->hop));
+                    memset(buffer + (s->n - s->hop), 0, sizeof(float) * (size_t)s->hop);
+                    for (int i = 0; i < s->n; i++) buffer[i] += s->ifftOut[i];
+                }
+                out[(size_t)c * (size_t)frames * (size_t)s->hop + (size_t)f * (size_t)s->hop + (size_t)t] = buffer[pos];
+                if (s->hop == ++pos) pos = 0;
+            }
+        }
+        s->pos[c] = pos;
+    }
+    return 0;
+}

@@ -1,0 +1,125 @@
+/*
+ * oracle_api.h -- TEST INFRASTRUCTURE ONLY (never linked into the product).
+ *
+ * One C interface, exported twice under the same symbol names:
+ *   oracle/_ref/libmaxiref.so   the UNMODIFIED reference classes, compiled from
+ *                               /root/reference/src by oracle/Makefile, driven
+ *                               by oracle/ref_shim.cpp ("kind: reference");
+ *   oracle/libmaxioracle.so     oracle/maxi_oracle.c, a plain-C restatement of
+ *                               the same algorithms ("kind: port"), pinned
+ *                               bit-for-bit against the first.
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+ * --impl reference legs may load either library.
+ *
+ * A "bank" is V independent voices, each one reference object per stage:
+ *     x = maxiOsc::<osc>(freq_v)                    src/maximilian.cpp:228-373
+ *     x = maxiEnv::adsr(x, trigger_v(t))            src/maximilian.cpp:1415-1466
+ *     x = maxiFilter::lores|hires / maxiSVF::play / maxiBiquad::play
+ *                                                   src/maximilian.cpp:455-484, src/maximilian.h:1305-1367
+ *     x = maxiDelayline::dl(x, size_v, feedback_v)  src/maximilian.cpp:420-429
+ *     out[t][v] = x ; mix[t][0..1] += maxiMix::stereo(x, pan_v)   src/maximilian.cpp:503-509
+ * called once per sample t, voices in ascending order inside each frame,
+ * exactly like a reference play() looping over an array of voices
+ * (cpp/commandline/maximilian_examples/15.polysynth/main.cpp:54-70).
+ */
+#ifndef MAXI_ORACLE_API_H
+#define MAXI_ORACLE_API_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* stage selectors (values shared with include/maxib200.h) */
+enum { MXO_OSC_SINEWAVE = 0, MXO_OSC_COSWAVE = 1, MXO_OSC_PHASOR = 2, MXO_OSC_SAW = 3,
+       MXO_OSC_SQUARE = 4, MXO_OSC_PULSE = 5, MXO_OSC_IMPULSE = 6, MXO_OSC_TRIANGLE = 7 };
+enum { MXO_FILT_NONE = 0, MXO_FILT_LORES = 1, MXO_FILT_HIRES = 2, MXO_FILT_SVF = 3, MXO_FILT_BIQUAD = 4 };
+enum { MXO_ENV_NONE = 0, MXO_ENV_ADSR = 1 };
+
+/* per-voice parameter / state arrays (double[V]) */
+enum {
+    MXO_P_FREQ = 0,       /* oscillator frequency, Hz */
+    MXO_P_PHASE = 1,      /* oscillator phase (maxiOsc::phaseReset); also a state */
+    MXO_P_DUTY = 2,       /* pulse duty */
+    MXO_P_CUTOFF = 3,     /* lores/hires cutoff1, SVF cutoff, biquad cutoff */
+    MXO_P_RESONANCE = 4,  /* lores/hires resonance, SVF resonance, biquad Q */
+    MXO_P_GAIN = 5,       /* biquad peakGain */
+    MXO_P_ENV_ATTACK = 6, /* maxiEnv::attack (raw coefficient) */
+    MXO_P_ENV_DECAY = 7,
+    MXO_P_ENV_SUSTAIN = 8,
+    MXO_P_ENV_RELEASE = 9,
+    MXO_P_ENV_HOLDTIME = 10, /* maxiEnv::holdtime, integral value */
+    MXO_P_DELAY_SIZE = 11,   /* dl() size argument, integral value */
+    MXO_P_DELAY_FEEDBACK = 12,
+    MXO_P_PAN = 13,          /* maxiMix::stereo x */
+    /* read-only state ids for mxo_bank_get */
+    MXO_S_FILT_0 = 32,    /* lores/hires x | svf v0z | biquad v[1] */
+    MXO_S_FILT_1 = 33,    /* lores/hires y | svf v1  | biquad v[2] */
+    MXO_S_FILT_2 = 34,    /* svf v2 */
+    MXO_S_ENV_AMPLITUDE = 35,
+    MXO_S_ENV_OUTPUT = 36,
+    MXO_S_ENV_HOLDCOUNT = 37,
+    MXO_S_ENV_FLAGS = 38, /* attack | decay<<1 | sustain<<2 | hold<<3 | release<<4 */
+    MXO_S_DELAY_PHASE = 39
+};
+
+typedef struct {
+    int32_t sample_rate;   /* maxiSettings::sampleRate */
+    int32_t osc_kind;
+    int32_t filt_kind;
+    int32_t biquad_type;   /* maxiBiquad::filterTypes, src/maximilian.h:1348-1357 */
+    int32_t env_kind;
+    int32_t delay_on;
+    int32_t delay_capacity; /* ring slots per voice for the port (reference: 705600 fixed) */
+    int32_t reserved;
+    double  svf_mix[4];    /* lpmix, bpmix, hpmix, notchmix of maxiSVF::play */
+} mxo_chain;
+
+void*   mxo_bank_create(const mxo_chain* chain, int32_t voices);
+void    mxo_bank_destroy(void* bank);
+int32_t mxo_bank_set(void* bank, int32_t id, const double* values);
+int32_t mxo_bank_get(void* bank, int32_t id, double* values);
+/* trigger_v(t) = 1 for trig_on[v] <= t < trig_off[v] (t = frame index inside this call), else 0;
+ * NULL pointers mean trigger 0 throughout. out: [nframes][V] or NULL; mix: [nframes][2] or NULL
+ * (mix is overwritten, not accumulated across calls). first/count restrict the call to a voice
+ * sub-range (used to thread the CPU baseline); pass 0, V for everything. */
+int32_t mxo_bank_process(void* bank, int32_t nframes, const int32_t* trig_on, const int32_t* trig_off,
+                         double* out, double* mix, int32_t first, int32_t count);
+/* copies ring slots [0, n) of voice v */
+int32_t mxo_bank_get_ring(void* bank, int32_t v, double* dst, int32_t n);
+
+/* parameter helpers = the reference setters */
+double  mxo_env_attack_coeff(double attackMS, int32_t sample_rate);   /* maxiEnv::setAttack   src/maximilian.cpp:1478-1480 */
+double  mxo_env_attack_ms_coeff(double attackMS, int32_t sample_rate);/* maxiEnv::setAttackMS src/maximilian.cpp:1484-1486 */
+double  mxo_env_decay_coeff(double ms, int32_t sample_rate);          /* setDecay / setRelease src/maximilian.cpp:1469-1476 */
+
+/* streaming STFT: C channels, each a maxiFFT::setup(fftSize, hopSize, fftSize), WITH_POLAR_CONVERSION.
+ * in: planar [C][n]. Frame f of channel c lands at index (c*max_frames + f)*bins in mags/phases/re/im
+ * (any of them may be NULL). Returns the number of frames fired per channel, or <0. */
+void*   mxo_stft_create(int32_t channels, int32_t fft_size, int32_t hop_size);
+void    mxo_stft_destroy(void* st);
+int32_t mxo_stft_process(void* st, const float* in, int32_t n, int32_t max_frames,
+                         float* mags, float* phases, float* re, float* im);
+int32_t mxo_stft_window(void* st, float* window);   /* fft_size floats */
+
+/* maxiMFCC::setup(numBins, numFilters, numCoeffs, minFreq, maxFreq) with maxiSettings::sampleRate = sample_rate.
+ * mags: [n][numBins] floats; coeffs: [n][numCoeffs]; melbands (optional): [n][numFilters] after the log stage. */
+void*   mxo_mfcc_create(int32_t num_bins, int32_t num_filters, int32_t num_coeffs,
+                        double min_freq, double max_freq, int32_t sample_rate);
+void    mxo_mfcc_destroy(void* m);
+int32_t mxo_mfcc_process(void* m, const float* mags, int32_t n, double* coeffs, double* melbands);
+
+/* maxiIFFT (SPECTRUM mode), C channels. mags/phases: frame f of channel c at (c*frames + f)*bins;
+ * out: planar [C][frames*hop]. */
+void*   mxo_istft_create(int32_t channels, int32_t fft_size, int32_t hop_size);
+void    mxo_istft_destroy(void* st);
+int32_t mxo_istft_process(void* st, const float* mags, const float* phases, int32_t frames, float* out);
+
+/* "reference" or "port" */
+const char* mxo_kind(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

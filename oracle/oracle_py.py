@@ -1,0 +1,270 @@
+"""ctypes loader for the two CPU oracles -- TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+legs may import this module (see oracle/oracle_api.h).  The product package
+maximilian_b200 never does.
+
+    load("port")       oracle/libmaxioracle.so   (oracle/maxi_oracle.c, plain-C restatement)
+    load("reference")  oracle/_ref/libmaxiref.so (the unmodified reference, compiled from
+                       /root/reference/src by oracle/Makefile; absent if never built)
+"""
+import ctypes as C
+import os
+import subprocess
+import threading
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+PATHS = {"port": os.path.join(HERE, "libmaxioracle.so"),
+         "reference": os.path.join(HERE, "_ref", "libmaxiref.so")}
+
+# stage selectors / ids: keep in sync with oracle_api.h
+OSC = dict(sinewave=0, coswave=1, phasor=2, saw=3, square=4, pulse=5, impulse=6, triangle=7)
+FILT = dict(none=0, lores=1, hires=2, svf=3, biquad=4)
+BIQUAD = dict(lowpass=0, highpass=1, bandpass=2, notch=3, peak=4, lowshelf=5, highshelf=6)
+P = dict(freq=0, phase=1, duty=2, cutoff=3, resonance=4, gain=5, env_attack=6, env_decay=7,
+         env_sustain=8, env_release=9, env_holdtime=10, delay_size=11, delay_feedback=12, pan=13,
+         filt0=32, filt1=33, filt2=34, env_amplitude=35, env_output=36, env_holdcount=37,
+         env_flags=38, delay_phase=39)
+
+
+class Chain(C.Structure):
+    _fields_ = [("sample_rate", C.c_int32), ("osc_kind", C.c_int32), ("filt_kind", C.c_int32),
+                ("biquad_type", C.c_int32), ("env_kind", C.c_int32), ("delay_on", C.c_int32),
+                ("delay_capacity", C.c_int32), ("reserved", C.c_int32), ("svf_mix", C.c_double * 4)]
+
+
+def build(kind="port"):
+    """Compile the oracle library with oracle/Makefile (building the checker is not using it)."""
+    target = "port" if kind == "port" else "ref"
+    subprocess.check_call(["make", "-s", "-C", HERE, target])
+
+
+_libs = {}
+
+
+def available(kind):
+    return os.path.exists(PATHS[kind])
+
+
+def load(kind="port"):
+    if kind in _libs:
+        return _libs[kind]
+    path = PATHS[kind]
+    if not os.path.exists(path):
+        build(kind)
+    lib = C.CDLL(path)
+    dp, ip, fp, vp = C.POINTER(C.c_double), C.POINTER(C.c_int32), C.POINTER(C.c_float), C.c_void_p
+    i32 = C.c_int32
+    sig = {
+        "mxo_kind": (C.c_char_p, []),
+        "mxo_bank_create": (vp, [C.POINTER(Chain), i32]),
+        "mxo_bank_destroy": (None, [vp]),
+        "mxo_bank_set": (i32, [vp, i32, dp]),
+        "mxo_bank_get": (i32, [vp, i32, dp]),
+        "mxo_bank_process": (i32, [vp, i32, ip, ip, dp, dp, i32, i32]),
+        "mxo_bank_get_ring": (i32, [vp, i32, dp, i32]),
+        "mxo_env_attack_coeff": (C.c_double, [C.c_double, i32]),
+        "mxo_env_attack_ms_coeff": (C.c_double, [C.c_double, i32]),
+        "mxo_env_decay_coeff": (C.c_double, [C.c_double, i32]),
+        "mxo_stft_create": (vp, [i32, i32, i32]),
+        "mxo_stft_destroy": (None, [vp]),
+        "mxo_stft_process": (i32, [vp, fp, i32, i32, fp, fp, fp, fp]),
+        "mxo_stft_window": (i32, [vp, fp]),
+        "mxo_mfcc_create": (vp, [i32, i32, i32, C.c_double, C.c_double, i32]),
+        "mxo_mfcc_destroy": (None, [vp]),
+        "mxo_mfcc_process": (i32, [vp, fp, i32, dp, dp]),
+        "mxo_istft_create": (vp, [i32, i32, i32]),
+        "mxo_istft_destroy": (None, [vp]),
+        "mxo_istft_process": (i32, [vp, fp, fp, i32, fp]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)
+        fn.restype, fn.argtypes = res, args
+    assert lib.mxo_kind().decode() == kind, (lib.mxo_kind(), kind)
+    _libs[kind] = lib
+    return lib
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double)) if a is not None else None
+
+
+def _fp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_float)) if a is not None else None
+
+
+def _ip(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int32)) if a is not None else None
+
+
+class Bank:
+    """V voices of  osc -> [adsr] -> [filter] -> [delay] -> out / stereo mix  on the CPU."""
+
+    def __init__(self, voices, osc="saw", filt="none", env=False, delay=False, sample_rate=48000,
+                 biquad_type="lowpass", svf_mix=(1.0, 0.0, 0.0, 0.0), delay_capacity=4096, kind="port"):
+        self.lib = load(kind)
+        self.V = int(voices)
+        ch = Chain(sample_rate, OSC[osc], FILT[filt], BIQUAD[biquad_type], 1 if env else 0,
+                   1 if delay else 0, delay_capacity, 0, (C.c_double * 4)(*svf_mix))
+        self.h = self.lib.mxo_bank_create(C.byref(ch), self.V)
+        if not self.h:
+            raise RuntimeError("mxo_bank_create failed")
+
+    def close(self):
+        if self.h:
+            self.lib.mxo_bank_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set(self, name, values):
+        a = np.ascontiguousarray(np.broadcast_to(np.asarray(values, dtype=np.float64), (self.V,)))
+        rc = self.lib.mxo_bank_set(self.h, P[name], _dp(a))
+        if rc:
+            raise RuntimeError(f"mxo_bank_set({name}) -> {rc}")
+
+    def get(self, name):
+        a = np.empty(self.V, dtype=np.float64)
+        rc = self.lib.mxo_bank_get(self.h, P[name], _dp(a))
+        if rc:
+            raise RuntimeError(f"mxo_bank_get({name}) -> {rc}")
+        return a
+
+    def ring(self, v, n):
+        a = np.empty(n, dtype=np.float64)
+        rc = self.lib.mxo_bank_get_ring(self.h, v, _dp(a), n)
+        if rc:
+            raise RuntimeError(f"mxo_bank_get_ring -> {rc}")
+        return a
+
+    def process(self, nframes, trig_on=None, trig_off=None, want_out=True, want_mix=False, threads=1):
+        """Returns (out[nframes][V] or None, mix[nframes][2] or None)."""
+        out = np.empty((nframes, self.V), dtype=np.float64) if want_out else None
+        ton = np.ascontiguousarray(trig_on, dtype=np.int32) if trig_on is not None else None
+        toff = np.ascontiguousarray(trig_off, dtype=np.int32) if trig_off is not None else None
+        threads = max(1, min(int(threads), self.V))
+        if threads == 1:
+            mix = np.empty((nframes, 2), dtype=np.float64) if want_mix else None
+            rc = self.lib.mxo_bank_process(self.h, nframes, _ip(ton), _ip(toff), _dp(out), _dp(mix), 0, self.V)
+            if rc:
+                raise RuntimeError(f"mxo_bank_process -> {rc}")
+            return out, mix
+        # voices statically partitioned over host threads (ctypes drops the GIL inside the call)
+        bounds = np.linspace(0, self.V, threads + 1).astype(int)
+        mixes = [np.empty((nframes, 2), dtype=np.float64) if want_mix else None for _ in range(threads)]
+        rcs = [0] * threads
+
+        def work(i):
+            rcs[i] = self.lib.mxo_bank_process(self.h, nframes, _ip(ton), _ip(toff), _dp(out), _dp(mixes[i]),
+                                               int(bounds[i]), int(bounds[i + 1] - bounds[i]))
+        ts = [threading.Thread(target=work, args=(i,)) for i in range(threads)]
+        [t.start() for t in ts]
+        [t.join() for t in ts]
+        if any(rcs):
+            raise RuntimeError(f"mxo_bank_process -> {rcs}")
+        mix = None
+        if want_mix:
+            mix = mixes[0].copy()
+            for m in mixes[1:]:
+                mix += m
+        return out, mix
+
+
+class Stft:
+    def __init__(self, channels, fft_size=1024, hop=512, kind="port"):
+        self.lib = load(kind)
+        self.C, self.n, self.hop, self.bins = channels, fft_size, hop, fft_size // 2
+        self.h = self.lib.mxo_stft_create(channels, fft_size, hop)
+        if not self.h:
+            raise RuntimeError("mxo_stft_create failed")
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.lib.mxo_stft_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def window(self):
+        w = np.empty(self.n, dtype=np.float32)
+        self.lib.mxo_stft_window(self.h, _fp(w))
+        return w
+
+    def process(self, x, want=("mags", "phases", "re", "im")):
+        """x: float32 [C][n] planar. Returns dict of float32 [C][frames][bins]."""
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        assert x.shape[0] == self.C
+        n = x.shape[1]
+        maxf = n // self.hop + 2
+        bufs = {k: (np.zeros((self.C, maxf, self.bins), dtype=np.float32) if k in want else None)
+                for k in ("mags", "phases", "re", "im")}
+        f = self.lib.mxo_stft_process(self.h, _fp(x), n, maxf, _fp(bufs["mags"]), _fp(bufs["phases"]),
+                                      _fp(bufs["re"]), _fp(bufs["im"]))
+        if f < 0:
+            raise RuntimeError(f"mxo_stft_process -> {f}")
+        return {k: np.ascontiguousarray(v[:, :f]) for k, v in bufs.items() if v is not None}
+
+
+class Mfcc:
+    def __init__(self, num_bins=512, num_filters=42, num_coeffs=40, min_freq=20.0, max_freq=20000.0,
+                 sample_rate=48000, kind="port"):
+        self.lib = load(kind)
+        self.bins, self.filters, self.coeffs = num_bins, num_filters, num_coeffs
+        self.h = self.lib.mxo_mfcc_create(num_bins, num_filters, num_coeffs, min_freq, max_freq, sample_rate)
+        if not self.h:
+            raise RuntimeError("mxo_mfcc_create failed")
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.lib.mxo_mfcc_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def process(self, mags):
+        """mags float32 [..., bins] -> (coeffs [..., numCoeffs], melbands [..., numFilters])."""
+        m = np.ascontiguousarray(mags, dtype=np.float32)
+        lead = m.shape[:-1]
+        n = int(np.prod(lead)) if lead else 1
+        co = np.empty((n, self.coeffs), dtype=np.float64)
+        mb = np.empty((n, self.filters), dtype=np.float64)
+        rc = self.lib.mxo_mfcc_process(self.h, _fp(m), n, _dp(co), _dp(mb))
+        if rc:
+            raise RuntimeError(f"mxo_mfcc_process -> {rc}")
+        return co.reshape(lead + (self.coeffs,)), mb.reshape(lead + (self.filters,))
+
+
+class Istft:
+    def __init__(self, channels, fft_size=1024, hop=512, kind="port"):
+        self.lib = load(kind)
+        self.C, self.n, self.hop, self.bins = channels, fft_size, hop, fft_size // 2
+        self.h = self.lib.mxo_istft_create(channels, fft_size, hop)
+        if not self.h:
+            raise RuntimeError("mxo_istft_create failed")
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.lib.mxo_istft_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def process(self, mags, phases):
+        """mags/phases float32 [C][frames][bins] -> float32 [C][frames*hop]."""
+        m = np.ascontiguousarray(mags, dtype=np.float32)
+        p = np.ascontiguousarray(phases, dtype=np.float32)
+        frames = m.shape[1]
+        out = np.empty((self.C, frames * self.hop), dtype=np.float32)
+        rc = self.lib.mxo_istft_process(self.h, _fp(m), _fp(p), frames, _fp(out))
+        if rc:
+            raise RuntimeError(f"mxo_istft_process -> {rc}")
+        return out

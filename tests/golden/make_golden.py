@@ -1,0 +1,111 @@
+"""Generates tests/golden/*.npz from the UNMODIFIED reference (oracle/_ref/libmaxiref.so, compiled
+from /root/reference by oracle/Makefile with -O2 -ffp-contract=off). Run in the build container:
+
+    python tests/golden/make_golden.py
+
+The reference's own tests hold no numeric expectations, so these vectors --
+outputs of the reference itself on seeded inputs -- are the pin. Inputs are stored beside the
+outputs so the fixtures are self-contained on the GPU box, where /root/reference does not exist.
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+from maximilian_b200 import workloads as W      # noqa: E402
+from oracle import oracle_py as O               # noqa: E402
+
+KIND = "reference"
+
+CHAINS = [  # (name, osc, filt, env, delay, kwargs)
+    ("sinewave_lores", "sinewave", "lores", False, False, {}),
+    ("saw_hires", "saw", "hires", False, False, {}),
+    ("saw_svf_lp", "saw", "svf", False, False, {}),
+    ("phasor_svf_mix", "phasor", "svf", False, False, {"svf_mix": (0.3, 0.2, 0.4, 0.1)}),
+    ("saw_biquad_lp", "saw", "biquad", False, False, {}),
+    ("triangle_biquad_peak", "triangle", "biquad", False, False, {"biquad_type": "peak"}),
+    ("pulse_none", "pulse", "none", False, False, {}),
+    ("square_none", "square", "none", False, False, {}),
+    ("impulse_none", "impulse", "none", False, False, {}),
+    ("coswave_none", "coswave", "none", False, False, {}),
+    ("saw_env_delay", "saw", "none", True, True, {"delay_capacity": 96}),
+    ("saw_env_lores_delay", "saw", "lores", True, True, {"delay_capacity": 96}),
+]
+
+
+configure = W.configure_bank
+
+
+def chains():
+    V, B, NB = 8, 96, 3
+    out = {"V": V, "B": B, "NB": NB}
+    for name, osc, filt, env, delay, kw in CHAINS:
+        p = W.voice_params(V, seed=1234, delay_size=kw.get("delay_capacity", 96), ragged_delay=True)
+        if name == "triangle_biquad_peak":
+            p["gain"] = np.linspace(-9.0, 9.0, V)
+        b = O.Bank(V, osc=osc, filt=filt, env=env, delay=delay, kind=KIND, **kw)
+        configure(b, filt, p, env, delay)
+        outs, mixes = [], []
+        for blk in range(NB):
+            on, off = W.gate(V, B, 4 * blk if blk < 2 else 1)     # two gated blocks, then a silent one
+            o, m = b.process(B, on, off, want_mix=True)
+            outs.append(o); mixes.append(m)
+        out[name + "/out"] = np.stack(outs)
+        out[name + "/mix"] = np.stack(mixes)
+        out[name + "/phase"] = b.get("phase")
+        if delay:
+            out[name + "/delay_phase"] = b.get("delay_phase").astype(np.int32)
+            out[name + "/ring"] = np.stack([b.ring(v, kw["delay_capacity"]) for v in range(V)])
+        if env:
+            out[name + "/env_flags"] = b.get("env_flags").astype(np.int32)
+            out[name + "/env_amplitude"] = b.get("env_amplitude")
+    np.savez_compressed(os.path.join(HERE, "chains.npz"), **out)
+
+
+def seeds():
+    """The SURVEY.md section 8(c) seed values, regenerated (sr 48000)."""
+    out = {}
+    b = O.Bank(1, osc="sinewave", filt="lores", kind=KIND); b.set("freq", 440); b.set("cutoff", 1000); b.set("resonance", 2.0)
+    out["sine440_lores_1000_2"] = b.process(8)[0].ravel()
+    b = O.Bank(1, osc="saw", filt="svf", kind=KIND); b.set("freq", 110); b.set("cutoff", 1000); b.set("resonance", 2.0)
+    out["saw110_svf_1000_2"] = b.process(8)[0].ravel()
+    b = O.Bank(1, osc="square", delay=True, kind=KIND); b.set("freq", 0); b.set("phase", 0.75)
+    b.set("delay_size", 4); b.set("delay_feedback", 0.5)
+    out["dl_1_4_05"] = b.process(10)[0].ravel()
+    lib = O.load(KIND)
+    a, d = lib.mxo_env_attack_coeff(1, 48000), lib.mxo_env_decay_coeff(2, 48000)
+    b = O.Bank(1, osc="square", env=True, kind=KIND); b.set("freq", 0); b.set("phase", 0.75)
+    b.set("env_attack", a); b.set("env_decay", d); b.set("env_sustain", .5); b.set("env_release", d); b.set("env_holdtime", 1)
+    out["adsr_1_2_05_2"] = b.process(14, [0], [6])[0].ravel()
+    out["adsr_coeffs"] = np.array([a, d])
+    np.savez_compressed(os.path.join(HERE, "seeds.npz"), **out)
+
+
+def spectral():
+    C, n, hop = 2, 1024, 512
+    x = W.channel_streams(C, 5 * hop, seed=4242)
+    st = O.Stft(C, n, hop, kind=KIND)
+    r = st.process(x)
+    mf = O.Mfcc(512, 42, 40, 20.0, 20000.0, 48000, kind=KIND)
+    co, mb = mf.process(r["mags"])
+    mf13 = O.Mfcc(512, 42, 13, 20.0, 20000.0, 44100, kind=KIND)
+    co13, _ = mf13.process(r["mags"])
+    y = O.Istft(C, n, hop, kind=KIND).process(r["mags"], r["phases"])
+    # hop 256 variant, short
+    x2 = W.channel_streams(1, 1024 + 3 * 256, seed=99)
+    r2 = O.Stft(1, 1024, 256, kind=KIND).process(x2)
+    np.savez_compressed(os.path.join(HERE, "spectral.npz"), x=x, window=st.window(), re=r["re"], im=r["im"],
+                        mags=r["mags"], phases=r["phases"], mfcc40=co, melbands=mb, mfcc13_44k=co13, istft=y,
+                        x_hop256=x2, mags_hop256=r2["mags"], re_hop256=r2["re"], im_hop256=r2["im"])
+
+
+if __name__ == "__main__":
+    O.build("reference")
+    chains(); seeds(); spectral()
+    for f in sorted(os.listdir(HERE)):
+        if f.endswith(".npz"):
+            print(f, os.path.getsize(os.path.join(HERE, f)), "bytes")

@@ -1,0 +1,216 @@
+"""Pins the plain-C oracle (oracle/maxi_oracle.c) BIT-FOR-BIT against the unmodified reference
+compiled from /root/reference (oracle/_ref/libmaxiref.so, built by oracle/Makefile).
+
+CPU only. Skipped when the compiled reference is neither present nor buildable (GPU box).
+Tolerance: none. fp64 and fp32 values are compared with ==, integer state exactly.
+"""
+import itertools
+
+import numpy as np
+import pytest
+
+from maximilian_b200 import workloads as W
+
+OSCS = ["sinewave", "coswave", "phasor", "saw", "square", "pulse", "impulse", "triangle"]
+FILTS = ["none", "lores", "hires", "svf", "biquad"]
+
+
+_configure = W.configure_bank
+
+
+def _pair(port, reference, V, **kw):
+    return port.Bank(V, kind="port", **kw), reference.Bank(V, kind="reference", **kw)
+
+
+def _same(a, b):
+    return np.array_equal(a, b, equal_nan=True)
+
+
+@pytest.mark.parametrize("osc,filt", list(itertools.product(OSCS, FILTS)))
+def test_osc_filter_chains_bit_exact(port, reference, osc, filt):
+    V, B = 37, 257
+    p = W.voice_params(V, seed=11)
+    a, b = _pair(port, reference, V, osc=osc, filt=filt)
+    _configure(a, filt, p, False, False); _configure(b, filt, p, False, False)
+    for _ in range(3):                        # state carried over consecutive blocks
+        oa, ma = a.process(B, want_mix=True)
+        ob, mb = b.process(B, want_mix=True)
+        assert _same(oa, ob)
+        assert _same(ma, mb)
+    for s in ("phase", "filt0", "filt1", "filt2"):
+        assert _same(a.get(s), b.get(s)), s
+
+
+@pytest.mark.parametrize("btype", ["lowpass", "highpass", "bandpass", "notch", "peak", "lowshelf", "highshelf"])
+@pytest.mark.parametrize("gain_sign", [1.0, -1.0])
+def test_biquad_types_bit_exact(port, reference, btype, gain_sign):
+    V, B = 16, 300
+    p = W.voice_params(V, seed=5)
+    p["gain"] = gain_sign * (0.5 + 11.5 * np.random.default_rng(3).random(V))
+    a, b = _pair(port, reference, V, osc="saw", filt="biquad", biquad_type=btype)
+    _configure(a, "biquad", p, False, False); _configure(b, "biquad", p, False, False)
+    oa, _ = a.process(B); ob, _ = b.process(B)
+    assert _same(oa, ob)
+
+
+@pytest.mark.parametrize("mix", [(1, 0, 0, 0), (0, 1, 0, 0), (0, 0, 1, 0), (0, 0, 0, 1), (0.3, 0.2, 0.4, 0.1)])
+def test_svf_mixes_bit_exact(port, reference, mix):
+    V, B = 16, 300
+    p = W.voice_params(V, seed=6)
+    p["res_svf"][0] = 0.0                     # res == 0 -> damping 0 branch (src/maximilian.h:1327)
+    a, b = _pair(port, reference, V, osc="saw", filt="svf", svf_mix=tuple(float(m) for m in mix))
+    _configure(a, "svf", p, False, False); _configure(b, "svf", p, False, False)
+    oa, _ = a.process(B); ob, _ = b.process(B)
+    assert _same(oa, ob)
+
+
+def test_lores_clamps_bit_exact(port, reference):
+    # cutoff < 10 -> 10, cutoff > sr -> sr (NaN: z == 1 gives 0/0), resonance < 1 -> 1  
+    V, B = 6, 64
+    p = W.voice_params(V, seed=2)
+    p["cutoff"] = np.array([1.0, 9.999, 10.0, 47999.0, 48000.0, 96000.0])
+    p["q_lores"] = np.array([0.0, 0.5, 1.0, 1.5, 2.0, 3.0])
+    for filt in ("lores", "hires"):
+        a, b = _pair(port, reference, V, osc="saw", filt=filt)
+        _configure(a, filt, p, False, False); _configure(b, filt, p, False, False)
+        oa, _ = a.process(B); ob, _ = b.process(B)
+        assert _same(oa, ob)
+        assert np.isnan(oa[-1, 4]) and np.isnan(oa[-1, 5])
+
+
+def test_sample_rates(port, reference):
+    for sr in (44100, 48000, 96000):
+        V, B = 8, 200
+        p = W.voice_params(V, seed=sr)
+        a, b = _pair(port, reference, V, osc="sinewave", filt="svf", sample_rate=sr)
+        _configure(a, "svf", p, False, False); _configure(b, "svf", p, False, False)
+        oa, _ = a.process(B); ob, _ = b.process(B)
+        assert _same(oa, ob)
+
+
+@pytest.mark.parametrize("filt", ["none", "lores"])
+def test_env_state_machine_bit_exact(port, reference, filt):
+    V, B = 64, 512
+    p = W.voice_params(V, seed=9)
+    p["env_holdtime"] = np.array([1, 1, 0, 5, 100, 1000, 1, 3] * (V // 8), dtype=np.float64)
+    a, b = _pair(port, reference, V, osc="saw", filt=filt, env=True)
+    _configure(a, filt, p, True, False); _configure(b, filt, p, True, False)
+    for blk in range(8):
+        on, off = W.gate(V, B, blk)
+        if blk == 5:                          # retrigger while still releasing, gate across the whole block
+            on[:] = 0; off[:] = B
+        oa, _ = a.process(B, on, off); ob, _ = b.process(B, on, off)
+        assert _same(oa, ob), blk
+        for s in ("env_amplitude", "env_output", "env_holdcount", "env_flags"):
+            assert _same(a.get(s), b.get(s)), (blk, s)
+
+
+def test_env_setters(port, reference):
+    la, lb = port.load("port"), reference.load("reference")
+    for ms in (0.5, 1.0, 2.0, 17.3, 500.0):
+        for sr in (44100, 48000):
+            assert la.mxo_env_attack_coeff(ms, sr) == lb.mxo_env_attack_coeff(ms, sr)
+            assert la.mxo_env_attack_ms_coeff(ms, sr) == lb.mxo_env_attack_ms_coeff(ms, sr)
+            assert la.mxo_env_decay_coeff(ms, sr) == lb.mxo_env_decay_coeff(ms, sr)
+    p = W.voice_params(8, seed=1)
+    att, dec, rel = W.env_coeffs(p)           # math.pow == libm pow
+    for i in range(8):
+        assert att[i] == lb.mxo_env_attack_coeff(p["attack_ms"][i], 48000)
+        assert dec[i] == lb.mxo_env_decay_coeff(p["decay_ms"][i], 48000)
+        assert rel[i] == lb.mxo_env_decay_coeff(p["release_ms"][i], 48000)
+
+
+def test_delayline_indices_and_ring_bit_exact(port, reference):
+    # small V: every reference maxiDelayline is a 5.6 MB object (src/maximilian.h:273)
+    V, B, cap = 12, 700, 512
+    p = W.voice_params(V, seed=4, delay_size=cap, ragged_delay=True)
+    p["delay_size"][:4] = [1, 2, 3, cap]
+    a, b = _pair(port, reference, V, osc="saw", env=True, delay=True, delay_capacity=cap)
+    _configure(a, "none", p, True, True); _configure(b, "none", p, True, True)
+    for blk in range(4):
+        on, off = W.gate(V, B, blk)
+        if blk == 2:                          # size shrinks mid-stream: phase >= size -> 0 on the next call (A6)
+            p["delay_size"] = np.maximum(1, p["delay_size"] // 2)
+            a.set("delay_size", p["delay_size"]); b.set("delay_size", p["delay_size"])
+        oa, _ = a.process(B, on, off); ob, _ = b.process(B, on, off)
+        assert _same(oa, ob), blk
+        assert np.array_equal(a.get("delay_phase"), b.get("delay_phase"))     # integer index: exact
+    for v in range(V):
+        assert _same(a.ring(v, cap), b.ring(v, cap)), v
+
+
+def test_delay_size_nonpositive(port, reference):
+    V, B = 3, 20
+    a, b = _pair(port, reference, V, osc="saw", delay=True, delay_capacity=16)
+    for k in (a, b):
+        k.set("freq", [100.0, 200.0, 300.0]); k.set("delay_size", [0.0, -3.0, 1.0]); k.set("delay_feedback", 0.7)
+    oa, _ = a.process(B); ob, _ = b.process(B)
+    assert _same(oa, ob)
+    assert np.array_equal(a.get("delay_phase"), b.get("delay_phase"))
+
+
+def test_threaded_partition_matches_serial(port):
+    V, B = 64, 128
+    p = W.voice_params(V, seed=3)
+    a = port.Bank(V, osc="saw", filt="biquad"); b = port.Bank(V, osc="saw", filt="biquad")
+    _configure(a, "biquad", p, False, False); _configure(b, "biquad", p, False, False)
+    oa, ma = a.process(B, want_mix=True, threads=1)
+    ob, mb = b.process(B, want_mix=True, threads=4)
+    assert _same(oa, ob)
+    np.testing.assert_allclose(ma, mb, rtol=1e-12, atol=1e-12)
+
+
+# ------------------------------------------------------------------ spectral
+
+@pytest.mark.parametrize("n,hop", [(1024, 512), (1024, 256), (512, 128), (256, 256), (64, 16)])
+def test_stft_bit_exact(port, reference, n, hop):
+    C = 5
+    x = W.channel_streams(C, 6 * n + 37, seed=n + hop)
+    x[1] *= 1000.0
+    x[2] = 0.0
+    a = port.Stft(C, n, hop, kind="port"); b = reference.Stft(C, n, hop, kind="reference")
+    assert _same(a.window(), b.window())
+    # feed in uneven chunks: the frame schedule (integer pos) must agree exactly
+    cuts = [0, 3, hop - 1, hop, 2 * n + 5, x.shape[1]]
+    for lo, hi in zip(cuts[:-1], cuts[1:]):
+        ra = a.process(x[:, lo:hi]); rb = b.process(x[:, lo:hi])
+        assert ra["mags"].shape == rb["mags"].shape
+        for k in ("re", "im", "mags", "phases"):
+            assert _same(ra[k], rb[k]), (k, lo, hi)
+
+
+def test_stft_frame_schedule(port):
+    # first frame after hop samples; 93 frames in 48000 samples at hop 512
+    s = port.Stft(1, 1024, 512)
+    r = s.process(np.zeros((1, 48000), dtype=np.float32))
+    assert r["mags"].shape[1] == 93
+    s = port.Stft(1, 1024, 512)
+    assert s.process(np.zeros((1, 511), dtype=np.float32))["mags"].shape[1] == 0
+    assert s.process(np.zeros((1, 1), dtype=np.float32))["mags"].shape[1] == 1
+
+
+@pytest.mark.parametrize("cfg", [(512, 42, 40, 20.0, 20000.0, 48000), (512, 42, 13, 20.0, 20000.0, 44100),
+                                 (512, 256, 13, 20.0, 20000.0, 48000), (256, 20, 12, 100.0, 8000.0, 48000)])
+def test_mfcc_bit_exact(port, reference, cfg):
+    bins = cfg[0]
+    st = port.Stft(3, 2 * bins, bins)
+    mags = st.process(W.channel_streams(3, 2 * bins * 8, seed=bins))["mags"]
+    mags[0, 0] = 0.0                                   # silent frame: log gate (> 1e-6) takes the 0 branch
+    a = port.Mfcc(*cfg, kind="port"); b = reference.Mfcc(*cfg, kind="reference")
+    ca, ma = a.process(mags); cb, mb = b.process(mags)
+    assert _same(ma, mb)
+    assert _same(ca, cb)
+    assert np.all(ma[..., 0] == 0.0)                   # filter 0 is never initialised by the reference (A13)
+
+
+@pytest.mark.parametrize("n,hop", [(1024, 512), (1024, 256), (256, 64)])
+def test_istft_bit_exact(port, reference, n, hop):
+    C = 3
+    x = W.channel_streams(C, 10 * n, seed=77)
+    r = port.Stft(C, n, hop).process(x)
+    a = port.Istft(C, n, hop, kind="port"); b = reference.Istft(C, n, hop, kind="reference")
+    F = r["mags"].shape[1]
+    for lo, hi in ((0, 3), (3, F)):
+        ya = a.process(r["mags"][:, lo:hi], r["phases"][:, lo:hi])
+        yb = b.process(r["mags"][:, lo:hi], r["phases"][:, lo:hi])
+        assert _same(ya, yb)
