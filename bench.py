@@ -1,0 +1,333 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the batched voice path on B200, one JSON line on stdout.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload svf|biquad|delay|mfcc] [--impl reference]
+
+A "step" is one block (1024 frames) of one bank: BASELINE.json configs[1] by default -- 1 Mi voices of
+maxiOsc::saw -> maxiSVF (low-pass mix), per-voice fp64 output materialised time-major in HBM. With N > 1
+(launched by torch.distributed.run, one rank per GPU) every rank owns its own 1 Mi voices (weak scaling)
+and the per-block stereo mix bus [1024][2] is sum-all-reduced over NCCL -- the path's only exchange step.
+
+  value      voice-samples/s of the whole job, inputs and state resident in HBM, CUDA-event timed, max over ranks
+  e2e        the same block through the C ABI with HOST control data: per step one fp64 frequency array
+             (8 MiB) is uploaded with mxb_bank_set_param from pinned memory and the stereo mix (16 KiB) is
+             read back by mxb_bank_process(MXB_MEM_SPLIT); the voice signals stay on the device
+  roofline   algorithmic bytes per launch / CUDA-event launch time against MEASURED_PEAKS.json
+  cpu_baseline  the reference's own scalar code (oracle/_ref, or the C port) on all host cores, bounded sample
+
+`--impl reference` times only that CPU leg with the same metric/config (rank 0; other ranks exit 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BLOCK = 1024
+SR = 48000
+
+WORKLOADS = {
+    # name: (voices/GPU, osc, filt, env, delay_taps, algorithmic bytes per voice-sample, description)
+    "svf": dict(voices=1 << 20, osc="saw", filt="svf", env=False, delay=0, bytes_per=8.0 + (88 + 32) / BLOCK,
+                desc="configs[1]: 1Mi voices maxiOsc::saw -> maxiSVF lp, 1024-frame block, fp64 out[1024][V] materialised"),
+    "biquad": dict(voices=1 << 20, osc="saw", filt="biquad", env=False, delay=0, bytes_per=8.0 + (80 + 24) / BLOCK,
+                   desc="configs[4] shard: 1Mi voices/GPU maxiOsc::saw -> maxiBiquad lowpass, fp64 out materialised + stereo mix"),
+    "delay": dict(voices=1 << 18, osc="saw", filt="none", env=True, delay=4096, bytes_per=24.0 + (108 + 60) / BLOCK,
+                  desc="configs[2]: 256Ki voices saw -> maxiEnv::adsr -> maxiDelayline::dl(4096), fp64 out materialised"),
+}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.rows, self.proc, self.device = [], None, device
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "50", "-i", str(self.device)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self, t0, t1):
+        rows = [r for (t, r) in self.rows if t0 <= t <= t1] or [r for (_, r) in self.rows]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"], "samples": 0}
+        sm = sorted(float(r[1]) for r in rows if r[1].replace(".", "").isdigit())
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            for i, n in enumerate(names):
+                if len(r) > 5 + i and r[5 + i].lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(rows[0][2]) if rows[0][2].replace(".", "").isdigit() else None,
+                "reasons": sorted(reasons), "samples": len(rows)}
+
+
+# ------------------------------------------------------------------------------------------- CPU reference leg
+
+def cpu_bank(wl, voices, kind):
+    from maximilian_b200 import workloads as W
+    from oracle import oracle_py as O
+    p = W.voice_params(voices, seed=W.SEED, delay_size=wl["delay"] or 4096)
+    b = O.Bank(voices, osc=wl["osc"], filt=wl["filt"], env=wl["env"], delay=wl["delay"] > 0, sample_rate=SR,
+               delay_capacity=max(wl["delay"], 1), kind=kind)
+    W.configure_bank(b, wl["filt"], p, wl["env"], wl["delay"] > 0)
+    return b
+
+
+def cpu_kind():
+    from oracle import oracle_py as O
+    if O.available("reference"):
+        return "reference"
+    O.build("port")
+    return "port"
+
+
+def cpu_sample_voices(wl):
+    # each reference maxiDelayline is a 5.6 MB object (src/maximilian.h:273): keep the sample in RAM
+    return 512 if wl["delay"] else 65536
+
+
+def run_cpu_blocks(bank, wl, voices, threads, nblocks, block_index0=0):
+    from maximilian_b200 import workloads as W
+    t0 = time.perf_counter()
+    for k in range(nblocks):
+        on = off = None
+        if wl["env"]:
+            on, off = W.gate(voices, BLOCK, block_index0 + k)
+        bank.process(BLOCK, on, off, want_out=True, want_mix=False, threads=threads)
+    return time.perf_counter() - t0
+
+
+def cpu_baseline(wl, budget_s=4.0):
+    kind = cpu_kind()
+    cores = os.cpu_count() or 1
+    voices = cpu_sample_voices(wl)
+    bank = cpu_bank(wl, voices, kind)
+    run_cpu_blocks(bank, wl, voices, cores, 1)                      # warm-up block
+    n, total = 0, 0.0
+    while total < budget_s and n < 64:
+        total += run_cpu_blocks(bank, wl, voices, cores, 1, 1 + n)
+        n += 1
+    v = voices * BLOCK * n / total
+    return {"value": v, "unit": "samples/s", "cores": cores, "kind": kind,
+            "sample": f"{voices} voices x {BLOCK} frames x {n} blocks of the same chain, voices partitioned over {cores} host threads"}
+
+
+def reference_arm(args, wl_name, wl):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    kind = cpu_kind()
+    cores = os.cpu_count() or 1
+    voices = cpu_sample_voices(wl)
+    bank = cpu_bank(wl, voices, kind)
+    run_cpu_blocks(bank, wl, voices, cores, args.warmup)
+    dt = run_cpu_blocks(bank, wl, voices, cores, args.steps, args.warmup)
+    v = voices * BLOCK * args.steps / dt
+    line = {"impl": "reference", "metric": "voice_samples_per_sec", "value": v, "unit": "samples/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": wl["desc"], "cpu_sample_voices": voices, "block": BLOCK, "sample_rate": SR},
+            "cpu_baseline": {"value": v, "unit": "samples/s", "cores": cores, "kind": kind,
+                             "sample": f"each step = {voices} voices x {BLOCK} frames of the same chain on {cores} host threads"},
+            "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ GPU leg
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--workload", default="svf", choices=sorted(WORKLOADS))
+    ap.add_argument("--mix", type=int, default=-1, help="1: also produce the stereo mix bus each block (default: only when gpus > 1)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--f32-out", action="store_true", help="store the materialised output as fp32 (declared in the JSON)")
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        reference_arm(args, args.workload, wl)
+        return
+    assert args.warmup >= 3, "timing rules: at least 3 warm-up steps"
+
+    import torch
+    import torch.distributed as dist
+    from maximilian_b200 import capi
+    from maximilian_b200 import workloads as W
+
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE {world}"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    want_mix = (args.mix == 1) or (args.mix < 0 and world > 1)
+
+    V = wl["voices"]
+    p = W.voice_params(V, seed=W.SEED + rank, delay_size=wl["delay"] or 4096)
+    ctx = capi.Context(local, SR)
+    bank = capi.Bank(V, osc=wl["osc"], filt=wl["filt"], env=wl["env"], delay=wl["delay"] > 0,
+                     delay_capacity=max(wl["delay"], 1), max_frames=BLOCK, ctx=ctx, sample_rate=SR)
+    W.configure_bank(bank, wl["filt"], p, wl["env"], wl["delay"] > 0)
+
+    out_dtype = torch.float32 if args.f32_out else torch.float64
+    out = torch.empty((BLOCK, V), dtype=out_dtype, device=dev)             # 8 GiB (fp64, 1 Mi voices) >> 126 MB L2
+    mix = torch.zeros((BLOCK, 2), dtype=torch.float64, device=dev)
+    gates = []
+    if wl["env"]:   # gate arrays for 4 consecutive blocks, resident on the device (control data of the resident leg)
+        for k in range(4):
+            on, off = W.gate(V, BLOCK, k, seed=W.SEED + rank)
+            gates.append((torch.from_numpy(on).to(dev), torch.from_numpy(off).to(dev)))
+    stream = torch.cuda.current_stream()
+
+    def step(k):
+        on_p = off_p = None
+        if gates:
+            on_p, off_p = gates[k % 4][0].data_ptr(), gates[k % 4][1].data_ptr()
+        bank.process_device(BLOCK, out_ptr=out.data_ptr(), mix_ptr=mix.data_ptr() if want_mix else None,
+                            trig_on_ptr=on_p, trig_off_ptr=off_p, f32=args.f32_out, stream=stream.cuda_stream)
+        if world > 1 and want_mix:
+            dist.all_reduce(mix)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for k in range(args.warmup):
+        step(k)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.12)
+    barrier()
+    launches0 = bank.launches
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    t_wall0 = time.perf_counter()
+    evs[0].record(stream)
+    for k in range(args.steps):
+        step(args.warmup + k)
+        evs[k + 1].record(stream)
+    torch.cuda.synchronize()
+    t_wall1 = time.perf_counter()
+    barrier()
+    launches = bank.launches - launches0
+    ms_total = evs[0].elapsed_time(evs[-1])
+    per_launch_ms = sorted(evs[i].elapsed_time(evs[i + 1]) for i in range(args.steps))
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    samples_per_step = V * BLOCK
+    value = world * samples_per_step * args.steps / (ms_max * 1e-3)
+    clocks = None
+    if rank == 0:
+        time.sleep(0.06)
+        sampler.stop()
+        clocks = sampler.summary(t_wall0, t_wall1)
+
+    # ---- end to end through the C ABI with host control data ------------------------------------------------
+    freq_host = torch.from_numpy(p["freq"].copy()).pin_memory()
+    mix_host = torch.zeros((BLOCK, 2), dtype=torch.float64).pin_memory()
+    fh, mh = freq_host.numpy(), mix_host.numpy()
+    on_h = off_h = None
+    if wl["env"]:
+        on, off = W.gate(V, BLOCK, 0, seed=W.SEED + rank)
+        on_t, off_t = torch.from_numpy(on).pin_memory(), torch.from_numpy(off).pin_memory()
+        on_h, off_h = on_t.numpy(), off_t.numpy()
+    e2e_steps = max(3, min(args.steps, 50))
+
+    def e2e_step():
+        bank.set_host_array("freq", fh)                                   # H2D: this block's control data
+        bank.process_split(BLOCK, out.data_ptr(), mh, on_h, off_h, f32=args.f32_out, stream=stream.cuda_stream)   # D2H: mix bus
+        if world > 1:
+            m = mix_host.to(dev, non_blocking=True)
+            dist.all_reduce(m)
+
+    for _ in range(3):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    t = torch.tensor([dt], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * samples_per_step * e2e_steps / float(t.item())
+    h2d = fh.nbytes + (on_h.nbytes + off_h.nbytes if on_h is not None else 0)
+    d2h = mh.nbytes
+
+    if rank == 0:
+        peak, peak_src = load_peaks()
+        med_ms = per_launch_ms[len(per_launch_ms) // 2]
+        avg_ms = ms_total / args.steps
+        bytes_per = (4.0 if args.f32_out else 8.0) + (wl["bytes_per"] - 8.0)
+        achieved = bytes_per * samples_per_step / (avg_ms * 1e-3) / 1e9
+        line = {
+            "metric": "voice_samples_per_sec", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": wl["desc"] + (" + stereo mix bus" if want_mix else ""), "voices_per_gpu": V, "block": BLOCK,
+                       "sample_rate": SR, "out_storage": "f32" if args.f32_out else "f64", "parallelism": f"voices sharded x{world}",
+                       "collective": "NCCL sum all-reduce of mix[1024][2] fp64 per block" if world > 1 and want_mix else "none",
+                       "l2": "no flush needed: each step writes %.1f GB, inputs+outputs >> 126 MB L2" % (samples_per_step * (4 if args.f32_out else 8) / 1e9)},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src, "kernel": "bank_kernel" if not wl["delay"] else "delay_bank_kernel",
+                         "algorithmic_bytes_per_voice_sample": bytes_per, "launch_ms_avg": avg_ms, "launch_ms_median": med_ms},
+            "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "steps": e2e_steps, "what": "mxb_bank_set_param(freq, pinned host) + mxb_bank_process(MXB_MEM_SPLIT): "
+                                                 "host gates in, host mix out, voice signals materialised on the device"},
+            "gpu_launches": launches, "clocks": clocks,
+        }
+        if not args.no_cpu and world == 1:
+            line["cpu_baseline"] = cpu_baseline(wl)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

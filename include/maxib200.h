@@ -1,0 +1,206 @@
+/*
+ * maxib200.h -- C ABI of libmaxib200.so: Maximilian's per-sample DSP hot path as batched
+ * many-voice block kernels for NVIDIA B200 (sm_100a).
+ *
+ * The reference has no plugin/FFI boundary: its interface is the C++ class surface
+ *   maxiOsc / maxiFilter / maxiSVF / maxiBiquad / maxiEnv / maxiDelayline / maxiMix
+ *   (src/maximilian.h:169-419, 888-932, 1281-1486) and maxiFFT / maxiIFFT / maxiMFCC
+ *   (src/libs/maxiFFT.h:46-156, src/libs/maxiMFCC.h:40-211),
+ * called once per sample from the audio callback routing() (cpp/commandline/player.cpp:25-44).
+ * This header is that surface restated for V voices x n frames per call: plain pointers and
+ * sizes, opaque handles, an int32 status on every entry point, no exceptions, no exit().
+ * include/maximilian_b200.hpp wraps it in C++ classes with the reference's names.
+ *
+ * Conventions
+ *   - every function returns MXB_OK (0) or a negative MXB_ERR_*; mxb_last_error() gives the text
+ *     (thread-local). Nothing here ever falls back to a CPU implementation: without a CUDA device
+ *     mxb_ctx_create fails with MXB_ERR_CUDA.
+ *   - `mem` says where ALL data pointers of that call live: MXB_MEM_HOST (the call copies in, runs,
+ *     copies out and returns when the results are in host memory) or MXB_MEM_DEVICE (asynchronous on
+ *     `stream`, a cudaStream_t passed as void*; NULL = the legacy default stream).
+ *   - one handle is driven from one thread/stream at a time (like the reference objects, which are
+ *     owned by the audio thread); different handles are independent.
+ *   - sample values are fp64 for the oscillator/filter/envelope/delay/mix path (the reference's
+ *     `double`), fp32 for the FFT path (the reference's `float`), fp64 for MFCCs.
+ */
+#ifndef MAXIB200_H
+#define MAXIB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MXB_VERSION 100
+
+/* status codes */
+enum {
+    MXB_OK = 0,
+    MXB_ERR_INVALID = -1,      /* bad argument (NULL handle, size out of range, unknown id) */
+    MXB_ERR_CUDA = -2,         /* CUDA runtime error, or no CUDA device */
+    MXB_ERR_ALLOC = -3,        /* out of host or device memory */
+    MXB_ERR_UNSUPPORTED = -4,  /* a combination this build has no kernel for */
+    MXB_ERR_STATE = -5         /* call out of order (e.g. parameter never set) */
+};
+
+/* MXB_MEM_SPLIT (mxb_bank_process only): control data (gates) and the mix bus in host memory, `out`
+ * in device memory -- the voice signals stay on the GPU for the next stage, the host gets the mix. */
+enum { MXB_MEM_HOST = 0, MXB_MEM_DEVICE = 1, MXB_MEM_SPLIT = 2 };
+enum { MXB_F64 = 0, MXB_F32 = 1 };
+
+/* oscillator kinds: maxiOsc methods, src/maximilian.cpp */
+enum {
+    MXB_OSC_SINEWAVE = 0,  /* :228-235 */
+    MXB_OSC_COSWAVE = 1,   /* :276-283 */
+    MXB_OSC_PHASOR = 2,    /* :285-291 */
+    MXB_OSC_SAW = 3,       /* :333-340 */
+    MXB_OSC_SQUARE = 4,    /* :293-300 */
+    MXB_OSC_PULSE = 5,     /* :302-311 */
+    MXB_OSC_IMPULSE = 6,   /* :312-319 */
+    MXB_OSC_TRIANGLE = 7   /* :362-373 */
+};
+/* filter kinds */
+enum {
+    MXB_FILT_NONE = 0,
+    MXB_FILT_LORES = 1,    /* maxiFilter::lores  src/maximilian.cpp:455-468 */
+    MXB_FILT_HIRES = 2,    /* maxiFilter::hires  src/maximilian.cpp:471-484 */
+    MXB_FILT_SVF = 3,      /* maxiSVF::play      src/maximilian.h:1305-1319 */
+    MXB_FILT_BIQUAD = 4    /* maxiBiquad::play   src/maximilian.h:1360-1367 */
+};
+/* maxiBiquad::filterTypes, src/maximilian.h:1348-1357 */
+enum { MXB_BQ_LOWPASS = 0, MXB_BQ_HIGHPASS, MXB_BQ_BANDPASS, MXB_BQ_NOTCH, MXB_BQ_PEAK, MXB_BQ_LOWSHELF, MXB_BQ_HIGHSHELF };
+enum { MXB_ENV_NONE = 0, MXB_ENV_ADSR = 1 /* maxiEnv::adsr(input, trigger) src/maximilian.cpp:1415-1466 */ };
+
+/* per-voice parameter / state arrays: double[voices] */
+enum {
+    MXB_P_FREQ = 0,           /* frequency argument of the maxiOsc method, Hz */
+    MXB_P_PHASE = 1,          /* maxiOsc::phaseReset (src/maximilian.cpp:222-226); readable as state */
+    MXB_P_DUTY = 2,           /* maxiOsc::pulse duty */
+    MXB_P_CUTOFF = 3,         /* lores/hires cutoff1 | maxiSVF::setCutoff | maxiBiquad::set cutoff */
+    MXB_P_RESONANCE = 4,      /* lores/hires resonance | maxiSVF::setResonance | maxiBiquad::set Q */
+    MXB_P_GAIN = 5,           /* maxiBiquad::set peakGain */
+    MXB_P_ENV_ATTACK = 6,     /* maxiEnv::attack  (public member; see mxb_env_coeffs for the setters) */
+    MXB_P_ENV_DECAY = 7,      /* maxiEnv::decay */
+    MXB_P_ENV_SUSTAIN = 8,    /* maxiEnv::sustain */
+    MXB_P_ENV_RELEASE = 9,    /* maxiEnv::release */
+    MXB_P_ENV_HOLDTIME = 10,  /* maxiEnv::holdtime (integral value; default 1, src/maximilian.h:913) */
+    MXB_P_DELAY_SIZE = 11,    /* maxiDelayline::dl size argument (integral value) */
+    MXB_P_DELAY_FEEDBACK = 12,/* maxiDelayline::dl feedback argument */
+    MXB_P_PAN = 13,           /* maxiMix::stereo x (src/maximilian.cpp:503-509) */
+    MXB_P_COUNT = 14,
+    /* read-only state (mxb_bank_get_state) */
+    MXB_S_FILT_0 = 32,        /* lores/hires x | svf v0z | biquad v[1] */
+    MXB_S_FILT_1 = 33,        /* lores/hires y | svf v1  | biquad v[2] */
+    MXB_S_FILT_2 = 34,        /* svf v2 */
+    MXB_S_ENV_AMPLITUDE = 35,
+    MXB_S_ENV_OUTPUT = 36,
+    MXB_S_ENV_HOLDCOUNT = 37,
+    MXB_S_ENV_FLAGS = 38,     /* attackphase | decayphase<<1 | sustainphase<<2 | holdphase<<3 | releasephase<<4 */
+    MXB_S_DELAY_PHASE = 39    /* maxiDelayline::phase (the ring index, an int in the reference) */
+};
+
+typedef struct mxb_ctx mxb_ctx;
+typedef struct mxb_bank mxb_bank;
+typedef struct mxb_stft mxb_stft;
+typedef struct mxb_mfcc mxb_mfcc;
+typedef struct mxb_istft mxb_istft;
+
+const char* mxb_last_error(void);
+int32_t mxb_version(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Context = one CUDA device + the sample rate. Replaces the process-global maxiSettings::setup()
+ * (src/maximilian.h:117-163); the rate is captured here instead of being re-read on every sample
+ * (src/maximilian.cpp:232,460). */
+int32_t mxb_ctx_create(int32_t device, int32_t sample_rate, mxb_ctx** ctx);
+int32_t mxb_ctx_destroy(mxb_ctx* ctx);
+int32_t mxb_ctx_sample_rate(const mxb_ctx* ctx);
+int32_t mxb_ctx_synchronize(mxb_ctx* ctx);
+/* page-locked host memory for MXB_MEM_HOST buffers (cudaHostAlloc); pageable memory works too, slower */
+int32_t mxb_host_alloc(mxb_ctx* ctx, uint64_t bytes, void** ptr);
+int32_t mxb_host_free(mxb_ctx* ctx, void* ptr);
+
+/* ------------------------------------------------------------------------------------------------
+ * Voice bank: `voices` independent voices, each the chain
+ *     x = maxiOsc::<osc_kind>(freq)  ->  [maxiEnv::adsr(x, trigger)]  ->  [filter]  ->
+ *         [maxiDelayline::dl(x, size, feedback)]  ->  out[t][v] = x,  mix[t][0..1] += maxiMix::stereo(x, pan)
+ * i.e. the body of a reference play() that loops over an array of voices
+ * (cpp/commandline/maximilian_examples/15.polysynth/main.cpp:54-70), for n frames per call.
+ * All state (phase, filter memory, envelope flags, delay ring and its int index) lives on the device
+ * between calls, exactly as it lives in the reference objects between play() calls. */
+typedef struct {
+    int32_t voices;
+    int32_t osc_kind;        /* MXB_OSC_* */
+    int32_t filt_kind;       /* MXB_FILT_* */
+    int32_t biquad_type;     /* MXB_BQ_*   (filt_kind == MXB_FILT_BIQUAD) */
+    int32_t env_kind;        /* MXB_ENV_* */
+    int32_t delay_taps;      /* 0 = no delay line; else ring slots per voice (reference: 705600 fixed, src/maximilian.h:273) */
+    int32_t max_frames;      /* largest n_frames a process call will use (maxiSettings::bufferSize) */
+    int32_t reserved;
+    double  svf_mix[4];      /* lpmix, bpmix, hpmix, notchmix arguments of maxiSVF::play */
+} mxb_bank_desc;
+
+int32_t mxb_bank_create(mxb_ctx* ctx, const mxb_bank_desc* desc, mxb_bank** bank);
+int32_t mxb_bank_destroy(mxb_bank* bank);
+int32_t mxb_bank_voices(const mxb_bank* bank);
+/* values: double[voices]. Filter coefficients are designed here, once per change, with the
+ * reference's own formulas (lores/hires src/maximilian.cpp:457-462, maxiSVF::setParams
+ * src/maximilian.h:1322-1334, maxiBiquad::set src/maximilian.h:1375-1479): block-constant
+ * parameters hoist out of the per-sample loop exactly. */
+int32_t mxb_bank_set_param(mxb_bank* bank, int32_t id, const double* values, int32_t mem);
+int32_t mxb_bank_get_state(mxb_bank* bank, int32_t id, double* values, int32_t mem);
+/* ring slots [0, n) of voice v (debug / checkpoint) */
+int32_t mxb_bank_get_ring(mxb_bank* bank, int32_t voice, double* dst, int32_t n, int32_t mem);
+/* One block. trigger_v(t) = 1 for trig_on[v] <= t < trig_off[v] (t counts frames inside this call),
+ * both NULL = trigger 0. out: [n_frames][voices] of out_dtype, or NULL. mix: double [n_frames][2]
+ * (overwritten), or NULL; voices are summed in a fixed order, so results are run-to-run identical. */
+int32_t mxb_bank_process(mxb_bank* bank, int32_t n_frames,
+                         const int32_t* trig_on, const int32_t* trig_off,
+                         void* out, int32_t out_dtype, double* mix,
+                         int32_t mem, void* stream);
+/* kernels launched by this library on behalf of `bank` since creation (for bench.py's gpu_launches) */
+int64_t mxb_bank_launch_count(const mxb_bank* bank);
+
+/* the reference's envelope setters, vectorised: kind 0 = setAttack (1 - pow(0.01, 1/(ms*sr*0.001))),
+ * 1 = setAttackMS (1/(ms/1000*sr)), 2 = setDecay == setRelease (pow(0.01, 1/(ms*sr*0.001))).
+ * src/maximilian.cpp:1469-1486. Host arrays. */
+int32_t mxb_env_coeffs(int32_t kind, const double* ms, int64_t n, int32_t sample_rate, double* coeff);
+
+/* ------------------------------------------------------------------------------------------------
+ * Streaming STFT over `channels` independent channels = one maxiFFT::setup(fft_size, hop_size, fft_size)
+ * + process(x, WITH_POLAR_CONVERSION) per channel (src/libs/maxiFFT.cpp:45-91). The transform replays
+ * the reference's float arithmetic (recurrence twiddles, conjugate sign, DC/Nyquist packed in bin 0,
+ * bin N/4 left untangled: src/libs/fft.cpp:118-282), so real/imag/magnitude are bit-identical.
+ * Sample (c, t) of the input is in[c*stride_c + t*stride_t] (planar: stride_c = n, stride_t = 1;
+ * time-major like a bank's out: stride_c = 1, stride_t = channels).
+ * Frame f of channel c is written at ((c*max_frames) + f)*bins of mags/phases/re/im (each optional)
+ * and at ((c*max_frames) + f)*num_coeffs of coeffs when an mfcc handle is given (fused: the spectrum
+ * never leaves the chip unless asked for). *n_frames receives the frames fired per channel. */
+int32_t mxb_stft_create(mxb_ctx* ctx, int32_t channels, int32_t fft_size, int32_t hop_size, mxb_stft** st);
+int32_t mxb_stft_destroy(mxb_stft* st);
+int32_t mxb_stft_process(mxb_stft* st, const float* in, int64_t stride_c, int64_t stride_t, int32_t n_samples,
+                         int32_t max_frames, float* mags, float* phases, float* re, float* im,
+                         mxb_mfcc* mfcc, double* coeffs, int32_t* n_frames, int32_t mem, void* stream);
+int64_t mxb_stft_launch_count(const mxb_stft* st);
+
+/* maxiMFCC::setup(numBins, numFilters, numCoeffs, minFreq, maxFreq) + mfcc() (src/libs/maxiMFCC.h:56-111,
+ * src/libs/maxiMFCC.cpp:48-66). mags: float [n][num_bins]; coeffs: double [n][num_coeffs];
+ * melbands (optional): double [n][num_filters] after the log stage. */
+int32_t mxb_mfcc_create(mxb_ctx* ctx, int32_t num_bins, int32_t num_filters, int32_t num_coeffs,
+                        double min_freq, double max_freq, mxb_mfcc** m);
+int32_t mxb_mfcc_destroy(mxb_mfcc* m);
+int32_t mxb_mfcc_process(mxb_mfcc* m, const float* mags, int64_t n, double* coeffs, double* melbands,
+                         int32_t mem, void* stream);
+
+/* maxiIFFT::setup + process(mags, phases, SPECTRUM) per channel (src/libs/maxiFFT.cpp:141-192).
+ * mags/phases: frame f of channel c at (c*frames + f)*bins; out: planar float [channels][frames*hop]. */
+int32_t mxb_istft_create(mxb_ctx* ctx, int32_t channels, int32_t fft_size, int32_t hop_size, mxb_istft** st);
+int32_t mxb_istft_destroy(mxb_istft* st);
+int32_t mxb_istft_process(mxb_istft* st, const float* mags, const float* phases, int32_t frames, float* out,
+                          int32_t mem, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MAXIB200_H */

@@ -1,0 +1,339 @@
+"""ctypes binding of libmaxib200.so (include/maxib200.h) -- the C ABI is the product boundary; this
+module only marshals numpy / raw device pointers into it. There is no CPU implementation behind these
+classes: a missing library or a missing CUDA device raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "lib", "libmaxib200.so")
+
+MEM_HOST, MEM_DEVICE = 0, 1
+F64, F32 = 0, 1
+
+OSC = dict(sinewave=0, coswave=1, phasor=2, saw=3, square=4, pulse=5, impulse=6, triangle=7)
+FILT = dict(none=0, lores=1, hires=2, svf=3, biquad=4)
+BIQUAD = dict(lowpass=0, highpass=1, bandpass=2, notch=3, peak=4, lowshelf=5, highshelf=6)
+P = dict(freq=0, phase=1, duty=2, cutoff=3, resonance=4, gain=5, env_attack=6, env_decay=7,
+         env_sustain=8, env_release=9, env_holdtime=10, delay_size=11, delay_feedback=12, pan=13,
+         filt0=32, filt1=33, filt2=34, env_amplitude=35, env_output=36, env_holdcount=37,
+         env_flags=38, delay_phase=39)
+
+EXPORTS = [
+    "mxb_last_error", "mxb_version", "mxb_ctx_create", "mxb_ctx_destroy", "mxb_ctx_sample_rate",
+    "mxb_ctx_synchronize", "mxb_host_alloc", "mxb_host_free",
+    "mxb_bank_create", "mxb_bank_destroy", "mxb_bank_voices", "mxb_bank_set_param", "mxb_bank_get_state",
+    "mxb_bank_get_ring", "mxb_bank_process", "mxb_bank_launch_count", "mxb_env_coeffs",
+    "mxb_stft_create", "mxb_stft_destroy", "mxb_stft_process", "mxb_stft_launch_count",
+    "mxb_mfcc_create", "mxb_mfcc_destroy", "mxb_mfcc_process",
+    "mxb_istft_create", "mxb_istft_destroy", "mxb_istft_process",
+]
+
+
+class MxbError(RuntimeError):
+    pass
+
+
+class BankDesc(C.Structure):
+    _fields_ = [("voices", C.c_int32), ("osc_kind", C.c_int32), ("filt_kind", C.c_int32),
+                ("biquad_type", C.c_int32), ("env_kind", C.c_int32), ("delay_taps", C.c_int32),
+                ("max_frames", C.c_int32), ("reserved", C.c_int32), ("svf_mix", C.c_double * 4)]
+
+
+_lib = None
+
+
+def lib():
+    """Load libmaxib200.so; raises if it has not been built (python -m maximilian_b200.build)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise MxbError(f"{LIB_PATH} is missing: build it with `python -m maximilian_b200.build` "
+                       "(there is no CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    vp, i32, i64, dbl = C.c_void_p, C.c_int32, C.c_int64, C.c_double
+    pp = C.POINTER(C.c_void_p)
+    sig = {
+        "mxb_last_error": (C.c_char_p, []),
+        "mxb_version": (i32, []),
+        "mxb_ctx_create": (i32, [i32, i32, pp]),
+        "mxb_ctx_destroy": (i32, [vp]),
+        "mxb_ctx_sample_rate": (i32, [vp]),
+        "mxb_ctx_synchronize": (i32, [vp]),
+        "mxb_host_alloc": (i32, [vp, C.c_uint64, pp]),
+        "mxb_host_free": (i32, [vp, vp]),
+        "mxb_bank_create": (i32, [vp, C.POINTER(BankDesc), pp]),
+        "mxb_bank_destroy": (i32, [vp]),
+        "mxb_bank_voices": (i32, [vp]),
+        "mxb_bank_set_param": (i32, [vp, i32, vp, i32]),
+        "mxb_bank_get_state": (i32, [vp, i32, vp, i32]),
+        "mxb_bank_get_ring": (i32, [vp, i32, vp, i32, i32]),
+        "mxb_bank_process": (i32, [vp, i32, vp, vp, vp, i32, vp, i32, vp]),
+        "mxb_bank_launch_count": (i64, [vp]),
+        "mxb_env_coeffs": (i32, [i32, vp, i64, i32, vp]),
+        "mxb_stft_create": (i32, [vp, i32, i32, i32, pp]),
+        "mxb_stft_destroy": (i32, [vp]),
+        "mxb_stft_process": (i32, [vp, vp, i64, i64, i32, i32, vp, vp, vp, vp, vp, vp, C.POINTER(i32), i32, vp]),
+        "mxb_stft_launch_count": (i64, [vp]),
+        "mxb_mfcc_create": (i32, [vp, i32, i32, i32, dbl, dbl, pp]),
+        "mxb_mfcc_destroy": (i32, [vp]),
+        "mxb_mfcc_process": (i32, [vp, vp, i64, vp, vp, i32, vp]),
+        "mxb_istft_create": (i32, [vp, i32, i32, i32, pp]),
+        "mxb_istft_destroy": (i32, [vp]),
+        "mxb_istft_process": (i32, [vp, vp, vp, i32, vp, i32, vp]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(L, name)          # AttributeError here = the library does not export a declared symbol
+        fn.restype, fn.argtypes = res, args
+    _lib = L
+    return L
+
+
+def check(rc, what=""):
+    if rc != 0:
+        raise MxbError(f"{what} -> {rc}: {lib().mxb_last_error().decode(errors='replace')}")
+
+
+def _np_ptr(a):
+    return C.c_void_p(a.ctypes.data) if a is not None else None
+
+
+def _ptr(x):
+    """numpy array -> host pointer; int -> raw (device) pointer; None -> NULL."""
+    if x is None:
+        return None
+    if isinstance(x, np.ndarray):
+        return C.c_void_p(x.ctypes.data)
+    return C.c_void_p(int(x))
+
+
+class Context:
+    """mxb_ctx: one CUDA device + the sample rate (the reference's maxiSettings::setup)."""
+
+    def __init__(self, device=0, sample_rate=48000):
+        self.h = C.c_void_p()
+        check(lib().mxb_ctx_create(device, sample_rate, C.byref(self.h)), "mxb_ctx_create")
+        self.device, self.sample_rate = device, sample_rate
+
+    def synchronize(self):
+        check(lib().mxb_ctx_synchronize(self.h), "mxb_ctx_synchronize")
+
+    def close(self):
+        if self.h:
+            lib().mxb_ctx_destroy(self.h)
+            self.h = None
+
+
+_default_ctx = {}
+
+
+def default_context(device=0, sample_rate=48000):
+    key = (device, sample_rate)
+    if key not in _default_ctx:
+        _default_ctx[key] = Context(device, sample_rate)
+    return _default_ctx[key]
+
+
+class Bank:
+    """V voices of  osc -> [adsr] -> [filter] -> [delay] -> out / stereo mix  on the GPU (mxb_bank)."""
+
+    def __init__(self, voices, osc="saw", filt="none", env=False, delay=False, sample_rate=48000,
+                 biquad_type="lowpass", svf_mix=(1.0, 0.0, 0.0, 0.0), delay_capacity=4096, max_frames=1024,
+                 ctx=None, device=0):
+        self.ctx = ctx or default_context(device, sample_rate)
+        if self.ctx.sample_rate != sample_rate:
+            raise MxbError("context sample rate differs from the requested one")
+        self.V = int(voices)
+        self.max_frames = int(max_frames)
+        d = BankDesc(self.V, OSC[osc], FILT[filt], BIQUAD[biquad_type], 1 if env else 0,
+                     int(delay_capacity) if delay else 0, self.max_frames, 0, (C.c_double * 4)(*svf_mix))
+        self.h = C.c_void_p()
+        check(lib().mxb_bank_create(self.ctx.h, C.byref(d), C.byref(self.h)), "mxb_bank_create")
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().mxb_bank_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- parameters / state ------------------------------------------------------------------
+    def set(self, name, values):
+        a = np.ascontiguousarray(np.broadcast_to(np.asarray(values, dtype=np.float64), (self.V,)))
+        check(lib().mxb_bank_set_param(self.h, P[name], _np_ptr(a), MEM_HOST), f"mxb_bank_set_param({name})")
+
+    def set_device(self, name, dev_ptr):
+        check(lib().mxb_bank_set_param(self.h, P[name], C.c_void_p(int(dev_ptr)), MEM_DEVICE), f"mxb_bank_set_param({name})")
+
+    def get(self, name):
+        a = np.empty(self.V, dtype=np.float64)
+        check(lib().mxb_bank_get_state(self.h, P[name], _np_ptr(a), MEM_HOST), f"mxb_bank_get_state({name})")
+        return a
+
+    def ring(self, v, n):
+        a = np.empty(n, dtype=np.float64)
+        check(lib().mxb_bank_get_ring(self.h, v, _np_ptr(a), n, MEM_HOST), "mxb_bank_get_ring")
+        return a
+
+    @property
+    def launches(self):
+        return int(lib().mxb_bank_launch_count(self.h))
+
+    # -- one block ---------------------------------------------------------------------------
+    def process(self, nframes, trig_on=None, trig_off=None, want_out=True, want_mix=False, out_dtype=np.float64,
+                out=None, mix=None):
+        """Host buffers in, host buffers out (MXB_MEM_HOST). Returns (out[nframes][V] | None, mix[nframes][2] | None)."""
+        f32 = np.dtype(out_dtype) == np.float32
+        if want_out and out is None:
+            out = np.empty((nframes, self.V), dtype=np.float32 if f32 else np.float64)
+        if want_mix and mix is None:
+            mix = np.empty((nframes, 2), dtype=np.float64)
+        ton = np.ascontiguousarray(trig_on, dtype=np.int32) if trig_on is not None else None
+        toff = np.ascontiguousarray(trig_off, dtype=np.int32) if trig_off is not None else None
+        check(lib().mxb_bank_process(self.h, nframes, _np_ptr(ton), _np_ptr(toff), _np_ptr(out if want_out else None),
+                                     F32 if f32 else F64, _np_ptr(mix if want_mix else None), MEM_HOST, None),
+              "mxb_bank_process")
+        return (out if want_out else None), (mix if want_mix else None)
+
+    def process_device(self, nframes, out_ptr=None, mix_ptr=None, trig_on_ptr=None, trig_off_ptr=None,
+                       f32=False, stream=0):
+        """Device pointers, asynchronous on `stream` (a raw cudaStream_t value)."""
+        check(lib().mxb_bank_process(self.h, nframes, _ptr(trig_on_ptr), _ptr(trig_off_ptr), _ptr(out_ptr),
+                                     F32 if f32 else F64, _ptr(mix_ptr), MEM_DEVICE, C.c_void_p(int(stream)) if stream else None),
+              "mxb_bank_process")
+
+
+    def process_split(self, nframes, out_ptr, mix, trig_on=None, trig_off=None, f32=False, stream=0):
+        """MXB_MEM_SPLIT: gates / mix are host numpy arrays, `out_ptr` is a raw device pointer (or None).
+        Returns when the mix is in host memory."""
+        check(lib().mxb_bank_process(self.h, nframes, _np_ptr(trig_on), _np_ptr(trig_off), _ptr(out_ptr),
+                                     F32 if f32 else F64, _np_ptr(mix), 2, C.c_void_p(int(stream)) if stream else None),
+              "mxb_bank_process")
+
+    def set_host_array(self, name, a):
+        """set() without the broadcast/convert step: `a` must be a contiguous float64 array of V values."""
+        check(lib().mxb_bank_set_param(self.h, P[name], C.c_void_p(a.ctypes.data), MEM_HOST), f"mxb_bank_set_param({name})")
+
+
+def env_coeffs(kind, ms, sample_rate=48000):
+    """maxiEnv setters, vectorised: kind 0 setAttack, 1 setAttackMS, 2 setDecay/setRelease."""
+    ms = np.ascontiguousarray(ms, dtype=np.float64)
+    out = np.empty_like(ms)
+    check(lib().mxb_env_coeffs(kind, _np_ptr(ms), ms.size, sample_rate, _np_ptr(out)), "mxb_env_coeffs")
+    return out
+
+
+class Stft:
+    """Streaming STFT over C channels (mxb_stft), optionally fused with an Mfcc."""
+
+    def __init__(self, channels, fft_size=1024, hop=512, ctx=None, device=0, sample_rate=48000):
+        self.ctx = ctx or default_context(device, sample_rate)
+        self.C, self.n, self.hop, self.bins = int(channels), int(fft_size), int(hop), int(fft_size) // 2
+        self.h = C.c_void_p()
+        check(lib().mxb_stft_create(self.ctx.h, self.C, self.n, self.hop, C.byref(self.h)), "mxb_stft_create")
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().mxb_stft_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def launches(self):
+        return int(lib().mxb_stft_launch_count(self.h))
+
+    def process(self, x, want=("mags", "phases", "re", "im"), mfcc=None):
+        """x: float32 [C][n] planar host array. Returns dict of [C][frames][bins] (+ 'mfcc' [C][frames][coeffs])."""
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        assert x.shape[0] == self.C
+        n = x.shape[1]
+        maxf = max(1, n // self.hop + 2)
+        bufs = {k: (np.zeros((self.C, maxf, self.bins), dtype=np.float32) if k in want else None)
+                for k in ("mags", "phases", "re", "im")}
+        co = np.zeros((self.C, maxf, mfcc.coeffs), dtype=np.float64) if mfcc is not None else None
+        nf = C.c_int32(0)
+        check(lib().mxb_stft_process(self.h, _np_ptr(x), n, 1, n, maxf, _np_ptr(bufs["mags"]), _np_ptr(bufs["phases"]),
+                                     _np_ptr(bufs["re"]), _np_ptr(bufs["im"]), mfcc.h if mfcc is not None else None,
+                                     _np_ptr(co), C.byref(nf), MEM_HOST, None), "mxb_stft_process")
+        f = nf.value
+        r = {k: np.ascontiguousarray(v[:, :f]) for k, v in bufs.items() if v is not None}
+        if co is not None:
+            r["mfcc"] = np.ascontiguousarray(co[:, :f])
+        return r
+
+    def process_device(self, in_ptr, stride_c, stride_t, n, max_frames, mags=None, phases=None, re=None, im=None,
+                       mfcc=None, coeffs=None, stream=0):
+        nf = C.c_int32(0)
+        check(lib().mxb_stft_process(self.h, _ptr(in_ptr), stride_c, stride_t, n, max_frames, _ptr(mags), _ptr(phases),
+                                     _ptr(re), _ptr(im), mfcc.h if mfcc is not None else None, _ptr(coeffs),
+                                     C.byref(nf), MEM_DEVICE, C.c_void_p(int(stream)) if stream else None), "mxb_stft_process")
+        return nf.value
+
+
+class Mfcc:
+    def __init__(self, num_bins=512, num_filters=42, num_coeffs=40, min_freq=20.0, max_freq=20000.0,
+                 ctx=None, device=0, sample_rate=48000):
+        self.ctx = ctx or default_context(device, sample_rate)
+        self.bins, self.filters, self.coeffs = int(num_bins), int(num_filters), int(num_coeffs)
+        self.h = C.c_void_p()
+        check(lib().mxb_mfcc_create(self.ctx.h, self.bins, self.filters, self.coeffs, float(min_freq), float(max_freq),
+                                    C.byref(self.h)), "mxb_mfcc_create")
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().mxb_mfcc_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def process(self, mags):
+        m = np.ascontiguousarray(mags, dtype=np.float32)
+        lead = m.shape[:-1]
+        n = int(np.prod(lead)) if lead else 1
+        co = np.empty((n, self.coeffs), dtype=np.float64)
+        mb = np.empty((n, self.filters), dtype=np.float64)
+        check(lib().mxb_mfcc_process(self.h, _np_ptr(m), n, _np_ptr(co), _np_ptr(mb), MEM_HOST, None), "mxb_mfcc_process")
+        return co.reshape(lead + (self.coeffs,)), mb.reshape(lead + (self.filters,))
+
+
+class Istft:
+    def __init__(self, channels, fft_size=1024, hop=512, ctx=None, device=0, sample_rate=48000):
+        self.ctx = ctx or default_context(device, sample_rate)
+        self.C, self.n, self.hop, self.bins = int(channels), int(fft_size), int(hop), int(fft_size) // 2
+        self.h = C.c_void_p()
+        check(lib().mxb_istft_create(self.ctx.h, self.C, self.n, self.hop, C.byref(self.h)), "mxb_istft_create")
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().mxb_istft_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def process(self, mags, phases):
+        m = np.ascontiguousarray(mags, dtype=np.float32)
+        p = np.ascontiguousarray(phases, dtype=np.float32)
+        frames = m.shape[1]
+        out = np.empty((self.C, frames * self.hop), dtype=np.float32)
+        check(lib().mxb_istft_process(self.h, _np_ptr(m), _np_ptr(p), frames, _np_ptr(out), MEM_HOST, None), "mxb_istft_process")
+        return out

@@ -1,0 +1,458 @@
+// Voice bank host side: handles, parameter upload, coefficient design (the reference's formulas, run once
+// per parameter change on the host with the same libm the reference uses), launches.
+#include <math.h>
+
+#include <new>
+
+#include "bank_kernels.cuh"
+#include "delay_kernels.cuh"
+
+using namespace mxb;
+
+struct mxb_bank {
+    mxb_ctx* ctx;
+    mxb_bank_desc desc;
+    int V;
+    bool set_mask[MXB_P_COUNT];
+    std::vector<double> hp[MXB_P_COUNT];     // host copies of the parameter arrays (coefficient design input)
+    double* dp[MXB_P_COUNT];                 // device copies
+    double* osc_out;
+    double *f0, *f1, *f2, *cf[5];
+    double *env_amp, *env_output;
+    long long *env_holdcount, *env_hold;
+    int* env_flags;
+    int *trig_on, *trig_off;                 // staging for MXB_MEM_HOST gates
+    int *dl_phase, *dl_size;
+    double* ring;                            // [V][delay_taps]
+    double* partials; size_t partials_len;
+    double* mix_dev;                         // [max_frames][2]
+    void* out_stage; size_t out_stage_bytes; // staging for MXB_MEM_HOST out
+    int64_t launches;
+};
+
+namespace {
+
+// maxiFilter::lores / hires coefficient part, src/maximilian.cpp:456-462 (identical in hires :472-478)
+void design_lores(const mxb_bank* b, std::vector<double>* cf) {
+    const double sr = (double)(size_t)b->ctx->sample_rate;
+    for (int v = 0; v < b->V; ++v) {
+        double cutoff = b->hp[MXB_P_CUTOFF][v], resonance = b->hp[MXB_P_RESONANCE][v];
+        if (cutoff < 10) cutoff = 10;
+        if (cutoff > sr) cutoff = sr;
+        if (resonance < 1.) resonance = 1.;
+        const double z = cos(6.283185307179586476925286766559 * cutoff / sr);
+        const double c = 2 - 2 * z;
+        const double r = (sqrt(2.0) * sqrt(-pow((z - 1.0), 3.0)) + resonance * (z - 1)) / (resonance * (z - 1));
+        cf[0][v] = c; cf[1][v] = r;
+    }
+}
+
+// maxiSVF::setParams, src/maximilian.h:1322-1334
+void design_svf(const mxb_bank* b, std::vector<double>* cf) {
+    const double sr = (double)(size_t)b->ctx->sample_rate;
+    for (int v = 0; v < b->V; ++v) {
+        const double freq = b->hp[MXB_P_CUTOFF][v], res = b->hp[MXB_P_RESONANCE][v];
+        const double g = tan(3.1415926535897932384626433832795 * freq / sr);
+        const double damping = res == 0 ? 0 : 1.0 / res;
+        const double k = damping;
+        const double ginv = g / (1.0 + g * (g + k));
+        cf[0][v] = ginv; cf[1][v] = 2.0 * (g + k) * ginv; cf[2][v] = g * ginv; cf[3][v] = 2.0 * ginv; cf[4][v] = k;
+    }
+}
+
+// maxiBiquad::set, src/maximilian.h:1375-1479
+void design_biquad(const mxb_bank* b, std::vector<double>* cf) {
+    const double sr = (double)(size_t)b->ctx->sample_rate;
+    const double SQRT2 = sqrt(2.0);
+    for (int v = 0; v < b->V; ++v) {
+        const double cutoff = b->hp[MXB_P_CUTOFF][v], Q = b->hp[MXB_P_RESONANCE][v], peakGain = b->hp[MXB_P_GAIN][v];
+        double norm = 0, a0 = 0, a1 = 0, a2 = 0, b1 = 0, b2 = 0;
+        const double G = pow(10.0, fabs(peakGain) / 20.0);
+        const double K = tan(3.1415926535897932384626433832795 * cutoff / sr);
+        switch (b->desc.biquad_type) {
+            case MXB_BQ_LOWPASS:
+                norm = 1.0 / (1.0 + K / Q + K * K);
+                a0 = K * K * norm; a1 = 2.0 * a0; a2 = a0;
+                b1 = 2.0 * (K * K - 1.0) * norm; b2 = (1.0 - K / Q + K * K) * norm; break;
+            case MXB_BQ_HIGHPASS:
+                norm = 1. / (1. + K / Q + K * K);
+                a0 = 1 * norm; a1 = -2 * a0; a2 = a0;
+                b1 = 2 * (K * K - 1) * norm; b2 = (1 - K / Q + K * K) * norm; break;
+            case MXB_BQ_BANDPASS:
+                norm = 1. / (1. + K / Q + K * K);
+                a0 = K / Q * norm; a1 = 0.; a2 = -a0;
+                b1 = 2. * (K * K - 1.) * norm; b2 = (1. - K / Q + K * K) * norm; break;
+            case MXB_BQ_NOTCH:
+                norm = 1. / (1. + K / Q + K * K);
+                a0 = (1. + K * K) * norm; a1 = 2. * (K * K - 1.) * norm; a2 = a0;
+                b1 = a1; b2 = (1. - K / Q + K * K) * norm; break;
+            case MXB_BQ_PEAK:
+                if (peakGain >= 0.0) {
+                    norm = 1. / (1. + 1. / Q * K + K * K);
+                    a0 = (1. + G / Q * K + K * K) * norm; a1 = 2. * (K * K - 1.) * norm;
+                    a2 = (1. - G / Q * K + K * K) * norm; b1 = a1; b2 = (1. - 1. / Q * K + K * K) * norm;
+                } else {
+                    norm = 1. / (1. + G / Q * K + K * K);
+                    a0 = (1. + 1 / Q * K + K * K) * norm; a1 = 2. * (K * K - 1) * norm;
+                    a2 = (1. - 1. / Q * K + K * K) * norm; b1 = a1; b2 = (1. - G / Q * K + K * K) * norm;
+                }
+                break;
+            case MXB_BQ_LOWSHELF:
+                if (peakGain >= 0.) {
+                    norm = 1. / (1. + SQRT2 * K + K * K);
+                    a0 = (1. + sqrt(2. * G) * K + G * K * K) * norm; a1 = 2. * (G * K * K - 1.) * norm;
+                    a2 = (1. - sqrt(2. * G) * K + G * K * K) * norm;
+                    b1 = 2. * (K * K - 1.) * norm; b2 = (1. - SQRT2 * K + K * K) * norm;
+                } else {
+                    norm = 1. / (1. + sqrt(2. * G) * K + G * K * K);
+                    a0 = (1. + SQRT2 * K + K * K) * norm; a1 = 2. * (K * K - 1.) * norm;
+                    a2 = (1. - SQRT2 * K + K * K) * norm;
+                    b1 = 2. * (G * K * K - 1.) * norm; b2 = (1. - sqrt(2. * G) * K + G * K * K) * norm;
+                }
+                break;
+            case MXB_BQ_HIGHSHELF:
+                if (peakGain >= 0.) {
+                    norm = 1. / (1. + SQRT2 * K + K * K);
+                    a0 = (G + sqrt(2. * G) * K + K * K) * norm; a1 = 2. * (K * K - G) * norm;
+                    a2 = (G - sqrt(2. * G) * K + K * K) * norm;
+                    b1 = 2. * (K * K - 1) * norm; b2 = (1. - SQRT2 * K + K * K) * norm;
+                } else {
+                    norm = 1. / (G + sqrt(2. * G) * K + K * K);
+                    a0 = (1. + SQRT2 * K + K * K) * norm; a1 = 2. * (K * K - 1.) * norm;
+                    a2 = (1. - SQRT2 * K + K * K) * norm;
+                    b1 = 2. * (K * K - G) * norm; b2 = (G - sqrt(2. * G) * K + K * K) * norm;
+                }
+                break;
+            default: break;
+        }
+        cf[0][v] = a0; cf[1][v] = a1; cf[2][v] = a2; cf[3][v] = b1; cf[4][v] = b2;
+    }
+}
+
+int redesign(mxb_bank* b) {
+    const int fk = b->desc.filt_kind;
+    if (fk == MXB_FILT_NONE) return MXB_OK;
+    if ((fk == MXB_FILT_LORES || fk == MXB_FILT_HIRES) && !(b->set_mask[MXB_P_CUTOFF] && b->set_mask[MXB_P_RESONANCE])) return MXB_OK;
+    if (fk == MXB_FILT_BIQUAD && !(b->set_mask[MXB_P_CUTOFF] && b->set_mask[MXB_P_RESONANCE])) return MXB_OK;   // untouched maxiBiquad: all-zero coefficients
+    std::vector<double> cf[5];
+    for (auto& c : cf) c.assign((size_t)b->V, 0.0);
+    if (fk == MXB_FILT_LORES || fk == MXB_FILT_HIRES) design_lores(b, cf);
+    else if (fk == MXB_FILT_SVF) design_svf(b, cf);
+    else design_biquad(b, cf);
+    for (int i = 0; i < 5; ++i) MXB_CUDA(cudaMemcpy(b->cf[i], cf[i].data(), sizeof(double) * (size_t)b->V, cudaMemcpyHostToDevice));
+    return MXB_OK;
+}
+
+__global__ void mix_reduce_kernel(const double* __restrict__ partials, double* __restrict__ mix, int rows, int W) {
+    // one warp per (frame, channel) row: lanes take a strided subset of the per-warp partial sums in
+    // ascending order, then a fixed xor tree -- the summation order never changes between runs.
+    const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const double* p = partials + (size_t)row * (size_t)W;
+    double s = 0.0;
+    for (int w = lane; w < W; w += 32) s += p[w];
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) s += __shfl_xor_sync(0xffffffffu, s, m);
+    if (lane == 0) mix[row] = s;
+}
+
+int free_bank(mxb_bank* b) {
+    if (!b) return MXB_OK;
+    for (int i = 0; i < MXB_P_COUNT; ++i) cudaFree(b->dp[i]);
+    cudaFree(b->osc_out); cudaFree(b->f0); cudaFree(b->f1); cudaFree(b->f2);
+    for (int i = 0; i < 5; ++i) cudaFree(b->cf[i]);
+    cudaFree(b->env_amp); cudaFree(b->env_output); cudaFree(b->env_holdcount); cudaFree(b->env_hold); cudaFree(b->env_flags);
+    cudaFree(b->trig_on); cudaFree(b->trig_off); cudaFree(b->dl_phase); cudaFree(b->dl_size); cudaFree(b->ring);
+    cudaFree(b->partials); cudaFree(b->mix_dev); cudaFree(b->out_stage);
+    delete b;
+    return MXB_OK;
+}
+
+int upload_fill(double* dst, size_t n, double value) {
+    std::vector<double> h(n, value);
+    MXB_CUDA(cudaMemcpy(dst, h.data(), sizeof(double) * n, cudaMemcpyHostToDevice));
+    return MXB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t mxb_bank_create(mxb_ctx* ctx, const mxb_bank_desc* d, mxb_bank** out) {
+    MXB_REQUIRE(ctx && d && out, MXB_ERR_INVALID, "mxb_bank_create: NULL argument");
+    *out = nullptr;
+    MXB_REQUIRE(d->voices > 0, MXB_ERR_INVALID, "mxb_bank_create: voices %d", d->voices);
+    MXB_REQUIRE(d->osc_kind >= MXB_OSC_SINEWAVE && d->osc_kind <= MXB_OSC_TRIANGLE, MXB_ERR_INVALID, "mxb_bank_create: osc_kind %d", d->osc_kind);
+    MXB_REQUIRE(d->filt_kind >= MXB_FILT_NONE && d->filt_kind <= MXB_FILT_BIQUAD, MXB_ERR_INVALID, "mxb_bank_create: filt_kind %d", d->filt_kind);
+    MXB_REQUIRE(d->biquad_type >= MXB_BQ_LOWPASS && d->biquad_type <= MXB_BQ_HIGHSHELF, MXB_ERR_INVALID, "mxb_bank_create: biquad_type %d", d->biquad_type);
+    MXB_REQUIRE(d->env_kind == MXB_ENV_NONE || d->env_kind == MXB_ENV_ADSR, MXB_ERR_INVALID, "mxb_bank_create: env_kind %d", d->env_kind);
+    MXB_REQUIRE(d->delay_taps >= 0, MXB_ERR_INVALID, "mxb_bank_create: delay_taps %d", d->delay_taps);
+    MXB_REQUIRE(d->max_frames > 0, MXB_ERR_INVALID, "mxb_bank_create: max_frames %d", d->max_frames);
+    DeviceGuard g(ctx->device);
+    MXB_REQUIRE(g.ok, MXB_ERR_CUDA, "mxb_bank_create: cudaSetDevice failed");
+    mxb_bank* b = new (std::nothrow) mxb_bank();
+    MXB_REQUIRE(b, MXB_ERR_ALLOC, "mxb_bank_create: out of host memory");
+    b->ctx = ctx; b->desc = *d; b->V = d->voices;
+    for (auto& p : b->dp) p = nullptr;
+    b->osc_out = b->f0 = b->f1 = b->f2 = nullptr;
+    for (auto& c : b->cf) c = nullptr;
+    b->env_amp = b->env_output = nullptr; b->env_holdcount = b->env_hold = nullptr; b->env_flags = nullptr;
+    b->trig_on = b->trig_off = b->dl_phase = b->dl_size = nullptr;
+    b->ring = b->partials = b->mix_dev = nullptr; b->partials_len = 0;
+    b->out_stage = nullptr; b->out_stage_bytes = 0; b->launches = 0;
+    const size_t V = (size_t)d->voices;
+    int rc = MXB_OK;
+#define TRY(x) do { rc = (x); if (rc != MXB_OK) { free_bank(b); return rc; } } while (0)
+    static const double defaults[MXB_P_COUNT] = {0, 0, 0.5, 1000.0, 1.0, 0, 0, 0, 0, 0, 1.0, 1.0, 0, 0.5};
+    for (int i = 0; i < MXB_P_COUNT; ++i) {
+        TRY(dev_alloc(&b->dp[i], V));
+        b->hp[i].assign(V, defaults[i]);
+        if (defaults[i] != 0.0) TRY(upload_fill(b->dp[i], V, defaults[i]));
+    }
+    TRY(dev_alloc(&b->osc_out, V));
+    TRY(dev_alloc(&b->f0, V)); TRY(dev_alloc(&b->f1, V)); TRY(dev_alloc(&b->f2, V));
+    for (int i = 0; i < 5; ++i) TRY(dev_alloc(&b->cf[i], V));
+    TRY(dev_alloc(&b->env_amp, V)); TRY(dev_alloc(&b->env_output, V));
+    TRY(dev_alloc(&b->env_holdcount, V)); TRY(dev_alloc(&b->env_hold, V)); TRY(dev_alloc(&b->env_flags, V));
+    {
+        std::vector<long long> one(V, 1);   // maxiEnv::holdtime = 1, src/maximilian.h:913
+        cudaError_t e = cudaMemcpy(b->env_hold, one.data(), sizeof(long long) * V, cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) { set_error("cudaMemcpy: %s", cudaGetErrorString(e)); free_bank(b); return MXB_ERR_CUDA; }
+    }
+    TRY(dev_alloc(&b->trig_on, V)); TRY(dev_alloc(&b->trig_off, V));
+    TRY(dev_alloc(&b->mix_dev, (size_t)d->max_frames * 2));
+    if (d->delay_taps > 0) {
+        TRY(dev_alloc(&b->dl_phase, V));
+        TRY(dev_alloc(&b->dl_size, V));
+        std::vector<int> one(V, 1);
+        cudaError_t e = cudaMemcpy(b->dl_size, one.data(), sizeof(int) * V, cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) { set_error("cudaMemcpy: %s", cudaGetErrorString(e)); free_bank(b); return MXB_ERR_CUDA; }
+        TRY(dev_alloc(&b->ring, dl_ring_doubles(V, d->delay_taps)));   // zeroed: maxiDelayline ctor memset, src/maximilian.cpp:415-417
+    }
+    if (d->filt_kind == MXB_FILT_SVF) {          // maxiSVF ctor: setParams(1000, 1), src/maximilian.h:1284
+        b->set_mask[MXB_P_CUTOFF] = b->set_mask[MXB_P_RESONANCE] = true;
+        TRY(redesign(b));
+        b->set_mask[MXB_P_CUTOFF] = b->set_mask[MXB_P_RESONANCE] = false;
+    }
+#undef TRY
+    *out = b;
+    return MXB_OK;
+}
+
+int32_t mxb_bank_destroy(mxb_bank* b) {
+    if (!b) return MXB_OK;
+    DeviceGuard g(b->ctx->device);
+    cudaDeviceSynchronize();
+    return free_bank(b);
+}
+
+int32_t mxb_bank_voices(const mxb_bank* b) { return b ? b->V : MXB_ERR_INVALID; }
+int64_t mxb_bank_launch_count(const mxb_bank* b) { return b ? b->launches : 0; }
+
+int32_t mxb_bank_set_param(mxb_bank* b, int32_t id, const double* values, int32_t mem) {
+    MXB_REQUIRE(b && values, MXB_ERR_INVALID, "mxb_bank_set_param: NULL argument");
+    MXB_REQUIRE(id >= 0 && id < MXB_P_COUNT, MXB_ERR_INVALID, "mxb_bank_set_param: unknown id %d", id);
+    MXB_REQUIRE(mem == MXB_MEM_HOST || mem == MXB_MEM_DEVICE, MXB_ERR_INVALID, "mxb_bank_set_param: mem %d", mem);
+    DeviceGuard g(b->ctx->device);
+    const size_t V = (size_t)b->V, bytes = sizeof(double) * V;
+    MXB_CUDA(cudaDeviceSynchronize());     // parameters change between blocks, never under a running one
+    if (mem == MXB_MEM_HOST) {
+        memcpy(b->hp[id].data(), values, bytes);
+        MXB_CUDA(cudaMemcpy(b->dp[id], values, bytes, cudaMemcpyHostToDevice));
+    } else {
+        MXB_CUDA(cudaMemcpy(b->dp[id], values, bytes, cudaMemcpyDeviceToDevice));
+        MXB_CUDA(cudaMemcpy(b->hp[id].data(), values, bytes, cudaMemcpyDeviceToHost));
+    }
+    b->set_mask[id] = true;
+    if (id == MXB_P_CUTOFF || id == MXB_P_RESONANCE || id == MXB_P_GAIN) {
+        int rc = redesign(b);
+        if (rc != MXB_OK) return rc;
+    } else if (id == MXB_P_ENV_HOLDTIME) {
+        std::vector<long long> h(V);
+        for (size_t v = 0; v < V; ++v) h[v] = (long long)b->hp[id][v];
+        MXB_CUDA(cudaMemcpy(b->env_hold, h.data(), sizeof(long long) * V, cudaMemcpyHostToDevice));
+    } else if (id == MXB_P_DELAY_SIZE && b->dl_size) {
+        std::vector<int> h(V);
+        for (size_t v = 0; v < V; ++v) {
+            const double s = b->hp[id][v];
+            MXB_REQUIRE(s <= (double)b->desc.delay_taps, MXB_ERR_INVALID,
+                        "mxb_bank_set_param: delay size %.0f of voice %zu exceeds delay_taps %d", s, v, b->desc.delay_taps);
+            h[v] = (int)s;
+        }
+        MXB_CUDA(cudaMemcpy(b->dl_size, h.data(), sizeof(int) * V, cudaMemcpyHostToDevice));
+    }
+    return MXB_OK;
+}
+
+int32_t mxb_bank_get_state(mxb_bank* b, int32_t id, double* values, int32_t mem) {
+    MXB_REQUIRE(b && values, MXB_ERR_INVALID, "mxb_bank_get_state: NULL argument");
+    MXB_REQUIRE(mem == MXB_MEM_HOST || mem == MXB_MEM_DEVICE, MXB_ERR_INVALID, "mxb_bank_get_state: mem %d", mem);
+    DeviceGuard g(b->ctx->device);
+    MXB_CUDA(cudaDeviceSynchronize());
+    const size_t V = (size_t)b->V;
+    const cudaMemcpyKind kind = mem == MXB_MEM_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+    const double* src = nullptr;
+    if (id >= 0 && id < MXB_P_COUNT) src = b->dp[id];
+    else if (id == MXB_S_FILT_0) src = b->f0;
+    else if (id == MXB_S_FILT_1) src = b->f1;
+    else if (id == MXB_S_FILT_2) src = b->f2;
+    else if (id == MXB_S_ENV_AMPLITUDE) src = b->env_amp;
+    else if (id == MXB_S_ENV_OUTPUT) src = b->env_output;
+    if (src) { MXB_CUDA(cudaMemcpy(values, src, sizeof(double) * V, kind)); return MXB_OK; }
+    // integer state, returned as doubles
+    std::vector<double> h(V, 0.0);
+    if (id == MXB_S_ENV_HOLDCOUNT) {
+        std::vector<long long> t(V);
+        MXB_CUDA(cudaMemcpy(t.data(), b->env_holdcount, sizeof(long long) * V, cudaMemcpyDeviceToHost));
+        for (size_t v = 0; v < V; ++v) h[v] = (double)t[v];
+    } else if (id == MXB_S_ENV_FLAGS || id == MXB_S_DELAY_PHASE) {
+        const int* s = id == MXB_S_ENV_FLAGS ? b->env_flags : b->dl_phase;
+        if (s) {
+            std::vector<int> t(V);
+            MXB_CUDA(cudaMemcpy(t.data(), s, sizeof(int) * V, cudaMemcpyDeviceToHost));
+            for (size_t v = 0; v < V; ++v) h[v] = (double)t[v];
+        }
+    } else {
+        set_error("mxb_bank_get_state: unknown id %d", id);
+        return MXB_ERR_INVALID;
+    }
+    MXB_CUDA(cudaMemcpy(values, h.data(), sizeof(double) * V, mem == MXB_MEM_HOST ? cudaMemcpyHostToHost : cudaMemcpyHostToDevice));
+    return MXB_OK;
+}
+
+int32_t mxb_bank_get_ring(mxb_bank* b, int32_t voice, double* dst, int32_t n, int32_t mem) {
+    MXB_REQUIRE(b && dst, MXB_ERR_INVALID, "mxb_bank_get_ring: NULL argument");
+    MXB_REQUIRE(b->ring, MXB_ERR_STATE, "mxb_bank_get_ring: bank has no delay line");
+    MXB_REQUIRE(voice >= 0 && voice < b->V && n >= 0 && n <= b->desc.delay_taps, MXB_ERR_INVALID, "mxb_bank_get_ring: voice %d n %d", voice, n);
+    DeviceGuard g(b->ctx->device);
+    MXB_CUDA(cudaDeviceSynchronize());
+    // de-interleave the chunked ring (delay_kernels.cuh): chunk c of this voice is 32 slots at (c*V + voice)*32
+    const cudaMemcpyKind kind = mem == MXB_MEM_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+    const size_t cb = sizeof(double) * kDlChunk;
+    const int full = n / kDlChunk, rem = n % kDlChunk;
+    const double* src = b->ring + (size_t)voice * kDlChunk;
+    if (full) MXB_CUDA(cudaMemcpy2D(dst, cb, src, cb * (size_t)b->V, cb, (size_t)full, kind));
+    if (rem) MXB_CUDA(cudaMemcpy(dst + (size_t)full * kDlChunk, src + (size_t)full * kDlChunk * (size_t)b->V, sizeof(double) * (size_t)rem, kind));
+    return MXB_OK;
+}
+
+int32_t mxb_bank_process(mxb_bank* b, int32_t n_frames, const int32_t* trig_on, const int32_t* trig_off,
+                         void* out, int32_t out_dtype, double* mix, int32_t mem, void* stream_) {
+    MXB_REQUIRE(b, MXB_ERR_INVALID, "mxb_bank_process: NULL bank");
+    MXB_REQUIRE(n_frames >= 0 && n_frames <= b->desc.max_frames, MXB_ERR_INVALID, "mxb_bank_process: n_frames %d (max_frames %d)", n_frames, b->desc.max_frames);
+    MXB_REQUIRE(mem == MXB_MEM_HOST || mem == MXB_MEM_DEVICE || mem == MXB_MEM_SPLIT, MXB_ERR_INVALID, "mxb_bank_process: mem %d", mem);
+    const bool host_ctl = mem != MXB_MEM_DEVICE;      // gates and mix in host memory
+    const bool host_out = mem == MXB_MEM_HOST;        // out in host memory
+    MXB_REQUIRE(out_dtype == MXB_F64 || out_dtype == MXB_F32, MXB_ERR_INVALID, "mxb_bank_process: out_dtype %d", out_dtype);
+    MXB_REQUIRE((trig_on == nullptr) == (trig_off == nullptr), MXB_ERR_INVALID, "mxb_bank_process: trig_on/trig_off must both be given or both NULL");
+    MXB_REQUIRE(out || mix, MXB_ERR_INVALID, "mxb_bank_process: neither out nor mix requested");
+    const int fk = b->desc.filt_kind;
+    if (fk == MXB_FILT_LORES || fk == MXB_FILT_HIRES)
+        MXB_REQUIRE(b->set_mask[MXB_P_CUTOFF] && b->set_mask[MXB_P_RESONANCE], MXB_ERR_STATE,
+                    "mxb_bank_process: lores/hires need MXB_P_CUTOFF and MXB_P_RESONANCE (they are call arguments in the reference)");
+    if (n_frames == 0) return MXB_OK;
+    DeviceGuard g(b->ctx->device);
+    cudaStream_t s = (cudaStream_t)stream_;
+    const size_t V = (size_t)b->V;
+    const size_t esz = out_dtype == MXB_F32 ? 4 : 8;
+
+    const int* d_on = trig_on; const int* d_off = trig_off;
+    void* d_out = out; double* d_mix = mix;
+    if (host_ctl) {
+        if (trig_on) {
+            MXB_CUDA(cudaMemcpyAsync(b->trig_on, trig_on, sizeof(int) * V, cudaMemcpyHostToDevice, s));
+            MXB_CUDA(cudaMemcpyAsync(b->trig_off, trig_off, sizeof(int) * V, cudaMemcpyHostToDevice, s));
+            d_on = b->trig_on; d_off = b->trig_off;
+        }
+        if (out && host_out) {
+            const size_t need = (size_t)n_frames * V * esz;
+            if (need > b->out_stage_bytes) {
+                MXB_CUDA(cudaStreamSynchronize(s));
+                cudaFree(b->out_stage); b->out_stage = nullptr; b->out_stage_bytes = 0;
+                cudaError_t e = cudaMalloc(&b->out_stage, need);
+                if (e != cudaSuccess) { set_error("mxb_bank_process: staging cudaMalloc(%zu): %s", need, cudaGetErrorString(e)); return MXB_ERR_ALLOC; }
+                b->out_stage_bytes = need;
+            }
+            d_out = b->out_stage;
+        }
+        if (mix) d_mix = b->mix_dev;
+    }
+
+    const int per_cta = kBankBlock * kBankVPT;
+    const int grid = (int)((V + per_cta - 1) / per_cta);
+    const int W = b->desc.delay_taps > 0 ? delay_bank_warps(b->V) : grid * (kBankBlock / 32);
+    if (mix) {
+        const size_t need = (size_t)b->desc.max_frames * 2 * (size_t)W;
+        if (need > b->partials_len) {
+            MXB_CUDA(cudaStreamSynchronize(s));
+            cudaFree(b->partials); b->partials = nullptr; b->partials_len = 0;
+            int rc = dev_alloc(&b->partials, need, false);
+            if (rc != MXB_OK) return rc;
+            b->partials_len = need;
+        }
+    }
+
+    BankArgs a;
+    memset(&a, 0, sizeof(a));
+    a.V = b->V; a.n_frames = n_frames; a.osc_kind = b->desc.osc_kind;
+    a.out_f32 = out_dtype == MXB_F32;
+    a.vec_ok = (V % kBankVPT == 0) && d_out && (((uintptr_t)d_out) % (esz * kBankVPT) == 0);
+    a.W = W;
+    a.sr = (double)(size_t)b->ctx->sample_rate;
+    for (int i = 0; i < 4; ++i) a.svf_mix[i] = b->desc.svf_mix[i];
+    a.freq = b->dp[MXB_P_FREQ]; a.duty = b->dp[MXB_P_DUTY]; a.phase = b->dp[MXB_P_PHASE]; a.osc_out = b->osc_out;
+    a.f0 = b->f0; a.f1 = b->f1; a.f2 = b->f2;
+    for (int i = 0; i < 5; ++i) a.cf[i] = b->cf[i];
+    a.env_att = b->dp[MXB_P_ENV_ATTACK]; a.env_dec = b->dp[MXB_P_ENV_DECAY];
+    a.env_sus = b->dp[MXB_P_ENV_SUSTAIN]; a.env_rel = b->dp[MXB_P_ENV_RELEASE];
+    a.env_hold = b->env_hold; a.env_amp = b->env_amp; a.env_output = b->env_output;
+    a.env_holdcount = b->env_holdcount; a.env_flags = b->env_flags;
+    a.trig_on = d_on; a.trig_off = d_off;
+    a.out = d_out; a.pan = b->dp[MXB_P_PAN]; a.partials = b->partials;
+
+    int osc_t = OSC_T_GENERIC;
+    if (b->desc.osc_kind == MXB_OSC_SINEWAVE) osc_t = OSC_T_SINE;
+    else if (b->desc.osc_kind == MXB_OSC_PHASOR) osc_t = OSC_T_PHASOR;
+    else if (b->desc.osc_kind == MXB_OSC_SAW) osc_t = OSC_T_SAW;
+    const int env = b->desc.env_kind == MXB_ENV_ADSR ? 1 : 0;
+    const bool svf_lp = fk == MXB_FILT_SVF && b->desc.svf_mix[0] == 1.0 && b->desc.svf_mix[1] == 0.0 &&
+                        b->desc.svf_mix[2] == 0.0 && b->desc.svf_mix[3] == 0.0;
+
+    int rc;
+    if (b->desc.delay_taps > 0) {
+        DelayArgs da;
+        da.phase = b->dl_phase; da.size = b->dl_size; da.feedback = b->dp[MXB_P_DELAY_FEEDBACK];
+        da.ring = b->ring; da.taps = b->desc.delay_taps; da.W_out = 0;
+        rc = launch_delay_bank(a, da, fk, svf_lp, env, out != nullptr, mix != nullptr, s);
+        if (rc != MXB_OK) return rc;
+    } else {
+        bank_launch_fn fn = launch_bank_none;
+        switch (fk) {
+            case MXB_FILT_LORES: fn = launch_bank_lores; break;
+            case MXB_FILT_HIRES: fn = launch_bank_hires; break;
+            case MXB_FILT_SVF: fn = svf_lp ? launch_bank_svf_lp : launch_bank_svf; break;
+            case MXB_FILT_BIQUAD: fn = launch_bank_biquad; break;
+            default: break;
+        }
+        const size_t smem = mix ? sizeof(double) * (kBankBlock / 32) * 2 * kMixTT * 33 : 0;
+        rc = fn(a, osc_t, env, out != nullptr, mix != nullptr, grid, smem, s);
+        if (rc != MXB_OK) return rc;
+    }
+    b->launches += 1;
+    if (mix) {
+        const int rows = n_frames * 2;
+        const int threads = 256, blocks = (rows * 32 + threads - 1) / threads;
+        mix_reduce_kernel<<<blocks, threads, 0, s>>>(b->partials, d_mix, rows, a.W);
+        MXB_CUDA(cudaGetLastError());
+        b->launches += 1;
+    }
+    if (host_ctl) {
+        if (out && host_out) MXB_CUDA(cudaMemcpyAsync(out, d_out, (size_t)n_frames * V * esz, cudaMemcpyDeviceToHost, s));
+        if (mix) MXB_CUDA(cudaMemcpyAsync(mix, d_mix, sizeof(double) * (size_t)n_frames * 2, cudaMemcpyDeviceToHost, s));
+        MXB_CUDA(cudaStreamSynchronize(s));
+    }
+    return MXB_OK;
+}
+
+}  // extern "C"

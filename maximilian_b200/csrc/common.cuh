@@ -1,0 +1,66 @@
+// Internal definitions shared by the translation units of libmaxib200.so (not installed).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include <string.h>
+#include <stdlib.h>
+#include <vector>
+
+#include "../../include/maxib200.h"
+
+namespace mxb {
+
+void set_error(const char* fmt, ...);
+
+#define MXB_CUDA(expr)                                                                         \
+    do {                                                                                       \
+        cudaError_t _e = (expr);                                                               \
+        if (_e != cudaSuccess) {                                                               \
+            mxb::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+            return MXB_ERR_CUDA;                                                               \
+        }                                                                                      \
+    } while (0)
+
+#define MXB_REQUIRE(cond, code, ...)        \
+    do {                                    \
+        if (!(cond)) {                      \
+            mxb::set_error(__VA_ARGS__);    \
+            return (code);                  \
+        }                                   \
+    } while (0)
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
+        if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+        if (prev == dev) prev = -1;
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+template <class T>
+inline int dev_alloc(T** p, size_t n, bool zero = true) {
+    void* q = nullptr;
+    cudaError_t e = cudaMalloc(&q, sizeof(T) * (n ? n : 1));
+    if (e != cudaSuccess) { set_error("cudaMalloc(%zu bytes): %s", sizeof(T) * n, cudaGetErrorString(e)); return MXB_ERR_ALLOC; }
+    if (zero) {
+        e = cudaMemset(q, 0, sizeof(T) * (n ? n : 1));
+        if (e != cudaSuccess) { set_error("cudaMemset: %s", cudaGetErrorString(e)); cudaFree(q); return MXB_ERR_CUDA; }
+    }
+    *p = (T*)q;
+    return MXB_OK;
+}
+
+}  // namespace mxb
+
+struct mxb_ctx {
+    int device;
+    int sample_rate;
+    int sm_count;
+    int cc_major, cc_minor;
+};

@@ -1,0 +1,34 @@
+// K2 interface: bank kernel with a maxiDelayline stage (see delay.cu).
+#pragma once
+
+#include "bank_kernels.cuh"
+
+namespace mxb {
+
+constexpr int kDlChunk = 32;     // ring slots per chunk = time steps per staged window
+
+// Ring storage is chunk-interleaved: slot r of voice v lives at ((r / 32) * V + v) * 32 + r % 32.
+// A voice's 32-slot chunk is 256 contiguous bytes (full sectors whatever its phase), and voices whose
+// ring indices run in step -- the common case: same size, started together -- read and write one
+// contiguous run of 32 * 256 B per warp and stage, i.e. streaming DRAM access.
+__host__ __device__ inline size_t dl_slot(size_t V, size_t v, int r) {
+    return (((size_t)(r >> 5)) * V + v) * kDlChunk + (size_t)(r & 31);
+}
+inline size_t dl_ring_doubles(size_t V, int taps) { return (size_t)((taps + kDlChunk - 1) / kDlChunk) * kDlChunk * V; }
+
+struct DelayArgs {
+    int* phase;              // maxiDelayline::phase per voice
+    const int* size;         // dl() size argument per voice
+    const double* feedback;
+    double* ring;
+    int taps;
+    int W_out;               // [out] warps in the launched grid (mix partials stride)
+};
+
+// warps the K2 grid will have for V voices (the caller sizes the mix partials with it)
+int delay_bank_warps(int V);
+
+int launch_delay_bank(const BankArgs& a, DelayArgs& d, int filt_kind, bool svf_lp, int env, bool out, bool mix,
+                      cudaStream_t s);
+
+}  // namespace mxb

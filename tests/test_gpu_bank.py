@@ -1,0 +1,229 @@
+"""GPU parity of the voice-bank kernels (K1 osc/env/filter, K2 delay line, K3 mix), through the C ABI
+(host buffers in, host buffers out) against the plain-C oracle and the committed golden vectors.
+
+Bars (SURVEY.md 8c / north_star):
+  * integer state (delay ring index, envelope flags/holdcount): exact
+  * fp64 sample values: within 1e-5 relative (north_star). What we actually assert is stronger: chains
+    without sin/cos are BIT-IDENTICAL to the reference (no FMA contraction, host-designed coefficients);
+    sinewave/coswave differ only by libdevice-vs-glibc sin (<= 2 ulp), asserted at 1e-12 absolute.
+  * stereo mix: sum over voices in a different (fixed) order: 1e-9 relative.
+"""
+import itertools
+
+import numpy as np
+import pytest
+
+import golden_checks as G
+from maximilian_b200 import capi
+from maximilian_b200 import workloads as W
+
+pytestmark = pytest.mark.gpu
+
+OSCS = ["sinewave", "coswave", "phasor", "saw", "square", "pulse", "impulse", "triangle"]
+FILTS = ["none", "lores", "hires", "svf", "biquad"]
+TRIG = {"sinewave", "coswave"}
+
+
+def gpu_bank(V, **kw):
+    return capi.Bank(V, **kw)
+
+
+def _close(got, ref, trig, what=""):
+    if trig:
+        assert np.array_equal(np.isnan(got), np.isnan(ref)), what
+        np.testing.assert_allclose(got, ref, rtol=1e-9, atol=1e-12, err_msg=what)
+    else:
+        assert np.array_equal(got, ref, equal_nan=True), f"{what}: not bit-identical, max abs err {np.nanmax(np.abs(got - ref))}"
+
+
+@pytest.mark.parametrize("case", G.chain_cases(), ids=lambda c: c[0])
+def test_golden_chains(case):
+    trig = case[1] in TRIG
+    G.run_chain_case(gpu_bank, case, exact=not trig, exact_mix=False)
+
+
+@pytest.mark.parametrize("osc,filt", list(itertools.product(OSCS, FILTS)))
+def test_every_osc_filter_pair_vs_oracle(port, osc, filt):
+    V, B = 333, 129
+    p = W.voice_params(V, seed=21)
+    g = gpu_bank(V, osc=osc, filt=filt, max_frames=B); o = port.Bank(V, osc=osc, filt=filt)
+    W.configure_bank(g, filt, p); W.configure_bank(o, filt, p)
+    for blk in range(3):
+        og, mg = g.process(B, want_mix=True); oo, mo = o.process(B, want_mix=True)
+        _close(og, oo, osc in TRIG, f"{osc}->{filt} blk{blk}")
+        np.testing.assert_allclose(mg, mo, rtol=1e-9, atol=1e-11)
+    for s in ("phase", "filt0", "filt1", "filt2"):
+        _close(g.get(s), o.get(s), osc in TRIG, s)
+
+
+@pytest.mark.parametrize("V", [1, 2, 33, 4096, 4097])
+@pytest.mark.parametrize("B", [1, 17, 512, 1024])
+def test_shapes_saw_svf(port, V, B):
+    p = W.voice_params(V, seed=V + B)
+    g = gpu_bank(V, osc="saw", filt="svf", max_frames=B); o = port.Bank(V, osc="saw", filt="svf")
+    W.configure_bank(g, "svf", p); W.configure_bank(o, "svf", p)
+    for blk in range(2):
+        og, _ = g.process(B); oo, _ = o.process(B)
+        _close(og, oo, False, f"V{V} B{B} blk{blk}")
+
+
+def test_config1_plumbing_one_voice_sine_lores(port):
+    # BASELINE.json configs[0]: 1 voice sinewave -> lores, 48 kHz, 512-sample blocks
+    g = gpu_bank(1, osc="sinewave", filt="lores", max_frames=512); o = port.Bank(1, osc="sinewave", filt="lores")
+    for b in (g, o):
+        b.set("freq", 440.0); b.set("cutoff", 1000.0); b.set("resonance", 2.0)
+    for blk in range(8):
+        og, _ = g.process(512); oo, _ = o.process(512)
+        np.testing.assert_allclose(og, oo, rtol=1e-9, atol=1e-12)
+
+
+@pytest.mark.parametrize("btype", ["lowpass", "highpass", "bandpass", "notch", "peak", "lowshelf", "highshelf"])
+def test_biquad_types(port, btype):
+    V, B = 64, 256
+    p = W.voice_params(V, seed=5)
+    p["gain"] = np.linspace(-12, 12, V)
+    g = gpu_bank(V, osc="saw", filt="biquad", biquad_type=btype, max_frames=B); o = port.Bank(V, osc="saw", filt="biquad", biquad_type=btype)
+    W.configure_bank(g, "biquad", p); W.configure_bank(o, "biquad", p)
+    og, _ = g.process(B); oo, _ = o.process(B)
+    _close(og, oo, False, btype)
+
+
+@pytest.mark.parametrize("mix", [(1, 0, 0, 0), (0, 1, 0, 0), (0, 0, 1, 0), (0, 0, 0, 1), (0.3, 0.2, 0.4, 0.1)])
+def test_svf_mix_weights(port, mix):
+    V, B = 64, 256
+    mix = tuple(float(m) for m in mix)
+    p = W.voice_params(V, seed=6); p["res_svf"][0] = 0.0
+    g = gpu_bank(V, osc="saw", filt="svf", svf_mix=mix, max_frames=B); o = port.Bank(V, osc="saw", filt="svf", svf_mix=mix)
+    W.configure_bank(g, "svf", p); W.configure_bank(o, "svf", p)
+    og, _ = g.process(B); oo, _ = o.process(B)
+    _close(og, oo, False, str(mix))
+
+
+def test_lores_clamps_and_nan(port):
+    V, B = 6, 64
+    p = W.voice_params(V, seed=2)
+    p["cutoff"] = np.array([1.0, 9.999, 10.0, 47999.0, 48000.0, 96000.0])
+    p["q_lores"] = np.array([0.0, 0.5, 1.0, 1.5, 2.0, 3.0])
+    for filt in ("lores", "hires"):
+        g = gpu_bank(V, osc="saw", filt=filt, max_frames=B); o = port.Bank(V, osc="saw", filt=filt)
+        W.configure_bank(g, filt, p); W.configure_bank(o, filt, p)
+        og, _ = g.process(B); oo, _ = o.process(B)
+        _close(og, oo, False, filt)
+        assert np.isnan(og[-1, 4])
+
+
+def test_lores_without_parameters_is_an_error():
+    g = gpu_bank(4, osc="saw", filt="lores", max_frames=8)
+    with pytest.raises(capi.MxbError):
+        g.process(8)
+
+
+@pytest.mark.parametrize("filt", ["none", "lores", "biquad"])
+def test_envelope_state_machine(port, filt):
+    V, B = 256, 512
+    p = W.voice_params(V, seed=9)
+    p["env_holdtime"] = np.array([1, 1, 0, 5, 100, 1000, 1, 3] * (V // 8), dtype=np.float64)
+    g = gpu_bank(V, osc="saw", filt=filt, env=True, max_frames=B); o = port.Bank(V, osc="saw", filt=filt, env=True)
+    W.configure_bank(g, filt, p, env=True); W.configure_bank(o, filt, p, env=True)
+    for blk in range(8):
+        on, off = W.gate(V, B, blk)
+        if blk == 5:
+            on[:] = 0; off[:] = B
+        og, _ = g.process(B, on, off); oo, _ = o.process(B, on, off)
+        _close(og, oo, False, f"env blk{blk}")
+        for s in ("env_holdcount", "env_flags"):
+            assert np.array_equal(g.get(s), o.get(s)), (blk, s)           # integer state: exact
+        for s in ("env_amplitude", "env_output"):
+            _close(g.get(s), o.get(s), False, s)
+
+
+@pytest.mark.parametrize("ragged", [False, True])
+@pytest.mark.parametrize("B", [1024, 700, 37])
+def test_delayline_index_exact(port, ragged, B):
+    V, cap = 200, 512
+    p = W.voice_params(V, seed=4, delay_size=cap, ragged_delay=ragged)
+    if ragged:
+        p["delay_size"][:8] = [1, 2, 3, 63, 64, 65, 96, cap]      # literal path below 64 slots, staged path from 64
+    g = gpu_bank(V, osc="saw", env=True, delay=True, delay_capacity=cap, max_frames=B)
+    o = port.Bank(V, osc="saw", env=True, delay=True, delay_capacity=cap)
+    W.configure_bank(g, "none", p, env=True, delay=True); W.configure_bank(o, "none", p, env=True, delay=True)
+    for blk in range(4):
+        on, off = W.gate(V, B, blk)
+        if blk == 2:       # ring shrinks between blocks: `phase >= size -> 0` on the next access
+            p["delay_size"] = np.maximum(1, p["delay_size"] // 2)
+            g.set("delay_size", p["delay_size"]); o.set("delay_size", p["delay_size"])
+        og, mg = g.process(B, on, off, want_mix=True); oo, mo = o.process(B, on, off, want_mix=True)
+        _close(og, oo, False, f"delay blk{blk}")
+        np.testing.assert_allclose(mg, mo, rtol=1e-9, atol=1e-11)
+        assert np.array_equal(g.get("delay_phase"), o.get("delay_phase")), blk     # int ring index: exact
+    for v in range(0, V, 17):
+        assert np.array_equal(g.ring(v, cap), o.ring(v, cap)), v
+
+
+def test_delay_with_filter_and_nonpositive_size(port):
+    V, B, cap = 40, 130, 128
+    p = W.voice_params(V, seed=8, delay_size=cap, ragged_delay=True)
+    p["delay_size"][:3] = [0.0, -3.0, 1.0]
+    g = gpu_bank(V, osc="triangle", filt="svf", delay=True, delay_capacity=cap, max_frames=B)
+    o = port.Bank(V, osc="triangle", filt="svf", delay=True, delay_capacity=cap)
+    W.configure_bank(g, "svf", p, delay=True); W.configure_bank(o, "svf", p, delay=True)
+    for blk in range(3):
+        og, _ = g.process(B); oo, _ = o.process(B)
+        _close(og, oo, False, f"blk{blk}")
+        assert np.array_equal(g.get("delay_phase"), o.get("delay_phase"))
+
+
+def test_delay_size_above_capacity_rejected():
+    g = gpu_bank(4, osc="saw", delay=True, delay_capacity=64, max_frames=8)
+    with pytest.raises(capi.MxbError):
+        g.set("delay_size", 65.0)
+
+
+def test_fp32_output_storage(port):
+    V, B = 512, 256
+    p = W.voice_params(V, seed=12)
+    g = gpu_bank(V, osc="saw", filt="biquad", max_frames=B); o = port.Bank(V, osc="saw", filt="biquad")
+    W.configure_bank(g, "biquad", p); W.configure_bank(o, "biquad", p)
+    og, _ = g.process(B, out_dtype=np.float32); oo, _ = o.process(B)
+    assert og.dtype == np.float32
+    assert np.array_equal(og, oo.astype(np.float32))          # state stays fp64; only the stored sample is rounded
+
+
+def test_mix_only_and_determinism(port):
+    V, B = 5000, 256
+    p = W.voice_params(V, seed=13)
+    runs = []
+    for _ in range(2):
+        g = gpu_bank(V, osc="saw", filt="biquad", max_frames=B)
+        W.configure_bank(g, "biquad", p)
+        _, m = g.process(B, want_out=False, want_mix=True)
+        runs.append(m)
+    assert np.array_equal(runs[0], runs[1])                     # fixed summation order
+    o = port.Bank(V, osc="saw", filt="biquad"); W.configure_bank(o, "biquad", p)
+    _, mo = o.process(B, want_out=False, want_mix=True)
+    np.testing.assert_allclose(runs[0], mo, rtol=1e-9, atol=1e-10)
+
+
+def test_full_size_properties_1m_voices():
+    """BASELINE.json configs[1] at full size (1M voices, saw -> SVF, 1024-frame block): too big for the CPU
+    oracle in seconds, so check size-independent properties: (a) voices are independent -- the first 4096
+    voices of the big bank equal a 4096-voice bank bit for bit; (b) the stereo mix equals the pan-weighted
+    sum of the materialised output (fp64 reassociation only); (c) a second identical run is bit-identical."""
+    V, B, S = 1 << 20, 1024, 4096
+    p = W.voice_params(V, seed=W.SEED)
+    big = gpu_bank(V, osc="saw", filt="svf", max_frames=B)
+    W.configure_bank(big, "svf", p)
+    out = np.empty((B, V), dtype=np.float32)          # fp32 storage keeps the host buffer at 4 GiB
+    _, mix = big.process(B, want_mix=True, out_dtype=np.float32, out=out)
+    small = gpu_bank(S, osc="saw", filt="svf", max_frames=B)
+    W.configure_bank(small, "svf", {k: v[:S] for k, v in p.items()})
+    os_, _ = small.process(B, out_dtype=np.float32)
+    assert np.array_equal(out[:, :S], os_)
+    pan = np.clip(p["pan"], 0, 1)
+    for t in (0, 1, 511, 1023):
+        row = out[t].astype(np.float64)
+        np.testing.assert_allclose(mix[t], [np.dot(row, np.sqrt(1 - pan)), np.dot(row, np.sqrt(pan))], rtol=1e-5, atol=1e-3)
+    big2 = gpu_bank(V, osc="saw", filt="svf", max_frames=B)
+    W.configure_bank(big2, "svf", p)
+    _, mix2 = big2.process(B, want_out=False, want_mix=True)
+    assert np.array_equal(mix, mix2)
