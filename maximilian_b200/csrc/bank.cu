@@ -381,7 +381,8 @@ int32_t mxb_bank_process(mxb_bank* b, int32_t n_frames, const int32_t* trig_on, 
 
     const int per_cta = kBankBlock * kBankVPT;
     const int grid = (int)((V + per_cta - 1) / per_cta);
-    const int W = b->desc.delay_taps > 0 ? delay_bank_warps(b->V) : grid * (kBankBlock / 32);
+    // warps that own at least one voice (warps past the end of the bank exit without writing partials)
+    const int W = b->desc.delay_taps > 0 ? delay_bank_warps(b->V) : (int)((V + 32 * kBankVPT - 1) / (32 * kBankVPT));
     if (mix) {
         const size_t need = (size_t)b->desc.max_frames * 2 * (size_t)W;
         if (need > b->partials_len) {

@@ -212,12 +212,12 @@ int launch_filt(const BankArgs& a, const DelayArgs& d, int osc_saw, int env, boo
 
 }  // namespace
 
-int delay_bank_warps(int V) { return ((V + kBankBlock - 1) / kBankBlock) * (kBankBlock / 32); }
+int delay_bank_warps(int V) { return (V + 31) / 32; }   // warps that own at least one voice
 
 int launch_delay_bank(const BankArgs& a_in, DelayArgs& d, int filt_kind, bool svf_lp, int env, bool out, bool mix, cudaStream_t s) {
     BankArgs a = a_in;
     const int grid = (a.V + kBankBlock - 1) / kBankBlock;
-    a.W = grid * (kBankBlock / 32);
+    a.W = delay_bank_warps(a.V);
     d.W_out = a.W;
     const int saw = a.osc_kind == MXB_OSC_SAW;
     switch (filt_kind) {

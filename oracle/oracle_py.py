@@ -143,9 +143,12 @@ class Bank:
             raise RuntimeError(f"mxo_bank_get_ring -> {rc}")
         return a
 
-    def process(self, nframes, trig_on=None, trig_off=None, want_out=True, want_mix=False, threads=1):
-        """Returns (out[nframes][V] or None, mix[nframes][2] or None)."""
-        out = np.empty((nframes, self.V), dtype=np.float64) if want_out else None
+    def process(self, nframes, trig_on=None, trig_off=None, want_out=True, want_mix=False, threads=1, out=None):
+        """Returns (out[nframes][V] or None, mix[nframes][2] or None). `out` may be a preallocated buffer."""
+        if want_out and out is None:
+            out = np.empty((nframes, self.V), dtype=np.float64)
+        if not want_out:
+            out = None
         ton = np.ascontiguousarray(trig_on, dtype=np.int32) if trig_on is not None else None
         toff = np.ascontiguousarray(trig_off, dtype=np.int32) if trig_off is not None else None
         threads = max(1, min(int(threads), self.V))
