@@ -350,8 +350,11 @@ def cpu_mfcc_run(channels, hops, threads, kind):
     from maximilian_b200 import workloads as W
     from oracle import oracle_py as O
     wl = MFCC_WL
+    threads = max(1, min(threads, channels // 8))      # at least 8 channels per host thread
     bounds = np.linspace(0, channels, threads + 1).astype(int)
-    x = W.channel_streams(channels, wl["hop"], seed=5)
+    # 16 hops per library call: the time goes to the reference's C++ loops, not to Python call overhead
+    calls, per_call = max(1, hops // 16), 16
+    x = W.channel_streams(channels, per_call * wl["hop"], seed=5)
     objs = []
     for i in range(threads):
         c = int(bounds[i + 1] - bounds[i])
@@ -376,7 +379,8 @@ def cpu_mfcc_run(channels, hops, threads, kind):
         [t.join() for t in ts]
         return time.perf_counter() - t0
     run(1)
-    return run(hops)
+    dt = run(calls)
+    return dt * hops / (calls * per_call)      # seconds per `hops` hops
 
 
 def main_mfcc(args):

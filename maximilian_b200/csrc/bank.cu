@@ -270,7 +270,11 @@ int32_t mxb_bank_set_param(mxb_bank* b, int32_t id, const double* values, int32_
         if (rc != MXB_OK) return rc;
     } else if (id == MXB_P_ENV_HOLDTIME) {
         std::vector<long long> h(V);
-        for (size_t v = 0; v < V; ++v) h[v] = (long long)b->hp[id][v];
+        for (size_t v = 0; v < V; ++v) {
+            // the kernels count holdcount/holdtime in 32-bit registers (holdcount never passes holdtime)
+            MXB_REQUIRE(fabs(b->hp[id][v]) < 2147483648.0, MXB_ERR_INVALID, "mxb_bank_set_param: holdtime %.0f of voice %zu does not fit 32 bits", b->hp[id][v], v);
+            h[v] = (long long)b->hp[id][v];
+        }
         MXB_CUDA(cudaMemcpy(b->env_hold, h.data(), sizeof(long long) * V, cudaMemcpyHostToDevice));
     } else if (id == MXB_P_DELAY_SIZE && b->dl_size) {
         std::vector<int> h(V);
