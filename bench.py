@@ -130,12 +130,10 @@ def run_cpu_blocks(bank, wl, voices, threads, nblocks, block_index0=0):
     from maximilian_b200 import workloads as W
     if voices not in _cpu_out:          # one output block, allocated and touched once (no page faults in the timed loop)
         _cpu_out[voices] = np.zeros((BLOCK, voices), dtype=np.float64)
+    from oracle import oracle_py as O
+    gates = [(W.gate(voices, BLOCK, block_index0 + k) if wl["env"] else (None, None)) for k in range(nblocks)]
     t0 = time.perf_counter()
-    for k in range(nblocks):
-        on = off = None
-        if wl["env"]:
-            on, off = W.gate(voices, BLOCK, block_index0 + k)
-        bank.process(BLOCK, on, off, want_out=True, want_mix=False, threads=threads, out=_cpu_out[voices])
+    O.run_blocks_threaded(bank, BLOCK, gates, threads, _cpu_out[voices])
     return time.perf_counter() - t0
 
 
@@ -146,9 +144,9 @@ def cpu_baseline(wl, budget_s=4.0):
     bank = cpu_bank(wl, voices, kind)
     run_cpu_blocks(bank, wl, voices, cores, 1)                      # warm-up block
     n, total = 0, 0.0
-    while total < budget_s and n < 64:
-        total += run_cpu_blocks(bank, wl, voices, cores, 1, 1 + n)
-        n += 1
+    while total < budget_s and n < 128:
+        total += run_cpu_blocks(bank, wl, voices, cores, 8, 1 + n)     # 8 blocks per thread start
+        n += 8
     v = voices * BLOCK * n / total
     return {"value": v, "unit": "samples/s", "cores": cores, "kind": kind,
             "sample": f"{voices} voices x {BLOCK} frames x {n} blocks of the same chain, voices partitioned over {cores} host threads"}
@@ -286,7 +284,7 @@ def main():
     e2e_steps = max(3, min(args.steps, 50))
 
     def e2e_step():
-        bank.set_host_array("freq", fh)                                   # H2D: this block's control data
+        bank.set_host_array("freq", fh, stream=stream.cuda_stream)        # H2D: this block's control data (stream-ordered)
         bank.process_split(BLOCK, out.data_ptr(), mh, on_h, off_h, f32=args.f32_out, stream=stream.cuda_stream)   # D2H: mix bus
         if world > 1:
             m = mix_host.to(dev, non_blocking=True)

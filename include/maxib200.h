@@ -149,6 +149,11 @@ int32_t mxb_bank_voices(const mxb_bank* bank);
  * src/maximilian.h:1322-1334, maxiBiquad::set src/maximilian.h:1375-1479): block-constant
  * parameters hoist out of the per-sample loop exactly. */
 int32_t mxb_bank_set_param(mxb_bank* bank, int32_t id, const double* values, int32_t mem);
+/* Stream-ordered variant for block-rate control data (a new frequency / pan / feedback array every block): one
+ * asynchronous copy on `stream`, no synchronisation; host memory should be page-locked. Parameters that need a
+ * host pass (cutoff / resonance / gain: coefficient design; holdtime / delay size: integer conversion) fall back
+ * to mxb_bank_set_param. The reference passes these values by argument on every sample. */
+int32_t mxb_bank_set_param_async(mxb_bank* bank, int32_t id, const double* values, int32_t mem, void* stream);
 int32_t mxb_bank_get_state(mxb_bank* bank, int32_t id, double* values, int32_t mem);
 /* ring slots [0, n) of voice v (debug / checkpoint) */
 int32_t mxb_bank_get_ring(mxb_bank* bank, int32_t voice, double* dst, int32_t n, int32_t mem);

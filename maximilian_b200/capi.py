@@ -24,7 +24,7 @@ P = dict(freq=0, phase=1, duty=2, cutoff=3, resonance=4, gain=5, env_attack=6, e
 EXPORTS = [
     "mxb_last_error", "mxb_version", "mxb_ctx_create", "mxb_ctx_destroy", "mxb_ctx_sample_rate",
     "mxb_ctx_synchronize", "mxb_host_alloc", "mxb_host_free",
-    "mxb_bank_create", "mxb_bank_destroy", "mxb_bank_voices", "mxb_bank_set_param", "mxb_bank_get_state",
+    "mxb_bank_create", "mxb_bank_destroy", "mxb_bank_voices", "mxb_bank_set_param", "mxb_bank_set_param_async", "mxb_bank_get_state",
     "mxb_bank_get_ring", "mxb_bank_process", "mxb_bank_launch_count", "mxb_env_coeffs",
     "mxb_stft_create", "mxb_stft_destroy", "mxb_stft_process", "mxb_stft_launch_count",
     "mxb_mfcc_create", "mxb_mfcc_destroy", "mxb_mfcc_process",
@@ -69,6 +69,7 @@ def lib():
         "mxb_bank_destroy": (i32, [vp]),
         "mxb_bank_voices": (i32, [vp]),
         "mxb_bank_set_param": (i32, [vp, i32, vp, i32]),
+        "mxb_bank_set_param_async": (i32, [vp, i32, vp, i32, vp]),
         "mxb_bank_get_state": (i32, [vp, i32, vp, i32]),
         "mxb_bank_get_ring": (i32, [vp, i32, vp, i32, i32]),
         "mxb_bank_process": (i32, [vp, i32, vp, vp, vp, i32, vp, i32, vp]),
@@ -217,9 +218,15 @@ class Bank:
                                      F32 if f32 else F64, _np_ptr(mix), 2, C.c_void_p(int(stream)) if stream else None),
               "mxb_bank_process")
 
-    def set_host_array(self, name, a):
-        """set() without the broadcast/convert step: `a` must be a contiguous float64 array of V values."""
-        check(lib().mxb_bank_set_param(self.h, P[name], C.c_void_p(a.ctypes.data), MEM_HOST), f"mxb_bank_set_param({name})")
+    def set_host_array(self, name, a, stream=None):
+        """set() without the broadcast/convert step: `a` must be a contiguous float64 array of V values.
+        With `stream` (a raw cudaStream_t value; 0 = default stream) the copy is stream-ordered and asynchronous
+        (mxb_bank_set_param_async; `a` should live in pinned memory)."""
+        if stream is None:
+            check(lib().mxb_bank_set_param(self.h, P[name], C.c_void_p(a.ctypes.data), MEM_HOST), f"mxb_bank_set_param({name})")
+        else:
+            check(lib().mxb_bank_set_param_async(self.h, P[name], C.c_void_p(a.ctypes.data), MEM_HOST,
+                                                 C.c_void_p(int(stream)) if stream else None), f"mxb_bank_set_param_async({name})")
 
 
 def env_coeffs(kind, ms, sample_rate=48000):

@@ -289,6 +289,21 @@ int32_t mxb_bank_set_param(mxb_bank* b, int32_t id, const double* values, int32_
     return MXB_OK;
 }
 
+int32_t mxb_bank_set_param_async(mxb_bank* b, int32_t id, const double* values, int32_t mem, void* stream_) {
+    MXB_REQUIRE(b && values, MXB_ERR_INVALID, "mxb_bank_set_param_async: NULL argument");
+    MXB_REQUIRE(id >= 0 && id < MXB_P_COUNT, MXB_ERR_INVALID, "mxb_bank_set_param_async: unknown id %d", id);
+    MXB_REQUIRE(mem == MXB_MEM_HOST || mem == MXB_MEM_DEVICE, MXB_ERR_INVALID, "mxb_bank_set_param_async: mem %d", mem);
+    const bool needs_host_pass = id == MXB_P_CUTOFF || id == MXB_P_RESONANCE || id == MXB_P_GAIN ||
+                                 id == MXB_P_ENV_HOLDTIME || id == MXB_P_DELAY_SIZE;
+    if (needs_host_pass) return mxb_bank_set_param(b, id, values, mem);      // coefficient design / integer conversion on the host
+    DeviceGuard g(b->ctx->device);
+    // plain per-voice values used as they are by the kernels: one stream-ordered copy, nothing else
+    MXB_CUDA(cudaMemcpyAsync(b->dp[id], values, sizeof(double) * (size_t)b->V,
+                             mem == MXB_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, (cudaStream_t)stream_));
+    b->set_mask[id] = true;
+    return MXB_OK;
+}
+
 int32_t mxb_bank_get_state(mxb_bank* b, int32_t id, double* values, int32_t mem) {
     MXB_REQUIRE(b && values, MXB_ERR_INVALID, "mxb_bank_get_state: NULL argument");
     MXB_REQUIRE(mem == MXB_MEM_HOST || mem == MXB_MEM_DEVICE, MXB_ERR_INVALID, "mxb_bank_get_state: mem %d", mem);

@@ -1,300 +1,7 @@
-// K2: oscillator -> [ADSR] -> [filter] -> maxiDelayline::dl -> out / stereo mix.
-//
-// maxiDelayline::dl (src/maximilian.cpp:420-429) reads ring[phase] and writes it back every sample:
-// 8 B read + 8 B write of ring traffic per voice-sample on top of the 8 B output -- the one genuinely
-// HBM-bound stage of the path. A thread walking its own ring straight out of global memory would issue
-// one 8-byte load per sample with 32 different lines per warp request; instead each WARP stages the next
-// 32 ring slots of each of its 32 voices through shared memory:
-//
-//   stage k+1:  32 cp.async requests, one per voice, lane = slot: 256 contiguous bytes each,
-//               issued before stage k is computed (double buffer, warp-private)
-//   stage k:    lane = voice; 32 steps of the chain, ring slot j of the window read and updated in smem
-//               (row stride 33 doubles: conflict-free for 64-bit accesses)
-//   write-back: the window returns to the ring the way it came, lane = slot, 256 B per request
-//
-// Two schedules share the per-step code:
-//   * uniform: every voice of the warp has the same ring size (a multiple of 32) and the same, chunk-aligned
-//     index -- voices started together, the common case. With the chunk-interleaved ring layout
-//     (delay_kernels.cuh) the warp's 32 windows are ONE contiguous 8 KB run: address arithmetic collapses to
-//     pointer increments and DRAM sees pure streaming.
-//   * generic: any per-voice size / phase (ragged banks, rings that shrank between blocks): each window is
-//     located per voice (wrap at `size`, chunk crossing), still 256 B per request. Voices whose ring is
-//     shorter than two windows (64 slots; a window would meet its own write-back) take the literal
-//     per-sample path against global memory.
-//
-// The ring index `phase` is an int and follows the reference statement for statement --
-// `if (phase >= size) phase = 0` BEFORE the access -- so index sequences are bit-exact.
+// K2 dispatcher: picks the instantiation (delay_k_*.cu) for a bank with a maxiDelayline stage.
 #include "delay_kernels.cuh"
 
 namespace mxb {
-
-namespace {
-
-constexpr int kStageDoubles = 32 * 33;            // one staged window tile per warp
-// Window buffers per warp. 1: load -> compute -> write back, latency hidden by the other warps of the SM (24 warps
-// fit); 2: the next window is in flight while this one is computed, but only 12 warps fit. Measured on B200
-// (profiles/): with 12 warps the issue slots starve on fixed-latency dependencies, so 1 wins.
-constexpr int kDlStages = 1;
-constexpr int kMixDoubles = 2 * kMixTT * 33;
-constexpr int kFastMinSize = 2 * kDlChunk;
-constexpr unsigned kFull = 0xffffffffu;
-
-__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc) {
-    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait1() { asm volatile("cp.async.wait_group 1;\n" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait0() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
-
-struct DlVoice {
-    double phase, oout, inc, duty, fb, gl, gr;
-    FiltRegs fr;
-    EnvRegs er;
-    int ph, size;
-    bool live, fast;
-};
-
-// 32 (or fewer) steps of one voice against its staged window `row` (ALLFAST) or, for short rings, against global memory
-template <int OSC, int FILT, int ENV, bool ALLFAST>
-__device__ __forceinline__ void dl_stage(DlVoice& s, double* row, const int tn, const int t0, const BankArgs& a, const DelayArgs& d,
-                                         const size_t V, const size_t v, const int lane, const int gwarp, double* mixtile,
-                                         const int do_out, const int do_mix) {
-    double* out64 = (double*)a.out + (size_t)t0 * V + v;
-    float* out32 = (float*)a.out + (size_t)t0 * V + v;
-    for (int h0 = 0; h0 < tn; h0 += kMixTT) {
-        const int hn = min(kMixTT, tn - h0);
-#pragma unroll 4
-        for (int jj = 0; jj < hn; ++jj) {
-            const int j = h0 + jj;
-            const int t = t0 + j;
-            double x = osc_tick<OSC>(s.phase, s.oout, s.inc, s.duty, a.osc_kind);
-            if (ENV) x = env_tick(s.er, x, t >= s.er.on && t < s.er.off);
-            x = filt_tick<FILT>(s.fr, x, a.svf_mix);
-            // maxiDelayline::dl, src/maximilian.cpp:420-429
-            double y = 0.0;
-            if (ALLFAST ? s.live : s.fast) {          // lanes past the end of the bank contribute an exact 0
-                const double m = row[j];
-                row[j] = (m * s.fb) + (x * s.fb) * 0.5;
-                y = m;
-            } else if (!ALLFAST && s.live) {
-                if (s.ph >= s.size) s.ph = 0;
-                const int idx = min(max(s.ph, 0), d.taps - 1);     // size <= taps is enforced when the parameter is set
-                double* slot = d.ring + dl_slot(V, v, idx);
-                const double m = *slot;
-                *slot = (m * s.fb) + (x * s.fb) * 0.5;
-                s.ph += 1;
-                y = m;
-            }
-            if (do_out) {
-                if (s.live) { if (a.out_f32) __stcs(out32, (float)y); else __stcs(out64, y); }
-                out64 += V; out32 += V;
-            }
-            if (do_mix) {
-                mixtile[(0 * kMixTT + jj) * 33 + lane] = y * s.gl;
-                mixtile[(1 * kMixTT + jj) * 33 + lane] = y * s.gr;
-            }
-        }
-        if (do_mix) {
-            __syncwarp();
-            const int ch = lane >> 4, rw = lane & 15;
-            if (rw < hn) {
-                const double* r = mixtile + (ch * kMixTT + rw) * 33;
-                double acc = 0.0;
-#pragma unroll
-                for (int q = 0; q < 32; ++q) acc += r[q];
-                a.partials[((size_t)(t0 + h0 + rw) * 2 + ch) * (size_t)a.W + (size_t)gwarp] = acc;
-            }
-            __syncwarp();
-        }
-    }
-}
-
-template <int OSC, int FILT, int ENV>
-__global__ void __launch_bounds__(kBankBlock) delay_bank_kernel(const BankArgs a, const DelayArgs d, const int do_out, const int do_mix) {
-    const int lane = threadIdx.x & 31;
-    const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const long long v0 = (long long)gwarp * 32;
-    if (v0 >= a.V) return;
-    const long long v = v0 + lane;
-    const size_t V = (size_t)a.V;
-
-    extern __shared__ double smem[];
-    const int per_warp = kDlStages * kStageDoubles + (do_mix ? kMixDoubles : 0);
-    double* wsm = smem + (size_t)(threadIdx.x >> 5) * per_warp;
-    double* mixtile = wsm + kDlStages * kStageDoubles;
-
-    // ---- per-voice state (lane = voice) ----
-    DlVoice s;
-    s.live = v < a.V;
-    const long long vv = s.live ? v : 0;
-    s.phase = a.phase[vv]; s.oout = a.osc_out[vv];
-    s.duty = (OSC == OSC_T_GENERIC) ? a.duty[vv] : 0.0;
-    s.inc = (1. / (a.sr / (a.freq[vv])));
-    if (FILT != FILT_T_NONE) {
-        s.fr.s0 = a.f0[vv]; s.fr.s1 = a.f1[vv]; s.fr.s2 = (FILT == FILT_T_SVF || FILT == FILT_T_SVF_LP) ? a.f2[vv] : 0.0;
-        s.fr.c0 = a.cf[0][vv]; s.fr.c1 = a.cf[1][vv];
-        if (FILT != FILT_T_LORES && FILT != FILT_T_HIRES) { s.fr.c2 = a.cf[2][vv]; s.fr.c3 = a.cf[3][vv]; s.fr.c4 = a.cf[4][vv]; }
-    }
-    if (ENV) {
-        s.er.amp = a.env_amp[vv]; s.er.output = a.env_output[vv];
-        s.er.att = a.env_att[vv]; s.er.dec = a.env_dec[vv]; s.er.sus = a.env_sus[vv]; s.er.rel = a.env_rel[vv];
-        s.er.holdcount = (int)a.env_holdcount[vv]; s.er.holdtime = (int)a.env_hold[vv]; env_unpack(s.er, a.env_flags[vv]);
-        s.er.on = a.trig_on ? a.trig_on[vv] : 0; s.er.off = a.trig_off ? a.trig_off[vv] : 0;
-    }
-    s.gl = s.gr = 0.0;
-    if (do_mix) {
-        double x = a.pan[vv];
-        if (x > 1) x = 1;
-        if (x < 0) x = 0;
-        s.gl = s.live ? sqrt(1.0 - x) : 0.0;
-        s.gr = s.live ? sqrt(x) : 0.0;
-    }
-    s.ph = d.phase[vv];
-    s.size = d.size[vv];
-    s.fb = d.feedback[vv];
-    s.fast = s.live && s.size >= kFastMinSize;
-    // ring index of the first access of the next window: the reference tests `phase >= size` before it reads
-    int base = (s.ph >= s.size) ? 0 : s.ph;
-
-    const int nstages = (a.n_frames + kDlChunk - 1) / kDlChunk;
-    const int size0 = __shfl_sync(kFull, s.size, 0), base0 = __shfl_sync(kFull, base, 0);     // lane 0 is always live
-    const bool uniform = __all_sync(kFull, !s.live || (s.fast && s.size == size0 && base == base0)) &&
-                         (size0 & 31) == 0 && (base0 & 31) == 0;
-    const int nlive = __popc(__ballot_sync(kFull, s.live));
-
-    if (uniform) {
-        // ---------------- all windows of the warp form one contiguous run of nlive * 256 B ----------------
-        const int nchunks = size0 >> 5;
-        int chunk = base0 >> 5;
-        auto run = [&](int c) { return d.ring + ((size_t)c * V + (size_t)v0) * kDlChunk + lane; };
-        auto load_run = [&](double* buf, int c) {
-            const double* src = run(c);
-            double* dst = buf + lane;
-#pragma unroll 8
-            for (int i = 0; i < nlive; ++i) cp_async8(dst + i * 33, src + i * kDlChunk);
-        };
-        if (kDlStages == 2) { load_run(wsm, chunk); cp_async_commit(); }
-        for (int k = 0; k < nstages; ++k) {
-            double* buf = wsm + (kDlStages == 2 ? (k & 1) * kStageDoubles : 0);
-            const int t0 = k * kDlChunk;
-            const int tn = min(kDlChunk, a.n_frames - t0);
-            int next_chunk = chunk + 1;
-            if (next_chunk >= nchunks) next_chunk = 0;
-            if (kDlStages == 2) {
-                if (k + 1 < nstages) load_run(wsm + ((k + 1) & 1) * kStageDoubles, next_chunk);
-                cp_async_commit();
-                cp_async_wait1();      // everything but the newest group has landed: stage k is in smem
-            } else {
-                load_run(buf, chunk);
-                cp_async_commit();
-                cp_async_wait0();
-            }
-            __syncwarp();
-            dl_stage<OSC, FILT, ENV, true>(s, buf + lane * 33, tn, t0, a, d, V, (size_t)vv, lane, gwarp, mixtile, do_out, do_mix);
-            __syncwarp();
-            if (lane < tn) {
-                double* dstg = d.ring + ((size_t)chunk * V + (size_t)v0) * kDlChunk + lane;
-                const double* srcs = buf + lane;
-#pragma unroll 8
-                for (int i = 0; i < nlive; ++i) dstg[i * kDlChunk] = srcs[i * 33];
-            }
-            __syncwarp();
-            chunk = next_chunk;
-        }
-        // phase += 1 after the last access: the window of the last stage started at slot 32*last_chunk
-        if (s.live) {
-            int last_chunk = (base0 >> 5) + (nstages - 1);
-            last_chunk %= nchunks;
-            const int tn_last = a.n_frames - (nstages - 1) * kDlChunk;
-            s.ph = last_chunk * kDlChunk + tn_last;
-        }
-    } else {
-        // ---------------- generic: per-voice size and phase ----------------
-        auto issue_loads = [&](double* buf, int wbase) {
-#pragma unroll 4
-            for (int i = 0; i < 32; ++i) {
-                const int f_i = __shfl_sync(kFull, (int)s.fast, i);
-                if (!f_i) continue;
-                const int b_i = __shfl_sync(kFull, wbase, i);
-                const int s_i = __shfl_sync(kFull, s.size, i);
-                int r = b_i + lane;
-                if (r >= s_i) r -= s_i;
-                cp_async8(buf + i * 33 + lane, d.ring + dl_slot(V, (size_t)(v0 + i), r));
-            }
-        };
-        if (kDlStages == 2) { issue_loads(wsm, base); cp_async_commit(); }
-        for (int k = 0; k < nstages; ++k) {
-            double* buf = wsm + (kDlStages == 2 ? (k & 1) * kStageDoubles : 0);
-            const int t0 = k * kDlChunk;
-            const int tn = min(kDlChunk, a.n_frames - t0);
-            int next_base = base + kDlChunk;
-            if (s.fast && next_base >= s.size) next_base -= s.size;
-            if (kDlStages == 2) {
-                if (k + 1 < nstages) issue_loads(wsm + ((k + 1) & 1) * kStageDoubles, next_base);
-                cp_async_commit();
-                cp_async_wait1();
-            } else {
-                issue_loads(buf, base);
-                cp_async_commit();
-                cp_async_wait0();
-            }
-            __syncwarp();
-            dl_stage<OSC, FILT, ENV, false>(s, buf + lane * 33, tn, t0, a, d, V, (size_t)vv, lane, gwarp, mixtile, do_out, do_mix);
-            __syncwarp();
-#pragma unroll 4
-            for (int i = 0; i < 32; ++i) {
-                const int f_i = __shfl_sync(kFull, (int)s.fast, i);
-                if (!f_i) continue;
-                const int b_i = __shfl_sync(kFull, base, i);
-                const int s_i = __shfl_sync(kFull, s.size, i);
-                if (lane < tn) {
-                    int r = b_i + lane;
-                    if (r >= s_i) r -= s_i;
-                    d.ring[dl_slot(V, (size_t)(v0 + i), r)] = buf[i * 33 + lane];
-                }
-            }
-            __syncwarp();
-            if (s.fast) {
-                int last = base + tn - 1;
-                if (last >= s.size) last -= s.size;
-                s.ph = last + 1;                     // phase += 1 after the last access of the window
-                base = (tn == kDlChunk) ? next_base : ((s.ph >= s.size) ? 0 : s.ph);
-            }
-        }
-    }
-
-    if (s.live) {
-        a.phase[v] = s.phase;
-        if (OSC == OSC_T_GENERIC) a.osc_out[v] = s.oout;
-        if (FILT != FILT_T_NONE) {
-            a.f0[v] = s.fr.s0; a.f1[v] = s.fr.s1;
-            if (FILT == FILT_T_SVF || FILT == FILT_T_SVF_LP) a.f2[v] = s.fr.s2;
-        }
-        if (ENV) { a.env_amp[v] = s.er.amp; a.env_output[v] = s.er.output; a.env_holdcount[v] = s.er.holdcount; a.env_flags[v] = env_pack(s.er); }
-        d.phase[v] = s.ph;
-    }
-}
-
-template <int OSC, int FILT, int ENV>
-int launch_one(const BankArgs& a, const DelayArgs& d, bool out, bool mix, int grid, cudaStream_t s) {
-    const size_t smem = sizeof(double) * (kBankBlock / 32) * (kDlStages * kStageDoubles + (mix ? kMixDoubles : 0));
-    auto kern = delay_bank_kernel<OSC, FILT, ENV>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) { set_error("delay_bank_kernel smem attribute (%zu B): %s", smem, cudaGetErrorString(e)); return MXB_ERR_CUDA; }
-    kern<<<grid, kBankBlock, smem, s>>>(a, d, out ? 1 : 0, mix ? 1 : 0);
-    e = cudaGetLastError();
-    if (e != cudaSuccess) { set_error("delay_bank_kernel launch: %s", cudaGetErrorString(e)); return MXB_ERR_CUDA; }
-    return MXB_OK;
-}
-
-template <int FILT>
-int launch_filt(const BankArgs& a, const DelayArgs& d, int osc_saw, int env, bool out, bool mix, int grid, cudaStream_t s) {
-    if (osc_saw) return env ? launch_one<OSC_T_SAW, FILT, 1>(a, d, out, mix, grid, s) : launch_one<OSC_T_SAW, FILT, 0>(a, d, out, mix, grid, s);
-    return env ? launch_one<OSC_T_GENERIC, FILT, 1>(a, d, out, mix, grid, s) : launch_one<OSC_T_GENERIC, FILT, 0>(a, d, out, mix, grid, s);
-}
-
-}  // namespace
 
 int delay_bank_warps(int V) { return (V + 31) / 32; }   // warps that own at least one voice
 
@@ -304,13 +11,14 @@ int launch_delay_bank(const BankArgs& a_in, DelayArgs& d, int filt_kind, bool sv
     a.W = delay_bank_warps(a.V);
     d.W_out = a.W;
     const int saw = a.osc_kind == MXB_OSC_SAW;
+    const int outmode = !out ? 0 : (a.out_f32 ? 2 : 1);      // DL_OUT_NONE / F64 / F32
     switch (filt_kind) {
-        case MXB_FILT_NONE:   return launch_filt<FILT_T_NONE>(a, d, saw, env, out, mix, grid, s);
-        case MXB_FILT_LORES:  return launch_filt<FILT_T_LORES>(a, d, saw, env, out, mix, grid, s);
-        case MXB_FILT_HIRES:  return launch_filt<FILT_T_HIRES>(a, d, saw, env, out, mix, grid, s);
-        case MXB_FILT_SVF:    return svf_lp ? launch_filt<FILT_T_SVF_LP>(a, d, saw, env, out, mix, grid, s)
-                                            : launch_filt<FILT_T_SVF>(a, d, saw, env, out, mix, grid, s);
-        case MXB_FILT_BIQUAD: return launch_filt<FILT_T_BIQUAD>(a, d, saw, env, out, mix, grid, s);
+        case MXB_FILT_NONE:   return launch_delay_none(a, d, saw, env, outmode, mix, grid, s);
+        case MXB_FILT_LORES:  return launch_delay_lores(a, d, saw, env, outmode, mix, grid, s);
+        case MXB_FILT_HIRES:  return launch_delay_hires(a, d, saw, env, outmode, mix, grid, s);
+        case MXB_FILT_SVF:    return svf_lp ? launch_delay_svf_lp(a, d, saw, env, outmode, mix, grid, s)
+                                            : launch_delay_svf(a, d, saw, env, outmode, mix, grid, s);
+        case MXB_FILT_BIQUAD: return launch_delay_biquad(a, d, saw, env, outmode, mix, grid, s);
         default: break;
     }
     set_error("launch_delay_bank: filt_kind %d", filt_kind);

@@ -31,4 +31,12 @@ int delay_bank_warps(int V);
 int launch_delay_bank(const BankArgs& a, DelayArgs& d, int filt_kind, bool svf_lp, int env, bool out, bool mix,
                       cudaStream_t s);
 
+// one launcher per filter family (delay_k_*.cu); outmode 0 none / 1 fp64 / 2 fp32
+int launch_delay_none(const BankArgs& a, const DelayArgs& d, int osc_saw, int env, int outmode, bool mix, int grid, cudaStream_t s);
+int launch_delay_lores(const BankArgs& a, const DelayArgs& d, int osc_saw, int env, int outmode, bool mix, int grid, cudaStream_t s);
+int launch_delay_hires(const BankArgs& a, const DelayArgs& d, int osc_saw, int env, int outmode, bool mix, int grid, cudaStream_t s);
+int launch_delay_svf(const BankArgs& a, const DelayArgs& d, int osc_saw, int env, int outmode, bool mix, int grid, cudaStream_t s);
+int launch_delay_svf_lp(const BankArgs& a, const DelayArgs& d, int osc_saw, int env, int outmode, bool mix, int grid, cudaStream_t s);
+int launch_delay_biquad(const BankArgs& a, const DelayArgs& d, int osc_saw, int env, int outmode, bool mix, int grid, cudaStream_t s);
+
 }  // namespace mxb

@@ -179,6 +179,29 @@ class Bank:
         return out, mix
 
 
+def run_blocks_threaded(bank, nframes, gates, threads, out):
+    """CPU-baseline driver: `len(gates)` consecutive blocks, voices statically partitioned over `threads` host
+    threads; every thread runs ALL blocks of its own voices (voices are independent, so no barrier between
+    blocks) -- one thread start per run, the time goes to the reference's per-sample loops.
+    gates: list of (trig_on, trig_off) int32 arrays or (None, None); out: [nframes][V] float64, reused."""
+    threads = max(1, min(int(threads), bank.V))
+    bounds = np.linspace(0, bank.V, threads + 1).astype(int)
+    rcs = [0] * threads
+
+    def work(i):
+        lo, n = int(bounds[i]), int(bounds[i + 1] - bounds[i])
+        for on, off in gates:
+            rc = bank.lib.mxo_bank_process(bank.h, nframes, _ip(on), _ip(off), _dp(out), None, lo, n)
+            if rc:
+                rcs[i] = rc
+                return
+    ts = [threading.Thread(target=work, args=(i,)) for i in range(threads)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    if any(rcs):
+        raise RuntimeError(f"mxo_bank_process -> {rcs}")
+
+
 class Stft:
     def __init__(self, channels, fft_size=1024, hop=512, kind="port"):
         self.lib = load(kind)
