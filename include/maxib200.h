@@ -70,7 +70,18 @@ enum {
 };
 /* maxiBiquad::filterTypes, src/maximilian.h:1348-1357 */
 enum { MXB_BQ_LOWPASS = 0, MXB_BQ_HIGHPASS, MXB_BQ_BANDPASS, MXB_BQ_NOTCH, MXB_BQ_PEAK, MXB_BQ_LOWSHELF, MXB_BQ_HIGHSHELF };
-enum { MXB_ENV_NONE = 0, MXB_ENV_ADSR = 1 /* maxiEnv::adsr(input, trigger) src/maximilian.cpp:1415-1466 */ };
+enum {
+    MXB_ENV_NONE = 0,
+    MXB_ENV_ADSR = 1,   /* maxiEnv::adsr(input, trigger) src/maximilian.cpp:1415-1466; the overload with explicit
+                           attack/decay/sustain/release/holdtime arguments (:1362-1413) is the same computation on
+                           its arguments, i.e. on the per-voice arrays below */
+    MXB_ENV_AR = 2      /* maxiEnv::ar(input, attack, release, holdtime, trigger) src/maximilian.cpp:1319-1358 */
+};
+/* delay_mode of mxb_bank_desc */
+enum {
+    MXB_DELAY_DL = 0,            /* maxiDelayline::dl              src/maximilian.cpp:420-429 */
+    MXB_DELAY_FROM_POSITION = 1  /* maxiDelayline::dlFromPosition  src/maximilian.cpp:431-439 */
+};
 
 /* per-voice parameter / state arrays: double[voices] */
 enum {
@@ -88,7 +99,8 @@ enum {
     MXB_P_DELAY_SIZE = 11,    /* maxiDelayline::dl size argument (integral value) */
     MXB_P_DELAY_FEEDBACK = 12,/* maxiDelayline::dl feedback argument */
     MXB_P_PAN = 13,           /* maxiMix::stereo x (src/maximilian.cpp:503-509) */
-    MXB_P_COUNT = 14,
+    MXB_P_DELAY_POSITION = 14,/* maxiDelayline::dlFromPosition position argument (integral value) */
+    MXB_P_COUNT = 15,
     /* read-only state (mxb_bank_get_state) */
     MXB_S_FILT_0 = 32,        /* lores/hires x | svf v0z | biquad v[1] */
     MXB_S_FILT_1 = 33,        /* lores/hires y | svf v1  | biquad v[2] */
@@ -137,7 +149,7 @@ typedef struct {
     int32_t env_kind;        /* MXB_ENV_* */
     int32_t delay_taps;      /* 0 = no delay line; else ring slots per voice (reference: 705600 fixed, src/maximilian.h:273) */
     int32_t max_frames;      /* largest n_frames a process call will use (maxiSettings::bufferSize) */
-    int32_t reserved;
+    int32_t delay_mode;      /* MXB_DELAY_* (delay_taps > 0) */
     double  svf_mix[4];      /* lpmix, bpmix, hpmix, notchmix arguments of maxiSVF::play */
 } mxb_bank_desc;
 

@@ -257,6 +257,14 @@ public:
         v_->desc_.env_kind = MXB_ENV_ADSR; v_->gate_ = trigger;
         return maxiSignal{v_, 2};
     }
+    /* maxiEnv::ar(input, attack, release, holdtime, trigger): attack/release are the raw per-sample coefficients the
+     * reference takes as arguments (defaults 1, 0.9, holdtime 1) */
+    maxiSignal ar(maxiSignal input, const maxiParam& attack, const maxiParam& release, const maxiParam& holdtime, const maxiGate& trigger) {
+        if (input.voices != v_ || input.stage != 1) throw maxiError(MXB_ERR_UNSUPPORTED, "maxiEnv::ar: input must be the oscillator of the same maxiVoices");
+        v_->desc_.env_kind = MXB_ENV_AR; v_->gate_ = trigger;
+        v_->setParam(MXB_P_ENV_ATTACK, attack); v_->setParam(MXB_P_ENV_RELEASE, release); v_->setParam(MXB_P_ENV_HOLDTIME, holdtime);
+        return maxiSignal{v_, 2};
+    }
 private:
     void coeff(int id, int kind, const maxiParam& ms) {
         std::vector<double> in = ms.isScalar() ? std::vector<double>(1, ms.scalar()) : ms.vec();
@@ -275,8 +283,14 @@ public:
     maxiDelayline(maxiVoices& v, int capacity) : v_(&v), capacity_(capacity) {}
     maxiSignal dl(maxiSignal input, const maxiParam& size, const maxiParam& feedback) {
         if (input.voices != v_ || input.stage < 1 || input.stage > 3) throw maxiError(MXB_ERR_UNSUPPORTED, "maxiDelayline::dl: input must come from the same maxiVoices");
-        v_->desc_.delay_taps = capacity_;
+        v_->desc_.delay_taps = capacity_; v_->desc_.delay_mode = MXB_DELAY_DL;
         v_->setParam(MXB_P_DELAY_SIZE, size); v_->setParam(MXB_P_DELAY_FEEDBACK, feedback);
+        return maxiSignal{v_, 4};
+    }
+    maxiSignal dlFromPosition(maxiSignal input, const maxiParam& size, const maxiParam& feedback, const maxiParam& position) {
+        if (input.voices != v_ || input.stage < 1 || input.stage > 3) throw maxiError(MXB_ERR_UNSUPPORTED, "maxiDelayline::dlFromPosition: input must come from the same maxiVoices");
+        v_->desc_.delay_taps = capacity_; v_->desc_.delay_mode = MXB_DELAY_FROM_POSITION;
+        v_->setParam(MXB_P_DELAY_SIZE, size); v_->setParam(MXB_P_DELAY_FEEDBACK, feedback); v_->setParam(MXB_P_DELAY_POSITION, position);
         return maxiSignal{v_, 4};
     }
 private:

@@ -17,7 +17,7 @@ OSC = dict(sinewave=0, coswave=1, phasor=2, saw=3, square=4, pulse=5, impulse=6,
 FILT = dict(none=0, lores=1, hires=2, svf=3, biquad=4)
 BIQUAD = dict(lowpass=0, highpass=1, bandpass=2, notch=3, peak=4, lowshelf=5, highshelf=6)
 P = dict(freq=0, phase=1, duty=2, cutoff=3, resonance=4, gain=5, env_attack=6, env_decay=7,
-         env_sustain=8, env_release=9, env_holdtime=10, delay_size=11, delay_feedback=12, pan=13,
+         env_sustain=8, env_release=9, env_holdtime=10, delay_size=11, delay_feedback=12, pan=13, delay_position=14,
          filt0=32, filt1=33, filt2=34, env_amplitude=35, env_output=36, env_holdcount=37,
          env_flags=38, delay_phase=39)
 
@@ -39,7 +39,11 @@ class MxbError(RuntimeError):
 class BankDesc(C.Structure):
     _fields_ = [("voices", C.c_int32), ("osc_kind", C.c_int32), ("filt_kind", C.c_int32),
                 ("biquad_type", C.c_int32), ("env_kind", C.c_int32), ("delay_taps", C.c_int32),
-                ("max_frames", C.c_int32), ("reserved", C.c_int32), ("svf_mix", C.c_double * 4)]
+                ("max_frames", C.c_int32), ("delay_mode", C.c_int32), ("svf_mix", C.c_double * 4)]
+
+
+ENV_KIND = {False: 0, None: 0, True: 1, "adsr": 1, "ar": 2}          # maxiEnv::adsr / maxiEnv::ar
+DELAY_MODE = {False: 0, None: 0, True: 0, "dl": 0, "position": 1}    # maxiDelayline::dl / dlFromPosition
 
 
 _lib = None
@@ -149,8 +153,8 @@ class Bank:
             raise MxbError("context sample rate differs from the requested one")
         self.V = int(voices)
         self.max_frames = int(max_frames)
-        d = BankDesc(self.V, OSC[osc], FILT[filt], BIQUAD[biquad_type], 1 if env else 0,
-                     int(delay_capacity) if delay else 0, self.max_frames, 0, (C.c_double * 4)(*svf_mix))
+        d = BankDesc(self.V, OSC[osc], FILT[filt], BIQUAD[biquad_type], ENV_KIND[env],
+                     int(delay_capacity) if delay else 0, self.max_frames, DELAY_MODE[delay], (C.c_double * 4)(*svf_mix))
         self.h = C.c_void_p()
         check(lib().mxb_bank_create(self.ctx.h, C.byref(d), C.byref(self.h)), "mxb_bank_create")
 

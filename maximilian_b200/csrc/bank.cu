@@ -22,7 +22,7 @@ struct mxb_bank {
     long long *env_holdcount, *env_hold;
     int* env_flags;
     int *trig_on, *trig_off;                 // staging for MXB_MEM_HOST gates
-    int *dl_phase, *dl_size;
+    int *dl_phase, *dl_size, *dl_pos;
     double* ring;                            // [V][delay_taps]
     double* partials; size_t partials_len;
     double* mix_dev;                         // [max_frames][2]
@@ -163,7 +163,7 @@ int free_bank(mxb_bank* b) {
     cudaFree(b->osc_out); cudaFree(b->f0); cudaFree(b->f1); cudaFree(b->f2);
     for (int i = 0; i < 5; ++i) cudaFree(b->cf[i]);
     cudaFree(b->env_amp); cudaFree(b->env_output); cudaFree(b->env_holdcount); cudaFree(b->env_hold); cudaFree(b->env_flags);
-    cudaFree(b->trig_on); cudaFree(b->trig_off); cudaFree(b->dl_phase); cudaFree(b->dl_size); cudaFree(b->ring);
+    cudaFree(b->trig_on); cudaFree(b->trig_off); cudaFree(b->dl_phase); cudaFree(b->dl_size); cudaFree(b->dl_pos); cudaFree(b->ring);
     cudaFree(b->partials); cudaFree(b->mix_dev); cudaFree(b->out_stage);
     delete b;
     return MXB_OK;
@@ -186,7 +186,8 @@ int32_t mxb_bank_create(mxb_ctx* ctx, const mxb_bank_desc* d, mxb_bank** out) {
     MXB_REQUIRE(d->osc_kind >= MXB_OSC_SINEWAVE && d->osc_kind <= MXB_OSC_TRIANGLE, MXB_ERR_INVALID, "mxb_bank_create: osc_kind %d", d->osc_kind);
     MXB_REQUIRE(d->filt_kind >= MXB_FILT_NONE && d->filt_kind <= MXB_FILT_BIQUAD, MXB_ERR_INVALID, "mxb_bank_create: filt_kind %d", d->filt_kind);
     MXB_REQUIRE(d->biquad_type >= MXB_BQ_LOWPASS && d->biquad_type <= MXB_BQ_HIGHSHELF, MXB_ERR_INVALID, "mxb_bank_create: biquad_type %d", d->biquad_type);
-    MXB_REQUIRE(d->env_kind == MXB_ENV_NONE || d->env_kind == MXB_ENV_ADSR, MXB_ERR_INVALID, "mxb_bank_create: env_kind %d", d->env_kind);
+    MXB_REQUIRE(d->env_kind == MXB_ENV_NONE || d->env_kind == MXB_ENV_ADSR || d->env_kind == MXB_ENV_AR, MXB_ERR_INVALID, "mxb_bank_create: env_kind %d", d->env_kind);
+    MXB_REQUIRE(d->delay_mode == MXB_DELAY_DL || d->delay_mode == MXB_DELAY_FROM_POSITION, MXB_ERR_INVALID, "mxb_bank_create: delay_mode %d", d->delay_mode);
     MXB_REQUIRE(d->delay_taps >= 0, MXB_ERR_INVALID, "mxb_bank_create: delay_taps %d", d->delay_taps);
     MXB_REQUIRE(d->max_frames > 0, MXB_ERR_INVALID, "mxb_bank_create: max_frames %d", d->max_frames);
     DeviceGuard g(ctx->device);
@@ -198,13 +199,13 @@ int32_t mxb_bank_create(mxb_ctx* ctx, const mxb_bank_desc* d, mxb_bank** out) {
     b->osc_out = b->f0 = b->f1 = b->f2 = nullptr;
     for (auto& c : b->cf) c = nullptr;
     b->env_amp = b->env_output = nullptr; b->env_holdcount = b->env_hold = nullptr; b->env_flags = nullptr;
-    b->trig_on = b->trig_off = b->dl_phase = b->dl_size = nullptr;
+    b->trig_on = b->trig_off = b->dl_phase = b->dl_size = b->dl_pos = nullptr;
     b->ring = b->partials = b->mix_dev = nullptr; b->partials_len = 0;
     b->out_stage = nullptr; b->out_stage_bytes = 0; b->launches = 0;
     const size_t V = (size_t)d->voices;
     int rc = MXB_OK;
 #define TRY(x) do { rc = (x); if (rc != MXB_OK) { free_bank(b); return rc; } } while (0)
-    static const double defaults[MXB_P_COUNT] = {0, 0, 0.5, 1000.0, 1.0, 0, 0, 0, 0, 0, 1.0, 1.0, 0, 0.5};
+    static const double defaults[MXB_P_COUNT] = {0, 0, 0.5, 1000.0, 1.0, 0, 0, 0, 0, 0, 1.0, 1.0, 0, 0.5, 0};
     for (int i = 0; i < MXB_P_COUNT; ++i) {
         TRY(dev_alloc(&b->dp[i], V));
         b->hp[i].assign(V, defaults[i]);
@@ -225,6 +226,7 @@ int32_t mxb_bank_create(mxb_ctx* ctx, const mxb_bank_desc* d, mxb_bank** out) {
     if (d->delay_taps > 0) {
         TRY(dev_alloc(&b->dl_phase, V));
         TRY(dev_alloc(&b->dl_size, V));
+        TRY(dev_alloc(&b->dl_pos, V));
         std::vector<int> one(V, 1);
         cudaError_t e = cudaMemcpy(b->dl_size, one.data(), sizeof(int) * V, cudaMemcpyHostToDevice);
         if (e != cudaSuccess) { set_error("cudaMemcpy: %s", cudaGetErrorString(e)); free_bank(b); return MXB_ERR_CUDA; }
@@ -276,6 +278,14 @@ int32_t mxb_bank_set_param(mxb_bank* b, int32_t id, const double* values, int32_
             h[v] = (long long)b->hp[id][v];
         }
         MXB_CUDA(cudaMemcpy(b->env_hold, h.data(), sizeof(long long) * V, cudaMemcpyHostToDevice));
+    } else if (id == MXB_P_DELAY_POSITION && b->dl_pos) {
+        std::vector<int> h(V);
+        for (size_t v = 0; v < V; ++v) {
+            const double s = b->hp[id][v];
+            MXB_REQUIRE(fabs(s) < 2147483648.0, MXB_ERR_INVALID, "mxb_bank_set_param: delay position %.0f of voice %zu does not fit an int", s, v);
+            h[v] = (int)s;
+        }
+        MXB_CUDA(cudaMemcpy(b->dl_pos, h.data(), sizeof(int) * V, cudaMemcpyHostToDevice));
     } else if (id == MXB_P_DELAY_SIZE && b->dl_size) {
         std::vector<int> h(V);
         for (size_t v = 0; v < V; ++v) {
@@ -294,7 +304,7 @@ int32_t mxb_bank_set_param_async(mxb_bank* b, int32_t id, const double* values, 
     MXB_REQUIRE(id >= 0 && id < MXB_P_COUNT, MXB_ERR_INVALID, "mxb_bank_set_param_async: unknown id %d", id);
     MXB_REQUIRE(mem == MXB_MEM_HOST || mem == MXB_MEM_DEVICE, MXB_ERR_INVALID, "mxb_bank_set_param_async: mem %d", mem);
     const bool needs_host_pass = id == MXB_P_CUTOFF || id == MXB_P_RESONANCE || id == MXB_P_GAIN ||
-                                 id == MXB_P_ENV_HOLDTIME || id == MXB_P_DELAY_SIZE;
+                                 id == MXB_P_ENV_HOLDTIME || id == MXB_P_DELAY_SIZE || id == MXB_P_DELAY_POSITION;
     if (needs_host_pass) return mxb_bank_set_param(b, id, values, mem);      // coefficient design / integer conversion on the host
     DeviceGuard g(b->ctx->device);
     // plain per-voice values used as they are by the kernels: one stream-ordered copy, nothing else
@@ -435,7 +445,8 @@ int32_t mxb_bank_process(mxb_bank* b, int32_t n_frames, const int32_t* trig_on, 
     if (b->desc.osc_kind == MXB_OSC_SINEWAVE) osc_t = OSC_T_SINE;
     else if (b->desc.osc_kind == MXB_OSC_PHASOR) osc_t = OSC_T_PHASOR;
     else if (b->desc.osc_kind == MXB_OSC_SAW) osc_t = OSC_T_SAW;
-    const int env = b->desc.env_kind == MXB_ENV_ADSR ? 1 : 0;
+    const int env = b->desc.env_kind != MXB_ENV_NONE ? 1 : 0;
+    a.env_ar = b->desc.env_kind == MXB_ENV_AR ? 1 : 0;
     const bool svf_lp = fk == MXB_FILT_SVF && b->desc.svf_mix[0] == 1.0 && b->desc.svf_mix[1] == 0.0 &&
                         b->desc.svf_mix[2] == 0.0 && b->desc.svf_mix[3] == 0.0;
 
@@ -444,6 +455,7 @@ int32_t mxb_bank_process(mxb_bank* b, int32_t n_frames, const int32_t* trig_on, 
         DelayArgs da;
         da.phase = b->dl_phase; da.size = b->dl_size; da.feedback = b->dp[MXB_P_DELAY_FEEDBACK];
         da.ring = b->ring; da.taps = b->desc.delay_taps; da.W_out = 0;
+        da.from_position = b->desc.delay_mode == MXB_DELAY_FROM_POSITION ? 1 : 0; da.position = b->dl_pos;
         rc = launch_delay_bank(a, da, fk, svf_lp, env, out != nullptr, mix != nullptr, s);
         if (rc != MXB_OK) return rc;
     } else {

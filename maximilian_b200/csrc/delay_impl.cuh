@@ -50,7 +50,7 @@ struct DlVoice {
     double phase, oout, inc, duty, fb, gl, gr;
     FiltRegs fr;
     EnvRegs er;
-    int ph, size;
+    int ph, size, pos;
     bool live, fast;
 };
 
@@ -67,7 +67,10 @@ __device__ __forceinline__ void dl_stage(DlVoice& s, double* row, const int tn, 
             const int j = h0 + jj;
             const int t = t0 + j;
             double x = osc_tick<OSC>(s.phase, s.oout, s.inc, s.duty, a.osc_kind);
-            if (ENV) x = env_tick(s.er, x, t >= s.er.on && t < s.er.off);
+            if (ENV) {
+                const bool trig = t >= s.er.on && t < s.er.off;
+                x = a.env_ar ? env_ar_tick(s.er, x, trig) : env_tick(s.er, x, trig);
+            }
             x = filt_tick<FILT>(s.fr, x, a.svf_mix);
             // maxiDelayline::dl, src/maximilian.cpp:420-429
             double y = 0.0;
@@ -80,9 +83,18 @@ __device__ __forceinline__ void dl_stage(DlVoice& s, double* row, const int tn, 
                 const int idx = min(max(s.ph, 0), d.taps - 1);     // size <= taps is enforced when the parameter is set
                 double* slot = d.ring + dl_slot(V, v, idx);
                 const double m = *slot;
-                *slot = (m * s.fb) + (x * s.fb) * 0.5;
+                if (d.from_position) {
+                    // maxiDelayline::dlFromPosition, src/maximilian.cpp:431-439: the output comes from `position`, the
+                    // write has chandiv (== 1) where dl() has 0.5
+                    int pos = s.pos;
+                    if (pos >= s.size) pos = 0;
+                    y = d.ring[dl_slot(V, v, min(max(pos, 0), d.taps - 1))];
+                    *slot = (m * s.fb) + (x * s.fb) * 1.0;
+                } else {
+                    *slot = (m * s.fb) + (x * s.fb) * 0.5;
+                    y = m;
+                }
                 s.ph += 1;
-                y = m;
             }
             if (OUTMODE == DL_OUT_F64) { if (s.live) __stcs(out64, y); out64 += V; }
             if (OUTMODE == DL_OUT_F32) { if (s.live) __stcs(out32, (float)y); out32 += V; }
@@ -149,7 +161,8 @@ __global__ void __launch_bounds__(kBankBlock) delay_bank_kernel(const BankArgs a
     s.ph = d.phase[vv];
     s.size = d.size[vv];
     s.fb = d.feedback[vv];
-    s.fast = s.live && s.size >= kFastMinSize;
+    s.pos = d.from_position ? d.position[vv] : 0;
+    s.fast = s.live && s.size >= kFastMinSize && !d.from_position;      // dlFromPosition: literal path
     // ring index of the first access of the next window: the reference tests `phase >= size` before it reads
     int base = (s.ph >= s.size) ? 0 : s.ph;
 

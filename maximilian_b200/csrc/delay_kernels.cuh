@@ -22,6 +22,8 @@ struct DelayArgs {
     const double* feedback;
     double* ring;
     int taps;
+    int from_position;       // 1: maxiDelayline::dlFromPosition
+    const int* position;     // its position argument per voice
     int W_out;               // [out] warps in the launched grid (mix partials stride)
 };
 

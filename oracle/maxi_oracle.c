@@ -149,7 +149,7 @@ void* mxo_bank_create(const mxo_chain* chain, int32_t voices) {
     const size_t V = (size_t)voices;
     b->chain = *chain;
     b->V = voices;
-    for (int i = 0; i <= MXO_P_PAN; ++i) b->p[i] = dalloc(V, 0.0);
+    for (int i = 0; i < MXO_P_COUNT; ++i) b->p[i] = dalloc(V, 0.0);
     for (size_t v = 0; v < V; ++v) {
         b->p[MXO_P_DUTY][v] = 0.5; b->p[MXO_P_DELAY_SIZE][v] = 1.0; b->p[MXO_P_PAN][v] = 0.5;
         b->p[MXO_P_ENV_HOLDTIME][v] = 1.0;          /* src/maximilian.h:913 */
@@ -183,7 +183,7 @@ void mxo_bank_destroy(void* h) {
 
 int32_t mxo_bank_set(void* h, int32_t id, const double* x) {
     bank_t* b = (bank_t*)h;
-    if (!b || !x || id < 0 || id > MXO_P_PAN) return -1;
+    if (!b || !x || id < 0 || id >= MXO_P_COUNT) return -1;
     memcpy(b->p[id], x, sizeof(double) * (size_t)b->V);
     if (id == MXO_P_CUTOFF || id == MXO_P_RESONANCE || id == MXO_P_GAIN) {
         if (b->chain.filt_kind == MXO_FILT_SVF) for (int v = 0; v < b->V; ++v) svf_set_params(b, v);
@@ -205,7 +205,7 @@ int32_t mxo_bank_get(void* h, int32_t id, double* x) {
             case MXO_S_ENV_HOLDCOUNT: x[v] = (double)b->env_holdcount[v]; break;
             case MXO_S_ENV_FLAGS: x[v] = (double)b->env_flags[v]; break;
             case MXO_S_DELAY_PHASE: x[v] = (double)b->dl_phase[v]; break;
-            default: if (id >= 0 && id <= MXO_P_PAN) x[v] = b->p[id][v]; else return -1;
+            default: if (id >= 0 && id < MXO_P_COUNT) x[v] = b->p[id][v]; else return -1;
         }
     }
     return 0;
@@ -312,6 +312,30 @@ static inline double env_adsr(bank_t* b, int v, double input, int trigger) {
     return output;
 }
 
+/* maxiEnv::ar(input, attack, release, holdtime, trigger), src/maximilian.cpp:1319-1358 (the arguments come from the
+ * per-voice attack / release / holdtime arrays) */
+static inline double env_ar(bank_t* b, int v, double input, int trigger) {
+    int fl = b->env_flags[v];
+    int attackphase = fl & 1, decayphase = (fl >> 1) & 1, sustainphase = (fl >> 2) & 1,
+        holdphase = (fl >> 3) & 1, releasephase = (fl >> 4) & 1;
+    double amplitude = b->env_amp[v], output = b->env_output[v];
+    int64_t holdcount = b->env_holdcount[v];
+    const double attack = b->p[MXO_P_ENV_ATTACK][v], release = b->p[MXO_P_ENV_RELEASE][v];
+    const int64_t holdtime = (int64_t)b->p[MXO_P_ENV_HOLDTIME][v];
+
+    if (trigger == 1 && attackphase != 1 && holdphase != 1) { holdcount = 0; releasephase = 0; attackphase = 1; }
+    if (attackphase == 1) { amplitude += (1 * attack); output = input * amplitude; }
+    if (amplitude >= 1) { amplitude = 1; attackphase = 0; holdphase = 1; }
+    if (holdcount < holdtime && holdphase == 1) { output = input; holdcount++; }
+    if (holdcount == holdtime && trigger == 1) { output = input; }
+    if (holdcount == holdtime && trigger != 1) { holdphase = 0; releasephase = 1; }
+    if (releasephase == 1 && amplitude > 0.) { output = input * (amplitude *= release); }
+
+    b->env_flags[v] = attackphase | decayphase << 1 | sustainphase << 2 | holdphase << 3 | releasephase << 4;
+    b->env_amp[v] = amplitude; b->env_output[v] = output; b->env_holdcount[v] = holdcount;
+    return output;
+}
+
 int32_t mxo_bank_process(void* h, int32_t nframes, const int32_t* trig_on, const int32_t* trig_off,
                          double* out, double* mix, int32_t first, int32_t count) {
     bank_t* b = (bank_t*)h;
@@ -326,6 +350,9 @@ int32_t mxo_bank_process(void* h, int32_t nframes, const int32_t* trig_on, const
             if (c->env_kind == MXO_ENV_ADSR) {
                 int trig = (trig_on && trig_off && t >= trig_on[v] && t < trig_off[v]) ? 1 : 0;
                 x = env_adsr(b, v, x, trig);
+            } else if (c->env_kind == MXO_ENV_AR) {
+                int trig = (trig_on && trig_off && t >= trig_on[v] && t < trig_off[v]) ? 1 : 0;
+                x = env_ar(b, v, x, trig);
             }
             switch (c->filt_kind) {
                 case MXO_FILT_LORES:
@@ -385,8 +412,18 @@ int32_t mxo_bank_process(void* h, int32_t nframes, const int32_t* trig_on, const
                 int phase = b->dl_phase[v];
                 if (phase >= size) phase = 0;
                 if (phase < 0 || phase >= c->delay_capacity) return -4;   /* the reference would index out of its 705600 slots */
-                double output = memory[phase];
-                memory[phase] = (memory[phase] * feedback) + (x * feedback) * 0.5;
+                double output;
+                if (c->delay_on == 2) {
+                    /* maxiDelayline::dlFromPosition, src/maximilian.cpp:431-439; chandiv (src/maximilian.cpp:53) is the float 1 */
+                    int position = (int)b->p[MXO_P_DELAY_POSITION][v];
+                    if (position >= size) position = 0;
+                    if (position < 0 || position >= c->delay_capacity) return -4;
+                    output = memory[position];
+                    memory[phase] = (memory[phase] * feedback) + (x * feedback) * 1.0f;
+                } else {
+                    output = memory[phase];
+                    memory[phase] = (memory[phase] * feedback) + (x * feedback) * 0.5;
+                }
                 phase += 1;
                 b->dl_phase[v] = phase;
                 x = output;

@@ -24,9 +24,13 @@ OSC = dict(sinewave=0, coswave=1, phasor=2, saw=3, square=4, pulse=5, impulse=6,
 FILT = dict(none=0, lores=1, hires=2, svf=3, biquad=4)
 BIQUAD = dict(lowpass=0, highpass=1, bandpass=2, notch=3, peak=4, lowshelf=5, highshelf=6)
 P = dict(freq=0, phase=1, duty=2, cutoff=3, resonance=4, gain=5, env_attack=6, env_decay=7,
-         env_sustain=8, env_release=9, env_holdtime=10, delay_size=11, delay_feedback=12, pan=13,
+         env_sustain=8, env_release=9, env_holdtime=10, delay_size=11, delay_feedback=12, pan=13, delay_position=14,
          filt0=32, filt1=33, filt2=34, env_amplitude=35, env_output=36, env_holdcount=37,
          env_flags=38, delay_phase=39)
+
+
+ENV_KIND = {False: 0, None: 0, True: 1, "adsr": 1, "ar": 2}
+DELAY_KIND = {False: 0, None: 0, True: 1, "dl": 1, "position": 2}
 
 
 class Chain(C.Structure):
@@ -106,8 +110,9 @@ class Bank:
                  biquad_type="lowpass", svf_mix=(1.0, 0.0, 0.0, 0.0), delay_capacity=4096, kind="port"):
         self.lib = load(kind)
         self.V = int(voices)
-        ch = Chain(sample_rate, OSC[osc], FILT[filt], BIQUAD[biquad_type], 1 if env else 0,
-                   1 if delay else 0, delay_capacity, 0, (C.c_double * 4)(*svf_mix))
+        # env: False | True/"adsr" | "ar";  delay: False | True/"dl" | "position" (dlFromPosition)
+        ch = Chain(sample_rate, OSC[osc], FILT[filt], BIQUAD[biquad_type], ENV_KIND[env],
+                   DELAY_KIND[delay], delay_capacity, 0, (C.c_double * 4)(*svf_mix))
         self.h = self.lib.mxo_bank_create(C.byref(ch), self.V)
         if not self.h:
             raise RuntimeError("mxo_bank_create failed")

@@ -116,6 +116,10 @@ void* mxo_bank_create(const mxo_chain* chain, int32_t voices) {
     b->p[MXO_P_DELAY_SIZE].assign(voices, 1.0);
     b->p[MXO_P_DELAY_FEEDBACK].assign(voices, 0.0);
     b->p[MXO_P_PAN].assign(voices, 0.5);
+    b->p[MXO_P_DELAY_POSITION].assign(voices, 0.0);
+    b->p[MXO_P_ENV_ATTACK].assign(voices, 0.0);
+    b->p[MXO_P_ENV_RELEASE].assign(voices, 0.0);
+    b->p[MXO_P_ENV_HOLDTIME].assign(voices, 1.0);
     return b;
 }
 
@@ -133,7 +137,7 @@ void mxo_bank_destroy(void* h) {
 
 int32_t mxo_bank_set(void* h, int32_t id, const double* x) {
     RefBank* b = (RefBank*)h;
-    if (!b || !x || id < 0 || id > MXO_P_PAN) return -1;
+    if (!b || !x || id < 0 || id >= MXO_P_COUNT) return -1;
     maxiSettings::setup((size_t)b->chain.sample_rate, 2, 1024);
     b->p[id].assign(x, x + b->V);
     switch (id) {
@@ -172,7 +176,7 @@ int32_t mxo_bank_get(void* h, int32_t id, double* x) {
                 break;
             case MXO_S_DELAY_PHASE: x[v] = b->delays ? (double)b->delays[v]->phase : 0.0; break;
             default:
-                if (id >= 0 && id <= MXO_P_PAN && !b->p[id].empty()) x[v] = b->p[id][v]; else return -1;
+                if (id >= 0 && id < MXO_P_COUNT && !b->p[id].empty()) x[v] = b->p[id][v]; else return -1;
         }
     }
     return 0;
@@ -201,6 +205,9 @@ int32_t mxo_bank_process(void* h, int32_t nframes, const int32_t* trig_on, const
             if (c.env_kind == MXO_ENV_ADSR) {
                 int trig = (trig_on && trig_off && t >= trig_on[v] && t < trig_off[v]) ? 1 : 0;
                 x = r.env.adsr(x, trig);
+            } else if (c.env_kind == MXO_ENV_AR) {
+                int trig = (trig_on && trig_off && t >= trig_on[v] && t < trig_off[v]) ? 1 : 0;
+                x = r.env.ar(x, b->p[MXO_P_ENV_ATTACK][v], b->p[MXO_P_ENV_RELEASE][v], (long)b->p[MXO_P_ENV_HOLDTIME][v], trig);
             }
             switch (c.filt_kind) {
                 case MXO_FILT_LORES: x = r.filt.lores(x, fc[v], q[v]); break;
@@ -209,7 +216,8 @@ int32_t mxo_bank_process(void* h, int32_t nframes, const int32_t* trig_on, const
                 case MXO_FILT_BIQUAD:x = r.bq.play(x); break;
                 default: break;
             }
-            if (c.delay_on) x = b->delays[v]->dl(x, (int)dsize[v], dfb[v]);
+            if (c.delay_on == 1) x = b->delays[v]->dl(x, (int)dsize[v], dfb[v]);
+            else if (c.delay_on == 2) x = b->delays[v]->dlFromPosition(x, (int)dsize[v], dfb[v], (int)b->p[MXO_P_DELAY_POSITION][v]);
             if (out) out[(size_t)t * V + v] = x;
             if (mix) { r.mixer.stereo(x, two, pan[v]); m0 += two[0]; m1 += two[1]; }
         }

@@ -173,6 +173,44 @@ def test_delay_with_filter_and_nonpositive_size(port):
         assert np.array_equal(g.get("delay_phase"), o.get("delay_phase"))
 
 
+def test_env_ar(port):
+    # maxiEnv::ar, src/maximilian.cpp:1319-1358 (output = input in the hold states; clamp test on every call)
+    V, B = 200, 400
+    p = W.voice_params(V, seed=19)
+    att, dec, rel = W.env_coeffs(p)
+    hold = np.array([1, 0, 5, 50, 300, 1, 2, 1000] * (V // 8), dtype=np.float64)
+    g = gpu_bank(V, osc="saw", filt="lores", env="ar", max_frames=B); o = port.Bank(V, osc="saw", filt="lores", env="ar")
+    for k in (g, o):
+        W.configure_bank(k, "lores", p)
+        k.set("env_attack", att); k.set("env_release", rel); k.set("env_holdtime", hold)
+    for blk in range(6):
+        on, off = W.gate(V, B, blk)
+        if blk == 3:
+            on[:] = 0; off[:] = B
+        og, _ = g.process(B, on, off); oo, _ = o.process(B, on, off)
+        _close(og, oo, False, f"ar blk{blk}")
+        for s in ("env_holdcount", "env_flags"):
+            assert np.array_equal(g.get(s), o.get(s)), (blk, s)
+
+
+def test_dl_from_position(port):
+    # maxiDelayline::dlFromPosition, src/maximilian.cpp:431-439
+    V, B, cap = 70, 300, 256
+    p = W.voice_params(V, seed=23, delay_size=cap, ragged_delay=True)
+    pos = np.random.default_rng(1).integers(0, 300, V).astype(np.float64)      # some >= size -> 0
+    g = gpu_bank(V, osc="saw", delay="position", delay_capacity=cap, max_frames=B)
+    o = port.Bank(V, osc="saw", delay="position", delay_capacity=cap)
+    for k in (g, o):
+        W.configure_bank(k, "none", p, False, True)
+        k.set("delay_position", pos)
+    for blk in range(3):
+        og, _ = g.process(B); oo, _ = o.process(B)
+        _close(og, oo, False, f"dlFromPosition blk{blk}")
+        assert np.array_equal(g.get("delay_phase"), o.get("delay_phase"))
+    for v in range(0, V, 9):
+        assert np.array_equal(g.ring(v, cap), o.ring(v, cap)), v
+
+
 def test_delay_size_above_capacity_rejected():
     g = gpu_bank(4, osc="saw", delay=True, delay_capacity=64, max_frames=8)
     with pytest.raises(capi.MxbError):

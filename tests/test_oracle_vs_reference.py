@@ -139,6 +139,43 @@ def test_delayline_indices_and_ring_bit_exact(port, reference):
         assert _same(a.ring(v, cap), b.ring(v, cap)), v
 
 
+def test_env_ar_bit_exact(port, reference):
+    # maxiEnv::ar(input, attack, release, holdtime, trigger), src/maximilian.cpp:1319-1358
+    V, B = 48, 400
+    p = W.voice_params(V, seed=19)
+    att, dec, rel = W.env_coeffs(p)
+    hold = np.array([1, 0, 5, 50, 300, 1, 2, 1000] * (V // 8), dtype=np.float64)
+    a, b = _pair(port, reference, V, osc="saw", filt="lores", env="ar")
+    for k in (a, b):
+        _configure(k, "lores", p)
+        k.set("env_attack", att); k.set("env_release", rel); k.set("env_holdtime", hold)
+    for blk in range(6):
+        on, off = W.gate(V, B, blk)
+        if blk == 3:
+            on[:] = 0; off[:] = B
+        oa, _ = a.process(B, on, off); ob, _ = b.process(B, on, off)
+        assert _same(oa, ob), blk
+        for s in ("env_amplitude", "env_output", "env_holdcount", "env_flags"):
+            assert _same(a.get(s), b.get(s)), (blk, s)
+
+
+def test_dl_from_position_bit_exact(port, reference):
+    # maxiDelayline::dlFromPosition, src/maximilian.cpp:431-439
+    V, B, cap = 10, 300, 256
+    p = W.voice_params(V, seed=23, delay_size=cap, ragged_delay=True)
+    pos = np.array([0, 1, 5, 63, 64, 100, 200, 255, 300, 17], dtype=np.float64)     # 300 >= size -> 0
+    a, b = _pair(port, reference, V, osc="saw", delay="position", delay_capacity=cap)
+    for k in (a, b):
+        _configure(k, "none", p, False, True)
+        k.set("delay_position", pos)
+    for blk in range(3):
+        oa, _ = a.process(B); ob, _ = b.process(B)
+        assert _same(oa, ob), blk
+        assert np.array_equal(a.get("delay_phase"), b.get("delay_phase"))
+    for v in range(V):
+        assert _same(a.ring(v, cap), b.ring(v, cap)), v
+
+
 def test_delay_size_nonpositive(port, reference):
     V, B = 3, 20
     a, b = _pair(port, reference, V, osc="saw", delay=True, delay_capacity=16)
