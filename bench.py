@@ -185,6 +185,8 @@ def main():
     ap.add_argument("--mix", type=int, default=-1, help="1: also produce the stereo mix bus each block (default: only when gpus > 1)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--f32-out", action="store_true", help="store the materialised output as fp32 (declared in the JSON)")
+    ap.add_argument("--collective", default="p2p", choices=["p2p", "nccl"],
+                    help="N > 1 mix-down: p2p = peer-memory exchange fused into the mix-reduce kernel (default); nccl = torch.distributed all_reduce")
     args = ap.parse_args()
     if args.workload == "mfcc":
         return main_mfcc(args)
@@ -214,6 +216,11 @@ def main():
     bank = capi.Bank(V, osc=wl["osc"], filt=wl["filt"], env=wl["env"], delay=wl["delay"] > 0,
                      delay_capacity=max(wl["delay"], 1), max_frames=BLOCK, ctx=ctx, sample_rate=SR)
     W.configure_bank(bank, wl["filt"], p, wl["env"], wl["delay"] > 0)
+    p2p = world > 1 and want_mix and args.collective == "p2p"
+    if p2p:
+        exch = capi.Exchange(ctx, rank, world, max_doubles=2 * BLOCK)
+        exch.connect_with_torch_distributed()      # the IPC handles travel over the process group; the data never does
+        exch.attach(bank)
 
     out_dtype = torch.float32 if args.f32_out else torch.float64
     out = torch.empty((BLOCK, V), dtype=out_dtype, device=dev)             # 8 GiB (fp64, 1 Mi voices) >> 126 MB L2
@@ -231,7 +238,7 @@ def main():
             on_p, off_p = gates[k % 4][0].data_ptr(), gates[k % 4][1].data_ptr()
         bank.process_device(BLOCK, out_ptr=out.data_ptr(), mix_ptr=mix.data_ptr() if want_mix else None,
                             trig_on_ptr=on_p, trig_off_ptr=off_p, f32=args.f32_out, stream=stream.cuda_stream)
-        if world > 1 and want_mix:
+        if world > 1 and want_mix and not p2p:
             dist.all_reduce(mix)
 
     def barrier():
@@ -287,8 +294,9 @@ def main():
         bank.set_host_array("freq", fh, stream=stream.cuda_stream)        # H2D: this block's control data (stream-ordered)
         bank.process_split(BLOCK, out.data_ptr(), mh, on_h, off_h, f32=args.f32_out, stream=stream.cuda_stream)   # D2H: mix bus
         if world > 1:
-            m = mix_host.to(dev, non_blocking=True)
-            dist.all_reduce(m)
+            if not p2p:            # with the peer-memory exchange attached the bus that came back is already the global one
+                m = mix_host.to(dev, non_blocking=True)
+                dist.all_reduce(m)
 
     for _ in range(3):
         e2e_step()
@@ -317,7 +325,9 @@ def main():
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": wl["desc"] + (" + stereo mix bus" if want_mix else ""), "voices_per_gpu": V, "block": BLOCK,
                        "sample_rate": SR, "out_storage": "f32" if args.f32_out else "f64", "parallelism": f"voices sharded x{world}",
-                       "collective": "NCCL sum all-reduce of mix[1024][2] fp64 per block" if world > 1 and want_mix else "none",
+                       "collective": ("none" if not (world > 1 and want_mix) else
+                                      "peer-memory exchange of mix[1024][2] fp64 fused into the mix-reduce kernel (CUDA IPC over NVLink, rank-ordered sum)" if p2p
+                                      else "NCCL sum all-reduce of mix[1024][2] fp64 per block"),
                        "l2": "no flush needed: each step writes %.1f GB, inputs+outputs >> 126 MB L2" % (samples_per_step * (4 if args.f32_out else 8) / 1e9)},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "peak_source": peak_src, "kernel": "bank_kernel" if not wl["delay"] else "delay_bank_kernel",

@@ -179,6 +179,23 @@ int32_t mxb_bank_process(mxb_bank* bank, int32_t n_frames,
 /* kernels launched by this library on behalf of `bank` since creation (for bench.py's gpu_launches) */
 int64_t mxb_bank_launch_count(const mxb_bank* bank);
 
+/* ------------------------------------------------------------------------------------------------
+ * Multi-GPU mix-down: one process per GPU, voices sharded, every rank ends each block with the SAME stereo bus
+ * = sum over all ranks, in rank order (bit-identical on every rank and from run to run). The exchange is a
+ * symmetric peer-mapped buffer (CUDA IPC over NVLink/NVSwitch); the reduction of the per-warp partials and the
+ * exchange with the peers run in ONE kernel (no NCCL call on the data path). Setup: every rank creates an
+ * exchange, publishes mxb_exchange_local_handle() to the others (any side channel: torch.distributed,
+ * MPI, a pipe), calls mxb_exchange_connect() with all handles in rank order, and attaches it to its bank;
+ * mxb_bank_process then delivers the all-reduced bus in `mix`. All ranks must process the same blocks in the
+ * same order. The reference has no counterpart: it is single-threaded. */
+typedef struct mxb_exchange mxb_exchange;
+#define MXB_EXCHANGE_HANDLE_BYTES 64
+int32_t mxb_exchange_create(mxb_ctx* ctx, int32_t rank, int32_t world, int32_t max_doubles, mxb_exchange** ex);
+int32_t mxb_exchange_local_handle(mxb_exchange* ex, void* handle, int32_t handle_bytes);
+int32_t mxb_exchange_connect(mxb_exchange* ex, const void* all_handles /* world x MXB_EXCHANGE_HANDLE_BYTES, rank order */);
+int32_t mxb_exchange_destroy(mxb_exchange* ex);
+int32_t mxb_bank_set_exchange(mxb_bank* bank, mxb_exchange* ex /* NULL detaches */);
+
 /* the reference's envelope setters, vectorised: kind 0 = setAttack (1 - pow(0.01, 1/(ms*sr*0.001))),
  * 1 = setAttackMS (1/(ms/1000*sr)), 2 = setDecay == setRelease (pow(0.01, 1/(ms*sr*0.001))).
  * src/maximilian.cpp:1469-1486. Host arrays. */

@@ -26,6 +26,7 @@ EXPORTS = [
     "mxb_ctx_synchronize", "mxb_host_alloc", "mxb_host_free",
     "mxb_bank_create", "mxb_bank_destroy", "mxb_bank_voices", "mxb_bank_set_param", "mxb_bank_set_param_async", "mxb_bank_get_state",
     "mxb_bank_get_ring", "mxb_bank_process", "mxb_bank_launch_count", "mxb_env_coeffs",
+    "mxb_exchange_create", "mxb_exchange_local_handle", "mxb_exchange_connect", "mxb_exchange_destroy", "mxb_bank_set_exchange",
     "mxb_stft_create", "mxb_stft_destroy", "mxb_stft_process", "mxb_stft_launch_count",
     "mxb_mfcc_create", "mxb_mfcc_destroy", "mxb_mfcc_process",
     "mxb_istft_create", "mxb_istft_destroy", "mxb_istft_process",
@@ -79,6 +80,11 @@ def lib():
         "mxb_bank_process": (i32, [vp, i32, vp, vp, vp, i32, vp, i32, vp]),
         "mxb_bank_launch_count": (i64, [vp]),
         "mxb_env_coeffs": (i32, [i32, vp, i64, i32, vp]),
+        "mxb_exchange_create": (i32, [vp, i32, i32, i32, pp]),
+        "mxb_exchange_local_handle": (i32, [vp, vp, i32]),
+        "mxb_exchange_connect": (i32, [vp, vp]),
+        "mxb_exchange_destroy": (i32, [vp]),
+        "mxb_bank_set_exchange": (i32, [vp, vp]),
         "mxb_stft_create": (i32, [vp, i32, i32, i32, pp]),
         "mxb_stft_destroy": (i32, [vp]),
         "mxb_stft_process": (i32, [vp, vp, i64, i64, i32, i32, vp, vp, vp, vp, vp, vp, C.POINTER(i32), i32, vp]),
@@ -231,6 +237,44 @@ class Bank:
         else:
             check(lib().mxb_bank_set_param_async(self.h, P[name], C.c_void_p(a.ctypes.data), MEM_HOST,
                                                  C.c_void_p(int(stream)) if stream else None), f"mxb_bank_set_param_async({name})")
+
+
+class Exchange:
+    """mxb_exchange: peer-memory mix-bus exchange between the ranks of one box (one process per GPU)."""
+    HANDLE_BYTES = 64
+
+    def __init__(self, ctx, rank, world, max_doubles=2 * 1024):
+        self.ctx, self.rank, self.world = ctx, rank, world
+        self.h = C.c_void_p()
+        check(lib().mxb_exchange_create(ctx.h, rank, world, max_doubles, C.byref(self.h)), "mxb_exchange_create")
+
+    def local_handle(self):
+        buf = C.create_string_buffer(self.HANDLE_BYTES)
+        check(lib().mxb_exchange_local_handle(self.h, buf, self.HANDLE_BYTES), "mxb_exchange_local_handle")
+        return bytes(buf.raw)
+
+    def connect(self, handles):
+        """handles: list of `world` byte strings (rank order), as returned by every rank's local_handle()."""
+        assert len(handles) == self.world
+        blob = b"".join(handles)
+        check(lib().mxb_exchange_connect(self.h, C.c_char_p(blob)), "mxb_exchange_connect")
+
+    def connect_with_torch_distributed(self):
+        """Exchange the IPC handles over an initialised torch.distributed process group."""
+        import torch.distributed as dist
+        handles = [None] * self.world
+        dist.all_gather_object(handles, self.local_handle())
+        self.connect(handles)
+        dist.barrier()
+
+    def attach(self, bank):
+        check(lib().mxb_bank_set_exchange(bank.h, self.h), "mxb_bank_set_exchange")
+        bank._exchange = self
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().mxb_exchange_destroy(self.h)
+            self.h = None
 
 
 def env_coeffs(kind, ms, sample_rate=48000):

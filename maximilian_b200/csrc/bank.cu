@@ -6,6 +6,7 @@
 
 #include "bank_kernels.cuh"
 #include "delay_kernels.cuh"
+#include "exchange.cuh"
 
 using namespace mxb;
 
@@ -28,6 +29,7 @@ struct mxb_bank {
     double* mix_dev;                         // [max_frames][2]
     void* out_stage; size_t out_stage_bytes; // staging for MXB_MEM_HOST out
     int64_t launches;
+    mxb_exchange* ex;                        // peer-memory mix exchange (multi-GPU), or NULL
 };
 
 namespace {
@@ -157,6 +159,51 @@ __global__ void mix_reduce_kernel(const double* __restrict__ partials, double* _
     if (lane == 0) mix[row] = s;
 }
 
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// K3 + K6 in one kernel: the local reduction of the per-warp partials (as mix_reduce_kernel) lands in this rank's slot
+// of the peer-mapped exchange buffer; the last CTA to finish publishes the slot, waits for every peer's flag and
+// adds the peers' buses, read straight from their HBM over NVLink, in rank order (protocol: exchange.cu).
+__global__ void mix_reduce_exchange_kernel(const double* __restrict__ partials, double* __restrict__ mix, int rows, int W, const ExchDev x) {
+    const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (row < rows) {
+        const double* p = partials + (size_t)row * (size_t)W;
+        double s = 0.0;
+        for (int w = lane; w < W; w += 32) s += p[w];
+#pragma unroll
+        for (int m = 16; m >= 1; m >>= 1) s += __shfl_xor_sync(0xffffffffu, s, m);
+        if (lane == 0) x.local_payload[row] = s;
+    }
+    __shared__ bool last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) last = atomicAdd(x.ticket, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!last) return;
+    if (threadIdx.x == 0) {
+        __threadfence_system();                       // cumulative: the other CTAs' rows were ordered before their ticket
+        st_release_sys(x.local_flag, x.seq1);
+        for (int r = 0; r < x.world; ++r)
+            if (r != x.rank) while (ld_acquire_sys(x.peer_flag[r]) < x.seq1) { }
+        *x.ticket = 0;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < rows; i += blockDim.x) {
+        double s = 0.0;
+        for (int r = 0; r < x.world; ++r)             // rank order on every rank: identical bits everywhere, every run
+            s += (r == x.rank) ? __ldcg(x.local_payload + i) : __ldcv(x.peer_payload[r] + i);
+        mix[i] = s;
+    }
+}
+
 int free_bank(mxb_bank* b) {
     if (!b) return MXB_OK;
     for (int i = 0; i < MXB_P_COUNT; ++i) cudaFree(b->dp[i]);
@@ -250,6 +297,13 @@ int32_t mxb_bank_destroy(mxb_bank* b) {
 }
 
 int32_t mxb_bank_voices(const mxb_bank* b) { return b ? b->V : MXB_ERR_INVALID; }
+
+int32_t mxb_bank_set_exchange(mxb_bank* b, mxb_exchange* ex) {
+    MXB_REQUIRE(b, MXB_ERR_INVALID, "mxb_bank_set_exchange: NULL bank");
+    if (ex) MXB_REQUIRE(ex->ctx->device == b->ctx->device, MXB_ERR_INVALID, "mxb_bank_set_exchange: exchange and bank live on different devices");
+    b->ex = ex;
+    return MXB_OK;
+}
 int64_t mxb_bank_launch_count(const mxb_bank* b) { return b ? b->launches : 0; }
 
 int32_t mxb_bank_set_param(mxb_bank* b, int32_t id, const double* values, int32_t mem) {
@@ -475,7 +529,13 @@ int32_t mxb_bank_process(mxb_bank* b, int32_t n_frames, const int32_t* trig_on, 
     if (mix) {
         const int rows = n_frames * 2;
         const int threads = 256, blocks = (rows * 32 + threads - 1) / threads;
-        mix_reduce_kernel<<<blocks, threads, 0, s>>>(b->partials, d_mix, rows, a.W);
+        if (b->ex) {
+            MXB_REQUIRE(b->ex->connected, MXB_ERR_STATE, "mxb_bank_process: the attached exchange is not connected to its peers");
+            MXB_REQUIRE(rows <= b->ex->max_doubles, MXB_ERR_INVALID, "mxb_bank_process: exchange holds %d values, the bus needs %d", b->ex->max_doubles, rows);
+            mix_reduce_exchange_kernel<<<blocks, threads, 0, s>>>(b->partials, d_mix, rows, a.W, exchange_next(b->ex));
+        } else {
+            mix_reduce_kernel<<<blocks, threads, 0, s>>>(b->partials, d_mix, rows, a.W);
+        }
         MXB_CUDA(cudaGetLastError());
         b->launches += 1;
     }

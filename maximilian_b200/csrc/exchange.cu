@@ -1,0 +1,99 @@
+// mxb_exchange: symmetric peer-memory buffers for the mix-bus all-reduce (see exchange.cuh, bank.cu).
+//
+// Protocol (per call, sequence number s, slot = s & 1, one buffer of two slots per rank, all peer-mapped with CUDA IPC):
+//   1. every rank writes its locally reduced bus into its own slot, then publishes flag[slot] = s + 1 (release, system scope)
+//   2. every rank waits until each peer's flag[slot] >= s + 1 (acquire, system scope), reads the peers' payloads over
+//      NVLink and adds them IN RANK ORDER -- every rank computes the same sum, bit for bit, run after run
+//   3. slot reuse at call s + 2 is safe: during call s + 1 this rank saw every peer's flag reach s + 2, i.e. every peer
+//      had started call s + 1 and therefore finished reading slot(s) (stream order on the peer)
+// One kernel does the local reduction and the exchange (bank.cu: mix_reduce_exchange_kernel); nothing here calls NCCL.
+#include <new>
+
+#include "exchange.cuh"
+
+using namespace mxb;
+
+namespace mxb {
+ExchDev exchange_next(mxb_exchange* ex) {
+    ExchDev d;
+    memset(&d, 0, sizeof(d));
+    const int slot = (int)(ex->seq & 1);
+    d.rank = ex->rank; d.world = ex->world; d.seq1 = ex->seq + 1; d.ticket = ex->ticket;
+    for (int r = 0; r < ex->world; ++r) {
+        unsigned char* base = ex->peers[r] + (size_t)slot * ex->slot_bytes;
+        d.peer_flag[r] = (const unsigned long long*)base;
+        d.peer_payload[r] = (const double*)(base + kExchFlagBytes);
+    }
+    unsigned char* mine = ex->local + (size_t)slot * ex->slot_bytes;
+    d.local_flag = (unsigned long long*)mine;
+    d.local_payload = (double*)(mine + kExchFlagBytes);
+    ex->seq += 1;
+    return d;
+}
+}  // namespace mxb
+
+extern "C" {
+
+int32_t mxb_exchange_create(mxb_ctx* ctx, int32_t rank, int32_t world, int32_t max_doubles, mxb_exchange** out) {
+    MXB_REQUIRE(ctx && out, MXB_ERR_INVALID, "mxb_exchange_create: NULL argument");
+    *out = nullptr;
+    MXB_REQUIRE(world >= 1 && world <= kExchMaxWorld && rank >= 0 && rank < world, MXB_ERR_INVALID, "mxb_exchange_create: rank %d of %d", rank, world);
+    MXB_REQUIRE(max_doubles > 0, MXB_ERR_INVALID, "mxb_exchange_create: max_doubles %d", max_doubles);
+    DeviceGuard g(ctx->device);
+    mxb_exchange* ex = new (std::nothrow) mxb_exchange();
+    MXB_REQUIRE(ex, MXB_ERR_ALLOC, "mxb_exchange_create: out of host memory");
+    memset(ex, 0, sizeof(*ex));
+    ex->ctx = ctx; ex->rank = rank; ex->world = world; ex->max_doubles = max_doubles;
+    ex->slot_bytes = ((size_t)kExchFlagBytes + sizeof(double) * (size_t)max_doubles + 127) & ~(size_t)127;
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, 2 * ex->slot_bytes);      // plain cudaMalloc: exportable with cudaIpcGetMemHandle
+    if (e != cudaSuccess) { set_error("mxb_exchange_create: cudaMalloc: %s", cudaGetErrorString(e)); delete ex; return MXB_ERR_ALLOC; }
+    ex->local = (unsigned char*)p;
+    e = cudaMemset(p, 0, 2 * ex->slot_bytes);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&ex->ticket, sizeof(unsigned int));
+    if (e == cudaSuccess) e = cudaMemset(ex->ticket, 0, sizeof(unsigned int));
+    if (e != cudaSuccess) { set_error("mxb_exchange_create: %s", cudaGetErrorString(e)); cudaFree(p); delete ex; return MXB_ERR_CUDA; }
+    ex->peers[rank] = ex->local;
+    ex->connected = (world == 1);
+    *out = ex;
+    return MXB_OK;
+}
+
+int32_t mxb_exchange_local_handle(mxb_exchange* ex, void* handle, int32_t handle_bytes) {
+    MXB_REQUIRE(ex && handle, MXB_ERR_INVALID, "mxb_exchange_local_handle: NULL argument");
+    MXB_REQUIRE(handle_bytes >= (int32_t)sizeof(cudaIpcMemHandle_t), MXB_ERR_INVALID, "mxb_exchange_local_handle: need %zu bytes", sizeof(cudaIpcMemHandle_t));
+    DeviceGuard g(ex->ctx->device);
+    cudaIpcMemHandle_t h;
+    MXB_CUDA(cudaIpcGetMemHandle(&h, ex->local));
+    memcpy(handle, &h, sizeof(h));
+    return MXB_OK;
+}
+
+int32_t mxb_exchange_connect(mxb_exchange* ex, const void* all_handles) {
+    MXB_REQUIRE(ex && all_handles, MXB_ERR_INVALID, "mxb_exchange_connect: NULL argument");
+    DeviceGuard g(ex->ctx->device);
+    const unsigned char* hs = (const unsigned char*)all_handles;
+    for (int r = 0; r < ex->world; ++r) {
+        if (r == ex->rank) continue;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, hs + (size_t)r * sizeof(h), sizeof(h));
+        void* p = nullptr;
+        MXB_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        ex->peers[r] = (unsigned char*)p;
+    }
+    ex->connected = true;
+    return MXB_OK;
+}
+
+int32_t mxb_exchange_destroy(mxb_exchange* ex) {
+    if (!ex) return MXB_OK;
+    DeviceGuard g(ex->ctx->device);
+    cudaDeviceSynchronize();
+    for (int r = 0; r < ex->world; ++r)
+        if (r != ex->rank && ex->peers[r]) cudaIpcCloseMemHandle(ex->peers[r]);
+    cudaFree(ex->local); cudaFree(ex->ticket);
+    delete ex;
+    return MXB_OK;
+}
+
+}  // extern "C"
