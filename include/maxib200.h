@@ -176,6 +176,15 @@ int32_t mxb_bank_process(mxb_bank* bank, int32_t n_frames,
                          const int32_t* trig_on, const int32_t* trig_off,
                          void* out, int32_t out_dtype, double* mix,
                          int32_t mem, void* stream);
+/* The same block with a per-sample oscillator frequency freq_tv[t][v] (n_frames x voices doubles, in the memory the
+ * gates live in; NULL = the block-constant MXB_P_FREQ). The reference takes the frequency by argument on every
+ * sample, so a patch may modulate it at audio rate -- FM: osc.sinewave(440 + lfo.sinewave(1)*100),
+ * cpp/commandline/maximilian_examples/5.FM1/main.cpp:29. Costs one 8-byte read per voice-sample. Built for
+ * oscillator -> [filter] -> out / mix chains; with an envelope or delay stage it returns MXB_ERR_UNSUPPORTED. */
+int32_t mxb_bank_process_fm(mxb_bank* bank, int32_t n_frames, const double* freq_tv,
+                            const int32_t* trig_on, const int32_t* trig_off,
+                            void* out, int32_t out_dtype, double* mix,
+                            int32_t mem, void* stream);
 /* kernels launched by this library on behalf of `bank` since creation (for bench.py's gpu_launches) */
 int64_t mxb_bank_launch_count(const mxb_bank* bank);
 

@@ -28,6 +28,7 @@ struct mxb_bank {
     double* partials; size_t partials_len;
     double* mix_dev;                         // [max_frames][2]
     void* out_stage; size_t out_stage_bytes; // staging for MXB_MEM_HOST out
+    double* fm_stage; size_t fm_stage_bytes; // staging for host-resident per-sample frequencies
     int64_t launches;
     mxb_exchange* ex;                        // peer-memory mix exchange (multi-GPU), or NULL
 };
@@ -211,7 +212,7 @@ int free_bank(mxb_bank* b) {
     for (int i = 0; i < 5; ++i) cudaFree(b->cf[i]);
     cudaFree(b->env_amp); cudaFree(b->env_output); cudaFree(b->env_holdcount); cudaFree(b->env_hold); cudaFree(b->env_flags);
     cudaFree(b->trig_on); cudaFree(b->trig_off); cudaFree(b->dl_phase); cudaFree(b->dl_size); cudaFree(b->dl_pos); cudaFree(b->ring);
-    cudaFree(b->partials); cudaFree(b->mix_dev); cudaFree(b->out_stage);
+    cudaFree(b->partials); cudaFree(b->mix_dev); cudaFree(b->out_stage); cudaFree(b->fm_stage);
     delete b;
     return MXB_OK;
 }
@@ -249,6 +250,7 @@ int32_t mxb_bank_create(mxb_ctx* ctx, const mxb_bank_desc* d, mxb_bank** out) {
     b->trig_on = b->trig_off = b->dl_phase = b->dl_size = b->dl_pos = nullptr;
     b->ring = b->partials = b->mix_dev = nullptr; b->partials_len = 0;
     b->out_stage = nullptr; b->out_stage_bytes = 0; b->launches = 0;
+    b->fm_stage = nullptr; b->fm_stage_bytes = 0;
     const size_t V = (size_t)d->voices;
     int rc = MXB_OK;
 #define TRY(x) do { rc = (x); if (rc != MXB_OK) { free_bank(b); return rc; } } while (0)
@@ -422,6 +424,11 @@ int32_t mxb_bank_get_ring(mxb_bank* b, int32_t voice, double* dst, int32_t n, in
 
 int32_t mxb_bank_process(mxb_bank* b, int32_t n_frames, const int32_t* trig_on, const int32_t* trig_off,
                          void* out, int32_t out_dtype, double* mix, int32_t mem, void* stream_) {
+    return mxb_bank_process_fm(b, n_frames, nullptr, trig_on, trig_off, out, out_dtype, mix, mem, stream_);
+}
+
+int32_t mxb_bank_process_fm(mxb_bank* b, int32_t n_frames, const double* freq_tv, const int32_t* trig_on, const int32_t* trig_off,
+                            void* out, int32_t out_dtype, double* mix, int32_t mem, void* stream_) {
     MXB_REQUIRE(b, MXB_ERR_INVALID, "mxb_bank_process: NULL bank");
     MXB_REQUIRE(n_frames >= 0 && n_frames <= b->desc.max_frames, MXB_ERR_INVALID, "mxb_bank_process: n_frames %d (max_frames %d)", n_frames, b->desc.max_frames);
     MXB_REQUIRE(mem == MXB_MEM_HOST || mem == MXB_MEM_DEVICE || mem == MXB_MEM_SPLIT, MXB_ERR_INVALID, "mxb_bank_process: mem %d", mem);
@@ -442,6 +449,23 @@ int32_t mxb_bank_process(mxb_bank* b, int32_t n_frames, const int32_t* trig_on, 
 
     const int* d_on = trig_on; const int* d_off = trig_off;
     void* d_out = out; double* d_mix = mix;
+    if (freq_tv)
+        MXB_REQUIRE(b->desc.env_kind == MXB_ENV_NONE && b->desc.delay_taps == 0, MXB_ERR_UNSUPPORTED,
+                    "mxb_bank_process_fm: per-sample frequency is built for oscillator -> filter -> out/mix chains only "
+                    "(no envelope, no delay line)");
+    const double* d_fm = freq_tv;
+    if (freq_tv && host_ctl) {       // per-sample frequencies are control data: they live where the gates live
+        const size_t need = sizeof(double) * (size_t)n_frames * V;
+        if (need > b->fm_stage_bytes) {
+            MXB_CUDA(cudaStreamSynchronize(s));
+            cudaFree(b->fm_stage); b->fm_stage = nullptr; b->fm_stage_bytes = 0;
+            cudaError_t e = cudaMalloc((void**)&b->fm_stage, need);
+            if (e != cudaSuccess) { set_error("mxb_bank_process_fm: staging cudaMalloc(%zu): %s", need, cudaGetErrorString(e)); return MXB_ERR_ALLOC; }
+            b->fm_stage_bytes = need;
+        }
+        MXB_CUDA(cudaMemcpyAsync(b->fm_stage, freq_tv, need, cudaMemcpyHostToDevice, s));
+        d_fm = b->fm_stage;
+    }
     if (host_ctl) {
         if (trig_on) {
             MXB_CUDA(cudaMemcpyAsync(b->trig_on, trig_on, sizeof(int) * V, cudaMemcpyHostToDevice, s));
@@ -485,6 +509,7 @@ int32_t mxb_bank_process(mxb_bank* b, int32_t n_frames, const int32_t* trig_on, 
     a.W = W;
     a.sr = (double)(size_t)b->ctx->sample_rate;
     for (int i = 0; i < 4; ++i) a.svf_mix[i] = b->desc.svf_mix[i];
+    a.freq_tv = d_fm;
     a.freq = b->dp[MXB_P_FREQ]; a.duty = b->dp[MXB_P_DUTY]; a.phase = b->dp[MXB_P_PHASE]; a.osc_out = b->osc_out;
     a.f0 = b->f0; a.f1 = b->f1; a.f2 = b->f2;
     for (int i = 0; i < 5; ++i) a.cf[i] = b->cf[i];

@@ -338,6 +338,11 @@ static inline double env_ar(bank_t* b, int v, double input, int trigger) {
 
 int32_t mxo_bank_process(void* h, int32_t nframes, const int32_t* trig_on, const int32_t* trig_off,
                          double* out, double* mix, int32_t first, int32_t count) {
+    return mxo_bank_process_fm(h, nframes, NULL, trig_on, trig_off, out, mix, first, count);
+}
+
+int32_t mxo_bank_process_fm(void* h, int32_t nframes, const double* freq_tv, const int32_t* trig_on, const int32_t* trig_off,
+                            double* out, double* mix, int32_t first, int32_t count) {
     bank_t* b = (bank_t*)h;
     if (!b || nframes < 0 || first < 0 || count < 0 || first + count > b->V) return -1;
     const mxo_chain* c = &b->chain;
@@ -346,7 +351,10 @@ int32_t mxo_bank_process(void* h, int32_t nframes, const int32_t* trig_on, const
     for (int t = 0; t < nframes; ++t) {
         double m0 = 0.0, m1 = 0.0;
         for (int v = first; v < first + count; ++v) {
-            double x = osc_tick(c->osc_kind, &b->p[MXO_P_PHASE][v], &b->osc_out[v], b->p[MXO_P_FREQ][v], b->p[MXO_P_DUTY][v], sr);
+            /* the reference takes the frequency by argument on every call: a patch may pass a new one each sample
+             * (FM: maximilian_examples/5.FM1/main.cpp:29) */
+            const double fq = freq_tv ? freq_tv[(size_t)t * (size_t)V + (size_t)v] : b->p[MXO_P_FREQ][v];
+            double x = osc_tick(c->osc_kind, &b->p[MXO_P_PHASE][v], &b->osc_out[v], fq, b->p[MXO_P_DUTY][v], sr);
             if (c->env_kind == MXO_ENV_ADSR) {
                 int trig = (trig_on && trig_off && t >= trig_on[v] && t < trig_off[v]) ? 1 : 0;
                 x = env_adsr(b, v, x, trig);

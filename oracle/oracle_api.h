@@ -90,6 +90,10 @@ int32_t mxo_bank_get(void* bank, int32_t id, double* values);
  * sub-range (used to thread the CPU baseline); pass 0, V for everything. */
 int32_t mxo_bank_process(void* bank, int32_t nframes, const int32_t* trig_on, const int32_t* trig_off,
                          double* out, double* mix, int32_t first, int32_t count);
+/* the same with a per-sample oscillator frequency freq_tv[t][v] (NULL = the MXO_P_FREQ array): frequency modulation,
+ * cpp/commandline/maximilian_examples/5.FM1/main.cpp:29 */
+int32_t mxo_bank_process_fm(void* bank, int32_t nframes, const double* freq_tv, const int32_t* trig_on, const int32_t* trig_off,
+                            double* out, double* mix, int32_t first, int32_t count);
 /* copies ring slots [0, n) of voice v */
 int32_t mxo_bank_get_ring(void* bank, int32_t v, double* dst, int32_t n);
 

@@ -184,6 +184,11 @@ int32_t mxo_bank_get(void* h, int32_t id, double* x) {
 
 int32_t mxo_bank_process(void* h, int32_t nframes, const int32_t* trig_on, const int32_t* trig_off,
                          double* out, double* mix, int32_t first, int32_t count) {
+    return mxo_bank_process_fm(h, nframes, nullptr, trig_on, trig_off, out, mix, first, count);
+}
+
+int32_t mxo_bank_process_fm(void* h, int32_t nframes, const double* freq_tv, const int32_t* trig_on, const int32_t* trig_off,
+                            double* out, double* mix, int32_t first, int32_t count) {
     RefBank* b = (RefBank*)h;
     if (!b || nframes < 0 || first < 0 || count < 0 || first + count > b->V) return -1;
     const mxo_chain& c = b->chain;
@@ -201,7 +206,7 @@ int32_t mxo_bank_process(void* h, int32_t nframes, const int32_t* trig_on, const
         double m0 = 0.0, m1 = 0.0;
         for (int v = first; v < first + count; ++v) {
             RefVoice& r = b->voices[v];
-            double x = run_osc(r.osc, c.osc_kind, freq[v], duty[v]);
+            double x = run_osc(r.osc, c.osc_kind, freq_tv ? freq_tv[(size_t)t * V + v] : freq[v], duty[v]);
             if (c.env_kind == MXO_ENV_ADSR) {
                 int trig = (trig_on && trig_off && t >= trig_on[v] && t < trig_off[v]) ? 1 : 0;
                 x = r.env.adsr(x, trig);

@@ -173,6 +173,31 @@ def test_delay_with_filter_and_nonpositive_size(port):
         assert np.array_equal(g.get("delay_phase"), o.get("delay_phase"))
 
 
+def test_per_sample_frequency_with_envelope_is_refused():
+    g = gpu_bank(8, osc="saw", env=True, max_frames=16)
+    with pytest.raises(capi.MxbError):
+        g.process(16, freq_tv=np.full((16, 8), 100.0))
+
+
+@pytest.mark.parametrize("osc,filt,delay", [("sinewave", "none", False), ("saw", "svf", False), ("phasor", "biquad", False),
+                                            ("triangle", "lores", False)])
+def test_per_sample_frequency_fm(port, osc, filt, delay):
+    """audio-rate modulated oscillator frequency, mxb_bank_process_fm."""
+    from test_oracle_vs_reference import fm_frequencies
+    V, B, cap = 130, 200, 128
+    p = W.voice_params(V, seed=31, delay_size=cap)
+    g = gpu_bank(V, osc=osc, filt=filt, delay=delay, delay_capacity=cap, max_frames=B)
+    o = port.Bank(V, osc=osc, filt=filt, delay=delay, delay_capacity=cap)
+    W.configure_bank(g, filt, p, False, delay); W.configure_bank(o, filt, p, False, delay)
+    for blk in range(3):
+        f = fm_frequencies(V, B, blk)
+        og, mg = g.process(B, freq_tv=f, want_mix=True); oo, mo = o.process(B, freq_tv=f, want_mix=True)
+        _close(og, oo, osc in TRIG, f"fm {osc} blk{blk}")
+        np.testing.assert_allclose(mg, mo, rtol=1e-9, atol=1e-11)
+    og, _ = g.process(B); oo, _ = o.process(B)
+    _close(og, oo, osc in TRIG, "back to block-constant frequency")
+
+
 def test_env_ar(port):
     # maxiEnv::ar, src/maximilian.cpp:1319-1358 (output = input in the hold states; clamp test on every call)
     V, B = 200, 400

@@ -139,6 +139,28 @@ def test_delayline_indices_and_ring_bit_exact(port, reference):
         assert _same(a.ring(v, cap), b.ring(v, cap)), v
 
 
+def fm_frequencies(V, B, blk, seed=5):
+    """freq[t][v] = carrier + depth * sin(2*pi*rate*t/sr): what 5.FM1's play() feeds its carrier (main.cpp:29)."""
+    rng = np.random.default_rng(seed)
+    carrier = 110.0 * np.exp2(3.0 * rng.random(V)); depth = 50.0 * rng.random(V); rate = 0.5 + 8.0 * rng.random(V)
+    t = (blk * B + np.arange(B))[:, None] / 48000.0
+    return carrier[None, :] + depth[None, :] * np.sin(2 * np.pi * rate[None, :] * t)
+
+
+@pytest.mark.parametrize("osc,filt", [("sinewave", "none"), ("saw", "svf"), ("triangle", "lores")])
+def test_per_sample_frequency_bit_exact(port, reference, osc, filt):
+    V, B = 21, 200
+    p = W.voice_params(V, seed=31)
+    a, b = _pair(port, reference, V, osc=osc, filt=filt)
+    _configure(a, filt, p); _configure(b, filt, p)
+    for blk in range(3):
+        f = fm_frequencies(V, B, blk)
+        oa, _ = a.process(B, freq_tv=f); ob, _ = b.process(B, freq_tv=f)
+        assert _same(oa, ob), blk
+    oa, _ = a.process(B); ob, _ = b.process(B)          # back to the block-constant frequency
+    assert _same(oa, ob)
+
+
 def test_env_ar_bit_exact(port, reference):
     # maxiEnv::ar(input, attack, release, holdtime, trigger), src/maximilian.cpp:1319-1358
     V, B = 48, 400
