@@ -100,14 +100,50 @@ class ClockSampler:
 
 # ------------------------------------------------------------------------------------------- CPU reference leg
 
-def cpu_bank(wl, voices, kind):
-    from maximilian_b200 import workloads as W
-    from oracle import oracle_py as O
-    p = W.voice_params(voices, seed=W.SEED, delay_size=wl["delay"] or 4096)
-    b = O.Bank(voices, osc=wl["osc"], filt=wl["filt"], env=wl["env"], delay=wl["delay"] > 0, sample_rate=SR,
-               delay_capacity=max(wl["delay"], 1), kind=kind)
-    W.configure_bank(b, wl["filt"], p, wl["env"], wl["delay"] > 0)
-    return b
+class CpuFarm:
+    """The reference on all host cores: `threads` workers, each owning its own slice of the voices as its own reference
+    objects and its own output slab, all created INSIDE the worker (first touch = local NUMA node). One thread start per
+    run; every worker runs all blocks of its voices (voices are independent: no barrier between blocks)."""
+
+    def __init__(self, wl, voices, threads, kind):
+        from maximilian_b200 import workloads as W
+        from oracle import oracle_py as O
+        self.wl, self.voices, self.kind = wl, voices, kind
+        self.threads = max(1, min(threads, voices))
+        self.bounds = np.linspace(0, voices, self.threads + 1).astype(int)
+        p = W.voice_params(voices, seed=W.SEED, delay_size=wl["delay"] or 4096)
+        self.parts = [None] * self.threads
+
+        def make(i):
+            lo, hi = int(self.bounds[i]), int(self.bounds[i + 1])
+            b = O.Bank(hi - lo, osc=wl["osc"], filt=wl["filt"], env=wl["env"], delay=wl["delay"] > 0, sample_rate=SR,
+                       delay_capacity=max(wl["delay"], 1), kind=kind)
+            W.configure_bank(b, wl["filt"], {k: v[lo:hi] for k, v in p.items()}, wl["env"], wl["delay"] > 0)
+            self.parts[i] = (b, np.zeros((BLOCK, hi - lo), dtype=np.float64))
+        self._par(make)
+
+    def _par(self, fn):
+        ts = [threading.Thread(target=fn, args=(i,)) for i in range(self.threads)]
+        [t.start() for t in ts]
+        [t.join() for t in ts]
+
+    def run(self, nblocks, block_index0=0):
+        """Seconds for `nblocks` consecutive blocks of the whole bank."""
+        from maximilian_b200 import workloads as W
+        from oracle import oracle_py as O
+        gates = [(W.gate(self.voices, BLOCK, block_index0 + k) if self.wl["env"] else (None, None)) for k in range(nblocks)]
+
+        def work(i):
+            lo, hi = int(self.bounds[i]), int(self.bounds[i + 1])
+            b, out = self.parts[i]
+            for on, off in gates:
+                on_i = np.ascontiguousarray(on[lo:hi]) if on is not None else None
+                off_i = np.ascontiguousarray(off[lo:hi]) if off is not None else None
+                rc = b.lib.mxo_bank_process(b.h, BLOCK, O._ip(on_i), O._ip(off_i), O._dp(out), None, 0, hi - lo)
+                assert rc == 0, rc
+        t0 = time.perf_counter()
+        self._par(work)
+        return time.perf_counter() - t0
 
 
 def cpu_kind():
@@ -123,33 +159,20 @@ def cpu_sample_voices(wl):
     return 512 if wl["delay"] else 65536
 
 
-_cpu_out = {}
-
-
-def run_cpu_blocks(bank, wl, voices, threads, nblocks, block_index0=0):
-    from maximilian_b200 import workloads as W
-    if voices not in _cpu_out:          # one output block, allocated and touched once (no page faults in the timed loop)
-        _cpu_out[voices] = np.zeros((BLOCK, voices), dtype=np.float64)
-    from oracle import oracle_py as O
-    gates = [(W.gate(voices, BLOCK, block_index0 + k) if wl["env"] else (None, None)) for k in range(nblocks)]
-    t0 = time.perf_counter()
-    O.run_blocks_threaded(bank, BLOCK, gates, threads, _cpu_out[voices])
-    return time.perf_counter() - t0
-
-
 def cpu_baseline(wl, budget_s=4.0):
     kind = cpu_kind()
     cores = os.cpu_count() or 1
     voices = cpu_sample_voices(wl)
-    bank = cpu_bank(wl, voices, kind)
-    run_cpu_blocks(bank, wl, voices, cores, 1)                      # warm-up block
+    farm = CpuFarm(wl, voices, cores, kind)
+    farm.run(1)                                                      # warm-up block
     n, total = 0, 0.0
     while total < budget_s and n < 128:
-        total += run_cpu_blocks(bank, wl, voices, cores, 8, 1 + n)     # 8 blocks per thread start
+        total += farm.run(8, 1 + n)                                  # 8 blocks per thread start
         n += 8
     v = voices * BLOCK * n / total
     return {"value": v, "unit": "samples/s", "cores": cores, "kind": kind,
-            "sample": f"{voices} voices x {BLOCK} frames x {n} blocks of the same chain, voices partitioned over {cores} host threads"}
+            "sample": f"{voices} voices x {BLOCK} frames x {n} blocks of the same chain; {farm.threads} host threads, each with its own "
+                      "slice of the voices as reference objects (frame-outer / voice-inner like a reference play())"}
 
 
 def reference_arm(args, wl_name, wl):
@@ -159,9 +182,9 @@ def reference_arm(args, wl_name, wl):
     kind = cpu_kind()
     cores = os.cpu_count() or 1
     voices = cpu_sample_voices(wl)
-    bank = cpu_bank(wl, voices, kind)
-    run_cpu_blocks(bank, wl, voices, cores, args.warmup)
-    dt = run_cpu_blocks(bank, wl, voices, cores, args.steps, args.warmup)
+    farm = CpuFarm(wl, voices, cores, kind)
+    farm.run(args.warmup)
+    dt = farm.run(args.steps, args.warmup)
     v = voices * BLOCK * args.steps / dt
     line = {"impl": "reference", "metric": "voice_samples_per_sec", "value": v, "unit": "samples/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,

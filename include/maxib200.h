@@ -227,6 +227,20 @@ int32_t mxb_stft_process(mxb_stft* st, const float* in, int64_t stride_c, int64_
                          mxb_mfcc* mfcc, double* coeffs, int32_t* n_frames, int32_t mem, void* stream);
 int64_t mxb_stft_launch_count(const mxb_stft* st);
 
+/* The same call with the per-frame spectral features of maxiFFT fused in as further optional outputs
+ * (SURVEY.md 8f-3): mags_db = getMagnitudesDB()/magsToDB (src/libs/maxiFFT.cpp:101-111, fft.cpp:526-534) laid out like
+ * mags; flatness / centroid = spectralFlatness() / spectralCentroid() (src/libs/maxiFFT.cpp:113-132), one float per
+ * frame at c*max_frames + f. The reference sums 512 floats in bin order; here each lane sums every 32nd bin and a
+ * shuffle tree combines the lanes: equal to float reassociation (asserted at 1e-4 relative). */
+typedef struct {
+    float *mags, *phases, *re, *im;      /* as in mxb_stft_process */
+    float *mags_db, *flatness, *centroid;
+    double* coeffs;                      /* with `mfcc` */
+} mxb_stft_outputs;
+int32_t mxb_stft_process2(mxb_stft* st, const float* in, int64_t stride_c, int64_t stride_t, int32_t n_samples,
+                          int32_t max_frames, const mxb_stft_outputs* out, mxb_mfcc* mfcc,
+                          int32_t* n_frames, int32_t mem, void* stream);
+
 /* maxiMFCC::setup(numBins, numFilters, numCoeffs, minFreq, maxFreq) + mfcc() (src/libs/maxiMFCC.h:56-111,
  * src/libs/maxiMFCC.cpp:48-66). mags: float [n][num_bins]; coeffs: double [n][num_coeffs];
  * melbands (optional): double [n][num_filters] after the log stage. */

@@ -27,7 +27,7 @@ EXPORTS = [
     "mxb_bank_create", "mxb_bank_destroy", "mxb_bank_voices", "mxb_bank_set_param", "mxb_bank_set_param_async", "mxb_bank_get_state",
     "mxb_bank_get_ring", "mxb_bank_process", "mxb_bank_process_fm", "mxb_bank_launch_count", "mxb_env_coeffs",
     "mxb_exchange_create", "mxb_exchange_local_handle", "mxb_exchange_connect", "mxb_exchange_destroy", "mxb_bank_set_exchange",
-    "mxb_stft_create", "mxb_stft_destroy", "mxb_stft_process", "mxb_stft_launch_count",
+    "mxb_stft_create", "mxb_stft_destroy", "mxb_stft_process", "mxb_stft_process2", "mxb_stft_launch_count",
     "mxb_mfcc_create", "mxb_mfcc_destroy", "mxb_mfcc_process",
     "mxb_istft_create", "mxb_istft_destroy", "mxb_istft_process",
 ]
@@ -41,6 +41,11 @@ class BankDesc(C.Structure):
     _fields_ = [("voices", C.c_int32), ("osc_kind", C.c_int32), ("filt_kind", C.c_int32),
                 ("biquad_type", C.c_int32), ("env_kind", C.c_int32), ("delay_taps", C.c_int32),
                 ("max_frames", C.c_int32), ("delay_mode", C.c_int32), ("svf_mix", C.c_double * 4)]
+
+
+class StftOutputs(C.Structure):
+    _fields_ = [("mags", C.c_void_p), ("phases", C.c_void_p), ("re", C.c_void_p), ("im", C.c_void_p),
+                ("mags_db", C.c_void_p), ("flatness", C.c_void_p), ("centroid", C.c_void_p), ("coeffs", C.c_void_p)]
 
 
 ENV_KIND = {False: 0, None: 0, True: 1, "adsr": 1, "ar": 2}          # maxiEnv::adsr / maxiEnv::ar
@@ -89,6 +94,7 @@ def lib():
         "mxb_stft_create": (i32, [vp, i32, i32, i32, pp]),
         "mxb_stft_destroy": (i32, [vp]),
         "mxb_stft_process": (i32, [vp, vp, i64, i64, i32, i32, vp, vp, vp, vp, vp, vp, C.POINTER(i32), i32, vp]),
+        "mxb_stft_process2": (i32, [vp, vp, i64, i64, i32, i32, C.POINTER(StftOutputs), vp, C.POINTER(i32), i32, vp]),
         "mxb_stft_launch_count": (i64, [vp]),
         "mxb_mfcc_create": (i32, [vp, i32, i32, i32, dbl, dbl, pp]),
         "mxb_mfcc_destroy": (i32, [vp]),
@@ -343,6 +349,20 @@ class Stft:
         if co is not None:
             r["mfcc"] = np.ascontiguousarray(co[:, :f])
         return r
+
+    def process_features(self, x):
+        """x: float32 [C][n] planar host array -> dict(mags, mags_db [C][frames][bins]; flatness, centroid [C][frames]):
+        maxiFFT::getMagnitudesDB / spectralFlatness / spectralCentroid fused into the transform (mxb_stft_process2)."""
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        n = x.shape[1]
+        maxf = max(1, n // self.hop + 2)
+        mags = np.zeros((self.C, maxf, self.bins), dtype=np.float32); db = np.zeros_like(mags)
+        fl = np.zeros((self.C, maxf), dtype=np.float32); ce = np.zeros_like(fl)
+        o = StftOutputs(mags.ctypes.data, None, None, None, db.ctypes.data, fl.ctypes.data, ce.ctypes.data, None)
+        nf = C.c_int32(0)
+        check(lib().mxb_stft_process2(self.h, _np_ptr(x), n, 1, n, maxf, C.byref(o), None, C.byref(nf), MEM_HOST, None), "mxb_stft_process2")
+        f = nf.value
+        return dict(mags=mags[:, :f].copy(), mags_db=db[:, :f].copy(), flatness=fl[:, :f].copy(), centroid=ce[:, :f].copy())
 
     def process_device(self, in_ptr, stride_c, stride_t, n, max_frames, mags=None, phases=None, re=None, im=None,
                        mfcc=None, coeffs=None, stream=0):

@@ -622,6 +622,43 @@ int32_t mxo_stft_process(void* h, const float* in, int32_t n, int32_t max_frames
     return frames;
 }
 
+/* fft::convToDB (src/libs/fft.cpp:526-534), maxiFFT::spectralFlatness / spectralCentroid (src/libs/maxiFFT.cpp:113-132).
+ * The unqualified log10 / fabs on floats are the float overloads in the reference; sums are float, in bin order. */
+int32_t mxo_spectral_features(const float* mags, int32_t n_frames, int32_t fft_size, int32_t sample_rate,
+                              float* db, float* flatness, float* centroid) {
+    if (!mags || n_frames < 0 || fft_size < 4 || (fft_size & (fft_size - 1))) return -1;
+    const int bins = fft_size / 2;
+    for (int fr = 0; fr < n_frames; ++fr) {
+        const float* magnitudes = mags + (size_t)fr * (size_t)bins;
+        if (db) {
+            float* out = db + (size_t)fr * (size_t)bins;
+            for (int i = 0; i < bins; i++) {
+                if (magnitudes[i] < 0.000001) out[i] = 0;
+                else out[i] = 20.0 * log10f(magnitudes[i] + 1);
+            }
+        }
+        if (flatness) {
+            float geometricMean = 0, arithmaticMean = 0;
+            for (size_t i = 0; i < (size_t)bins; i++) {
+                if (magnitudes[i] != 0) geometricMean += logf(magnitudes[i]);
+                arithmaticMean += magnitudes[i];
+            }
+            geometricMean = expf(geometricMean / (float)bins);
+            arithmaticMean /= (float)bins;
+            flatness[fr] = arithmaticMean != 0 ? geometricMean / arithmaticMean : 0;
+        }
+        if (centroid) {
+            float x = 0, y = 0;
+            for (size_t i = 0; i < (size_t)bins; i++) {
+                x += fabsf(magnitudes[i]) * i;
+                y += fabsf(magnitudes[i]);
+            }
+            centroid[fr] = y != 0 ? x / y * ((float)(size_t)sample_rate / fft_size) : 0;
+        }
+    }
+    return 0;
+}
+
 /* =================================================================== MFCC */
 
 typedef struct {

@@ -111,6 +111,13 @@ int32_t mxo_stft_process(void* st, const float* in, int32_t n, int32_t max_frame
                          float* mags, float* phases, float* re, float* im);
 int32_t mxo_stft_window(void* st, float* window);   /* fft_size floats */
 
+/* Per-frame spectral features of maxiFFT computed from magnitudes[n_frames][bins] (bins = fft_size/2):
+ * db[n_frames][bins] = maxiFFT::magsToDB / fft::convToDB (src/libs/maxiFFT.cpp:101-111, src/libs/fft.cpp:526-534),
+ * flatness[n_frames] = maxiFFT::spectralFlatness (:113-123), centroid[n_frames] = maxiFFT::spectralCentroid (:125-132)
+ * with maxiSettings::sampleRate = sample_rate. Any output may be NULL. */
+int32_t mxo_spectral_features(const float* mags, int32_t n_frames, int32_t fft_size, int32_t sample_rate,
+                              float* db, float* flatness, float* centroid);
+
 /* maxiMFCC::setup(numBins, numFilters, numCoeffs, minFreq, maxFreq) with maxiSettings::sampleRate = sample_rate.
  * mags: [n][numBins] floats; coeffs: [n][numCoeffs]; melbands (optional): [n][numFilters] after the log stage. */
 void*   mxo_mfcc_create(int32_t num_bins, int32_t num_filters, int32_t num_coeffs,

@@ -77,6 +77,7 @@ def load(kind="port"):
         "mxo_stft_destroy": (None, [vp]),
         "mxo_stft_process": (i32, [vp, fp, i32, i32, fp, fp, fp, fp]),
         "mxo_stft_window": (i32, [vp, fp]),
+        "mxo_spectral_features": (i32, [fp, i32, i32, i32, fp, fp, fp]),
         "mxo_mfcc_create": (vp, [i32, i32, i32, C.c_double, C.c_double, i32]),
         "mxo_mfcc_destroy": (None, [vp]),
         "mxo_mfcc_process": (i32, [vp, fp, i32, dp, dp]),
@@ -253,6 +254,19 @@ class Stft:
         if f < 0:
             raise RuntimeError(f"mxo_stft_process -> {f}")
         return {k: np.ascontiguousarray(v[:, :f]) for k, v in bufs.items() if v is not None}
+
+
+def spectral_features(mags, fft_size, sample_rate=48000, kind="port"):
+    """mags float32 [..., bins] -> (db [..., bins], flatness [...], centroid [...]) : maxiFFT::magsToDB / spectralFlatness / spectralCentroid."""
+    lib = load(kind)
+    m = np.ascontiguousarray(mags, dtype=np.float32)
+    lead = m.shape[:-1]
+    n = int(np.prod(lead)) if lead else 1
+    db = np.empty_like(m); fl = np.empty(n, dtype=np.float32); ce = np.empty(n, dtype=np.float32)
+    rc = lib.mxo_spectral_features(_fp(m), n, fft_size, sample_rate, _fp(db), _fp(fl), _fp(ce))
+    if rc:
+        raise RuntimeError(f"mxo_spectral_features -> {rc}")
+    return db, fl.reshape(lead), ce.reshape(lead)
 
 
 class Mfcc:

@@ -292,6 +292,24 @@ int32_t mxo_stft_window(void* h, float* w) {
     memcpy(w, s->f[0]->window.data(), sizeof(float) * s->n); return 0;
 }
 
+/* the reference methods themselves, run on a maxiFFT whose (private) magnitudes vector is loaded with each frame */
+int32_t mxo_spectral_features(const float* mags, int32_t n_frames, int32_t fft_size, int32_t sample_rate,
+                              float* db, float* flatness, float* centroid) {
+    if (!mags || n_frames < 0 || fft_size < 4 || (fft_size & (fft_size - 1))) return -1;
+    maxiSettings::setup((size_t)sample_rate, 2, 1024);
+    maxiFFT f;
+    f.setup(fft_size, fft_size / 2, fft_size);
+    const int bins = fft_size / 2;
+    for (int i = 0; i < n_frames; ++i) {
+        memcpy(f.magnitudes.data(), mags + (size_t)i * bins, sizeof(float) * bins);
+        f.recalc = true;
+        if (db) memcpy(db + (size_t)i * bins, f.getMagnitudesDB().data(), sizeof(float) * bins);
+        if (flatness) flatness[i] = f.spectralFlatness();
+        if (centroid) centroid[i] = f.spectralCentroid();
+    }
+    return 0;
+}
+
 /* ------------------------------------------------------------------ MFCC */
 struct RefMfcc { int bins, filters, coeffs; maxiMFCC m; std::vector<float> spec; };
 

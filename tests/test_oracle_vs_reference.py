@@ -262,6 +262,18 @@ def test_mfcc_bit_exact(port, reference, cfg):
     assert np.all(ma[..., 0] == 0.0)                   # filter 0 is never initialised by the reference (A13)
 
 
+def test_spectral_features_bit_exact(port, reference):
+    # maxiFFT::magsToDB / spectralFlatness / spectralCentroid, src/libs/maxiFFT.cpp:101-132
+    mags = port.Stft(3, 1024, 512).process(W.channel_streams(3, 8192, seed=8))["mags"]
+    mags[0, 0] = 0.0                                  # all-zero frame: both features return 0
+    mags[1, 1, :7] = 0.0                              # zeros are skipped by the geometric mean
+    for sr in (44100, 48000):
+        a = port.spectral_features(mags, 1024, sr, kind="port")
+        b = reference.spectral_features(mags, 1024, sr, kind="reference")
+        for x, y in zip(a, b):
+            assert _same(x, y)
+
+
 @pytest.mark.parametrize("n,hop", [(1024, 512), (1024, 256), (256, 64)])
 def test_istft_bit_exact(port, reference, n, hop):
     C = 3
