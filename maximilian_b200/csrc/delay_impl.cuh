@@ -1,25 +1,30 @@
-// K2: oscillator -> [ADSR] -> [filter] -> maxiDelayline::dl -> out / stereo mix.   (kernel template; the
+// K2: oscillator -> [envelope] -> [filter] -> maxiDelayline::dl -> out / stereo mix.   (kernel template; the
 // instantiations live in delay_k_*.cu, one translation unit per filter family, the dispatcher in delay.cu)
 //
 // maxiDelayline::dl (src/maximilian.cpp:420-429) reads ring[phase] and writes it back every sample:
 // 8 B read + 8 B write of ring traffic per voice-sample on top of the 8 B output -- the one genuinely
 // HBM-bound stage of the path. A thread walking its own ring straight out of global memory would issue
 // one 8-byte load per sample with 32 different lines per warp request; instead each WARP stages the next
-// 32 ring slots of each of its 32 voices through shared memory:
+// T = 16 ring slots of each of its 32 voices through shared memory, double-buffered:
 //
-//   load:       32 cp.async requests, one per voice, lane = slot: 256 contiguous bytes each (warp-private tile)
-//   compute:    lane = voice; 32 steps of the chain, ring slot j of the window read and updated in smem
-//               (row stride 33 doubles: conflict-free for 64-bit accesses)
-//   write-back: the window returns to the ring the way it came, lane = slot, 256 B per request
+//   prefetch k+1: 16 cp.async requests, two voices each, lane&15 = slot: 128 contiguous bytes per voice, in flight
+//                 while window k is computed (warp-private tiles, no __syncthreads anywhere)
+//   compute k:    lane = voice; 16 steps of the chain, ring slot j of the window read and updated in smem
+//                 (row stride 17 doubles: conflict-free for 64-bit accesses)
+//   write-back:   the window returns to the ring the way it came, 128 B per voice and request
+//
+// History (profiles/r01_delay_kernel_v*.txt): 32-slot windows double-buffered = 12 warps/SM, issue-starved (0.47-0.69 of
+// the HBM peak); single-buffered 24 warps (0.78) left too few bytes in flight; 16-slot windows give both: 24 warps/SM
+// AND a prefetch in flight for every warp all the time.
 //
 // Two schedules share the per-step code:
-//   * uniform: every voice of the warp has the same ring size (a multiple of 32) and the same, chunk-aligned
+//   * uniform: every voice of the warp has the same ring size (a multiple of 16) and the same, chunk-aligned
 //     index -- voices started together, the common case. With the chunk-interleaved ring layout
-//     (delay_kernels.cuh) the warp's 32 windows are ONE contiguous 8 KB run: address arithmetic collapses to
+//     (delay_kernels.cuh) the warp's 32 windows are ONE contiguous 4 KB run: address arithmetic collapses to
 //     pointer increments and DRAM sees pure streaming.
 //   * generic: any per-voice size / phase (ragged banks, rings that shrank between blocks): each window is
-//     located per voice (wrap at `size`, chunk crossing), still 256 B per request. Voices whose ring is
-//     shorter than two windows (64 slots) take the literal per-sample path against global memory.
+//     located per voice (wrap at `size`, chunk crossing), still 128 B per voice. Voices whose ring is
+//     shorter than two windows (32 slots), and dlFromPosition, take the literal per-sample path against global memory.
 //
 // The ring index `phase` is an int and follows the reference statement for statement --
 // `if (phase >= size) phase = 0` BEFORE the access -- so index sequences are bit-exact.
@@ -28,15 +33,16 @@
 
 namespace mxb {
 
-constexpr int kStageDoubles = 32 * 33;            // one staged window tile per warp
-// Window buffers per warp. 1: load -> compute -> write back, latency hidden by the other warps of the SM (24 warps
-// fit); 2: the next window is in flight while this one is computed, but only 12 warps fit. Measured on B200
-// (profiles/r01_delay_kernel_v2/v3): with 12 warps the issue slots starve on fixed-latency dependencies, so 1 wins.
-constexpr int kDlStages = 1;
+constexpr int kDlT = kDlChunk;                    // steps per staged window
+constexpr int kDlRow = kDlT + 1;                  // tile row stride in doubles
+constexpr int kStageDoubles = 32 * kDlRow;        // one staged window tile per warp
+constexpr int kDlStages = 2;                      // double buffer
+constexpr int kDlVoicesPerReq = 32 / kDlT;        // voices covered by one cooperative request (2)
 constexpr int kMixDoubles = 2 * kMixTT * 33;
-constexpr int kFastMinSize = 2 * kDlChunk;
+constexpr int kFastMinSize = 2 * kDlT;
 constexpr unsigned kFull = 0xffffffffu;
 enum { DL_OUT_NONE = 0, DL_OUT_F64 = 1, DL_OUT_F32 = 2 };
+static_assert(kDlT == kMixTT, "one staged window = one mix tile");
 
 __device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc) {
     const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -44,7 +50,6 @@ __device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc) 
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait1() { asm volatile("cp.async.wait_group 1;\n" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait0() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 
 struct DlVoice {
     double phase, oout, inc, duty, fb, gl, gr;
@@ -54,67 +59,63 @@ struct DlVoice {
     bool live, fast;
 };
 
-// 32 (or fewer) steps of one voice against its staged window `row` (ALLFAST) or, for short rings, against global memory
+// one window (<= 16 steps) of one voice against its staged row (ALLFAST) or, for short rings, against global memory
 template <int OSC, int FILT, int ENV, bool ALLFAST, int OUTMODE, bool MIX>
 __device__ __forceinline__ void dl_stage(DlVoice& s, double* row, const int tn, const int t0, const BankArgs& a, const DelayArgs& d,
                                          const size_t V, const size_t v, const int lane, const int gwarp, double* mixtile) {
     double* out64 = (double*)a.out + (size_t)t0 * V + v;
     float* out32 = (float*)a.out + (size_t)t0 * V + v;
-    for (int h0 = 0; h0 < tn; h0 += kMixTT) {
-        const int hn = min(kMixTT, tn - h0);
 #pragma unroll 4
-        for (int jj = 0; jj < hn; ++jj) {
-            const int j = h0 + jj;
-            const int t = t0 + j;
-            double x = osc_tick<OSC>(s.phase, s.oout, s.inc, s.duty, a.osc_kind);
-            if (ENV) {
-                const bool trig = t >= s.er.on && t < s.er.off;
-                x = a.env_ar ? env_ar_tick(s.er, x, trig) : env_tick(s.er, x, trig);
-            }
-            x = filt_tick<FILT>(s.fr, x, a.svf_mix);
-            // maxiDelayline::dl, src/maximilian.cpp:420-429
-            double y = 0.0;
-            if (ALLFAST ? s.live : s.fast) {          // lanes past the end of the bank contribute an exact 0
-                const double m = row[j];
-                row[j] = (m * s.fb) + (x * s.fb) * 0.5;
+    for (int j = 0; j < tn; ++j) {
+        const int t = t0 + j;
+        double x = osc_tick<OSC>(s.phase, s.oout, s.inc, s.duty, a.osc_kind);
+        if (ENV) {
+            const bool trig = t >= s.er.on && t < s.er.off;
+            x = a.env_ar ? env_ar_tick(s.er, x, trig) : env_tick(s.er, x, trig);
+        }
+        x = filt_tick<FILT>(s.fr, x, a.svf_mix);
+        // maxiDelayline::dl, src/maximilian.cpp:420-429
+        double y = 0.0;
+        if (ALLFAST ? s.live : s.fast) {          // lanes past the end of the bank contribute an exact 0
+            const double m = row[j];
+            row[j] = (m * s.fb) + (x * s.fb) * 0.5;
+            y = m;
+        } else if (!ALLFAST && s.live) {
+            if (s.ph >= s.size) s.ph = 0;
+            const int idx = min(max(s.ph, 0), d.taps - 1);     // size <= taps is enforced when the parameter is set
+            double* slot = d.ring + dl_slot(V, v, idx);
+            const double m = *slot;
+            if (d.from_position) {
+                // maxiDelayline::dlFromPosition, src/maximilian.cpp:431-439: the output comes from `position`, the
+                // write has chandiv (== 1) where dl() has 0.5
+                int pos = s.pos;
+                if (pos >= s.size) pos = 0;
+                y = d.ring[dl_slot(V, v, min(max(pos, 0), d.taps - 1))];
+                *slot = (m * s.fb) + (x * s.fb) * 1.0;
+            } else {
+                *slot = (m * s.fb) + (x * s.fb) * 0.5;
                 y = m;
-            } else if (!ALLFAST && s.live) {
-                if (s.ph >= s.size) s.ph = 0;
-                const int idx = min(max(s.ph, 0), d.taps - 1);     // size <= taps is enforced when the parameter is set
-                double* slot = d.ring + dl_slot(V, v, idx);
-                const double m = *slot;
-                if (d.from_position) {
-                    // maxiDelayline::dlFromPosition, src/maximilian.cpp:431-439: the output comes from `position`, the
-                    // write has chandiv (== 1) where dl() has 0.5
-                    int pos = s.pos;
-                    if (pos >= s.size) pos = 0;
-                    y = d.ring[dl_slot(V, v, min(max(pos, 0), d.taps - 1))];
-                    *slot = (m * s.fb) + (x * s.fb) * 1.0;
-                } else {
-                    *slot = (m * s.fb) + (x * s.fb) * 0.5;
-                    y = m;
-                }
-                s.ph += 1;
             }
-            if (OUTMODE == DL_OUT_F64) { if (s.live) __stcs(out64, y); out64 += V; }
-            if (OUTMODE == DL_OUT_F32) { if (s.live) __stcs(out32, (float)y); out32 += V; }
-            if (MIX) {
-                mixtile[(0 * kMixTT + jj) * 33 + lane] = y * s.gl;
-                mixtile[(1 * kMixTT + jj) * 33 + lane] = y * s.gr;
-            }
+            s.ph += 1;
         }
+        if (OUTMODE == DL_OUT_F64) { if (s.live) __stcs(out64, y); out64 += V; }
+        if (OUTMODE == DL_OUT_F32) { if (s.live) __stcs(out32, (float)y); out32 += V; }
         if (MIX) {
-            __syncwarp();
-            const int ch = lane >> 4, rw = lane & 15;
-            if (rw < hn) {
-                const double* r = mixtile + (ch * kMixTT + rw) * 33;
-                double acc = 0.0;
-#pragma unroll
-                for (int q = 0; q < 32; ++q) acc += r[q];
-                a.partials[((size_t)(t0 + h0 + rw) * 2 + ch) * (size_t)a.W + (size_t)gwarp] = acc;
-            }
-            __syncwarp();
+            mixtile[(0 * kMixTT + j) * 33 + lane] = y * s.gl;
+            mixtile[(1 * kMixTT + j) * 33 + lane] = y * s.gr;
         }
+    }
+    if (MIX) {
+        __syncwarp();
+        const int ch = lane >> 4, rw = lane & 15;
+        if (rw < tn) {
+            const double* r = mixtile + (ch * kMixTT + rw) * 33;
+            double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;       // fixed order: deterministic
+#pragma unroll
+            for (int q = 0; q < 32; q += 4) { s0 += r[q]; s1 += r[q + 1]; s2 += r[q + 2]; s3 += r[q + 3]; }
+            a.partials[((size_t)(t0 + rw) * 2 + ch) * (size_t)a.W + (size_t)gwarp] = (s0 + s1) + (s2 + s3);
+        }
+        __syncwarp();
     }
 }
 
@@ -166,101 +167,96 @@ __global__ void __launch_bounds__(kBankBlock) delay_bank_kernel(const BankArgs a
     // ring index of the first access of the next window: the reference tests `phase >= size` before it reads
     int base = (s.ph >= s.size) ? 0 : s.ph;
 
-    const int nstages = (a.n_frames + kDlChunk - 1) / kDlChunk;
+    const int nstages = (a.n_frames + kDlT - 1) / kDlT;
     const int size0 = __shfl_sync(kFull, s.size, 0), base0 = __shfl_sync(kFull, base, 0);     // lane 0 is always live
     const bool uniform = __all_sync(kFull, !s.live || (s.fast && s.size == size0 && base == base0)) &&
-                         (size0 & 31) == 0 && (base0 & 31) == 0;
+                         (size0 & (kDlT - 1)) == 0 && (base0 & (kDlT - 1)) == 0;
     const int nlive = __popc(__ballot_sync(kFull, s.live));
+    const int sl = lane & (kDlT - 1), hv = lane >> kDlShift;        // slot within a window / which voice of a request
 
     if (uniform) {
-        // ---------------- all windows of the warp form one contiguous run of nlive * 256 B ----------------
-        const int nchunks = size0 >> 5;
-        int chunk = base0 >> 5;
-        auto run = [&](int c) { return d.ring + ((size_t)c * V + (size_t)v0) * kDlChunk + lane; };
+        // ---------------- all windows of the warp form one contiguous run of nlive * 128 B ----------------
+        const int nchunks = size0 >> kDlShift;
+        int chunk = base0 >> kDlShift;
+        const int nreq = (nlive + kDlVoicesPerReq - 1) / kDlVoicesPerReq;
         auto load_run = [&](double* buf, int c) {
-            const double* src = run(c);
-            double* dst = buf + lane;
+            // voice i = 2*q + hv of request q: global run + i*16 + slot, tile row i
+            const double* src = d.ring + ((size_t)c * V + (size_t)v0) * kDlChunk + (size_t)hv * kDlChunk + sl;
+            double* dst = buf + hv * kDlRow + sl;
 #pragma unroll 8
-            for (int i = 0; i < nlive; ++i) cp_async8(dst + i * 33, src + i * kDlChunk);
+            for (int q = 0; q < nreq; ++q)
+                if (kDlVoicesPerReq * q + hv < nlive) cp_async8(dst + q * kDlVoicesPerReq * kDlRow, src + (size_t)q * kDlVoicesPerReq * kDlChunk);
         };
-        if (kDlStages == 2) { load_run(wsm, chunk); cp_async_commit(); }
+        load_run(wsm, chunk);
+        cp_async_commit();
         for (int k = 0; k < nstages; ++k) {
-            double* buf = wsm + (kDlStages == 2 ? (k & 1) * kStageDoubles : 0);
-            const int t0 = k * kDlChunk;
-            const int tn = min(kDlChunk, a.n_frames - t0);
+            double* buf = wsm + (k & 1) * kStageDoubles;
+            const int t0 = k * kDlT;
+            const int tn = min(kDlT, a.n_frames - t0);
             int next_chunk = chunk + 1;
             if (next_chunk >= nchunks) next_chunk = 0;
-            if (kDlStages == 2) {
-                if (k + 1 < nstages) load_run(wsm + ((k + 1) & 1) * kStageDoubles, next_chunk);
-                cp_async_commit();
-                cp_async_wait1();      // everything but the newest group has landed: stage k is in smem
-            } else {
-                load_run(buf, chunk);
-                cp_async_commit();
-                cp_async_wait0();
-            }
+            if (k + 1 < nstages) load_run(wsm + ((k + 1) & 1) * kStageDoubles, next_chunk);
+            cp_async_commit();
+            cp_async_wait1();          // everything but the newest group has landed: window k is in smem
             __syncwarp();
-            dl_stage<OSC, FILT, ENV, true, OUTMODE, MIX>(s, buf + lane * 33, tn, t0, a, d, V, (size_t)vv, lane, gwarp, mixtile);
+            dl_stage<OSC, FILT, ENV, true, OUTMODE, MIX>(s, buf + lane * kDlRow, tn, t0, a, d, V, (size_t)vv, lane, gwarp, mixtile);
             __syncwarp();
-            if (lane < tn) {
-                double* dstg = d.ring + ((size_t)chunk * V + (size_t)v0) * kDlChunk + lane;
-                const double* srcs = buf + lane;
+            if (sl < tn) {
+                double* dstg = d.ring + ((size_t)chunk * V + (size_t)v0) * kDlChunk + (size_t)hv * kDlChunk + sl;
+                const double* srcs = buf + hv * kDlRow + sl;
 #pragma unroll 8
-                for (int i = 0; i < nlive; ++i) dstg[i * kDlChunk] = srcs[i * 33];
+                for (int q = 0; q < nreq; ++q)
+                    if (kDlVoicesPerReq * q + hv < nlive) dstg[(size_t)q * kDlVoicesPerReq * kDlChunk] = srcs[q * kDlVoicesPerReq * kDlRow];
             }
             __syncwarp();
             chunk = next_chunk;
         }
-        // phase += 1 after the last access: the window of the last stage started at slot 32*last_chunk
+        // phase += 1 after the last access: the window of the last stage started at slot 16*last_chunk
         if (s.live) {
-            int last_chunk = (base0 >> 5) + (nstages - 1);
+            int last_chunk = (base0 >> kDlShift) + (nstages - 1);
             last_chunk %= nchunks;
-            const int tn_last = a.n_frames - (nstages - 1) * kDlChunk;
-            s.ph = last_chunk * kDlChunk + tn_last;
+            const int tn_last = a.n_frames - (nstages - 1) * kDlT;
+            s.ph = last_chunk * kDlT + tn_last;
         }
     } else {
         // ---------------- generic: per-voice size and phase ----------------
         auto issue_loads = [&](double* buf, int wbase) {
 #pragma unroll 4
-            for (int i = 0; i < 32; ++i) {
+            for (int q = 0; q < 32 / kDlVoicesPerReq; ++q) {
+                const int i = kDlVoicesPerReq * q + hv;                    // the voice this lane serves in request q
                 const int f_i = __shfl_sync(kFull, (int)s.fast, i);
-                if (!f_i) continue;
                 const int b_i = __shfl_sync(kFull, wbase, i);
                 const int s_i = __shfl_sync(kFull, s.size, i);
-                int r = b_i + lane;
+                if (!f_i) continue;
+                int r = b_i + sl;
                 if (r >= s_i) r -= s_i;
-                cp_async8(buf + i * 33 + lane, d.ring + dl_slot(V, (size_t)(v0 + i), r));
+                cp_async8(buf + i * kDlRow + sl, d.ring + dl_slot(V, (size_t)(v0 + i), r));
             }
         };
-        if (kDlStages == 2) { issue_loads(wsm, base); cp_async_commit(); }
+        issue_loads(wsm, base);
+        cp_async_commit();
         for (int k = 0; k < nstages; ++k) {
-            double* buf = wsm + (kDlStages == 2 ? (k & 1) * kStageDoubles : 0);
-            const int t0 = k * kDlChunk;
-            const int tn = min(kDlChunk, a.n_frames - t0);
-            int next_base = base + kDlChunk;
+            double* buf = wsm + (k & 1) * kStageDoubles;
+            const int t0 = k * kDlT;
+            const int tn = min(kDlT, a.n_frames - t0);
+            int next_base = base + kDlT;
             if (s.fast && next_base >= s.size) next_base -= s.size;
-            if (kDlStages == 2) {
-                if (k + 1 < nstages) issue_loads(wsm + ((k + 1) & 1) * kStageDoubles, next_base);
-                cp_async_commit();
-                cp_async_wait1();
-            } else {
-                issue_loads(buf, base);
-                cp_async_commit();
-                cp_async_wait0();
-            }
+            if (k + 1 < nstages) issue_loads(wsm + ((k + 1) & 1) * kStageDoubles, next_base);
+            cp_async_commit();
+            cp_async_wait1();
             __syncwarp();
-            dl_stage<OSC, FILT, ENV, false, OUTMODE, MIX>(s, buf + lane * 33, tn, t0, a, d, V, (size_t)vv, lane, gwarp, mixtile);
+            dl_stage<OSC, FILT, ENV, false, OUTMODE, MIX>(s, buf + lane * kDlRow, tn, t0, a, d, V, (size_t)vv, lane, gwarp, mixtile);
             __syncwarp();
 #pragma unroll 4
-            for (int i = 0; i < 32; ++i) {
+            for (int q = 0; q < 32 / kDlVoicesPerReq; ++q) {
+                const int i = kDlVoicesPerReq * q + hv;
                 const int f_i = __shfl_sync(kFull, (int)s.fast, i);
-                if (!f_i) continue;
                 const int b_i = __shfl_sync(kFull, base, i);
                 const int s_i = __shfl_sync(kFull, s.size, i);
-                if (lane < tn) {
-                    int r = b_i + lane;
+                if (f_i && sl < tn) {
+                    int r = b_i + sl;
                     if (r >= s_i) r -= s_i;
-                    d.ring[dl_slot(V, (size_t)(v0 + i), r)] = buf[i * 33 + lane];
+                    d.ring[dl_slot(V, (size_t)(v0 + i), r)] = buf[i * kDlRow + sl];
                 }
             }
             __syncwarp();
@@ -268,7 +264,7 @@ __global__ void __launch_bounds__(kBankBlock) delay_bank_kernel(const BankArgs a
                 int last = base + tn - 1;
                 if (last >= s.size) last -= s.size;
                 s.ph = last + 1;                     // phase += 1 after the last access of the window
-                base = (tn == kDlChunk) ? next_base : ((s.ph >= s.size) ? 0 : s.ph);
+                base = (tn == kDlT) ? next_base : ((s.ph >= s.size) ? 0 : s.ph);
             }
         }
     }

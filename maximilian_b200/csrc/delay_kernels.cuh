@@ -5,14 +5,15 @@
 
 namespace mxb {
 
-constexpr int kDlChunk = 32;     // ring slots per chunk = time steps per staged window
+constexpr int kDlShift = 4;
+constexpr int kDlChunk = 1 << kDlShift;     // ring slots per chunk = time steps per staged window (16)
 
-// Ring storage is chunk-interleaved: slot r of voice v lives at ((r / 32) * V + v) * 32 + r % 32.
-// A voice's 32-slot chunk is 256 contiguous bytes (full sectors whatever its phase), and voices whose
+// Ring storage is chunk-interleaved: slot r of voice v lives at ((r / 16) * V + v) * 16 + r % 16.
+// A voice's 16-slot chunk is 128 contiguous bytes (4 full sectors whatever its phase), and voices whose
 // ring indices run in step -- the common case: same size, started together -- read and write one
-// contiguous run of 32 * 256 B per warp and stage, i.e. streaming DRAM access.
+// contiguous run of 32 * 128 B per warp and stage, i.e. streaming DRAM access.
 __host__ __device__ inline size_t dl_slot(size_t V, size_t v, int r) {
-    return (((size_t)(r >> 5)) * V + v) * kDlChunk + (size_t)(r & 31);
+    return (((size_t)(r >> kDlShift)) * V + v) * kDlChunk + (size_t)(r & (kDlChunk - 1));
 }
 inline size_t dl_ring_doubles(size_t V, int taps) { return (size_t)((taps + kDlChunk - 1) / kDlChunk) * kDlChunk * V; }
 
