@@ -5,13 +5,18 @@
 
 A "step" is one block (1024 frames) of one bank: BASELINE.json configs[1] by default -- 1 Mi voices of
 maxiOsc::saw -> maxiSVF (low-pass mix), per-voice fp64 output materialised time-major in HBM. With N > 1
-(launched by torch.distributed.run, one rank per GPU) every rank owns its own 1 Mi voices (weak scaling)
-and the per-block stereo mix bus [1024][2] is sum-all-reduced over NCCL -- the path's only exchange step.
+(launched by torch.distributed.run, one rank per GPU) every rank owns its own 1 Mi voices (weak scaling);
+voices are independent, so the headline block has no collective at any N.
 
   value      voice-samples/s of the whole job, inputs and state resident in HBM, CUDA-event timed, max over ranks
+  mixdown    BASELINE.json configs[4] in "mix mode" (SURVEY.md 8(d) config 5), timed separately in the same run:
+             1 Mi voices/GPU saw -> maxiBiquad -> maxiMix::stereo -> sum over voices, only the stereo bus is
+             written; for N > 1 the bus is summed over the GPUs -- the path's only exchange step (--collective
+             p2p: peer-memory exchange fused into the mix-reduce kernel; nccl: all_reduce). fp64-pipe bound,
+             reported as such. `--mix 1` instead adds the bus to the headline block (output AND bus).
   e2e        the same block through the C ABI with HOST control data: per step one fp64 frequency array
-             (8 MiB) is uploaded with mxb_bank_set_param from pinned memory and the stereo mix (16 KiB) is
-             read back by mxb_bank_process(MXB_MEM_SPLIT); the voice signals stay on the device
+             (8 MiB) is uploaded stream-ordered with mxb_bank_set_param_async from pinned memory and the stereo
+             mix (16 KiB) is read back by mxb_bank_process(MXB_MEM_SPLIT); the voice signals stay on the device
   roofline   algorithmic bytes per launch / CUDA-event launch time against MEASURED_PEAKS.json
   cpu_baseline  the reference's own scalar code (oracle/_ref, or the C port) on all host cores, bounded sample
 
@@ -53,6 +58,17 @@ def load_peaks():
         except Exception:
             pass
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def load_traffic(key):
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the dominant kernel of workload `key`,
+    from the committed `ncu --set full` capture of this same bench command (profiles/traffic.json names the summary
+    file each figure was read from). None when no capture of that configuration is committed."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))[key]
+        return {"traffic": float(d["dram_bytes_per_launch"]), "traffic_unit": "bytes/launch", "traffic_source": d["source"]}
+    except Exception:
+        return {"traffic": None}
 
 
 class ClockSampler:
@@ -198,6 +214,61 @@ def reference_arm(args, wl_name, wl):
 
 # ------------------------------------------------------------------------------------------------ GPU leg
 
+def measure_mixdown(args, torch, dist, capi, W, ctx, dev, rank, world, mix, stream, barrier, sm_mhz):
+    """BASELINE.json configs[4] in SURVEY.md 8(d)'s "mix mode", one shard per GPU: 1 Mi voices maxiOsc::saw ->
+    maxiBiquad -> maxiMix::stereo -> sum over voices; no per-voice output is written, the stereo bus [1024][2] is the
+    result. With N > 1 the bus is summed over the GPUs (the path's only exchange step). The kernel moves 0.1 B per
+    voice-sample, so it is reported against the fp64 pipe, not against HBM; it is never
+    mixed into the headline."""
+    wl = WORKLOADS["biquad"]
+    V = wl["voices"]
+    p = W.voice_params(V, seed=W.SEED + 100 + rank)
+    bank = capi.Bank(V, osc=wl["osc"], filt=wl["filt"], env=False, delay=False, delay_capacity=1, max_frames=BLOCK,
+                     ctx=ctx, sample_rate=SR)
+    W.configure_bank(bank, wl["filt"], p, False, False)
+    p2p = world > 1 and args.collective == "p2p"
+    if p2p:
+        exch = capi.Exchange(ctx, rank, world, max_doubles=2 * BLOCK)
+        exch.connect_with_torch_distributed()      # the IPC handles travel over the process group; the data never does
+        exch.attach(bank)
+    steps = max(3, min(args.steps, 50))
+
+    def step():
+        bank.process_device(BLOCK, out_ptr=None, mix_ptr=mix.data_ptr(), stream=stream.cuda_stream)
+        if world > 1 and not p2p:
+            dist.all_reduce(mix)
+
+    for _ in range(3):
+        step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(steps):
+        step()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item()) / steps
+    # fp64-pipe instructions per voice-sample in the SASS of this instantiation: saw 3 (DSETP, 2 DADD), biquad 9
+    # (5 DMUL, 4 DADD: -fmad=false keeps the reference's roundings), mix 2 (DMUL/DFMA per channel) + 1 (row sums)
+    instr = 15.0
+    rate = instr * V * BLOCK / (ms * 1e-3)                    # fp64 lane-instructions per second per GPU
+    pipe_peak = 148 * 64 * (sm_mhz or 1920.0) * 1e6           # 64 fp64 lanes per SM (16 per sub-partition), one instr per lane-clock
+    res = {"workload": "configs[4] shard, mix mode: 1Mi voices/GPU maxiOsc::saw -> maxiBiquad lowpass -> maxiMix::stereo -> sum over voices, "
+                       "stereo bus [1024][2] fp64 per block, no per-voice output",
+           "value": world * V * BLOCK / (ms * 1e-3), "unit": "samples/s", "ms_per_step": ms, "steps": steps,
+           "bound": "fp64 pipe", "fp64_instr_per_voice_sample": instr, "fp64_pipe_frac_per_gpu": rate / pipe_peak,
+           "fp64_pipe_peak": "148 SMs x 64 lanes x %.0f MHz (sampled SM clock)" % (sm_mhz or 1920.0),
+           "collective": ("none (one GPU)" if world == 1 else
+                          "peer-memory exchange of mix[1024][2] fp64 fused into the mix-reduce kernel (CUDA IPC over NVLink, rank-ordered sum)"
+                          if p2p else "NCCL sum all-reduce of mix[1024][2] fp64 per block")}
+    del bank
+    return res
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -205,7 +276,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--workload", default="svf", choices=sorted(WORKLOADS) + ["mfcc"])
-    ap.add_argument("--mix", type=int, default=-1, help="1: also produce the stereo mix bus each block (default: only when gpus > 1)")
+    ap.add_argument("--mix", type=int, default=-1,
+                    help="1: the timed block also produces the stereo mix bus (+ the cross-GPU mix-down when gpus > 1). Default: the "
+                         "headline block is the configured chain alone (same work at every N) and the mix-down configuration "
+                         "(configs[4]) is timed separately and reported under 'mixdown'")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--f32-out", action="store_true", help="store the materialised output as fp32 (declared in the JSON)")
     ap.add_argument("--collective", default="p2p", choices=["p2p", "nccl"],
@@ -231,7 +305,7 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    want_mix = (args.mix == 1) or (args.mix < 0 and world > 1)
+    want_mix = args.mix == 1
 
     V = wl["voices"]
     p = W.voice_params(V, seed=W.SEED + rank, delay_size=wl["delay"] or 4096)
@@ -302,6 +376,14 @@ def main():
         sampler.stop()
         clocks = sampler.summary(t_wall0, t_wall1)
 
+    # ---- configs[4] shard: osc -> maxiBiquad + stereo mix bus (+ cross-GPU mix-down), timed on its own -------
+    mixdown = None
+    if args.mix < 0 and not wl["delay"]:
+        mhz = torch.tensor([float((clocks or {}).get("sm_mhz") or 0.0)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.broadcast(mhz, 0)
+        mixdown = measure_mixdown(args, torch, dist, capi, W, ctx, dev, rank, world, mix, stream, barrier, float(mhz.item()) or None)
+
     # ---- end to end through the C ABI with host control data ------------------------------------------------
     freq_host = torch.from_numpy(p["freq"].copy()).pin_memory()
     mix_host = torch.zeros((BLOCK, 2), dtype=torch.float64).pin_memory()
@@ -353,13 +435,17 @@ def main():
                                       else "NCCL sum all-reduce of mix[1024][2] fp64 per block"),
                        "l2": "no flush needed: each step writes %.1f GB, inputs+outputs >> 126 MB L2" % (samples_per_step * (4 if args.f32_out else 8) / 1e9)},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "kernel": "bank_kernel" if not wl["delay"] else "delay_bank_kernel",
+                         **load_traffic(args.workload + ("_mix" if want_mix else "") + ("_f32" if args.f32_out else "")),
+                         "algorithmic_bytes_per_launch": bytes_per * samples_per_step,
+                         "peak_source": peak_src, "kernel": "bank_kernel" if not wl["delay"] else "delay_bank_kernel",
                          "algorithmic_bytes_per_voice_sample": bytes_per, "launch_ms_avg": avg_ms, "launch_ms_median": med_ms},
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "what": "mxb_bank_set_param(freq, pinned host) + mxb_bank_process(MXB_MEM_SPLIT): "
                                                  "host gates in, host mix out, voice signals materialised on the device"},
             "gpu_launches": launches, "clocks": clocks,
         }
+        if mixdown is not None:
+            line["mixdown"] = mixdown
         if not args.no_cpu and world == 1:
             line["cpu_baseline"] = cpu_baseline(wl)
         print(json.dumps(line), flush=True)
@@ -514,7 +600,8 @@ def main_mfcc(args):
                 "data": "synthetic",
                 "config": {"workload": wl["desc"], "channels_per_gpu": C, "parallelism": f"channels sharded x{world}", "collective": "none",
                            "l2": "per step 134 MB of samples in + 268 MB of assembly state r/w + 21 MB out: larger than the 126 MB L2"},
-                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, **load_traffic("mfcc"),
+                             "algorithmic_bytes_per_launch": wl["bytes_per"] * C,
                              "peak_source": peak_src, "kernel": "stft_kernel", "algorithmic_bytes_per_frame": wl["bytes_per"],
                              "launch_ms_avg": avg_ms, "note": "ALU/shuffle bound by design of the reference transform (fp32 radix-2 + fp64 mel/DCT); "
                                                             "HBM fraction is reported as north_star asks, not expected to be high"},
