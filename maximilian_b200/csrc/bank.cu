@@ -169,9 +169,9 @@ __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned l
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
-// K3 + K6 in one kernel: the local reduction of the per-warp partials (as mix_reduce_kernel) lands in this rank's slot
-// of the peer-mapped exchange buffer; the last CTA to finish publishes the slot, waits for every peer's flag and
-// adds the peers' buses, read straight from their HBM over NVLink, in rank order (protocol: exchange.cu).
+// K3 + K6 in one kernel: every row sum of the local reduction (as mix_reduce_kernel) is PUSHED into this rank's lane
+// of every rank's exchange buffer over NVLink (posted stores); the last CTA to finish publishes the flags, waits on
+// its own (local) flags for every peer and adds the world buses in rank order (protocol: exchange.cu).
 __global__ void mix_reduce_exchange_kernel(const double* __restrict__ partials, double* __restrict__ mix, int rows, int W, const ExchDev x) {
     const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
@@ -181,26 +181,25 @@ __global__ void mix_reduce_exchange_kernel(const double* __restrict__ partials, 
         for (int w = lane; w < W; w += 32) s += p[w];
 #pragma unroll
         for (int m = 16; m >= 1; m >>= 1) s += __shfl_xor_sync(0xffffffffu, s, m);
-        if (lane == 0) x.local_payload[row] = s;
+        if (lane < x.world) x.dst_payload[lane][row] = s;          // lane r -> rank r's buffer (xor tree: every lane holds s)
     }
     __shared__ bool last;
-    __threadfence();
+    __threadfence_system();                           // this CTA's peer stores are ordered before its ticket
     __syncthreads();
     if (threadIdx.x == 0) last = atomicAdd(x.ticket, 1u) == gridDim.x - 1;
     __syncthreads();
     if (!last) return;
-    if (threadIdx.x == 0) {
-        __threadfence_system();                       // cumulative: the other CTAs' rows were ordered before their ticket
-        st_release_sys(x.local_flag, x.seq1);
-        for (int r = 0; r < x.world; ++r)
-            if (r != x.rank) while (ld_acquire_sys(x.peer_flag[r]) < x.seq1) { }
-        *x.ticket = 0;
+    if (threadIdx.x < x.world) {
+        __threadfence_system();                       // cumulative: the other CTAs' stores were ordered before their tickets
+        st_release_sys(x.dst_flag[threadIdx.x], x.seq1);
+        while (ld_acquire_sys(x.src_flags + (size_t)threadIdx.x * (kExchFlagBytes / sizeof(unsigned long long))) < x.seq1) { }
     }
+    if (threadIdx.x == 0) *x.ticket = 0;
     __syncthreads();
     for (int i = threadIdx.x; i < rows; i += blockDim.x) {
         double s = 0.0;
         for (int r = 0; r < x.world; ++r)             // rank order on every rank: identical bits everywhere, every run
-            s += (r == x.rank) ? __ldcg(x.local_payload + i) : __ldcv(x.peer_payload[r] + i);
+            s += __ldcg(x.src_payload + (size_t)r * (size_t)x.stride + i);
         mix[i] = s;
     }
 }

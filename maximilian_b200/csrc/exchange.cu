@@ -1,11 +1,14 @@
 // mxb_exchange: symmetric peer-memory buffers for the mix-bus all-reduce (see exchange.cuh, bank.cu).
 //
-// Protocol (per call, sequence number s, slot = s & 1, one buffer of two slots per rank, all peer-mapped with CUDA IPC):
-//   1. every rank writes its locally reduced bus into its own slot, then publishes flag[slot] = s + 1 (release, system scope)
-//   2. every rank waits until each peer's flag[slot] >= s + 1 (acquire, system scope), reads the peers' payloads over
-//      NVLink and adds them IN RANK ORDER -- every rank computes the same sum, bit for bit, run after run
-//   3. slot reuse at call s + 2 is safe: during call s + 1 this rank saw every peer's flag reach s + 2, i.e. every peer
-//      had started call s + 1 and therefore finished reading slot(s) (stream order on the peer)
+// Protocol (per call, sequence number s, slot = s & 1; every rank owns flags[world] + payload[2 slots][world][n], all
+// peer-mapped with CUDA IPC). PUSH model -- nothing is ever read over NVLink, nobody polls remote memory:
+//   1. every rank stores each locally reduced bus value into payload[slot][its rank] of EVERY rank's buffer (posted
+//      peer stores, issued by the reducing warps as they finish), then -- once all of its CTAs are done -- publishes
+//      flags[its rank] = s + 1 in every rank's buffer (release, system scope)
+//   2. every rank waits on its OWN flags (local polling, acquire, system scope) until all of them reach s + 1 and adds
+//      the world buses, all in local HBM, IN RANK ORDER -- every rank computes the same sum, bit for bit, every run
+//   3. slot reuse at call s + 2 is safe: a rank finishes call s + 1 only after every peer's flag reached s + 2, i.e.
+//      after every peer had launched call s + 1 and therefore finished reading slot(s) (stream order on the peer)
 // One kernel does the local reduction and the exchange (bank.cu: mix_reduce_exchange_kernel); nothing here calls NCCL.
 #include <new>
 
@@ -17,16 +20,14 @@ namespace mxb {
 ExchDev exchange_next(mxb_exchange* ex) {
     ExchDev d;
     memset(&d, 0, sizeof(d));
-    const int slot = (int)(ex->seq & 1);
-    d.rank = ex->rank; d.world = ex->world; d.seq1 = ex->seq + 1; d.ticket = ex->ticket;
+    const size_t slot_off = ex->flags_bytes + (size_t)(ex->seq & 1) * ex->slot_bytes;
+    d.rank = ex->rank; d.world = ex->world; d.stride = ex->max_doubles; d.seq1 = ex->seq + 1; d.ticket = ex->ticket;
     for (int r = 0; r < ex->world; ++r) {
-        unsigned char* base = ex->peers[r] + (size_t)slot * ex->slot_bytes;
-        d.peer_flag[r] = (const unsigned long long*)base;
-        d.peer_payload[r] = (const double*)(base + kExchFlagBytes);
+        d.dst_flag[r] = (unsigned long long*)(ex->peers[r] + (size_t)ex->rank * kExchFlagBytes);
+        d.dst_payload[r] = (double*)(ex->peers[r] + slot_off) + (size_t)ex->rank * (size_t)ex->max_doubles;
     }
-    unsigned char* mine = ex->local + (size_t)slot * ex->slot_bytes;
-    d.local_flag = (unsigned long long*)mine;
-    d.local_payload = (double*)(mine + kExchFlagBytes);
+    d.src_flags = (const unsigned long long*)ex->local;
+    d.src_payload = (const double*)(ex->local + slot_off);
     ex->seq += 1;
     return d;
 }
@@ -44,12 +45,14 @@ int32_t mxb_exchange_create(mxb_ctx* ctx, int32_t rank, int32_t world, int32_t m
     MXB_REQUIRE(ex, MXB_ERR_ALLOC, "mxb_exchange_create: out of host memory");
     memset(ex, 0, sizeof(*ex));
     ex->ctx = ctx; ex->rank = rank; ex->world = world; ex->max_doubles = max_doubles;
-    ex->slot_bytes = ((size_t)kExchFlagBytes + sizeof(double) * (size_t)max_doubles + 127) & ~(size_t)127;
+    ex->flags_bytes = (size_t)kExchMaxWorld * kExchFlagBytes;
+    ex->slot_bytes = (sizeof(double) * (size_t)max_doubles * (size_t)world + 127) & ~(size_t)127;
+    const size_t total = ex->flags_bytes + 2 * ex->slot_bytes;
     void* p = nullptr;
-    cudaError_t e = cudaMalloc(&p, 2 * ex->slot_bytes);      // plain cudaMalloc: exportable with cudaIpcGetMemHandle
+    cudaError_t e = cudaMalloc(&p, total);                   // plain cudaMalloc: exportable with cudaIpcGetMemHandle
     if (e != cudaSuccess) { set_error("mxb_exchange_create: cudaMalloc: %s", cudaGetErrorString(e)); delete ex; return MXB_ERR_ALLOC; }
     ex->local = (unsigned char*)p;
-    e = cudaMemset(p, 0, 2 * ex->slot_bytes);
+    e = cudaMemset(p, 0, total);
     if (e == cudaSuccess) e = cudaMalloc((void**)&ex->ticket, sizeof(unsigned int));
     if (e == cudaSuccess) e = cudaMemset(ex->ticket, 0, sizeof(unsigned int));
     if (e != cudaSuccess) { set_error("mxb_exchange_create: %s", cudaGetErrorString(e)); cudaFree(p); delete ex; return MXB_ERR_CUDA; }
