@@ -146,18 +146,29 @@ int redesign(mxb_bank* b) {
     return MXB_OK;
 }
 
-__global__ void mix_reduce_kernel(const double* __restrict__ partials, double* __restrict__ mix, int rows, int W) {
-    // one warp per (frame, channel) row: lanes take a strided subset of the per-warp partial sums in
-    // ascending order, then a fixed xor tree -- the summation order never changes between runs.
-    const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (row >= rows) return;
-    const double* p = partials + (size_t)row * (size_t)W;
-    double s = 0.0;
-    for (int w = lane; w < W; w += 32) s += p[w];
+constexpr int kMixReduceThreads = 128;
+
+// Sum of one (frame, channel) row of per-warp partials by one CTA: every thread adds a strided subset in ascending
+// order (two interleaved chains), a fixed xor tree per warp, then the four warp sums in a fixed order -- the
+// summation order never changes between runs. Returned to every thread of warp 0; other warps get 0.
+__device__ __forceinline__ double mix_row_sum(const double* __restrict__ p, const int W, double* sm) {
+    double s0 = 0.0, s1 = 0.0;
+    int w = threadIdx.x;
+    for (; w + kMixReduceThreads < W; w += 2 * kMixReduceThreads) { s0 += p[w]; s1 += p[w + kMixReduceThreads]; }
+    if (w < W) s0 += p[w];
+    double s = s0 + s1;
 #pragma unroll
     for (int m = 16; m >= 1; m >>= 1) s += __shfl_xor_sync(0xffffffffu, s, m);
-    if (lane == 0) mix[row] = s;
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = s;
+    __syncthreads();
+    return threadIdx.x < 32 ? (sm[0] + sm[1]) + (sm[2] + sm[3]) : 0.0;
+}
+
+__global__ void __launch_bounds__(kMixReduceThreads) mix_reduce_kernel(const double* __restrict__ partials, double* __restrict__ mix, int rows, int W) {
+    __shared__ double sm[kMixReduceThreads / 32];
+    const int row = blockIdx.x;                       // one CTA per row: rows CTAs keep enough loads in flight for HBM
+    const double s = mix_row_sum(partials + (size_t)row * (size_t)W, W, sm);
+    if (threadIdx.x == 0) mix[row] = s;
 }
 
 __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
@@ -172,17 +183,11 @@ __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned l
 // K3 + K6 in one kernel: every row sum of the local reduction (as mix_reduce_kernel) is PUSHED into this rank's lane
 // of every rank's exchange buffer over NVLink (posted stores); the last CTA to finish publishes the flags, waits on
 // its own (local) flags for every peer and adds the world buses in rank order (protocol: exchange.cu).
-__global__ void mix_reduce_exchange_kernel(const double* __restrict__ partials, double* __restrict__ mix, int rows, int W, const ExchDev x) {
-    const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (row < rows) {
-        const double* p = partials + (size_t)row * (size_t)W;
-        double s = 0.0;
-        for (int w = lane; w < W; w += 32) s += p[w];
-#pragma unroll
-        for (int m = 16; m >= 1; m >>= 1) s += __shfl_xor_sync(0xffffffffu, s, m);
-        if (lane < x.world) x.dst_payload[lane][row] = s;          // lane r -> rank r's buffer (xor tree: every lane holds s)
-    }
+__global__ void __launch_bounds__(kMixReduceThreads) mix_reduce_exchange_kernel(const double* __restrict__ partials, double* __restrict__ mix, int rows, int W, const ExchDev x) {
+    __shared__ double sm[kMixReduceThreads / 32];
+    const int row = blockIdx.x;
+    const double s = mix_row_sum(partials + (size_t)row * (size_t)W, W, sm);
+    if (threadIdx.x < x.world) x.dst_payload[threadIdx.x][row] = s;      // thread r -> rank r's buffer
     __shared__ bool last;
     __threadfence_system();                           // this CTA's peer stores are ordered before its ticket
     __syncthreads();
@@ -552,7 +557,7 @@ int32_t mxb_bank_process_fm(mxb_bank* b, int32_t n_frames, const double* freq_tv
     b->launches += 1;
     if (mix) {
         const int rows = n_frames * 2;
-        const int threads = 256, blocks = (rows * 32 + threads - 1) / threads;
+        const int threads = kMixReduceThreads, blocks = rows;
         if (b->ex) {
             MXB_REQUIRE(b->ex->connected, MXB_ERR_STATE, "mxb_bank_process: the attached exchange is not connected to its peers");
             MXB_REQUIRE(rows <= b->ex->max_doubles, MXB_ERR_INVALID, "mxb_bank_process: exchange holds %d values, the bus needs %d", b->ex->max_doubles, rows);
