@@ -60,16 +60,24 @@ struct DlVoice {
 };
 
 // one window (<= 16 steps) of one voice against its staged row (ALLFAST) or, for short rings, against global memory
-template <int OSC, int FILT, int ENV, bool ALLFAST, int OUTMODE, bool MIX>
+// ESTEADY: every voice of the warp spends this whole window in one of the two steady states of maxiEnv::adsr (see
+// dl_window); `relmode` tells which one this lane is in.
+template <int OSC, int FILT, int ENV, bool ALLFAST, int OUTMODE, bool MIX, bool ESTEADY>
 __device__ __forceinline__ void dl_stage(DlVoice& s, double* row, const int tn, const int t0, const BankArgs& a, const DelayArgs& d,
-                                         const size_t V, const size_t v, const int lane, const int gwarp, double* mixtile) {
+                                         const size_t V, const size_t v, const int lane, const int gwarp, double* mixtile,
+                                         const bool relmode) {
     double* out64 = (double*)a.out + (size_t)t0 * V + v;
     float* out32 = (float*)a.out + (size_t)t0 * V + v;
 #pragma unroll 4
     for (int j = 0; j < tn; ++j) {
         const int t = t0 + j;
         double x = osc_tick<OSC>(s.phase, s.oout, s.inc, s.duty, a.osc_kind);
-        if (ENV) {
+        if (ENV && ESTEADY) {
+            // what env_tick() reduces to in the steady states -- same operands, same roundings
+            if (relmode) { if (s.er.amp > 0.) { s.er.amp *= s.er.rel; s.er.output = x * s.er.amp; } }
+            else s.er.output = x * s.er.amp;
+            x = s.er.output;
+        } else if (ENV) {
             const bool trig = t >= s.er.on && t < s.er.off;
             x = a.env_ar ? env_ar_tick(s.er, x, trig) : env_tick(s.er, x, trig);
         }
@@ -117,6 +125,30 @@ __device__ __forceinline__ void dl_stage(DlVoice& s, double* row, const int tn, 
         }
         __syncwarp();
     }
+}
+
+// One window of the warp. An ADSR envelope spends most of its life in two states in which maxiEnv::adsr
+// (src/maximilian.cpp:1415-1466) does nothing but multiply:
+//   release: no trigger, flags == {release}: `if (amplitude > 0) { amplitude *= release; output = input*amplitude; }`
+//   sustain: trigger held, flags == {hold}, holdcount >= holdtime: `output = input*amplitude`
+// (every other statement of the function is a no-op there: the first four tests fail on the flags, `holdphase = false;
+// releasephase = true` re-assigns what is already set). When the gate does not change inside the window and every
+// voice of the warp is in one of the two, the window runs those statements alone; otherwise the full state machine.
+template <int OSC, int FILT, int ENV, bool ALLFAST, int OUTMODE, bool MIX>
+__device__ __forceinline__ void dl_window(DlVoice& s, double* row, const int tn, const int t0, const BankArgs& a, const DelayArgs& d,
+                                          const size_t V, const size_t v, const int lane, const int gwarp, double* mixtile) {
+    if (ENV) {
+        const EnvRegs& e = s.er;
+        const bool notrig = e.off <= t0 || e.on >= t0 + tn || e.on >= e.off;
+        const bool alltrig = e.on <= t0 && e.off >= t0 + tn;
+        const bool relmode = e.st == ENV_R && notrig;
+        const bool susmode = e.st == ENV_H && e.holdcount >= e.holdtime && alltrig;
+        if (!a.env_ar && __all_sync(kFull, relmode || susmode || !s.live)) {
+            dl_stage<OSC, FILT, ENV, ALLFAST, OUTMODE, MIX, true>(s, row, tn, t0, a, d, V, v, lane, gwarp, mixtile, relmode);
+            return;
+        }
+    }
+    dl_stage<OSC, FILT, ENV, ALLFAST, OUTMODE, MIX, false>(s, row, tn, t0, a, d, V, v, lane, gwarp, mixtile, false);
 }
 
 template <int OSC, int FILT, int ENV, int OUTMODE, bool MIX>
@@ -183,6 +215,11 @@ __global__ void __launch_bounds__(kBankBlock) delay_bank_kernel(const BankArgs a
             // voice i = 2*q + hv of request q: global run + i*16 + slot, tile row i
             const double* src = d.ring + ((size_t)c * V + (size_t)v0) * kDlChunk + (size_t)hv * kDlChunk + sl;
             double* dst = buf + hv * kDlRow + sl;
+            if (nlive == 32) {           // full warp: 16 requests at compile-time offsets, no predicates
+#pragma unroll
+                for (int q = 0; q < 32 / kDlVoicesPerReq; ++q) cp_async8(dst + q * kDlVoicesPerReq * kDlRow, src + q * kDlVoicesPerReq * kDlChunk);
+                return;
+            }
 #pragma unroll 8
             for (int q = 0; q < nreq; ++q)
                 if (kDlVoicesPerReq * q + hv < nlive) cp_async8(dst + q * kDlVoicesPerReq * kDlRow, src + (size_t)q * kDlVoicesPerReq * kDlChunk);
@@ -199,9 +236,14 @@ __global__ void __launch_bounds__(kBankBlock) delay_bank_kernel(const BankArgs a
             cp_async_commit();
             cp_async_wait1();          // everything but the newest group has landed: window k is in smem
             __syncwarp();
-            dl_stage<OSC, FILT, ENV, true, OUTMODE, MIX>(s, buf + lane * kDlRow, tn, t0, a, d, V, (size_t)vv, lane, gwarp, mixtile);
+            dl_window<OSC, FILT, ENV, true, OUTMODE, MIX>(s, buf + lane * kDlRow, tn, t0, a, d, V, (size_t)vv, lane, gwarp, mixtile);
             __syncwarp();
-            if (sl < tn) {
+            if (nlive == 32 && tn == kDlT) {
+                double* dstg = d.ring + ((size_t)chunk * V + (size_t)v0) * kDlChunk + (size_t)hv * kDlChunk + sl;
+                const double* srcs = buf + hv * kDlRow + sl;
+#pragma unroll
+                for (int q = 0; q < 32 / kDlVoicesPerReq; ++q) dstg[q * kDlVoicesPerReq * kDlChunk] = srcs[q * kDlVoicesPerReq * kDlRow];
+            } else if (sl < tn) {
                 double* dstg = d.ring + ((size_t)chunk * V + (size_t)v0) * kDlChunk + (size_t)hv * kDlChunk + sl;
                 const double* srcs = buf + hv * kDlRow + sl;
 #pragma unroll 8
@@ -245,7 +287,7 @@ __global__ void __launch_bounds__(kBankBlock) delay_bank_kernel(const BankArgs a
             cp_async_commit();
             cp_async_wait1();
             __syncwarp();
-            dl_stage<OSC, FILT, ENV, false, OUTMODE, MIX>(s, buf + lane * kDlRow, tn, t0, a, d, V, (size_t)vv, lane, gwarp, mixtile);
+            dl_window<OSC, FILT, ENV, false, OUTMODE, MIX>(s, buf + lane * kDlRow, tn, t0, a, d, V, (size_t)vv, lane, gwarp, mixtile);
             __syncwarp();
 #pragma unroll 4
             for (int q = 0; q < 32 / kDlVoicesPerReq; ++q) {

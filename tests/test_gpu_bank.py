@@ -160,6 +160,37 @@ def test_delayline_index_exact(port, ragged, B):
         assert np.array_equal(g.ring(v, cap), o.ring(v, cap)), v
 
 
+@pytest.mark.parametrize("filt", ["none", "svf"])
+def test_delay_envelope_steady_windows(port, filt):
+    """K2 runs whole windows in which every voice of a warp sits in the sustain or the release state of maxiEnv::adsr
+    through two-statement shortcuts: gates held over whole blocks, releases that last for blocks, amplitudes that
+    underflow to exactly 0 (release 0.5 and 0.0), mixed with warps that are mid-attack -- all bit-identical."""
+    V, B, cap = 160, 256, 128
+    p = W.voice_params(V, seed=12, delay_size=cap)
+    g = gpu_bank(V, osc="saw", filt=filt, env=True, delay=True, delay_capacity=cap, max_frames=B)
+    o = port.Bank(V, osc="saw", filt=filt, env=True, delay=True, delay_capacity=cap)
+    W.configure_bank(g, filt, p, env=True, delay=True); W.configure_bank(o, filt, p, env=True, delay=True)
+    rng = np.random.default_rng(12)
+    att = np.where(np.arange(V) < 128, 0.5, 0.001)                 # warps 0-3 reach hold within a few steps, warp 4 never
+    dec = np.full(V, 0.5); sus = np.full(V, 0.3)
+    rel = np.choose(np.arange(V) % 4, [0.999, 0.5, 0.0, 0.9])
+    hold = np.choose(np.arange(V) % 3, [1.0, 5.0, 40.0])
+    for b in (g, o):
+        b.set("env_attack", att); b.set("env_decay", dec); b.set("env_sustain", sus); b.set("env_release", rel)
+        b.set("env_holdtime", hold)
+    t_on = rng.integers(0, 20, V).astype(np.int32); t_mid = rng.integers(40, 200, V).astype(np.int32)
+    zeros, full = np.zeros(V, np.int32), np.full(V, B, np.int32)
+    gates = [(t_on, full), (zeros, full), (zeros, full), (zeros, t_mid)] + [(zeros, zeros)] * 8
+    for blk, (on, off) in enumerate(gates):
+        og, _ = g.process(B, on, off); oo, _ = o.process(B, on, off)
+        _close(og, oo, False, f"steady blk{blk}")
+        for s in ("env_holdcount", "env_flags", "delay_phase"):
+            assert np.array_equal(g.get(s), o.get(s)), (blk, s)
+        for s in ("env_amplitude", "env_output"):
+            _close(g.get(s), o.get(s), False, s)
+    assert np.count_nonzero(g.get("env_amplitude") == 0.0) >= V // 4      # the release-to-zero case was reached
+
+
 def test_delay_with_filter_and_nonpositive_size(port):
     V, B, cap = 40, 130, 128
     p = W.voice_params(V, seed=8, delay_size=cap, ragged_delay=True)
