@@ -185,6 +185,20 @@ int32_t mxb_bank_process_fm(mxb_bank* bank, int32_t n_frames, const double* freq
                             const int32_t* trig_on, const int32_t* trig_off,
                             void* out, int32_t out_dtype, double* mix,
                             int32_t mem, void* stream);
+/* ... and with a per-sample filter cutoff cutoff_tv[t][v] as well (either pointer may be NULL). maxiFilter::lores/hires
+ * take the cutoff as an argument of every call (src/maximilian.cpp:455,471) and a maxiSVF patch calls setCutoff() before
+ * play() on every sample (src/maximilian.h:1287-1290): a swept filter. The coefficient design (cos/sqrt/pow, tan) then
+ * runs per sample on the device -- libdevice instead of glibc, so results agree to rounding of those functions (asserted
+ * at 1e-9 relative) instead of bit for bit. The modulation lasts for this call; MXB_P_CUTOFF is in force again afterwards.
+ * maxiBiquad (whose set() is a design routine, not a per-sample argument), envelope and delay stages: MXB_ERR_UNSUPPORTED. */
+typedef struct {
+    const double* freq_tv;      /* [n_frames][voices] or NULL */
+    const double* cutoff_tv;    /* [n_frames][voices] or NULL */
+} mxb_modulation;
+int32_t mxb_bank_process_mod(mxb_bank* bank, int32_t n_frames, const mxb_modulation* mod,
+                             const int32_t* trig_on, const int32_t* trig_off,
+                             void* out, int32_t out_dtype, double* mix,
+                             int32_t mem, void* stream);
 /* kernels launched by this library on behalf of `bank` since creation (for bench.py's gpu_launches) */
 int64_t mxb_bank_launch_count(const mxb_bank* bank);
 

@@ -369,13 +369,21 @@ public:
     bool process(const float* values, int nSamples, fftModes mode = WITH_POLAR_CONVERSION) {
         const int maxf = nSamples / hop_ + 2;
         const size_t len = (size_t)C_ * (size_t)maxf * (size_t)bins_;
+        const bool polar = mode == WITH_POLAR_CONVERSION;
         re_.resize(len); im_.resize(len);
-        if (mode == WITH_POLAR_CONVERSION) { mags_.resize(len); phases_.resize(len); }
+        if (polar) {
+            mags_.resize(len); phases_.resize(len); magsdb_.resize(len);
+            flatness_.assign((size_t)C_ * (size_t)maxf, 0.f); centroid_.assign((size_t)C_ * (size_t)maxf, 0.f);
+        }
+        mxb_stft_outputs o;
+        o.mags = polar ? mags_.data() : nullptr; o.phases = polar ? phases_.data() : nullptr;
+        o.re = re_.data(); o.im = im_.data();
+        o.mags_db = polar ? magsdb_.data() : nullptr;
+        o.flatness = polar ? flatness_.data() : nullptr; o.centroid = polar ? centroid_.data() : nullptr;
+        o.coeffs = nullptr;
         int32_t nf = 0;
-        maxib200_detail::check(mxb_stft_process(h_, values, nSamples, 1, nSamples, maxf,
-                                                mode == WITH_POLAR_CONVERSION ? mags_.data() : nullptr,
-                                                mode == WITH_POLAR_CONVERSION ? phases_.data() : nullptr, re_.data(), im_.data(),
-                                                nullptr, nullptr, &nf, MXB_MEM_HOST, nullptr), "mxb_stft_process");
+        maxib200_detail::check(mxb_stft_process2(h_, values, nSamples, 1, nSamples, maxf, &o, nullptr, &nf, MXB_MEM_HOST, nullptr),
+                               "mxb_stft_process2");
         frames_ = nf; maxf_ = maxf;
         return nf > 0;
     }
@@ -383,6 +391,11 @@ public:
     int frameStride() const { return maxf_; }     /* frame f of channel c starts at ((c*frameStride()) + f)*getNumBins() */
     std::vector<float>& getMagnitudes() { return mags_; }
     std::vector<float>& getPhases() { return phases_; }
+    /* the spectral post-processors (src/libs/maxiFFT.cpp:101-132), computed by the same kernel while the magnitudes are on chip */
+    std::vector<float>& magsToDB() { return magsdb_; }                 /* laid out like getMagnitudes() */
+    std::vector<float>& getMagnitudesDB() { return magsdb_; }
+    std::vector<float>& spectralFlatness() { return flatness_; }       /* frame f of channel c at c*frameStride() + f */
+    std::vector<float>& spectralCentroid() { return centroid_; }
     float* getReal() { return re_.data(); }
     float* getImag() { return im_.data(); }
     int getNumBins() { return bins_; }
@@ -393,7 +406,7 @@ private:
     int C_, device_;
     mxb_ctx* ctx_ = nullptr; mxb_stft* h_ = nullptr;
     int fftSize_ = 0, hop_ = 0, bins_ = 0, frames_ = 0, maxf_ = 0;
-    std::vector<float> mags_, phases_, re_, im_;
+    std::vector<float> mags_, phases_, re_, im_, magsdb_, flatness_, centroid_;
 };
 
 /* maxiIFFT (SPECTRUM mode), src/libs/maxiFFT.h:125-156; COMPLEX mode yields zeros in the reference on Linux and is not offered */

@@ -25,7 +25,7 @@ EXPORTS = [
     "mxb_last_error", "mxb_version", "mxb_ctx_create", "mxb_ctx_destroy", "mxb_ctx_sample_rate",
     "mxb_ctx_synchronize", "mxb_host_alloc", "mxb_host_free",
     "mxb_bank_create", "mxb_bank_destroy", "mxb_bank_voices", "mxb_bank_set_param", "mxb_bank_set_param_async", "mxb_bank_get_state",
-    "mxb_bank_get_ring", "mxb_bank_process", "mxb_bank_process_fm", "mxb_bank_launch_count", "mxb_env_coeffs",
+    "mxb_bank_get_ring", "mxb_bank_process", "mxb_bank_process_fm", "mxb_bank_process_mod", "mxb_bank_launch_count", "mxb_env_coeffs",
     "mxb_exchange_create", "mxb_exchange_local_handle", "mxb_exchange_connect", "mxb_exchange_destroy", "mxb_bank_set_exchange",
     "mxb_stft_create", "mxb_stft_destroy", "mxb_stft_process", "mxb_stft_process2", "mxb_stft_launch_count",
     "mxb_mfcc_create", "mxb_mfcc_destroy", "mxb_mfcc_process",
@@ -41,6 +41,10 @@ class BankDesc(C.Structure):
     _fields_ = [("voices", C.c_int32), ("osc_kind", C.c_int32), ("filt_kind", C.c_int32),
                 ("biquad_type", C.c_int32), ("env_kind", C.c_int32), ("delay_taps", C.c_int32),
                 ("max_frames", C.c_int32), ("delay_mode", C.c_int32), ("svf_mix", C.c_double * 4)]
+
+
+class Modulation(C.Structure):
+    _fields_ = [("freq_tv", C.c_void_p), ("cutoff_tv", C.c_void_p)]
 
 
 class StftOutputs(C.Structure):
@@ -84,6 +88,7 @@ def lib():
         "mxb_bank_get_ring": (i32, [vp, i32, vp, i32, i32]),
         "mxb_bank_process": (i32, [vp, i32, vp, vp, vp, i32, vp, i32, vp]),
         "mxb_bank_process_fm": (i32, [vp, i32, vp, vp, vp, vp, i32, vp, i32, vp]),
+        "mxb_bank_process_mod": (i32, [vp, i32, C.POINTER(Modulation), vp, vp, vp, i32, vp, i32, vp]),
         "mxb_bank_launch_count": (i64, [vp]),
         "mxb_env_coeffs": (i32, [i32, vp, i64, i32, vp]),
         "mxb_exchange_create": (i32, [vp, i32, i32, i32, pp]),
@@ -206,12 +211,15 @@ class Bank:
 
     # -- one block ---------------------------------------------------------------------------
     def process(self, nframes, trig_on=None, trig_off=None, want_out=True, want_mix=False, out_dtype=np.float64,
-                out=None, mix=None, freq_tv=None):
+                out=None, mix=None, freq_tv=None, cutoff_tv=None):
         """Host buffers in, host buffers out (MXB_MEM_HOST). Returns (out[nframes][V] | None, mix[nframes][2] | None).
-        freq_tv: optional per-sample oscillator frequency [nframes][V] (mxb_bank_process_fm)."""
-        if freq_tv is not None:
-            f = np.ascontiguousarray(freq_tv, dtype=np.float64)
-            assert f.shape == (nframes, self.V)
+        freq_tv / cutoff_tv: optional per-sample oscillator frequency / filter cutoff [nframes][V] (mxb_bank_process_mod)."""
+        if freq_tv is not None or cutoff_tv is not None:
+            f = np.ascontiguousarray(freq_tv, dtype=np.float64) if freq_tv is not None else None
+            cu = np.ascontiguousarray(cutoff_tv, dtype=np.float64) if cutoff_tv is not None else None
+            assert f is None or f.shape == (nframes, self.V)
+            assert cu is None or cu.shape == (nframes, self.V)
+            mod = Modulation(_np_ptr(f), _np_ptr(cu))
             f32 = np.dtype(out_dtype) == np.float32
             if want_out and out is None:
                 out = np.empty((nframes, self.V), dtype=np.float32 if f32 else np.float64)
@@ -219,9 +227,9 @@ class Bank:
                 mix = np.empty((nframes, 2), dtype=np.float64)
             ton = np.ascontiguousarray(trig_on, dtype=np.int32) if trig_on is not None else None
             toff = np.ascontiguousarray(trig_off, dtype=np.int32) if trig_off is not None else None
-            check(lib().mxb_bank_process_fm(self.h, nframes, _np_ptr(f), _np_ptr(ton), _np_ptr(toff),
-                                            _np_ptr(out if want_out else None), F32 if f32 else F64,
-                                            _np_ptr(mix if want_mix else None), MEM_HOST, None), "mxb_bank_process_fm")
+            check(lib().mxb_bank_process_mod(self.h, nframes, C.byref(mod), _np_ptr(ton), _np_ptr(toff),
+                                             _np_ptr(out if want_out else None), F32 if f32 else F64,
+                                             _np_ptr(mix if want_mix else None), MEM_HOST, None), "mxb_bank_process_mod")
             return (out if want_out else None), (mix if want_mix else None)
         f32 = np.dtype(out_dtype) == np.float32
         if want_out and out is None:

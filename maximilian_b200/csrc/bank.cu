@@ -29,6 +29,7 @@ struct mxb_bank {
     double* mix_dev;                         // [max_frames][2]
     void* out_stage; size_t out_stage_bytes; // staging for MXB_MEM_HOST out
     double* fm_stage; size_t fm_stage_bytes; // staging for host-resident per-sample frequencies
+    double* cm_stage; size_t cm_stage_bytes; // ... and cutoffs
     int64_t launches;
     mxb_exchange* ex;                        // peer-memory mix exchange (multi-GPU), or NULL
 };
@@ -216,7 +217,7 @@ int free_bank(mxb_bank* b) {
     for (int i = 0; i < 5; ++i) cudaFree(b->cf[i]);
     cudaFree(b->env_amp); cudaFree(b->env_output); cudaFree(b->env_holdcount); cudaFree(b->env_hold); cudaFree(b->env_flags);
     cudaFree(b->trig_on); cudaFree(b->trig_off); cudaFree(b->dl_phase); cudaFree(b->dl_size); cudaFree(b->dl_pos); cudaFree(b->ring);
-    cudaFree(b->partials); cudaFree(b->mix_dev); cudaFree(b->out_stage); cudaFree(b->fm_stage);
+    cudaFree(b->partials); cudaFree(b->mix_dev); cudaFree(b->out_stage); cudaFree(b->fm_stage); cudaFree(b->cm_stage);
     delete b;
     return MXB_OK;
 }
@@ -255,6 +256,7 @@ int32_t mxb_bank_create(mxb_ctx* ctx, const mxb_bank_desc* d, mxb_bank** out) {
     b->ring = b->partials = b->mix_dev = nullptr; b->partials_len = 0;
     b->out_stage = nullptr; b->out_stage_bytes = 0; b->launches = 0;
     b->fm_stage = nullptr; b->fm_stage_bytes = 0;
+    b->cm_stage = nullptr; b->cm_stage_bytes = 0;
     const size_t V = (size_t)d->voices;
     int rc = MXB_OK;
 #define TRY(x) do { rc = (x); if (rc != MXB_OK) { free_bank(b); return rc; } } while (0)
@@ -433,7 +435,15 @@ int32_t mxb_bank_process(mxb_bank* b, int32_t n_frames, const int32_t* trig_on, 
 
 int32_t mxb_bank_process_fm(mxb_bank* b, int32_t n_frames, const double* freq_tv, const int32_t* trig_on, const int32_t* trig_off,
                             void* out, int32_t out_dtype, double* mix, int32_t mem, void* stream_) {
+    mxb_modulation m; m.freq_tv = freq_tv; m.cutoff_tv = nullptr;
+    return mxb_bank_process_mod(b, n_frames, &m, trig_on, trig_off, out, out_dtype, mix, mem, stream_);
+}
+
+int32_t mxb_bank_process_mod(mxb_bank* b, int32_t n_frames, const mxb_modulation* mod, const int32_t* trig_on, const int32_t* trig_off,
+                             void* out, int32_t out_dtype, double* mix, int32_t mem, void* stream_) {
     MXB_REQUIRE(b, MXB_ERR_INVALID, "mxb_bank_process: NULL bank");
+    const double* freq_tv = mod ? mod->freq_tv : nullptr;
+    const double* cutoff_tv = mod ? mod->cutoff_tv : nullptr;
     MXB_REQUIRE(n_frames >= 0 && n_frames <= b->desc.max_frames, MXB_ERR_INVALID, "mxb_bank_process: n_frames %d (max_frames %d)", n_frames, b->desc.max_frames);
     MXB_REQUIRE(mem == MXB_MEM_HOST || mem == MXB_MEM_DEVICE || mem == MXB_MEM_SPLIT, MXB_ERR_INVALID, "mxb_bank_process: mem %d", mem);
     const bool host_ctl = mem != MXB_MEM_DEVICE;      // gates and mix in host memory
@@ -453,23 +463,32 @@ int32_t mxb_bank_process_fm(mxb_bank* b, int32_t n_frames, const double* freq_tv
 
     const int* d_on = trig_on; const int* d_off = trig_off;
     void* d_out = out; double* d_mix = mix;
-    if (freq_tv)
+    if (freq_tv || cutoff_tv)
         MXB_REQUIRE(b->desc.env_kind == MXB_ENV_NONE && b->desc.delay_taps == 0, MXB_ERR_UNSUPPORTED,
-                    "mxb_bank_process_fm: per-sample frequency is built for oscillator -> filter -> out/mix chains only "
+                    "mxb_bank_process_mod: per-sample parameters are built for oscillator -> filter -> out/mix chains only "
                     "(no envelope, no delay line)");
-    const double* d_fm = freq_tv;
-    if (freq_tv && host_ctl) {       // per-sample frequencies are control data: they live where the gates live
+    if (cutoff_tv)
+        MXB_REQUIRE(fk == MXB_FILT_LORES || fk == MXB_FILT_HIRES || fk == MXB_FILT_SVF, MXB_ERR_UNSUPPORTED,
+                    "mxb_bank_process_mod: per-sample cutoff is built for lores / hires / maxiSVF");
+    // per-sample parameters are control data: they live where the gates live
+    auto stage = [&](const double* src, double** buf, size_t* cap, const double** dev) -> int {
+        *dev = src;
+        if (!src || !host_ctl) return MXB_OK;
         const size_t need = sizeof(double) * (size_t)n_frames * V;
-        if (need > b->fm_stage_bytes) {
+        if (need > *cap) {
             MXB_CUDA(cudaStreamSynchronize(s));
-            cudaFree(b->fm_stage); b->fm_stage = nullptr; b->fm_stage_bytes = 0;
-            cudaError_t e = cudaMalloc((void**)&b->fm_stage, need);
-            if (e != cudaSuccess) { set_error("mxb_bank_process_fm: staging cudaMalloc(%zu): %s", need, cudaGetErrorString(e)); return MXB_ERR_ALLOC; }
-            b->fm_stage_bytes = need;
+            cudaFree(*buf); *buf = nullptr; *cap = 0;
+            cudaError_t e = cudaMalloc((void**)buf, need);
+            if (e != cudaSuccess) { set_error("mxb_bank_process_mod: staging cudaMalloc(%zu): %s", need, cudaGetErrorString(e)); return MXB_ERR_ALLOC; }
+            *cap = need;
         }
-        MXB_CUDA(cudaMemcpyAsync(b->fm_stage, freq_tv, need, cudaMemcpyHostToDevice, s));
-        d_fm = b->fm_stage;
-    }
+        MXB_CUDA(cudaMemcpyAsync(*buf, src, need, cudaMemcpyHostToDevice, s));
+        *dev = *buf;
+        return MXB_OK;
+    };
+    const double *d_fm = nullptr, *d_cm = nullptr;
+    { int rc0 = stage(freq_tv, &b->fm_stage, &b->fm_stage_bytes, &d_fm); if (rc0 != MXB_OK) return rc0; }
+    { int rc0 = stage(cutoff_tv, &b->cm_stage, &b->cm_stage_bytes, &d_cm); if (rc0 != MXB_OK) return rc0; }
     if (host_ctl) {
         if (trig_on) {
             MXB_CUDA(cudaMemcpyAsync(b->trig_on, trig_on, sizeof(int) * V, cudaMemcpyHostToDevice, s));
@@ -513,7 +532,7 @@ int32_t mxb_bank_process_fm(mxb_bank* b, int32_t n_frames, const double* freq_tv
     a.W = W;
     a.sr = (double)(size_t)b->ctx->sample_rate;
     for (int i = 0; i < 4; ++i) a.svf_mix[i] = b->desc.svf_mix[i];
-    a.freq_tv = d_fm;
+    a.freq_tv = d_fm; a.cutoff_tv = d_cm; a.res = b->dp[MXB_P_RESONANCE];
     a.freq = b->dp[MXB_P_FREQ]; a.duty = b->dp[MXB_P_DUTY]; a.phase = b->dp[MXB_P_PHASE]; a.osc_out = b->osc_out;
     a.f0 = b->f0; a.f1 = b->f1; a.f2 = b->f2;
     for (int i = 0; i < 5; ++i) a.cf[i] = b->cf[i];

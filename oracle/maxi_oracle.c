@@ -343,11 +343,17 @@ int32_t mxo_bank_process(void* h, int32_t nframes, const int32_t* trig_on, const
 
 int32_t mxo_bank_process_fm(void* h, int32_t nframes, const double* freq_tv, const int32_t* trig_on, const int32_t* trig_off,
                             double* out, double* mix, int32_t first, int32_t count) {
+    return mxo_bank_process_mod(h, nframes, freq_tv, NULL, trig_on, trig_off, out, mix, first, count);
+}
+
+int32_t mxo_bank_process_mod(void* h, int32_t nframes, const double* freq_tv, const double* cutoff_tv, const int32_t* trig_on,
+                             const int32_t* trig_off, double* out, double* mix, int32_t first, int32_t count) {
     bank_t* b = (bank_t*)h;
     if (!b || nframes < 0 || first < 0 || count < 0 || first + count > b->V) return -1;
     const mxo_chain* c = &b->chain;
     const int V = b->V;
     const double sr = (double)(size_t)c->sample_rate;     /* maxiSettings::sampleRate is a size_t, src/maximilian.h:124 */
+    if (cutoff_tv && c->filt_kind == MXO_FILT_BIQUAD) return -3;
     for (int t = 0; t < nframes; ++t) {
         double m0 = 0.0, m1 = 0.0;
         for (int v = first; v < first + count; ++v) {
@@ -366,7 +372,8 @@ int32_t mxo_bank_process_fm(void* h, int32_t nframes, const double* freq_tv, con
                 case MXO_FILT_LORES:
                 case MXO_FILT_HIRES: {
                     /* maxiFilter::lores / hires, src/maximilian.cpp:455-468 / 471-484 */
-                    double input = x, cutoff = b->p[MXO_P_CUTOFF][v], resonance = b->p[MXO_P_RESONANCE][v];
+                    double input = x, resonance = b->p[MXO_P_RESONANCE][v];
+                    double cutoff = cutoff_tv ? cutoff_tv[(size_t)t * (size_t)V + (size_t)v] : b->p[MXO_P_CUTOFF][v];
                     double fx = b->f0[v], fy = b->f1[v];
                     if (cutoff < 10) cutoff = 10;
                     if (cutoff > sr) cutoff = sr;
@@ -383,7 +390,17 @@ int32_t mxo_bank_process_fm(void* h, int32_t nframes, const double* freq_tv, con
                 }
                 case MXO_FILT_SVF: {
                     /* maxiSVF::play, src/maximilian.h:1305-1319 */
-                    const double g1 = b->cf[0][v], g2 = b->cf[1][v], g3 = b->cf[2][v], g4 = b->cf[3][v], k = b->cf[4][v];
+                    double g1 = b->cf[0][v], g2 = b->cf[1][v], g3 = b->cf[2][v], g4 = b->cf[3][v], k = b->cf[4][v];
+                    if (cutoff_tv) {
+                        /* maxiSVF::setCutoff -> setParams(cutoff, res), src/maximilian.h:1287-1290,1322-1334, called by
+                         * the patch before play(); the object's own members keep MXO_P_CUTOFF for the calls after this one */
+                        const double freq = cutoff_tv[(size_t)t * (size_t)V + (size_t)v], res = b->p[MXO_P_RESONANCE][v];
+                        const double g = tan(MAXI_PI * freq / sr);
+                        const double damping = res == 0 ? 0 : 1.0 / res;
+                        const double ginv = g / (1.0 + g * (g + damping));
+                        k = damping;
+                        g1 = ginv; g2 = 2.0 * (g + k) * ginv; g3 = g * ginv; g4 = 2.0 * ginv;
+                    }
                     double w = x, v0z = b->f0[v], v1 = b->f1[v], v2 = b->f2[v];
                     double low, band, high, notch;
                     double v1z = v1;

@@ -189,6 +189,11 @@ int32_t mxo_bank_process(void* h, int32_t nframes, const int32_t* trig_on, const
 
 int32_t mxo_bank_process_fm(void* h, int32_t nframes, const double* freq_tv, const int32_t* trig_on, const int32_t* trig_off,
                             double* out, double* mix, int32_t first, int32_t count) {
+    return mxo_bank_process_mod(h, nframes, freq_tv, nullptr, trig_on, trig_off, out, mix, first, count);
+}
+
+int32_t mxo_bank_process_mod(void* h, int32_t nframes, const double* freq_tv, const double* cutoff_tv, const int32_t* trig_on,
+                             const int32_t* trig_off, double* out, double* mix, int32_t first, int32_t count) {
     RefBank* b = (RefBank*)h;
     if (!b || nframes < 0 || first < 0 || count < 0 || first + count > b->V) return -1;
     const mxo_chain& c = b->chain;
@@ -200,7 +205,8 @@ int32_t mxo_bank_process_fm(void* h, int32_t nframes, const double* freq_tv, con
     const double* dsize = b->p[MXO_P_DELAY_SIZE].data();
     const double* dfb = b->p[MXO_P_DELAY_FEEDBACK].data();
     const double* pan = b->p[MXO_P_PAN].data();
-    if ((c.filt_kind == MXO_FILT_LORES || c.filt_kind == MXO_FILT_HIRES) && (!fc || !q)) return -2;
+    if ((c.filt_kind == MXO_FILT_LORES || c.filt_kind == MXO_FILT_HIRES) && ((!fc && !cutoff_tv) || !q)) return -2;
+    if (cutoff_tv && c.filt_kind == MXO_FILT_BIQUAD) return -3;
     std::vector<double> two(2, 0.0);
     for (int t = 0; t < nframes; ++t) {
         double m0 = 0.0, m1 = 0.0;
@@ -215,9 +221,11 @@ int32_t mxo_bank_process_fm(void* h, int32_t nframes, const double* freq_tv, con
                 x = r.env.ar(x, b->p[MXO_P_ENV_ATTACK][v], b->p[MXO_P_ENV_RELEASE][v], (long)b->p[MXO_P_ENV_HOLDTIME][v], trig);
             }
             switch (c.filt_kind) {
-                case MXO_FILT_LORES: x = r.filt.lores(x, fc[v], q[v]); break;
-                case MXO_FILT_HIRES: x = r.filt.hires(x, fc[v], q[v]); break;
-                case MXO_FILT_SVF:   x = r.svf.play(x, c.svf_mix[0], c.svf_mix[1], c.svf_mix[2], c.svf_mix[3]); break;
+                case MXO_FILT_LORES: x = r.filt.lores(x, cutoff_tv ? cutoff_tv[(size_t)t * V + v] : fc[v], q[v]); break;
+                case MXO_FILT_HIRES: x = r.filt.hires(x, cutoff_tv ? cutoff_tv[(size_t)t * V + v] : fc[v], q[v]); break;
+                case MXO_FILT_SVF:
+                    if (cutoff_tv) r.svf.setCutoff(cutoff_tv[(size_t)t * V + v]);     // the patch's per-sample setter call
+                    x = r.svf.play(x, c.svf_mix[0], c.svf_mix[1], c.svf_mix[2], c.svf_mix[3]); break;
                 case MXO_FILT_BIQUAD:x = r.bq.play(x); break;
                 default: break;
             }
@@ -228,6 +236,8 @@ int32_t mxo_bank_process_fm(void* h, int32_t nframes, const double* freq_tv, con
         }
         if (mix) { mix[2 * t] = m0; mix[2 * t + 1] = m1; }
     }
+    if (cutoff_tv && c.filt_kind == MXO_FILT_SVF && fc)      // the modulation lasts for this call
+        for (int v = first; v < first + count; ++v) b->voices[v].svf.setCutoff(fc[v]);
     return 0;
 }
 

@@ -14,13 +14,61 @@ SRC = os.path.join(ROOT, "tests", "cpp", "patch_poly.cpp")
 EXE = os.path.join(ROOT, "tests", "cpp", "patch_poly")
 
 
-def compile_patch():
+def compile_patch(src=SRC, exe=EXE):
     lib = build.build()
     libdir = os.path.dirname(lib)
-    cmd = ["g++", "-std=c++17", "-O2", "-Wall", "-I", os.path.join(ROOT, "include"), SRC, "-o", EXE,
+    cmd = ["g++", "-std=c++17", "-O2", "-Wall", "-I", os.path.join(ROOT, "include"), src, "-o", exe,
            "-L", libdir, "-lmaxib200", "-Wl,-rpath," + libdir]
     subprocess.check_call(cmd)
-    return EXE
+    return exe
+
+
+SRC_SPEC = os.path.join(ROOT, "tests", "cpp", "patch_spectral.cpp")
+EXE_SPEC = os.path.join(ROOT, "tests", "cpp", "patch_spectral")
+
+
+def test_spectral_patch_compiles_against_the_dropin_header():
+    exe = compile_patch(SRC_SPEC, EXE_SPEC)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 2 and "usage" in r.stderr
+
+
+@pytest.mark.gpu
+def test_spectral_patch_matches_oracle(port, tmp_path):
+    """maxiFFT / maxiMFCC / maxiIFFT of the C++ layer, fed in ragged chunks, against the oracle fed sample by sample."""
+    exe = compile_patch(SRC_SPEC, EXE_SPEC)
+    C, N, bins, hop, nc = 5, 7 * 1024 + 100, 512, 512, 13
+    x = W.channel_streams(C, N, seed=44)
+    x.tofile(tmp_path / "in.bin")
+    r = subprocess.run([exe, str(tmp_path / "in.bin"), str(tmp_path / "out.bin"), str(C), str(N)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    raw = open(tmp_path / "out.bin", "rb").read()
+    F = int(np.frombuffer(raw, dtype=np.int32, count=1)[0]); off = 4
+
+    def take(dtype, shape):
+        nonlocal off
+        n = int(np.prod(shape)); a = np.frombuffer(raw, dtype=dtype, count=n, offset=off).reshape(shape)
+        off += a.nbytes
+        return a
+    mags, phases, db = take(np.float32, (C, F, bins)), take(np.float32, (C, F, bins)), take(np.float32, (C, F, bins))
+    flat, cent = take(np.float32, (C, F)), take(np.float32, (C, F))
+    co, y = take(np.float64, (C, F, nc)), take(np.float32, (C, F * hop))
+    assert off == len(raw)
+
+    o = port.Stft(C, 1024, hop).process(x)
+    assert o["mags"].shape == (C, F, bins)                        # frame schedule
+    assert np.array_equal(mags, o["mags"])                        # bit-identical magnitudes
+    d = np.angle(np.exp(1j * (phases.astype(np.float64) - o["phases"])))
+    assert np.abs(d[o["mags"] > 1e-3 * o["mags"].max(axis=-1, keepdims=True)]).max() <= 1e-4
+    odb, ofl, oce = port.spectral_features(o["mags"], 1024, 48000)
+    np.testing.assert_allclose(db, odb, rtol=2e-6, atol=1e-6)
+    np.testing.assert_allclose(flat, ofl, rtol=1e-4, atol=1e-7)
+    np.testing.assert_allclose(cent, oce, rtol=1e-4, atol=1e-3)
+    oc, _ = port.Mfcc(bins, 42, nc, 20.0, 20000.0, 48000).process(o["mags"])
+    np.testing.assert_allclose(co, oc, rtol=1e-9, atol=1e-12)
+    oy = port.Istft(C, 1024, hop).process(o["mags"], o["phases"])
+    # the resynthesis starts from this side's own phases (atan2f ulps away from the oracle's) and adds cosf/sinf ulps
+    assert np.abs(y - oy).max() <= 2e-5 * np.abs(oy).max()
 
 
 def test_patch_compiles_against_the_dropin_header():

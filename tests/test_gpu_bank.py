@@ -229,6 +229,35 @@ def test_per_sample_frequency_fm(port, osc, filt, delay):
     _close(og, oo, osc in TRIG, "back to block-constant frequency")
 
 
+@pytest.mark.parametrize("osc,filt,fm", [("saw", "svf", False), ("saw", "lores", False), ("phasor", "hires", True), ("square", "svf", True)])
+def test_per_sample_cutoff(port, osc, filt, fm):
+    """SURVEY.md 8(f) rank 1 / A6b: a filter cutoff that changes every sample (lores/hires call argument; maxiSVF::setCutoff
+    before every play()). The coefficient design runs per sample with libdevice's cos/sqrt/pow/tan instead of glibc's:
+    not bit-identical any more -- 1e-9 relative + 1e-12 (north_star's bar is 1e-5)."""
+    from test_oracle_vs_reference import cutoff_sweeps, fm_frequencies
+    V, B = 133, 192
+    p = W.voice_params(V, seed=33)
+    g = gpu_bank(V, osc=osc, filt=filt, max_frames=B); o = port.Bank(V, osc=osc, filt=filt)
+    W.configure_bank(g, filt, p); W.configure_bank(o, filt, p)
+    for blk in range(3):
+        cu = cutoff_sweeps(V, B, blk); f = fm_frequencies(V, B, blk) if fm else None
+        og, mg = g.process(B, freq_tv=f, cutoff_tv=cu, want_mix=True); oo, mo = o.process(B, freq_tv=f, cutoff_tv=cu, want_mix=True)
+        np.testing.assert_allclose(og, oo, rtol=1e-9, atol=1e-12, err_msg=f"swept {filt} blk{blk}")
+        np.testing.assert_allclose(mg, mo, rtol=1e-9, atol=1e-11)
+    og, _ = g.process(B); oo, _ = o.process(B)        # the block-constant MXB_P_CUTOFF is in force again
+    np.testing.assert_allclose(og, oo, rtol=1e-9, atol=1e-12)
+
+
+def test_per_sample_cutoff_refused_where_not_built():
+    g = gpu_bank(8, osc="saw", filt="biquad", max_frames=16)
+    g.set("cutoff", 500.0); g.set("resonance", 1.0); g.set("gain", 0.0)
+    with pytest.raises(capi.MxbError):
+        g.process(16, cutoff_tv=np.full((16, 8), 300.0))
+    g = gpu_bank(8, osc="saw", filt="svf", env=True, max_frames=16)
+    with pytest.raises(capi.MxbError):
+        g.process(16, cutoff_tv=np.full((16, 8), 300.0))
+
+
 def test_env_ar(port):
     # maxiEnv::ar, src/maximilian.cpp:1319-1358 (output = input in the hold states; clamp test on every call)
     V, B = 200, 400

@@ -161,6 +161,39 @@ def test_per_sample_frequency_bit_exact(port, reference, osc, filt):
     assert _same(oa, ob)
 
 
+def cutoff_sweeps(V, B, blk, seed=6):
+    """cutoff[t][v] = centre * 2^(depth * sin(2*pi*rate*t/sr)): an LFO-swept filter, 60 Hz .. 12 kHz."""
+    rng = np.random.default_rng(seed)
+    centre = 200.0 * np.exp2(4.0 * rng.random(V)); depth = 1.5 * rng.random(V); rate = 0.2 + 6.0 * rng.random(V)
+    t = (blk * B + np.arange(B))[:, None] / 48000.0
+    return centre[None, :] * np.exp2(depth[None, :] * np.sin(2 * np.pi * rate[None, :] * t))
+
+
+@pytest.mark.parametrize("osc,filt,fm", [("saw", "svf", False), ("saw", "lores", False), ("phasor", "hires", True), ("square", "svf", True)])
+def test_per_sample_cutoff_bit_exact(port, reference, osc, filt, fm):
+    # lores/hires take the cutoff per call; the SVF patch calls setCutoff() per sample (src/maximilian.h:1287-1290)
+    V, B = 19, 160
+    p = W.voice_params(V, seed=33)
+    a, b = _pair(port, reference, V, osc=osc, filt=filt)
+    _configure(a, filt, p); _configure(b, filt, p)
+    for blk in range(3):
+        cu = cutoff_sweeps(V, B, blk); f = fm_frequencies(V, B, blk) if fm else None
+        oa, ma = a.process(B, freq_tv=f, cutoff_tv=cu, want_mix=True); ob, mb = b.process(B, freq_tv=f, cutoff_tv=cu, want_mix=True)
+        assert _same(oa, ob) and _same(ma, mb), blk
+    oa, _ = a.process(B); ob, _ = b.process(B)          # the block-constant cutoff is in force again
+    assert _same(oa, ob)
+    for s in ("filt0", "filt1"):
+        assert _same(a.get(s), b.get(s)), s
+
+
+def test_per_sample_cutoff_not_for_biquad(port, reference):
+    for lib in (port, reference):
+        bq = lib.Bank(4, osc="saw", filt="biquad")
+        bq.set("cutoff", 800.0); bq.set("resonance", 1.0); bq.set("gain", 0.0)
+        with pytest.raises(RuntimeError):
+            bq.process(8, cutoff_tv=np.full((8, 4), 500.0))
+
+
 def test_env_ar_bit_exact(port, reference):
     # maxiEnv::ar(input, attack, release, holdtime, trigger), src/maximilian.cpp:1319-1358
     V, B = 48, 400
