@@ -101,7 +101,7 @@ enum {
     MXB_P_PAN = 13,           /* maxiMix::stereo x (src/maximilian.cpp:503-509) */
     MXB_P_DELAY_POSITION = 14,/* maxiDelayline::dlFromPosition position argument (integral value) */
     MXB_P_COUNT = 15,
-    /* read-only state (mxb_bank_get_state) */
+    /* state (mxb_bank_get_state / mxb_bank_set_state) */
     MXB_S_FILT_0 = 32,        /* lores/hires x | svf v0z | biquad v[1] */
     MXB_S_FILT_1 = 33,        /* lores/hires y | svf v1  | biquad v[2] */
     MXB_S_FILT_2 = 34,        /* svf v2 */
@@ -109,7 +109,8 @@ enum {
     MXB_S_ENV_OUTPUT = 36,
     MXB_S_ENV_HOLDCOUNT = 37,
     MXB_S_ENV_FLAGS = 38,     /* attackphase | decayphase<<1 | sustainphase<<2 | holdphase<<3 | releasephase<<4 */
-    MXB_S_DELAY_PHASE = 39    /* maxiDelayline::phase (the ring index, an int in the reference) */
+    MXB_S_DELAY_PHASE = 39,   /* maxiDelayline::phase (the ring index, an int in the reference) */
+    MXB_S_OSC_OUTPUT = 40     /* maxiOsc::output (square / pulse / triangle hold their last value in it) */
 };
 
 typedef struct mxb_ctx mxb_ctx;
@@ -169,6 +170,13 @@ int32_t mxb_bank_set_param_async(mxb_bank* bank, int32_t id, const double* value
 int32_t mxb_bank_get_state(mxb_bank* bank, int32_t id, double* values, int32_t mem);
 /* ring slots [0, n) of voice v (debug / checkpoint) */
 int32_t mxb_bank_get_ring(mxb_bank* bank, int32_t voice, double* dst, int32_t n, int32_t mem);
+/* The reference's objects hold their state by value (src/maximilian.h:266-281, 888-932): a patch checkpoints or forks a
+ * voice by copying the object and restores it by assigning members. The counterparts: mxb_bank_set_state writes one
+ * MXB_S_* array (integral ones arrive as doubles, as mxb_bank_get_state returns them), mxb_bank_set_ring one voice's
+ * ring slots, mxb_bank_clone makes a deep copy of the whole bank (parameters, coefficients, state, rings). */
+int32_t mxb_bank_set_state(mxb_bank* bank, int32_t id, const double* values, int32_t mem);
+int32_t mxb_bank_set_ring(mxb_bank* bank, int32_t voice, const double* src, int32_t n, int32_t mem);
+int32_t mxb_bank_clone(mxb_bank* bank, mxb_bank** copy);
 /* One block. trigger_v(t) = 1 for trig_on[v] <= t < trig_off[v] (t counts frames inside this call),
  * both NULL = trigger 0. out: [n_frames][voices] of out_dtype, or NULL. mix: double [n_frames][2]
  * (overwritten), or NULL; voices are summed in a fixed order, so results are run-to-run identical. */
@@ -190,10 +198,15 @@ int32_t mxb_bank_process_fm(mxb_bank* bank, int32_t n_frames, const double* freq
  * play() on every sample (src/maximilian.h:1287-1290): a swept filter. The coefficient design (cos/sqrt/pow, tan) then
  * runs per sample on the device -- libdevice instead of glibc, so results agree to rounding of those functions (asserted
  * at 1e-9 relative) instead of bit for bit. The modulation lasts for this call; MXB_P_CUTOFF is in force again afterwards.
- * maxiBiquad (whose set() is a design routine, not a per-sample argument), envelope and delay stages: MXB_ERR_UNSUPPORTED. */
+ * maxiBiquad (whose set() is a design routine, not a per-sample argument), envelope and delay stages: MXB_ERR_UNSUPPORTED.
+ * delay_size_tv[t][v] (integral values, 1 .. delay_taps): the `size` argument of maxiDelayline::dl / dlFromPosition, which a
+ * flanger or chorus changes on every call (maxiFlanger::flange, src/maximilian.h:1144-1180). Works on any chain with a
+ * delay stage (not together with freq_tv / cutoff_tv); the ring is then addressed slot by slot in HBM (the staged-window
+ * schedule needs a size that holds for a block), indices exactly as the reference computes them. */
 typedef struct {
-    const double* freq_tv;      /* [n_frames][voices] or NULL */
-    const double* cutoff_tv;    /* [n_frames][voices] or NULL */
+    const double* freq_tv;        /* [n_frames][voices] or NULL */
+    const double* cutoff_tv;      /* [n_frames][voices] or NULL */
+    const double* delay_size_tv;  /* [n_frames][voices] or NULL */
 } mxb_modulation;
 int32_t mxb_bank_process_mod(mxb_bank* bank, int32_t n_frames, const mxb_modulation* mod,
                              const int32_t* trig_on, const int32_t* trig_off,

@@ -19,13 +19,13 @@ BIQUAD = dict(lowpass=0, highpass=1, bandpass=2, notch=3, peak=4, lowshelf=5, hi
 P = dict(freq=0, phase=1, duty=2, cutoff=3, resonance=4, gain=5, env_attack=6, env_decay=7,
          env_sustain=8, env_release=9, env_holdtime=10, delay_size=11, delay_feedback=12, pan=13, delay_position=14,
          filt0=32, filt1=33, filt2=34, env_amplitude=35, env_output=36, env_holdcount=37,
-         env_flags=38, delay_phase=39)
+         env_flags=38, delay_phase=39, osc_output=40)
 
 EXPORTS = [
     "mxb_last_error", "mxb_version", "mxb_ctx_create", "mxb_ctx_destroy", "mxb_ctx_sample_rate",
     "mxb_ctx_synchronize", "mxb_host_alloc", "mxb_host_free",
     "mxb_bank_create", "mxb_bank_destroy", "mxb_bank_voices", "mxb_bank_set_param", "mxb_bank_set_param_async", "mxb_bank_get_state",
-    "mxb_bank_get_ring", "mxb_bank_process", "mxb_bank_process_fm", "mxb_bank_process_mod", "mxb_bank_launch_count", "mxb_env_coeffs",
+    "mxb_bank_get_ring", "mxb_bank_set_state", "mxb_bank_set_ring", "mxb_bank_clone", "mxb_bank_process", "mxb_bank_process_fm", "mxb_bank_process_mod", "mxb_bank_launch_count", "mxb_env_coeffs",
     "mxb_exchange_create", "mxb_exchange_local_handle", "mxb_exchange_connect", "mxb_exchange_destroy", "mxb_bank_set_exchange",
     "mxb_stft_create", "mxb_stft_destroy", "mxb_stft_process", "mxb_stft_process2", "mxb_stft_launch_count",
     "mxb_mfcc_create", "mxb_mfcc_destroy", "mxb_mfcc_process",
@@ -44,7 +44,7 @@ class BankDesc(C.Structure):
 
 
 class Modulation(C.Structure):
-    _fields_ = [("freq_tv", C.c_void_p), ("cutoff_tv", C.c_void_p)]
+    _fields_ = [("freq_tv", C.c_void_p), ("cutoff_tv", C.c_void_p), ("delay_size_tv", C.c_void_p)]
 
 
 class StftOutputs(C.Structure):
@@ -86,6 +86,9 @@ def lib():
         "mxb_bank_set_param_async": (i32, [vp, i32, vp, i32, vp]),
         "mxb_bank_get_state": (i32, [vp, i32, vp, i32]),
         "mxb_bank_get_ring": (i32, [vp, i32, vp, i32, i32]),
+        "mxb_bank_set_state": (i32, [vp, i32, vp, i32]),
+        "mxb_bank_set_ring": (i32, [vp, i32, vp, i32, i32]),
+        "mxb_bank_clone": (i32, [vp, pp]),
         "mxb_bank_process": (i32, [vp, i32, vp, vp, vp, i32, vp, i32, vp]),
         "mxb_bank_process_fm": (i32, [vp, i32, vp, vp, vp, vp, i32, vp, i32, vp]),
         "mxb_bank_process_mod": (i32, [vp, i32, C.POINTER(Modulation), vp, vp, vp, i32, vp, i32, vp]),
@@ -205,21 +208,41 @@ class Bank:
         check(lib().mxb_bank_get_ring(self.h, v, _np_ptr(a), n, MEM_HOST), "mxb_bank_get_ring")
         return a
 
+    def set_state(self, name, values):
+        """mxb_bank_set_state: one MXB_S_* array (filt0.., env_*, delay_phase, osc_output)."""
+        a = np.ascontiguousarray(np.broadcast_to(np.asarray(values, dtype=np.float64), (self.V,)))
+        check(lib().mxb_bank_set_state(self.h, P[name], _np_ptr(a), MEM_HOST), f"mxb_bank_set_state({name})")
+
+    def set_ring(self, v, values):
+        a = np.ascontiguousarray(values, dtype=np.float64)
+        check(lib().mxb_bank_set_ring(self.h, v, _np_ptr(a), a.size, MEM_HOST), "mxb_bank_set_ring")
+
+    def clone(self):
+        """mxb_bank_clone: a deep copy (parameters, coefficients, state, rings) on the same context."""
+        other = object.__new__(Bank)
+        other.ctx, other.V, other.max_frames = self.ctx, self.V, self.max_frames
+        other.h = C.c_void_p()
+        check(lib().mxb_bank_clone(self.h, C.byref(other.h)), "mxb_bank_clone")
+        return other
+
     @property
     def launches(self):
         return int(lib().mxb_bank_launch_count(self.h))
 
     # -- one block ---------------------------------------------------------------------------
     def process(self, nframes, trig_on=None, trig_off=None, want_out=True, want_mix=False, out_dtype=np.float64,
-                out=None, mix=None, freq_tv=None, cutoff_tv=None):
+                out=None, mix=None, freq_tv=None, cutoff_tv=None, delay_size_tv=None):
         """Host buffers in, host buffers out (MXB_MEM_HOST). Returns (out[nframes][V] | None, mix[nframes][2] | None).
-        freq_tv / cutoff_tv: optional per-sample oscillator frequency / filter cutoff [nframes][V] (mxb_bank_process_mod)."""
-        if freq_tv is not None or cutoff_tv is not None:
+        freq_tv / cutoff_tv / delay_size_tv: optional per-sample oscillator frequency / filter cutoff / delay size [nframes][V]
+        (mxb_bank_process_mod)."""
+        if freq_tv is not None or cutoff_tv is not None or delay_size_tv is not None:
             f = np.ascontiguousarray(freq_tv, dtype=np.float64) if freq_tv is not None else None
             cu = np.ascontiguousarray(cutoff_tv, dtype=np.float64) if cutoff_tv is not None else None
             assert f is None or f.shape == (nframes, self.V)
             assert cu is None or cu.shape == (nframes, self.V)
-            mod = Modulation(_np_ptr(f), _np_ptr(cu))
+            ds = np.ascontiguousarray(delay_size_tv, dtype=np.float64) if delay_size_tv is not None else None
+            assert ds is None or ds.shape == (nframes, self.V)
+            mod = Modulation(_np_ptr(f), _np_ptr(cu), _np_ptr(ds))
             f32 = np.dtype(out_dtype) == np.float32
             if want_out and out is None:
                 out = np.empty((nframes, self.V), dtype=np.float32 if f32 else np.float64)

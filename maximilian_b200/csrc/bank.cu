@@ -30,6 +30,7 @@ struct mxb_bank {
     void* out_stage; size_t out_stage_bytes; // staging for MXB_MEM_HOST out
     double* fm_stage; size_t fm_stage_bytes; // staging for host-resident per-sample frequencies
     double* cm_stage; size_t cm_stage_bytes; // ... and cutoffs
+    double* ds_stage; size_t ds_stage_bytes; // ... and delay sizes
     int64_t launches;
     mxb_exchange* ex;                        // peer-memory mix exchange (multi-GPU), or NULL
 };
@@ -217,7 +218,7 @@ int free_bank(mxb_bank* b) {
     for (int i = 0; i < 5; ++i) cudaFree(b->cf[i]);
     cudaFree(b->env_amp); cudaFree(b->env_output); cudaFree(b->env_holdcount); cudaFree(b->env_hold); cudaFree(b->env_flags);
     cudaFree(b->trig_on); cudaFree(b->trig_off); cudaFree(b->dl_phase); cudaFree(b->dl_size); cudaFree(b->dl_pos); cudaFree(b->ring);
-    cudaFree(b->partials); cudaFree(b->mix_dev); cudaFree(b->out_stage); cudaFree(b->fm_stage); cudaFree(b->cm_stage);
+    cudaFree(b->partials); cudaFree(b->mix_dev); cudaFree(b->out_stage); cudaFree(b->fm_stage); cudaFree(b->cm_stage); cudaFree(b->ds_stage);
     delete b;
     return MXB_OK;
 }
@@ -257,6 +258,7 @@ int32_t mxb_bank_create(mxb_ctx* ctx, const mxb_bank_desc* d, mxb_bank** out) {
     b->out_stage = nullptr; b->out_stage_bytes = 0; b->launches = 0;
     b->fm_stage = nullptr; b->fm_stage_bytes = 0;
     b->cm_stage = nullptr; b->cm_stage_bytes = 0;
+    b->ds_stage = nullptr; b->ds_stage_bytes = 0;
     const size_t V = (size_t)d->voices;
     int rc = MXB_OK;
 #define TRY(x) do { rc = (x); if (rc != MXB_OK) { free_bank(b); return rc; } } while (0)
@@ -390,6 +392,7 @@ int32_t mxb_bank_get_state(mxb_bank* b, int32_t id, double* values, int32_t mem)
     else if (id == MXB_S_FILT_2) src = b->f2;
     else if (id == MXB_S_ENV_AMPLITUDE) src = b->env_amp;
     else if (id == MXB_S_ENV_OUTPUT) src = b->env_output;
+    else if (id == MXB_S_OSC_OUTPUT) src = b->osc_out;
     if (src) { MXB_CUDA(cudaMemcpy(values, src, sizeof(double) * V, kind)); return MXB_OK; }
     // integer state, returned as doubles
     std::vector<double> h(V, 0.0);
@@ -418,13 +421,99 @@ int32_t mxb_bank_get_ring(mxb_bank* b, int32_t voice, double* dst, int32_t n, in
     MXB_REQUIRE(voice >= 0 && voice < b->V && n >= 0 && n <= b->desc.delay_taps, MXB_ERR_INVALID, "mxb_bank_get_ring: voice %d n %d", voice, n);
     DeviceGuard g(b->ctx->device);
     MXB_CUDA(cudaDeviceSynchronize());
-    // de-interleave the chunked ring (delay_kernels.cuh): chunk c of this voice is 32 slots at (c*V + voice)*32
+    // de-interleave the chunked ring (delay_kernels.cuh): chunk c of this voice is kDlChunk slots at (c*V + voice)*kDlChunk
     const cudaMemcpyKind kind = mem == MXB_MEM_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
     const size_t cb = sizeof(double) * kDlChunk;
     const int full = n / kDlChunk, rem = n % kDlChunk;
     const double* src = b->ring + (size_t)voice * kDlChunk;
     if (full) MXB_CUDA(cudaMemcpy2D(dst, cb, src, cb * (size_t)b->V, cb, (size_t)full, kind));
     if (rem) MXB_CUDA(cudaMemcpy(dst + (size_t)full * kDlChunk, src + (size_t)full * kDlChunk * (size_t)b->V, sizeof(double) * (size_t)rem, kind));
+    return MXB_OK;
+}
+
+int32_t mxb_bank_set_ring(mxb_bank* b, int32_t voice, const double* src, int32_t n, int32_t mem) {
+    MXB_REQUIRE(b && src, MXB_ERR_INVALID, "mxb_bank_set_ring: NULL argument");
+    MXB_REQUIRE(b->ring, MXB_ERR_STATE, "mxb_bank_set_ring: bank has no delay line");
+    MXB_REQUIRE(voice >= 0 && voice < b->V && n >= 0 && n <= b->desc.delay_taps, MXB_ERR_INVALID, "mxb_bank_set_ring: voice %d n %d", voice, n);
+    MXB_REQUIRE(mem == MXB_MEM_HOST || mem == MXB_MEM_DEVICE, MXB_ERR_INVALID, "mxb_bank_set_ring: mem %d", mem);
+    DeviceGuard g(b->ctx->device);
+    MXB_CUDA(cudaDeviceSynchronize());
+    const cudaMemcpyKind kind = mem == MXB_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
+    const size_t cb = sizeof(double) * kDlChunk;
+    const int full = n / kDlChunk, rem = n % kDlChunk;
+    double* dst = b->ring + (size_t)voice * kDlChunk;
+    if (full) MXB_CUDA(cudaMemcpy2D(dst, cb * (size_t)b->V, src, cb, cb, (size_t)full, kind));
+    if (rem) MXB_CUDA(cudaMemcpy(dst + (size_t)full * kDlChunk * (size_t)b->V, src + (size_t)full * kDlChunk, sizeof(double) * (size_t)rem, kind));
+    return MXB_OK;
+}
+
+int32_t mxb_bank_set_state(mxb_bank* b, int32_t id, const double* values, int32_t mem) {
+    MXB_REQUIRE(b && values, MXB_ERR_INVALID, "mxb_bank_set_state: NULL argument");
+    MXB_REQUIRE(mem == MXB_MEM_HOST || mem == MXB_MEM_DEVICE, MXB_ERR_INVALID, "mxb_bank_set_state: mem %d", mem);
+    DeviceGuard g(b->ctx->device);
+    MXB_CUDA(cudaDeviceSynchronize());
+    const size_t V = (size_t)b->V;
+    double* dst = nullptr;
+    if (id == MXB_S_FILT_0) dst = b->f0;
+    else if (id == MXB_S_FILT_1) dst = b->f1;
+    else if (id == MXB_S_FILT_2) dst = b->f2;
+    else if (id == MXB_S_ENV_AMPLITUDE) dst = b->env_amp;
+    else if (id == MXB_S_ENV_OUTPUT) dst = b->env_output;
+    else if (id == MXB_S_OSC_OUTPUT) dst = b->osc_out;
+    if (dst) {
+        MXB_CUDA(cudaMemcpy(dst, values, sizeof(double) * V, mem == MXB_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice));
+        return MXB_OK;
+    }
+    MXB_REQUIRE(id == MXB_S_ENV_HOLDCOUNT || id == MXB_S_ENV_FLAGS || id == MXB_S_DELAY_PHASE, MXB_ERR_INVALID,
+                "mxb_bank_set_state: unknown id %d (parameters go through mxb_bank_set_param)", id);
+    std::vector<double> h(V);                     // integer state arrives as doubles, like mxb_bank_get_state returns it
+    MXB_CUDA(cudaMemcpy(h.data(), values, sizeof(double) * V, mem == MXB_MEM_HOST ? cudaMemcpyHostToHost : cudaMemcpyDeviceToHost));
+    if (id == MXB_S_ENV_HOLDCOUNT) {
+        std::vector<long long> t(V);
+        for (size_t v = 0; v < V; ++v) {
+            MXB_REQUIRE(fabs(h[v]) < 2147483648.0, MXB_ERR_INVALID, "mxb_bank_set_state: holdcount[%zu] = %g", v, h[v]);
+            t[v] = (long long)h[v];
+        }
+        MXB_CUDA(cudaMemcpy(b->env_holdcount, t.data(), sizeof(long long) * V, cudaMemcpyHostToDevice));
+    } else {
+        int* d = id == MXB_S_ENV_FLAGS ? b->env_flags : b->dl_phase;
+        MXB_REQUIRE(d, MXB_ERR_STATE, "mxb_bank_set_state: bank has no delay line");
+        std::vector<int> t(V);
+        for (size_t v = 0; v < V; ++v) {
+            MXB_REQUIRE(fabs(h[v]) < 2147483648.0, MXB_ERR_INVALID, "mxb_bank_set_state: value[%zu] = %g", v, h[v]);
+            t[v] = (int)h[v];
+            if (id == MXB_S_ENV_FLAGS) t[v] &= 31;
+        }
+        MXB_CUDA(cudaMemcpy(d, t.data(), sizeof(int) * V, cudaMemcpyHostToDevice));
+    }
+    return MXB_OK;
+}
+
+// Deep copy: parameters, designed coefficients, every state array and the delay rings -- what copying an array of the
+// reference's objects (they hold their state by value, src/maximilian.h:266-281) does. The copy lives on the same context.
+int32_t mxb_bank_clone(mxb_bank* src, mxb_bank** out) {
+    MXB_REQUIRE(src && out, MXB_ERR_INVALID, "mxb_bank_clone: NULL argument");
+    *out = nullptr;
+    mxb_bank* b = nullptr;
+    int rc = mxb_bank_create(src->ctx, &src->desc, &b);
+    if (rc != MXB_OK) return rc;
+    DeviceGuard g(src->ctx->device);
+    const size_t V = (size_t)src->V;
+    cudaError_t e = cudaDeviceSynchronize();
+    auto cp = [&](void* d, const void* s, size_t bytes) { if (e == cudaSuccess && d && s) e = cudaMemcpy(d, s, bytes, cudaMemcpyDeviceToDevice); };
+    for (int i = 0; i < MXB_P_COUNT; ++i) { b->hp[i] = src->hp[i]; b->set_mask[i] = src->set_mask[i]; cp(b->dp[i], src->dp[i], sizeof(double) * V); }
+    cp(b->osc_out, src->osc_out, sizeof(double) * V);
+    cp(b->f0, src->f0, sizeof(double) * V); cp(b->f1, src->f1, sizeof(double) * V); cp(b->f2, src->f2, sizeof(double) * V);
+    for (int i = 0; i < 5; ++i) cp(b->cf[i], src->cf[i], sizeof(double) * V);
+    cp(b->env_amp, src->env_amp, sizeof(double) * V); cp(b->env_output, src->env_output, sizeof(double) * V);
+    cp(b->env_holdcount, src->env_holdcount, sizeof(long long) * V); cp(b->env_hold, src->env_hold, sizeof(long long) * V);
+    cp(b->env_flags, src->env_flags, sizeof(int) * V);
+    if (src->desc.delay_taps > 0) {
+        cp(b->dl_phase, src->dl_phase, sizeof(int) * V); cp(b->dl_size, src->dl_size, sizeof(int) * V); cp(b->dl_pos, src->dl_pos, sizeof(int) * V);
+        cp(b->ring, src->ring, sizeof(double) * dl_ring_doubles(V, src->desc.delay_taps));
+    }
+    if (e != cudaSuccess) { set_error("mxb_bank_clone: %s", cudaGetErrorString(e)); mxb_bank_destroy(b); return MXB_ERR_CUDA; }
+    *out = b;
     return MXB_OK;
 }
 
@@ -435,7 +524,7 @@ int32_t mxb_bank_process(mxb_bank* b, int32_t n_frames, const int32_t* trig_on, 
 
 int32_t mxb_bank_process_fm(mxb_bank* b, int32_t n_frames, const double* freq_tv, const int32_t* trig_on, const int32_t* trig_off,
                             void* out, int32_t out_dtype, double* mix, int32_t mem, void* stream_) {
-    mxb_modulation m; m.freq_tv = freq_tv; m.cutoff_tv = nullptr;
+    mxb_modulation m; m.freq_tv = freq_tv; m.cutoff_tv = nullptr; m.delay_size_tv = nullptr;
     return mxb_bank_process_mod(b, n_frames, &m, trig_on, trig_off, out, out_dtype, mix, mem, stream_);
 }
 
@@ -444,6 +533,7 @@ int32_t mxb_bank_process_mod(mxb_bank* b, int32_t n_frames, const mxb_modulation
     MXB_REQUIRE(b, MXB_ERR_INVALID, "mxb_bank_process: NULL bank");
     const double* freq_tv = mod ? mod->freq_tv : nullptr;
     const double* cutoff_tv = mod ? mod->cutoff_tv : nullptr;
+    const double* dsize_tv = mod ? mod->delay_size_tv : nullptr;
     MXB_REQUIRE(n_frames >= 0 && n_frames <= b->desc.max_frames, MXB_ERR_INVALID, "mxb_bank_process: n_frames %d (max_frames %d)", n_frames, b->desc.max_frames);
     MXB_REQUIRE(mem == MXB_MEM_HOST || mem == MXB_MEM_DEVICE || mem == MXB_MEM_SPLIT, MXB_ERR_INVALID, "mxb_bank_process: mem %d", mem);
     const bool host_ctl = mem != MXB_MEM_DEVICE;      // gates and mix in host memory
@@ -470,6 +560,8 @@ int32_t mxb_bank_process_mod(mxb_bank* b, int32_t n_frames, const mxb_modulation
     if (cutoff_tv)
         MXB_REQUIRE(fk == MXB_FILT_LORES || fk == MXB_FILT_HIRES || fk == MXB_FILT_SVF, MXB_ERR_UNSUPPORTED,
                     "mxb_bank_process_mod: per-sample cutoff is built for lores / hires / maxiSVF");
+    if (dsize_tv)
+        MXB_REQUIRE(b->desc.delay_taps > 0, MXB_ERR_UNSUPPORTED, "mxb_bank_process_mod: delay_size_tv on a bank without a delay line");
     // per-sample parameters are control data: they live where the gates live
     auto stage = [&](const double* src, double** buf, size_t* cap, const double** dev) -> int {
         *dev = src;
@@ -489,6 +581,8 @@ int32_t mxb_bank_process_mod(mxb_bank* b, int32_t n_frames, const mxb_modulation
     const double *d_fm = nullptr, *d_cm = nullptr;
     { int rc0 = stage(freq_tv, &b->fm_stage, &b->fm_stage_bytes, &d_fm); if (rc0 != MXB_OK) return rc0; }
     { int rc0 = stage(cutoff_tv, &b->cm_stage, &b->cm_stage_bytes, &d_cm); if (rc0 != MXB_OK) return rc0; }
+    const double* d_ds = nullptr;
+    { int rc0 = stage(dsize_tv, &b->ds_stage, &b->ds_stage_bytes, &d_ds); if (rc0 != MXB_OK) return rc0; }
     if (host_ctl) {
         if (trig_on) {
             MXB_CUDA(cudaMemcpyAsync(b->trig_on, trig_on, sizeof(int) * V, cudaMemcpyHostToDevice, s));
@@ -558,6 +652,7 @@ int32_t mxb_bank_process_mod(mxb_bank* b, int32_t n_frames, const mxb_modulation
         da.phase = b->dl_phase; da.size = b->dl_size; da.feedback = b->dp[MXB_P_DELAY_FEEDBACK];
         da.ring = b->ring; da.taps = b->desc.delay_taps; da.W_out = 0;
         da.from_position = b->desc.delay_mode == MXB_DELAY_FROM_POSITION ? 1 : 0; da.position = b->dl_pos;
+        da.size_tv = d_ds;
         rc = launch_delay_bank(a, da, fk, svf_lp, env, out != nullptr, mix != nullptr, s);
         if (rc != MXB_OK) return rc;
     } else {

@@ -89,15 +89,17 @@ __device__ __forceinline__ void dl_stage(DlVoice& s, double* row, const int tn, 
             row[j] = (m * s.fb) + (x * s.fb) * 0.5;
             y = m;
         } else if (!ALLFAST && s.live) {
-            if (s.ph >= s.size) s.ph = 0;
-            const int idx = min(max(s.ph, 0), d.taps - 1);     // size <= taps is enforced when the parameter is set
+            // `size` is an argument of every call in the reference: with size_tv a new one each sample (double -> int)
+            const int sz = d.size_tv ? (int)d.size_tv[(size_t)t * V + v] : s.size;
+            if (s.ph >= sz) s.ph = 0;
+            const int idx = min(max(s.ph, 0), d.taps - 1);     // size <= taps: enforced for the parameter, the caller's contract for size_tv
             double* slot = d.ring + dl_slot(V, v, idx);
             const double m = *slot;
             if (d.from_position) {
                 // maxiDelayline::dlFromPosition, src/maximilian.cpp:431-439: the output comes from `position`, the
                 // write has chandiv (== 1) where dl() has 0.5
                 int pos = s.pos;
-                if (pos >= s.size) pos = 0;
+                if (pos >= sz) pos = 0;
                 y = d.ring[dl_slot(V, v, min(max(pos, 0), d.taps - 1))];
                 *slot = (m * s.fb) + (x * s.fb) * 1.0;
             } else {
@@ -195,7 +197,7 @@ __global__ void __launch_bounds__(kBankBlock) delay_bank_kernel(const BankArgs a
     s.size = d.size[vv];
     s.fb = d.feedback[vv];
     s.pos = d.from_position ? d.position[vv] : 0;
-    s.fast = s.live && s.size >= kFastMinSize && !d.from_position;      // dlFromPosition: literal path
+    s.fast = s.live && s.size >= kFastMinSize && !d.from_position && !d.size_tv;      // dlFromPosition, per-sample size: literal path
     // ring index of the first access of the next window: the reference tests `phase >= size` before it reads
     int base = (s.ph >= s.size) ? 0 : s.ph;
 

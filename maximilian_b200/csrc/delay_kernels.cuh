@@ -25,6 +25,7 @@ struct DelayArgs {
     int taps;
     int from_position;       // 1: maxiDelayline::dlFromPosition
     const int* position;     // its position argument per voice
+    const double* size_tv;   // optional per-sample size argument [n_frames][V] (integral values), else NULL
     int W_out;               // [out] warps in the launched grid (mix partials stride)
 };
 

@@ -343,17 +343,18 @@ int32_t mxo_bank_process(void* h, int32_t nframes, const int32_t* trig_on, const
 
 int32_t mxo_bank_process_fm(void* h, int32_t nframes, const double* freq_tv, const int32_t* trig_on, const int32_t* trig_off,
                             double* out, double* mix, int32_t first, int32_t count) {
-    return mxo_bank_process_mod(h, nframes, freq_tv, NULL, trig_on, trig_off, out, mix, first, count);
+    return mxo_bank_process_mod(h, nframes, freq_tv, NULL, NULL, trig_on, trig_off, out, mix, first, count);
 }
 
-int32_t mxo_bank_process_mod(void* h, int32_t nframes, const double* freq_tv, const double* cutoff_tv, const int32_t* trig_on,
-                             const int32_t* trig_off, double* out, double* mix, int32_t first, int32_t count) {
+int32_t mxo_bank_process_mod(void* h, int32_t nframes, const double* freq_tv, const double* cutoff_tv, const double* delay_size_tv,
+                             const int32_t* trig_on, const int32_t* trig_off, double* out, double* mix, int32_t first, int32_t count) {
     bank_t* b = (bank_t*)h;
     if (!b || nframes < 0 || first < 0 || count < 0 || first + count > b->V) return -1;
     const mxo_chain* c = &b->chain;
     const int V = b->V;
     const double sr = (double)(size_t)c->sample_rate;     /* maxiSettings::sampleRate is a size_t, src/maximilian.h:124 */
     if (cutoff_tv && c->filt_kind == MXO_FILT_BIQUAD) return -3;
+    if (delay_size_tv && !c->delay_on) return -3;
     for (int t = 0; t < nframes; ++t) {
         double m0 = 0.0, m1 = 0.0;
         for (int v = first; v < first + count; ++v) {
@@ -431,7 +432,8 @@ int32_t mxo_bank_process_mod(void* h, int32_t nframes, const double* freq_tv, co
             }
             if (c->delay_on) {
                 /* maxiDelayline::dl, src/maximilian.cpp:420-429 */
-                const int size = (int)b->p[MXO_P_DELAY_SIZE][v];
+                /* `size` is an int argument of every call: a flanger passes a new one each sample (double -> int conversion) */
+                const int size = delay_size_tv ? (int)delay_size_tv[(size_t)t * (size_t)V + (size_t)v] : (int)b->p[MXO_P_DELAY_SIZE][v];
                 const double feedback = b->p[MXO_P_DELAY_FEEDBACK][v];
                 double* memory = b->ring + (size_t)v * (size_t)c->delay_capacity;
                 int phase = b->dl_phase[v];

@@ -97,8 +97,10 @@ int32_t mxo_bank_process_fm(void* bank, int32_t nframes, const double* freq_tv, 
 /* ... and a per-sample filter cutoff cutoff_tv[t][v] (NULL = the MXO_P_CUTOFF array): lores/hires take the cutoff as an
  * argument of every call (src/maximilian.cpp:455,471); for maxiSVF the patch calls setCutoff() before play() on every
  * sample (src/maximilian.h:1287-1290, tests/svftest in the reference). The modulation lasts for this call: afterwards
- * the MXO_P_CUTOFF values are in force again. Not available for maxiBiquad (returns -3). */
-int32_t mxo_bank_process_mod(void* bank, int32_t nframes, const double* freq_tv, const double* cutoff_tv,
+ * the MXO_P_CUTOFF values are in force again. Not available for maxiBiquad (returns -3).
+ * delay_size_tv[t][v] (integral values): the `size` argument of maxiDelayline::dl / dlFromPosition, which a flanger or
+ * chorus changes on every call (src/maximilian.cpp:420,431; maxiFlanger::flange, src/maximilian.h:1144-1180). */
+int32_t mxo_bank_process_mod(void* bank, int32_t nframes, const double* freq_tv, const double* cutoff_tv, const double* delay_size_tv,
                              const int32_t* trig_on, const int32_t* trig_off, double* out, double* mix, int32_t first, int32_t count);
 /* copies ring slots [0, n) of voice v */
 int32_t mxo_bank_get_ring(void* bank, int32_t v, double* dst, int32_t n);

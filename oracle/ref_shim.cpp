@@ -189,11 +189,11 @@ int32_t mxo_bank_process(void* h, int32_t nframes, const int32_t* trig_on, const
 
 int32_t mxo_bank_process_fm(void* h, int32_t nframes, const double* freq_tv, const int32_t* trig_on, const int32_t* trig_off,
                             double* out, double* mix, int32_t first, int32_t count) {
-    return mxo_bank_process_mod(h, nframes, freq_tv, nullptr, trig_on, trig_off, out, mix, first, count);
+    return mxo_bank_process_mod(h, nframes, freq_tv, nullptr, nullptr, trig_on, trig_off, out, mix, first, count);
 }
 
-int32_t mxo_bank_process_mod(void* h, int32_t nframes, const double* freq_tv, const double* cutoff_tv, const int32_t* trig_on,
-                             const int32_t* trig_off, double* out, double* mix, int32_t first, int32_t count) {
+int32_t mxo_bank_process_mod(void* h, int32_t nframes, const double* freq_tv, const double* cutoff_tv, const double* delay_size_tv,
+                             const int32_t* trig_on, const int32_t* trig_off, double* out, double* mix, int32_t first, int32_t count) {
     RefBank* b = (RefBank*)h;
     if (!b || nframes < 0 || first < 0 || count < 0 || first + count > b->V) return -1;
     const mxo_chain& c = b->chain;
@@ -207,6 +207,7 @@ int32_t mxo_bank_process_mod(void* h, int32_t nframes, const double* freq_tv, co
     const double* pan = b->p[MXO_P_PAN].data();
     if ((c.filt_kind == MXO_FILT_LORES || c.filt_kind == MXO_FILT_HIRES) && ((!fc && !cutoff_tv) || !q)) return -2;
     if (cutoff_tv && c.filt_kind == MXO_FILT_BIQUAD) return -3;
+    if (delay_size_tv && !c.delay_on) return -3;
     std::vector<double> two(2, 0.0);
     for (int t = 0; t < nframes; ++t) {
         double m0 = 0.0, m1 = 0.0;
@@ -229,8 +230,9 @@ int32_t mxo_bank_process_mod(void* h, int32_t nframes, const double* freq_tv, co
                 case MXO_FILT_BIQUAD:x = r.bq.play(x); break;
                 default: break;
             }
-            if (c.delay_on == 1) x = b->delays[v]->dl(x, (int)dsize[v], dfb[v]);
-            else if (c.delay_on == 2) x = b->delays[v]->dlFromPosition(x, (int)dsize[v], dfb[v], (int)b->p[MXO_P_DELAY_POSITION][v]);
+            const int dsz = delay_size_tv ? (int)delay_size_tv[(size_t)t * V + v] : (int)dsize[v];
+            if (c.delay_on == 1) x = b->delays[v]->dl(x, dsz, dfb[v]);
+            else if (c.delay_on == 2) x = b->delays[v]->dlFromPosition(x, dsz, dfb[v], (int)b->p[MXO_P_DELAY_POSITION][v]);
             if (out) out[(size_t)t * V + v] = x;
             if (mix) { r.mixer.stereo(x, two, pan[v]); m0 += two[0]; m1 += two[1]; }
         }

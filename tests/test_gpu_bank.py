@@ -191,6 +191,64 @@ def test_delay_envelope_steady_windows(port, filt):
     assert np.count_nonzero(g.get("env_amplitude") == 0.0) >= V // 4      # the release-to-zero case was reached
 
 
+@pytest.mark.parametrize("delay", ["dl", "position"])
+def test_per_sample_delay_size(port, delay):
+    """the `size` argument of dl()/dlFromPosition() changing on every call (flanger / chorus):
+    ring indices and samples bit-identical, block after block, then back to the block-constant size."""
+    from test_oracle_vs_reference import flanger_sizes
+    V, B, cap = 100, 300, 256
+    p = W.voice_params(V, seed=41, delay_size=cap, ragged_delay=True)
+    g = gpu_bank(V, osc="saw", filt="lores", env=True, delay=delay, delay_capacity=cap, max_frames=B)
+    o = port.Bank(V, osc="saw", filt="lores", env=True, delay=delay, delay_capacity=cap)
+    W.configure_bank(g, "lores", p, env=True, delay=True); W.configure_bank(o, "lores", p, env=True, delay=True)
+    if delay == "position":
+        pos = (np.arange(V) % 40).astype(np.float64) * 3.0
+        g.set("delay_position", pos); o.set("delay_position", pos)
+    for blk in range(3):
+        on, off = W.gate(V, B, blk); sz = flanger_sizes(V, B, blk, cap)
+        og, mg = g.process(B, on, off, delay_size_tv=sz, want_mix=True); oo, mo = o.process(B, on, off, delay_size_tv=sz, want_mix=True)
+        _close(og, oo, False, f"swept size blk{blk}")
+        np.testing.assert_allclose(mg, mo, rtol=1e-9, atol=1e-11)
+        assert np.array_equal(g.get("delay_phase"), o.get("delay_phase")), blk
+    og, _ = g.process(B); oo, _ = o.process(B)
+    _close(og, oo, False, "back to the block-constant size")
+    for v in range(0, V, 9):
+        assert np.array_equal(g.ring(v, cap), o.ring(v, cap)), v
+    nd = gpu_bank(8, osc="saw", max_frames=16)
+    with pytest.raises(capi.MxbError):
+        nd.process(16, delay_size_tv=np.full((16, 8), 4.0))
+
+
+def test_clone_and_state_restore(port):
+    """The reference's voices are value objects: copying one forks it, assigning its members restores it. mxb_bank_clone is
+    the copy; get_state/get_ring -> set_state/set_ring into a freshly configured bank is the member-wise restore. Both
+    continue bit-identically (and identically to the oracle, which never stopped)."""
+    V, B, cap = 70, 128, 64
+    p = W.voice_params(V, seed=17, delay_size=cap, ragged_delay=True)
+    mk = lambda: gpu_bank(V, osc="pulse", filt="svf", env=True, delay=True, delay_capacity=cap, max_frames=B)
+    g = mk(); o = port.Bank(V, osc="pulse", filt="svf", env=True, delay=True, delay_capacity=cap)
+    W.configure_bank(g, "svf", p, env=True, delay=True); W.configure_bank(o, "svf", p, env=True, delay=True)
+    for blk in range(2):
+        on, off = W.gate(V, B, blk)
+        g.process(B, on, off); o.process(B, on, off)
+    c = g.clone()                                                   # fork
+    r = mk(); W.configure_bank(r, "svf", p, env=True, delay=True)   # member-wise restore into a fresh bank
+    r.set("phase", g.get("phase"))
+    for s in ("osc_output", "filt0", "filt1", "filt2", "env_amplitude", "env_output", "env_holdcount", "env_flags", "delay_phase"):
+        r.set_state(s, g.get(s))
+    for v in range(V):
+        r.set_ring(v, g.ring(v, cap))
+    for blk in range(2, 4):
+        on, off = W.gate(V, B, blk)
+        og, _ = g.process(B, on, off); oc, _ = c.process(B, on, off); orr, _ = r.process(B, on, off); oo, _ = o.process(B, on, off)
+        assert np.array_equal(og, oo) and np.array_equal(oc, oo) and np.array_equal(orr, oo), blk
+    c.set("freq", 2.0 * p["freq"])                                  # the copies are independent of each other
+    oc, _ = c.process(B); og, _ = g.process(B)
+    assert not np.array_equal(oc, og)
+    with pytest.raises(capi.MxbError):
+        g.set_state("freq", p["freq"])                              # parameters go through set_param
+
+
 def test_delay_with_filter_and_nonpositive_size(port):
     V, B, cap = 40, 130, 128
     p = W.voice_params(V, seed=8, delay_size=cap, ragged_delay=True)

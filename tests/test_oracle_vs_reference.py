@@ -194,6 +194,37 @@ def test_per_sample_cutoff_not_for_biquad(port, reference):
             bq.process(8, cutoff_tv=np.full((8, 4), 500.0))
 
 
+def flanger_sizes(V, B, blk, cap, seed=7):
+    """size[t][v] = delay + triangle-ish LFO * depth * delay + 1, like maxiFlanger::flange feeds dl() (src/maximilian.h:1144-1180);
+    some voices sweep down to 1 slot, some stay constant; every value <= cap."""
+    rng = np.random.default_rng(seed)
+    delay = rng.integers(8, cap // 2, V).astype(np.float64); depth = rng.random(V); rate = 0.5 + 20.0 * rng.random(V)
+    depth[::5] = 0.0
+    t = (blk * B + np.arange(B))[:, None] / 48000.0
+    lfo = 2.0 * np.abs(2.0 * ((rate[None, :] * t) % 1.0) - 1.0) - 1.0
+    return np.clip(np.floor(delay[None, :] + lfo * depth[None, :] * delay[None, :] + 1.0), 1, cap)
+
+
+@pytest.mark.parametrize("delay", ["dl", "position"])
+def test_per_sample_delay_size_bit_exact(port, reference, delay):
+    V, B, cap = 10, 300, 256            # small V: every reference maxiDelayline is a 5.6 MB object
+    p = W.voice_params(V, seed=41, delay_size=cap, ragged_delay=True)
+    a, b = _pair(port, reference, V, osc="saw", filt="lores", env=True, delay=delay, delay_capacity=cap)
+    _configure(a, "lores", p, True, True); _configure(b, "lores", p, True, True)
+    if delay == "position":
+        pos = np.arange(V, dtype=np.float64) * 3.0
+        a.set("delay_position", pos); b.set("delay_position", pos)
+    for blk in range(3):
+        on, off = W.gate(V, B, blk); sz = flanger_sizes(V, B, blk, cap)
+        oa, _ = a.process(B, on, off, delay_size_tv=sz); ob, _ = b.process(B, on, off, delay_size_tv=sz)
+        assert _same(oa, ob), blk
+        assert np.array_equal(a.get("delay_phase"), b.get("delay_phase"))
+    oa, _ = a.process(B); ob, _ = b.process(B)          # back to the block-constant size
+    assert _same(oa, ob)
+    for v in range(V):
+        assert _same(a.ring(v, cap), b.ring(v, cap)), v
+
+
 def test_env_ar_bit_exact(port, reference):
     # maxiEnv::ar(input, attack, release, holdtime, trigger), src/maximilian.cpp:1319-1358
     V, B = 48, 400
