@@ -58,7 +58,8 @@ enum {
     MXB_OSC_SQUARE = 4,    /* :293-300 */
     MXB_OSC_PULSE = 5,     /* :302-311 */
     MXB_OSC_IMPULSE = 6,   /* :312-319 */
-    MXB_OSC_TRIANGLE = 7   /* :362-373 */
+    MXB_OSC_TRIANGLE = 7,  /* :362-373 */
+    MXB_OSC_PHASORBETWEEN = 8  /* :321-330, phasorBetween(frequency, startphase, endphase) */
 };
 /* filter kinds */
 enum {
@@ -100,7 +101,9 @@ enum {
     MXB_P_DELAY_FEEDBACK = 12,/* maxiDelayline::dl feedback argument */
     MXB_P_PAN = 13,           /* maxiMix::stereo x (src/maximilian.cpp:503-509) */
     MXB_P_DELAY_POSITION = 14,/* maxiDelayline::dlFromPosition position argument (integral value) */
-    MXB_P_COUNT = 15,
+    MXB_P_PHASOR_START = 15,  /* maxiOsc::phasorBetween startphase */
+    MXB_P_PHASOR_END = 16,    /* maxiOsc::phasorBetween endphase (default 1) */
+    MXB_P_COUNT = 17,
     /* state (mxb_bank_get_state / mxb_bank_set_state) */
     MXB_S_FILT_0 = 32,        /* lores/hires x | svf v0z | biquad v[1] */
     MXB_S_FILT_1 = 33,        /* lores/hires y | svf v1  | biquad v[2] */

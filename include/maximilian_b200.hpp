@@ -187,6 +187,10 @@ public:
     maxiSignal triangle(const maxiParam& frequency) { return osc(MXB_OSC_TRIANGLE, frequency); }
     maxiSignal impulse(const maxiParam& frequency) { return osc(MXB_OSC_IMPULSE, frequency); }
     maxiSignal pulse(const maxiParam& frequency, const maxiParam& duty) { v_->setParam(MXB_P_DUTY, duty); return osc(MXB_OSC_PULSE, frequency); }
+    maxiSignal phasorBetween(const maxiParam& frequency, const maxiParam& startphase, const maxiParam& endphase) {
+        v_->setParam(MXB_P_PHASOR_START, startphase); v_->setParam(MXB_P_PHASOR_END, endphase);
+        return osc(MXB_OSC_PHASORBETWEEN, frequency);
+    }
     void phaseReset(const maxiParam& phaseIn) { v_->setParam(MXB_P_PHASE, phaseIn); }
 private:
     maxiSignal osc(int kind, const maxiParam& f) { v_->desc_.osc_kind = kind; v_->setParam(MXB_P_FREQ, f); return maxiSignal{v_, 1}; }

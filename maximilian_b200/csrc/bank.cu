@@ -237,7 +237,7 @@ int32_t mxb_bank_create(mxb_ctx* ctx, const mxb_bank_desc* d, mxb_bank** out) {
     MXB_REQUIRE(ctx && d && out, MXB_ERR_INVALID, "mxb_bank_create: NULL argument");
     *out = nullptr;
     MXB_REQUIRE(d->voices > 0, MXB_ERR_INVALID, "mxb_bank_create: voices %d", d->voices);
-    MXB_REQUIRE(d->osc_kind >= MXB_OSC_SINEWAVE && d->osc_kind <= MXB_OSC_TRIANGLE, MXB_ERR_INVALID, "mxb_bank_create: osc_kind %d", d->osc_kind);
+    MXB_REQUIRE(d->osc_kind >= MXB_OSC_SINEWAVE && d->osc_kind <= MXB_OSC_PHASORBETWEEN, MXB_ERR_INVALID, "mxb_bank_create: osc_kind %d", d->osc_kind);
     MXB_REQUIRE(d->filt_kind >= MXB_FILT_NONE && d->filt_kind <= MXB_FILT_BIQUAD, MXB_ERR_INVALID, "mxb_bank_create: filt_kind %d", d->filt_kind);
     MXB_REQUIRE(d->biquad_type >= MXB_BQ_LOWPASS && d->biquad_type <= MXB_BQ_HIGHSHELF, MXB_ERR_INVALID, "mxb_bank_create: biquad_type %d", d->biquad_type);
     MXB_REQUIRE(d->env_kind == MXB_ENV_NONE || d->env_kind == MXB_ENV_ADSR || d->env_kind == MXB_ENV_AR, MXB_ERR_INVALID, "mxb_bank_create: env_kind %d", d->env_kind);
@@ -262,7 +262,7 @@ int32_t mxb_bank_create(mxb_ctx* ctx, const mxb_bank_desc* d, mxb_bank** out) {
     const size_t V = (size_t)d->voices;
     int rc = MXB_OK;
 #define TRY(x) do { rc = (x); if (rc != MXB_OK) { free_bank(b); return rc; } } while (0)
-    static const double defaults[MXB_P_COUNT] = {0, 0, 0.5, 1000.0, 1.0, 0, 0, 0, 0, 0, 1.0, 1.0, 0, 0.5, 0};
+    static const double defaults[MXB_P_COUNT] = {0, 0, 0.5, 1000.0, 1.0, 0, 0, 0, 0, 0, 1.0, 1.0, 0, 0.5, 0, 0, 1.0};
     for (int i = 0; i < MXB_P_COUNT; ++i) {
         TRY(dev_alloc(&b->dp[i], V));
         b->hp[i].assign(V, defaults[i]);
@@ -627,7 +627,7 @@ int32_t mxb_bank_process_mod(mxb_bank* b, int32_t n_frames, const mxb_modulation
     a.sr = (double)(size_t)b->ctx->sample_rate;
     for (int i = 0; i < 4; ++i) a.svf_mix[i] = b->desc.svf_mix[i];
     a.freq_tv = d_fm; a.cutoff_tv = d_cm; a.res = b->dp[MXB_P_RESONANCE];
-    a.freq = b->dp[MXB_P_FREQ]; a.duty = b->dp[MXB_P_DUTY]; a.phase = b->dp[MXB_P_PHASE]; a.osc_out = b->osc_out;
+    a.freq = b->dp[MXB_P_FREQ]; a.duty = b->dp[MXB_P_DUTY]; a.pstart = b->dp[MXB_P_PHASOR_START]; a.pend = b->dp[MXB_P_PHASOR_END]; a.phase = b->dp[MXB_P_PHASE]; a.osc_out = b->osc_out;
     a.f0 = b->f0; a.f1 = b->f1; a.f2 = b->f2;
     for (int i = 0; i < 5; ++i) a.cf[i] = b->cf[i];
     a.env_att = b->dp[MXB_P_ENV_ATTACK]; a.env_dec = b->dp[MXB_P_ENV_DECAY];

@@ -52,7 +52,7 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 __device__ __forceinline__ void cp_async_wait1() { asm volatile("cp.async.wait_group 1;\n" ::: "memory"); }
 
 struct DlVoice {
-    double phase, oout, inc, duty, fb, gl, gr;
+    double phase, oout, inc, duty, pend, fb, gl, gr;
     FiltRegs fr;
     EnvRegs er;
     int ph, size, pos;
@@ -71,7 +71,7 @@ __device__ __forceinline__ void dl_stage(DlVoice& s, double* row, const int tn, 
 #pragma unroll 4
     for (int j = 0; j < tn; ++j) {
         const int t = t0 + j;
-        double x = osc_tick<OSC>(s.phase, s.oout, s.inc, s.duty, a.osc_kind);
+        double x = osc_tick<OSC>(s.phase, s.oout, s.inc, s.duty, a.osc_kind, s.pend);
         if (ENV && ESTEADY) {
             // what env_tick() reduces to in the steady states -- same operands, same roundings
             if (relmode) { if (s.er.amp > 0.) { s.er.amp *= s.er.rel; s.er.output = x * s.er.amp; } }
@@ -172,8 +172,10 @@ __global__ void __launch_bounds__(kBankBlock) delay_bank_kernel(const BankArgs a
     s.live = v < a.V;
     const long long vv = s.live ? v : 0;
     s.phase = a.phase[vv]; s.oout = a.osc_out[vv];
-    s.duty = (OSC == OSC_T_GENERIC) ? a.duty[vv] : 0.0;
-    s.inc = (1. / (a.sr / (a.freq[vv])));
+    const bool pb = OSC == OSC_T_GENERIC && a.osc_kind == MXB_OSC_PHASORBETWEEN;      // duty / pend carry startphase / endphase
+    s.duty = (OSC == OSC_T_GENERIC) ? (pb ? a.pstart[vv] : a.duty[vv]) : 0.0;
+    s.pend = pb ? a.pend[vv] : 0.0;
+    s.inc = pb ? ((s.pend - s.duty) / (a.sr / (a.freq[vv]))) : (1. / (a.sr / (a.freq[vv])));
     if (FILT != FILT_T_NONE) {
         s.fr.s0 = a.f0[vv]; s.fr.s1 = a.f1[vv]; s.fr.s2 = (FILT == FILT_T_SVF || FILT == FILT_T_SVF_LP) ? a.f2[vv] : 0.0;
         s.fr.c0 = a.cf[0][vv]; s.fr.c1 = a.cf[1][vv];

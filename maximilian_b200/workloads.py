@@ -37,6 +37,10 @@ def voice_params(voices, seed=SEED, delay_size=4096, ragged_delay=False):
     else:
         p["delay_size"] = np.full(voices, float(delay_size))
     p["delay_feedback"] = 0.1 + 0.8 * u(voices)
+    # maxiOsc::phasorBetween(f, startphase, endphase): derived from draws above, so that the seeded sequences (and the
+    # golden fixtures generated from them) stay what they were
+    p["phasor_start"] = 0.4 * p["duty"]
+    p["phasor_end"] = 0.5 + 0.5 * p["pan"]
     return p
 
 
@@ -77,6 +81,8 @@ def configure_bank(bank, filt, p, env=False, delay=False, sample_rate=SAMPLE_RAT
     """Hand one parameter set to anything with a .set(name, values) method
     (the GPU bank and both CPU oracles share the parameter names)."""
     bank.set("freq", p["freq"]); bank.set("phase", p["phase"]); bank.set("duty", p["duty"])
+    if "phasor_start" in p:
+        bank.set("phasor_start", p["phasor_start"]); bank.set("phasor_end", p["phasor_end"])
     if filt in ("lores", "hires"):
         bank.set("cutoff", p["cutoff"]); bank.set("resonance", p["q_lores"])
     elif filt == "svf":

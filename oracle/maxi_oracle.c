@@ -39,7 +39,7 @@ const char* mxo_kind(void) { return "port"; }
 typedef struct {
     mxo_chain chain;
     int V;
-    double* p[16];          /* parameter arrays, index = MXO_P_* */
+    double* p[MXO_P_COUNT]; /* parameter arrays, index = MXO_P_* */
     /* oscillator state: src/maximilian.h:172-177 (phase, output) */
     double* osc_out;        /* maxiOsc::output, read by square()/pulse() when no branch fires */
     /* filter state */
@@ -151,7 +151,7 @@ void* mxo_bank_create(const mxo_chain* chain, int32_t voices) {
     b->V = voices;
     for (int i = 0; i < MXO_P_COUNT; ++i) b->p[i] = dalloc(V, 0.0);
     for (size_t v = 0; v < V; ++v) {
-        b->p[MXO_P_DUTY][v] = 0.5; b->p[MXO_P_DELAY_SIZE][v] = 1.0; b->p[MXO_P_PAN][v] = 0.5;
+        b->p[MXO_P_DUTY][v] = 0.5; b->p[MXO_P_DELAY_SIZE][v] = 1.0; b->p[MXO_P_PAN][v] = 0.5; b->p[MXO_P_PHASOR_END][v] = 1.0;
         b->p[MXO_P_ENV_HOLDTIME][v] = 1.0;          /* src/maximilian.h:913 */
         b->p[MXO_P_CUTOFF][v] = 1000.0; b->p[MXO_P_RESONANCE][v] = 1.0;   /* maxiSVF ctor, src/maximilian.h:1284 */
     }
@@ -219,9 +219,10 @@ int32_t mxo_bank_get_ring(void* h, int32_t v, double* dst, int32_t n) {
 }
 
 /* maxiOsc::*, src/maximilian.cpp:228-235 (sinewave), 276-283 (coswave), 285-291 (phasor),
- * 293-300 (square), 302-311 (pulse), 312-319 (impulse), 333-340 (saw), 362-373 (triangle).
+ * 293-300 (square), 302-311 (pulse), 312-319 (impulse), 321-330 (phasorBetween), 333-340 (saw), 362-373 (triangle).
  * The increment is 1./(sampleRate/frequency) with sampleRate a size_t: two divides, kept. */
-static inline double osc_tick(int kind, double* phase_p, double* output_p, double frequency, double duty, double sr) {
+static inline double osc_tick(int kind, double* phase_p, double* output_p, double frequency, double duty, double sr,
+                              double startphase, double endphase) {
     double phase = *phase_p, output = *output_p;
     switch (kind) {
         case MXO_OSC_SINEWAVE:
@@ -271,6 +272,14 @@ static inline double osc_tick(int kind, double* phase_p, double* output_p, doubl
             phase += (1. / (sr / (frequency)));
             if (phase <= 0.5) output = (phase - 0.25) * 4;
             else output = ((1.0 - phase) - 0.25) * 4;
+            break;
+        case MXO_OSC_PHASORBETWEEN:
+            output = phase;
+            if (phase < startphase) {
+                phase = startphase;
+            }
+            if (phase >= endphase) phase = startphase;
+            phase += ((endphase - startphase) / (sr / (frequency)));
             break;
         default: break;
     }
@@ -361,7 +370,8 @@ int32_t mxo_bank_process_mod(void* h, int32_t nframes, const double* freq_tv, co
             /* the reference takes the frequency by argument on every call: a patch may pass a new one each sample
              * (FM: maximilian_examples/5.FM1/main.cpp:29) */
             const double fq = freq_tv ? freq_tv[(size_t)t * (size_t)V + (size_t)v] : b->p[MXO_P_FREQ][v];
-            double x = osc_tick(c->osc_kind, &b->p[MXO_P_PHASE][v], &b->osc_out[v], fq, b->p[MXO_P_DUTY][v], sr);
+            double x = osc_tick(c->osc_kind, &b->p[MXO_P_PHASE][v], &b->osc_out[v], fq, b->p[MXO_P_DUTY][v], sr,
+                                b->p[MXO_P_PHASOR_START][v], b->p[MXO_P_PHASOR_END][v]);
             if (c->env_kind == MXO_ENV_ADSR) {
                 int trig = (trig_on && trig_off && t >= trig_on[v] && t < trig_off[v]) ? 1 : 0;
                 x = env_adsr(b, v, x, trig);

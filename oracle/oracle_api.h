@@ -33,7 +33,8 @@ extern "C" {
 
 /* stage selectors (values shared with include/maxib200.h) */
 enum { MXO_OSC_SINEWAVE = 0, MXO_OSC_COSWAVE = 1, MXO_OSC_PHASOR = 2, MXO_OSC_SAW = 3,
-       MXO_OSC_SQUARE = 4, MXO_OSC_PULSE = 5, MXO_OSC_IMPULSE = 6, MXO_OSC_TRIANGLE = 7 };
+       MXO_OSC_SQUARE = 4, MXO_OSC_PULSE = 5, MXO_OSC_IMPULSE = 6, MXO_OSC_TRIANGLE = 7,
+       MXO_OSC_PHASORBETWEEN = 8 };   /* maxiOsc::phasorBetween(frequency, startphase, endphase), src/maximilian.cpp:321-330 */
 enum { MXO_FILT_NONE = 0, MXO_FILT_LORES = 1, MXO_FILT_HIRES = 2, MXO_FILT_SVF = 3, MXO_FILT_BIQUAD = 4 };
 enum { MXO_ENV_NONE = 0, MXO_ENV_ADSR = 1 /* maxiEnv::adsr(input, trigger) */,
        MXO_ENV_AR = 2 /* maxiEnv::ar(input, attack, release, holdtime, trigger), src/maximilian.cpp:1319-1358 */ };
@@ -56,7 +57,9 @@ enum {
     MXO_P_DELAY_FEEDBACK = 12,
     MXO_P_PAN = 13,          /* maxiMix::stereo x */
     MXO_P_DELAY_POSITION = 14, /* dlFromPosition position argument, integral value */
-    MXO_P_COUNT = 15,
+    MXO_P_PHASOR_START = 15,   /* phasorBetween startphase */
+    MXO_P_PHASOR_END = 16,     /* phasorBetween endphase */
+    MXO_P_COUNT = 17,
     /* read-only state ids for mxo_bank_get */
     MXO_S_FILT_0 = 32,    /* lores/hires x | svf v0z | biquad v[1] */
     MXO_S_FILT_1 = 33,    /* lores/hires y | svf v1  | biquad v[2] */

@@ -20,12 +20,12 @@ PATHS = {"port": os.path.join(HERE, "libmaxioracle.so"),
          "reference": os.path.join(HERE, "_ref", "libmaxiref.so")}
 
 # stage selectors / ids: keep in sync with oracle_api.h
-OSC = dict(sinewave=0, coswave=1, phasor=2, saw=3, square=4, pulse=5, impulse=6, triangle=7)
+OSC = dict(sinewave=0, coswave=1, phasor=2, saw=3, square=4, pulse=5, impulse=6, triangle=7, phasorbetween=8)
 FILT = dict(none=0, lores=1, hires=2, svf=3, biquad=4)
 BIQUAD = dict(lowpass=0, highpass=1, bandpass=2, notch=3, peak=4, lowshelf=5, highshelf=6)
 P = dict(freq=0, phase=1, duty=2, cutoff=3, resonance=4, gain=5, env_attack=6, env_decay=7,
          env_sustain=8, env_release=9, env_holdtime=10, delay_size=11, delay_feedback=12, pan=13, delay_position=14,
-         filt0=32, filt1=33, filt2=34, env_amplitude=35, env_output=36, env_holdcount=37,
+         phasor_start=15, phasor_end=16, filt0=32, filt1=33, filt2=34, env_amplitude=35, env_output=36, env_holdcount=37,
          env_flags=38, delay_phase=39)
 
 

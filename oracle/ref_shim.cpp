@@ -49,7 +49,7 @@ struct RefBank {
     int V;
     RefVoice* voices;          /* calloc'ed, placement-constructed */
     maxiDelayline** delays;    /* one 5.6 MB object per voice when delay_on */
-    std::vector<double> p[16];
+    std::vector<double> p[MXO_P_COUNT];
 };
 
 template <class T> T* zeroed_new() {
@@ -74,7 +74,7 @@ void apply_biquad(RefBank* b) {
     }
 }
 
-inline double run_osc(maxiOsc& o, int kind, double f, double duty) {
+inline double run_osc(maxiOsc& o, int kind, double f, double duty, double pstart, double pend) {
     switch (kind) {
         case MXO_OSC_SINEWAVE: return o.sinewave(f);
         case MXO_OSC_COSWAVE:  return o.coswave(f);
@@ -84,6 +84,7 @@ inline double run_osc(maxiOsc& o, int kind, double f, double duty) {
         case MXO_OSC_PULSE:    return o.pulse(f, duty);
         case MXO_OSC_IMPULSE:  return o.impulse(f);
         case MXO_OSC_TRIANGLE: return o.triangle(f);
+        case MXO_OSC_PHASORBETWEEN: return o.phasorBetween(f, pstart, pend);
     }
     return 0.0;
 }
@@ -113,6 +114,8 @@ void* mxo_bank_create(const mxo_chain* chain, int32_t voices) {
     /* defaults so that an unset parameter behaves like an untouched reference object */
     b->p[MXO_P_FREQ].assign(voices, 0.0);
     b->p[MXO_P_DUTY].assign(voices, 0.5);
+    b->p[MXO_P_PHASOR_START].assign(voices, 0.0);
+    b->p[MXO_P_PHASOR_END].assign(voices, 1.0);
     b->p[MXO_P_DELAY_SIZE].assign(voices, 1.0);
     b->p[MXO_P_DELAY_FEEDBACK].assign(voices, 0.0);
     b->p[MXO_P_PAN].assign(voices, 0.5);
@@ -213,7 +216,8 @@ int32_t mxo_bank_process_mod(void* h, int32_t nframes, const double* freq_tv, co
         double m0 = 0.0, m1 = 0.0;
         for (int v = first; v < first + count; ++v) {
             RefVoice& r = b->voices[v];
-            double x = run_osc(r.osc, c.osc_kind, freq_tv ? freq_tv[(size_t)t * V + v] : freq[v], duty[v]);
+            double x = run_osc(r.osc, c.osc_kind, freq_tv ? freq_tv[(size_t)t * V + v] : freq[v], duty[v],
+                               b->p[MXO_P_PHASOR_START][v], b->p[MXO_P_PHASOR_END][v]);
             if (c.env_kind == MXO_ENV_ADSR) {
                 int trig = (trig_on && trig_off && t >= trig_on[v] && t < trig_off[v]) ? 1 : 0;
                 x = r.env.adsr(x, trig);

@@ -19,7 +19,7 @@ from maximilian_b200 import workloads as W
 
 pytestmark = pytest.mark.gpu
 
-OSCS = ["sinewave", "coswave", "phasor", "saw", "square", "pulse", "impulse", "triangle"]
+OSCS = ["sinewave", "coswave", "phasor", "saw", "square", "pulse", "impulse", "triangle", "phasorbetween"]
 FILTS = ["none", "lores", "hires", "svf", "biquad"]
 TRIG = {"sinewave", "coswave"}
 
@@ -249,12 +249,13 @@ def test_clone_and_state_restore(port):
         g.set_state("freq", p["freq"])                              # parameters go through set_param
 
 
-def test_delay_with_filter_and_nonpositive_size(port):
+@pytest.mark.parametrize("osc", ["triangle", "phasorbetween"])
+def test_delay_with_filter_and_nonpositive_size(port, osc):
     V, B, cap = 40, 130, 128
     p = W.voice_params(V, seed=8, delay_size=cap, ragged_delay=True)
     p["delay_size"][:3] = [0.0, -3.0, 1.0]
-    g = gpu_bank(V, osc="triangle", filt="svf", delay=True, delay_capacity=cap, max_frames=B)
-    o = port.Bank(V, osc="triangle", filt="svf", delay=True, delay_capacity=cap)
+    g = gpu_bank(V, osc=osc, filt="svf", delay=True, delay_capacity=cap, max_frames=B)
+    o = port.Bank(V, osc=osc, filt="svf", delay=True, delay_capacity=cap)
     W.configure_bank(g, "svf", p, delay=True); W.configure_bank(o, "svf", p, delay=True)
     for blk in range(3):
         og, _ = g.process(B); oo, _ = o.process(B)
@@ -269,7 +270,7 @@ def test_per_sample_frequency_with_envelope_is_refused():
 
 
 @pytest.mark.parametrize("osc,filt,delay", [("sinewave", "none", False), ("saw", "svf", False), ("phasor", "biquad", False),
-                                            ("triangle", "lores", False)])
+                                            ("triangle", "lores", False), ("phasorbetween", "hires", False)])
 def test_per_sample_frequency_fm(port, osc, filt, delay):
     """audio-rate modulated oscillator frequency, mxb_bank_process_fm."""
     from test_oracle_vs_reference import fm_frequencies

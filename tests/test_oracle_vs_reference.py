@@ -11,7 +11,7 @@ import pytest
 
 from maximilian_b200 import workloads as W
 
-OSCS = ["sinewave", "coswave", "phasor", "saw", "square", "pulse", "impulse", "triangle"]
+OSCS = ["sinewave", "coswave", "phasor", "saw", "square", "pulse", "impulse", "triangle", "phasorbetween"]
 FILTS = ["none", "lores", "hires", "svf", "biquad"]
 
 
