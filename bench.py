@@ -214,6 +214,27 @@ def reference_arm(args, wl_name, wl):
 
 # ------------------------------------------------------------------------------------------------ GPU leg
 
+def onbox_peaks(torch, out):
+    """the streaming-WRITE and copy bandwidth of THIS box, measured with library kernels on the output
+    buffer the bank just wrote (torch fill_ / copy_, best of 5, CUDA events), reported beside the driver-measured copy
+    peak: the bank kernel is write-only traffic, which the copy figure does not isolate."""
+    try:
+        flat = out.view(-1)
+        half = flat.numel() // 2
+        a, b = flat[:half], flat[half:2 * half]
+        best_fill = best_copy = 0.0
+        for _ in range(5):
+            e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            e0.record(); flat.fill_(0.0); e1.record(); b.copy_(a); e2.record()
+            torch.cuda.synchronize()
+            best_fill = max(best_fill, flat.numel() * flat.element_size() / (e0.elapsed_time(e1) * 1e-3) / 1e9)
+            best_copy = max(best_copy, 2 * half * flat.element_size() / (e1.elapsed_time(e2) * 1e-3) / 1e9)
+        return {"fill_gbs": best_fill, "copy_gbs": best_copy,
+                "how": "torch fill_ over the %.1f GB output buffer (write-only) and copy_ of one half onto the other (read+write bytes), best of 5" % (flat.numel() * flat.element_size() / 1e9)}
+    except Exception as e:      # a missing number must not take the bench line down
+        return {"error": str(e)[:200]}
+
+
 def measure_mixdown(args, torch, dist, capi, W, ctx, dev, rank, world, mix, stream, barrier, sm_mhz):
     """BASELINE.json configs[4] in SURVEY.md 8(d)'s "mix mode", one shard per GPU: 1 Mi voices maxiOsc::saw ->
     maxiBiquad -> maxiMix::stereo -> sum over voices; no per-voice output is written, the stereo bus [1024][2] is the
@@ -418,6 +439,8 @@ def main():
     h2d = fh.nbytes + (on_h.nbytes + off_h.nbytes if on_h is not None else 0)
     d2h = mh.nbytes
 
+    onbox = onbox_peaks(torch, out) if rank == 0 else None
+
     if rank == 0:
         peak, peak_src = load_peaks()
         med_ms = per_launch_ms[len(per_launch_ms) // 2]
@@ -444,6 +467,9 @@ def main():
                                                  "host gates in, host mix out, voice signals materialised on the device"},
             "gpu_launches": launches, "clocks": clocks,
         }
+        if onbox:
+            line["roofline"]["onbox_peaks"] = onbox
+            line["roofline"]["frac_of_onbox_fill"] = achieved / onbox["fill_gbs"]
         if mixdown is not None:
             line["mixdown"] = mixdown
         if not args.no_cpu and world == 1:

@@ -38,6 +38,21 @@
 
 #include "maxib200.h"
 
+/* Source compatibility with patches written against src/maximilian.h: the reference header pulls
+ * namespace std in (:54) and defines these (:55-67), and user patches rely on both (`vector<double>`, `cout`, PI). */
+#ifndef MAXIMILIAN_B200_NO_STD_NAMESPACE
+using namespace std;
+#endif
+#ifndef PI
+#define PI 3.1415926535897932384626433832795
+#endif
+#ifndef TWOPI
+#define TWOPI 6.283185307179586476925286766559
+#endif
+#ifndef CHEERP_EXPORT
+#define CHEERP_EXPORT
+#endif
+
 struct maxiError : std::runtime_error {
     int code;
     maxiError(int c, const std::string& what) : std::runtime_error(what), code(c) {}
@@ -260,6 +275,13 @@ public:
         if (input.voices != v_ || input.stage != 1) throw maxiError(MXB_ERR_UNSUPPORTED, "maxiEnv::adsr: input must be the oscillator of the same maxiVoices");
         v_->desc_.env_kind = MXB_ENV_ADSR; v_->gate_ = trigger;
         return maxiSignal{v_, 2};
+    }
+    /* the overload that takes the raw coefficients as arguments (src/maximilian.cpp:1362-1413): the same state machine */
+    maxiSignal adsr(maxiSignal input, const maxiParam& attack, const maxiParam& decay, const maxiParam& sustain, const maxiParam& release,
+                    const maxiParam& holdtime, const maxiGate& trigger) {
+        v_->setParam(MXB_P_ENV_ATTACK, attack); v_->setParam(MXB_P_ENV_DECAY, decay); v_->setParam(MXB_P_ENV_SUSTAIN, sustain);
+        v_->setParam(MXB_P_ENV_RELEASE, release); v_->setParam(MXB_P_ENV_HOLDTIME, holdtime);
+        return adsr(input, trigger);
     }
     /* maxiEnv::ar(input, attack, release, holdtime, trigger): attack/release are the raw per-sample coefficients the
      * reference takes as arguments (defaults 1, 0.9, holdtime 1) */
