@@ -66,6 +66,52 @@ def chains():
     np.savez_compressed(os.path.join(HERE, "chains.npz"), **out)
 
 
+MODS = [  # (name, osc, filt, env, delay, which per-sample arrays)
+    ("phasorbetween_hires", "phasorbetween", "hires", False, False, ()),
+    ("saw_svf_swept_cutoff", "saw", "svf", False, False, ("cutoff",)),
+    ("phasor_lores_swept_cutoff_fm", "phasor", "lores", False, False, ("cutoff", "freq")),
+    ("saw_env_lores_flanged_delay", "saw", "lores", True, True, ("delay_size",)),
+]
+
+
+def mod_arrays(V, B, blk, cap):
+    """Per-sample parameter arrays of the modulated cases (deterministic; stored in the fixture as well)."""
+    rng = np.random.default_rng(77)
+    t = (blk * B + np.arange(B))[:, None] / 48000.0
+    centre = 200.0 * np.exp2(4.0 * rng.random(V)); depth = 1.5 * rng.random(V); rate = 0.2 + 6.0 * rng.random(V)
+    cutoff = centre[None, :] * np.exp2(depth[None, :] * np.sin(2 * np.pi * rate[None, :] * t))
+    carrier = 110.0 * np.exp2(3.0 * rng.random(V)); fdepth = 50.0 * rng.random(V); frate = 0.5 + 8.0 * rng.random(V)
+    freq = carrier[None, :] + fdepth[None, :] * np.sin(2 * np.pi * frate[None, :] * t)
+    delay = rng.integers(8, cap // 2, V).astype(np.float64); ddepth = rng.random(V); drate = 0.5 + 20.0 * rng.random(V)
+    lfo = 2.0 * np.abs(2.0 * ((drate[None, :] * t) % 1.0) - 1.0) - 1.0
+    dsize = np.clip(np.floor(delay[None, :] + lfo * ddepth[None, :] * delay[None, :] + 1.0), 1, cap)
+    return {"cutoff": cutoff, "freq": freq, "delay_size": dsize}
+
+
+def mods():
+    """SURVEY.md 8(a)-3 phasorBetween and the 8(f) per-sample arguments (frequency, cutoff, delay size), from the reference."""
+    V, B, NB, cap = 8, 96, 3, 96
+    out = {"V": V, "B": B, "NB": NB, "cap": cap}
+    for name, osc, filt, env, delay, which in MODS:
+        p = W.voice_params(V, seed=4321, delay_size=cap, ragged_delay=True)
+        b = O.Bank(V, osc=osc, filt=filt, env=env, delay=delay, delay_capacity=cap, kind=KIND)
+        configure(b, filt, p, env, delay)
+        outs, mixes = [], []
+        for blk in range(NB):
+            on, off = W.gate(V, B, 4 * blk if blk < 2 else 1)
+            m = mod_arrays(V, B, blk, cap)
+            kw = {k + "_tv": m[k] for k in which}
+            for k in which:
+                out[f"{name}/{k}_tv/{blk}"] = m[k]
+            o, mx = b.process(B, on if env else None, off if env else None, want_mix=True, **kw)
+            outs.append(o); mixes.append(mx)
+        out[name + "/out"] = np.stack(outs); out[name + "/mix"] = np.stack(mixes)
+        out[name + "/phase"] = b.get("phase")
+        if delay:
+            out[name + "/delay_phase"] = b.get("delay_phase").astype(np.int32)
+    np.savez_compressed(os.path.join(HERE, "mods.npz"), **out)
+
+
 def seeds():
     """The SURVEY.md section 8(c) seed values, regenerated (sr 48000)."""
     out = {}
@@ -105,7 +151,7 @@ def spectral():
 
 if __name__ == "__main__":
     O.build("reference")
-    chains(); seeds(); spectral()
+    chains(); seeds(); spectral(); mods()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)), "bytes")

@@ -78,3 +78,31 @@ def run_chain_case(make_bank, case, exact, exact_mix=None):
         assert np.array_equal(b.get("env_flags").astype(np.int32), g[name + "/env_flags"]), name
         assert_samples_close(b.get("env_amplitude"), g[name + "/env_amplitude"], exact, name + " amp")
     return worst
+
+
+def mod_cases():
+    return _load_make_golden().MODS
+
+
+def run_mod_case(make_bank, case, exact, rtol=1e-9):
+    """Replays one tests/golden/mods.npz case (phasorBetween / per-sample frequency, cutoff, delay size). `exact`:
+    compare bits; else |g - r| <= rtol*|r| + 1e-12 (device libm in the per-sample coefficient design)."""
+    name, osc, filt, env, delay, which = case
+    g = load("mods")
+    V, B, NB, cap = int(g["V"]), int(g["B"]), int(g["NB"]), int(g["cap"])
+    p = W.voice_params(V, seed=4321, delay_size=cap, ragged_delay=True)
+    b = make_bank(V, osc=osc, filt=filt, env=env, delay=delay, delay_capacity=cap)
+    W.configure_bank(b, filt, p, env, delay)
+    for blk in range(NB):
+        on, off = W.gate(V, B, 4 * blk if blk < 2 else 1)
+        kw = {k + "_tv": g[f"{name}/{k}_tv/{blk}"] for k in which}
+        o, m = b.process(B, on if env else None, off if env else None, want_mix=True, **kw)
+        if exact:
+            assert np.array_equal(o, g[name + "/out"][blk], equal_nan=True), f"{name} blk{blk}"
+        else:
+            np.testing.assert_allclose(o, g[name + "/out"][blk], rtol=rtol, atol=1e-12, err_msg=f"{name} blk{blk}")
+        np.testing.assert_allclose(m, g[name + "/mix"][blk], rtol=max(rtol, 1e-9), atol=1e-11)
+    if exact:
+        assert np.array_equal(b.get("phase"), g[name + "/phase"]), name
+    if delay:
+        assert np.array_equal(b.get("delay_phase").astype(np.int32), g[name + "/delay_phase"]), name

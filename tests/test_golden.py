@@ -15,6 +15,12 @@ def test_chain_golden_exact(port, case):
     G.run_chain_case(lambda V, **kw: port.Bank(V, kind="port", **kw), case, exact=True)
 
 
+@pytest.mark.parametrize("case", G.mod_cases(), ids=lambda c: c[0])
+def test_modulated_golden_exact(port, case):
+    """phasorBetween and the per-sample frequency / cutoff / delay-size arguments (tests/golden/mods.npz)."""
+    G.run_mod_case(lambda V, **kw: port.Bank(V, kind="port", **kw), case, exact=True)
+
+
 def test_survey_seed_values(port):
     g = G.load("seeds")
     # literal values quoted in SURVEY.md section 8(c)

@@ -42,6 +42,13 @@ def test_golden_chains(case):
     G.run_chain_case(gpu_bank, case, exact=not trig, exact_mix=False)
 
 
+@pytest.mark.parametrize("case", G.mod_cases(), ids=lambda c: c[0])
+def test_golden_modulated(case):
+    """tests/golden/mods.npz (from the compiled reference): bit-identical unless the cutoff is swept, where the coefficient
+    design runs on the device (libdevice cos/sqrt/pow/tan): 1e-9 relative."""
+    G.run_mod_case(gpu_bank, case, exact="cutoff" not in case[5])
+
+
 @pytest.mark.parametrize("osc,filt", list(itertools.product(OSCS, FILTS)))
 def test_every_osc_filter_pair_vs_oracle(port, osc, filt):
     V, B = 333, 129
