@@ -9,16 +9,22 @@ maxiOsc::saw -> maxiSVF (low-pass mix), per-voice fp64 output materialised time-
 voices are independent, so the headline block has no collective at any N.
 
   value      voice-samples/s of the whole job, inputs and state resident in HBM, CUDA-event timed, max over ranks
+  workloads  (N = 1, default run) the other BASELINE.json configurations measured the same way in the same run, each with
+             its own value / roofline / e2e / cpu_baseline:  biquad_bank = configs[4]'s shard in bank mode (saw ->
+             maxiBiquad, output materialised), delay = configs[2] (256 Ki voices saw -> ADSR -> 4096-tap delay line),
+             mfcc = configs[3] (64 Ki channels FFT-1024 / hop 512 + 40 MFCCs, frames/s)
   mixdown    BASELINE.json configs[4] in "mix mode" (SURVEY.md 8(d) config 5), timed separately in the same run:
              1 Mi voices/GPU saw -> maxiBiquad -> maxiMix::stereo -> sum over voices, only the stereo bus is
              written; for N > 1 the bus is summed over the GPUs -- the path's only exchange step (--collective
              p2p: peer-memory exchange fused into the mix-reduce kernel; nccl: all_reduce). fp64-pipe bound,
-             reported as such. `--mix 1` instead adds the bus to the headline block (output AND bus).
-  e2e        the same block through the C ABI with HOST control data: per step one fp64 frequency array
-             (8 MiB) is uploaded stream-ordered with mxb_bank_set_param_async from pinned memory and the stereo
-             mix (16 KiB) is read back by mxb_bank_process(MXB_MEM_SPLIT); the voice signals stay on the device
+             reported as such; `check` compares the exchanged bus with an NCCL all-reduce of the local buses.
+             `--mix 1` instead adds the bus to the headline block (output AND bus).
+  e2e        the same block through the C ABI with HOST control data, pipelined: per step one fp64 frequency array
+             (8 MiB, pinned) goes up with mxb_bank_set_param_async (double-buffered, copy stream) and the stereo mix
+             (16 KiB) comes back with mxb_bank_process(MXB_MEM_SPLIT | MXB_MEM_ASYNC); the voice signals stay on the device
   roofline   algorithmic bytes per launch / CUDA-event launch time against MEASURED_PEAKS.json
-  cpu_baseline  the reference's own scalar code (oracle/_ref, or the C port) on all host cores, bounded sample
+  cpu_baseline  the reference's own scalar code (oracle/_ref) on all host cores (pinned threads, >= 3 s timed), the
+             -O2 parity build and an -O3 -march=x86-64-v3 build side by side; a reported baseline, not the target
 
 `--impl reference` times only that CPU leg with the same metric/config (rank 0; other ranks exit 0).
 """
@@ -47,6 +53,7 @@ WORKLOADS = {
     "delay": dict(voices=1 << 18, osc="saw", filt="none", env=True, delay=4096, bytes_per=24.0 + (108 + 60) / BLOCK,
                   desc="configs[2]: 256Ki voices saw -> maxiEnv::adsr -> maxiDelayline::dl(4096), fp64 out materialised"),
 }
+CPU_BLOCKS_PER_STEP = 8       # the reference arm: one step = this many consecutive blocks of the CPU sample (32 for the delay chain)
 
 
 def load_peaks():
@@ -117,97 +124,184 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------- CPU reference leg
 
 class CpuFarm:
-    """The reference on all host cores: `threads` workers, each owning its own slice of the voices as its own reference
-    objects and its own output slab, all created INSIDE the worker (first touch = local NUMA node). One thread start per
-    run; every worker runs all blocks of its voices (voices are independent: no barrier between blocks)."""
+    """The reference on all host cores. `threads` persistent workers, each pinned to one core of this process's
+    affinity mask (sched_setaffinity), each building its OWN slice of the work inside the worker (first touch = local NUMA
+    node). A run releases all workers through a barrier and times until the last one is back at the next barrier: thread
+    start-up, object construction and page faults of fresh buffers are outside the clock."""
 
-    def __init__(self, wl, voices, threads, kind):
-        from maximilian_b200 import workloads as W
-        from oracle import oracle_py as O
-        self.wl, self.voices, self.kind = wl, voices, kind
-        self.threads = max(1, min(threads, voices))
-        self.bounds = np.linspace(0, voices, self.threads + 1).astype(int)
-        p = W.voice_params(voices, seed=W.SEED, delay_size=wl["delay"] or 4096)
+    def __init__(self, threads, make_part):
+        cores = sorted(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else list(range(os.cpu_count() or 1))
+        self.threads = max(1, threads)
+        self.cores = cores
         self.parts = [None] * self.threads
+        self.job = None
+        self.err = []
+        self._go = threading.Barrier(self.threads + 1)
+        self._done = threading.Barrier(self.threads + 1)
+        self._ts = [threading.Thread(target=self._worker, args=(i, make_part), daemon=True) for i in range(self.threads)]
+        [t.start() for t in self._ts]
+        self._done.wait()                      # every worker has built its part
 
-        def make(i):
-            lo, hi = int(self.bounds[i]), int(self.bounds[i + 1])
-            b = O.Bank(hi - lo, osc=wl["osc"], filt=wl["filt"], env=wl["env"], delay=wl["delay"] > 0, sample_rate=SR,
-                       delay_capacity=max(wl["delay"], 1), kind=kind)
-            W.configure_bank(b, wl["filt"], {k: v[lo:hi] for k, v in p.items()}, wl["env"], wl["delay"] > 0)
-            self.parts[i] = (b, np.zeros((BLOCK, hi - lo), dtype=np.float64))
-        self._par(make)
+    def _worker(self, i, make_part):
+        try:
+            if hasattr(os, "sched_setaffinity"):
+                os.sched_setaffinity(threading.get_native_id(), {self.cores[i % len(self.cores)]})
+        except Exception:
+            pass
+        try:
+            self.parts[i] = make_part(i)
+        except Exception as e:                 # noqa: BLE001 -- reported by run()
+            self.err.append(repr(e))
+        self._done.wait()
+        while True:
+            self._go.wait()
+            if self.job is None:
+                return
+            try:
+                self.job(i, self.parts[i])
+            except Exception as e:             # noqa: BLE001
+                self.err.append(repr(e))
+            self._done.wait()
 
-    def _par(self, fn):
-        ts = [threading.Thread(target=fn, args=(i,)) for i in range(self.threads)]
-        [t.start() for t in ts]
-        [t.join() for t in ts]
-
-    def run(self, nblocks, block_index0=0):
-        """Seconds for `nblocks` consecutive blocks of the whole bank."""
-        from maximilian_b200 import workloads as W
-        from oracle import oracle_py as O
-        gates = [(W.gate(self.voices, BLOCK, block_index0 + k) if self.wl["env"] else (None, None)) for k in range(nblocks)]
-
-        def work(i):
-            lo, hi = int(self.bounds[i]), int(self.bounds[i + 1])
-            b, out = self.parts[i]
-            for on, off in gates:
-                on_i = np.ascontiguousarray(on[lo:hi]) if on is not None else None
-                off_i = np.ascontiguousarray(off[lo:hi]) if off is not None else None
-                rc = b.lib.mxo_bank_process(b.h, BLOCK, O._ip(on_i), O._ip(off_i), O._dp(out), None, 0, hi - lo)
-                assert rc == 0, rc
+    def run(self, job):
+        """Seconds for job(i, part) on every worker, barrier to barrier."""
+        assert not self.err, self.err
+        self.job = job
+        self._go.wait()
         t0 = time.perf_counter()
-        self._par(work)
-        return time.perf_counter() - t0
+        self._done.wait()
+        dt = time.perf_counter() - t0
+        assert not self.err, self.err
+        return dt
+
+    def close(self):
+        self.job = None
+        try:
+            self._go.wait(timeout=5)
+        except Exception:
+            pass
 
 
-def cpu_kind():
+def cpu_kinds():
+    """[parity build, best-effort build] of the compiled reference, or the C port when the reference is absent."""
     from oracle import oracle_py as O
-    if O.available("reference"):
-        return "reference"
-    O.build("port")
-    return "port"
+    kinds = [k for k in ("reference", "reference_o3") if O.available(k)]
+    if not kinds:
+        O.build("port")
+        kinds = ["port"]
+    return kinds
+
+
+CPU_FLAGS = {"reference": "-O2 -ffp-contract=off (the parity build the oracle tests use)",
+             "reference_o3": "-O3 -march=x86-64-v3 (AVX2 + FMA, contraction allowed; best-effort CPU, timed only)",
+             "port": "-O2 -ffp-contract=off (plain-C restatement)"}
 
 
 def cpu_sample_voices(wl):
-    # each reference maxiDelayline is a 5.6 MB object (src/maximilian.h:273): keep the sample in RAM
-    return 512 if wl["delay"] else 65536
+    # each reference maxiDelayline is a 5.6 MB object (src/maximilian.h:273): keep the sample in RAM (16 voices per core,
+    # 512 .. 2048 voices = 2.9 .. 11.5 GB)
+    if wl["delay"]:
+        cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+        return int(min(2048, max(512, 16 * cores)))
+    return 65536
 
 
-def cpu_baseline(wl, budget_s=4.0):
-    kind = cpu_kind()
-    cores = os.cpu_count() or 1
+def cpu_blocks_per_step(wl):
+    return 32 if wl["delay"] else CPU_BLOCKS_PER_STEP
+
+
+def bank_farm(wl, voices, kind):
+    from maximilian_b200 import workloads as W
+    from oracle import oracle_py as O
+    O.load(kind)
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    threads = max(1, min(cores, voices))
+    bounds = np.linspace(0, voices, threads + 1).astype(int)
+    p = W.voice_params(voices, seed=W.SEED, delay_size=wl["delay"] or 4096)
+
+    def make(i):
+        lo, hi = int(bounds[i]), int(bounds[i + 1])
+        b = O.Bank(hi - lo, osc=wl["osc"], filt=wl["filt"], env=wl["env"], delay=wl["delay"] > 0, sample_rate=SR,
+                   delay_capacity=max(wl["delay"], 1), kind=kind)
+        W.configure_bank(b, wl["filt"], {k: v[lo:hi] for k, v in p.items()}, wl["env"], wl["delay"] > 0)
+        out = np.zeros((BLOCK, hi - lo), dtype=np.float64)
+        out[:] = 1.0                                        # touch every page here, on the worker's own core
+        return b, out, lo, hi
+    return CpuFarm(threads, make), threads
+
+
+def bank_job(wl, voices, nblocks, block_index0=0):
+    from maximilian_b200 import workloads as W
+    from oracle import oracle_py as O
+    gates = [(W.gate(voices, BLOCK, block_index0 + k) if wl["env"] else (None, None)) for k in range(nblocks)]
+
+    def job(i, part):
+        b, out, lo, hi = part
+        for on, off in gates:
+            on_i = np.ascontiguousarray(on[lo:hi]) if on is not None else None
+            off_i = np.ascontiguousarray(off[lo:hi]) if off is not None else None
+            rc = b.lib.mxo_bank_process(b.h, BLOCK, O._ip(on_i), O._ip(off_i), O._dp(out), None, 0, hi - lo)
+            assert rc == 0, rc
+    return job
+
+
+def cpu_bank_rate(wl, kind, budget_s, steps=None, warm=1):
+    """voice-samples/s of the reference on all cores; >= budget_s seconds timed (or exactly `steps` steps of
+    CPU_BLOCKS_PER_STEP blocks for the reference arm)."""
     voices = cpu_sample_voices(wl)
-    farm = CpuFarm(wl, voices, cores, kind)
-    farm.run(1)                                                      # warm-up block
+    farm, threads = bank_farm(wl, voices, kind)
+    farm.run(bank_job(wl, voices, warm, 0))
     n, total = 0, 0.0
-    while total < budget_s and n < 128:
-        total += farm.run(8, 1 + n)                                  # 8 blocks per thread start
-        n += 8
-    v = voices * BLOCK * n / total
-    return {"value": v, "unit": "samples/s", "cores": cores, "kind": kind,
-            "sample": f"{voices} voices x {BLOCK} frames x {n} blocks of the same chain; {farm.threads} host threads, each with its own "
-                      "slice of the voices as reference objects (frame-outer / voice-inner like a reference play())"}
+    if steps is not None:
+        total = farm.run(bank_job(wl, voices, steps * cpu_blocks_per_step(wl), warm))
+        n = steps * cpu_blocks_per_step(wl)
+    else:
+        per = CPU_BLOCKS_PER_STEP
+        while total < budget_s and n < 4096:
+            dt = farm.run(bank_job(wl, voices, per, warm + n))
+            total += dt; n += per
+            if dt < budget_s / 4:
+                per *= 2                                    # few, long timed regions
+    farm.close()
+    return voices * BLOCK * n / total, voices, threads, n, total
+
+
+def cpu_baseline(wl, budget_s=3.0):
+    kinds = cpu_kinds()
+    res = {}
+    for k in kinds:
+        v, voices, threads, n, total = cpu_bank_rate(wl, k, budget_s)
+        res[k] = dict(value=v, flags=CPU_FLAGS[k], blocks=n, seconds=total)
+    main = kinds[0]
+    out = {"value": res[main]["value"], "unit": "samples/s", "cores": threads, "kind": "reference" if main.startswith("reference") else "port",
+           "flags": res[main]["flags"], "timed_seconds": res[main]["seconds"],
+           "sample": f"{voices} voices x {BLOCK} frames x {res[main]['blocks']} blocks of the same chain; {threads} pinned host threads, each with its own "
+                     "slice of the voices as reference objects (frame-outer / voice-inner like a reference play())"}
+    if len(kinds) > 1:
+        out["best_effort"] = {"value": res[kinds[1]]["value"], "flags": res[kinds[1]]["flags"], "timed_seconds": res[kinds[1]]["seconds"]}
+    return out
 
 
 def reference_arm(args, wl_name, wl):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    kind = cpu_kind()
-    cores = os.cpu_count() or 1
-    voices = cpu_sample_voices(wl)
-    farm = CpuFarm(wl, voices, cores, kind)
-    farm.run(args.warmup)
-    dt = farm.run(args.steps, args.warmup)
-    v = voices * BLOCK * args.steps / dt
+    kinds = cpu_kinds()
+    kind = kinds[-1]                           # the fastest build of the unmodified reference that exists here
+    v, voices, threads, n, dt = cpu_bank_rate(wl, kind, None, steps=args.steps, warm=max(1, args.warmup))
+    extra = {}
+    if len(kinds) > 1:
+        v2, _, _, n2, dt2 = cpu_bank_rate(wl, kinds[0], 2.0)
+        extra = {"parity_build": {"value": v2, "flags": CPU_FLAGS[kinds[0]], "timed_seconds": dt2}}
     line = {"impl": "reference", "metric": "voice_samples_per_sec", "value": v, "unit": "samples/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": wl["desc"], "cpu_sample_voices": voices, "block": BLOCK, "sample_rate": SR},
-            "cpu_baseline": {"value": v, "unit": "samples/s", "cores": cores, "kind": kind,
-                             "sample": f"each step = {voices} voices x {BLOCK} frames of the same chain on {cores} host threads"},
+            "config": {"workload": wl["desc"], "cpu_sample_voices": voices, "block": BLOCK, "sample_rate": SR,
+                       "blocks_per_step": cpu_blocks_per_step(wl)},
+            "cpu_baseline": {"value": v, "unit": "samples/s", "cores": threads, "kind": "reference" if kind.startswith("reference") else "port",
+                             "flags": CPU_FLAGS[kind], "timed_seconds": dt,
+                             "sample": f"each step = {voices} voices x {BLOCK} frames x {cpu_blocks_per_step(wl)} blocks of the same chain on {threads} pinned host threads",
+                             **extra},
             "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -235,23 +329,245 @@ def onbox_peaks(torch, out):
         return {"error": str(e)[:200]}
 
 
-def measure_mixdown(args, torch, dist, capi, W, ctx, dev, rank, world, mix, stream, barrier, sm_mhz):
+def pcie_rates(torch, dev, mb=256):
+    """Pinned-memory copy rates of this box (GB/s), the ceiling of every e2e number that moves bulk data."""
+    try:
+        h = torch.empty(mb << 20, dtype=torch.uint8).pin_memory()
+        d = torch.empty(mb << 20, dtype=torch.uint8, device=dev)
+        best = [0.0, 0.0]
+        for _ in range(4):
+            e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            e0.record(); d.copy_(h, non_blocking=True); e1.record(); h.copy_(d, non_blocking=True); e2.record()
+            torch.cuda.synchronize()
+            best[0] = max(best[0], (mb << 20) / (e0.elapsed_time(e1) * 1e-3) / 1e9)
+            best[1] = max(best[1], (mb << 20) / (e1.elapsed_time(e2) * 1e-3) / 1e9)
+        return {"h2d_gbs": best[0], "d2h_gbs": best[1]}
+    except Exception as e:
+        return {"error": str(e)[:200]}
+
+
+class Env:
+    """Process-wide pieces shared by the legs."""
+    pass
+
+
+def setup_env(args):
+    import torch
+    import torch.distributed as dist
+    from maximilian_b200 import capi
+    from maximilian_b200 import workloads as W
+    E = Env()
+    E.torch, E.dist, E.capi, E.W = torch, dist, capi, W
+    E.rank = int(os.environ.get("RANK", "0")); E.world = int(os.environ.get("WORLD_SIZE", "1"))
+    E.local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert E.world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE {E.world}"
+    torch.cuda.set_device(E.local)
+    E.dev = torch.device("cuda", E.local)
+    if E.world > 1:
+        dist.init_process_group("nccl", device_id=E.dev)
+    E.ctx = capi.Context(E.local, SR)
+    E.stream = torch.cuda.current_stream()
+    E.sampler = ClockSampler(E.local)
+    if E.rank == 0:
+        E.sampler.start()
+        time.sleep(0.12)
+    return E
+
+
+def barrier(E):
+    if E.world > 1:
+        E.dist.barrier()
+    E.torch.cuda.synchronize()
+
+
+def max_over_ranks(E, x):
+    t = E.torch.tensor([x], dtype=E.torch.float64, device=E.dev)
+    if E.world > 1:
+        E.dist.all_reduce(t, op=E.dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def bank_leg(E, args, wl_name, steps, warmup, want_mix=False, with_onbox=False, full_readback=False):
+    """One bank workload: resident-throughput, roofline and the pipelined e2e number."""
+    torch, capi, W = E.torch, E.capi, E.W
+    wl = WORKLOADS[wl_name]
+    V = wl["voices"]
+    rank, world, dev, stream = E.rank, E.world, E.dev, E.stream
+    p = W.voice_params(V, seed=W.SEED + rank, delay_size=wl["delay"] or 4096)
+    bank = capi.Bank(V, osc=wl["osc"], filt=wl["filt"], env=wl["env"], delay=wl["delay"] > 0,
+                     delay_capacity=max(wl["delay"], 1), max_frames=BLOCK, ctx=E.ctx, sample_rate=SR)
+    W.configure_bank(bank, wl["filt"], p, wl["env"], wl["delay"] > 0)
+    p2p = world > 1 and want_mix and args.collective == "p2p"
+    if p2p:
+        exch = capi.Exchange(E.ctx, rank, world, max_doubles=2 * BLOCK)
+        exch.connect_with_torch_distributed()      # the IPC handles travel over the process group; the data never does
+        exch.attach(bank)
+    out_dtype = torch.float32 if args.f32_out else torch.float64
+    out = torch.empty((BLOCK, V), dtype=out_dtype, device=dev)             # 8 GiB (fp64, 1 Mi voices) >> 126 MB L2
+    mix = torch.zeros((BLOCK, 2), dtype=torch.float64, device=dev)
+    gates = []
+    if wl["env"]:   # gate arrays for 4 consecutive blocks, resident on the device (control data of the resident leg)
+        for k in range(4):
+            on, off = W.gate(V, BLOCK, k, seed=W.SEED + rank)
+            gates.append((torch.from_numpy(on).to(dev), torch.from_numpy(off).to(dev)))
+
+    def step(k):
+        on_p = off_p = None
+        if gates:
+            on_p, off_p = gates[k % 4][0].data_ptr(), gates[k % 4][1].data_ptr()
+        bank.process_device(BLOCK, out_ptr=out.data_ptr(), mix_ptr=mix.data_ptr() if want_mix else None,
+                            trig_on_ptr=on_p, trig_off_ptr=off_p, f32=args.f32_out, stream=stream.cuda_stream)
+        if world > 1 and want_mix and not p2p:
+            E.dist.all_reduce(mix)
+
+    for k in range(warmup):
+        step(k)
+    barrier(E)
+    launches0 = bank.launches
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+    t_wall0 = time.perf_counter()
+    evs[0].record(stream)
+    for k in range(steps):
+        step(warmup + k)
+        evs[k + 1].record(stream)
+    torch.cuda.synchronize()
+    t_wall1 = time.perf_counter()
+    barrier(E)
+    launches = bank.launches - launches0
+    ms_total = evs[0].elapsed_time(evs[-1])
+    per_launch_ms = sorted(evs[i].elapsed_time(evs[i + 1]) for i in range(steps))
+    ms_max = max_over_ranks(E, ms_total)
+    samples_per_step = V * BLOCK
+    value = world * samples_per_step * steps / (ms_max * 1e-3)
+
+    # ---- end to end through the C ABI with host control data, pipelined over three streams ---------------------------
+    # per step: this block's frequency array goes up from pinned memory on the bank's copy stream (double-buffered on the
+    # device), the block runs on the process stream, its stereo bus comes down into one of two pinned host buffers; the
+    # host never blocks inside the loop -- one synchronisation at the end, inside the timed region.
+    freq_host = [torch.from_numpy(p["freq"].copy()).pin_memory() for _ in range(2)]
+    mix_host = [torch.zeros((BLOCK, 2), dtype=torch.float64).pin_memory() for _ in range(2)]
+    on_h = off_h = None
+    if wl["env"]:
+        on, off = W.gate(V, BLOCK, 0, seed=W.SEED + rank)
+        on_t, off_t = torch.from_numpy(on).pin_memory(), torch.from_numpy(off).pin_memory()
+        on_h, off_h = on_t.numpy(), off_t.numpy()
+    e2e_steps = max(3, min(steps, 50))
+
+    def e2e_step(k):
+        fh, mh = freq_host[k & 1].numpy(), mix_host[k & 1].numpy()
+        bank.set_host_array("freq", fh, stream=stream.cuda_stream)        # H2D: this block's control data (copy stream)
+        bank.process_split(BLOCK, out.data_ptr(), mh, on_h, off_h, f32=args.f32_out, stream=stream.cuda_stream, wait=False)   # D2H: mix bus
+        if world > 1 and want_mix and not p2p:     # with the peer-memory exchange attached the bus that comes back is already the global one
+            torch.cuda.current_stream().synchronize()
+            m = mix_host[k & 1].to(dev, non_blocking=True)
+            E.dist.all_reduce(m)
+
+    for k in range(3):
+        e2e_step(k)
+    barrier(E)
+    t0 = time.perf_counter()
+    for k in range(e2e_steps):
+        e2e_step(k)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    e2e_value = world * samples_per_step * e2e_steps / max_over_ranks(E, dt)
+    h2d = freq_host[0].numpy().nbytes + (on_h.nbytes + off_h.nbytes if on_h is not None else 0)
+    d2h = mix_host[0].numpy().nbytes
+
+    res = {"value": value, "unit": "samples/s", "ms_per_step": ms_max / steps, "steps": steps, "warmup": warmup, "gpu_launches": launches}
+    if rank == 0:
+        peak, peak_src = load_peaks()
+        med_ms = per_launch_ms[len(per_launch_ms) // 2]
+        avg_ms = ms_total / steps
+        bytes_per = (4.0 if args.f32_out else 8.0) + (wl["bytes_per"] - 8.0)
+        achieved = bytes_per * samples_per_step / (avg_ms * 1e-3) / 1e9
+        res["config"] = {"workload": wl["desc"] + (" + stereo mix bus" if want_mix else ""), "voices_per_gpu": V, "block": BLOCK,
+                         "sample_rate": SR, "out_storage": "f32" if args.f32_out else "f64", "parallelism": f"voices sharded x{world}",
+                         "collective": ("none" if not (world > 1 and want_mix) else
+                                        "peer-memory exchange of mix[1024][2] fp64 fused into the mix-reduce kernel (CUDA IPC over NVLink, rank-ordered sum)" if p2p
+                                        else "NCCL sum all-reduce of mix[1024][2] fp64 per block"),
+                         "l2": "no flush needed: each step writes %.1f GB, inputs+outputs >> 126 MB L2" % (samples_per_step * (4 if args.f32_out else 8) / 1e9)}
+        res["roofline"] = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                           **load_traffic(wl_name + ("_mix" if want_mix else "") + ("_f32" if args.f32_out else "")),
+                           "algorithmic_bytes_per_launch": bytes_per * samples_per_step,
+                           "peak_source": peak_src, "kernel": "bank_kernel" if not wl["delay"] else "delay_bank_kernel",
+                           "algorithmic_bytes_per_voice_sample": bytes_per, "launch_ms_avg": avg_ms, "launch_ms_median": med_ms}
+        res["e2e"] = {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                      "steps": e2e_steps, "frac_of_resident": e2e_value / value,
+                      "what": "per step mxb_bank_set_param_async(freq, pinned host; copy stream, double-buffered) + "
+                              "mxb_bank_process(MXB_MEM_SPLIT|MXB_MEM_ASYNC): host gates in, host mix out, voice signals "
+                              "materialised on the device; one synchronisation at the end of the timed region"}
+        res["clocks"] = E.sampler.summary(t_wall0, t_wall1)
+        if with_onbox:
+            onbox = onbox_peaks(torch, out)
+            res["roofline"]["onbox_peaks"] = onbox
+            if "fill_gbs" in onbox:
+                res["roofline"]["frac_of_onbox_fill"] = achieved / onbox["fill_gbs"]
+    if full_readback and world == 1:
+        # the whole per-voice result back in host memory (MXB_MEM_HOST): PCIe-bound by construction, 8 B per voice-sample
+        try:
+            hout = torch.empty((BLOCK, V), dtype=out_dtype).pin_memory()
+            ho = hout.numpy()
+            bank.process(BLOCK, out=ho, out_dtype=ho.dtype)
+            t0 = time.perf_counter()
+            for _ in range(2):
+                bank.process(BLOCK, out=ho, out_dtype=ho.dtype)
+            dt = (time.perf_counter() - t0) / 2
+            res["e2e_full_readback"] = {"value": samples_per_step / dt, "unit": "samples/s", "d2h_bytes_per_step": int(ho.nbytes), "steps": 2,
+                                        "what": "mxb_bank_process(MXB_MEM_HOST): the whole out[1024][V] returns to pinned host memory every block (PCIe-bound)"}
+            del hout, ho
+        except Exception as e:
+            res["e2e_full_readback"] = {"error": str(e)[:200]}
+    del bank, out
+    torch.cuda.empty_cache()
+    return res
+
+
+def measure_mixdown(E, args, sm_mhz):
     """BASELINE.json configs[4] in SURVEY.md 8(d)'s "mix mode", one shard per GPU: 1 Mi voices maxiOsc::saw ->
     maxiBiquad -> maxiMix::stereo -> sum over voices; no per-voice output is written, the stereo bus [1024][2] is the
     result. With N > 1 the bus is summed over the GPUs (the path's only exchange step). The kernel moves 0.1 B per
     voice-sample, so it is reported against the fp64 pipe, not against HBM; it is never
     mixed into the headline."""
+    torch, dist, capi, W = E.torch, E.dist, E.capi, E.W
+    rank, world, dev, stream = E.rank, E.world, E.dev, E.stream
     wl = WORKLOADS["biquad"]
     V = wl["voices"]
     p = W.voice_params(V, seed=W.SEED + 100 + rank)
     bank = capi.Bank(V, osc=wl["osc"], filt=wl["filt"], env=False, delay=False, delay_capacity=1, max_frames=BLOCK,
-                     ctx=ctx, sample_rate=SR)
+                     ctx=E.ctx, sample_rate=SR)
     W.configure_bank(bank, wl["filt"], p, False, False)
+    mix = torch.zeros((BLOCK, 2), dtype=torch.float64, device=dev)
     p2p = world > 1 and args.collective == "p2p"
+    check = None
     if p2p:
-        exch = capi.Exchange(ctx, rank, world, max_doubles=2 * BLOCK)
+        exch = capi.Exchange(E.ctx, rank, world, max_doubles=2 * BLOCK)
         exch.connect_with_torch_distributed()      # the IPC handles travel over the process group; the data never does
+        # correctness of the fused exchange, before anything is timed: a clone of the bank (same state, no exchange) gives
+        # this rank's LOCAL bus; an NCCL sum all-reduce of the local buses must equal the exchanged bus to fp64
+        # reassociation, and the exchanged bus must be the same bits on every rank
+        twin = bank.clone()
         exch.attach(bank)
+        local = torch.zeros_like(mix)
+        ok, worst = True, 0.0
+        for _ in range(3):
+            bank.process_device(BLOCK, out_ptr=None, mix_ptr=mix.data_ptr(), stream=stream.cuda_stream)
+            twin.process_device(BLOCK, out_ptr=None, mix_ptr=local.data_ptr(), stream=stream.cuda_stream)
+            ref = local.clone()
+            dist.all_reduce(ref)
+            err = float(((mix - ref).abs() / (ref.abs() + 1e-9)).max().item())
+            worst = max(worst, err)
+            gathered = [torch.empty_like(mix) for _ in range(world)]
+            dist.all_gather(gathered, mix)
+            same = all(bool(torch.equal(g, gathered[0])) for g in gathered)
+            ok = ok and err <= 1e-12 and same
+        ok = ok and exch.status() == 0
+        flag = torch.tensor([1.0 if ok else 0.0], dtype=torch.float64, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        check = {"result": "ok" if flag.item() == 1.0 else "FAILED", "max_rel_err_vs_nccl_allreduce": worst,
+                 "what": "3 blocks: peer-exchanged bus == NCCL sum all-reduce of the ranks' local buses (<= 1e-12 relative), "
+                         "bit-equal on every rank, no exchange time-out"}
+        del twin
     steps = max(3, min(args.steps, 50))
 
     def step():
@@ -261,18 +577,35 @@ def measure_mixdown(args, torch, dist, capi, W, ctx, dev, rank, world, mix, stre
 
     for _ in range(3):
         step()
-    barrier()
+    barrier(E)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     for _ in range(steps):
         step()
     e1.record(stream)
     torch.cuda.synchronize()
-    barrier()
-    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item()) / steps
+    barrier(E)
+    ms = max_over_ranks(E, e0.elapsed_time(e1)) / steps
+    # e2e of mix mode: the WHOLE result of the block (the stereo bus) lands in host memory every step, the block's
+    # frequency array goes up every step; pipelined like the headline's e2e
+    freq_host = [torch.from_numpy(p["freq"].copy()).pin_memory() for _ in range(2)]
+    mix_host = [torch.zeros((BLOCK, 2), dtype=torch.float64).pin_memory() for _ in range(2)]
+
+    def e2e_step(k):
+        bank.set_host_array("freq", freq_host[k & 1].numpy(), stream=stream.cuda_stream)
+        bank.process_split(BLOCK, None, mix_host[k & 1].numpy(), stream=stream.cuda_stream, wait=False)
+        if world > 1 and not p2p:
+            torch.cuda.current_stream().synchronize()
+            m = mix_host[k & 1].to(dev, non_blocking=True)
+            dist.all_reduce(m)
+    for k in range(3):
+        e2e_step(k)
+    barrier(E)
+    t0 = time.perf_counter()
+    for k in range(steps):
+        e2e_step(k)
+    torch.cuda.synchronize()
+    e2e_dt = max_over_ranks(E, time.perf_counter() - t0)
     # fp64-pipe instructions per voice-sample in the SASS of this instantiation: saw 3 (DSETP, 2 DADD), biquad 9
     # (5 DMUL, 4 DADD: -fmad=false keeps the reference's roundings), mix 2 (DMUL/DFMA per channel) + 1 (row sums)
     instr = 15.0
@@ -283,11 +616,176 @@ def measure_mixdown(args, torch, dist, capi, W, ctx, dev, rank, world, mix, stre
            "value": world * V * BLOCK / (ms * 1e-3), "unit": "samples/s", "ms_per_step": ms, "steps": steps,
            "bound": "fp64 pipe", "fp64_instr_per_voice_sample": instr, "fp64_pipe_frac_per_gpu": rate / pipe_peak,
            "fp64_pipe_peak": "148 SMs x 64 lanes x %.0f MHz (sampled SM clock)" % (sm_mhz or 1920.0),
+           "e2e": {"value": world * V * BLOCK * steps / e2e_dt, "unit": "samples/s", "h2d_bytes_per_step": int(freq_host[0].numpy().nbytes),
+                   "d2h_bytes_per_step": int(mix_host[0].numpy().nbytes), "steps": steps,
+                   "what": "frequency array up, the block's whole result (the stereo bus) down into pinned host memory, every step"},
            "collective": ("none (one GPU)" if world == 1 else
                           "peer-memory exchange of mix[1024][2] fp64 fused into the mix-reduce kernel (CUDA IPC over NVLink, rank-ordered sum)"
                           if p2p else "NCCL sum all-reduce of mix[1024][2] fp64 per block")}
+    if check is not None:
+        res["check"] = check
     del bank
+    torch.cuda.empty_cache()
     return res
+
+
+# ------------------------------------------------------------------------------- configs[3]: FFT + MFCC frames/s
+
+MFCC_WL = dict(channels=65536, fft=1024, hop=512, filters=42, coeffs=40, hops_per_step=8,
+               # minimum traffic per (channel, hop) frame: 512 new fp32 samples in, 40 fp64 coefficients out (SURVEY.md 8d)
+               bytes_per=512 * 4 + 40 * 8,
+               desc="configs[3]: 64Ki channels maxiFFT(1024, hop 512) + maxiMFCC(42 filters, 40 coeffs), streaming, "
+                    "8 hops (524288 frames) per step, fused: spectra stay on chip, fp64 MFCCs written")
+
+
+def mfcc_farm(channels, kind):
+    from maximilian_b200 import workloads as W
+    from oracle import oracle_py as O
+    O.load(kind)
+    wl = MFCC_WL
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    threads = max(1, min(cores, channels // 8))      # at least 8 channels per host thread
+    bounds = np.linspace(0, channels, threads + 1).astype(int)
+    per_call = 16       # hops per library call: the time goes to the reference's C++ loops, not to Python call overhead
+    x = W.channel_streams(channels, per_call * wl["hop"], seed=5)
+
+    def make(i):
+        c = int(bounds[i + 1] - bounds[i])
+        return (O.Stft(c, wl["fft"], wl["hop"], kind=kind), O.Mfcc(wl["fft"] // 2, wl["filters"], wl["coeffs"], 20.0, 20000.0, SR, kind=kind),
+                np.ascontiguousarray(x[bounds[i]:bounds[i + 1]]))
+    return CpuFarm(threads, make), threads, per_call
+
+
+def cpu_mfcc_rate(kind, budget_s, channels=4096, calls=None):
+    """frames/s of maxiFFT + maxiMFCC per channel on all cores."""
+    farm, threads, per_call = mfcc_farm(channels, kind)
+
+    def job_n(n):
+        def job(i, part):
+            st, mf, xi = part
+            for _ in range(n):
+                r = st.process(xi, want=("mags",))
+                mf.process(r["mags"])
+        return job
+    farm.run(job_n(1))
+    n, total = 0, 0.0
+    if calls is not None:
+        total = farm.run(job_n(calls)); n = calls
+    else:
+        per = 1
+        while total < budget_s and n < 1024:
+            dt = farm.run(job_n(per))
+            total += dt; n += per
+            if dt < budget_s / 4:
+                per *= 2
+    farm.close()
+    return channels * per_call * n / total, channels, threads, n * per_call, total
+
+
+def cpu_baseline_mfcc(budget_s=3.0):
+    kinds = cpu_kinds()
+    res = {}
+    for k in kinds:
+        v, ch, threads, hops, total = cpu_mfcc_rate(k, budget_s)
+        res[k] = dict(value=v, flags=CPU_FLAGS[k], hops=hops, seconds=total)
+    main = kinds[0]
+    out = {"value": res[main]["value"], "unit": "frames/s", "cores": threads, "kind": "reference" if main.startswith("reference") else "port",
+           "flags": res[main]["flags"], "timed_seconds": res[main]["seconds"],
+           "sample": f"{ch} channels x {res[main]['hops']} hops, maxiFFT+maxiMFCC per channel, channels partitioned over {threads} pinned host threads"}
+    if len(kinds) > 1:
+        out["best_effort"] = {"value": res[kinds[1]]["value"], "flags": res[kinds[1]]["flags"], "timed_seconds": res[kinds[1]]["seconds"]}
+    return out
+
+
+def mfcc_leg(E, args, steps, warmup):
+    torch, capi, W = E.torch, E.capi, E.W
+    rank, world, dev, stream = E.rank, E.world, E.dev, E.stream
+    wl = MFCC_WL
+    C, n, hop, H = wl["channels"], wl["fft"], wl["hop"], wl["hops_per_step"]
+    st = capi.Stft(C, n, hop, ctx=E.ctx); mf = capi.Mfcc(n // 2, wl["filters"], wl["coeffs"], 20.0, 20000.0, ctx=E.ctx)
+    base = W.channel_streams(1024, H * hop, seed=5 + rank)
+    x_host = torch.from_numpy(np.tile(base, (C // 1024, 1))).pin_memory()           # [C][H*hop] planar fp32, 1 GiB
+    x = x_host.to(dev)
+    coeffs = torch.empty((C, H, wl["coeffs"]), dtype=torch.float64, device=dev)
+    co_host = torch.empty((C, H, wl["coeffs"]), dtype=torch.float64).pin_memory()
+
+    def step():
+        f = st.process_device(x.data_ptr(), H * hop, 1, H * hop, H, mfcc=mf, coeffs=coeffs.data_ptr(), stream=stream.cuda_stream)
+        assert f == H
+
+    for _ in range(warmup):
+        step()
+    barrier(E)
+    l0 = st.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    tw0 = time.perf_counter()
+    e0.record(stream)
+    for _ in range(steps):
+        step()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    tw1 = time.perf_counter()
+    barrier(E)
+    ms = e0.elapsed_time(e1)
+    ms_max = max_over_ranks(E, ms)
+    frames_per_step = C * H
+    value = world * frames_per_step * steps / (ms_max * 1e-3)
+    launches = st.launches - l0
+    # e2e: host samples in (pinned), host MFCCs out, through the C ABI (MXB_MEM_HOST): the library slices the channels and
+    # pipelines upload / transform / download over three streams
+    import ctypes as C_
+    xh, ch_ = x_host.numpy(), co_host.numpy()
+    nf = C_.c_int32(0)
+
+    def e2e_step():
+        capi.check(capi.lib().mxb_stft_process(st.h, xh.ctypes.data, H * hop, 1, H * hop, H, None, None, None, None, mf.h, ch_.ctypes.data,
+                                               C_.byref(nf), capi.MEM_HOST, C_.c_void_p(stream.cuda_stream)), "mxb_stft_process")
+    e2e_steps = max(3, min(steps, 10))
+    for _ in range(2):
+        e2e_step()
+    barrier(E)
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    e2e_dt = max_over_ranks(E, time.perf_counter() - t0)
+    e2e_value = world * frames_per_step * e2e_steps / e2e_dt
+    res = {"metric": "fft_mfcc_frames_per_sec", "value": value, "unit": "frames/s", "ms_per_step": ms_max / steps, "steps": steps, "warmup": warmup,
+           "gpu_launches": launches}
+    if rank == 0:
+        peak, peak_src = load_peaks()
+        avg_ms = ms / steps
+        achieved = wl["bytes_per"] * frames_per_step / (avg_ms * 1e-3) / 1e9
+        pcie = pcie_rates(torch, dev)
+        res["config"] = {"workload": wl["desc"], "channels_per_gpu": C, "hops_per_step": H, "parallelism": f"channels sharded x{world}", "collective": "none",
+                         "l2": "per step 1.07 GB of samples in + 168 MB of MFCCs out: larger than the 126 MB L2"}
+        res["roofline"] = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, **load_traffic("mfcc"),
+                           "algorithmic_bytes_per_launch": wl["bytes_per"] * frames_per_step,
+                           "peak_source": peak_src, "kernel": "stft_stream_kernel", "algorithmic_bytes_per_frame": wl["bytes_per"],
+                           "launch_ms_avg": avg_ms, "note": "fp32 issue bound by design of the reference transform (bit-exact radix-2 replay + fp64 mel/DCT); "
+                                                          "HBM fraction is reported as north_star asks, not expected to be high"}
+        e2e_bytes = int(xh.nbytes) + int(ch_.nbytes)
+        res["e2e"] = {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": int(xh.nbytes), "d2h_bytes_per_step": int(ch_.nbytes),
+                      "steps": e2e_steps, "pcie": pcie,
+                      "what": "mxb_stft_process(MXB_MEM_HOST): pinned host samples in, fused STFT+MFCC, host MFCCs out; channel slices pipelined "
+                              "over copy-in / compute / copy-out streams"}
+        if "h2d_gbs" in pcie:
+            # the link moves both directions at once: the floor is the slower of the two transfers
+            floor_s = max(xh.nbytes / (pcie["h2d_gbs"] * 1e9), ch_.nbytes / (pcie["d2h_gbs"] * 1e9))
+            res["e2e"]["frac_of_pcie_floor"] = (floor_s * e2e_steps) / e2e_dt
+            res["e2e"]["bytes_per_step"] = e2e_bytes
+        res["clocks"] = E.sampler.summary(tw0, tw1)
+    del st, mf, x, coeffs
+    torch.cuda.empty_cache()
+    return res
+
+
+def finish(E):
+    if E.rank == 0:
+        time.sleep(0.06)
+        E.sampler.stop()
+    if E.world > 1:
+        E.dist.destroy_process_group()
 
 
 def main():
@@ -296,353 +794,91 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200")
-    ap.add_argument("--workload", default="svf", choices=sorted(WORKLOADS) + ["mfcc"])
+    ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS) + ["mfcc"],
+                    help="headline workload (default svf = BASELINE.json configs[1]; without this flag and with one GPU the other "
+                         "configurations are measured too and reported under 'workloads')")
     ap.add_argument("--mix", type=int, default=-1,
                     help="1: the timed block also produces the stereo mix bus (+ the cross-GPU mix-down when gpus > 1). Default: the "
                          "headline block is the configured chain alone (same work at every N) and the mix-down configuration "
                          "(configs[4]) is timed separately and reported under 'mixdown'")
-    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline legs")
+    ap.add_argument("--no-extras", action="store_true", help="headline workload only")
     ap.add_argument("--f32-out", action="store_true", help="store the materialised output as fp32 (declared in the JSON)")
     ap.add_argument("--collective", default="p2p", choices=["p2p", "nccl"],
                     help="N > 1 mix-down: p2p = peer-memory exchange fused into the mix-reduce kernel (default); nccl = torch.distributed all_reduce")
     args = ap.parse_args()
-    if args.workload == "mfcc":
-        return main_mfcc(args)
-    wl = WORKLOADS[args.workload]
+    extras_wanted = args.workload is None and not args.no_extras
+    wl_name = args.workload or "svf"
     if args.impl == "reference":
-        reference_arm(args, args.workload, wl)
-        return
+        if wl_name == "mfcc":
+            return reference_arm_mfcc(args)
+        return reference_arm(args, wl_name, WORKLOADS[wl_name])
     assert args.warmup >= 3, "timing rules: at least 3 warm-up steps"
+    E = setup_env(args)
 
-    import torch
-    import torch.distributed as dist
-    from maximilian_b200 import capi
-    from maximilian_b200 import workloads as W
+    if wl_name == "mfcc":
+        head = mfcc_leg(E, args, args.steps, args.warmup)
+        if E.rank == 0:
+            line = {"metric": "fft_mfcc_frames_per_sec", "value": head["value"], "unit": "frames/s", "n_gpus": E.world, "steps": args.steps,
+                    "warmup": args.warmup, "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                    "dtype": "f32", "data": "synthetic", "config": head["config"], "roofline": head["roofline"], "e2e": head["e2e"],
+                    "gpu_launches": head["gpu_launches"], "clocks": head["clocks"]}
+            if not args.no_cpu and E.world == 1:
+                line["cpu_baseline"] = cpu_baseline_mfcc()
+            print(json.dumps(line), flush=True)
+        return finish(E)
 
-    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE {world}"
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
     want_mix = args.mix == 1
-
-    V = wl["voices"]
-    p = W.voice_params(V, seed=W.SEED + rank, delay_size=wl["delay"] or 4096)
-    ctx = capi.Context(local, SR)
-    bank = capi.Bank(V, osc=wl["osc"], filt=wl["filt"], env=wl["env"], delay=wl["delay"] > 0,
-                     delay_capacity=max(wl["delay"], 1), max_frames=BLOCK, ctx=ctx, sample_rate=SR)
-    W.configure_bank(bank, wl["filt"], p, wl["env"], wl["delay"] > 0)
-    p2p = world > 1 and want_mix and args.collective == "p2p"
-    if p2p:
-        exch = capi.Exchange(ctx, rank, world, max_doubles=2 * BLOCK)
-        exch.connect_with_torch_distributed()      # the IPC handles travel over the process group; the data never does
-        exch.attach(bank)
-
-    out_dtype = torch.float32 if args.f32_out else torch.float64
-    out = torch.empty((BLOCK, V), dtype=out_dtype, device=dev)             # 8 GiB (fp64, 1 Mi voices) >> 126 MB L2
-    mix = torch.zeros((BLOCK, 2), dtype=torch.float64, device=dev)
-    gates = []
-    if wl["env"]:   # gate arrays for 4 consecutive blocks, resident on the device (control data of the resident leg)
-        for k in range(4):
-            on, off = W.gate(V, BLOCK, k, seed=W.SEED + rank)
-            gates.append((torch.from_numpy(on).to(dev), torch.from_numpy(off).to(dev)))
-    stream = torch.cuda.current_stream()
-
-    def step(k):
-        on_p = off_p = None
-        if gates:
-            on_p, off_p = gates[k % 4][0].data_ptr(), gates[k % 4][1].data_ptr()
-        bank.process_device(BLOCK, out_ptr=out.data_ptr(), mix_ptr=mix.data_ptr() if want_mix else None,
-                            trig_on_ptr=on_p, trig_off_ptr=off_p, f32=args.f32_out, stream=stream.cuda_stream)
-        if world > 1 and want_mix and not p2p:
-            dist.all_reduce(mix)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for k in range(args.warmup):
-        step(k)
-    barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-        time.sleep(0.12)
-    barrier()
-    launches0 = bank.launches
-    evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
-    t_wall0 = time.perf_counter()
-    evs[0].record(stream)
-    for k in range(args.steps):
-        step(args.warmup + k)
-        evs[k + 1].record(stream)
-    torch.cuda.synchronize()
-    t_wall1 = time.perf_counter()
-    barrier()
-    launches = bank.launches - launches0
-    ms_total = evs[0].elapsed_time(evs[-1])
-    per_launch_ms = sorted(evs[i].elapsed_time(evs[i + 1]) for i in range(args.steps))
-    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
-    samples_per_step = V * BLOCK
-    value = world * samples_per_step * args.steps / (ms_max * 1e-3)
-    clocks = None
-    if rank == 0:
-        time.sleep(0.06)
-        sampler.stop()
-        clocks = sampler.summary(t_wall0, t_wall1)
-
-    # ---- configs[4] shard: osc -> maxiBiquad + stereo mix bus (+ cross-GPU mix-down), timed on its own -------
+    head = bank_leg(E, args, wl_name, args.steps, args.warmup, want_mix=want_mix, with_onbox=True, full_readback=extras_wanted)
     mixdown = None
-    if args.mix < 0 and not wl["delay"]:
-        mhz = torch.tensor([float((clocks or {}).get("sm_mhz") or 0.0)], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.broadcast(mhz, 0)
-        mixdown = measure_mixdown(args, torch, dist, capi, W, ctx, dev, rank, world, mix, stream, barrier, float(mhz.item()) or None)
-
-    # ---- end to end through the C ABI with host control data ------------------------------------------------
-    freq_host = torch.from_numpy(p["freq"].copy()).pin_memory()
-    mix_host = torch.zeros((BLOCK, 2), dtype=torch.float64).pin_memory()
-    fh, mh = freq_host.numpy(), mix_host.numpy()
-    on_h = off_h = None
-    if wl["env"]:
-        on, off = W.gate(V, BLOCK, 0, seed=W.SEED + rank)
-        on_t, off_t = torch.from_numpy(on).pin_memory(), torch.from_numpy(off).pin_memory()
-        on_h, off_h = on_t.numpy(), off_t.numpy()
-    e2e_steps = max(3, min(args.steps, 50))
-
-    def e2e_step():
-        bank.set_host_array("freq", fh, stream=stream.cuda_stream)        # H2D: this block's control data (stream-ordered)
-        bank.process_split(BLOCK, out.data_ptr(), mh, on_h, off_h, f32=args.f32_out, stream=stream.cuda_stream)   # D2H: mix bus
-        if world > 1:
-            if not p2p:            # with the peer-memory exchange attached the bus that came back is already the global one
-                m = mix_host.to(dev, non_blocking=True)
-                dist.all_reduce(m)
-
-    for _ in range(3):
-        e2e_step()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        e2e_step()
-    torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
-    t = torch.tensor([dt], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * samples_per_step * e2e_steps / float(t.item())
-    h2d = fh.nbytes + (on_h.nbytes + off_h.nbytes if on_h is not None else 0)
-    d2h = mh.nbytes
-
-    onbox = onbox_peaks(torch, out) if rank == 0 else None
-
-    if rank == 0:
-        peak, peak_src = load_peaks()
-        med_ms = per_launch_ms[len(per_launch_ms) // 2]
-        avg_ms = ms_total / args.steps
-        bytes_per = (4.0 if args.f32_out else 8.0) + (wl["bytes_per"] - 8.0)
-        achieved = bytes_per * samples_per_step / (avg_ms * 1e-3) / 1e9
-        line = {
-            "metric": "voice_samples_per_sec", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": wl["desc"] + (" + stereo mix bus" if want_mix else ""), "voices_per_gpu": V, "block": BLOCK,
-                       "sample_rate": SR, "out_storage": "f32" if args.f32_out else "f64", "parallelism": f"voices sharded x{world}",
-                       "collective": ("none" if not (world > 1 and want_mix) else
-                                      "peer-memory exchange of mix[1024][2] fp64 fused into the mix-reduce kernel (CUDA IPC over NVLink, rank-ordered sum)" if p2p
-                                      else "NCCL sum all-reduce of mix[1024][2] fp64 per block"),
-                       "l2": "no flush needed: each step writes %.1f GB, inputs+outputs >> 126 MB L2" % (samples_per_step * (4 if args.f32_out else 8) / 1e9)},
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         **load_traffic(args.workload + ("_mix" if want_mix else "") + ("_f32" if args.f32_out else "")),
-                         "algorithmic_bytes_per_launch": bytes_per * samples_per_step,
-                         "peak_source": peak_src, "kernel": "bank_kernel" if not wl["delay"] else "delay_bank_kernel",
-                         "algorithmic_bytes_per_voice_sample": bytes_per, "launch_ms_avg": avg_ms, "launch_ms_median": med_ms},
-            "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": e2e_steps, "what": "mxb_bank_set_param(freq, pinned host) + mxb_bank_process(MXB_MEM_SPLIT): "
-                                                 "host gates in, host mix out, voice signals materialised on the device"},
-            "gpu_launches": launches, "clocks": clocks,
-        }
-        if onbox:
-            line["roofline"]["onbox_peaks"] = onbox
-            line["roofline"]["frac_of_onbox_fill"] = achieved / onbox["fill_gbs"]
+    if args.mix < 0 and not WORKLOADS[wl_name]["delay"]:
+        mhz = E.torch.tensor([float((head.get("clocks") or {}).get("sm_mhz") or 0.0)], dtype=E.torch.float64, device=E.dev)
+        if E.world > 1:
+            E.dist.broadcast(mhz, 0)
+        mixdown = measure_mixdown(E, args, float(mhz.item()) or None)
+    extras = None
+    if extras_wanted and E.world == 1:
+        xs = max(3, min(args.steps, 40)); xw = max(3, min(args.warmup, 5))
+        extras = {}
+        for key, name in (("biquad_bank", "biquad"), ("delay", "delay")):
+            r = bank_leg(E, args, name, xs, xw)
+            if not args.no_cpu:
+                r["cpu_baseline"] = cpu_baseline(WORKLOADS[name], budget_s=3.0)
+            extras[key] = r
+        r = mfcc_leg(E, args, max(3, min(args.steps, 20)), xw)
+        if not args.no_cpu:
+            r["cpu_baseline"] = cpu_baseline_mfcc(3.0)
+        extras["mfcc"] = r
+    if E.rank == 0:
+        line = {"metric": "voice_samples_per_sec", "value": head["value"], "unit": "samples/s", "n_gpus": E.world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": head["config"], "roofline": head["roofline"],
+                "e2e": head["e2e"], "gpu_launches": head["gpu_launches"], "clocks": head["clocks"]}
+        if "e2e_full_readback" in head:
+            line["e2e_full_readback"] = head["e2e_full_readback"]
         if mixdown is not None:
             line["mixdown"] = mixdown
-        if not args.no_cpu and world == 1:
-            line["cpu_baseline"] = cpu_baseline(wl)
+        if extras is not None:
+            line["workloads"] = extras
+        if not args.no_cpu and E.world == 1:
+            line["cpu_baseline"] = cpu_baseline(WORKLOADS[wl_name], budget_s=4.0)
         print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    finish(E)
 
 
-# ------------------------------------------------------------------------------- configs[3]: FFT + MFCC frames/s
-
-MFCC_WL = dict(channels=65536, fft=1024, hop=512, filters=42, coeffs=40,
-               # minimum traffic per (channel, hop) frame: 512 new fp32 samples in, 40 fp64 coefficients out (SURVEY.md 8d)
-               bytes_per=512 * 4 + 40 * 8,
-               desc="configs[3]: 64Ki channels maxiFFT(1024, hop 512) + maxiMFCC(42 filters, 40 coeffs), streaming, "
-                    "one hop (65536 frames) per step, fused: spectra stay on chip, fp64 MFCCs written")
-
-
-def cpu_mfcc_run(channels, hops, threads, kind):
-    """threads x (maxiFFT + maxiMFCC per channel) over `hops` hops; returns seconds for the timed hops."""
-    from maximilian_b200 import workloads as W
-    from oracle import oracle_py as O
-    wl = MFCC_WL
-    threads = max(1, min(threads, channels // 8))      # at least 8 channels per host thread
-    bounds = np.linspace(0, channels, threads + 1).astype(int)
-    # 16 hops per library call: the time goes to the reference's C++ loops, not to Python call overhead
-    calls, per_call = max(1, hops // 16), 16
-    x = W.channel_streams(channels, per_call * wl["hop"], seed=5)
-    objs = []
-    for i in range(threads):
-        c = int(bounds[i + 1] - bounds[i])
-        if c <= 0:
-            objs.append(None)
-            continue
-        objs.append((O.Stft(c, wl["fft"], wl["hop"], kind=kind), O.Mfcc(wl["fft"] // 2, wl["filters"], wl["coeffs"], 20.0, 20000.0, SR, kind=kind),
-                     np.ascontiguousarray(x[bounds[i]:bounds[i + 1]])))
-
-    def work(i, n):
-        if objs[i] is None:
-            return
-        st, mf, xi = objs[i]
-        for _ in range(n):
-            r = st.process(xi, want=("mags",))
-            mf.process(r["mags"])
-
-    def run(n):
-        ts = [threading.Thread(target=work, args=(i, n)) for i in range(threads)]
-        t0 = time.perf_counter()
-        [t.start() for t in ts]
-        [t.join() for t in ts]
-        return time.perf_counter() - t0
-    run(1)
-    dt = run(calls)
-    return dt * hops / (calls * per_call)      # seconds per `hops` hops
-
-
-def main_mfcc(args):
-    wl = MFCC_WL
-    if args.impl == "reference":
-        if int(os.environ.get("RANK", "0")) != 0:
-            return
-        kind = cpu_kind(); cores = os.cpu_count() or 1
-        ch = 4096
-        dt = cpu_mfcc_run(ch, args.steps, cores, kind)
-        v = ch * args.steps / dt
-        print(json.dumps({"impl": "reference", "metric": "fft_mfcc_frames_per_sec", "value": v, "unit": "frames/s", "n_gpus": args.gpus,
-                          "steps": args.steps, "warmup": 1, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
-                          "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": {"workload": wl["desc"], "cpu_sample_channels": ch},
-                          "cpu_baseline": {"value": v, "unit": "frames/s", "cores": cores, "kind": kind,
-                                           "sample": f"each step = one hop of {ch} channels on {cores} host threads"},
-                          "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
+def reference_arm_mfcc(args):
+    if int(os.environ.get("RANK", "0")) != 0:
         return
-    import torch
-    import torch.distributed as dist
-    from maximilian_b200 import capi
-    from maximilian_b200 import workloads as W
-    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)       # no collective on this path: channels shard, replicas only
-    C, n, hop = wl["channels"], wl["fft"], wl["hop"]
-    ctx = capi.Context(local, SR)
-    st = capi.Stft(C, n, hop, ctx=ctx); mf = capi.Mfcc(n // 2, wl["filters"], wl["coeffs"], 20.0, 20000.0, ctx=ctx)
-    base = W.channel_streams(1024, hop, seed=5 + rank)
-    x_host = torch.from_numpy(np.tile(base, (C // 1024, 1))).pin_memory()           # [C][hop] planar fp32, 128 MiB
-    x = x_host.to(dev)
-    coeffs = torch.empty((C, 1, wl["coeffs"]), dtype=torch.float64, device=dev)
-    co_host = torch.empty((C, 1, wl["coeffs"]), dtype=torch.float64).pin_memory()
-    stream = torch.cuda.current_stream()
-
-    def step():
-        f = st.process_device(x.data_ptr(), hop, 1, hop, 1, mfcc=mf, coeffs=coeffs.data_ptr(), stream=stream.cuda_stream)
-        assert f == 1
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-    for _ in range(args.warmup):
-        step()
-    barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start(); time.sleep(0.12)
-    barrier()
-    l0 = st.launches
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    tw0 = time.perf_counter()
-    e0.record(stream)
-    for _ in range(args.steps):
-        step()
-    e1.record(stream)
-    torch.cuda.synchronize()
-    tw1 = time.perf_counter()
-    barrier()
-    ms = e0.elapsed_time(e1)
-    t = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
-    value = world * C * args.steps / (ms_max * 1e-3)
-    launches = st.launches - l0
-    clocks = None
-    if rank == 0:
-        time.sleep(0.06); sampler.stop(); clocks = sampler.summary(tw0, tw1)
-    # e2e: host samples in (pinned), host MFCCs out, through the C ABI (MXB_MEM_HOST)
-    import ctypes as C_
-    xh, ch_ = x_host.numpy(), co_host.numpy()
-    nf = C_.c_int32(0)
-
-    def e2e_step():
-        capi.check(capi.lib().mxb_stft_process(st.h, xh.ctypes.data, hop, 1, hop, 1, None, None, None, None, mf.h, ch_.ctypes.data,
-                                               C_.byref(nf), capi.MEM_HOST, C_.c_void_p(stream.cuda_stream)), "mxb_stft_process")
-    e2e_steps = max(3, min(args.steps, 30))
-    for _ in range(3):
-        e2e_step()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        e2e_step()
-    torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
-    t = torch.tensor([dt], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * C * e2e_steps / float(t.item())
-    if rank == 0:
-        peak, peak_src = load_peaks()
-        avg_ms = ms / args.steps
-        achieved = wl["bytes_per"] * C / (avg_ms * 1e-3) / 1e9
-        line = {"metric": "fft_mfcc_frames_per_sec", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-                "data": "synthetic",
-                "config": {"workload": wl["desc"], "channels_per_gpu": C, "parallelism": f"channels sharded x{world}", "collective": "none",
-                           "l2": "per step 134 MB of samples in + 268 MB of assembly state r/w + 21 MB out: larger than the 126 MB L2"},
-                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, **load_traffic("mfcc"),
-                             "algorithmic_bytes_per_launch": wl["bytes_per"] * C,
-                             "peak_source": peak_src, "kernel": "stft_kernel", "algorithmic_bytes_per_frame": wl["bytes_per"],
-                             "launch_ms_avg": avg_ms, "note": "ALU/shuffle bound by design of the reference transform (fp32 radix-2 + fp64 mel/DCT); "
-                                                            "HBM fraction is reported as north_star asks, not expected to be high"},
-                "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": int(xh.nbytes), "d2h_bytes_per_step": int(ch_.nbytes),
-                        "steps": e2e_steps, "what": "mxb_stft_process(MXB_MEM_HOST): pinned host samples in, fused STFT+MFCC, host MFCCs out"},
-                "gpu_launches": launches, "clocks": clocks}
-        if not args.no_cpu and world == 1:
-            kind = cpu_kind(); cores = os.cpu_count() or 1
-            ch = 4096
-            dtc = cpu_mfcc_run(ch, 8, cores, kind)
-            line["cpu_baseline"] = {"value": ch * 8 / dtc, "unit": "frames/s", "cores": cores, "kind": kind,
-                                    "sample": f"{ch} channels x 8 hops, maxiFFT+maxiMFCC per channel, channels partitioned over {cores} host threads"}
-        print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    wl = MFCC_WL
+    kind = cpu_kinds()[-1]
+    v, ch, threads, hops, dt = cpu_mfcc_rate(kind, None, calls=4 * max(1, args.steps))
+    print(json.dumps({"impl": "reference", "metric": "fft_mfcc_frames_per_sec", "value": v, "unit": "frames/s", "n_gpus": args.gpus,
+                      "steps": args.steps, "warmup": 1, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+                      "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": {"workload": wl["desc"], "cpu_sample_channels": ch, "hops_per_step": 64},
+                      "cpu_baseline": {"value": v, "unit": "frames/s", "cores": threads, "kind": "reference" if kind.startswith("reference") else "port",
+                                       "flags": CPU_FLAGS[kind], "timed_seconds": dt,
+                                       "sample": f"each step = 64 hops of {ch} channels on {threads} pinned host threads"},
+                      "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
 
 
 if __name__ == "__main__":

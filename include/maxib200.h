@@ -46,7 +46,13 @@ enum {
 
 /* MXB_MEM_SPLIT (mxb_bank_process only): control data (gates) and the mix bus in host memory, `out`
  * in device memory -- the voice signals stay on the GPU for the next stage, the host gets the mix. */
-enum { MXB_MEM_HOST = 0, MXB_MEM_DEVICE = 1, MXB_MEM_SPLIT = 2 };
+enum { MXB_MEM_HOST = 0, MXB_MEM_DEVICE = 1, MXB_MEM_SPLIT = 2,
+       /* flag, OR-ed into MXB_MEM_HOST / MXB_MEM_SPLIT of mxb_bank_process*: do not wait. The call returns once the copies and
+        * kernels are enqueued on `stream`; host buffers must be page-locked (mxb_host_alloc) and are valid after the stream or
+        * the context (mxb_ctx_synchronize) has been synchronised. A block loop then never stalls the host: block k+1's control
+        * data goes up (mxb_bank_set_param_async, double-buffered on the bank's copy stream) while block k computes and block
+        * k-1's mix comes down. */
+       MXB_MEM_ASYNC = 0x100 };
 enum { MXB_F64 = 0, MXB_F32 = 1 };
 
 /* oscillator kinds: maxiOsc methods, src/maximilian.cpp */
@@ -160,15 +166,19 @@ typedef struct {
 int32_t mxb_bank_create(mxb_ctx* ctx, const mxb_bank_desc* desc, mxb_bank** bank);
 int32_t mxb_bank_destroy(mxb_bank* bank);
 int32_t mxb_bank_voices(const mxb_bank* bank);
-/* values: double[voices]. Filter coefficients are designed here, once per change, with the
+/* values: double[voices]. Ordered like a cudaMemcpy on the legacy default stream (after every block enqueued on blocking
+ * streams; no device-wide synchronisation). Filter coefficients are designed here, once per change (host threads share
+ * a large bank), with the
  * reference's own formulas (lores/hires src/maximilian.cpp:457-462, maxiSVF::setParams
  * src/maximilian.h:1322-1334, maxiBiquad::set src/maximilian.h:1375-1479): block-constant
  * parameters hoist out of the per-sample loop exactly. */
 int32_t mxb_bank_set_param(mxb_bank* bank, int32_t id, const double* values, int32_t mem);
-/* Stream-ordered variant for block-rate control data (a new frequency / pan / feedback array every block): one
- * asynchronous copy on `stream`, no synchronisation; host memory should be page-locked. Parameters that need a
- * host pass (cutoff / resonance / gain: coefficient design; holdtime / delay size: integer conversion) fall back
- * to mxb_bank_set_param. The reference passes these values by argument on every sample. */
+/* Asynchronous variant for block-rate control data (a new frequency / pan / feedback array every block); takes effect
+ * with the NEXT mxb_bank_process call. From host memory (page-locked; unchanged until that block has started) the copy
+ * runs on the bank's own copy stream into the second of two device buffers, overlapping the blocks already enqueued;
+ * the next block waits for it on its stream and switches buffers. From device memory it is one copy on `stream`.
+ * Parameters that need a host pass (cutoff / resonance / gain: coefficient design; holdtime / delay size: integer
+ * conversion) fall back to mxb_bank_set_param. The reference passes these values by argument on every sample. */
 int32_t mxb_bank_set_param_async(mxb_bank* bank, int32_t id, const double* values, int32_t mem, void* stream);
 int32_t mxb_bank_get_state(mxb_bank* bank, int32_t id, double* values, int32_t mem);
 /* ring slots [0, n) of voice v (debug / checkpoint) */
@@ -232,6 +242,11 @@ typedef struct mxb_exchange mxb_exchange;
 int32_t mxb_exchange_create(mxb_ctx* ctx, int32_t rank, int32_t world, int32_t max_doubles, mxb_exchange** ex);
 int32_t mxb_exchange_local_handle(mxb_exchange* ex, void* handle, int32_t handle_bytes);
 int32_t mxb_exchange_connect(mxb_exchange* ex, const void* all_handles /* world x MXB_EXCHANGE_HANDLE_BYTES, rank order */);
+/* The kernel's wait for the peers' flags is bounded (5 s; environment MXB_EXCHANGE_TIMEOUT_MS at creation): a rank that
+ * died or never launched its block must not hang the others. *timed_out_ranks receives a bit mask of the ranks whose
+ * contribution was missing from some bus so far (0 = every bus complete); synchronises the device. mxb_bank_process in
+ * MXB_MEM_HOST / MXB_MEM_SPLIT mode checks it itself and returns MXB_ERR_STATE. */
+int32_t mxb_exchange_status(mxb_exchange* ex, int32_t* timed_out_ranks);
 int32_t mxb_exchange_destroy(mxb_exchange* ex);
 int32_t mxb_bank_set_exchange(mxb_bank* bank, mxb_exchange* ex /* NULL detaches */);
 

@@ -160,7 +160,7 @@ private:
 
     bool sameChain() const {
         return built_.osc_kind == desc_.osc_kind && built_.filt_kind == desc_.filt_kind && built_.env_kind == desc_.env_kind &&
-               built_.biquad_type == desc_.biquad_type && built_.delay_taps == desc_.delay_taps &&
+               built_.biquad_type == desc_.biquad_type && built_.delay_taps == desc_.delay_taps && built_.delay_mode == desc_.delay_mode &&
                std::memcmp(built_.svf_mix, desc_.svf_mix, sizeof(desc_.svf_mix)) == 0;
     }
     void setParam(int id, const maxiParam& p) {
@@ -442,8 +442,10 @@ public:
     explicit maxiIFFT(int channels = 1, int device = 0) : C_(channels), device_(device) {}
     ~maxiIFFT() { if (h_) mxb_istft_destroy(h_); if (ctx_) mxb_ctx_destroy(ctx_); }
     maxiIFFT(const maxiIFFT&) = delete;
-    void setup(int fftSize = 1024, int hopSize = 512, int /*windowSize*/ = 0) {
+    void setup(int fftSize = 1024, int hopSize = 512, int windowSize = 0) {
         using maxib200_detail::check;
+        /* the reference windows with genWindow(3, windowSize ? windowSize : fftSize) (maxiFFT.cpp:141-152): another size is another window */
+        if (windowSize != 0 && windowSize != fftSize) throw maxiError(MXB_ERR_UNSUPPORTED, "maxiIFFT::setup: windowSize must be 0 or fftSize");
         check(mxb_ctx_create(device_, (int32_t)maxiSettings::sampleRate, &ctx_), "mxb_ctx_create");
         check(mxb_istft_create(ctx_, C_, fftSize, hopSize, &h_), "mxb_istft_create");
         hop_ = hopSize; bins_ = fftSize / 2;

@@ -10,7 +10,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("MXB_LIB_PATH") or os.path.join(HERE, "lib", "libmaxib200.so")   # override: A/B builds of the same ABI
 
-MEM_HOST, MEM_DEVICE = 0, 1
+MEM_HOST, MEM_DEVICE, MEM_SPLIT, MEM_ASYNC = 0, 1, 2, 0x100
 F64, F32 = 0, 1
 
 OSC = dict(sinewave=0, coswave=1, phasor=2, saw=3, square=4, pulse=5, impulse=6, triangle=7, phasorbetween=8)
@@ -26,7 +26,7 @@ EXPORTS = [
     "mxb_ctx_synchronize", "mxb_host_alloc", "mxb_host_free",
     "mxb_bank_create", "mxb_bank_destroy", "mxb_bank_voices", "mxb_bank_set_param", "mxb_bank_set_param_async", "mxb_bank_get_state",
     "mxb_bank_get_ring", "mxb_bank_set_state", "mxb_bank_set_ring", "mxb_bank_clone", "mxb_bank_process", "mxb_bank_process_fm", "mxb_bank_process_mod", "mxb_bank_launch_count", "mxb_env_coeffs",
-    "mxb_exchange_create", "mxb_exchange_local_handle", "mxb_exchange_connect", "mxb_exchange_destroy", "mxb_bank_set_exchange",
+    "mxb_exchange_create", "mxb_exchange_local_handle", "mxb_exchange_connect", "mxb_exchange_status", "mxb_exchange_destroy", "mxb_bank_set_exchange",
     "mxb_stft_create", "mxb_stft_destroy", "mxb_stft_process", "mxb_stft_process2", "mxb_stft_launch_count",
     "mxb_mfcc_create", "mxb_mfcc_destroy", "mxb_mfcc_process",
     "mxb_istft_create", "mxb_istft_destroy", "mxb_istft_process",
@@ -97,6 +97,7 @@ def lib():
         "mxb_exchange_create": (i32, [vp, i32, i32, i32, pp]),
         "mxb_exchange_local_handle": (i32, [vp, vp, i32]),
         "mxb_exchange_connect": (i32, [vp, vp]),
+        "mxb_exchange_status": (i32, [vp, C.POINTER(i32)]),
         "mxb_exchange_destroy": (i32, [vp]),
         "mxb_bank_set_exchange": (i32, [vp, vp]),
         "mxb_stft_create": (i32, [vp, i32, i32, i32, pp]),
@@ -274,11 +275,13 @@ class Bank:
               "mxb_bank_process")
 
 
-    def process_split(self, nframes, out_ptr, mix, trig_on=None, trig_off=None, f32=False, stream=0):
+    def process_split(self, nframes, out_ptr, mix, trig_on=None, trig_off=None, f32=False, stream=0, wait=True):
         """MXB_MEM_SPLIT: gates / mix are host numpy arrays, `out_ptr` is a raw device pointer (or None).
-        Returns when the mix is in host memory."""
+        Returns when the mix is in host memory; with wait=False (MXB_MEM_ASYNC; page-locked host arrays) as soon as the
+        block is enqueued -- the mix is valid after the stream / context has been synchronised."""
         check(lib().mxb_bank_process(self.h, nframes, _np_ptr(trig_on), _np_ptr(trig_off), _ptr(out_ptr),
-                                     F32 if f32 else F64, _np_ptr(mix), 2, C.c_void_p(int(stream)) if stream else None),
+                                     F32 if f32 else F64, _np_ptr(mix), MEM_SPLIT | (0 if wait else MEM_ASYNC),
+                                     C.c_void_p(int(stream)) if stream else None),
               "mxb_bank_process")
 
     def set_host_array(self, name, a, stream=None):
@@ -319,6 +322,12 @@ class Exchange:
         dist.all_gather_object(handles, self.local_handle())
         self.connect(handles)
         dist.barrier()
+
+    def status(self):
+        """Bit mask of ranks whose contribution was missing from some bus (0 = all exchanges completed)."""
+        m = C.c_int32(0)
+        check(lib().mxb_exchange_status(self.h, C.byref(m)), "mxb_exchange_status")
+        return m.value
 
     def attach(self, bank):
         check(lib().mxb_bank_set_exchange(bank.h, self.h), "mxb_bank_set_exchange")

@@ -1,8 +1,10 @@
 // Voice bank host side: handles, parameter upload, coefficient design (the reference's formulas, run once
 // per parameter change on the host with the same libm the reference uses), launches.
 #include <math.h>
+#include <algorithm>
 
 #include <new>
+#include <thread>
 
 #include "bank_kernels.cuh"
 #include "delay_kernels.cuh"
@@ -16,7 +18,16 @@ struct mxb_bank {
     int V;
     bool set_mask[MXB_P_COUNT];
     std::vector<double> hp[MXB_P_COUNT];     // host copies of the parameter arrays (coefficient design input)
-    double* dp[MXB_P_COUNT];                 // device copies
+    double* dp[MXB_P_COUNT];                 // device copies: the buffer the next block reads (== dp_buf[id][dp_cur[id]])
+    // Block-rate control data uploaded with mxb_bank_set_param_async from host memory is double-buffered: the copy of block
+    // k+1's values runs on a private copy stream into the buffer block k is NOT reading, so it overlaps block k's kernel.
+    double* dp_buf[MXB_P_COUNT][2];          // [1] allocated on first asynchronous host upload
+    int dp_cur[MXB_P_COUNT];
+    bool dp_pending[MXB_P_COUNT];            // an upload into dp_buf[id][1 - cur] is in flight: the next block flips to it
+    cudaEvent_t ev_up[MXB_P_COUNT];          // upload finished (copy stream)
+    cudaEvent_t ev_read[MXB_P_COUNT][2];     // last kernel that read dp_buf[id][k] finished (process stream)
+    bool ev_read_set[MXB_P_COUNT][2];
+    cudaStream_t up_stream;
     double* osc_out;
     double *f0, *f1, *f2, *cf[5];
     double *env_amp, *env_output;
@@ -38,9 +49,9 @@ struct mxb_bank {
 namespace {
 
 // maxiFilter::lores / hires coefficient part, src/maximilian.cpp:456-462 (identical in hires :472-478)
-void design_lores(const mxb_bank* b, std::vector<double>* cf) {
+void design_lores(const mxb_bank* b, std::vector<double>* cf, const int v_lo, const int v_hi) {
     const double sr = (double)(size_t)b->ctx->sample_rate;
-    for (int v = 0; v < b->V; ++v) {
+    for (int v = v_lo; v < v_hi; ++v) {
         double cutoff = b->hp[MXB_P_CUTOFF][v], resonance = b->hp[MXB_P_RESONANCE][v];
         if (cutoff < 10) cutoff = 10;
         if (cutoff > sr) cutoff = sr;
@@ -53,9 +64,9 @@ void design_lores(const mxb_bank* b, std::vector<double>* cf) {
 }
 
 // maxiSVF::setParams, src/maximilian.h:1322-1334
-void design_svf(const mxb_bank* b, std::vector<double>* cf) {
+void design_svf(const mxb_bank* b, std::vector<double>* cf, const int v_lo, const int v_hi) {
     const double sr = (double)(size_t)b->ctx->sample_rate;
-    for (int v = 0; v < b->V; ++v) {
+    for (int v = v_lo; v < v_hi; ++v) {
         const double freq = b->hp[MXB_P_CUTOFF][v], res = b->hp[MXB_P_RESONANCE][v];
         const double g = tan(3.1415926535897932384626433832795 * freq / sr);
         const double damping = res == 0 ? 0 : 1.0 / res;
@@ -66,10 +77,10 @@ void design_svf(const mxb_bank* b, std::vector<double>* cf) {
 }
 
 // maxiBiquad::set, src/maximilian.h:1375-1479
-void design_biquad(const mxb_bank* b, std::vector<double>* cf) {
+void design_biquad(const mxb_bank* b, std::vector<double>* cf, const int v_lo, const int v_hi) {
     const double sr = (double)(size_t)b->ctx->sample_rate;
     const double SQRT2 = sqrt(2.0);
-    for (int v = 0; v < b->V; ++v) {
+    for (int v = v_lo; v < v_hi; ++v) {
         const double cutoff = b->hp[MXB_P_CUTOFF][v], Q = b->hp[MXB_P_RESONANCE][v], peakGain = b->hp[MXB_P_GAIN][v];
         double norm = 0, a0 = 0, a1 = 0, a2 = 0, b1 = 0, b2 = 0;
         const double G = pow(10.0, fabs(peakGain) / 20.0);
@@ -141,9 +152,21 @@ int redesign(mxb_bank* b) {
     if (fk == MXB_FILT_BIQUAD && !(b->set_mask[MXB_P_CUTOFF] && b->set_mask[MXB_P_RESONANCE])) return MXB_OK;   // untouched maxiBiquad: all-zero coefficients
     std::vector<double> cf[5];
     for (auto& c : cf) c.assign((size_t)b->V, 0.0);
-    if (fk == MXB_FILT_LORES || fk == MXB_FILT_HIRES) design_lores(b, cf);
-    else if (fk == MXB_FILT_SVF) design_svf(b, cf);
-    else design_biquad(b, cf);
+    // the design runs on the host with the libm the reference calls (bit-identical coefficients); a large bank is split
+    // over host threads (voices are independent), so that one cutoff change on 1 Mi voices costs a block, not dozens
+    auto part = [&](int lo, int hi) {
+        if (fk == MXB_FILT_LORES || fk == MXB_FILT_HIRES) design_lores(b, cf, lo, hi);
+        else if (fk == MXB_FILT_SVF) design_svf(b, cf, lo, hi);
+        else design_biquad(b, cf, lo, hi);
+    };
+    const unsigned hw = std::thread::hardware_concurrency();
+    const int nt = b->V < 32768 ? 1 : (int)std::min<unsigned>(hw ? hw : 1u, 32u);
+    if (nt <= 1) part(0, b->V);
+    else {
+        std::vector<std::thread> ts;
+        for (int i = 0; i < nt; ++i) ts.emplace_back(part, (int)((long long)b->V * i / nt), (int)((long long)b->V * (i + 1) / nt));
+        for (auto& t : ts) t.join();
+    }
     for (int i = 0; i < 5; ++i) MXB_CUDA(cudaMemcpy(b->cf[i], cf[i].data(), sizeof(double) * (size_t)b->V, cudaMemcpyHostToDevice));
     return MXB_OK;
 }
@@ -178,6 +201,11 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
     asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
@@ -199,7 +227,13 @@ __global__ void __launch_bounds__(kMixReduceThreads) mix_reduce_exchange_kernel(
     if (threadIdx.x < x.world) {
         __threadfence_system();                       // cumulative: the other CTAs' stores were ordered before their tickets
         st_release_sys(x.dst_flag[threadIdx.x], x.seq1);
-        while (ld_acquire_sys(x.src_flags + (size_t)threadIdx.x * (kExchFlagBytes / sizeof(unsigned long long))) < x.seq1) { }
+        // bounded wait: a peer that died (or never launched this block) costs timeout_ns, not a hung box; the bus is then
+        // incomplete and bit `rank` of *status says whose part is missing (mxb_exchange_status / mxb_bank_process report it)
+        const unsigned long long t0 = globaltimer_ns();
+        unsigned spins = 0;
+        while (ld_acquire_sys(x.src_flags + (size_t)threadIdx.x * (kExchFlagBytes / sizeof(unsigned long long))) < x.seq1) {
+            if ((++spins & 1023u) == 0 && globaltimer_ns() - t0 > x.timeout_ns) { atomicOr(x.status, 1u << threadIdx.x); break; }
+        }
     }
     if (threadIdx.x == 0) *x.ticket = 0;
     __syncthreads();
@@ -213,7 +247,12 @@ __global__ void __launch_bounds__(kMixReduceThreads) mix_reduce_exchange_kernel(
 
 int free_bank(mxb_bank* b) {
     if (!b) return MXB_OK;
-    for (int i = 0; i < MXB_P_COUNT; ++i) cudaFree(b->dp[i]);
+    for (int i = 0; i < MXB_P_COUNT; ++i) {
+        cudaFree(b->dp_buf[i][0]); cudaFree(b->dp_buf[i][1]);
+        if (b->ev_up[i]) cudaEventDestroy(b->ev_up[i]);
+        for (int k = 0; k < 2; ++k) if (b->ev_read[i][k]) cudaEventDestroy(b->ev_read[i][k]);
+    }
+    if (b->up_stream) cudaStreamDestroy(b->up_stream);
     cudaFree(b->osc_out); cudaFree(b->f0); cudaFree(b->f1); cudaFree(b->f2);
     for (int i = 0; i < 5; ++i) cudaFree(b->cf[i]);
     cudaFree(b->env_amp); cudaFree(b->env_output); cudaFree(b->env_holdcount); cudaFree(b->env_hold); cudaFree(b->env_flags);
@@ -249,7 +288,11 @@ int32_t mxb_bank_create(mxb_ctx* ctx, const mxb_bank_desc* d, mxb_bank** out) {
     mxb_bank* b = new (std::nothrow) mxb_bank();
     MXB_REQUIRE(b, MXB_ERR_ALLOC, "mxb_bank_create: out of host memory");
     b->ctx = ctx; b->desc = *d; b->V = d->voices;
-    for (auto& p : b->dp) p = nullptr;
+    for (int i = 0; i < MXB_P_COUNT; ++i) {
+        b->dp[i] = b->dp_buf[i][0] = b->dp_buf[i][1] = nullptr; b->dp_cur[i] = 0; b->dp_pending[i] = false;
+        b->ev_up[i] = nullptr; b->ev_read[i][0] = b->ev_read[i][1] = nullptr; b->ev_read_set[i][0] = b->ev_read_set[i][1] = false;
+    }
+    b->up_stream = nullptr; b->ex = nullptr;
     b->osc_out = b->f0 = b->f1 = b->f2 = nullptr;
     for (auto& c : b->cf) c = nullptr;
     b->env_amp = b->env_output = nullptr; b->env_holdcount = b->env_hold = nullptr; b->env_flags = nullptr;
@@ -264,7 +307,8 @@ int32_t mxb_bank_create(mxb_ctx* ctx, const mxb_bank_desc* d, mxb_bank** out) {
 #define TRY(x) do { rc = (x); if (rc != MXB_OK) { free_bank(b); return rc; } } while (0)
     static const double defaults[MXB_P_COUNT] = {0, 0, 0.5, 1000.0, 1.0, 0, 0, 0, 0, 0, 1.0, 1.0, 0, 0.5, 0, 0, 1.0};
     for (int i = 0; i < MXB_P_COUNT; ++i) {
-        TRY(dev_alloc(&b->dp[i], V));
+        TRY(dev_alloc(&b->dp_buf[i][0], V));
+        b->dp[i] = b->dp_buf[i][0];
         b->hp[i].assign(V, defaults[i]);
         if (defaults[i] != 0.0) TRY(upload_fill(b->dp[i], V, defaults[i]));
     }
@@ -322,7 +366,10 @@ int32_t mxb_bank_set_param(mxb_bank* b, int32_t id, const double* values, int32_
     MXB_REQUIRE(mem == MXB_MEM_HOST || mem == MXB_MEM_DEVICE, MXB_ERR_INVALID, "mxb_bank_set_param: mem %d", mem);
     DeviceGuard g(b->ctx->device);
     const size_t V = (size_t)b->V, bytes = sizeof(double) * V;
-    MXB_CUDA(cudaDeviceSynchronize());     // parameters change between blocks, never under a running one
+    // Parameters change between blocks. The copies below run on the legacy default stream: they are ordered after every
+    // block already enqueued on it or on any other blocking stream; a caller driving the bank from a NON-blocking stream
+    // synchronises that stream first. An asynchronous upload still in flight for this id is superseded.
+    if (b->dp_pending[id]) { MXB_CUDA(cudaEventSynchronize(b->ev_up[id])); b->dp_pending[id] = false; }
     if (mem == MXB_MEM_HOST) {
         memcpy(b->hp[id].data(), values, bytes);
         MXB_CUDA(cudaMemcpy(b->dp[id], values, bytes, cudaMemcpyHostToDevice));
@@ -354,8 +401,9 @@ int32_t mxb_bank_set_param(mxb_bank* b, int32_t id, const double* values, int32_
         std::vector<int> h(V);
         for (size_t v = 0; v < V; ++v) {
             const double s = b->hp[id][v];
-            MXB_REQUIRE(s <= (double)b->desc.delay_taps, MXB_ERR_INVALID,
-                        "mxb_bank_set_param: delay size %.0f of voice %zu exceeds delay_taps %d", s, v, b->desc.delay_taps);
+            // the reference takes any int (size <= 0 pins the index to slot 0); NaN / out-of-int values have no int conversion
+            MXB_REQUIRE(s == s && s > -2147483649.0 && s <= (double)b->desc.delay_taps, MXB_ERR_INVALID,
+                        "mxb_bank_set_param: delay size %g of voice %zu is not an int <= delay_taps %d", s, v, b->desc.delay_taps);
             h[v] = (int)s;
         }
         MXB_CUDA(cudaMemcpy(b->dl_size, h.data(), sizeof(int) * V, cudaMemcpyHostToDevice));
@@ -371,9 +419,24 @@ int32_t mxb_bank_set_param_async(mxb_bank* b, int32_t id, const double* values, 
                                  id == MXB_P_ENV_HOLDTIME || id == MXB_P_DELAY_SIZE || id == MXB_P_DELAY_POSITION;
     if (needs_host_pass) return mxb_bank_set_param(b, id, values, mem);      // coefficient design / integer conversion on the host
     DeviceGuard g(b->ctx->device);
-    // plain per-voice values used as they are by the kernels: one stream-ordered copy, nothing else
-    MXB_CUDA(cudaMemcpyAsync(b->dp[id], values, sizeof(double) * (size_t)b->V,
-                             mem == MXB_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, (cudaStream_t)stream_));
+    const size_t bytes = sizeof(double) * (size_t)b->V;
+    if (mem == MXB_MEM_DEVICE) {
+        // the source was produced on `stream`: one stream-ordered device copy into the buffer the next block reads
+        MXB_CUDA(cudaMemcpyAsync(b->dp[id], values, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream_));
+        b->set_mask[id] = true;
+        return MXB_OK;
+    }
+    // Host source: the upload goes to the buffer the running / enqueued blocks do NOT read, on the bank's own copy stream,
+    // so it overlaps them; the next mxb_bank_process waits for it (event) and switches over. The buffer being overwritten
+    // was last read two blocks ago: the copy waits for that kernel only.
+    if (!b->up_stream) MXB_CUDA(cudaStreamCreateWithFlags(&b->up_stream, cudaStreamNonBlocking));
+    if (!b->ev_up[id]) MXB_CUDA(cudaEventCreateWithFlags(&b->ev_up[id], cudaEventDisableTiming));
+    const int tgt = 1 - b->dp_cur[id];
+    if (!b->dp_buf[id][tgt]) { int rc = dev_alloc(&b->dp_buf[id][tgt], (size_t)b->V, false); if (rc != MXB_OK) return rc; }
+    if (b->ev_read_set[id][tgt]) MXB_CUDA(cudaStreamWaitEvent(b->up_stream, b->ev_read[id][tgt], 0));
+    MXB_CUDA(cudaMemcpyAsync(b->dp_buf[id][tgt], values, bytes, cudaMemcpyHostToDevice, b->up_stream));
+    MXB_CUDA(cudaEventRecord(b->ev_up[id], b->up_stream));
+    b->dp_pending[id] = true;
     b->set_mask[id] = true;
     return MXB_OK;
 }
@@ -481,6 +544,8 @@ int32_t mxb_bank_set_state(mxb_bank* b, int32_t id, const double* values, int32_
         std::vector<int> t(V);
         for (size_t v = 0; v < V; ++v) {
             MXB_REQUIRE(fabs(h[v]) < 2147483648.0, MXB_ERR_INVALID, "mxb_bank_set_state: value[%zu] = %g", v, h[v]);
+            // a negative ring index is an out-of-bounds access in the reference (memory[phase]); refused here
+            if (id == MXB_S_DELAY_PHASE) MXB_REQUIRE(h[v] >= 0.0, MXB_ERR_INVALID, "mxb_bank_set_state: delay phase[%zu] = %g is negative", v, h[v]);
             t[v] = (int)h[v];
             if (id == MXB_S_ENV_FLAGS) t[v] &= 31;
         }
@@ -501,7 +566,7 @@ int32_t mxb_bank_clone(mxb_bank* src, mxb_bank** out) {
     const size_t V = (size_t)src->V;
     cudaError_t e = cudaDeviceSynchronize();
     auto cp = [&](void* d, const void* s, size_t bytes) { if (e == cudaSuccess && d && s) e = cudaMemcpy(d, s, bytes, cudaMemcpyDeviceToDevice); };
-    for (int i = 0; i < MXB_P_COUNT; ++i) { b->hp[i] = src->hp[i]; b->set_mask[i] = src->set_mask[i]; cp(b->dp[i], src->dp[i], sizeof(double) * V); }
+    for (int i = 0; i < MXB_P_COUNT; ++i) { b->hp[i] = src->hp[i]; b->set_mask[i] = src->set_mask[i]; cp(b->dp[i], src->dp[i], sizeof(double) * V); }   // (an upload still in flight on the source is not part of its state yet)
     cp(b->osc_out, src->osc_out, sizeof(double) * V);
     cp(b->f0, src->f0, sizeof(double) * V); cp(b->f1, src->f1, sizeof(double) * V); cp(b->f2, src->f2, sizeof(double) * V);
     for (int i = 0; i < 5; ++i) cp(b->cf[i], src->cf[i], sizeof(double) * V);
@@ -535,6 +600,8 @@ int32_t mxb_bank_process_mod(mxb_bank* b, int32_t n_frames, const mxb_modulation
     const double* cutoff_tv = mod ? mod->cutoff_tv : nullptr;
     const double* dsize_tv = mod ? mod->delay_size_tv : nullptr;
     MXB_REQUIRE(n_frames >= 0 && n_frames <= b->desc.max_frames, MXB_ERR_INVALID, "mxb_bank_process: n_frames %d (max_frames %d)", n_frames, b->desc.max_frames);
+    const bool async_host = (mem & MXB_MEM_ASYNC) != 0;   // host buffers, but return as soon as everything is enqueued
+    mem &= ~MXB_MEM_ASYNC;
     MXB_REQUIRE(mem == MXB_MEM_HOST || mem == MXB_MEM_DEVICE || mem == MXB_MEM_SPLIT, MXB_ERR_INVALID, "mxb_bank_process: mem %d", mem);
     const bool host_ctl = mem != MXB_MEM_DEVICE;      // gates and mix in host memory
     const bool host_out = mem == MXB_MEM_HOST;        // out in host memory
@@ -545,6 +612,10 @@ int32_t mxb_bank_process_mod(mxb_bank* b, int32_t n_frames, const mxb_modulation
     if (fk == MXB_FILT_LORES || fk == MXB_FILT_HIRES)
         MXB_REQUIRE(b->set_mask[MXB_P_CUTOFF] && b->set_mask[MXB_P_RESONANCE], MXB_ERR_STATE,
                     "mxb_bank_process: lores/hires need MXB_P_CUTOFF and MXB_P_RESONANCE (they are call arguments in the reference)");
+    if (mix && b->ex) {     // before any kernel runs: a refused call must leave phase / filter / envelope / ring state untouched
+        MXB_REQUIRE(b->ex->connected, MXB_ERR_STATE, "mxb_bank_process: the attached exchange is not connected to its peers");
+        MXB_REQUIRE(n_frames * 2 <= b->ex->max_doubles, MXB_ERR_INVALID, "mxb_bank_process: exchange holds %d values, the bus needs %d", b->ex->max_doubles, n_frames * 2);
+    }
     if (n_frames == 0) return MXB_OK;
     DeviceGuard g(b->ctx->device);
     cudaStream_t s = (cudaStream_t)stream_;
@@ -618,6 +689,11 @@ int32_t mxb_bank_process_mod(mxb_bank* b, int32_t n_frames, const mxb_modulation
         }
     }
 
+    for (int id = 0; id < MXB_P_COUNT; ++id) {
+        if (!b->dp_pending[id]) continue;                 // an asynchronous host upload for this block: wait for it on the stream, switch over
+        MXB_CUDA(cudaStreamWaitEvent(s, b->ev_up[id], 0));
+        b->dp_cur[id] ^= 1; b->dp[id] = b->dp_buf[id][b->dp_cur[id]]; b->dp_pending[id] = false;
+    }
     BankArgs a;
     memset(&a, 0, sizeof(a));
     a.V = b->V; a.n_frames = n_frames; a.osc_kind = b->desc.osc_kind;
@@ -669,12 +745,17 @@ int32_t mxb_bank_process_mod(mxb_bank* b, int32_t n_frames, const mxb_modulation
         if (rc != MXB_OK) return rc;
     }
     b->launches += 1;
+    for (int id = 0; id < MXB_P_COUNT; ++id) {            // double-buffered parameters: remember when this block's reads are over
+        if (!b->dp_buf[id][1]) continue;
+        const int c = b->dp_cur[id];
+        if (!b->ev_read[id][c]) MXB_CUDA(cudaEventCreateWithFlags(&b->ev_read[id][c], cudaEventDisableTiming));
+        MXB_CUDA(cudaEventRecord(b->ev_read[id][c], s));
+        b->ev_read_set[id][c] = true;
+    }
     if (mix) {
         const int rows = n_frames * 2;
         const int threads = kMixReduceThreads, blocks = rows;
         if (b->ex) {
-            MXB_REQUIRE(b->ex->connected, MXB_ERR_STATE, "mxb_bank_process: the attached exchange is not connected to its peers");
-            MXB_REQUIRE(rows <= b->ex->max_doubles, MXB_ERR_INVALID, "mxb_bank_process: exchange holds %d values, the bus needs %d", b->ex->max_doubles, rows);
             mix_reduce_exchange_kernel<<<blocks, threads, 0, s>>>(b->partials, d_mix, rows, a.W, exchange_next(b->ex));
         } else {
             mix_reduce_kernel<<<blocks, threads, 0, s>>>(b->partials, d_mix, rows, a.W);
@@ -685,7 +766,13 @@ int32_t mxb_bank_process_mod(mxb_bank* b, int32_t n_frames, const mxb_modulation
     if (host_ctl) {
         if (out && host_out) MXB_CUDA(cudaMemcpyAsync(out, d_out, (size_t)n_frames * V * esz, cudaMemcpyDeviceToHost, s));
         if (mix) MXB_CUDA(cudaMemcpyAsync(mix, d_mix, sizeof(double) * (size_t)n_frames * 2, cudaMemcpyDeviceToHost, s));
+        if (async_host) return MXB_OK;            // results are valid once `stream` (or the context) has been synchronised
         MXB_CUDA(cudaStreamSynchronize(s));
+        if (mix && b->ex) {       // the call is synchronous in this mode: a timed-out exchange is an error of THIS call
+            unsigned int m = 0;
+            MXB_CUDA(cudaMemcpy(&m, b->ex->status, sizeof(m), cudaMemcpyDeviceToHost));
+            MXB_REQUIRE(m == 0, MXB_ERR_STATE, "mxb_bank_process: mix exchange timed out waiting for rank mask 0x%x (bus incomplete)", m);
+        }
     }
     return MXB_OK;
 }

@@ -317,7 +317,7 @@ __global__ void __launch_bounds__(kBankBlock) delay_bank_kernel(const BankArgs a
 
     if (s.live) {
         a.phase[v] = s.phase;
-        if (OSC == OSC_T_GENERIC) a.osc_out[v] = s.oout;
+        a.osc_out[v] = s.oout;
         if (FILT != FILT_T_NONE) {
             a.f0[v] = s.fr.s0; a.f1[v] = s.fr.s1;
             if (FILT == FILT_T_SVF || FILT == FILT_T_SVF_LP) a.f2[v] = s.fr.s2;

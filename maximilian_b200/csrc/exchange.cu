@@ -21,7 +21,7 @@ ExchDev exchange_next(mxb_exchange* ex) {
     ExchDev d;
     memset(&d, 0, sizeof(d));
     const size_t slot_off = ex->flags_bytes + (size_t)(ex->seq & 1) * ex->slot_bytes;
-    d.rank = ex->rank; d.world = ex->world; d.stride = ex->max_doubles; d.seq1 = ex->seq + 1; d.ticket = ex->ticket;
+    d.rank = ex->rank; d.world = ex->world; d.stride = ex->max_doubles; d.seq1 = ex->seq + 1; d.ticket = ex->ticket; d.status = ex->status; d.timeout_ns = ex->timeout_ns;
     for (int r = 0; r < ex->world; ++r) {
         d.dst_flag[r] = (unsigned long long*)(ex->peers[r] + (size_t)ex->rank * kExchFlagBytes);
         d.dst_payload[r] = (double*)(ex->peers[r] + slot_off) + (size_t)ex->rank * (size_t)ex->max_doubles;
@@ -55,6 +55,13 @@ int32_t mxb_exchange_create(mxb_ctx* ctx, int32_t rank, int32_t world, int32_t m
     e = cudaMemset(p, 0, total);
     if (e == cudaSuccess) e = cudaMalloc((void**)&ex->ticket, sizeof(unsigned int));
     if (e == cudaSuccess) e = cudaMemset(ex->ticket, 0, sizeof(unsigned int));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&ex->status, sizeof(unsigned int));
+    if (e == cudaSuccess) e = cudaMemset(ex->status, 0, sizeof(unsigned int));
+    {   // a dead peer must not hang the others: the flag wait is bounded (the kernel then reports through `status`)
+        const char* t = getenv("MXB_EXCHANGE_TIMEOUT_MS");
+        const double ms = t ? atof(t) : 5000.0;
+        ex->timeout_ns = (unsigned long long)((ms > 0.0 ? ms : 5000.0) * 1e6);
+    }
     if (e != cudaSuccess) { set_error("mxb_exchange_create: %s", cudaGetErrorString(e)); cudaFree(p); delete ex; return MXB_ERR_CUDA; }
     ex->peers[rank] = ex->local;
     ex->connected = (world == 1);
@@ -88,13 +95,22 @@ int32_t mxb_exchange_connect(mxb_exchange* ex, const void* all_handles) {
     return MXB_OK;
 }
 
+int32_t mxb_exchange_status(mxb_exchange* ex, int32_t* timed_out_ranks) {
+    MXB_REQUIRE(ex && timed_out_ranks, MXB_ERR_INVALID, "mxb_exchange_status: NULL argument");
+    DeviceGuard g(ex->ctx->device);
+    unsigned int m = 0;
+    MXB_CUDA(cudaMemcpy(&m, ex->status, sizeof(m), cudaMemcpyDeviceToHost));      // synchronises with the kernels that may set it
+    *timed_out_ranks = (int32_t)m;
+    return MXB_OK;
+}
+
 int32_t mxb_exchange_destroy(mxb_exchange* ex) {
     if (!ex) return MXB_OK;
     DeviceGuard g(ex->ctx->device);
     cudaDeviceSynchronize();
     for (int r = 0; r < ex->world; ++r)
         if (r != ex->rank && ex->peers[r]) cudaIpcCloseMemHandle(ex->peers[r]);
-    cudaFree(ex->local); cudaFree(ex->ticket);
+    cudaFree(ex->local); cudaFree(ex->ticket); cudaFree(ex->status);
     delete ex;
     return MXB_OK;
 }

@@ -19,6 +19,8 @@ struct ExchDev {                              // passed to the kernel by value
     int rank, world, stride;                  // stride = max_doubles (doubles between two source ranks' payloads)
     unsigned long long seq1;                  // value the flags reach when this call's payload is published
     unsigned int* ticket;                     // last-CTA election
+    unsigned int* status;                     // bit r set: rank r's flag did not arrive within timeout_ns (sticky)
+    unsigned long long timeout_ns;            // bound of the flag wait
 };
 
 }  // namespace mxb
@@ -32,6 +34,8 @@ struct mxb_exchange {
     bool connected;
     unsigned long long seq;                   // calls so far
     unsigned int* ticket;
+    unsigned int* status;                     // device word, see ExchDev::status
+    unsigned long long timeout_ns;            // default 5 s; MXB_EXCHANGE_TIMEOUT_MS overrides
 };
 
 namespace mxb {

@@ -205,6 +205,7 @@ int32_t mxo_bank_get(void* h, int32_t id, double* x) {
             case MXO_S_ENV_HOLDCOUNT: x[v] = (double)b->env_holdcount[v]; break;
             case MXO_S_ENV_FLAGS: x[v] = (double)b->env_flags[v]; break;
             case MXO_S_DELAY_PHASE: x[v] = (double)b->dl_phase[v]; break;
+            case MXO_S_OSC_OUTPUT: x[v] = b->osc_out[v]; break;
             default: if (id >= 0 && id < MXO_P_COUNT) x[v] = b->p[id][v]; else return -1;
         }
     }

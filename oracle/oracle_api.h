@@ -68,7 +68,8 @@ enum {
     MXO_S_ENV_OUTPUT = 36,
     MXO_S_ENV_HOLDCOUNT = 37,
     MXO_S_ENV_FLAGS = 38, /* attack | decay<<1 | sustain<<2 | hold<<3 | release<<4 */
-    MXO_S_DELAY_PHASE = 39
+    MXO_S_DELAY_PHASE = 39,
+    MXO_S_OSC_OUTPUT = 40  /* maxiOsc::output (assigned by every method but impulse) */
 };
 
 typedef struct {

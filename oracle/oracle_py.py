@@ -17,7 +17,9 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 PATHS = {"port": os.path.join(HERE, "libmaxioracle.so"),
-         "reference": os.path.join(HERE, "_ref", "libmaxiref.so")}
+         "reference": os.path.join(HERE, "_ref", "libmaxiref.so"),
+         # the same unmodified sources at -O3 -march=x86-64-v3: a CPU baseline to TIME (bench.py), never a checker
+         "reference_o3": os.path.join(HERE, "_ref", "libmaxiref_o3.so")}
 
 # stage selectors / ids: keep in sync with oracle_api.h
 OSC = dict(sinewave=0, coswave=1, phasor=2, saw=3, square=4, pulse=5, impulse=6, triangle=7, phasorbetween=8)
@@ -26,7 +28,7 @@ BIQUAD = dict(lowpass=0, highpass=1, bandpass=2, notch=3, peak=4, lowshelf=5, hi
 P = dict(freq=0, phase=1, duty=2, cutoff=3, resonance=4, gain=5, env_attack=6, env_decay=7,
          env_sustain=8, env_release=9, env_holdtime=10, delay_size=11, delay_feedback=12, pan=13, delay_position=14,
          phasor_start=15, phasor_end=16, filt0=32, filt1=33, filt2=34, env_amplitude=35, env_output=36, env_holdcount=37,
-         env_flags=38, delay_phase=39)
+         env_flags=38, delay_phase=39, osc_output=40)
 
 
 ENV_KIND = {False: 0, None: 0, True: 1, "adsr": 1, "ar": 2}
@@ -89,7 +91,7 @@ def load(kind="port"):
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
         fn.restype, fn.argtypes = res, args
-    assert lib.mxo_kind().decode() == kind, (lib.mxo_kind(), kind)
+    assert kind.startswith(lib.mxo_kind().decode()), (lib.mxo_kind(), kind)
     _libs[kind] = lib
     return lib
 

@@ -178,6 +178,7 @@ int32_t mxo_bank_get(void* h, int32_t id, double* x) {
                                 (r.env.holdphase & 1) << 3 | (r.env.releasephase & 1) << 4);
                 break;
             case MXO_S_DELAY_PHASE: x[v] = b->delays ? (double)b->delays[v]->phase : 0.0; break;
+            case MXO_S_OSC_OUTPUT: x[v] = r.osc.output; break;
             default:
                 if (id >= 0 && id < MXO_P_COUNT && !b->p[id].empty()) x[v] = b->p[id][v]; else return -1;
         }

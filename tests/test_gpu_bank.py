@@ -59,7 +59,7 @@ def test_every_osc_filter_pair_vs_oracle(port, osc, filt):
         og, mg = g.process(B, want_mix=True); oo, mo = o.process(B, want_mix=True)
         _close(og, oo, osc in TRIG, f"{osc}->{filt} blk{blk}")
         np.testing.assert_allclose(mg, mo, rtol=1e-9, atol=1e-11)
-    for s in ("phase", "filt0", "filt1", "filt2"):
+    for s in ("phase", "filt0", "filt1", "filt2", "osc_output"):      # maxiOsc::output: assigned by every method but impulse
         _close(g.get(s), o.get(s), osc in TRIG, s)
 
 
@@ -393,26 +393,83 @@ def test_mix_only_and_determinism(port):
     np.testing.assert_allclose(runs[0], mo, rtol=1e-9, atol=1e-10)
 
 
-def test_full_size_properties_1m_voices():
-    """BASELINE.json configs[1] at full size (1M voices, saw -> SVF, 1024-frame block): too big for the CPU
-    oracle in seconds, so check size-independent properties: (a) voices are independent -- the first 4096
-    voices of the big bank equal a 4096-voice bank bit for bit; (b) the stereo mix equals the pan-weighted
-    sum of the materialised output (fp64 reassociation only); (c) a second identical run is bit-identical."""
-    V, B, S = 1 << 20, 1024, 4096
+def _slice_indices(V, n_each=704, mid=640):
+    """2048 voices: the first and last warps of the bank and a run in the middle (CTA- and warp-boundary crossing)."""
+    return np.concatenate([np.arange(0, n_each), np.arange(V // 2 - mid // 2, V // 2 + mid // 2), np.arange(V - n_each, V)])
+
+
+def test_full_size_1m_voices_vs_oracle_slices(port):
+    """BASELINE.json configs[1] at its own size (1 Mi voices, saw -> SVF low-pass, 1024-frame blocks, device buffers as in
+    bench.py), three consecutive blocks: a 2048-voice slice (first / middle / last warps of the grid) of the materialised
+    output is compared BIT FOR BIT with the CPU oracle run on those voices, the filter state and phases of the slice
+    likewise; the stereo bus equals the pan-weighted sum of the materialised output (fp64 reassociation only) and a
+    second identical bank reproduces it bit for bit (fixed summation order)."""
+    import torch
+    V, B = 1 << 20, 1024
+    dev = torch.device("cuda", 0)
     p = W.voice_params(V, seed=W.SEED)
+    idx = _slice_indices(V)
     big = gpu_bank(V, osc="saw", filt="svf", max_frames=B)
     W.configure_bank(big, "svf", p)
-    out = np.empty((B, V), dtype=np.float32)          # fp32 storage keeps the host buffer at 4 GiB
-    _, mix = big.process(B, want_mix=True, out_dtype=np.float32, out=out)
-    small = gpu_bank(S, osc="saw", filt="svf", max_frames=B)
-    W.configure_bank(small, "svf", {k: v[:S] for k, v in p.items()})
-    os_, _ = small.process(B, out_dtype=np.float32)
-    assert np.array_equal(out[:, :S], os_)
-    pan = np.clip(p["pan"], 0, 1)
-    for t in (0, 1, 511, 1023):
-        row = out[t].astype(np.float64)
-        np.testing.assert_allclose(mix[t], [np.dot(row, np.sqrt(1 - pan)), np.dot(row, np.sqrt(pan))], rtol=1e-5, atol=1e-3)
+    o = port.Bank(idx.size, osc="saw", filt="svf"); W.configure_bank(o, "svf", {k: v[idx] for k, v in p.items()})
+    out = torch.empty((B, V), dtype=torch.float64, device=dev)
+    mix = torch.empty((B, 2), dtype=torch.float64, device=dev)
+    tidx = torch.from_numpy(idx).to(dev)
+    pan = torch.from_numpy(np.clip(p["pan"], 0, 1)).to(dev)
+    for blk in range(3):
+        big.process_device(B, out_ptr=out.data_ptr(), mix_ptr=mix.data_ptr())
+        torch.cuda.synchronize()
+        oo, _ = o.process(B)
+        got = out[:, tidx].cpu().numpy()
+        assert np.array_equal(got, oo), f"blk{blk}: slice differs from the oracle, max {np.abs(got - oo).max()}"
+        ref_mix = torch.stack([out @ torch.sqrt(1 - pan), out @ torch.sqrt(pan)], dim=1)
+        torch.testing.assert_close(mix, ref_mix, rtol=1e-9, atol=1e-7)
+    for s_ in ("phase", "filt0", "filt1", "filt2", "osc_output"):
+        assert np.array_equal(big.get(s_)[idx], o.get(s_)), s_
+    mix1 = mix.cpu().numpy()
+    del out
     big2 = gpu_bank(V, osc="saw", filt="svf", max_frames=B)
     W.configure_bank(big2, "svf", p)
-    _, mix2 = big2.process(B, want_out=False, want_mix=True)
-    assert np.array_equal(mix, mix2)
+    for blk in range(3):
+        big2.process_device(B, out_ptr=None, mix_ptr=mix.data_ptr())
+    torch.cuda.synchronize()
+    assert np.array_equal(mix.cpu().numpy(), mix1)           # mix-only kernel == out+mix kernel, run to run
+
+
+@pytest.mark.parametrize("ragged", [False, True])
+def test_full_size_config2_delay_256k_voices_4096_taps_vs_oracle_slices(port, ragged):
+    """BASELINE.json configs[2] at its own parameters: 262 144 voices, saw -> maxiEnv::adsr -> maxiDelayline::dl with a
+    4096-slot ring per voice (8 GiB of rings, 64-bit slot arithmetic), 1024-frame blocks, 5 consecutive blocks with
+    note gates (so the ring index wraps: 5 * 1024 > 4096) -- the uniform 4 KB-run schedule (ragged=False) and the
+    per-voice schedule (ragged sizes in [1024, 4096]). A 2048-voice slice (first / middle / last warps) of the output,
+    the int ring index, the envelope state and the FULL ring contents of 24 of those voices are compared bit for bit with
+    the CPU oracle run on those voices; shard invariance: the first 4096 voices as their own bank give the same bits."""
+    import torch
+    V, B, cap, NB = 1 << 18, 1024, 4096, 5
+    dev = torch.device("cuda", 0)
+    p = W.voice_params(V, seed=W.SEED + 2, delay_size=cap, ragged_delay=ragged)
+    idx = _slice_indices(V)
+    big = gpu_bank(V, osc="saw", env=True, delay=True, delay_capacity=cap, max_frames=B)
+    W.configure_bank(big, "none", p, env=True, delay=True)
+    o = port.Bank(idx.size, osc="saw", env=True, delay=True, delay_capacity=cap)
+    W.configure_bank(o, "none", {k: v[idx] for k, v in p.items()}, env=True, delay=True)
+    S = 4096
+    small = gpu_bank(S, osc="saw", env=True, delay=True, delay_capacity=cap, max_frames=B)
+    W.configure_bank(small, "none", {k: v[:S] for k, v in p.items()}, env=True, delay=True)
+    out = torch.empty((B, V), dtype=torch.float64, device=dev)
+    tidx = torch.from_numpy(idx).to(dev)
+    for blk in range(NB):
+        on, off = W.gate(V, B, 4 * (blk // 2) if blk % 2 == 0 else 1, seed=W.SEED + blk)
+        d_on, d_off = torch.from_numpy(on).to(dev), torch.from_numpy(off).to(dev)
+        big.process_device(B, out_ptr=out.data_ptr(), trig_on_ptr=d_on.data_ptr(), trig_off_ptr=d_off.data_ptr())
+        torch.cuda.synchronize()
+        oo, _ = o.process(B, on[idx], off[idx])
+        got = out[:, tidx].cpu().numpy()
+        assert np.array_equal(got, oo), f"blk{blk}: slice differs from the oracle, max {np.abs(got - oo).max()}"
+        os_, _ = small.process(B, on[:S], off[:S])
+        assert np.array_equal(out[:, :S].cpu().numpy(), os_), f"blk{blk}: shard invariance"
+        assert np.array_equal(big.get("delay_phase")[idx], o.get("delay_phase")), blk          # int ring index: exact
+    for s_ in ("env_holdcount", "env_flags", "env_amplitude", "env_output", "phase"):
+        assert np.array_equal(big.get(s_)[idx], o.get(s_)), s_
+    for k in range(0, idx.size, idx.size // 24):
+        assert np.array_equal(big.ring(int(idx[k]), cap), o.ring(k, cap)), f"ring of voice {idx[k]}"

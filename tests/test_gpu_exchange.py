@@ -25,47 +25,32 @@ def test_world_of_one_is_the_plain_mix():
         assert np.array_equal(ma, mb)
 
 
-def _rank(rank, world, q_in, q_out, results):
-    import torch
-    torch.cuda.set_device(rank)
-    from maximilian_b200 import shard
-    ctx = capi.Context(rank, 48000)
-    p = W.voice_params(V, seed=3)
-    lo, hi = shard.shard_range(V, rank, world)
-    bank = capi.Bank(hi - lo, osc="saw", filt="biquad", max_frames=B, ctx=ctx)
-    W.configure_bank(bank, "biquad", {k: v[lo:hi] for k, v in p.items()})
-    ex = capi.Exchange(ctx, rank, world, max_doubles=2 * B)
-    q_out.put((rank, ex.local_handle()))
-    handles = q_in.get(timeout=120)
-    ex.connect(handles)
-    ex.attach(bank)
-    mixes = []
-    for _ in range(NBLK):
-        _, m = bank.process(B, want_out=False, want_mix=True)
-        mixes.append(m.copy())
-    results.put((rank, np.stack(mixes)))
-
-
 def test_two_ranks_share_one_bus(port):
     import torch
-    import torch.multiprocessing as mp
+    from maximilian_b200 import shard
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs (gpurun --gpus 2)")
-    world = 2
-    ctx = mp.get_context("spawn")
-    q_ins = [ctx.Queue() for _ in range(world)]
-    q_out, results = ctx.Queue(), ctx.Queue()
-    procs = [ctx.Process(target=_rank, args=(r, world, q_ins[r], q_out, results)) for r in range(world)]
-    [p.start() for p in procs]
-    hs = dict(q_out.get(timeout=120) for _ in range(world))
+    world = min(torch.cuda.device_count(), 4)
+    res = shard.run_exchange_ranks(world, V, B, NBLK, seed=3)
     for r in range(world):
-        q_ins[r].put([hs[k] for k in range(world)])
-    res = dict(results.get(timeout=300) for _ in range(world))
-    [p.join(timeout=60) for p in procs]
-    assert all(p.exitcode == 0 for p in procs)
-    assert np.array_equal(res[0], res[1])                       # same bits on every rank
+        buses, err, status = res[r]
+        assert err is None and status == 0, (r, err, status)
+        assert np.array_equal(buses, res[0][0])                 # same bits on every rank
     p = W.voice_params(V, seed=3)
     o = port.Bank(V, osc="saw", filt="biquad"); W.configure_bank(o, "biquad", p)
     for k in range(NBLK):
         _, mo = o.process(B, want_out=False, want_mix=True)
-        np.testing.assert_allclose(res[0][k], mo, rtol=1e-9, atol=1e-10)
+        np.testing.assert_allclose(res[0][0][k], mo, rtol=1e-9, atol=1e-10)
+
+
+def test_a_silent_peer_times_out_instead_of_hanging():
+    """Rank 1 connects and never launches a block: rank 0's exchange kernel gives up after the bounded wait
+    (MXB_EXCHANGE_TIMEOUT_MS), mxb_bank_process returns MXB_ERR_STATE and the status mask names the missing rank."""
+    import torch
+    from maximilian_b200 import shard
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (gpurun --gpus 2)")
+    res = shard.run_exchange_ranks(2, V, B, 2, seed=3, silent_rank=1, timeout_ms=300)
+    buses, err, status = res[0]
+    assert err is not None and "timed out" in err, err
+    assert status == 0b10
