@@ -66,6 +66,7 @@ enum {
     MXB_OSC_IMPULSE = 6,   /* :312-319 */
     MXB_OSC_TRIANGLE = 7,  /* :362-373 */
     MXB_OSC_PHASORBETWEEN = 8  /* :321-330, phasorBetween(frequency, startphase, endphase) */
+    /* 9..11: the table oscillators, patch stages only (MXB_OSC_SINEBUF ...) */
 };
 /* filter kinds */
 enum {
@@ -227,6 +228,74 @@ int32_t mxb_bank_process_mod(mxb_bank* bank, int32_t n_frames, const mxb_modulat
                              int32_t mem, void* stream);
 /* kernels launched by this library on behalf of `bank` since creation (for bench.py's gpu_launches) */
 int64_t mxb_bank_launch_count(const mxb_bank* bank);
+
+/* ------------------------------------------------------------------------------------------------
+ * Voice patch: a per-voice signal GRAPH, run sample by sample for `voices` voices -- the body of any reference play()
+ * written with the classes of this path. The bank above is hard-wired to osc -> env -> filter -> delay -> mix (the chains
+ * BASELINE.json measures, at the HBM roofline); a patch expresses what real patches do and the bank cannot: two
+ * oscillators summed into one filter, an LFO added to a frequency or a cutoff, the envelope multiplying the FILTER OUTPUT
+ * (cpp/commandline/maximilian_examples/15.polysynth/main.cpp:54-70), a trigger that changes on any sample
+ * (10.Filters/main.cpp:27-36), and the rest of the family: table oscillators, one-pole filters, maxiDCBlocker,
+ * maxiNonlinearity, maxiEnvGen, maxiFlanger. One interpreting kernel runs the stage list (warp-uniform dispatch: every
+ * voice runs the same program); state lives on the device between calls like a bank's.
+ *
+ * A stage computes dst = op(src...) on 16 per-voice registers that read 0 until written within the sample. Operands: */
+#define MXB_STAGE_SRCS 8
+#define MXB_NONE (-1)
+#define MXB_REG(i)   (i)             /* register i, 0..15 */
+#define MXB_PARAM(j) (0x100 + (j))   /* per-voice parameter array j (mxb_patch_set_param), 0..31 */
+#define MXB_CONST(k) (0x200 + (k))   /* scalar k of mxb_patch_desc.consts, 0..63 */
+#define MXB_INPUT(m) (0x300 + (m))   /* per-sample input stream m of mxb_patch_process: double [n_frames][voices], 0..7 */
+/* oscillator kinds of MXB_OP_OSC beyond MXB_OSC_*: the table oscillators (tables: mxb_ctx_set_tables) */
+enum { MXB_OSC_SINEBUF = 9 /* maxiOsc::sinebuf src/maximilian.cpp:266-274 */, MXB_OSC_SINEBUF4 = 10 /* :237-264 */, MXB_OSC_SAWN = 11 /* :342-359 */ };
+/* filter kinds of MXB_OP_FILTER beyond MXB_FILT_LORES / HIRES */
+enum { MXB_FILT_LOPASS = 5 /* maxiFilter::lopass src/maximilian.cpp:442-446 */, MXB_FILT_HIPASS = 6 /* :449-453 */, MXB_FILT_BANDPASS = 7 /* :487-500 */ };
+/* maxiNonlinearity (src/maximilian.h:1046-1137) */
+enum { MXB_NL_ATANDIST = 0, MXB_NL_FASTATANDIST, MXB_NL_SOFTCLIP, MXB_NL_HARDCLIP, MXB_NL_ASYMCLIP, MXB_NL_FASTATAN };
+#define MXB_ENVGEN_HOLD (-46692.0)   /* maxiEnvGen::HOLD, src/maximilian.h:2271 */
+enum {
+    MXB_OP_OSC = 1,      /* kind MXB_OSC_*: src0 frequency, src1 duty | startphase, src2 endphase.              state: phase, output */
+    MXB_OP_ENV_ADSR,     /* maxiEnv::adsr(input, attack, decay, sustain, release, holdtime, trigger) src/maximilian.cpp:1362-1413:
+                            src0 input, src1 trigger ((int)value == 1), src2..6 attack decay sustain release holdtime. state: amplitude, output, holdcount, flags */
+    MXB_OP_ENV_AR,       /* maxiEnv::ar :1319-1358: src0 input, src1 trigger, src2 attack, src3 release, src4 holdtime */
+    MXB_OP_ENVGEN,       /* maxiEnvGen::play(trigger) src/maximilian.h:2276-2357, segments from mxb_patch_desc.eg_*: src0 trigger */
+    MXB_OP_FILTER,       /* kind MXB_FILT_LORES | HIRES | LOPASS | HIPASS | BANDPASS: src0 input, src1 cutoff, src2 resonance */
+    MXB_OP_SVF,          /* maxiSVF setCutoff + setResonance + play src/maximilian.h:1287-1334: src0 input, src1 cutoff, src2 resonance, src3..6 lp bp hp notch mix */
+    MXB_OP_BIQUAD,       /* kind MXB_BQ_*: maxiBiquad::set + play src/maximilian.h:1360-1479: src0 input, src1 cutoff, src2 Q, src3 peakGain */
+    MXB_OP_DCBLOCK,      /* maxiDCBlocker::play src/maximilian.h:1255-1267: src0 input, src1 R.                  state: xm1, ym1 */
+    MXB_OP_NONLIN,       /* kind MXB_NL_*: src0 input, src1 shape | a, src2 b */
+    MXB_OP_DELAY,        /* kind MXB_DELAY_*: maxiDelayline::dl / dlFromPosition: src0 input, src1 size, src2 feedback, src3 position. state: phase */
+    MXB_OP_FLANGER,      /* maxiFlanger::flange src/maximilian.h:1144-1180: src0 input, src1 delay, src2 feedback, src3 speed, src4 depth. state: dl phase, lfo phase, lfo output */
+    MXB_OP_ADD, MXB_OP_SUB, MXB_OP_MUL, MXB_OP_DIV,   /* src0 (+ - * /) src1: the arithmetic a play() does between the calls */
+    MXB_OP_MIX_STEREO,   /* maxiMix::stereo(src0, two, src1 = pan) summed into the bus (src/maximilian.cpp:503-509) */
+    MXB_OP_OUT           /* out[t][voice] = src0 */
+};
+typedef struct { int32_t op, kind, dst, reserved; int32_t src[MXB_STAGE_SRCS]; } mxb_stage;
+typedef struct {
+    int32_t voices, n_stages, n_params, n_consts, n_inputs, max_frames;
+    int32_t delay_taps;           /* ring slots per voice of every DELAY / FLANGER stage */
+    int32_t eg_stages, eg_loop, eg_retrigger;     /* maxiEnvGen::setup(levels, times, curves, looping, allowRetrigger): eg_stages + 1 levels */
+    const mxb_stage* stages;
+    const double* consts;
+    const double *eg_levels, *eg_times /* ms or MXB_ENVGEN_HOLD */, *eg_curves;
+} mxb_patch_desc;
+typedef struct mxb_patch mxb_patch;
+/* The reference's lookup tables sineBuffer[514] and transition[1001] (src/maximilian.cpp:63, 67-200) are DATA of the
+ * reference: an integration passes its own arrays (they have external linkage there). sine_before: the double that
+ * maxiOsc::sinebuf4 reads at sineBuffer[-1] on the one sample per cycle where its phase has just wrapped into [-1, 0)
+ * (an out-of-bounds read in the reference, src/maximilian.cpp:251); pass (&sineBuffer[0])[-1] for bit parity with a given
+ * build, or sineBuffer[511] for the periodic extension the author intended. */
+int32_t mxb_ctx_set_tables(mxb_ctx* ctx, const double* sine514, const double* transition1001, double sine_before);
+int32_t mxb_patch_create(mxb_ctx* ctx, const mxb_patch_desc* desc, mxb_patch** patch);
+int32_t mxb_patch_destroy(mxb_patch* patch);
+int32_t mxb_patch_set_param(mxb_patch* patch, int32_t j, const double* values, int32_t mem);
+/* state slot `slot` of stage `stage` (the order given with the ops above; integral members arrive / return as doubles) */
+int32_t mxb_patch_set_state(mxb_patch* patch, int32_t stage, int32_t slot, const double* values, int32_t mem);
+int32_t mxb_patch_get_state(mxb_patch* patch, int32_t stage, int32_t slot, double* values, int32_t mem);
+int32_t mxb_patch_get_ring(mxb_patch* patch, int32_t stage, int32_t voice, double* dst, int32_t n, int32_t mem);
+/* inputs: n_inputs pointers to double [n_frames][voices]; out: [n_frames][voices] or NULL; mix: [n_frames][2] or NULL */
+int32_t mxb_patch_process(mxb_patch* patch, int32_t n_frames, const double* const* inputs, double* out, double* mix, int32_t mem, void* stream);
+int64_t mxb_patch_launch_count(const mxb_patch* patch);
 
 /* ------------------------------------------------------------------------------------------------
  * Multi-GPU mix-down: one process per GPU, voices sharded, every rank ends each block with the SAME stereo bus

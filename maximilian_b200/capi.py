@@ -30,6 +30,8 @@ EXPORTS = [
     "mxb_stft_create", "mxb_stft_destroy", "mxb_stft_process", "mxb_stft_process2", "mxb_stft_launch_count",
     "mxb_mfcc_create", "mxb_mfcc_destroy", "mxb_mfcc_process",
     "mxb_istft_create", "mxb_istft_destroy", "mxb_istft_process",
+    "mxb_ctx_set_tables", "mxb_patch_create", "mxb_patch_destroy", "mxb_patch_set_param", "mxb_patch_set_state", "mxb_patch_get_state",
+    "mxb_patch_get_ring", "mxb_patch_process", "mxb_patch_launch_count",
 ]
 
 
@@ -111,6 +113,15 @@ def lib():
         "mxb_istft_create": (i32, [vp, i32, i32, i32, pp]),
         "mxb_istft_destroy": (i32, [vp]),
         "mxb_istft_process": (i32, [vp, vp, vp, i32, vp, i32, vp]),
+        "mxb_ctx_set_tables": (i32, [vp, vp, vp, dbl]),
+        "mxb_patch_create": (i32, [vp, vp, pp]),
+        "mxb_patch_destroy": (i32, [vp]),
+        "mxb_patch_set_param": (i32, [vp, i32, vp, i32]),
+        "mxb_patch_set_state": (i32, [vp, i32, i32, vp, i32]),
+        "mxb_patch_get_state": (i32, [vp, i32, i32, vp, i32]),
+        "mxb_patch_get_ring": (i32, [vp, i32, i32, vp, i32, i32]),
+        "mxb_patch_process": (i32, [vp, i32, vp, vp, vp, i32, vp]),
+        "mxb_patch_launch_count": (i64, [vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)          # AttributeError here = the library does not export a declared symbol
@@ -468,3 +479,89 @@ class Istft:
         out = np.empty((self.C, frames * self.hop), dtype=np.float32)
         check(lib().mxb_istft_process(self.h, _np_ptr(m), _np_ptr(p), frames, _np_ptr(out), MEM_HOST, None), "mxb_istft_process")
         return out
+
+
+# ------------------------------------------------------------------------------------------------ voice patches
+
+class Stage(C.Structure):
+    _fields_ = [("op", C.c_int32), ("kind", C.c_int32), ("dst", C.c_int32), ("reserved", C.c_int32), ("src", C.c_int32 * 8)]
+
+
+class PatchDesc(C.Structure):
+    _fields_ = [("voices", C.c_int32), ("n_stages", C.c_int32), ("n_params", C.c_int32), ("n_consts", C.c_int32), ("n_inputs", C.c_int32),
+                ("max_frames", C.c_int32), ("delay_taps", C.c_int32), ("eg_stages", C.c_int32), ("eg_loop", C.c_int32), ("eg_retrigger", C.c_int32),
+                ("stages", C.POINTER(Stage)), ("consts", C.POINTER(C.c_double)),
+                ("eg_levels", C.POINTER(C.c_double)), ("eg_times", C.POINTER(C.c_double)), ("eg_curves", C.POINTER(C.c_double))]
+
+
+def set_tables(sine514, transition1001, sine_before, ctx=None, device=0, sample_rate=48000):
+    """mxb_ctx_set_tables: the reference's sineBuffer / transition arrays (data of the reference, handed in by the caller)."""
+    ctx = ctx or default_context(device, sample_rate)
+    s = np.ascontiguousarray(sine514, dtype=np.float64); t = np.ascontiguousarray(transition1001, dtype=np.float64)
+    assert s.size == 514 and t.size == 1001
+    check(lib().mxb_ctx_set_tables(ctx.h, _np_ptr(s), _np_ptr(t), float(sine_before)), "mxb_ctx_set_tables")
+
+
+class Patch:
+    """mxb_patch: a per-voice signal graph (maximilian_b200.patchdef.PatchDef) run by the interpreting kernel."""
+
+    def __init__(self, defn, voices, max_frames=1024, delay_taps=0, ctx=None, device=0, sample_rate=48000):
+        self.ctx = ctx or default_context(device, sample_rate)
+        self.defn, self.V, self.max_frames = defn, int(voices), int(max_frames)
+        st = (Stage * len(defn.stages))()
+        for i, (op, kind, dst, src) in enumerate(defn.stages):
+            st[i].op, st[i].kind, st[i].dst, st[i].reserved = op, kind, dst, 0
+            for k in range(8):
+                st[i].src[k] = src[k]
+        consts = (C.c_double * max(1, len(defn.consts)))(*defn.consts)
+        eg = defn.eg or ([0.0], [], [], False, False)
+        lv = (C.c_double * max(1, len(eg[0])))(*eg[0]); tm = (C.c_double * max(1, len(eg[1])))(*eg[1]); cv = (C.c_double * max(1, len(eg[2])))(*eg[2])
+        d = PatchDesc(self.V, len(defn.stages), len(defn.params), len(defn.consts), len(defn.inputs), self.max_frames, int(delay_taps),
+                      len(eg[1]), int(eg[3]), int(eg[4]), st, consts, lv, tm, cv)
+        self.h = C.c_void_p()
+        check(lib().mxb_patch_create(self.ctx.h, C.byref(d), C.byref(self.h)), "mxb_patch_create")
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().mxb_patch_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set(self, name, values):
+        a = np.ascontiguousarray(np.broadcast_to(np.asarray(values, dtype=np.float64), (self.V,)))
+        check(lib().mxb_patch_set_param(self.h, self.defn.params.index(name), _np_ptr(a), MEM_HOST), f"mxb_patch_set_param({name})")
+
+    def get_state(self, stage, slot):
+        a = np.empty(self.V, dtype=np.float64)
+        check(lib().mxb_patch_get_state(self.h, stage, slot, _np_ptr(a), MEM_HOST), "mxb_patch_get_state")
+        return a
+
+    def set_state(self, stage, slot, values):
+        a = np.ascontiguousarray(np.broadcast_to(np.asarray(values, dtype=np.float64), (self.V,)))
+        check(lib().mxb_patch_set_state(self.h, stage, slot, _np_ptr(a), MEM_HOST), "mxb_patch_set_state")
+
+    def ring(self, stage, v, n):
+        a = np.empty(n, dtype=np.float64)
+        check(lib().mxb_patch_get_ring(self.h, stage, v, _np_ptr(a), n, MEM_HOST), "mxb_patch_get_ring")
+        return a
+
+    @property
+    def launches(self):
+        return int(lib().mxb_patch_launch_count(self.h))
+
+    def process(self, nframes, inputs=None, want_out=True, want_mix=False):
+        """inputs: dict name -> float64 [nframes][V]. Returns (out[nframes][V] | None, mix[nframes][2] | None)."""
+        inputs = inputs or {}
+        arrs = [np.ascontiguousarray(inputs[n], dtype=np.float64) for n in self.defn.inputs]
+        for a in arrs:
+            assert a.shape == (nframes, self.V)
+        ptrs = (C.c_void_p * max(1, len(arrs)))(*[a.ctypes.data for a in arrs])
+        out = np.empty((nframes, self.V), dtype=np.float64) if want_out else None
+        mix = np.empty((nframes, 2), dtype=np.float64) if want_mix else None
+        check(lib().mxb_patch_process(self.h, nframes, ptrs, _np_ptr(out), _np_ptr(mix), MEM_HOST, None), "mxb_patch_process")
+        return out, mix

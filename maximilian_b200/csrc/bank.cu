@@ -9,6 +9,7 @@
 #include "bank_kernels.cuh"
 #include "delay_kernels.cuh"
 #include "exchange.cuh"
+#include "filter_design.cuh"
 
 using namespace mxb;
 
@@ -48,100 +49,26 @@ struct mxb_bank {
 
 namespace {
 
-// maxiFilter::lores / hires coefficient part, src/maximilian.cpp:456-462 (identical in hires :472-478)
+// coefficient design, once per parameter change, on the host with the libm the reference calls (filter_design.cuh holds the
+// reference's formulas, shared with the per-sample device design of patch stages)
 void design_lores(const mxb_bank* b, std::vector<double>* cf, const int v_lo, const int v_hi) {
     const double sr = (double)(size_t)b->ctx->sample_rate;
-    for (int v = v_lo; v < v_hi; ++v) {
-        double cutoff = b->hp[MXB_P_CUTOFF][v], resonance = b->hp[MXB_P_RESONANCE][v];
-        if (cutoff < 10) cutoff = 10;
-        if (cutoff > sr) cutoff = sr;
-        if (resonance < 1.) resonance = 1.;
-        const double z = cos(6.283185307179586476925286766559 * cutoff / sr);
-        const double c = 2 - 2 * z;
-        const double r = (sqrt(2.0) * sqrt(-pow((z - 1.0), 3.0)) + resonance * (z - 1)) / (resonance * (z - 1));
-        cf[0][v] = c; cf[1][v] = r;
-    }
+    for (int v = v_lo; v < v_hi; ++v) design_lores_one(b->hp[MXB_P_CUTOFF][v], b->hp[MXB_P_RESONANCE][v], sr, cf[0][v], cf[1][v]);
 }
-
-// maxiSVF::setParams, src/maximilian.h:1322-1334
 void design_svf(const mxb_bank* b, std::vector<double>* cf, const int v_lo, const int v_hi) {
     const double sr = (double)(size_t)b->ctx->sample_rate;
     for (int v = v_lo; v < v_hi; ++v) {
-        const double freq = b->hp[MXB_P_CUTOFF][v], res = b->hp[MXB_P_RESONANCE][v];
-        const double g = tan(3.1415926535897932384626433832795 * freq / sr);
-        const double damping = res == 0 ? 0 : 1.0 / res;
-        const double k = damping;
-        const double ginv = g / (1.0 + g * (g + k));
-        cf[0][v] = ginv; cf[1][v] = 2.0 * (g + k) * ginv; cf[2][v] = g * ginv; cf[3][v] = 2.0 * ginv; cf[4][v] = k;
+        double c[5];
+        design_svf_one(b->hp[MXB_P_CUTOFF][v], b->hp[MXB_P_RESONANCE][v], sr, c);
+        for (int i = 0; i < 5; ++i) cf[i][v] = c[i];
     }
 }
-
-// maxiBiquad::set, src/maximilian.h:1375-1479
 void design_biquad(const mxb_bank* b, std::vector<double>* cf, const int v_lo, const int v_hi) {
     const double sr = (double)(size_t)b->ctx->sample_rate;
-    const double SQRT2 = sqrt(2.0);
     for (int v = v_lo; v < v_hi; ++v) {
-        const double cutoff = b->hp[MXB_P_CUTOFF][v], Q = b->hp[MXB_P_RESONANCE][v], peakGain = b->hp[MXB_P_GAIN][v];
-        double norm = 0, a0 = 0, a1 = 0, a2 = 0, b1 = 0, b2 = 0;
-        const double G = pow(10.0, fabs(peakGain) / 20.0);
-        const double K = tan(3.1415926535897932384626433832795 * cutoff / sr);
-        switch (b->desc.biquad_type) {
-            case MXB_BQ_LOWPASS:
-                norm = 1.0 / (1.0 + K / Q + K * K);
-                a0 = K * K * norm; a1 = 2.0 * a0; a2 = a0;
-                b1 = 2.0 * (K * K - 1.0) * norm; b2 = (1.0 - K / Q + K * K) * norm; break;
-            case MXB_BQ_HIGHPASS:
-                norm = 1. / (1. + K / Q + K * K);
-                a0 = 1 * norm; a1 = -2 * a0; a2 = a0;
-                b1 = 2 * (K * K - 1) * norm; b2 = (1 - K / Q + K * K) * norm; break;
-            case MXB_BQ_BANDPASS:
-                norm = 1. / (1. + K / Q + K * K);
-                a0 = K / Q * norm; a1 = 0.; a2 = -a0;
-                b1 = 2. * (K * K - 1.) * norm; b2 = (1. - K / Q + K * K) * norm; break;
-            case MXB_BQ_NOTCH:
-                norm = 1. / (1. + K / Q + K * K);
-                a0 = (1. + K * K) * norm; a1 = 2. * (K * K - 1.) * norm; a2 = a0;
-                b1 = a1; b2 = (1. - K / Q + K * K) * norm; break;
-            case MXB_BQ_PEAK:
-                if (peakGain >= 0.0) {
-                    norm = 1. / (1. + 1. / Q * K + K * K);
-                    a0 = (1. + G / Q * K + K * K) * norm; a1 = 2. * (K * K - 1.) * norm;
-                    a2 = (1. - G / Q * K + K * K) * norm; b1 = a1; b2 = (1. - 1. / Q * K + K * K) * norm;
-                } else {
-                    norm = 1. / (1. + G / Q * K + K * K);
-                    a0 = (1. + 1 / Q * K + K * K) * norm; a1 = 2. * (K * K - 1) * norm;
-                    a2 = (1. - 1. / Q * K + K * K) * norm; b1 = a1; b2 = (1. - G / Q * K + K * K) * norm;
-                }
-                break;
-            case MXB_BQ_LOWSHELF:
-                if (peakGain >= 0.) {
-                    norm = 1. / (1. + SQRT2 * K + K * K);
-                    a0 = (1. + sqrt(2. * G) * K + G * K * K) * norm; a1 = 2. * (G * K * K - 1.) * norm;
-                    a2 = (1. - sqrt(2. * G) * K + G * K * K) * norm;
-                    b1 = 2. * (K * K - 1.) * norm; b2 = (1. - SQRT2 * K + K * K) * norm;
-                } else {
-                    norm = 1. / (1. + sqrt(2. * G) * K + G * K * K);
-                    a0 = (1. + SQRT2 * K + K * K) * norm; a1 = 2. * (K * K - 1.) * norm;
-                    a2 = (1. - SQRT2 * K + K * K) * norm;
-                    b1 = 2. * (G * K * K - 1.) * norm; b2 = (1. - sqrt(2. * G) * K + G * K * K) * norm;
-                }
-                break;
-            case MXB_BQ_HIGHSHELF:
-                if (peakGain >= 0.) {
-                    norm = 1. / (1. + SQRT2 * K + K * K);
-                    a0 = (G + sqrt(2. * G) * K + K * K) * norm; a1 = 2. * (K * K - G) * norm;
-                    a2 = (G - sqrt(2. * G) * K + K * K) * norm;
-                    b1 = 2. * (K * K - 1) * norm; b2 = (1. - SQRT2 * K + K * K) * norm;
-                } else {
-                    norm = 1. / (G + sqrt(2. * G) * K + K * K);
-                    a0 = (1. + SQRT2 * K + K * K) * norm; a1 = 2. * (K * K - 1.) * norm;
-                    a2 = (1. - SQRT2 * K + K * K) * norm;
-                    b1 = 2. * (K * K - G) * norm; b2 = (G - sqrt(2. * G) * K + K * K) * norm;
-                }
-                break;
-            default: break;
-        }
-        cf[0][v] = a0; cf[1][v] = a1; cf[2][v] = a2; cf[3][v] = b1; cf[4][v] = b2;
+        double c[5];
+        design_biquad_one(b->desc.biquad_type, b->hp[MXB_P_CUTOFF][v], b->hp[MXB_P_RESONANCE][v], b->hp[MXB_P_GAIN][v], sr, c);
+        for (int i = 0; i < 5; ++i) cf[i][v] = c[i];
     }
 }
 

@@ -63,4 +63,6 @@ struct mxb_ctx {
     int sample_rate;
     int sm_count;
     int cc_major, cc_minor;
+    double* d_sine;          // sineBuffer[514] ++ transition[1001] of the reference (mxb_ctx_set_tables), or NULL
+    double sine_before;
 };

@@ -1,0 +1,423 @@
+// K4s: the 1024-point streaming STFT (+ fused MFCC) kernel -- included by spectral.cu.
+//
+// Same arithmetic as stft_kernel<16> (the reference's float radix-2 transform replayed butterfly for butterfly, see the
+// head of spectral.cu), different schedule:
+//
+//   * one warp transforms TWO channels at once, frame f of channel 2k in the low half and of channel 2k+1 in the high
+//     half of packed f32x2 registers: every butterfly, untangle and power step is one FMUL2 / FADD2 / FFMA2 (sm_100
+//     packed fp32, per-half IEEE round-to-nearest) instead of two scalar instructions. ptxas contracts a packed mul
+//     feeding a packed add into one FFMA2 even for .rn operands, which would change the roundings; sums of products are
+//     therefore written fma(p, 1, q) / fma(q, -1, p) with the +-1 coming from kernel arguments (opaque to the optimiser):
+//     round(p*1 + q) is the separately rounded sum the reference computes.
+//   * a warp walks the consecutive frames of its channel pair (pair-major order): the n - hop samples two frames share
+//     are re-read from L1/L2, never from DRAM, and with several hops per call the assembly buffer (maxiFFT::buffer) is
+//     read and written once per call instead of once per frame.
+//   * frames are loaded straight from global memory in bit-reversed order (lane-contiguous float2 requests, 256 B per
+//     request), windowed and packed in registers -- no staging pass through shared memory.
+//   * the last radix-2 stage, the real-FFT untangling pass and the magnitudes run as ONE pass over shared memory: the
+//     lane that owns point p also owns 256 - p, so it holds all four inputs of bins p, 256 - p, 256 + p and 512 - p.
+//   * mel chains of both frames are spread over the lanes widest first (84 chains over 32 lanes in 3 passes); the DCT of
+//     the 8 frames a 4-warp group has in flight is one fp64 tensor-core row tile behind the group's own named barrier
+//     (one barrier per batch: the mel rows are double-buffered).
+#pragma once
+
+namespace {
+
+typedef unsigned long long u64;
+
+__device__ __forceinline__ u64 pk2(float lo, float hi) { u64 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void upk2(u64 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ u64 add2(u64 a, u64 b) { u64 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ u64 sub2(u64 a, u64 b) { u64 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ u64 mul2(u64 a, u64 b) { u64 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) { u64 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+
+struct Pk { u64 one, mone, half, mhalf; };        // (1,1) (-1,-1) (.5,.5) (-.5,-.5), from kernel arguments
+
+// fft.cpp:184-192 on two frames at once; w.x = (wx, wx), w.y = (wy, wy)
+__device__ __forceinline__ void butterfly2(u64& Rj, u64& Ij, u64& Rk, u64& Ik, const ulonglong2 w, const Pk& c) {
+    const u64 tr = fma2(mul2(w.y, Ik), c.mone, mul2(w.x, Rk));       // round(wx*Rk - wy*Ik), both products rounded first
+    const u64 ti = fma2(mul2(w.y, Rk), c.one, mul2(w.x, Ik));        // round(wx*Ik + wy*Rk)
+    Rk = sub2(Rj, tr);
+    Ik = sub2(Ij, ti);
+    Rj = add2(Rj, tr);
+    Ij = add2(Ij, ti);
+}
+
+// fft.cpp:256-272 for the pair (i, i3 = half - i) on two frames at once; w.x = (wr, wr), w.y = (wi, wi).
+// NEED3: also produce the i3 side (bins above half/2).
+template <bool NEED3>
+__device__ __forceinline__ void untangle2(u64& Ri, u64& Ii, u64& R3, u64& I3, const ulonglong2 w, const Pk& c) {
+    const u64 h1r = mul2(c.half, add2(Ri, R3));
+    const u64 h1i = mul2(c.half, sub2(Ii, I3));
+    const u64 h2r = mul2(c.half, add2(Ii, I3));
+    const u64 h2i = mul2(c.mhalf, sub2(Ri, R3));
+    const u64 a1 = mul2(w.x, h2r), a2 = mul2(w.y, h2i), a3 = mul2(w.x, h2i), a4 = mul2(w.y, h2r);
+    Ri = fma2(a2, c.mone, fma2(a1, c.one, h1r));                      // (h1r + a1) - a2
+    Ii = fma2(a4, c.one, fma2(a3, c.one, h1i));                       // (h1i + a3) + a4
+    if (NEED3) {
+        R3 = fma2(a2, c.one, fma2(a1, c.mone, h1r));                  // (h1r - a1) + a2
+        I3 = fma2(a4, c.one, fma2(h1i, c.mone, a3));                  // (-h1i + a3) + a4
+    }
+}
+
+constexpr int kStreamWarps = 8;                 // warps per CTA = channel pairs in flight per CTA (16 frames per DCT batch)
+constexpr int kStreamN = 1024, kStreamHalf = 512;
+__device__ __forceinline__ int psi16(int p) { return p + (p >> 4); }          // padded index of a 16-byte point record
+
+struct StreamSmem { size_t off_tw, off_uw, off_win, off_w, off_lo, off_mel, off_work, total; int melstride; };
+__host__ __device__ inline StreamSmem stream_smem_layout(int nw, int nf) {
+    StreamSmem L;
+    L.off_tw = 0;                                                          // float4[512]: (wx, wx, wy, wy) at (be - 1) + n
+    L.off_uw = L.off_tw + sizeof(float4) * 512;                            // float4[256]: (wr, wr, wi, wi)
+    L.off_win = L.off_uw + sizeof(float4) * 256;                           // float[1024]
+    L.off_w = align16(L.off_win + sizeof(float) * kStreamN);               // double[nw] band weights
+    L.off_lo = align16(L.off_w + sizeof(double) * (size_t)nw);             // int[3*nf]
+    L.melstride = (nf + 3) & ~3;
+    L.off_mel = align16(L.off_lo + sizeof(int) * (size_t)(3 * nf));        // double[2][16][melstride]
+    L.off_work = align16(L.off_mel + sizeof(double) * 2 * 2 * kStreamWarps * (size_t)L.melstride);
+    L.total = L.off_work + sizeof(ulonglong2) * (size_t)kStreamWarps * (kStreamHalf + kStreamHalf / 16);
+    return L;
+}
+
+struct StreamArgs {
+    StftArgs a;
+    const float4* tw4;        // [511] forward twiddles, natural (be - 1) + n order, halves duplicated
+    const float4* uw4;        // [256] untangle pairs, halves duplicated
+    Pk pk;
+};
+
+__device__ __forceinline__ constexpr int brev4c(int r) { return ((r & 1) << 3) | ((r & 2) << 1) | ((r & 4) >> 1) | ((r & 8) >> 3); }
+
+// sample i of one frame: i < split from the assembly buffer, else from the new samples
+__device__ __forceinline__ float frame_sample(const float* hp, const float* ip, long long stride_t, int split, int i) {
+    return i < split ? hp[i] : ip[(long long)i * stride_t];
+}
+
+// FULL = false: nothing but MFCCs leaves the kernel and the mel bank reads bins < 256 only: the upper-half outputs of the
+// untangling pass and their magnitudes are never formed.
+template <bool FULL>
+__global__ void __launch_bounds__(kStreamWarps * 32, 2) stft_stream_kernel(const StreamArgs sa) {
+    const StftArgs& a = sa.a;
+    extern __shared__ float4 smem4[];
+    unsigned char* sm = (unsigned char*)smem4;
+    constexpr int n = kStreamN, half = kStreamHalf;
+    const int nw = a.has_mfcc ? a.mf.nw : 0, nf = a.has_mfcc ? a.mf.filters : 0;
+    const StreamSmem L = stream_smem_layout(nw, nf);
+    ulonglong2* s_tw = (ulonglong2*)(sm + L.off_tw);
+    ulonglong2* s_uw = (ulonglong2*)(sm + L.off_uw);
+    float* s_win = (float*)(sm + L.off_win);
+    double* s_w = (double*)(sm + L.off_w);
+    int* s_lo = (int*)(sm + L.off_lo);
+    double* s_mel = (double*)(sm + L.off_mel);
+    const int melstride = L.melstride;
+    for (int i = threadIdx.x; i < half - 1; i += blockDim.x) ((float4*)s_tw)[i] = sa.tw4[i];
+    for (int i = threadIdx.x; i < half / 2; i += blockDim.x) ((float4*)s_uw)[i] = sa.uw4[i];
+    for (int i = threadIdx.x; i < n; i += blockDim.x) s_win[i] = a.window[i];
+    for (int i = threadIdx.x; i < nw; i += blockDim.x) s_w[i] = a.mf.w[i];
+    for (int i = threadIdx.x; i < nf; i += blockDim.x) { s_lo[i] = a.mf.lo[i]; s_lo[nf + i] = a.mf.cnt[i]; s_lo[2 * nf + i] = a.mf.off[i]; }
+    for (int i = threadIdx.x; i < 2 * 2 * kStreamWarps * melstride; i += blockDim.x) s_mel[i] = 0.0;     // K padding stays zero
+    __syncthreads();
+
+    const Pk pk = sa.pk;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int Lr = (int)(__brev((unsigned)lane) >> 27);          // bit-reversed lane: the frame samples this lane loads
+    const int low4 = lane & 15, b8 = lane >> 4;
+    ulonglong2* sW = (ulonglong2*)(sm + L.off_work) + (size_t)warp * (half + half / 16);
+    float* s_mag = (float*)sW;                                   // [2][512] magnitudes, after the spectrum has been consumed
+
+    const int C = a.C, frames = a.frames, hop = a.hop;
+    const int npairs = (C + 1) >> 1;
+    const int npb = (npairs + kStreamWarps - 1) / kStreamWarps;
+    const bool planar = a.stride_t == 1;
+    unsigned bc = 0;                                             // batches this CTA has run (mel row buffer = bc & 1)
+#pragma unroll 1
+    for (int pb = blockIdx.x; pb < npb; pb += gridDim.x) {
+        const int pair = pb * kStreamWarps + warp;
+        const int cA = 2 * pair, cB = cA + 1;
+        const bool vA = cA < C, vB = cB < C;
+        const int cBs = vB ? cB : cA;                            // a missing second channel re-reads the first (its results are dropped)
+#pragma unroll 1
+        for (int f = 0; f < frames; ++f, ++bc) {
+            double* melrow = s_mel + ((size_t)(bc & 1) * 2 * kStreamWarps + 2 * warp) * melstride;     // rows 2w (A), 2w + 1 (B)
+            if (vA) {
+                // ---- fft::calcFFT windowing (fft.cpp:499-505) + RealFFT even/odd packing (:238-241) + bit-reversed copy (:146-150):
+                // register r <- complex sample rev4(r)*32 + rev5(lane), i.e. real samples 64*rev4(r) + 2*Lr and the next one
+                const long long s0 = (long long)f * hop;
+                const long long sp = (long long)a.pos0 - s0;
+                const int split = sp < 0 ? 0 : (sp > n ? n : (int)sp);
+                const float* hpA = a.hist + (size_t)cA * n + s0;
+                const float* hpB = a.hist + (size_t)cBs * n + s0;
+                const float* ipA = a.in + (long long)cA * a.stride_c + (s0 - a.pos0) * a.stride_t;
+                const float* ipB = a.in + (long long)cBs * a.stride_c + (s0 - a.pos0) * a.stride_t;
+                u64 R[16], I[16];
+                // fast path: unit sample stride, 8-byte aligned rows, and a buffer/new-sample boundary on a multiple of 64 samples
+                // (then all lanes of a request read the same source: the steady state of a stream fed whole hops)
+                const bool vec = planar && (split & 63) == 0 &&
+                                 ((((uintptr_t)hpA) | ((uintptr_t)hpB) | ((uintptr_t)ipA) | ((uintptr_t)ipB)) & 7) == 0;
+                if (vec) {
+                    const float* wl = s_win + 2 * Lr;
+                    const float *hA = hpA + 2 * Lr, *hB = hpB + 2 * Lr, *iA = ipA + 2 * Lr, *iB = ipB + 2 * Lr;
+#pragma unroll
+                    for (int g = 0; g < 2; ++g) {          // two groups of eight requests per channel: 32 raw values in flight
+                        float2 xa[8], xb[8];
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) {
+                            const int r = 8 * g + k;
+                            const bool fromhist = 64 * brev4c(r) < split;      // warp-uniform
+                            xa[k] = *(const float2*)((fromhist ? hA : iA) + 64 * brev4c(r));
+                            xb[k] = *(const float2*)((fromhist ? hB : iB) + 64 * brev4c(r));
+                        }
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) {
+                            const int r = 8 * g + k;
+                            const float2 w = *(const float2*)(wl + 64 * brev4c(r));
+                            R[r] = pk2(__fmul_rn(xa[k].x, w.x), __fmul_rn(xb[k].x, w.x));
+                            I[r] = pk2(__fmul_rn(xa[k].y, w.y), __fmul_rn(xb[k].y, w.y));
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int r = 0; r < 16; ++r) {
+                        const int i = 64 * brev4c(r) + 2 * Lr;
+                        const float w0 = s_win[i], w1 = s_win[i + 1];
+                        R[r] = pk2(__fmul_rn(frame_sample(hpA, ipA, a.stride_t, split, i), w0), __fmul_rn(frame_sample(hpB, ipB, a.stride_t, split, i), w0));
+                        I[r] = pk2(__fmul_rn(frame_sample(hpA, ipA, a.stride_t, split, i + 1), w1), __fmul_rn(frame_sample(hpB, ipB, a.stride_t, split, i + 1), w1));
+                    }
+                }
+                if (planar && f + 2 < frames) {
+                    // the new samples of the frame after next, one 128-byte line per lane (16 lanes per channel = hop 512), into L2
+                    const float* pfa = (lane < 16 ? ipA : ipB) + 2 * hop + (n - hop) + (lane & 15) * 32;
+                    if ((lane & 15) * 32 < hop) asm volatile("prefetch.global.L2 [%0];" :: "l"(pfa));
+                }
+                // ---- FFT() stages with BlockEnd 1, 2, 4, 8: lane-local on 16 consecutive points ----
+                {
+                    int off = 0;
+#pragma unroll
+                    for (int be = 1; be < 16; be <<= 1) {
+#pragma unroll
+                        for (int blk = 0; blk < 16; blk += 2 * be)
+#pragma unroll
+                            for (int q = 0; q < be; ++q) butterfly2(R[blk + q], I[blk + q], R[blk + q + be], I[blk + q + be], s_tw[off + q], pk);
+                        off += be;
+                    }
+                }
+                // transpose: point lane*16 + r -> (lane >> 4)*256 + r*16 + (lane & 15)
+#pragma unroll
+                for (int r = 0; r < 16; ++r) sW[psi16(lane * 16 + r)] = make_ulonglong2(R[r], I[r]);
+                __syncwarp();
+#pragma unroll
+                for (int r = 0; r < 16; ++r) { const ulonglong2 v = sW[psi16(b8 * 256 + r * 16 + low4)]; R[r] = v.x; I[r] = v.y; }
+                __syncwarp();
+                // ---- stages with BlockEnd 16, 32, 64, 128: partner register r | m, twiddle n = (r & (m - 1))*16 + low4 ----
+#pragma unroll
+                for (int m = 1; m < 16; m <<= 1) {
+                    const ulonglong2* t = s_tw + (16 * m - 1) + low4;
+#pragma unroll
+                    for (int r = 0; r < 16; ++r) {
+                        if (r & m) continue;
+                        butterfly2(R[r], I[r], R[r | m], I[r | m], t[(r & (m - 1)) * 16], pk);
+                    }
+                }
+#pragma unroll
+                for (int r = 0; r < 16; ++r) sW[psi16(b8 * 256 + r * 16 + low4)] = make_ulonglong2(R[r], I[r]);
+                __syncwarp();
+                // ---- last stage (BlockEnd 256) + RealFFT untangling (fft.cpp:256-275) + cartToPol (:507-515), one pass ----
+                // item p: butterflies (p, p+256) and (256-p, 512-p) give X[p], X[p+256], X[256-p], X[512-p]: the inputs of
+                // untangle pairs (p, 512-p) and (256-p, 256+p). Lane 0's first item is the odd one out: butterflies (128, 384)
+                // and (0, 256), pair (128, 384), DC/Nyquist packing of bin 0, bin 256 left as it is (N/4 is never untangled).
+                const size_t oA = ((size_t)cA * a.max_frames + f) * half, oB = ((size_t)cBs * a.max_frames + f) * half;
+                float mg[4][4];                                  // [item][A bin1, B bin1, A bin3, B bin3] (+ FULL: written out directly)
+                // psi16(32*it + lane) = lane + (lane >> 4) + 34*it;  psi16(256 - 32*it - lane) = u + (u >> 4) + 238 - 34*it with u = 32 - lane
+                const int ia0 = lane + (lane >> 4), iq0 = (32 - lane) + ((32 - lane) >> 4) + 238;
+                float fgmA = 0.f, famA = 0.f, fxA = 0.f, fgmB = 0.f, famB = 0.f, fxB = 0.f;
+                const bool feat = FULL && (a.flatness != nullptr || a.centroid != nullptr);
+#pragma unroll
+                for (int it = 0; it < 4; ++it) {
+                    const int p = it * 32 + lane;
+                    const bool special = it == 0 && lane == 0;
+                    const int pa = special ? 128 : p, pq = special ? 0 : 256 - p;
+                    const int ia = (it == 0 && special) ? psi16(128) : ia0 + 34 * it, iq = (it == 0 && special) ? 0 : iq0 - 34 * it;
+                    ulonglong2 Aj = sW[ia], Ak = sW[ia + 272], Bj = sW[iq], Bk = sW[iq + 272];
+                    butterfly2(Aj.x, Aj.y, Ak.x, Ak.y, s_tw[255 + pa], pk);
+                    butterfly2(Bj.x, Bj.y, Bk.x, Bk.y, s_tw[255 + pq], pk);
+                    // pair 1: (i, i3) = (pa, special ? 384 : 512 - p); pair 2 (generic items only): (256 - p, 256 + p)
+                    u64 R3 = special ? Ak.x : Bk.x, I3 = special ? Ak.y : Bk.y;
+                    untangle2<FULL>(Aj.x, Aj.y, R3, I3, s_uw[pa], pk);
+                    u64 U2r = Bj.x, U2i = Bj.y, U23r = Ak.x, U23i = Ak.y;
+                    // MFCC-only: pair 2 feeds bin 256 - p alone; when no lane of this item row has it below the mel bank's last
+                    // bin the pair is skipped (lane 0's bin 0 is patched in below)
+                    const bool skip2 = !FULL && 225 - 32 * it >= a.mf.maxbin;
+                    if (!skip2) untangle2<FULL>(U2r, U2i, U23r, U23i, s_uw[special ? 1 : pq], pk);
+                    if (it == 0) {      // lane 0: bin 0 = (re + im, re - im) of X[0] (fft.cpp:274-275), bin 256 = X[256]
+                        const u64 dcr = add2(Bj.x, Bj.y), dci = sub2(Bj.x, Bj.y);
+                        U2r = special ? dcr : U2r; U2i = special ? dci : U2i;
+                        U23r = special ? Bk.x : U23r; U23i = special ? Bk.y : U23i;
+                    }
+                    // bins: b1 <- pair 1 i side, b2 <- pair 1 i3 side, b3 <- pair 2 i side, b4 <- pair 2 i3 side
+                    const int b1 = pa, b3 = pq;
+                    {
+                        float pA, pB;
+                        upk2(fma2(mul2(Aj.x, Aj.x), pk.one, mul2(Aj.y, Aj.y)), pA, pB);
+                        mg[it][0] = sqrtf(pA); mg[it][1] = sqrtf(pB);
+                        upk2(fma2(mul2(U2r, U2r), pk.one, mul2(U2i, U2i)), pA, pB);
+                        mg[it][2] = sqrtf(pA); mg[it][3] = sqrtf(pB);
+                    }
+                    if (FULL) {
+                        const int b2 = special ? 384 : 512 - p, b4 = special ? 256 : 256 + p;
+                        float m2A, m2B, m4A, m4B;
+                        {
+                            float pA, pB;
+                            upk2(fma2(mul2(R3, R3), pk.one, mul2(I3, I3)), pA, pB);
+                            m2A = sqrtf(pA); m2B = sqrtf(pB);
+                            upk2(fma2(mul2(U23r, U23r), pk.one, mul2(U23i, U23i)), pA, pB);
+                            m4A = sqrtf(pA); m4B = sqrtf(pB);
+                        }
+                        const int bb[4] = {b1, b2, b3, b4};
+                        const u64 re[4] = {Aj.x, R3, U2r, U23r}, im[4] = {Aj.y, I3, U2i, U23i};
+                        const float mA[4] = {mg[it][0], m2A, mg[it][2], m4A}, mB[4] = {mg[it][1], m2B, mg[it][3], m4B};
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            float reA, reB, imA, imB;
+                            upk2(re[k], reA, reB); upk2(im[k], imA, imB);
+                            const int b = bb[k];
+                            if (a.re) { a.re[oA + b] = reA; if (vB) a.re[oB + b] = reB; }
+                            if (a.im) { a.im[oA + b] = imA; if (vB) a.im[oB + b] = imB; }
+                            if (a.mags) { a.mags[oA + b] = mA[k]; if (vB) a.mags[oB + b] = mB[k]; }
+                            if (a.phases) { a.phases[oA + b] = atan2f(imA, reA); if (vB) a.phases[oB + b] = atan2f(imB, reB); }
+                            // fft::convToDB, src/libs/fft.cpp:526-534: float log10 of (mag + 1), scaled in double, stored as float
+                            if (a.mags_db) {
+                                a.mags_db[oA + b] = (double)mA[k] < 0.000001 ? 0.f : (float)(20.0 * (double)log10f(__fadd_rn(mA[k], 1.f)));
+                                if (vB) a.mags_db[oB + b] = (double)mB[k] < 0.000001 ? 0.f : (float)(20.0 * (double)log10f(__fadd_rn(mB[k], 1.f)));
+                            }
+                            if (feat) {     // maxiFFT::spectralFlatness / spectralCentroid, src/libs/maxiFFT.cpp:113-132 (lane-strided partial sums)
+                                if (mA[k] != 0.f) fgmA = __fadd_rn(fgmA, logf(mA[k]));
+                                famA = __fadd_rn(famA, mA[k]); fxA = __fadd_rn(fxA, __fmul_rn(fabsf(mA[k]), (float)b));
+                                if (mB[k] != 0.f) fgmB = __fadd_rn(fgmB, logf(mB[k]));
+                                famB = __fadd_rn(famB, mB[k]); fxB = __fadd_rn(fxB, __fmul_rn(fabsf(mB[k]), (float)b));
+                            }
+                        }
+                        // the mel stage may read any bin: all four magnitudes go to shared memory below
+                        mg[it][0] = mA[0]; mg[it][1] = mB[0]; mg[it][2] = mA[2]; mg[it][3] = mB[2];
+                        // (b2 / b4 magnitudes are parked in the untangle outputs' registers)
+                        Ak.x = pk2(m2A, m2B); Ak.y = pk2(m4A, m4B);
+                        // keep them for the write after the pass
+                        R[it] = Ak.x; I[it] = Ak.y;
+                    }
+                }
+                __syncwarp();                                    // every lane has read its points: the area becomes s_mag[2][512]
+#pragma unroll
+                for (int it = 0; it < 4; ++it) {
+                    const int p = it * 32 + lane;
+                    const bool special = it == 0 && lane == 0;
+                    const int b1 = special ? 128 : p, b3 = special ? 0 : 256 - p;
+                    s_mag[b1] = mg[it][0]; s_mag[half + b1] = mg[it][1];
+                    s_mag[b3] = mg[it][2]; s_mag[half + b3] = mg[it][3];
+                    if (FULL) {
+                        const int b2 = special ? 384 : 512 - p, b4 = special ? 256 : 256 + p;
+                        float x, y;
+                        upk2(R[it], x, y); s_mag[b2] = x; s_mag[half + b2] = y;
+                        upk2(I[it], x, y); s_mag[b4] = x; s_mag[half + b4] = y;
+                    }
+                }
+                if (feat) {
+#pragma unroll
+                    for (int m = 16; m >= 1; m >>= 1) {
+                        fgmA = __fadd_rn(fgmA, __shfl_xor_sync(0xffffffffu, fgmA, m)); famA = __fadd_rn(famA, __shfl_xor_sync(0xffffffffu, famA, m));
+                        fxA = __fadd_rn(fxA, __shfl_xor_sync(0xffffffffu, fxA, m));
+                        fgmB = __fadd_rn(fgmB, __shfl_xor_sync(0xffffffffu, fgmB, m)); famB = __fadd_rn(famB, __shfl_xor_sync(0xffffffffu, famB, m));
+                        fxB = __fadd_rn(fxB, __shfl_xor_sync(0xffffffffu, fxB, m));
+                    }
+                    if (lane == 0) {
+                        const size_t ofA = (size_t)cA * a.max_frames + f, ofB = (size_t)cBs * a.max_frames + f;
+                        if (a.flatness) {
+                            a.flatness[ofA] = (famA / (float)half) != 0.f ? expf(fgmA / (float)half) / (famA / (float)half) : 0.f;
+                            if (vB) a.flatness[ofB] = (famB / (float)half) != 0.f ? expf(fgmB / (float)half) / (famB / (float)half) : 0.f;
+                        }
+                        if (a.centroid) {
+                            a.centroid[ofA] = famA != 0.f ? __fmul_rn(fxA / famA, a.bin_hz) : 0.f;
+                            if (vB) a.centroid[ofB] = famB != 0.f ? __fmul_rn(fxB / famB, a.bin_hz) : 0.f;
+                        }
+                    }
+                }
+                __syncwarp();
+                // ---- mel stage of maxiMFCC::mfcc (maxiMFCC.cpp:48-66) for both frames: chain g = (filter nf-1-g/2, frame g&1),
+                // widest filters first, ascending-bin fp64 sums exactly like the reference's dense loop ----
+                if (a.has_mfcc) {
+                    for (int g0 = 0; g0 < 2 * nf; g0 += 32) {
+                        const int g = g0 + lane;
+                        const bool act = g < 2 * nf;
+                        const int fl = act ? nf - 1 - (g >> 1) : 0, fr = g & 1;
+                        const int cnt = act ? s_lo[nf + fl] : 0;
+                        const int maxc = __reduce_max_sync(0xffffffffu, cnt);     // warp-uniform trip count, predicated body
+                        const double* w = s_w + s_lo[2 * nf + fl];
+                        const float* mag = s_mag + fr * half + s_lo[fl];
+                        double acc = 0.0;
+#pragma unroll 4
+                        for (int q = 0; q < maxc; ++q)
+                            if (q < cnt) acc = __dadd_rn(acc, __dmul_rn(w[q], (double)mag[q]));
+                        if (act) melrow[fr * melstride + fl] = acc > 0.000001 ? log(__dmul_rn(acc, acc)) : 0.0;
+                    }
+                }
+                __syncwarp();
+            } else if (a.has_mfcc) {
+                for (int k = lane; k < 2 * melstride; k += 32) melrow[k] = 0.0;
+            }
+            if (a.has_mfcc) {
+                // ---- maxiMFCC::dct (maxiMFCC.h:98-111): the 8 frames of a 4-warp group are one row tile of a fp64 tensor-core
+                // contraction [8 x filters] . [filters x coeffs] (mma.sync m8n8k4, SASS DMMA); the group meets at its own named
+                // barrier once per batch (mel rows double-buffered), the column tiles are dealt over its 4 warps. The B
+                // fragments come pre-arranged per (tile, k-step, lane) from global memory (L1-resident, one coalesced request). ----
+                const int grp = warp >> 2, wg = warp & 3;
+                if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory");       // literal ids: a register id would reserve all 16 barriers
+                else asm volatile("bar.sync 2, 128;" ::: "memory");
+                const double* arow = s_mel + ((size_t)(bc & 1) * 2 * kStreamWarps + 8 * grp + (lane >> 2)) * melstride + (lane & 3);
+                const int ntiles = (a.mf.coeffs + 7) >> 3, ksteps = melstride >> 2;
+                const double ncf = (double)(unsigned)a.mf.coeffs;
+                for (int nt = wg; nt < ntiles; nt += 4) {
+                    const double* bfrag = a.mf.dctf + (size_t)nt * ksteps * 32 + lane;
+                    double c0 = 0.0, c1 = 0.0;
+#pragma unroll 4
+                    for (int ks = 0; ks < ksteps; ++ks) {
+                        const double av = arow[4 * ks];                                   // columns >= filters are zero
+                        const double bv = __ldg(bfrag + 32 * ks);
+                        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};\n"
+                                     : "+d"(c0), "+d"(c1) : "d"(av), "d"(bv));
+                    }
+                    const int fi = 8 * grp + (lane >> 2);        // frame of the CTA's batch: warp fi >> 1, channel A / B = fi & 1
+                    const int ch = 2 * (pb * kStreamWarps + (fi >> 1)) + (fi & 1);
+                    if (ch < C) {
+                        double* o = a.coeffs + ((size_t)ch * a.max_frames + f) * a.mf.coeffs;
+                        const int cc = nt * 8 + 2 * (lane & 3);
+                        if (cc < a.mf.coeffs) o[cc] = c0 / ncf;
+                        if (cc + 1 < a.mf.coeffs) o[cc + 1] = c1 / ncf;
+                    }
+                }
+            }
+        }
+        // ---- the channels' next assembly buffers: the unconsumed tail of (buffer ++ new samples), maxiFFT.cpp:85-87 applied
+        // `frames` times. It goes to the OTHER buffer (double-buffered across calls). ----
+        if (vA && a.newpos > 0) {
+            const long long consumed = (long long)frames * hop;
+#pragma unroll 1
+            for (int k = 0; k < 2; ++k) {
+                const int c = k ? cB : cA;
+                if (c >= C) break;
+                const float* hsrc = a.hist + (size_t)c * n;
+                const float* isrc = a.in + (long long)c * a.stride_c;
+                float* nx = a.next + (size_t)c * n;
+                const long long fromin = consumed - a.pos0;               // first new-sample index of the tail when none of it is history
+                if (planar && fromin >= 0 && (a.newpos & 3) == 0 && ((((uintptr_t)(isrc + fromin)) | ((uintptr_t)nx)) & 15) == 0) {
+                    for (int i = 4 * lane; i < a.newpos; i += 128) *(float4*)(nx + i) = *(const float4*)(isrc + fromin + i);
+                } else {
+                    for (int i = lane; i < a.newpos; i += 32) {
+                        const long long s = consumed + i;
+                        nx[i] = s < a.pos0 ? hsrc[s] : isrc[(s - a.pos0) * a.stride_t];
+                    }
+                }
+            }
+        }
+    }
+}
+
+}  // namespace

@@ -486,6 +486,456 @@ double mxo_env_attack_coeff(double attackMS, int32_t sr) { return 1 - pow(0.01, 
 double mxo_env_attack_ms_coeff(double attackMS, int32_t sr) { return 1.0 / (attackMS / 1000.0 * (double)(size_t)sr); }
 double mxo_env_decay_coeff(double ms, int32_t sr) { return pow(0.01, 1.0 / (ms * (double)(size_t)sr * 0.001)); }
 
+/* ================================================================= patches
+ * A patch is a per-voice signal graph: the body of a reference play() as a list of stages over 16 registers
+ * (oracle_api.h). Every stage body below restates one reference method; state lives in st[] slots per (stage, voice). */
+
+static double g_sine[514], g_transition[1001], g_sine_before = 0.0;
+static int g_tables_set = 0;
+
+/* sineBuffer / transition (src/maximilian.cpp:63, 67-200) are data of the reference: they are handed in at run time
+ * (from the compiled reference, or from tests/golden/tables.npz), never copied into this file. sine_before: the double
+ * sinebuf4 reads at sineBuffer[-1] on its wrap sample (an out-of-bounds read in the reference). */
+int32_t mxo_set_tables(const double* sine514, const double* transition1001, double sine_before) {
+    if (!sine514 || !transition1001) return -1;
+    memcpy(g_sine, sine514, sizeof(g_sine)); memcpy(g_transition, transition1001, sizeof(g_transition));
+    g_sine_before = sine_before; g_tables_set = 1;
+    return 0;
+}
+int32_t mxo_get_tables(double* sine514, double* transition1001, double* sine_before) {
+    if (!g_tables_set) return -1;
+    memcpy(sine514, g_sine, sizeof(g_sine)); memcpy(transition1001, g_transition, sizeof(g_transition));
+    *sine_before = g_sine_before;
+    return 0;
+}
+
+typedef struct { double startlevel, endlevel, currentlevel, gradient, curve; size_t length, counter; int hold; } eg_stage_t;
+
+typedef struct {
+    mxo_patch_desc d;
+    mxo_stage* stages;
+    double* consts;
+    int* sbase; int* ringof;
+    int n_state, n_rings;
+    double* params;   /* [n_params][V] */
+    double* state;    /* [n_state][V] */
+    double* rings;    /* [n_rings][V][taps] */
+    double reg[16];
+    eg_stage_t eg[16];
+} patch_t;
+
+static int p_state_slots(const mxo_stage* g) {
+    switch (g->op) {
+        case MXO_OP_OSC: return 2;
+        case MXO_OP_ENV_ADSR: case MXO_OP_ENV_AR: return 4;
+        case MXO_OP_ENVGEN: return 12;
+        case MXO_OP_FILTER: return 2;
+        case MXO_OP_SVF: return 3;
+        case MXO_OP_BIQUAD: return 2;
+        case MXO_OP_DCBLOCK: return 2;
+        case MXO_OP_DELAY: return 1;
+        case MXO_OP_FLANGER: return 3;
+        default: return 0;
+    }
+}
+
+void* mxo_patch_create(const mxo_patch_desc* d) {
+    if (!d || d->voices <= 0 || d->n_stages <= 0 || d->n_stages > 64 || !d->stages) return NULL;
+    patch_t* p = (patch_t*)calloc(1, sizeof(patch_t));
+    p->d = *d;
+    p->stages = (mxo_stage*)malloc(sizeof(mxo_stage) * (size_t)d->n_stages);
+    memcpy(p->stages, d->stages, sizeof(mxo_stage) * (size_t)d->n_stages);
+    p->consts = (double*)calloc(64, sizeof(double));
+    if (d->n_consts) memcpy(p->consts, d->consts, sizeof(double) * (size_t)d->n_consts);
+    p->sbase = (int*)calloc((size_t)d->n_stages, sizeof(int)); p->ringof = (int*)calloc((size_t)d->n_stages, sizeof(int));
+    for (int i = 0; i < d->n_stages; ++i) {
+        p->sbase[i] = p->n_state; p->n_state += p_state_slots(&p->stages[i]);
+        const int ring = p->stages[i].op == MXO_OP_DELAY || p->stages[i].op == MXO_OP_FLANGER;
+        p->ringof[i] = ring ? p->n_rings++ : -1;
+    }
+    const size_t V = (size_t)d->voices;
+    p->params = (double*)calloc((size_t)(d->n_params ? d->n_params : 1) * V, sizeof(double));
+    p->state = (double*)calloc((size_t)(p->n_state ? p->n_state : 1) * V, sizeof(double));
+    if (p->n_rings) p->rings = (double*)calloc((size_t)p->n_rings * V * (size_t)d->delay_taps, sizeof(double));
+    /* maxiTrigger: previousValue = 1, firstTrigger = 1 (src/maximilian.h:583-584) */
+    for (int i = 0; i < d->n_stages; ++i)
+        if (p->stages[i].op == MXO_OP_ENVGEN)
+            for (int k = 6; k < 12; ++k) for (size_t v = 0; v < V; ++v) p->state[(size_t)(p->sbase[i] + k) * V + v] = 1.0;
+    /* maxiEnvGen::setup / setupSegmentTime, src/maximilian.h:2371-2402, 2524-2538 */
+    {
+        double accumulatedTime = 0;
+        const double sr = (double)(size_t)d->sample_rate;
+        for (int i = 0; i < d->eg_stages && i < 16; ++i) {
+            eg_stage_t* s = &p->eg[i];
+            s->startlevel = d->eg_levels[i]; s->endlevel = d->eg_levels[i + 1];
+            const double stageTime = d->eg_times[i];
+            if (stageTime == MXO_ENVGEN_HOLD) { s->length = 0; s->hold = 1; s->gradient = 0; }
+            else {
+                double len = ((stageTime / 1000.0) * sr) + accumulatedTime;
+                s->length = (size_t)floor(len);
+                accumulatedTime = len - s->length;
+                s->gradient = 1.0 / s->length;
+                s->hold = 0;
+            }
+            s->curve = d->eg_curves[i]; s->counter = 0; s->currentlevel = 0;
+        }
+    }
+    return p;
+}
+
+void mxo_patch_destroy(void* h) {
+    patch_t* p = (patch_t*)h; if (!p) return;
+    free(p->stages); free(p->consts); free(p->sbase); free(p->ringof); free(p->params); free(p->state); free(p->rings); free(p);
+}
+
+int32_t mxo_patch_set_param(void* h, int32_t j, const double* x) {
+    patch_t* p = (patch_t*)h; if (!p || !x || j < 0 || j >= p->d.n_params) return -1;
+    memcpy(p->params + (size_t)j * (size_t)p->d.voices, x, sizeof(double) * (size_t)p->d.voices);
+    return 0;
+}
+int32_t mxo_patch_set_state(void* h, int32_t stage, int32_t slot, const double* x) {
+    patch_t* p = (patch_t*)h; if (!p || !x || stage < 0 || stage >= p->d.n_stages || slot < 0 || slot >= p_state_slots(&p->stages[stage])) return -1;
+    memcpy(p->state + (size_t)(p->sbase[stage] + slot) * (size_t)p->d.voices, x, sizeof(double) * (size_t)p->d.voices);
+    return 0;
+}
+int32_t mxo_patch_get_state(void* h, int32_t stage, int32_t slot, double* x) {
+    patch_t* p = (patch_t*)h; if (!p || !x || stage < 0 || stage >= p->d.n_stages || slot < 0 || slot >= p_state_slots(&p->stages[stage])) return -1;
+    memcpy(x, p->state + (size_t)(p->sbase[stage] + slot) * (size_t)p->d.voices, sizeof(double) * (size_t)p->d.voices);
+    return 0;
+}
+int32_t mxo_patch_get_ring(void* h, int32_t stage, int32_t v, double* dst, int32_t n) {
+    patch_t* p = (patch_t*)h;
+    if (!p || !dst || stage < 0 || stage >= p->d.n_stages || p->ringof[stage] < 0 || v < 0 || v >= p->d.voices || n < 0 || n > p->d.delay_taps) return -1;
+    memcpy(dst, p->rings + ((size_t)p->ringof[stage] * (size_t)p->d.voices + (size_t)v) * (size_t)p->d.delay_taps, sizeof(double) * (size_t)n);
+    return 0;
+}
+
+/* maxiOsc::sinebuf4 / sinebuf / sawn, src/maximilian.cpp:237-274, 342-359 */
+static double p_osc_table(int kind, double* phase_p, double* output_p, double frequency, double sr) {
+    double phase = *phase_p, output;
+    if (kind == MXO_OSC_SINEBUF4) {
+        double remainder, a, b, c, d, a1, a2, a3;
+        phase += 512. / (sr / (frequency));
+        if (phase >= 511) phase -= 512;
+        remainder = phase - floor(phase);
+        if (phase == 0) {
+            a = g_sine[(long)512]; b = g_sine[(long)phase]; c = g_sine[(long)phase + 1]; d = g_sine[(long)phase + 2];
+        } else {
+            a = ((long)phase - 1 < 0) ? g_sine_before : g_sine[(long)phase - 1];
+            b = g_sine[(long)phase]; c = g_sine[(long)phase + 1]; d = g_sine[(long)phase + 2];
+        }
+        a1 = 0.5f * (c - a);
+        a2 = a - 2.5 * b + 2.f * c - 0.5f * d;
+        a3 = 0.5f * (d - a) + 1.5f * (b - c);
+        output = (double)(((a3 * remainder + a2) * remainder + a1) * remainder + b);
+    } else if (kind == MXO_OSC_SINEBUF) {
+        double remainder;
+        phase += 512. / (sr / (frequency * 1.0f));          /* chandiv == 1, src/maximilian.cpp:53 */
+        if (phase >= 511) phase -= 512;
+        remainder = phase - floor(phase);
+        output = (double)((1 - remainder) * g_sine[1 + (long)phase] + remainder * g_sine[2 + (long)phase]);
+    } else {
+        if (phase >= 0.5) phase -= 1.0;
+        phase += (1. / (sr / (frequency)));
+        double temp = (8820.22 / frequency) * phase;
+        if (temp < -0.5) temp = -0.5;
+        if (temp > 0.5) temp = 0.5;
+        temp *= 1000.0f;
+        temp += 500.0f;
+        double remainder = temp - floor(temp);
+        /* transition[1 + (long)temp] is one past the table when temp == 1000; remainder is 0 there */
+        double t1 = (1 + (long)temp <= 1000) ? g_transition[1 + (long)temp] : 0.0;
+        output = (double)((1.0f - remainder) * g_transition[(long)temp] + remainder * t1) - phase;
+    }
+    *phase_p = phase; *output_p = output;
+    return output;
+}
+
+/* maxiEnv::adsr(input, attack, decay, sustain, release, holdtime, trigger), src/maximilian.cpp:1362-1413 (the same
+ * state machine as the member-parameter overload :1415-1466); st = amplitude, output, holdcount, flags */
+static double p_env_adsr(double* st, size_t V, double input, int trigger, double attack, double decay, double sustain, double release, long holdtime) {
+    double amplitude = st[0], output = st[V];
+    long holdcount = (long)st[2 * V];
+    int fl = (int)st[3 * V];
+    int attackphase = fl & 1, decayphase = (fl >> 1) & 1, sustainphase = (fl >> 2) & 1, holdphase = (fl >> 3) & 1, releasephase = (fl >> 4) & 1;
+    if (trigger == 1 && attackphase != 1 && holdphase != 1 && decayphase != 1) {
+        holdcount = 0; decayphase = 0; sustainphase = 0; releasephase = 0; attackphase = 1;
+    }
+    if (attackphase == 1) {
+        releasephase = 0;
+        amplitude += (1 * attack);
+        output = input * amplitude;
+        if (amplitude >= 1) { amplitude = 1; attackphase = 0; decayphase = 1; }
+    }
+    if (decayphase == 1) {
+        output = input * (amplitude *= decay);
+        if (amplitude <= sustain) { decayphase = 0; holdphase = 1; }
+    }
+    if (holdcount < holdtime && holdphase == 1) { output = input * amplitude; holdcount++; }
+    if (holdcount >= holdtime && trigger == 1) { output = input * amplitude; }
+    if (holdcount >= holdtime && trigger != 1) { holdphase = 0; releasephase = 1; }
+    if (releasephase == 1 && amplitude > 0.) { output = input * (amplitude *= release); }
+    st[0] = amplitude; st[V] = output; st[2 * V] = (double)holdcount;
+    st[3 * V] = (double)(attackphase | decayphase << 1 | sustainphase << 2 | holdphase << 3 | releasephase << 4);
+    return output;
+}
+
+/* maxiEnv::ar, src/maximilian.cpp:1319-1358 */
+static double p_env_ar(double* st, size_t V, double input, int trigger, double attack, double release, long holdtime) {
+    double amplitude = st[0], output = st[V];
+    long holdcount = (long)st[2 * V];
+    int fl = (int)st[3 * V];
+    int attackphase = fl & 1, decayphase = (fl >> 1) & 1, sustainphase = (fl >> 2) & 1, holdphase = (fl >> 3) & 1, releasephase = (fl >> 4) & 1;
+    if (trigger == 1 && attackphase != 1 && holdphase != 1) { holdcount = 0; releasephase = 0; attackphase = 1; }
+    if (attackphase == 1) { amplitude += (1 * attack); output = input * amplitude; }
+    if (amplitude >= 1) { amplitude = 1; attackphase = 0; holdphase = 1; }
+    if (holdcount < holdtime && holdphase == 1) { output = input; holdcount++; }
+    if (holdcount == holdtime && trigger == 1) { output = input; }
+    if (holdcount == holdtime && trigger != 1) { holdphase = 0; releasephase = 1; }
+    if (releasephase == 1 && amplitude > 0.) { output = input * (amplitude *= release); }
+    st[0] = amplitude; st[V] = output; st[2 * V] = (double)holdcount;
+    st[3 * V] = (double)(attackphase | decayphase << 1 | sustainphase << 2 | holdphase << 3 | releasephase << 4);
+    return output;
+}
+
+/* maxiTrigger::onZX, src/maximilian.h:564-585 */
+static double p_on_zx(double* previousValue, double* firstTrigger, double input) {
+    double isZX = 0.0;
+    if ((*previousValue <= 0.0 || *firstTrigger != 0.0) && input > 0) isZX = 1.0;
+    *previousValue = input; *firstTrigger = 0;
+    return isZX;
+}
+
+/* maxiEnvGen::play, src/maximilian.h:2276-2357; the per-stage counter / currentlevel of the reference are zero for every
+ * stage but the current one, so one pair per voice carries them */
+static double p_envgen(const patch_t* p, double* st, size_t V, double trigger) {
+    double envval = st[0]; size_t phase = (size_t)st[V]; int state = (int)st[2 * V]; int nxc = st[3 * V] != 0.0;
+    size_t counter = (size_t)st[4 * V]; double currentlevel = st[5 * V];
+    const size_t nst = (size_t)p->d.eg_stages;
+    int run = 1;
+#define P_RESET() do { counter = 0; currentlevel = 0; phase = 0; state = 1; } while (0)
+    if (state == 0) {
+        if (p_on_zx(&st[6 * V], &st[7 * V], trigger)) { if (nst > 0) { state = 1; nxc = 0; } else run = 0; }
+        else run = 0;
+    }
+    if (run && state == 1) {
+        const eg_stage_t* cs = &p->eg[phase < nst ? phase : 0];
+        if (p_on_zx(&st[8 * V], &st[9 * V], -trigger)) nxc = 1;
+        if (cs->hold) state = 2;
+        else {
+            double val = pow(currentlevel, cs->curve);
+            val = fmax(fmin(val, 1.0), 0.0);                         /* maxiMap::linlin, src/maximilian.h:801-805 */
+            envval = ((val - 0.0) / (1.0 - 0.0) * (cs->endlevel - cs->startlevel)) + cs->startlevel;
+            counter++;
+            if (counter == cs->length) { counter = 0; currentlevel = 0; phase++; }
+            else currentlevel += cs->gradient;
+            if (p->d.eg_retrigger) { if (p_on_zx(&st[10 * V], &st[11 * V], trigger)) { nxc = 0; P_RESET(); } }
+            run = 0;
+        }
+    }
+    if (run && state == 2) {
+        if (p_on_zx(&st[8 * V], &st[9 * V], -trigger)) nxc = 1;
+        if (nxc) { state = 1; phase++; }
+        if (p->d.eg_retrigger) { if (p_on_zx(&st[10 * V], &st[11 * V], trigger)) { nxc = 0; P_RESET(); } }
+    }
+    if (phase == nst) { P_RESET(); if (!p->d.eg_loop) state = 0; }
+#undef P_RESET
+    st[0] = envval; st[V] = (double)phase; st[2 * V] = (double)state; st[3 * V] = nxc ? 1.0 : 0.0; st[4 * V] = (double)counter; st[5 * V] = currentlevel;
+    return envval;
+}
+
+/* maxiBiquad::set for one voice (the expressions of biquad_set above, src/maximilian.h:1375-1479) */
+static void p_biquad_set(int type, double cutoff, double Q, double peakGain, double sr, double* cf) {
+    bank_t b; double c0, c1, c2, c3, c4; double pc = cutoff, pq = Q, pg = peakGain;
+    memset(&b, 0, sizeof(b));
+    b.chain.sample_rate = (int32_t)sr; b.chain.biquad_type = type;
+    b.p[MXO_P_CUTOFF] = &pc; b.p[MXO_P_RESONANCE] = &pq; b.p[MXO_P_GAIN] = &pg;
+    b.cf[0] = &c0; b.cf[1] = &c1; b.cf[2] = &c2; b.cf[3] = &c3; b.cf[4] = &c4;
+    biquad_set(&b, 0);
+    cf[0] = c0; cf[1] = c1; cf[2] = c2; cf[3] = c3; cf[4] = c4;
+}
+
+int32_t mxo_patch_process(void* h, int32_t nframes, const double* const* inputs, double* out, double* mix) {
+    patch_t* p = (patch_t*)h;
+    if (!p || nframes < 0) return -1;
+    const size_t V = (size_t)p->d.voices;
+    const double sr = (double)(size_t)p->d.sample_rate;
+    const int taps = p->d.delay_taps;
+    for (int t = 0; t < nframes; ++t) {
+        double m0 = 0.0, m1 = 0.0;
+        for (size_t v = 0; v < V; ++v) {
+            double* reg = p->reg;
+            for (int i = 0; i < 16; ++i) reg[i] = 0.0;          /* registers read 0 until a stage of this sample writes them */
+#define FETCH(s) ((s) < 0 ? 0.0 : ((s) >> 8) == 0 ? reg[(s) & 0xff] : ((s) >> 8) == 1 ? p->params[(size_t)((s) & 0xff) * V + v] : \
+                  ((s) >> 8) == 2 ? p->consts[(s) & 0xff] : inputs[(s) & 0xff][(size_t)t * V + v])
+            for (int si = 0; si < p->d.n_stages; ++si) {
+                const mxo_stage* g = &p->stages[si];
+                double* st = p->state + (size_t)p->sbase[si] * V + v;      /* slot k at st[k * V] */
+                double y = 0.0;
+                switch (g->op) {
+                    case MXO_OP_OSC: {
+                        const double f = FETCH(g->src[0]);
+                        if (g->kind >= MXO_OSC_SINEBUF) y = p_osc_table(g->kind, &st[0], &st[V], f, sr);
+                        else y = osc_tick(g->kind, &st[0], &st[V], f, FETCH(g->src[1]), sr, FETCH(g->src[1]), FETCH(g->src[2]));
+                        break;
+                    }
+                    case MXO_OP_ENV_ADSR:
+                        y = p_env_adsr(st, V, FETCH(g->src[0]), (int)FETCH(g->src[1]), FETCH(g->src[2]), FETCH(g->src[3]), FETCH(g->src[4]),
+                                       FETCH(g->src[5]), (long)FETCH(g->src[6]));
+                        break;
+                    case MXO_OP_ENV_AR:
+                        y = p_env_ar(st, V, FETCH(g->src[0]), (int)FETCH(g->src[1]), FETCH(g->src[2]), FETCH(g->src[3]), (long)FETCH(g->src[4]));
+                        break;
+                    case MXO_OP_ENVGEN: y = p_envgen(p, st, V, FETCH(g->src[0])); break;
+                    case MXO_OP_FILTER: {
+                        const double input = FETCH(g->src[0]);
+                        if (g->kind == MXO_FILT_LORES || g->kind == MXO_FILT_HIRES) {
+                            /* maxiFilter::lores / hires, src/maximilian.cpp:455-468 / 471-484 */
+                            double cutoff = FETCH(g->src[1]), resonance = FETCH(g->src[2]);
+                            double fx = st[0], fy = st[V];
+                            if (cutoff < 10) cutoff = 10;
+                            if (cutoff > sr) cutoff = sr;
+                            if (resonance < 1.) resonance = 1.;
+                            double z = cos(MAXI_TWOPI * cutoff / sr);
+                            double cc = 2 - 2 * z;
+                            double r = (sqrt(2.0) * sqrt(-pow((z - 1.0), 3.0)) + resonance * (z - 1)) / (resonance * (z - 1));
+                            fx = fx + (input - fy) * cc;
+                            fy = fy + fx;
+                            fx = fx * r;
+                            st[0] = fx; st[V] = fy;
+                            y = g->kind == MXO_FILT_LORES ? fy : input - fy;
+                        } else if (g->kind == MXO_FILT_LOPASS) {       /* src/maximilian.cpp:442-446 (outputs[0] defined as 0 initially) */
+                            const double cutoff = FETCH(g->src[1]);
+                            y = st[0] + cutoff * (input - st[0]);
+                            st[0] = y;
+                        } else if (g->kind == MXO_FILT_HIPASS) {       /* :449-453 */
+                            const double cutoff = FETCH(g->src[1]);
+                            y = input - (st[0] + cutoff * (input - st[0]));
+                            st[0] = y;
+                        } else {                                        /* bandpass, :487-500 */
+                            double cutoff = FETCH(g->src[1]), resonance = FETCH(g->src[2]);
+                            if (cutoff > (sr * 0.5)) cutoff = (sr * 0.5);
+                            if (resonance >= 1.) resonance = 0.999999;
+                            double z = cos(MAXI_TWOPI * cutoff / sr);
+                            double i0 = (1 - resonance) * (sqrt(resonance * (resonance - 4.0 * pow(z, 2.0) + 2.0) + 1));
+                            double i1 = 2 * z * resonance;
+                            double i2 = pow((resonance * -1), 2);
+                            y = i0 * input + i1 * st[0] + i2 * st[V];
+                            st[V] = st[0];
+                            st[0] = y;
+                        }
+                        break;
+                    }
+                    case MXO_OP_SVF: {
+                        /* maxiSVF::setCutoff + setResonance (setParams, src/maximilian.h:1322-1334) then play (:1305-1319) */
+                        const double w = FETCH(g->src[0]), freq = FETCH(g->src[1]), res = FETCH(g->src[2]);
+                        const double gg = tan(MAXI_PI * freq / sr);
+                        const double k = res == 0 ? 0 : 1.0 / res;
+                        const double ginv = gg / (1.0 + gg * (gg + k));
+                        const double g1 = ginv, g2 = 2.0 * (gg + k) * ginv, g3 = gg * ginv, g4 = 2.0 * ginv;
+                        double v0z = st[0], v1 = st[V], v2 = st[2 * V];
+                        double v1z = v1, v2z = v2;
+                        double v3 = w + v0z - 2.0 * v2z;
+                        v1 += g1 * v3 - g2 * v1z;
+                        v2 += g3 * v3 + g4 * v1z;
+                        v0z = w;
+                        const double low = v2, band = v1, high = w - k * v1 - v2, notch = w - k * v1;
+                        st[0] = v0z; st[V] = v1; st[2 * V] = v2;
+                        y = (low * FETCH(g->src[3])) + (band * FETCH(g->src[4])) + (high * FETCH(g->src[5])) + (notch * FETCH(g->src[6]));
+                        break;
+                    }
+                    case MXO_OP_BIQUAD: {
+                        double cf[5];
+                        p_biquad_set(g->kind, FETCH(g->src[1]), FETCH(g->src[2]), FETCH(g->src[3]), sr, cf);
+                        const double x = FETCH(g->src[0]);
+                        double v1 = st[0], v2 = st[V];
+                        double v0 = x - (cf[3] * v1) - (cf[4] * v2);
+                        y = (cf[0] * v0) + (cf[1] * v1) + (cf[2] * v2);
+                        st[V] = v1; st[0] = v0;
+                        break;
+                    }
+                    case MXO_OP_DCBLOCK: {          /* maxiDCBlocker::play, src/maximilian.h:1261-1266 */
+                        const double input = FETCH(g->src[0]), R = FETCH(g->src[1]);
+                        double ym1 = input - st[0] + R * st[V];
+                        st[V] = ym1; st[0] = input;
+                        y = ym1;
+                        break;
+                    }
+                    case MXO_OP_NONLIN: {           /* maxiNonlinearity, src/maximilian.h:1076-1137 */
+                        double x = FETCH(g->src[0]);
+                        const double p1 = FETCH(g->src[1]), p2 = FETCH(g->src[2]);
+                        switch (g->kind) {
+                            case MXO_NL_ATANDIST: x = (1.0 / atan(p1)) * atan(x * p1); break;
+                            case MXO_NL_FASTATANDIST: x = (1.0 / (p1 / (1.0 + 0.28 * (p1 * p1)))) * ((x * p1) / (1.0 + 0.28 * ((x * p1) * (x * p1)))); break;
+                            case MXO_NL_SOFTCLIP: if (x >= 1) x = 1; else if (x <= -1) x = -1; else x = (2 / 3.0) * (x - pow(x, 3) / 3.0); break;
+                            case MXO_NL_HARDCLIP: x = x >= 1 ? 1 : (x <= -1 ? -1 : x); break;
+                            case MXO_NL_ASYMCLIP: if (x >= 1) x = 1; else if (x <= -1) x = -1; else if (x < 0) x = -(pow(-x, p1)); else x = pow(x, p2); break;
+                            default: x = (x / (1.0 + 0.28 * (x * x))); break;
+                        }
+                        y = x;
+                        break;
+                    }
+                    case MXO_OP_DELAY:
+                    case MXO_OP_FLANGER: {
+                        double* memory = p->rings + ((size_t)p->ringof[si] * V + v) * (size_t)taps;
+                        const double input = FETCH(g->src[0]);
+                        int size; double feedback;
+                        if (g->op == MXO_OP_DELAY) { size = (int)FETCH(g->src[1]); feedback = FETCH(g->src[2]); }
+                        else {
+                            /* maxiFlanger::flange, src/maximilian.h:1167-1175 */
+                            const unsigned int delay = (unsigned int)FETCH(g->src[1]);
+                            feedback = FETCH(g->src[2]);
+                            const double speed = FETCH(g->src[3]), depth = FETCH(g->src[4]);
+                            double lfoVal = osc_tick(MXO_OSC_TRIANGLE, &st[V], &st[2 * V], speed, 0.0, sr, 0.0, 0.0);
+                            size = (int)(delay + (lfoVal * depth * delay) + 1);
+                        }
+                        int phase = (int)st[0];
+                        if (phase >= size) phase = 0;                     /* maxiDelayline::dl, src/maximilian.cpp:420-429 */
+                        if (phase < 0 || phase >= taps) return -4;
+                        double output;
+                        if (g->op == MXO_OP_DELAY && g->kind == 1) {      /* dlFromPosition, :431-439 */
+                            int position = (int)FETCH(g->src[3]);
+                            if (position >= size) position = 0;
+                            if (position < 0 || position >= taps) return -4;
+                            output = memory[position];
+                            memory[phase] = (memory[phase] * feedback) + (input * feedback) * 1.0f;
+                        } else {
+                            output = memory[phase];
+                            memory[phase] = (memory[phase] * feedback) + (input * feedback) * 0.5;
+                        }
+                        phase += 1;
+                        st[0] = (double)phase;
+                        if (g->op == MXO_OP_FLANGER) {
+                            double normalise = (1 - fabs(output));
+                            output *= normalise;
+                            y = (output + input) / 2.0;
+                        } else y = output;
+                        break;
+                    }
+                    case MXO_OP_ADD: y = FETCH(g->src[0]) + FETCH(g->src[1]); break;
+                    case MXO_OP_SUB: y = FETCH(g->src[0]) - FETCH(g->src[1]); break;
+                    case MXO_OP_MUL: y = FETCH(g->src[0]) * FETCH(g->src[1]); break;
+                    case MXO_OP_DIV: y = FETCH(g->src[0]) / FETCH(g->src[1]); break;
+                    case MXO_OP_MIX_STEREO: {       /* maxiMix::stereo, src/maximilian.cpp:503-509 */
+                        const double in = FETCH(g->src[0]);
+                        double x = FETCH(g->src[1]);
+                        if (x > 1) x = 1;
+                        if (x < 0) x = 0;
+                        m0 += in * sqrt(1.0 - x); m1 += in * sqrt(x);
+                        break;
+                    }
+                    case MXO_OP_OUT: if (out) out[(size_t)t * V + v] = FETCH(g->src[0]); break;
+                    default: return -2;
+                }
+                if (g->dst >= 0) reg[g->dst] = y;
+            }
+#undef FETCH
+        }
+        if (mix) { mix[2 * t] = m0; mix[2 * t + 1] = m1; }
+    }
+    return 0;
+}
+
 /* ==================================================================== FFT */
 
 /* ReverseBits, src/libs/fft.cpp:75-85 (the lazily built gFFTBitTable, :87-112, holds the same values) */

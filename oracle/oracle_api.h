@@ -143,6 +143,34 @@ void*   mxo_istft_create(int32_t channels, int32_t fft_size, int32_t hop_size);
 void    mxo_istft_destroy(void* st);
 int32_t mxo_istft_process(void* st, const float* mags, const float* phases, int32_t frames, float* out);
 
+/* ---- voice patches: the stage lists of include/maxib200.h (mxb_stage / mxb_patch_desc), same codes, run on the CPU ---- */
+enum { MXO_OSC_SINEBUF = 9, MXO_OSC_SINEBUF4 = 10, MXO_OSC_SAWN = 11 };                 /* src/maximilian.cpp:266-274, 237-264, 342-359 */
+enum { MXO_FILT_LOPASS = 5, MXO_FILT_HIPASS = 6, MXO_FILT_BANDPASS = 7 };                /* src/maximilian.cpp:442-453, 487-500 */
+enum { MXO_NL_ATANDIST = 0, MXO_NL_FASTATANDIST, MXO_NL_SOFTCLIP, MXO_NL_HARDCLIP, MXO_NL_ASYMCLIP, MXO_NL_FASTATAN };   /* src/maximilian.h:1046-1137 */
+#define MXO_ENVGEN_HOLD (-46692.0)                                                       /* maxiEnvGen::HOLD, src/maximilian.h:2271 */
+enum { MXO_OP_OSC = 1, MXO_OP_ENV_ADSR, MXO_OP_ENV_AR, MXO_OP_ENVGEN, MXO_OP_FILTER, MXO_OP_SVF, MXO_OP_BIQUAD, MXO_OP_DCBLOCK, MXO_OP_NONLIN,
+       MXO_OP_DELAY, MXO_OP_FLANGER, MXO_OP_ADD, MXO_OP_SUB, MXO_OP_MUL, MXO_OP_DIV, MXO_OP_MIX_STEREO, MXO_OP_OUT };
+typedef struct { int32_t op, kind, dst, reserved; int32_t src[8]; } mxo_stage;      /* operands: 0..15 register, 0x100+j parameter, 0x200+k constant, 0x300+m input, -1 none */
+typedef struct {
+    int32_t voices, n_stages, n_params, n_consts, n_inputs, sample_rate;
+    int32_t delay_taps;
+    int32_t eg_stages, eg_loop, eg_retrigger;
+    const mxo_stage* stages;
+    const double* consts;
+    const double *eg_levels, *eg_times, *eg_curves;
+} mxo_patch_desc;
+/* sineBuffer[514] / transition[1001] of the reference (src/maximilian.cpp:63, 67-200) and the double before sineBuffer[0] that
+ * sinebuf4 reads on its wrap sample. The compiled reference returns its own; the port is handed them (mxo_set_tables). */
+int32_t mxo_set_tables(const double* sine514, const double* transition1001, double sine_before);
+int32_t mxo_get_tables(double* sine514, double* transition1001, double* sine_before);
+void*   mxo_patch_create(const mxo_patch_desc* desc);
+void    mxo_patch_destroy(void* patch);
+int32_t mxo_patch_set_param(void* patch, int32_t j, const double* values);
+int32_t mxo_patch_set_state(void* patch, int32_t stage, int32_t slot, const double* values);
+int32_t mxo_patch_get_state(void* patch, int32_t stage, int32_t slot, double* values);
+int32_t mxo_patch_get_ring(void* patch, int32_t stage, int32_t voice, double* dst, int32_t n);
+int32_t mxo_patch_process(void* patch, int32_t nframes, const double* const* inputs, double* out, double* mix);
+
 /* "reference" or "port" */
 const char* mxo_kind(void);
 

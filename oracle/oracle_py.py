@@ -333,3 +333,119 @@ class Istft:
         if rc:
             raise RuntimeError(f"mxo_istft_process -> {rc}")
         return out
+
+
+# ------------------------------------------------------------------------------------------------ voice patches
+
+class MxoStage(C.Structure):
+    _fields_ = [("op", C.c_int32), ("kind", C.c_int32), ("dst", C.c_int32), ("reserved", C.c_int32), ("src", C.c_int32 * 8)]
+
+
+class MxoPatchDesc(C.Structure):
+    _fields_ = [("voices", C.c_int32), ("n_stages", C.c_int32), ("n_params", C.c_int32), ("n_consts", C.c_int32), ("n_inputs", C.c_int32),
+                ("sample_rate", C.c_int32), ("delay_taps", C.c_int32), ("eg_stages", C.c_int32), ("eg_loop", C.c_int32), ("eg_retrigger", C.c_int32),
+                ("stages", C.POINTER(MxoStage)), ("consts", C.POINTER(C.c_double)),
+                ("eg_levels", C.POINTER(C.c_double)), ("eg_times", C.POINTER(C.c_double)), ("eg_curves", C.POINTER(C.c_double))]
+
+
+def _patch_sigs(lib):
+    if getattr(lib, "_patch_sigs_done", False):
+        return
+    dp, vp, i32 = C.POINTER(C.c_double), C.c_void_p, C.c_int32
+    lib.mxo_set_tables.restype, lib.mxo_set_tables.argtypes = i32, [dp, dp, C.c_double]
+    lib.mxo_get_tables.restype, lib.mxo_get_tables.argtypes = i32, [dp, dp, dp]
+    lib.mxo_patch_create.restype, lib.mxo_patch_create.argtypes = vp, [C.POINTER(MxoPatchDesc)]
+    lib.mxo_patch_destroy.restype, lib.mxo_patch_destroy.argtypes = None, [vp]
+    lib.mxo_patch_set_param.restype, lib.mxo_patch_set_param.argtypes = i32, [vp, i32, dp]
+    lib.mxo_patch_set_state.restype, lib.mxo_patch_set_state.argtypes = i32, [vp, i32, i32, dp]
+    lib.mxo_patch_get_state.restype, lib.mxo_patch_get_state.argtypes = i32, [vp, i32, i32, dp]
+    lib.mxo_patch_get_ring.restype, lib.mxo_patch_get_ring.argtypes = i32, [vp, i32, i32, dp, i32]
+    lib.mxo_patch_process.restype, lib.mxo_patch_process.argtypes = i32, [vp, i32, C.POINTER(C.c_void_p), dp, dp]
+    lib._patch_sigs_done = True
+
+
+def get_tables(kind="reference"):
+    """(sineBuffer[514], transition[1001], sine_before) as the library `kind` holds them (the compiled reference: its own)."""
+    lib = load(kind); _patch_sigs(lib)
+    s = np.empty(514); t = np.empty(1001); b = C.c_double(0.0)
+    rc = lib.mxo_get_tables(_dp(s), _dp(t), C.byref(b))
+    if rc:
+        raise RuntimeError(f"mxo_get_tables -> {rc}")
+    return s, t, b.value
+
+
+def set_tables(sine514, transition1001, sine_before, kind="port"):
+    lib = load(kind); _patch_sigs(lib)
+    s = np.ascontiguousarray(sine514, dtype=np.float64); t = np.ascontiguousarray(transition1001, dtype=np.float64)
+    rc = lib.mxo_set_tables(_dp(s), _dp(t), float(sine_before))
+    if rc:
+        raise RuntimeError(f"mxo_set_tables -> {rc}")
+
+
+class Patch:
+    """A maximilian_b200.patchdef.PatchDef on the CPU (kind: 'port' = maxi_oracle.c, 'reference' = the reference's own objects)."""
+
+    def __init__(self, defn, voices, sample_rate=48000, delay_taps=0, kind="port", **_):
+        self.lib = load(kind); _patch_sigs(self.lib)
+        self.defn, self.V = defn, int(voices)
+        st = (MxoStage * len(defn.stages))()
+        for i, (op, k, dst, src) in enumerate(defn.stages):
+            st[i].op, st[i].kind, st[i].dst, st[i].reserved = op, k, dst, 0
+            for j in range(8):
+                st[i].src[j] = src[j]
+        consts = (C.c_double * max(1, len(defn.consts)))(*defn.consts)
+        eg = defn.eg or ([0.0], [], [], False, False)
+        lv = (C.c_double * max(1, len(eg[0])))(*eg[0]); tm = (C.c_double * max(1, len(eg[1])))(*eg[1]); cv = (C.c_double * max(1, len(eg[2])))(*eg[2])
+        d = MxoPatchDesc(self.V, len(defn.stages), len(defn.params), len(defn.consts), len(defn.inputs), sample_rate, int(delay_taps),
+                         len(eg[1]), int(eg[3]), int(eg[4]), st, consts, lv, tm, cv)
+        self._keep = (st, consts, lv, tm, cv)
+        self.h = self.lib.mxo_patch_create(C.byref(d))
+        if not self.h:
+            raise RuntimeError("mxo_patch_create failed")
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.lib.mxo_patch_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def set(self, name, values):
+        a = np.ascontiguousarray(np.broadcast_to(np.asarray(values, dtype=np.float64), (self.V,)))
+        rc = self.lib.mxo_patch_set_param(self.h, self.defn.params.index(name), _dp(a))
+        if rc:
+            raise RuntimeError(f"mxo_patch_set_param({name}) -> {rc}")
+
+    def get_state(self, stage, slot):
+        a = np.empty(self.V, dtype=np.float64)
+        rc = self.lib.mxo_patch_get_state(self.h, stage, slot, _dp(a))
+        if rc:
+            raise RuntimeError(f"mxo_patch_get_state -> {rc}")
+        return a
+
+    def set_state(self, stage, slot, values):
+        a = np.ascontiguousarray(np.broadcast_to(np.asarray(values, dtype=np.float64), (self.V,)))
+        rc = self.lib.mxo_patch_set_state(self.h, stage, slot, _dp(a))
+        if rc:
+            raise RuntimeError(f"mxo_patch_set_state -> {rc}")
+
+    def ring(self, stage, v, n):
+        a = np.empty(n, dtype=np.float64)
+        rc = self.lib.mxo_patch_get_ring(self.h, stage, v, _dp(a), n)
+        if rc:
+            raise RuntimeError(f"mxo_patch_get_ring -> {rc}")
+        return a
+
+    def process(self, nframes, inputs=None, want_out=True, want_mix=False):
+        inputs = inputs or {}
+        arrs = [np.ascontiguousarray(inputs[n], dtype=np.float64) for n in self.defn.inputs]
+        for a in arrs:
+            assert a.shape == (nframes, self.V)
+        ptrs = (C.c_void_p * max(1, len(arrs)))(*[a.ctypes.data for a in arrs])
+        out = np.empty((nframes, self.V), dtype=np.float64) if want_out else None
+        mix = np.empty((nframes, 2), dtype=np.float64) if want_mix else None
+        rc = self.lib.mxo_patch_process(self.h, nframes, ptrs, _dp(out), _dp(mix))
+        if rc:
+            raise RuntimeError(f"mxo_patch_process -> {rc}")
+        return out, mix

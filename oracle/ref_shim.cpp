@@ -33,6 +33,9 @@
 
 #include "oracle_api.h"
 
+extern double sineBuffer[514];      /* src/maximilian.cpp:63 (external linkage there, not declared in the header) */
+extern double transition[1001];     /* src/maximilian.cpp:67 */
+
 namespace {
 
 struct RefVoice {
@@ -381,6 +384,264 @@ int32_t mxo_istft_process(void* h, const float* mags, const float* phases, int32
             for (int t = 0; t < s->hop; ++t)
                 out[(size_t)c * frames * s->hop + (size_t)f * s->hop + t] = s->f[c]->process(s->mg, s->ph, maxiIFFT::SPECTRUM);
         }
+    }
+    return 0;
+}
+
+}  // extern "C"
+
+/* ------------------------------------------------------------------ patches
+ * The same stage list as the port's interpreter (oracle_api.h), every stage being a call of the reference method on a
+ * reference object that lives in zero-filled storage, one object per (stage, voice). No DSP of its own. */
+namespace {
+
+struct RefStageObj {
+    maxiOsc osc; maxiEnv env; maxiFilter filt; maxiSVF svf; maxiBiquad bq; maxiDCBlocker dc; maxiNonlinearity nl; maxiMix mixer;
+};
+
+struct RefPatch {
+    mxo_patch_desc d;
+    std::vector<mxo_stage> stages;
+    std::vector<double> consts;
+    std::vector<std::vector<double>> params;
+    std::vector<RefStageObj*> objs;            /* [stage] -> calloc'ed array of V objects (light stages) */
+    std::vector<maxiDelayline**> delays;       /* [stage] -> V delay lines (5.6 MB each) or null */
+    std::vector<maxiFlanger**> flangers;
+    std::vector<maxiEnvGen*> envgens;          /* [stage] -> array of V */
+};
+
+int ref_state_slots(const mxo_stage& g) {
+    switch (g.op) {
+        case MXO_OP_OSC: return 2;
+        case MXO_OP_ENV_ADSR: case MXO_OP_ENV_AR: return 4;
+        case MXO_OP_ENVGEN: return 12;
+        case MXO_OP_FILTER: return 2;
+        case MXO_OP_SVF: return 3;
+        case MXO_OP_BIQUAD: return 2;
+        case MXO_OP_DCBLOCK: return 2;
+        case MXO_OP_DELAY: return 1;
+        case MXO_OP_FLANGER: return 3;
+        default: return 0;
+    }
+}
+
+/* address of state slot `slot` of stage `si`, voice v, inside the reference object (nullptr: integer / bool members, handled apart) */
+double* ref_slot_ptr(RefPatch* p, int si, int slot, int v) {
+    const mxo_stage& g = p->stages[si];
+    RefStageObj* o = p->objs[si] ? &p->objs[si][v] : nullptr;
+    switch (g.op) {
+        case MXO_OP_OSC: return slot == 0 ? &o->osc.phase : &o->osc.output;
+        case MXO_OP_ENV_ADSR: case MXO_OP_ENV_AR: return slot == 0 ? &o->env.amplitude : slot == 1 ? &o->env.output : nullptr;
+        case MXO_OP_FILTER:
+            if (g.kind == MXO_FILT_LORES || g.kind == MXO_FILT_HIRES) return slot == 0 ? &o->filt.x : &o->filt.y;
+            if (g.kind == MXO_FILT_BANDPASS) return slot == 0 ? &o->filt.outputs[1] : &o->filt.outputs[2];
+            return slot == 0 ? &o->filt.outputs[0] : nullptr;
+        case MXO_OP_SVF: return slot == 0 ? &o->svf.v0z : slot == 1 ? &o->svf.v1 : &o->svf.v2;
+        case MXO_OP_BIQUAD: return slot == 0 ? &o->bq.v[1] : &o->bq.v[2];
+        case MXO_OP_DCBLOCK: return slot == 0 ? &o->dc.xm1 : &o->dc.ym1;
+        case MXO_OP_FLANGER: return slot == 1 ? &p->flangers[si][v]->lfo.phase : slot == 2 ? &p->flangers[si][v]->lfo.output : nullptr;
+        default: return nullptr;
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t mxo_set_tables(const double*, const double*, double) { return 0; }     /* the reference has its own */
+int32_t mxo_get_tables(double* sine514, double* transition1001, double* sine_before) {
+    memcpy(sine514, sineBuffer, sizeof(double) * 514);
+    memcpy(transition1001, transition, sizeof(double) * 1001);
+    *sine_before = (&sineBuffer[0])[-1];       /* what sinebuf4 reads on its wrap sample in THIS build of the reference */
+    return 0;
+}
+
+void* mxo_patch_create(const mxo_patch_desc* d) {
+    if (!d || d->voices <= 0 || d->n_stages <= 0 || d->n_stages > 64 || !d->stages) return nullptr;
+    maxiSettings::setup((size_t)d->sample_rate, 2, 1024);
+    RefPatch* p = new RefPatch();
+    p->d = *d;
+    p->stages.assign(d->stages, d->stages + d->n_stages);
+    p->consts.assign(64, 0.0);
+    for (int i = 0; i < d->n_consts; ++i) p->consts[i] = d->consts[i];
+    p->params.assign((size_t)d->n_params, std::vector<double>((size_t)d->voices, 0.0));
+    const int V = d->voices;
+    for (int si = 0; si < d->n_stages; ++si) {
+        const mxo_stage& g = p->stages[si];
+        RefStageObj* o = (RefStageObj*)calloc((size_t)V, sizeof(RefStageObj));
+        for (int v = 0; v < V; ++v) new (&o[v]) RefStageObj();
+        p->objs.push_back(o);
+        maxiDelayline** dl = nullptr; maxiFlanger** fl = nullptr; maxiEnvGen* eg = nullptr;
+        if (g.op == MXO_OP_DELAY) { dl = (maxiDelayline**)calloc((size_t)V, sizeof(void*)); for (int v = 0; v < V; ++v) dl[v] = zeroed_new<maxiDelayline>(); }
+        if (g.op == MXO_OP_FLANGER) { fl = (maxiFlanger**)calloc((size_t)V, sizeof(void*)); for (int v = 0; v < V; ++v) fl[v] = zeroed_new<maxiFlanger>(); }
+        if (g.op == MXO_OP_ENVGEN) {
+            eg = new maxiEnvGen[V];
+            std::vector<double> levels(d->eg_levels, d->eg_levels + d->eg_stages + 1), times(d->eg_times, d->eg_times + d->eg_stages),
+                curves(d->eg_curves, d->eg_curves + d->eg_stages);
+            std::streambuf* old = std::cout.rdbuf(nullptr);              /* setup() prints every segment */
+            for (int v = 0; v < V; ++v) eg[v].setup(levels, times, curves, d->eg_loop != 0, d->eg_retrigger != 0);
+            std::cout.rdbuf(old);
+        }
+        p->delays.push_back(dl); p->flangers.push_back(fl); p->envgens.push_back(eg);
+    }
+    return p;
+}
+
+void mxo_patch_destroy(void* h) {
+    RefPatch* p = (RefPatch*)h; if (!p) return;
+    for (size_t si = 0; si < p->stages.size(); ++si) {
+        free(p->objs[si]);
+        if (p->delays[si]) { for (int v = 0; v < p->d.voices; ++v) free(p->delays[si][v]); free(p->delays[si]); }
+        if (p->flangers[si]) { for (int v = 0; v < p->d.voices; ++v) free(p->flangers[si][v]); free(p->flangers[si]); }
+        delete[] p->envgens[si];
+    }
+    delete p;
+}
+
+int32_t mxo_patch_set_param(void* h, int32_t j, const double* x) {
+    RefPatch* p = (RefPatch*)h; if (!p || !x || j < 0 || j >= p->d.n_params) return -1;
+    p->params[j].assign(x, x + p->d.voices);
+    return 0;
+}
+
+int32_t mxo_patch_set_state(void* h, int32_t stage, int32_t slot, const double* x) {
+    RefPatch* p = (RefPatch*)h;
+    if (!p || !x || stage < 0 || stage >= p->d.n_stages || slot < 0 || slot >= ref_state_slots(p->stages[stage])) return -1;
+    for (int v = 0; v < p->d.voices; ++v) { double* q = ref_slot_ptr(p, stage, slot, v); if (!q) return -3; *q = x[v]; }
+    return 0;
+}
+
+int32_t mxo_patch_get_state(void* h, int32_t stage, int32_t slot, double* x) {
+    RefPatch* p = (RefPatch*)h;
+    if (!p || !x || stage < 0 || stage >= p->d.n_stages || slot < 0 || slot >= ref_state_slots(p->stages[stage])) return -1;
+    const mxo_stage& g = p->stages[stage];
+    for (int v = 0; v < p->d.voices; ++v) {
+        double* q = ref_slot_ptr(p, stage, slot, v);
+        if (q) { x[v] = *q; continue; }
+        if (g.op == MXO_OP_ENV_ADSR || g.op == MXO_OP_ENV_AR) {
+            maxiEnv& e = p->objs[stage][v].env;
+            x[v] = slot == 2 ? (double)e.holdcount
+                             : (double)((e.attackphase & 1) | (e.decayphase & 1) << 1 | (e.sustainphase & 1) << 2 | (e.holdphase & 1) << 3 | (e.releasephase & 1) << 4);
+        } else if (g.op == MXO_OP_DELAY) x[v] = (double)p->delays[stage][v]->phase;
+        else if (g.op == MXO_OP_FLANGER) x[v] = (double)p->flangers[stage][v]->dl.phase;
+        else if (g.op == MXO_OP_ENVGEN) {
+            maxiEnvGen& e = p->envgens[stage][v];
+            switch (slot) {
+                case 0: x[v] = e.envval; break;
+                case 1: x[v] = (double)e.phase; break;
+                case 2: x[v] = (double)(int)e.state; break;
+                case 3: x[v] = e.nxcHappened ? 1.0 : 0.0; break;
+                case 4: x[v] = e.phase < e.stages.size() ? (double)e.stages[e.phase].counter : 0.0; break;
+                case 5: x[v] = e.phase < e.stages.size() ? e.stages[e.phase].currentlevel : 0.0; break;
+                case 6: x[v] = e.trigDetector.previousValue; break;
+                case 7: x[v] = e.trigDetector.firstTrigger ? 1.0 : 0.0; break;
+                case 8: x[v] = e.holdDetector.previousValue; break;
+                case 9: x[v] = e.holdDetector.firstTrigger ? 1.0 : 0.0; break;
+                case 10: x[v] = e.retriggerDetector.previousValue; break;
+                default: x[v] = e.retriggerDetector.firstTrigger ? 1.0 : 0.0; break;
+            }
+        } else return -3;
+    }
+    return 0;
+}
+
+int32_t mxo_patch_get_ring(void* h, int32_t stage, int32_t v, double* dst, int32_t n) {
+    RefPatch* p = (RefPatch*)h;
+    if (!p || !dst || stage < 0 || stage >= p->d.n_stages || v < 0 || v >= p->d.voices || n < 0 || n > 88200 * 8) return -1;
+    if (p->delays[stage]) memcpy(dst, p->delays[stage][v]->memory, sizeof(double) * (size_t)n);
+    else if (p->flangers[stage]) memcpy(dst, p->flangers[stage][v]->dl.memory, sizeof(double) * (size_t)n);
+    else return -1;
+    return 0;
+}
+
+int32_t mxo_patch_process(void* h, int32_t nframes, const double* const* inputs, double* out, double* mix) {
+    RefPatch* p = (RefPatch*)h;
+    if (!p || nframes < 0) return -1;
+    maxiSettings::setup((size_t)p->d.sample_rate, 2, 1024);
+    const size_t V = (size_t)p->d.voices;
+    std::vector<double> two(2, 0.0);
+    double reg[16];
+    for (int t = 0; t < nframes; ++t) {
+        double m0 = 0.0, m1 = 0.0;
+        for (size_t v = 0; v < V; ++v) {
+            for (double& r : reg) r = 0.0;
+            auto F = [&](int s) -> double {
+                if (s < 0) return 0.0;
+                const int k = s & 0xff;
+                switch (s >> 8) {
+                    case 0: return reg[k];
+                    case 1: return p->params[k][v];
+                    case 2: return p->consts[k];
+                    default: return inputs[k][(size_t)t * V + v];
+                }
+            };
+            for (int si = 0; si < p->d.n_stages; ++si) {
+                const mxo_stage& g = p->stages[si];
+                RefStageObj& o = p->objs[si][v];
+                double y = 0.0;
+                switch (g.op) {
+                    case MXO_OP_OSC:
+                        switch (g.kind) {
+                            case MXO_OSC_SINEBUF: y = o.osc.sinebuf(F(g.src[0])); break;
+                            case MXO_OSC_SINEBUF4: y = o.osc.sinebuf4(F(g.src[0])); break;
+                            case MXO_OSC_SAWN: y = o.osc.sawn(F(g.src[0])); break;
+                            default: y = run_osc(o.osc, g.kind, F(g.src[0]), F(g.src[1]), F(g.src[1]), F(g.src[2])); break;
+                        }
+                        break;
+                    case MXO_OP_ENV_ADSR:
+                        y = o.env.adsr(F(g.src[0]), F(g.src[2]), F(g.src[3]), F(g.src[4]), F(g.src[5]), (long)F(g.src[6]), (int)F(g.src[1]));
+                        break;
+                    case MXO_OP_ENV_AR:
+                        y = o.env.ar(F(g.src[0]), F(g.src[2]), F(g.src[3]), (long)F(g.src[4]), (int)F(g.src[1]));
+                        break;
+                    case MXO_OP_ENVGEN: y = p->envgens[si][v].play(F(g.src[0])); break;
+                    case MXO_OP_FILTER:
+                        switch (g.kind) {
+                            case MXO_FILT_LORES: y = o.filt.lores(F(g.src[0]), F(g.src[1]), F(g.src[2])); break;
+                            case MXO_FILT_HIRES: y = o.filt.hires(F(g.src[0]), F(g.src[1]), F(g.src[2])); break;
+                            case MXO_FILT_LOPASS: y = o.filt.lopass(F(g.src[0]), F(g.src[1])); break;
+                            case MXO_FILT_HIPASS: y = o.filt.hipass(F(g.src[0]), F(g.src[1])); break;
+                            default: y = o.filt.bandpass(F(g.src[0]), F(g.src[1]), F(g.src[2])); break;
+                        }
+                        break;
+                    case MXO_OP_SVF:
+                        o.svf.setCutoff(F(g.src[1])); o.svf.setResonance(F(g.src[2]));
+                        y = o.svf.play(F(g.src[0]), F(g.src[3]), F(g.src[4]), F(g.src[5]), F(g.src[6]));
+                        break;
+                    case MXO_OP_BIQUAD:
+                        o.bq.set((maxiBiquad::filterTypes)g.kind, F(g.src[1]), F(g.src[2]), F(g.src[3]));
+                        y = o.bq.play(F(g.src[0]));
+                        break;
+                    case MXO_OP_DCBLOCK: y = o.dc.play(F(g.src[0]), F(g.src[1])); break;
+                    case MXO_OP_NONLIN:
+                        switch (g.kind) {
+                            case MXO_NL_ATANDIST: y = o.nl.atanDist(F(g.src[0]), F(g.src[1])); break;
+                            case MXO_NL_FASTATANDIST: y = o.nl.fastAtanDist(F(g.src[0]), F(g.src[1])); break;
+                            case MXO_NL_SOFTCLIP: y = o.nl.softclip(F(g.src[0])); break;
+                            case MXO_NL_HARDCLIP: y = o.nl.hardclip(F(g.src[0])); break;
+                            case MXO_NL_ASYMCLIP: y = o.nl.asymclip(F(g.src[0]), F(g.src[1]), F(g.src[2])); break;
+                            default: y = o.nl.fastatan(F(g.src[0])); break;
+                        }
+                        break;
+                    case MXO_OP_DELAY:
+                        if (g.kind == 1) y = p->delays[si][v]->dlFromPosition(F(g.src[0]), (int)F(g.src[1]), F(g.src[2]), (int)F(g.src[3]));
+                        else y = p->delays[si][v]->dl(F(g.src[0]), (int)F(g.src[1]), F(g.src[2]));
+                        break;
+                    case MXO_OP_FLANGER:
+                        y = p->flangers[si][v]->flange(F(g.src[0]), (unsigned int)F(g.src[1]), F(g.src[2]), F(g.src[3]), F(g.src[4]));
+                        break;
+                    case MXO_OP_ADD: y = F(g.src[0]) + F(g.src[1]); break;
+                    case MXO_OP_SUB: y = F(g.src[0]) - F(g.src[1]); break;
+                    case MXO_OP_MUL: y = F(g.src[0]) * F(g.src[1]); break;
+                    case MXO_OP_DIV: y = F(g.src[0]) / F(g.src[1]); break;
+                    case MXO_OP_MIX_STEREO: o.mixer.stereo(F(g.src[0]), two, F(g.src[1])); m0 += two[0]; m1 += two[1]; break;
+                    case MXO_OP_OUT: if (out) out[(size_t)t * V + v] = F(g.src[0]); break;
+                    default: return -2;
+                }
+                if (g.dst >= 0) reg[g.dst] = y;
+            }
+        }
+        if (mix) { mix[2 * t] = m0; mix[2 * t + 1] = m1; }
     }
     return 0;
 }

@@ -149,9 +149,37 @@ def spectral():
                         x_hop256=x2, mags_hop256=r2["mags"], re_hop256=r2["re"], im_hop256=r2["im"])
 
 
+def tables():
+    """sineBuffer[514], transition[1001] and the double in front of sineBuffer (read by sinebuf4 on its wrap sample) as the
+    compiled reference holds them: data the product and the C port are handed at run time (mxb_ctx_set_tables / mxo_set_tables)."""
+    s, t, b = O.get_tables(KIND)
+    np.savez_compressed(os.path.join(HERE, "tables.npz"), sine=s, transition=t, sine_before=np.float64(b))
+
+
+def patches():
+    """Voice patches (tests/patch_cases.py) run by the reference's own objects: outputs, buses and inputs of 3 blocks."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import patch_cases as PC
+    V, B, NB = 12, 160, 3
+    out = {"V": V, "B": B, "NB": NB}
+    for name, d, params, inputs, exact, taps in PC.cases():
+        p = O.Patch(d, V, delay_taps=taps, kind=KIND)
+        for k, v in params(V, 2468).items():
+            p.set(k, v)
+        outs, mixes = [], []
+        for blk in range(NB):
+            ins = inputs(V, B, blk, 1357)
+            for k, a in ins.items():
+                out[f"{name}/in/{k}/{blk}"] = a
+            o, m = p.process(B, ins, want_mix=True)
+            outs.append(o); mixes.append(m)
+        out[name + "/out"] = np.stack(outs); out[name + "/mix"] = np.stack(mixes)
+    np.savez_compressed(os.path.join(HERE, "patches.npz"), **out)
+
+
 if __name__ == "__main__":
     O.build("reference")
-    chains(); seeds(); spectral(); mods()
+    chains(); seeds(); spectral(); mods(); tables(); patches()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)), "bytes")
