@@ -355,6 +355,28 @@ int32_t mxb_stft_process2(mxb_stft* st, const float* in, int64_t stride_c, int64
                           int32_t max_frames, const mxb_stft_outputs* out, mxb_mfcc* mfcc,
                           int32_t* n_frames, int32_t mem, void* stream);
 
+/* maxiFFTOctaveAnalyzer (src/libs/maxiFFT.h:162-205, maxiFFT.cpp:201-300) and maxiBark (src/libs/maxiBark.h:36-126)
+ * as further epilogues of the transform, computed per frame from the magnitudes while they are in shared memory.
+ * mxb_octave = setup(samplingRate, nBandsInTheFFT, nAveragesPerOctave) for every channel of one mxb_stft: the bin -> band map and the
+ * per-channel averages / peaks / peakHoldTimes (state carried from frame to frame and call to call, zero at creation; the reference
+ * leaves them uninitialised). mxb_octave_config sets the public members peakHoldTime, peakDecayRate, linearEQIntercept, linearEQSlope.
+ * octave_averages / octave_peaks: float [channels][max_frames][mxb_octave_n_averages()] after each frame's calculate().
+ * bark != 0: maxiBarkScaleAnalyser::setup(sample rate of the context, fft_size); bark_specific / bark_relative: double
+ * [channels][max_frames][24] (specificLoudness / relativeLoudness of the magnitudes), bark_total: double [channels][max_frames].
+ * pow(sum, 0.23) is libdevice's: 1e-12 relative. Built into the 1024-point kernel; other sizes: MXB_ERR_UNSUPPORTED. */
+typedef struct mxb_octave mxb_octave;
+int32_t mxb_octave_create(mxb_ctx* ctx, int32_t channels, float sampling_rate, int32_t n_bands, int32_t n_per_octave, mxb_octave** o);
+int32_t mxb_octave_destroy(mxb_octave* o);
+int32_t mxb_octave_n_averages(const mxb_octave* o);
+int32_t mxb_octave_config(mxb_octave* o, int32_t peak_hold_time, float peak_decay_rate, float eq_intercept, float eq_slope);
+typedef struct {
+    mxb_octave* octave; float *octave_averages, *octave_peaks;
+    int32_t bark; double *bark_specific, *bark_relative, *bark_total;
+} mxb_stft_post;
+int32_t mxb_stft_process3(mxb_stft* st, const float* in, int64_t stride_c, int64_t stride_t, int32_t n_samples,
+                          int32_t max_frames, const mxb_stft_outputs* out, const mxb_stft_post* post, mxb_mfcc* mfcc,
+                          int32_t* n_frames, int32_t mem, void* stream);
+
 /* maxiMFCC::setup(numBins, numFilters, numCoeffs, minFreq, maxFreq) + mfcc() (src/libs/maxiMFCC.h:56-111,
  * src/libs/maxiMFCC.cpp:48-66). mags: float [n][num_bins]; coeffs: double [n][num_coeffs];
  * melbands (optional): double [n][num_filters] after the log stage. */

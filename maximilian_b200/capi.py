@@ -30,6 +30,7 @@ EXPORTS = [
     "mxb_stft_create", "mxb_stft_destroy", "mxb_stft_process", "mxb_stft_process2", "mxb_stft_launch_count",
     "mxb_mfcc_create", "mxb_mfcc_destroy", "mxb_mfcc_process",
     "mxb_istft_create", "mxb_istft_destroy", "mxb_istft_process",
+    "mxb_octave_create", "mxb_octave_destroy", "mxb_octave_n_averages", "mxb_octave_config", "mxb_stft_process3",
     "mxb_ctx_set_tables", "mxb_patch_create", "mxb_patch_destroy", "mxb_patch_set_param", "mxb_patch_set_state", "mxb_patch_get_state",
     "mxb_patch_get_ring", "mxb_patch_process", "mxb_patch_launch_count",
 ]
@@ -113,6 +114,11 @@ def lib():
         "mxb_istft_create": (i32, [vp, i32, i32, i32, pp]),
         "mxb_istft_destroy": (i32, [vp]),
         "mxb_istft_process": (i32, [vp, vp, vp, i32, vp, i32, vp]),
+        "mxb_octave_create": (i32, [vp, i32, C.c_float, i32, i32, pp]),
+        "mxb_octave_destroy": (i32, [vp]),
+        "mxb_octave_n_averages": (i32, [vp]),
+        "mxb_octave_config": (i32, [vp, i32, C.c_float, C.c_float, C.c_float]),
+        "mxb_stft_process3": (i32, [vp, vp, i64, i64, i32, i32, C.POINTER(StftOutputs), vp, vp, C.POINTER(i32), i32, vp]),
         "mxb_ctx_set_tables": (i32, [vp, vp, vp, dbl]),
         "mxb_patch_create": (i32, [vp, vp, pp]),
         "mxb_patch_destroy": (i32, [vp]),
@@ -422,6 +428,59 @@ class Stft:
                                      _ptr(re), _ptr(im), mfcc.h if mfcc is not None else None, _ptr(coeffs),
                                      C.byref(nf), MEM_DEVICE, C.c_void_p(int(stream)) if stream else None), "mxb_stft_process")
         return nf.value
+
+
+class StftPost(C.Structure):
+    _fields_ = [("octave", C.c_void_p), ("octave_averages", C.c_void_p), ("octave_peaks", C.c_void_p),
+                ("bark", C.c_int32), ("bark_specific", C.c_void_p), ("bark_relative", C.c_void_p), ("bark_total", C.c_void_p)]
+
+
+class Octave:
+    """mxb_octave: maxiFFTOctaveAnalyzer::setup for every channel of one Stft (state: averages, peaks, hold times on the device)."""
+
+    def __init__(self, channels, sampling_rate, n_bands, n_per_octave, ctx=None, device=0, sample_rate=48000):
+        self.ctx = ctx or default_context(device, sample_rate)
+        self.h = C.c_void_p()
+        check(lib().mxb_octave_create(self.ctx.h, int(channels), float(sampling_rate), int(n_bands), int(n_per_octave), C.byref(self.h)), "mxb_octave_create")
+        self.C, self.n_averages = int(channels), int(lib().mxb_octave_n_averages(self.h))
+
+    def config(self, peak_hold_time=0, peak_decay_rate=0.9, eq_intercept=1.0, eq_slope=0.0):
+        check(lib().mxb_octave_config(self.h, int(peak_hold_time), float(peak_decay_rate), float(eq_intercept), float(eq_slope)), "mxb_octave_config")
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().mxb_octave_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def stft_process_post(st, x, octave=None, bark=False):
+    """Stft.process with the octave-analyser / Bark epilogues (mxb_stft_process3): x float32 [C][n] planar host array ->
+    dict(mags [C][F][bins], averages / peaks [C][F][nAverages], bark_specific / bark_relative [C][F][24], bark_total [C][F])."""
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    n = x.shape[1]
+    maxf = max(1, n // st.hop + 2)
+    mags = np.zeros((st.C, maxf, st.bins), dtype=np.float32)
+    o = StftOutputs(mags.ctypes.data, None, None, None, None, None, None, None)
+    nA = octave.n_averages if octave is not None else 1
+    av = np.zeros((st.C, maxf, nA), dtype=np.float32); pk = np.zeros_like(av)
+    bs = np.zeros((st.C, maxf, 24)); br = np.zeros_like(bs); bt = np.zeros((st.C, maxf))
+    post = StftPost(octave.h if octave is not None else None, av.ctypes.data if octave is not None else None, pk.ctypes.data if octave is not None else None,
+                    1 if bark else 0, bs.ctypes.data if bark else None, br.ctypes.data if bark else None, bt.ctypes.data if bark else None)
+    nf = C.c_int32(0)
+    check(lib().mxb_stft_process3(st.h, _np_ptr(x), n, 1, n, maxf, C.byref(o), C.byref(post), None, C.byref(nf), MEM_HOST, None), "mxb_stft_process3")
+    f = nf.value
+    r = dict(mags=mags[:, :f].copy())
+    if octave is not None:
+        r.update(averages=av[:, :f].copy(), peaks=pk[:, :f].copy())
+    if bark:
+        r.update(bark_specific=bs[:, :f].copy(), bark_relative=br[:, :f].copy(), bark_total=bt[:, :f].copy())
+    return r
 
 
 class Mfcc:

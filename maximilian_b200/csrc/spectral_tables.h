@@ -153,4 +153,66 @@ inline MfccTables mfcc_tables(unsigned numBins, unsigned numFilters, unsigned nu
     return t;
 }
 
+// maxiFFTOctaveAnalyzer::setup, src/libs/maxiFFT.cpp:201-256 (float arithmetic; pow on floats is powf there): the bin -> averaging
+// band map, turned into the RUNS of bins whose running sum calculate() (:264-287) stores: a run ends ON the first bin whose band
+// differs from the previous bin's, and its average goes to every band in [previous band, this band).
+struct OctaveMap { int n_avg; std::vector<int> runs; };     // runs: first bin, last bin (inclusive), first band, one past the last band
+inline OctaveMap octave_map(float samplingRate, int nBandsInTheFFT, int nAveragesPerOctave) {
+    OctaveMap m;
+    const int nSpectrum = nBandsInTheFFT;
+    const float spectrumFrequencySpan = (samplingRate / 2.0f) / (float)(nSpectrum);
+    if (nAveragesPerOctave == 0) nAveragesPerOctave = 1;
+    const float averageFrequencyIncrement = powf(2.0f, 1.0f / (float)(nAveragesPerOctave));
+    const float firstOctaveFrequency = 55.0f;
+    std::vector<int> spe2avg((size_t)nSpectrum);
+    int avgidx = 0;
+    float averageFreq = firstOctaveFrequency;
+    float spectrumFreq = spectrumFrequencySpan;
+    for (int speidx = 0; speidx < nSpectrum; speidx++) {
+        while (spectrumFreq > averageFreq) { avgidx++; averageFreq *= averageFrequencyIncrement; }
+        spe2avg[(size_t)speidx] = avgidx;
+        spectrumFreq += spectrumFrequencySpan;
+    }
+    m.n_avg = avgidx;
+    int last_avgidx = 0, first = 0;
+    for (int speidx = 0; speidx < nSpectrum; speidx++) {
+        const int a = spe2avg[(size_t)speidx];
+        if (a != last_avgidx) {
+            m.runs.push_back(first); m.runs.push_back(speidx); m.runs.push_back(last_avgidx); m.runs.push_back(a < m.n_avg ? a : m.n_avg);
+            first = speidx + 1;
+        }
+        last_avgidx = a;
+    }
+    if (first < nSpectrum && last_avgidx < m.n_avg) {       // "the last average was probably not calculated..."
+        m.runs.push_back(first); m.runs.push_back(nSpectrum - 1); m.runs.push_back(last_avgidx); m.runs.push_back(last_avgidx + 1);
+    }
+    return m;
+}
+
+// maxiBarkScaleAnalyser::setup, src/libs/maxiBark.h:40-61: bbLimits[0..24]. binToHz is unsigned integer arithmetic returned as a
+// double (:30-32), currentBandEnd an int (:52); the reference writes bbLimits[24] into the member behind its int[24].
+inline std::vector<int> bark_limits(unsigned int sR, unsigned int bS) {
+    const unsigned int specSize = bS / 2;
+    const int NUM_BARK_BANDS = 24;
+    std::vector<double> barkScale((size_t)specSize);
+    std::vector<int> bbLimits(32, 0);
+    for (unsigned int i = 0; i < specSize; i++) {
+        const double hz = (double)(i * sR / bS);
+        barkScale[i] = 13.0 * atan(hz / 1315.8) + 3.5 * atan(pow((hz / 7518.0), 2));
+    }
+    bbLimits[0] = 0;
+    int currentBandEnd = barkScale[specSize - 1] / NUM_BARK_BANDS;
+    int currentBand = 1;
+    for (unsigned int i = 0; i < specSize; i++) {
+        while (barkScale[i] > currentBandEnd) {
+            if (currentBand < 32) bbLimits[(size_t)currentBand] = (int)i;
+            currentBand++;
+            currentBandEnd = currentBand * barkScale[specSize - 1] / NUM_BARK_BANDS;
+        }
+    }
+    bbLimits[NUM_BARK_BANDS] = (int)specSize - 1;
+    bbLimits.resize(25);
+    return bbLimits;
+}
+
 }  // namespace mxb

@@ -359,6 +359,67 @@ __global__ void __launch_bounds__(kStreamWarps * 32, 2) stft_stream_kernel(const
                         if (act) melrow[fr * melstride + fl] = acc > 0.000001 ? log(__dmul_rn(acc, acc)) : 0.0;
                     }
                 }
+                if (FULL && (a.oct_nruns > 0 || a.bark_lim != nullptr)) {
+                    // ---- maxiFFTOctaveAnalyzer::calculate (maxiFFT.cpp:264-300) and maxiBark (maxiBark.h:63-113) on the magnitudes
+                    // still in shared memory. Octave: one lane per run of bins (the reference's running float sum closes a run ON the
+                    // first bin of the next averaging band), then one lane per averaging band for the peak-hold logic; the bands'
+                    // averages / peaks / hold counters are per-channel state carried from frame to frame in HBM (this warp walks
+                    // the channel's frames in order). Bark: one lane per band, double sums in bin order, pow, max, total.
+                    double* bsc = (double*)sW + 512;                          // 24 doubles of scratch behind s_mag[2][512]
+#pragma unroll 1
+                    for (int fr = 0; fr < 2; ++fr) {
+                        const int c = fr ? cB : cA;
+                        if (c >= C) break;
+                        const float* mag = s_mag + fr * half;
+                        const size_t of = (size_t)c * a.max_frames + f;
+                        if (a.oct_nruns > 0) {
+                            const int nA = a.oct_navg;
+                            float* avs = a.oct_avg_state + (size_t)c * nA; float* pks = a.oct_peak_state + (size_t)c * nA; int* hds = a.oct_hold_state + (size_t)c * nA;
+                            for (int r = lane; r < a.oct_nruns; r += 32) {
+                                const int4 run = ((const int4*)a.oct_runs)[r];          // first bin, last bin, first band, one past the last band
+                                float sum = 0.f;
+                                for (int b = run.x; b <= run.y; ++b)
+                                    sum = __fadd_rn(sum, __fmul_rn(mag[b], __fadd_rn(a.oct_icpt, __fmul_rn((float)b, a.oct_slope))));
+                                const float av = __fdiv_rn(sum, (float)(run.y - run.x + 1));
+                                for (int j = run.z; j < run.w; ++j) avs[j] = av;
+                            }
+                            __syncwarp();
+                            for (int i = lane; i < nA; i += 32) {
+                                const float av = avs[i];
+                                float pk = pks[i]; int hd = hds[i];
+                                if (av >= pk) { pk = av; hd = a.oct_hold; }
+                                else { if (hd > 0) hd--; else pk = __fmul_rn(pk, a.oct_decay); }
+                                pks[i] = pk; hds[i] = hd;
+                                if (a.oct_avg_out) a.oct_avg_out[of * nA + i] = av;
+                                if (a.oct_peak_out) a.oct_peak_out[of * nA + i] = pk;
+                            }
+                            __syncwarp();
+                        }
+                        if (a.bark_lim != nullptr) {
+                            double spec = 0.0;
+                            if (lane < 24) {
+                                double sum = 0.0;
+                                for (int j = a.bark_lim[lane]; j < a.bark_lim[lane + 1]; ++j) sum = __dadd_rn(sum, (double)mag[j]);
+                                spec = pow(sum, 0.23);
+                                bsc[lane] = spec;
+                            }
+                            double mx = spec > 0.0 ? spec : 0.0;                   // `if (specific[i] > max) max = specific[i]` from max = 0
+#pragma unroll
+                            for (int m = 16; m >= 1; m >>= 1) { const double o = __shfl_xor_sync(0xffffffffu, mx, m); mx = o > mx ? o : mx; }
+                            __syncwarp();
+                            if (lane < 24) {
+                                if (a.bark_specific) a.bark_specific[of * 24 + lane] = spec;
+                                if (a.bark_relative) a.bark_relative[of * 24 + lane] = spec / mx;
+                            }
+                            if (lane == 0 && a.bark_total) {
+                                double t = 0.0;
+                                for (int i = 0; i < 24; ++i) t = __dadd_rn(t, bsc[i]);
+                                a.bark_total[of] = t;
+                            }
+                            __syncwarp();
+                        }
+                    }
+                }
                 __syncwarp();
             } else if (a.has_mfcc) {
                 for (int k = lane; k < 2 * melstride; k += 32) melrow[k] = 0.0;

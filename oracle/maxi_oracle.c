@@ -1139,6 +1139,123 @@ int32_t mxo_spectral_features(const float* mags, int32_t n_frames, int32_t fft_s
     return 0;
 }
 
+/* ======================================================= spectral analysers */
+
+typedef struct { int C, nSpectrum, nAverages; int* spe2avg; float *averages, *peaks; int* peakHoldTimes;
+                 int peakHoldTime; float peakDecayRate, linearEQIntercept, linearEQSlope; } octave_t;
+
+/* maxiFFTOctaveAnalyzer::setup, src/libs/maxiFFT.cpp:201-262 (float arithmetic throughout; pow on floats is powf there) */
+void* mxo_octave_create(int32_t channels, float samplingRate, int32_t nBandsInTheFFT, int32_t nAveragesPerOctave) {
+    if (channels <= 0 || nBandsInTheFFT <= 0) return NULL;
+    octave_t* o = (octave_t*)calloc(1, sizeof(octave_t));
+    o->C = channels; o->nSpectrum = nBandsInTheFFT;
+    float spectrumFrequencySpan = (samplingRate / 2.0f) / (float)(o->nSpectrum);
+    if (nAveragesPerOctave == 0) nAveragesPerOctave = 1;
+    float averageFrequencyIncrement = powf(2.0f, 1.0f / (float)(nAveragesPerOctave));
+    float firstOctaveFrequency = 55.0f;
+    o->spe2avg = (int*)calloc((size_t)o->nSpectrum, sizeof(int));
+    int avgidx = 0;
+    float averageFreq = firstOctaveFrequency;
+    float spectrumFreq = spectrumFrequencySpan;
+    for (int speidx = 0; speidx < o->nSpectrum; speidx++) {
+        while (spectrumFreq > averageFreq) { avgidx++; averageFreq *= averageFrequencyIncrement; }
+        o->spe2avg[speidx] = avgidx;
+        spectrumFreq += spectrumFrequencySpan;
+    }
+    o->nAverages = avgidx;
+    o->averages = (float*)calloc((size_t)channels * (size_t)(avgidx ? avgidx : 1), sizeof(float));
+    o->peaks = (float*)calloc((size_t)channels * (size_t)(avgidx ? avgidx : 1), sizeof(float));
+    o->peakHoldTimes = (int*)calloc((size_t)channels * (size_t)(avgidx ? avgidx : 1), sizeof(int));
+    o->peakHoldTime = 0; o->peakDecayRate = 0.9f; o->linearEQIntercept = 1.0f; o->linearEQSlope = 0.0f;
+    return o;
+}
+void mxo_octave_destroy(void* h) { octave_t* o = (octave_t*)h; if (!o) return; free(o->spe2avg); free(o->averages); free(o->peaks); free(o->peakHoldTimes); free(o); }
+int32_t mxo_octave_n_averages(void* h) { return h ? ((octave_t*)h)->nAverages : -1; }
+int32_t mxo_octave_config(void* h, int32_t hold, float decay, float intercept, float slope) {
+    octave_t* o = (octave_t*)h; if (!o) return -1;
+    o->peakHoldTime = hold; o->peakDecayRate = decay; o->linearEQIntercept = intercept; o->linearEQSlope = slope;
+    return 0;
+}
+/* maxiFFTOctaveAnalyzer::calculate, src/libs/maxiFFT.cpp:264-300 */
+int32_t mxo_octave_process(void* h, const float* mags, int32_t frames, float* avg_out, float* peak_out) {
+    octave_t* o = (octave_t*)h;
+    if (!o || !mags || frames < 0) return -1;
+    const int nA = o->nAverages;
+    for (int c = 0; c < o->C; ++c) {
+        float* averages = o->averages + (size_t)c * nA; float* peaks = o->peaks + (size_t)c * nA; int* peakHoldTimes = o->peakHoldTimes + (size_t)c * nA;
+        for (int f = 0; f < frames; ++f) {
+            const float* fftData = mags + ((size_t)c * frames + f) * (size_t)o->nSpectrum;
+            int last_avgidx = 0;
+            float sum = 0.0f;
+            int count = 0;
+            for (int speidx = 0; speidx < o->nSpectrum; speidx++) {
+                count++;
+                sum += fftData[speidx] * (o->linearEQIntercept + (float)(speidx)*o->linearEQSlope);
+                int avgidx = o->spe2avg[speidx];
+                if (avgidx != last_avgidx) {
+                    for (int j = last_avgidx; j < avgidx; j++) averages[j] = sum / (float)(count);
+                    count = 0;
+                    sum = 0.0f;
+                }
+                last_avgidx = avgidx;
+            }
+            if ((count > 0) && (last_avgidx < nA)) averages[last_avgidx] = sum / (float)(count);
+            for (int i = 0; i < nA; i++) {
+                if (averages[i] >= peaks[i]) { peaks[i] = averages[i]; peakHoldTimes[i] = o->peakHoldTime; }
+                else { if (peakHoldTimes[i] > 0) peakHoldTimes[i]--; else peaks[i] *= o->peakDecayRate; }
+            }
+            if (avg_out) memcpy(avg_out + ((size_t)c * frames + f) * nA, averages, sizeof(float) * (size_t)nA);
+            if (peak_out) memcpy(peak_out + ((size_t)c * frames + f) * nA, peaks, sizeof(float) * (size_t)nA);
+        }
+    }
+    return 0;
+}
+
+/* maxiBarkScaleAnalyser, src/libs/maxiBark.h:25-126. binToHz is UNSIGNED INTEGER arithmetic (bin*sR/bS) returned as a double;
+ * currentBandEnd is an int; bbLimits has 24 slots and setup() writes bbLimits[24] (the member behind it): 25 slots here. */
+int32_t mxo_bark(const float* spectrum, int32_t n_frames, int32_t sample_rate, int32_t buffer_size, double* specific_out, double* relative_out, double* total_out) {
+    if (!spectrum || n_frames < 0 || buffer_size < 4 || buffer_size / 2 > 2048) return -1;
+    const unsigned int sR = (unsigned int)sample_rate, bS = (unsigned int)buffer_size, specSize = bS / 2;
+    const int NUM_BARK_BANDS = 24;
+    static double barkScale[2048];
+    int bbLimits[32];
+    memset(bbLimits, 0, sizeof(bbLimits));
+    for (unsigned int i = 0; i < specSize; i++) {
+        double hz = (double)(i * sR / bS);
+        barkScale[i] = 13.0 * atan(hz / 1315.8) + 3.5 * atan(pow((hz / 7518.0), 2));
+    }
+    bbLimits[0] = 0;
+    int currentBandEnd = barkScale[specSize - 1] / NUM_BARK_BANDS;
+    int currentBand = 1;
+    for (unsigned int i = 0; i < specSize; i++) {
+        while (barkScale[i] > currentBandEnd) {
+            if (currentBand < 32) bbLimits[currentBand] = (int)i;
+            currentBand++;
+            currentBandEnd = currentBand * barkScale[specSize - 1] / NUM_BARK_BANDS;
+        }
+    }
+    bbLimits[NUM_BARK_BANDS] = (int)specSize - 1;
+    for (int f = 0; f < n_frames; ++f) {
+        const float* normalisedSpectrum = spectrum + (size_t)f * specSize;
+        double specific[24];
+        for (int i = 0; i < NUM_BARK_BANDS; i++) {
+            double sum = 0;
+            for (int j = bbLimits[i]; j < bbLimits[i + 1]; j++) sum += normalisedSpectrum[j];
+            specific[i] = pow(sum, 0.23);
+        }
+        double max = 0;
+        for (int i = 0; i < NUM_BARK_BANDS; i++) if (specific[i] > max) max = specific[i];
+        double total = 0;
+        for (int i = 0; i < 24; i++) total += specific[i];
+        for (int i = 0; i < NUM_BARK_BANDS; i++) {
+            if (specific_out) specific_out[(size_t)f * 24 + i] = specific[i];
+            if (relative_out) relative_out[(size_t)f * 24 + i] = specific[i] / max;
+        }
+        if (total_out) total_out[f] = total;
+    }
+    return 0;
+}
+
 /* =================================================================== MFCC */
 
 typedef struct {

@@ -171,6 +171,19 @@ int32_t mxo_patch_get_state(void* patch, int32_t stage, int32_t slot, double* va
 int32_t mxo_patch_get_ring(void* patch, int32_t stage, int32_t voice, double* dst, int32_t n);
 int32_t mxo_patch_process(void* patch, int32_t nframes, const double* const* inputs, double* out, double* mix);
 
+/* maxiFFTOctaveAnalyzer (src/libs/maxiFFT.h:162-205, maxiFFT.cpp:201-300), one analyser per channel, fed magnitude frames:
+ * mags[C][frames][n_bands] -> averages / peaks [C][frames][nAverages] (the values after each calculate()). averages[], peaks[]
+ * and peakHoldTimes[] start at zero (the reference leaves them uninitialised). config: the public members peakHoldTime,
+ * peakDecayRate, linearEQIntercept, linearEQSlope. */
+void*   mxo_octave_create(int32_t channels, float sampling_rate, int32_t n_bands, int32_t n_per_octave);
+void    mxo_octave_destroy(void* o);
+int32_t mxo_octave_n_averages(void* o);
+int32_t mxo_octave_config(void* o, int32_t peak_hold_time, float peak_decay_rate, float eq_intercept, float eq_slope);
+int32_t mxo_octave_process(void* o, const float* mags, int32_t frames, float* averages, float* peaks);
+/* maxiBarkScaleAnalyser::setup(sample_rate, buffer_size) + specificLoudness / relativeLoudness / totalLoudness
+ * (src/libs/maxiBark.h:36-126) on spectrum[n_frames][buffer_size/2]: specific, relative [n_frames][24], total [n_frames] */
+int32_t mxo_bark(const float* spectrum, int32_t n_frames, int32_t sample_rate, int32_t buffer_size, double* specific, double* relative, double* total);
+
 /* "reference" or "port" */
 const char* mxo_kind(void);
 

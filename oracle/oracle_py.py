@@ -449,3 +449,64 @@ class Patch:
         if rc:
             raise RuntimeError(f"mxo_patch_process -> {rc}")
         return out, mix
+
+
+# ------------------------------------------------------------------------------------------------ octave analyser / bark
+
+def _post_sigs(lib):
+    if getattr(lib, "_post_sigs_done", False):
+        return
+    fp, dp, vp, i32 = C.POINTER(C.c_float), C.POINTER(C.c_double), C.c_void_p, C.c_int32
+    lib.mxo_octave_create.restype, lib.mxo_octave_create.argtypes = vp, [i32, C.c_float, i32, i32]
+    lib.mxo_octave_destroy.restype, lib.mxo_octave_destroy.argtypes = None, [vp]
+    lib.mxo_octave_n_averages.restype, lib.mxo_octave_n_averages.argtypes = i32, [vp]
+    lib.mxo_octave_config.restype, lib.mxo_octave_config.argtypes = i32, [vp, i32, C.c_float, C.c_float, C.c_float]
+    lib.mxo_octave_process.restype, lib.mxo_octave_process.argtypes = i32, [vp, fp, i32, fp, fp]
+    lib.mxo_bark.restype, lib.mxo_bark.argtypes = i32, [fp, i32, i32, i32, dp, dp, dp]
+    lib._post_sigs_done = True
+
+
+class Octave:
+    """maxiFFTOctaveAnalyzer per channel: mags float32 [C][frames][bands] -> (averages, peaks) float32 [C][frames][nAverages]."""
+
+    def __init__(self, channels, sampling_rate, n_bands, n_per_octave, kind="port"):
+        self.lib = load(kind); _post_sigs(self.lib)
+        self.C, self.bands = channels, n_bands
+        self.h = self.lib.mxo_octave_create(channels, float(sampling_rate), n_bands, n_per_octave)
+        if not self.h:
+            raise RuntimeError("mxo_octave_create failed")
+        self.n_averages = self.lib.mxo_octave_n_averages(self.h)
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.lib.mxo_octave_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def config(self, peak_hold_time=0, peak_decay_rate=0.9, eq_intercept=1.0, eq_slope=0.0):
+        self.lib.mxo_octave_config(self.h, int(peak_hold_time), float(peak_decay_rate), float(eq_intercept), float(eq_slope))
+
+    def process(self, mags):
+        m = np.ascontiguousarray(mags, dtype=np.float32)
+        assert m.shape[0] == self.C and m.shape[2] == self.bands
+        f = m.shape[1]
+        av = np.empty((self.C, f, self.n_averages), dtype=np.float32); pk = np.empty_like(av)
+        rc = self.lib.mxo_octave_process(self.h, _fp(m), f, _fp(av), _fp(pk))
+        if rc:
+            raise RuntimeError(f"mxo_octave_process -> {rc}")
+        return av, pk
+
+
+def bark(spectrum, sample_rate, buffer_size, kind="port"):
+    """maxiBark on float32 [..., buffer_size/2] -> (specific [..., 24], relative [..., 24], total [...])."""
+    lib = load(kind); _post_sigs(lib)
+    m = np.ascontiguousarray(spectrum, dtype=np.float32)
+    lead = m.shape[:-1]
+    n = int(np.prod(lead)) if lead else 1
+    sp = np.empty((n, 24)); rl = np.empty((n, 24)); tt = np.empty(n)
+    rc = lib.mxo_bark(_fp(m), n, int(sample_rate), int(buffer_size), _dp(sp), _dp(rl), _dp(tt))
+    if rc:
+        raise RuntimeError(f"mxo_bark -> {rc}")
+    return sp.reshape(lead + (24,)), rl.reshape(lead + (24,)), tt.reshape(lead)

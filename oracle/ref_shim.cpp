@@ -30,6 +30,13 @@
 #include "maximilian.h"
 #include "maxiFFT.h"
 #include "maxiMFCC.h"
+/* maxiBarkScaleAnalyser::setup writes bbLimits[24] of an int[24] (src/libs/maxiBark.h:52-60): undefined behaviour that GCC's
+ * loop optimisations turn into a crash at -O2. The class is compiled without optimisation (same arithmetic, IEEE either way);
+ * the shim gives the object room behind bbLimits. */
+#pragma GCC push_options
+#pragma GCC optimize ("O0")
+#include "maxiBark.h"
+#pragma GCC pop_options
 
 #include "oracle_api.h"
 
@@ -645,5 +652,69 @@ int32_t mxo_patch_process(void* h, int32_t nframes, const double* const* inputs,
     }
     return 0;
 }
+
+}  // extern "C"
+
+/* ------------------------------------------------------------------ octave analyser / bark */
+struct RefOctave { int C; std::vector<maxiFFTOctaveAnalyzer*> a; };
+
+extern "C" {
+
+void* mxo_octave_create(int32_t channels, float sampling_rate, int32_t n_bands, int32_t n_per_octave) {
+    if (channels <= 0 || n_bands <= 0) return nullptr;
+    RefOctave* o = new RefOctave(); o->C = channels;
+    for (int c = 0; c < channels; ++c) {
+        maxiFFTOctaveAnalyzer* a = new maxiFFTOctaveAnalyzer();
+        a->setup(sampling_rate, n_bands, n_per_octave);
+        /* averages / peaks / peakHoldTimes come from new[] uninitialised: defined as zero */
+        for (int i = 0; i < a->nAverages; ++i) { a->averages[i] = 0.f; a->peaks[i] = 0.f; a->peakHoldTimes[i] = 0; }
+        o->a.push_back(a);
+    }
+    return o;
+}
+void mxo_octave_destroy(void* h) { RefOctave* o = (RefOctave*)h; if (!o) return; for (auto* a : o->a) delete a; delete o; }
+int32_t mxo_octave_n_averages(void* h) { return h ? ((RefOctave*)h)->a[0]->nAverages : -1; }
+int32_t mxo_octave_config(void* h, int32_t hold, float decay, float intercept, float slope) {
+    RefOctave* o = (RefOctave*)h; if (!o) return -1;
+    for (auto* a : o->a) { a->peakHoldTime = hold; a->peakDecayRate = decay; a->linearEQIntercept = intercept; a->linearEQSlope = slope; }
+    return 0;
+}
+int32_t mxo_octave_process(void* h, const float* mags, int32_t frames, float* averages, float* peaks) {
+    RefOctave* o = (RefOctave*)h;
+    if (!o || !mags || frames < 0) return -1;
+    for (int c = 0; c < o->C; ++c) {
+        maxiFFTOctaveAnalyzer* a = o->a[c];
+        const int nA = a->nAverages, nS = a->nSpectrum;
+        std::vector<float> frame((size_t)nS);
+        for (int f = 0; f < frames; ++f) {
+            memcpy(frame.data(), mags + ((size_t)c * frames + f) * nS, sizeof(float) * nS);
+            a->calculate(frame.data());
+            if (averages) memcpy(averages + ((size_t)c * frames + f) * nA, a->averages, sizeof(float) * nA);
+            if (peaks) memcpy(peaks + ((size_t)c * frames + f) * nA, a->peaks, sizeof(float) * nA);
+        }
+    }
+    return 0;
+}
+
+#pragma GCC push_options
+#pragma GCC optimize ("O0")
+int32_t mxo_bark(const float* spectrum, int32_t n_frames, int32_t sample_rate, int32_t buffer_size, double* specific, double* relative, double* total) {
+    if (!spectrum || n_frames < 0 || buffer_size < 4 || buffer_size / 2 > 2048) return -1;
+    /* setup() writes bbLimits[24], one int past the array, into the member behind it: give the object room */
+    struct Room { maxiBark b; int pad[8]; };
+    Room* r = (Room*)calloc(1, sizeof(Room));
+    r->b.setup((unsigned)sample_rate, (unsigned)buffer_size);
+    const int spec = buffer_size / 2;
+    std::vector<float> frame((size_t)spec);
+    for (int f = 0; f < n_frames; ++f) {
+        memcpy(frame.data(), spectrum + (size_t)f * spec, sizeof(float) * spec);
+        if (specific) memcpy(specific + (size_t)f * 24, r->b.specificLoudness(frame.data()), sizeof(double) * 24);
+        if (relative) memcpy(relative + (size_t)f * 24, r->b.relativeLoudness(frame.data()), sizeof(double) * 24);
+        if (total) total[f] = r->b.totalLoudness(frame.data())[0];
+    }
+    free(r);
+    return 0;
+}
+#pragma GCC pop_options
 
 }  // extern "C"

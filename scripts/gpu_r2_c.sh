@@ -1,6 +1,6 @@
 # round 2, run C: STFT stream kernel v2 (group barriers, fragment-ordered DCT, vector tail, uniform mel loop)
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_spectral.py tests/test_cpp_dropin.py -m gpu -q > gpurun_out/c_pytest.log 2>&1; grep -E "^(FAILED|ERROR)" gpurun_out/c_pytest.log | head -30; tail -3 gpurun_out/c_pytest.log
+timeout 900 python -m pytest tests/test_gpu_spectral.py tests/test_cpp_dropin.py tests/test_gpu_patch.py -m gpu -q > gpurun_out/c_pytest.log 2>&1; grep -E "^(FAILED|ERROR)" gpurun_out/c_pytest.log | head -30; tail -3 gpurun_out/c_pytest.log
 timeout 300 python bench.py --workload mfcc --steps 30 --warmup 5 --no-cpu > gpurun_out/c_bench_mfcc.json 2> gpurun_out/c_bench_mfcc.err; echo "bench rc=$?"; tail -c 400 gpurun_out/c_bench_mfcc.err
 python -c "
 import json; d=json.loads(open('gpurun_out/c_bench_mfcc.json').read().strip().splitlines()[-1]); print('mfcc', d['value'], d['roofline']['frac'], 'e2e', d['e2e']['value'])"

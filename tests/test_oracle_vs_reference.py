@@ -349,3 +349,32 @@ def test_istft_bit_exact(port, reference, n, hop):
         ya = a.process(r["mags"][:, lo:hi], r["phases"][:, lo:hi])
         yb = b.process(r["mags"][:, lo:hi], r["phases"][:, lo:hi])
         assert _same(ya, yb)
+
+
+# ---- maxiFFTOctaveAnalyzer / maxiBark ------------------------------------------------------------------------
+
+@pytest.mark.parametrize("per_octave,sr", [(1, 48000), (3, 48000), (3, 44100), (6, 48000), (0, 48000)])
+def test_octave_analyser_port_equals_reference(port, reference, per_octave, sr):
+    """maxiFFTOctaveAnalyzer::setup + calculate per channel (float sums in bin order, peak hold / decay carried across frames and
+    calls), with the public members changed from their defaults: averages and peaks bit for bit."""
+    x = W.channel_streams(3, 1024 * 9, seed=5)
+    mags = port.Stft(3, 1024, 512, kind="port").process(x)["mags"]
+    a = port.Octave(3, sr, 512, per_octave, kind="port"); b = reference.Octave(3, sr, 512, per_octave, kind="reference")
+    assert a.n_averages == b.n_averages > 0
+    a.config(2, 0.8, 1.0, 0.01); b.config(2, 0.8, 1.0, 0.01)
+    for lo, hi in ((0, 5), (5, mags.shape[1])):
+        ra = a.process(mags[:, lo:hi]); rb = b.process(mags[:, lo:hi])
+        assert np.array_equal(ra[0], rb[0]) and np.array_equal(ra[1], rb[1]), (lo, hi)
+
+
+@pytest.mark.parametrize("sr,bs", [(48000, 1024), (44100, 1024), (48000, 512), (22050, 256)])
+def test_bark_port_equals_reference(port, reference, sr, bs):
+    """maxiBarkScaleAnalyser: integer binToHz, int band ends, the 25th band limit written behind bbLimits[24] -- specific, relative and
+    total loudness bit for bit (the reference class is compiled at -O0 inside the shim: its setup() is undefined behaviour that -O2
+    turns into a crash)."""
+    x = W.channel_streams(3, 1024 * 9, seed=6)
+    mags = np.ascontiguousarray(port.Stft(3, 1024, 512, kind="port").process(x)["mags"][..., :bs // 2])
+    pa = port.bark(mags, sr, bs, "port"); pb = reference.bark(mags, sr, bs, "reference")
+    for u, v in zip(pa, pb):
+        assert np.array_equal(u, v, equal_nan=True)
+    assert np.all(pa[1].max(axis=-1) == 1.0)
