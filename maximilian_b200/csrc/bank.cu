@@ -172,6 +172,13 @@ __global__ void __launch_bounds__(kMixReduceThreads) mix_reduce_exchange_kernel(
     }
 }
 
+// ring slots [0, n) of one voice <-> a linear array (set != 0: linear -> ring)
+__global__ void ring_linear_kernel(double* __restrict__ ring, size_t V, size_t voice, double* __restrict__ lin, int n, int set) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    if (set) ring[dl_slot(V, voice, r)] = lin[r]; else lin[r] = ring[dl_slot(V, voice, r)];
+}
+
 int free_bank(mxb_bank* b) {
     if (!b) return MXB_OK;
     for (int i = 0; i < MXB_P_COUNT; ++i) {
@@ -409,15 +416,18 @@ int32_t mxb_bank_get_ring(mxb_bank* b, int32_t voice, double* dst, int32_t n, in
     MXB_REQUIRE(b && dst, MXB_ERR_INVALID, "mxb_bank_get_ring: NULL argument");
     MXB_REQUIRE(b->ring, MXB_ERR_STATE, "mxb_bank_get_ring: bank has no delay line");
     MXB_REQUIRE(voice >= 0 && voice < b->V && n >= 0 && n <= b->desc.delay_taps, MXB_ERR_INVALID, "mxb_bank_get_ring: voice %d n %d", voice, n);
+    MXB_REQUIRE(mem == MXB_MEM_HOST || mem == MXB_MEM_DEVICE, MXB_ERR_INVALID, "mxb_bank_get_ring: mem %d", mem);
+    if (n == 0) return MXB_OK;
     DeviceGuard g(b->ctx->device);
-    MXB_CUDA(cudaDeviceSynchronize());
-    // de-interleave the chunked ring (delay_kernels.cuh): chunk c of this voice is kDlChunk slots at (c*V + voice)*kDlChunk
-    const cudaMemcpyKind kind = mem == MXB_MEM_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
-    const size_t cb = sizeof(double) * kDlChunk;
-    const int full = n / kDlChunk, rem = n % kDlChunk;
-    const double* src = b->ring + (size_t)voice * kDlChunk;
-    if (full) MXB_CUDA(cudaMemcpy2D(dst, cb, src, cb * (size_t)b->V, cb, (size_t)full, kind));
-    if (rem) MXB_CUDA(cudaMemcpy(dst + (size_t)full * kDlChunk, src + (size_t)full * kDlChunk * (size_t)b->V, sizeof(double) * (size_t)rem, kind));
+    // the ring is chunk-interleaved and swizzled (delay_kernels.cuh): one small kernel walks the voice's slots
+    double* d_lin = dst;
+    if (mem == MXB_MEM_HOST) { int rc = dev_alloc(&d_lin, (size_t)n, false); if (rc != MXB_OK) return rc; }
+    ring_linear_kernel<<<(n + 255) / 256, 256>>>(b->ring, (size_t)b->V, (size_t)voice, d_lin, n, 0);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess && mem == MXB_MEM_HOST) e = cudaMemcpy(dst, d_lin, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost);
+    else if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (mem == MXB_MEM_HOST) cudaFree(d_lin);
+    if (e != cudaSuccess) { set_error("mxb_bank_get_ring: %s", cudaGetErrorString(e)); return MXB_ERR_CUDA; }
     return MXB_OK;
 }
 
@@ -426,14 +436,19 @@ int32_t mxb_bank_set_ring(mxb_bank* b, int32_t voice, const double* src, int32_t
     MXB_REQUIRE(b->ring, MXB_ERR_STATE, "mxb_bank_set_ring: bank has no delay line");
     MXB_REQUIRE(voice >= 0 && voice < b->V && n >= 0 && n <= b->desc.delay_taps, MXB_ERR_INVALID, "mxb_bank_set_ring: voice %d n %d", voice, n);
     MXB_REQUIRE(mem == MXB_MEM_HOST || mem == MXB_MEM_DEVICE, MXB_ERR_INVALID, "mxb_bank_set_ring: mem %d", mem);
+    if (n == 0) return MXB_OK;
     DeviceGuard g(b->ctx->device);
-    MXB_CUDA(cudaDeviceSynchronize());
-    const cudaMemcpyKind kind = mem == MXB_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
-    const size_t cb = sizeof(double) * kDlChunk;
-    const int full = n / kDlChunk, rem = n % kDlChunk;
-    double* dst = b->ring + (size_t)voice * kDlChunk;
-    if (full) MXB_CUDA(cudaMemcpy2D(dst, cb * (size_t)b->V, src, cb, cb, (size_t)full, kind));
-    if (rem) MXB_CUDA(cudaMemcpy(dst + (size_t)full * kDlChunk * (size_t)b->V, src + (size_t)full * kDlChunk, sizeof(double) * (size_t)rem, kind));
+    double* d_lin = const_cast<double*>(src);
+    if (mem == MXB_MEM_HOST) {
+        int rc = dev_alloc(&d_lin, (size_t)n, false); if (rc != MXB_OK) return rc;
+        cudaError_t e0 = cudaMemcpy(d_lin, src, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice);
+        if (e0 != cudaSuccess) { cudaFree(d_lin); set_error("mxb_bank_set_ring: %s", cudaGetErrorString(e0)); return MXB_ERR_CUDA; }
+    }
+    ring_linear_kernel<<<(n + 255) / 256, 256>>>(b->ring, (size_t)b->V, (size_t)voice, d_lin, n, 1);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (mem == MXB_MEM_HOST) cudaFree(d_lin);
+    if (e != cudaSuccess) { set_error("mxb_bank_set_ring: %s", cudaGetErrorString(e)); return MXB_ERR_CUDA; }
     return MXB_OK;
 }
 

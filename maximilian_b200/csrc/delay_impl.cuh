@@ -7,11 +7,13 @@
 // one 8-byte load per sample with 32 different lines per warp request; instead each WARP stages the next
 // T = 16 ring slots of each of its 32 voices through shared memory, double-buffered:
 //
-//   prefetch k+1: 16 cp.async requests, two voices each, lane&15 = slot: 128 contiguous bytes per voice, in flight
-//                 while window k is computed (warp-private tiles, no __syncthreads anywhere)
+//   prefetch k+1: uniform schedule: ONE bulk copy (cp.async.bulk.shared.global, SASS UBLKCP) of the warp's 4 KB run, completion
+//                 on an mbarrier, in flight while window k is computed; generic schedule: 16 cp.async requests, two voices
+//                 each (warp-private tiles, no __syncthreads anywhere)
 //   compute k:    lane = voice; 16 steps of the chain, ring slot j of the window read and updated in smem
-//                 (row stride 17 doubles: conflict-free for 64-bit accesses)
-//   write-back:   the window returns to the ring the way it came, 128 B per voice and request
+//                 (uniform: rows of 16 doubles, slot j at position j ^ (lane % 16) -- the swizzle of the HBM layout;
+//                 generic: row stride 17 doubles; both conflict-free for 64-bit accesses)
+//   write-back:   uniform: one bulk copy smem -> HBM (cp.async.bulk.global.shared, bulk group); generic: per-slot stores
 //
 // History (profiles/r01_delay_kernel_v*.txt): 32-slot windows double-buffered = 12 warps/SM, issue-starved (0.47-0.69 of
 // the HBM peak); single-buffered 24 warps (0.78) left too few bytes in flight; 16-slot windows give both: 24 warps/SM
@@ -51,6 +53,28 @@ __device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc) 
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait1() { asm volatile("cp.async.wait_group 1;\n" ::: "memory"); }
 
+// ---- bulk asynchronous copies (the TMA engine, 1-D form) with mbarrier completion ----
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* b, int count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* b, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* b, unsigned parity) {
+    asm volatile("{\n.reg .pred p;\nMXB_WAIT_%=:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra MXB_DONE_%=;\nbra MXB_WAIT_%=;\nMXB_DONE_%=:\n}"
+                 ::"r"(smem_u32(b)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, unsigned bytes, unsigned long long* b) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(b)) : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void* gdst, const void* smem_src, unsigned bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(smem_src)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }   // sources read: smem reusable
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }           // writes performed
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 struct DlVoice {
     double phase, oout, inc, duty, pend, fb, gl, gr;
     FiltRegs fr;
@@ -65,7 +89,7 @@ struct DlVoice {
 template <int OSC, int FILT, int ENV, bool ALLFAST, int OUTMODE, bool MIX, bool ESTEADY>
 __device__ __forceinline__ void dl_stage(DlVoice& s, double* row, const int tn, const int t0, const BankArgs& a, const DelayArgs& d,
                                          const size_t V, const size_t v, const int lane, const int gwarp, double* mixtile,
-                                         const bool relmode) {
+                                         const bool relmode, const int swz) {
     double* out64 = (double*)a.out + (size_t)t0 * V + v;
     float* out32 = (float*)a.out + (size_t)t0 * V + v;
 #pragma unroll 4
@@ -85,8 +109,8 @@ __device__ __forceinline__ void dl_stage(DlVoice& s, double* row, const int tn, 
         // maxiDelayline::dl, src/maximilian.cpp:420-429
         double y = 0.0;
         if (ALLFAST ? s.live : s.fast) {          // lanes past the end of the bank contribute an exact 0
-            const double m = row[j];
-            row[j] = (m * s.fb) + (x * s.fb) * 0.5;
+            const double m = row[j ^ swz];             // swz: lane % 16 on the bulk-copied (swizzled) image, 0 on padded rows
+            row[j ^ swz] = (m * s.fb) + (x * s.fb) * 0.5;
             y = m;
         } else if (!ALLFAST && s.live) {
             // `size` is an argument of every call in the reference: with size_tv a new one each sample (double -> int)
@@ -138,7 +162,7 @@ __device__ __forceinline__ void dl_stage(DlVoice& s, double* row, const int tn, 
 // voice of the warp is in one of the two, the window runs those statements alone; otherwise the full state machine.
 template <int OSC, int FILT, int ENV, bool ALLFAST, int OUTMODE, bool MIX>
 __device__ __forceinline__ void dl_window(DlVoice& s, double* row, const int tn, const int t0, const BankArgs& a, const DelayArgs& d,
-                                          const size_t V, const size_t v, const int lane, const int gwarp, double* mixtile) {
+                                          const size_t V, const size_t v, const int lane, const int gwarp, double* mixtile, const int swz) {
     if (ENV) {
         const EnvRegs& e = s.er;
         const bool notrig = e.off <= t0 || e.on >= t0 + tn || e.on >= e.off;
@@ -146,11 +170,11 @@ __device__ __forceinline__ void dl_window(DlVoice& s, double* row, const int tn,
         const bool relmode = e.st == ENV_R && notrig;
         const bool susmode = e.st == ENV_H && e.holdcount >= e.holdtime && alltrig;
         if (!a.env_ar && __all_sync(kFull, relmode || susmode || !s.live)) {
-            dl_stage<OSC, FILT, ENV, ALLFAST, OUTMODE, MIX, true>(s, row, tn, t0, a, d, V, v, lane, gwarp, mixtile, relmode);
+            dl_stage<OSC, FILT, ENV, ALLFAST, OUTMODE, MIX, true>(s, row, tn, t0, a, d, V, v, lane, gwarp, mixtile, relmode, swz);
             return;
         }
     }
-    dl_stage<OSC, FILT, ENV, ALLFAST, OUTMODE, MIX, false>(s, row, tn, t0, a, d, V, v, lane, gwarp, mixtile, false);
+    dl_stage<OSC, FILT, ENV, ALLFAST, OUTMODE, MIX, false>(s, row, tn, t0, a, d, V, v, lane, gwarp, mixtile, false, swz);
 }
 
 template <int OSC, int FILT, int ENV, int OUTMODE, bool MIX>
@@ -162,8 +186,10 @@ __global__ void __launch_bounds__(kBankBlock) delay_bank_kernel(const BankArgs a
     const long long v = v0 + lane;
     const size_t V = (size_t)a.V;
 
-    extern __shared__ double smem[];
-    constexpr int per_warp = kDlStages * kStageDoubles + (MIX ? kMixDoubles : 0);
+    extern __shared__ __align__(128) double smem[];
+    __shared__ unsigned long long s_bar[kBankBlock / 32][kDlStages];     // one mbarrier per warp and stage (bulk loads)
+    constexpr int per_warp = kDlStages * kStageDoubles + (MIX ? kMixDoubles : 0);      // a multiple of 16 doubles: stages stay 128-byte aligned
+    static_assert((kStageDoubles * 8) % 128 == 0 && (per_warp * 8) % 128 == 0, "bulk copies need aligned stages");
     double* wsm = smem + (size_t)(threadIdx.x >> 5) * per_warp;
     double* mixtile = wsm + kDlStages * kStageDoubles;
 
@@ -211,52 +237,39 @@ __global__ void __launch_bounds__(kBankBlock) delay_bank_kernel(const BankArgs a
     const int sl = lane & (kDlT - 1), hv = lane >> kDlShift;        // slot within a window / which voice of a request
 
     if (uniform) {
-        // ---------------- all windows of the warp form one contiguous run of nlive * 128 B ----------------
+        // ---------------- all windows of the warp form one contiguous run of nlive * 128 B: one bulk copy each way ----------------
         const int nchunks = size0 >> kDlShift;
         int chunk = base0 >> kDlShift;
-        const int nreq = (nlive + kDlVoicesPerReq - 1) / kDlVoicesPerReq;
-        auto load_run = [&](double* buf, int c) {
-            // voice i = 2*q + hv of request q: global run + i*16 + slot, tile row i
-            const double* src = d.ring + ((size_t)c * V + (size_t)v0) * kDlChunk + (size_t)hv * kDlChunk + sl;
-            double* dst = buf + hv * kDlRow + sl;
-            if (nlive == 32) {           // full warp: 16 requests at compile-time offsets, no predicates
-#pragma unroll
-                for (int q = 0; q < 32 / kDlVoicesPerReq; ++q) cp_async8(dst + q * kDlVoicesPerReq * kDlRow, src + q * kDlVoicesPerReq * kDlChunk);
-                return;
-            }
-#pragma unroll 8
-            for (int q = 0; q < nreq; ++q)
-                if (kDlVoicesPerReq * q + hv < nlive) cp_async8(dst + q * kDlVoicesPerReq * kDlRow, src + (size_t)q * kDlVoicesPerReq * kDlChunk);
-        };
-        load_run(wsm, chunk);
-        cp_async_commit();
+        const unsigned bytes = (unsigned)nlive * (kDlChunk * 8u);
+        unsigned long long* bar = s_bar[threadIdx.x >> 5];
+        double* run = d.ring + (size_t)v0 * kDlChunk;                      // chunk c of this warp's voices starts at run + c * V * 16
+        if (lane == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); }
+        fence_proxy_async();                                                // the initialised barriers become visible to the copy engine
+        __syncwarp();
+        if (lane == 0) { mbar_expect_tx(&bar[0], bytes); bulk_g2s(wsm, run + (size_t)chunk * V * kDlChunk, bytes, &bar[0]); }
+        const int swz = lane & (kDlChunk - 1);
         for (int k = 0; k < nstages; ++k) {
-            double* buf = wsm + (k & 1) * kStageDoubles;
+            const int sidx = k & 1;
+            double* buf = wsm + sidx * kStageDoubles;
             const int t0 = k * kDlT;
             const int tn = min(kDlT, a.n_frames - t0);
             int next_chunk = chunk + 1;
             if (next_chunk >= nchunks) next_chunk = 0;
-            if (k + 1 < nstages) load_run(wsm + ((k + 1) & 1) * kStageDoubles, next_chunk);
-            cp_async_commit();
-            cp_async_wait1();          // everything but the newest group has landed: window k is in smem
-            __syncwarp();
-            dl_window<OSC, FILT, ENV, true, OUTMODE, MIX>(s, buf + lane * kDlRow, tn, t0, a, d, V, (size_t)vv, lane, gwarp, mixtile);
-            __syncwarp();
-            if (nlive == 32 && tn == kDlT) {
-                double* dstg = d.ring + ((size_t)chunk * V + (size_t)v0) * kDlChunk + (size_t)hv * kDlChunk + sl;
-                const double* srcs = buf + hv * kDlRow + sl;
-#pragma unroll
-                for (int q = 0; q < 32 / kDlVoicesPerReq; ++q) dstg[q * kDlVoicesPerReq * kDlChunk] = srcs[q * kDlVoicesPerReq * kDlRow];
-            } else if (sl < tn) {
-                double* dstg = d.ring + ((size_t)chunk * V + (size_t)v0) * kDlChunk + (size_t)hv * kDlChunk + sl;
-                const double* srcs = buf + hv * kDlRow + sl;
-#pragma unroll 8
-                for (int q = 0; q < nreq; ++q)
-                    if (kDlVoicesPerReq * q + hv < nlive) dstg[(size_t)q * kDlVoicesPerReq * kDlChunk] = srcs[q * kDlVoicesPerReq * kDlRow];
+            if (k + 1 < nstages && lane == 0) {
+                // the other stage still feeds the write-back of window k-1: wait until the engine has READ it (a ring of two chunks
+                // also needs that write-back performed: the next window is the very chunk it writes)
+                if (nchunks < 3) bulk_wait_all(); else bulk_wait_read0();
+                mbar_expect_tx(&bar[sidx ^ 1], bytes);
+                bulk_g2s(wsm + (sidx ^ 1) * kStageDoubles, run + (size_t)next_chunk * V * kDlChunk, bytes, &bar[sidx ^ 1]);
             }
+            mbar_wait(&bar[sidx], (unsigned)(k >> 1) & 1u);                 // window k has landed
+            dl_window<OSC, FILT, ENV, true, OUTMODE, MIX>(s, buf + lane * kDlChunk, tn, t0, a, d, V, (size_t)vv, lane, gwarp, mixtile, swz);
+            fence_proxy_async();                                            // this lane's updates of the window, ordered before the engine reads them
             __syncwarp();
+            if (lane == 0) { bulk_s2g(run + (size_t)chunk * V * kDlChunk, buf, bytes); bulk_commit(); }
             chunk = next_chunk;
         }
+        if (lane == 0) bulk_wait_all();
         // phase += 1 after the last access: the window of the last stage started at slot 16*last_chunk
         if (s.live) {
             int last_chunk = (base0 >> kDlShift) + (nstages - 1);
@@ -291,7 +304,7 @@ __global__ void __launch_bounds__(kBankBlock) delay_bank_kernel(const BankArgs a
             cp_async_commit();
             cp_async_wait1();
             __syncwarp();
-            dl_window<OSC, FILT, ENV, false, OUTMODE, MIX>(s, buf + lane * kDlRow, tn, t0, a, d, V, (size_t)vv, lane, gwarp, mixtile);
+            dl_window<OSC, FILT, ENV, false, OUTMODE, MIX>(s, buf + lane * kDlRow, tn, t0, a, d, V, (size_t)vv, lane, gwarp, mixtile, 0);
             __syncwarp();
 #pragma unroll 4
             for (int q = 0; q < 32 / kDlVoicesPerReq; ++q) {

@@ -8,12 +8,15 @@ namespace mxb {
 constexpr int kDlShift = 4;
 constexpr int kDlChunk = 1 << kDlShift;     // ring slots per chunk = time steps per staged window (16)
 
-// Ring storage is chunk-interleaved: slot r of voice v lives at ((r / 16) * V + v) * 16 + r % 16.
+// Ring storage is chunk-interleaved and swizzled: slot r of voice v lives at ((r / 16) * V + v) * 16 + ((r % 16) ^ (v % 16)).
 // A voice's 16-slot chunk is 128 contiguous bytes (4 full sectors whatever its phase), and voices whose
 // ring indices run in step -- the common case: same size, started together -- read and write one
-// contiguous run of 32 * 128 B per warp and stage, i.e. streaming DRAM access.
+// contiguous run of 32 * 128 B per warp and stage: ONE bulk copy (cp.async.bulk, the TMA engine) in each direction moves a
+// warp's window between HBM and shared memory. The XOR with the voice index is what makes the image that lands in shared
+// memory usable as it is: lane v reads slot j of its row at position j ^ (v % 16), so the 16 lanes of a half-warp hit 16
+// different 8-byte bank pairs -- conflict-free without padding, which a bulk copy could not produce.
 __host__ __device__ inline size_t dl_slot(size_t V, size_t v, int r) {
-    return (((size_t)(r >> kDlShift)) * V + v) * kDlChunk + (size_t)(r & (kDlChunk - 1));
+    return (((size_t)(r >> kDlShift)) * V + v) * kDlChunk + (size_t)((r ^ (int)v) & (kDlChunk - 1));
 }
 inline size_t dl_ring_doubles(size_t V, int taps) { return (size_t)((taps + kDlChunk - 1) / kDlChunk) * kDlChunk * V; }
 

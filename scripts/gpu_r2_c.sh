@@ -1,7 +1,11 @@
 # round 2, run C: STFT stream kernel v2 (group barriers, fragment-ordered DCT, vector tail, uniform mel loop)
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_spectral.py tests/test_cpp_dropin.py tests/test_gpu_patch.py -m gpu -q > gpurun_out/c_pytest.log 2>&1; grep -E "^(FAILED|ERROR)" gpurun_out/c_pytest.log | head -30; tail -3 gpurun_out/c_pytest.log
+timeout 1500 python -m pytest tests -m gpu -q > gpurun_out/c_pytest.log 2>&1; grep -E "^(FAILED|ERROR)" gpurun_out/c_pytest.log | head -30; tail -3 gpurun_out/c_pytest.log
 timeout 300 python bench.py --workload mfcc --steps 30 --warmup 5 --no-cpu > gpurun_out/c_bench_mfcc.json 2> gpurun_out/c_bench_mfcc.err; echo "bench rc=$?"; tail -c 400 gpurun_out/c_bench_mfcc.err
 python -c "
 import json; d=json.loads(open('gpurun_out/c_bench_mfcc.json').read().strip().splitlines()[-1]); print('mfcc', d['value'], d['roofline']['frac'], 'e2e', d['e2e']['value'])"
+timeout 300 python bench.py --workload delay --steps 40 --warmup 5 --no-cpu > gpurun_out/c_bench_delay.json 2> gpurun_out/c_bench_delay.err; echo "delay rc=$?"; tail -c 300 gpurun_out/c_bench_delay.err
+python -c "
+import json; d=json.loads(open('gpurun_out/c_bench_delay.json').read().strip().splitlines()[-1]); print('delay', d['value'], d['roofline']['frac'], 'e2e', d['e2e']['value'])"
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:delay_bank_kernel -s 3 -c 1 -f -o gpurun_out/prof_r02_delay_bulk python bench.py --workload delay --steps 3 --warmup 3 --no-cpu > /dev/null 2>&1; echo ncu-delay rc=$?
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:stft_stream -s 3 -c 1 -f -o gpurun_out/prof_r02_stft_stream_v2 python bench.py --workload mfcc --steps 3 --warmup 3 --no-cpu > /dev/null 2>&1; echo ncu rc=$?
