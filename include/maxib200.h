@@ -202,7 +202,7 @@ int32_t mxb_bank_process(mxb_bank* bank, int32_t n_frames,
  * gates live in; NULL = the block-constant MXB_P_FREQ). The reference takes the frequency by argument on every
  * sample, so a patch may modulate it at audio rate -- FM: osc.sinewave(440 + lfo.sinewave(1)*100),
  * cpp/commandline/maximilian_examples/5.FM1/main.cpp:29. Costs one 8-byte read per voice-sample. Built for
- * oscillator -> [filter] -> out / mix chains; with an envelope or delay stage it returns MXB_ERR_UNSUPPORTED. */
+ * oscillator -> [envelope] -> [filter] -> out / mix chains; with a delay stage it returns MXB_ERR_UNSUPPORTED (use a voice patch). */
 int32_t mxb_bank_process_fm(mxb_bank* bank, int32_t n_frames, const double* freq_tv,
                             const int32_t* trig_on, const int32_t* trig_off,
                             void* out, int32_t out_dtype, double* mix,
@@ -212,7 +212,7 @@ int32_t mxb_bank_process_fm(mxb_bank* bank, int32_t n_frames, const double* freq
  * play() on every sample (src/maximilian.h:1287-1290): a swept filter. The coefficient design (cos/sqrt/pow, tan) then
  * runs per sample on the device -- libdevice instead of glibc, so results agree to rounding of those functions (asserted
  * at 1e-9 relative) instead of bit for bit. The modulation lasts for this call; MXB_P_CUTOFF is in force again afterwards.
- * maxiBiquad (whose set() is a design routine, not a per-sample argument), envelope and delay stages: MXB_ERR_UNSUPPORTED.
+ * maxiBiquad (whose set() is a design routine, not a per-sample argument) and delay stages: MXB_ERR_UNSUPPORTED (voice patches cover both).
  * delay_size_tv[t][v] (integral values, 1 .. delay_taps): the `size` argument of maxiDelayline::dl / dlFromPosition, which a
  * flanger or chorus changes on every call (maxiFlanger::flange, src/maximilian.h:1144-1180). Works on any chain with a
  * delay stage (not together with freq_tv / cutoff_tv); the ring is then addressed slot by slot in HBM (the staged-window
@@ -221,11 +221,18 @@ typedef struct {
     const double* freq_tv;        /* [n_frames][voices] or NULL */
     const double* cutoff_tv;      /* [n_frames][voices] or NULL */
     const double* delay_size_tv;  /* [n_frames][voices] or NULL */
+    const uint8_t* trig_tv;       /* [n_frames][voices] bytes or NULL: maxiEnv::trigger for EVERY sample (1 = note on), in place of the
+                                     trig_on / trig_off interval -- the trigger is a public int a patch writes at any sample
+                                     (src/maximilian.h:913, maximilian_examples/10.Filters/main.cpp:27-36): several notes per block */
 } mxb_modulation;
 int32_t mxb_bank_process_mod(mxb_bank* bank, int32_t n_frames, const mxb_modulation* mod,
                              const int32_t* trig_on, const int32_t* trig_off,
                              void* out, int32_t out_dtype, double* mix,
                              int32_t mem, void* stream);
+/* Block-dispatch shim, the counterpart of routing() in cpp/commandline/player.cpp:25-44 (RtAudio callback): fills the driver's
+ * interleaved RTAUDIO_FLOAT64 buffer interleaved_out[n_frames][channels] (host memory) with the next block of the bank's
+ * stereo bus (channels 0 / 1; further channels silent; one channel: the left bus). Synchronous, trigger 0. */
+int32_t mxb_play_block(mxb_bank* bank, double* interleaved_out, int32_t n_frames, int32_t channels);
 /* kernels launched by this library on behalf of `bank` since creation (for bench.py's gpu_launches) */
 int64_t mxb_bank_launch_count(const mxb_bank* bank);
 

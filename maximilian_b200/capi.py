@@ -25,7 +25,7 @@ EXPORTS = [
     "mxb_last_error", "mxb_version", "mxb_ctx_create", "mxb_ctx_destroy", "mxb_ctx_sample_rate",
     "mxb_ctx_synchronize", "mxb_host_alloc", "mxb_host_free",
     "mxb_bank_create", "mxb_bank_destroy", "mxb_bank_voices", "mxb_bank_set_param", "mxb_bank_set_param_async", "mxb_bank_get_state",
-    "mxb_bank_get_ring", "mxb_bank_set_state", "mxb_bank_set_ring", "mxb_bank_clone", "mxb_bank_process", "mxb_bank_process_fm", "mxb_bank_process_mod", "mxb_bank_launch_count", "mxb_env_coeffs",
+    "mxb_bank_get_ring", "mxb_bank_set_state", "mxb_bank_set_ring", "mxb_bank_clone", "mxb_bank_process", "mxb_bank_process_fm", "mxb_bank_process_mod", "mxb_play_block", "mxb_bank_launch_count", "mxb_env_coeffs",
     "mxb_exchange_create", "mxb_exchange_local_handle", "mxb_exchange_connect", "mxb_exchange_status", "mxb_exchange_destroy", "mxb_bank_set_exchange",
     "mxb_stft_create", "mxb_stft_destroy", "mxb_stft_process", "mxb_stft_process2", "mxb_stft_launch_count",
     "mxb_mfcc_create", "mxb_mfcc_destroy", "mxb_mfcc_process",
@@ -47,7 +47,7 @@ class BankDesc(C.Structure):
 
 
 class Modulation(C.Structure):
-    _fields_ = [("freq_tv", C.c_void_p), ("cutoff_tv", C.c_void_p), ("delay_size_tv", C.c_void_p)]
+    _fields_ = [("freq_tv", C.c_void_p), ("cutoff_tv", C.c_void_p), ("delay_size_tv", C.c_void_p), ("trig_tv", C.c_void_p)]
 
 
 class StftOutputs(C.Structure):
@@ -95,6 +95,7 @@ def lib():
         "mxb_bank_process": (i32, [vp, i32, vp, vp, vp, i32, vp, i32, vp]),
         "mxb_bank_process_fm": (i32, [vp, i32, vp, vp, vp, vp, i32, vp, i32, vp]),
         "mxb_bank_process_mod": (i32, [vp, i32, C.POINTER(Modulation), vp, vp, vp, i32, vp, i32, vp]),
+        "mxb_play_block": (i32, [vp, vp, i32, i32]),
         "mxb_bank_launch_count": (i64, [vp]),
         "mxb_env_coeffs": (i32, [i32, vp, i64, i32, vp]),
         "mxb_exchange_create": (i32, [vp, i32, i32, i32, pp]),
@@ -249,18 +250,20 @@ class Bank:
 
     # -- one block ---------------------------------------------------------------------------
     def process(self, nframes, trig_on=None, trig_off=None, want_out=True, want_mix=False, out_dtype=np.float64,
-                out=None, mix=None, freq_tv=None, cutoff_tv=None, delay_size_tv=None):
+                out=None, mix=None, freq_tv=None, cutoff_tv=None, delay_size_tv=None, trig_tv=None):
         """Host buffers in, host buffers out (MXB_MEM_HOST). Returns (out[nframes][V] | None, mix[nframes][2] | None).
         freq_tv / cutoff_tv / delay_size_tv: optional per-sample oscillator frequency / filter cutoff / delay size [nframes][V]
         (mxb_bank_process_mod)."""
-        if freq_tv is not None or cutoff_tv is not None or delay_size_tv is not None:
+        if freq_tv is not None or cutoff_tv is not None or delay_size_tv is not None or trig_tv is not None:
+            tv = np.ascontiguousarray(trig_tv, dtype=np.uint8) if trig_tv is not None else None
+            assert tv is None or tv.shape == (nframes, self.V)
             f = np.ascontiguousarray(freq_tv, dtype=np.float64) if freq_tv is not None else None
             cu = np.ascontiguousarray(cutoff_tv, dtype=np.float64) if cutoff_tv is not None else None
             assert f is None or f.shape == (nframes, self.V)
             assert cu is None or cu.shape == (nframes, self.V)
             ds = np.ascontiguousarray(delay_size_tv, dtype=np.float64) if delay_size_tv is not None else None
             assert ds is None or ds.shape == (nframes, self.V)
-            mod = Modulation(_np_ptr(f), _np_ptr(cu), _np_ptr(ds))
+            mod = Modulation(_np_ptr(f), _np_ptr(cu), _np_ptr(ds), _np_ptr(tv))
             f32 = np.dtype(out_dtype) == np.float32
             if want_out and out is None:
                 out = np.empty((nframes, self.V), dtype=np.float32 if f32 else np.float64)
@@ -283,6 +286,12 @@ class Bank:
                                      F32 if f32 else F64, _np_ptr(mix if want_mix else None), MEM_HOST, None),
               "mxb_bank_process")
         return (out if want_out else None), (mix if want_mix else None)
+
+    def play_block(self, nframes, channels=2):
+        """mxb_play_block: the interleaved buffer an audio callback would hand to the driver."""
+        buf = np.empty((nframes, channels), dtype=np.float64)
+        check(lib().mxb_play_block(self.h, _np_ptr(buf), nframes, channels), "mxb_play_block")
+        return buf
 
     def process_device(self, nframes, out_ptr=None, mix_ptr=None, trig_on_ptr=None, trig_off_ptr=None,
                        f32=False, stream=0):

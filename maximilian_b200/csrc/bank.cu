@@ -43,6 +43,7 @@ struct mxb_bank {
     double* fm_stage; size_t fm_stage_bytes; // staging for host-resident per-sample frequencies
     double* cm_stage; size_t cm_stage_bytes; // ... and cutoffs
     double* ds_stage; size_t ds_stage_bytes; // ... and delay sizes
+    unsigned char* tv_stage; size_t tv_stage_bytes;   // ... and per-sample triggers
     int64_t launches;
     mxb_exchange* ex;                        // peer-memory mix exchange (multi-GPU), or NULL
 };
@@ -191,7 +192,7 @@ int free_bank(mxb_bank* b) {
     for (int i = 0; i < 5; ++i) cudaFree(b->cf[i]);
     cudaFree(b->env_amp); cudaFree(b->env_output); cudaFree(b->env_holdcount); cudaFree(b->env_hold); cudaFree(b->env_flags);
     cudaFree(b->trig_on); cudaFree(b->trig_off); cudaFree(b->dl_phase); cudaFree(b->dl_size); cudaFree(b->dl_pos); cudaFree(b->ring);
-    cudaFree(b->partials); cudaFree(b->mix_dev); cudaFree(b->out_stage); cudaFree(b->fm_stage); cudaFree(b->cm_stage); cudaFree(b->ds_stage);
+    cudaFree(b->partials); cudaFree(b->mix_dev); cudaFree(b->out_stage); cudaFree(b->fm_stage); cudaFree(b->cm_stage); cudaFree(b->ds_stage); cudaFree(b->tv_stage);
     delete b;
     return MXB_OK;
 }
@@ -236,6 +237,7 @@ int32_t mxb_bank_create(mxb_ctx* ctx, const mxb_bank_desc* d, mxb_bank** out) {
     b->fm_stage = nullptr; b->fm_stage_bytes = 0;
     b->cm_stage = nullptr; b->cm_stage_bytes = 0;
     b->ds_stage = nullptr; b->ds_stage_bytes = 0;
+    b->tv_stage = nullptr; b->tv_stage_bytes = 0;
     const size_t V = (size_t)d->voices;
     int rc = MXB_OK;
 #define TRY(x) do { rc = (x); if (rc != MXB_OK) { free_bank(b); return rc; } } while (0)
@@ -531,7 +533,7 @@ int32_t mxb_bank_process(mxb_bank* b, int32_t n_frames, const int32_t* trig_on, 
 
 int32_t mxb_bank_process_fm(mxb_bank* b, int32_t n_frames, const double* freq_tv, const int32_t* trig_on, const int32_t* trig_off,
                             void* out, int32_t out_dtype, double* mix, int32_t mem, void* stream_) {
-    mxb_modulation m; m.freq_tv = freq_tv; m.cutoff_tv = nullptr; m.delay_size_tv = nullptr;
+    mxb_modulation m; m.freq_tv = freq_tv; m.cutoff_tv = nullptr; m.delay_size_tv = nullptr; m.trig_tv = nullptr;
     return mxb_bank_process_mod(b, n_frames, &m, trig_on, trig_off, out, out_dtype, mix, mem, stream_);
 }
 
@@ -541,6 +543,11 @@ int32_t mxb_bank_process_mod(mxb_bank* b, int32_t n_frames, const mxb_modulation
     const double* freq_tv = mod ? mod->freq_tv : nullptr;
     const double* cutoff_tv = mod ? mod->cutoff_tv : nullptr;
     const double* dsize_tv = mod ? mod->delay_size_tv : nullptr;
+    const uint8_t* trig_tv = mod ? mod->trig_tv : nullptr;
+    if (trig_tv) {
+        MXB_REQUIRE(b->desc.env_kind != MXB_ENV_NONE, MXB_ERR_INVALID, "mxb_bank_process_mod: trig_tv on a bank without an envelope stage");
+        MXB_REQUIRE(!trig_on && !trig_off, MXB_ERR_INVALID, "mxb_bank_process_mod: trig_tv replaces trig_on / trig_off (pass NULL for both)");
+    }
     MXB_REQUIRE(n_frames >= 0 && n_frames <= b->desc.max_frames, MXB_ERR_INVALID, "mxb_bank_process: n_frames %d (max_frames %d)", n_frames, b->desc.max_frames);
     const bool async_host = (mem & MXB_MEM_ASYNC) != 0;   // host buffers, but return as soon as everything is enqueued
     mem &= ~MXB_MEM_ASYNC;
@@ -567,9 +574,9 @@ int32_t mxb_bank_process_mod(mxb_bank* b, int32_t n_frames, const mxb_modulation
     const int* d_on = trig_on; const int* d_off = trig_off;
     void* d_out = out; double* d_mix = mix;
     if (freq_tv || cutoff_tv)
-        MXB_REQUIRE(b->desc.env_kind == MXB_ENV_NONE && b->desc.delay_taps == 0, MXB_ERR_UNSUPPORTED,
-                    "mxb_bank_process_mod: per-sample parameters are built for oscillator -> filter -> out/mix chains only "
-                    "(no envelope, no delay line)");
+        MXB_REQUIRE(b->desc.delay_taps == 0, MXB_ERR_UNSUPPORTED,
+                    "mxb_bank_process_mod: per-sample frequency / cutoff are built for oscillator -> [envelope] -> filter -> out/mix chains "
+                    "(a chain with a delay line: use a voice patch, mxb_patch_*)");
     if (cutoff_tv)
         MXB_REQUIRE(fk == MXB_FILT_LORES || fk == MXB_FILT_HIRES || fk == MXB_FILT_SVF, MXB_ERR_UNSUPPORTED,
                     "mxb_bank_process_mod: per-sample cutoff is built for lores / hires / maxiSVF");
@@ -596,6 +603,19 @@ int32_t mxb_bank_process_mod(mxb_bank* b, int32_t n_frames, const mxb_modulation
     { int rc0 = stage(cutoff_tv, &b->cm_stage, &b->cm_stage_bytes, &d_cm); if (rc0 != MXB_OK) return rc0; }
     const double* d_ds = nullptr;
     { int rc0 = stage(dsize_tv, &b->ds_stage, &b->ds_stage_bytes, &d_ds); if (rc0 != MXB_OK) return rc0; }
+    const unsigned char* d_tv = trig_tv;
+    if (trig_tv && host_ctl) {
+        const size_t need = (size_t)n_frames * V;
+        if (need > b->tv_stage_bytes) {
+            MXB_CUDA(cudaStreamSynchronize(s));
+            cudaFree(b->tv_stage); b->tv_stage = nullptr; b->tv_stage_bytes = 0;
+            cudaError_t e = cudaMalloc((void**)&b->tv_stage, need);
+            if (e != cudaSuccess) { set_error("mxb_bank_process_mod: staging cudaMalloc(%zu): %s", need, cudaGetErrorString(e)); return MXB_ERR_ALLOC; }
+            b->tv_stage_bytes = need;
+        }
+        MXB_CUDA(cudaMemcpyAsync(b->tv_stage, trig_tv, need, cudaMemcpyHostToDevice, s));
+        d_tv = b->tv_stage;
+    }
     if (host_ctl) {
         if (trig_on) {
             MXB_CUDA(cudaMemcpyAsync(b->trig_on, trig_on, sizeof(int) * V, cudaMemcpyHostToDevice, s));
@@ -652,7 +672,7 @@ int32_t mxb_bank_process_mod(mxb_bank* b, int32_t n_frames, const mxb_modulation
     a.env_sus = b->dp[MXB_P_ENV_SUSTAIN]; a.env_rel = b->dp[MXB_P_ENV_RELEASE];
     a.env_hold = b->env_hold; a.env_amp = b->env_amp; a.env_output = b->env_output;
     a.env_holdcount = b->env_holdcount; a.env_flags = b->env_flags;
-    a.trig_on = d_on; a.trig_off = d_off;
+    a.trig_on = d_on; a.trig_off = d_off; a.trig_tv = d_tv;
     a.out = d_out; a.pan = b->dp[MXB_P_PAN]; a.partials = b->partials;
 
     int osc_t = OSC_T_GENERIC;
@@ -716,6 +736,21 @@ int32_t mxb_bank_process_mod(mxb_bank* b, int32_t n_frames, const mxb_modulation
             MXB_REQUIRE(m == 0, MXB_ERR_STATE, "mxb_bank_process: mix exchange timed out waiting for rank mask 0x%x (bus incomplete)", m);
         }
     }
+    return MXB_OK;
+}
+
+// The block-dispatch shim: what routing() does for a reference patch (cpp/commandline/player.cpp:25-44) -- fill the audio
+// driver's interleaved RTAUDIO_FLOAT64 buffer [n_frames][channels] with the next block: the bank's stereo bus goes to channels
+// 0 and 1 (a mono device gets the left bus), further channels are silent.
+int32_t mxb_play_block(mxb_bank* b, double* interleaved_out, int32_t n_frames, int32_t channels) {
+    MXB_REQUIRE(b && interleaved_out, MXB_ERR_INVALID, "mxb_play_block: NULL argument");
+    MXB_REQUIRE(channels >= 1 && n_frames >= 0, MXB_ERR_INVALID, "mxb_play_block: channels %d n_frames %d", channels, n_frames);
+    if (channels == 2) return mxb_bank_process(b, n_frames, nullptr, nullptr, nullptr, MXB_F64, interleaved_out, MXB_MEM_HOST, nullptr);
+    std::vector<double> bus((size_t)n_frames * 2);
+    int rc = mxb_bank_process(b, n_frames, nullptr, nullptr, nullptr, MXB_F64, bus.data(), MXB_MEM_HOST, nullptr);
+    if (rc != MXB_OK) return rc;
+    for (int t = 0; t < n_frames; ++t)
+        for (int c = 0; c < channels; ++c) interleaved_out[(size_t)t * channels + c] = c < 2 ? bus[(size_t)t * 2 + c] : 0.0;
     return MXB_OK;
 }
 

@@ -11,8 +11,8 @@
 //                 on an mbarrier, in flight while window k is computed; generic schedule: 16 cp.async requests, two voices
 //                 each (warp-private tiles, no __syncthreads anywhere)
 //   compute k:    lane = voice; 16 steps of the chain, ring slot j of the window read and updated in smem
-//                 (uniform: rows of 16 doubles, slot j at position j ^ (lane % 16) -- the swizzle of the HBM layout;
-//                 generic: row stride 17 doubles; both conflict-free for 64-bit accesses)
+//                 (rows of 16 doubles, slot j at position j ^ (lane % 16) -- the swizzle of the HBM layout, so the uniform
+//                 schedule's bulk image and the generic schedule's per-slot staging look the same: conflict-free for 64-bit accesses)
 //   write-back:   uniform: one bulk copy smem -> HBM (cp.async.bulk.global.shared, bulk group); generic: per-slot stores
 //
 // History (profiles/r01_delay_kernel_v*.txt): 32-slot windows double-buffered = 12 warps/SM, issue-starved (0.47-0.69 of
@@ -36,8 +36,11 @@
 namespace mxb {
 
 constexpr int kDlT = kDlChunk;                    // steps per staged window
-constexpr int kDlRow = kDlT + 1;                  // tile row stride in doubles
-constexpr int kStageDoubles = 32 * kDlRow;        // one staged window tile per warp
+constexpr int kDlRow = kDlT;                      // tile row stride in doubles: unpadded, slot j of row i at position j ^ (i % 16)
+constexpr int kStageDoubles = 32 * kDlRow;        // one staged window tile per warp (4 KB: the image one bulk copy moves)
+// CTA shape of K2. Without a mix tile a warp needs 8 KB of staging: 14 warps per CTA, 2 CTAs per SM = 28 warps/SM, and 256 Ki
+// voices (8192 voice-warps over 148 SMs) run as two full waves. With the mix tile (12.9 KB per warp): 4 warps per CTA.
+template <bool MIX> struct DelayShape { static constexpr int kThreads = MIX ? 128 : 448; };
 constexpr int kDlStages = 2;                      // double buffer
 constexpr int kDlVoicesPerReq = 32 / kDlT;        // voices covered by one cooperative request (2)
 constexpr int kMixDoubles = 2 * kMixTT * 33;
@@ -102,14 +105,14 @@ __device__ __forceinline__ void dl_stage(DlVoice& s, double* row, const int tn, 
             else s.er.output = x * s.er.amp;
             x = s.er.output;
         } else if (ENV) {
-            const bool trig = t >= s.er.on && t < s.er.off;
+            const bool trig = a.trig_tv ? (s.live && a.trig_tv[(size_t)t * V + v] == 1) : (t >= s.er.on && t < s.er.off);
             x = a.env_ar ? env_ar_tick(s.er, x, trig) : env_tick(s.er, x, trig);
         }
         x = filt_tick<FILT>(s.fr, x, a.svf_mix);
         // maxiDelayline::dl, src/maximilian.cpp:420-429
         double y = 0.0;
         if (ALLFAST ? s.live : s.fast) {          // lanes past the end of the bank contribute an exact 0
-            const double m = row[j ^ swz];             // swz: lane % 16 on the bulk-copied (swizzled) image, 0 on padded rows
+            const double m = row[j ^ swz];             // swz = lane % 16: the swizzle of the staged image (and of the HBM layout)
             row[j ^ swz] = (m * s.fb) + (x * s.fb) * 0.5;
             y = m;
         } else if (!ALLFAST && s.live) {
@@ -169,7 +172,7 @@ __device__ __forceinline__ void dl_window(DlVoice& s, double* row, const int tn,
         const bool alltrig = e.on <= t0 && e.off >= t0 + tn;
         const bool relmode = e.st == ENV_R && notrig;
         const bool susmode = e.st == ENV_H && e.holdcount >= e.holdtime && alltrig;
-        if (!a.env_ar && __all_sync(kFull, relmode || susmode || !s.live)) {
+        if (!a.env_ar && !a.trig_tv && __all_sync(kFull, relmode || susmode || !s.live)) {
             dl_stage<OSC, FILT, ENV, ALLFAST, OUTMODE, MIX, true>(s, row, tn, t0, a, d, V, v, lane, gwarp, mixtile, relmode, swz);
             return;
         }
@@ -178,7 +181,7 @@ __device__ __forceinline__ void dl_window(DlVoice& s, double* row, const int tn,
 }
 
 template <int OSC, int FILT, int ENV, int OUTMODE, bool MIX>
-__global__ void __launch_bounds__(kBankBlock) delay_bank_kernel(const BankArgs a, const DelayArgs d) {
+__global__ void __launch_bounds__(DelayShape<MIX>::kThreads) delay_bank_kernel(const BankArgs a, const DelayArgs d) {
     const int lane = threadIdx.x & 31;
     const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long v0 = (long long)gwarp * 32;
@@ -187,7 +190,7 @@ __global__ void __launch_bounds__(kBankBlock) delay_bank_kernel(const BankArgs a
     const size_t V = (size_t)a.V;
 
     extern __shared__ __align__(128) double smem[];
-    __shared__ unsigned long long s_bar[kBankBlock / 32][kDlStages];     // one mbarrier per warp and stage (bulk loads)
+    __shared__ unsigned long long s_bar[DelayShape<MIX>::kThreads / 32][kDlStages];     // one mbarrier per warp and stage (bulk loads)
     constexpr int per_warp = kDlStages * kStageDoubles + (MIX ? kMixDoubles : 0);      // a multiple of 16 doubles: stages stay 128-byte aligned
     static_assert((kStageDoubles * 8) % 128 == 0 && (per_warp * 8) % 128 == 0, "bulk copies need aligned stages");
     double* wsm = smem + (size_t)(threadIdx.x >> 5) * per_warp;
@@ -289,7 +292,7 @@ __global__ void __launch_bounds__(kBankBlock) delay_bank_kernel(const BankArgs a
                 if (!f_i) continue;
                 int r = b_i + sl;
                 if (r >= s_i) r -= s_i;
-                cp_async8(buf + i * kDlRow + sl, d.ring + dl_slot(V, (size_t)(v0 + i), r));
+                cp_async8(buf + i * kDlRow + (sl ^ (i & (kDlT - 1))), d.ring + dl_slot(V, (size_t)(v0 + i), r));
             }
         };
         issue_loads(wsm, base);
@@ -304,7 +307,7 @@ __global__ void __launch_bounds__(kBankBlock) delay_bank_kernel(const BankArgs a
             cp_async_commit();
             cp_async_wait1();
             __syncwarp();
-            dl_window<OSC, FILT, ENV, false, OUTMODE, MIX>(s, buf + lane * kDlRow, tn, t0, a, d, V, (size_t)vv, lane, gwarp, mixtile, 0);
+            dl_window<OSC, FILT, ENV, false, OUTMODE, MIX>(s, buf + lane * kDlRow, tn, t0, a, d, V, (size_t)vv, lane, gwarp, mixtile, lane & (kDlT - 1));
             __syncwarp();
 #pragma unroll 4
             for (int q = 0; q < 32 / kDlVoicesPerReq; ++q) {
@@ -315,7 +318,7 @@ __global__ void __launch_bounds__(kBankBlock) delay_bank_kernel(const BankArgs a
                 if (f_i && sl < tn) {
                     int r = b_i + sl;
                     if (r >= s_i) r -= s_i;
-                    d.ring[dl_slot(V, (size_t)(v0 + i), r)] = buf[i * kDlRow + sl];
+                    d.ring[dl_slot(V, (size_t)(v0 + i), r)] = buf[i * kDlRow + (sl ^ (i & (kDlT - 1)))];
                 }
             }
             __syncwarp();
@@ -342,11 +345,13 @@ __global__ void __launch_bounds__(kBankBlock) delay_bank_kernel(const BankArgs a
 
 template <int OSC, int FILT, int ENV, int OUTMODE, bool MIX>
 inline int launch_delay_one(const BankArgs& a, const DelayArgs& d, int grid, cudaStream_t s) {
-    constexpr size_t smem = sizeof(double) * (kBankBlock / 32) * (kDlStages * kStageDoubles + (MIX ? kMixDoubles : 0));
+    constexpr int threads = DelayShape<MIX>::kThreads;
+    constexpr size_t smem = sizeof(double) * (threads / 32) * (kDlStages * kStageDoubles + (MIX ? kMixDoubles : 0));
+    grid = (a.V + threads - 1) / threads;
     auto kern = delay_bank_kernel<OSC, FILT, ENV, OUTMODE, MIX>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { set_error("delay_bank_kernel smem attribute (%zu B): %s", smem, cudaGetErrorString(e)); return MXB_ERR_CUDA; }
-    kern<<<grid, kBankBlock, smem, s>>>(a, d);
+    kern<<<grid, threads, smem, s>>>(a, d);
     e = cudaGetLastError();
     if (e != cudaSuccess) { set_error("delay_bank_kernel launch: %s", cudaGetErrorString(e)); return MXB_ERR_CUDA; }
     return MXB_OK;

@@ -106,6 +106,9 @@ int32_t mxo_bank_process_fm(void* bank, int32_t nframes, const double* freq_tv, 
  * chorus changes on every call (src/maximilian.cpp:420,431; maxiFlanger::flange, src/maximilian.h:1144-1180). */
 int32_t mxo_bank_process_mod(void* bank, int32_t nframes, const double* freq_tv, const double* cutoff_tv, const double* delay_size_tv,
                              const int32_t* trig_on, const int32_t* trig_off, double* out, double* mix, int32_t first, int32_t count);
+/* ... and with maxiEnv::trigger given for every sample: trig_tv[t][v] bytes (NULL = the trig_on / trig_off interval) */
+int32_t mxo_bank_process_mod2(void* bank, int32_t nframes, const double* freq_tv, const double* cutoff_tv, const double* delay_size_tv,
+                              const uint8_t* trig_tv, const int32_t* trig_on, const int32_t* trig_off, double* out, double* mix, int32_t first, int32_t count);
 /* copies ring slots [0, n) of voice v */
 int32_t mxo_bank_get_ring(void* bank, int32_t v, double* dst, int32_t n);
 

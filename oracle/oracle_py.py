@@ -72,6 +72,7 @@ def load(kind="port"):
         "mxo_bank_process": (i32, [vp, i32, ip, ip, dp, dp, i32, i32]),
         "mxo_bank_process_fm": (i32, [vp, i32, dp, ip, ip, dp, dp, i32, i32]),
         "mxo_bank_process_mod": (i32, [vp, i32, dp, dp, dp, ip, ip, dp, dp, i32, i32]),
+        "mxo_bank_process_mod2": (i32, [vp, i32, dp, dp, dp, C.POINTER(C.c_uint8), ip, ip, dp, dp, i32, i32]),
         "mxo_bank_get_ring": (i32, [vp, i32, dp, i32]),
         "mxo_env_attack_coeff": (C.c_double, [C.c_double, i32]),
         "mxo_env_attack_ms_coeff": (C.c_double, [C.c_double, i32]),
@@ -154,13 +155,24 @@ class Bank:
         return a
 
     def process(self, nframes, trig_on=None, trig_off=None, want_out=True, want_mix=False, threads=1, out=None, freq_tv=None,
-                cutoff_tv=None, delay_size_tv=None):
+                cutoff_tv=None, delay_size_tv=None, trig_tv=None):
         """Returns (out[nframes][V] or None, mix[nframes][2] or None). `out` may be a preallocated buffer.
         freq_tv / cutoff_tv / delay_size_tv: optional per-sample oscillator frequency / filter cutoff / delay size [nframes][V]."""
         if want_out and out is None:
             out = np.empty((nframes, self.V), dtype=np.float64)
         if not want_out:
             out = None
+        if trig_tv is not None:
+            tv = np.ascontiguousarray(trig_tv, dtype=np.uint8)
+            assert tv.shape == (nframes, self.V) and trig_on is None
+            f = np.ascontiguousarray(freq_tv, dtype=np.float64) if freq_tv is not None else None
+            cu = np.ascontiguousarray(cutoff_tv, dtype=np.float64) if cutoff_tv is not None else None
+            mix = np.empty((nframes, 2), dtype=np.float64) if want_mix else None
+            rc = self.lib.mxo_bank_process_mod2(self.h, nframes, _dp(f), _dp(cu), None, tv.ctypes.data_as(C.POINTER(C.c_uint8)), None, None,
+                                                _dp(out), _dp(mix), 0, self.V)
+            if rc:
+                raise RuntimeError(f"mxo_bank_process_mod2 -> {rc}")
+            return out, mix
         if freq_tv is not None or cutoff_tv is not None or delay_size_tv is not None:
             f = np.ascontiguousarray(freq_tv, dtype=np.float64) if freq_tv is not None else None
             cu = np.ascontiguousarray(cutoff_tv, dtype=np.float64) if cutoff_tv is not None else None

@@ -208,6 +208,13 @@ int32_t mxo_bank_process_fm(void* h, int32_t nframes, const double* freq_tv, con
 
 int32_t mxo_bank_process_mod(void* h, int32_t nframes, const double* freq_tv, const double* cutoff_tv, const double* delay_size_tv,
                              const int32_t* trig_on, const int32_t* trig_off, double* out, double* mix, int32_t first, int32_t count) {
+    return mxo_bank_process_mod2(h, nframes, freq_tv, cutoff_tv, delay_size_tv, nullptr, trig_on, trig_off, out, mix, first, count);
+}
+
+/* ... and with the envelope's trigger given for every sample: trig_tv[t][v] bytes, maxiEnv::trigger as the patch sets it before each
+ * call (src/maximilian.h:913; cpp/commandline/maximilian_examples/10.Filters/main.cpp:27-36) */
+int32_t mxo_bank_process_mod2(void* h, int32_t nframes, const double* freq_tv, const double* cutoff_tv, const double* delay_size_tv,
+                              const uint8_t* trig_tv, const int32_t* trig_on, const int32_t* trig_off, double* out, double* mix, int32_t first, int32_t count) {
     RefBank* b = (RefBank*)h;
     if (!b || nframes < 0 || first < 0 || count < 0 || first + count > b->V) return -1;
     const mxo_chain& c = b->chain;
@@ -230,10 +237,10 @@ int32_t mxo_bank_process_mod(void* h, int32_t nframes, const double* freq_tv, co
             double x = run_osc(r.osc, c.osc_kind, freq_tv ? freq_tv[(size_t)t * V + v] : freq[v], duty[v],
                                b->p[MXO_P_PHASOR_START][v], b->p[MXO_P_PHASOR_END][v]);
             if (c.env_kind == MXO_ENV_ADSR) {
-                int trig = (trig_on && trig_off && t >= trig_on[v] && t < trig_off[v]) ? 1 : 0;
+                int trig = trig_tv ? (int)trig_tv[(size_t)t * (size_t)V + (size_t)v] : (trig_on && trig_off && t >= trig_on[v] && t < trig_off[v]) ? 1 : 0;
                 x = r.env.adsr(x, trig);
             } else if (c.env_kind == MXO_ENV_AR) {
-                int trig = (trig_on && trig_off && t >= trig_on[v] && t < trig_off[v]) ? 1 : 0;
+                int trig = trig_tv ? (int)trig_tv[(size_t)t * (size_t)V + (size_t)v] : (trig_on && trig_off && t >= trig_on[v] && t < trig_off[v]) ? 1 : 0;
                 x = r.env.ar(x, b->p[MXO_P_ENV_ATTACK][v], b->p[MXO_P_ENV_RELEASE][v], (long)b->p[MXO_P_ENV_HOLDTIME][v], trig);
             }
             switch (c.filt_kind) {

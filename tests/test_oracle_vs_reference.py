@@ -378,3 +378,22 @@ def test_bark_port_equals_reference(port, reference, sr, bs):
     for u, v in zip(pa, pb):
         assert np.array_equal(u, v, equal_nan=True)
     assert np.all(pa[1].max(axis=-1) == 1.0)
+
+
+@pytest.mark.parametrize("filt,delay,env", [("none", False, "adsr"), ("lores", False, "ar"), ("svf", True, "adsr")])
+def test_per_sample_trigger_port_equals_reference(port, reference, filt, delay, env):
+    """maxiEnv::trigger written on every sample (mxo_bank_process_mod2): several notes per block, both envelope kinds."""
+    rng = np.random.default_rng(5)
+    V, B, cap = 12, 400, 64
+    p = W.voice_params(V, seed=61, delay_size=cap, ragged_delay=True)
+    a = port.Bank(V, osc="saw", filt=filt, env=env, delay=delay, delay_capacity=cap, kind="port")
+    b = reference.Bank(V, osc="saw", filt=filt, env=env, delay=delay, delay_capacity=cap, kind="reference")
+    W.configure_bank(a, filt, p, env=True, delay=delay); W.configure_bank(b, filt, p, env=True, delay=delay)
+    for blk in range(3):
+        tv = (rng.random((B, V)) < 0.5).astype(np.uint8)
+        tv[:, 0] = 0; tv[:, 1] = 1
+        tv[100:250, 2:6] = 1; tv[250:260, 2:6] = 0; tv[260:300, 2:6] = 1
+        oa, ma = a.process(B, trig_tv=tv, want_mix=True); ob, mb = b.process(B, trig_tv=tv, want_mix=True)
+        assert np.array_equal(oa, ob) and np.array_equal(ma, mb), blk
+        for s_ in ("env_holdcount", "env_flags", "env_amplitude", "env_output"):
+            assert np.array_equal(a.get(s_), b.get(s_)), (blk, s_)
