@@ -33,7 +33,9 @@
 #include <cstring>
 #include <memory>
 #include <stdexcept>
+#include <initializer_list>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "maxib200.h"
@@ -76,11 +78,13 @@ public:
     static size_t getSampleRate() { return sampleRate; }
 };
 
-/* A per-voice parameter: one double per voice, or a scalar broadcast to all voices (what the reference passes
- * by value on every sample). */
+/* A per-voice parameter: one double per voice (a std::vector that outlives play()), or a scalar (what the reference passes by
+ * value on every sample). Scalars are compiled into the patch as constants: a scalar that changes from block to block is a
+ * different patch -- pass a per-voice vector for block-rate control. */
 class maxiParam {
 public:
     maxiParam(double scalar = 0.0) : scalar_(scalar), vec_(nullptr) {}
+    maxiParam(int scalar) : scalar_((double)scalar), vec_(nullptr) {}
     maxiParam(const std::vector<double>& perVoice) : scalar_(0.0), vec_(&perVoice) {}
     bool isScalar() const { return vec_ == nullptr; }
     double scalar() const { return scalar_; }
@@ -97,132 +101,357 @@ struct maxiGate {
     maxiGate() {}
     maxiGate(const std::vector<int32_t>& on_, const std::vector<int32_t>& off_) : on(&on_), off(&off_) {}
 };
+/* a per-sample control stream for the current block: values[t * voices + v] (maxiEnv::trigger written by the patch on any sample,
+ * audio-rate modulation computed elsewhere) */
+struct maxiStream {
+    const double* values = nullptr;
+    explicit maxiStream(const double* v) : values(v) {}
+    explicit maxiStream(const std::vector<double>& v) : values(v.data()) {}
+};
 
 class maxiVoices;
-/* the signal flowing between stages: a token tying a stage output to its bank */
+/* The signal flowing between the calls of a play(): a handle to a value of the recorded program (register, parameter or constant). */
 struct maxiSignal {
     maxiVoices* voices = nullptr;
-    int stage = 0;     /* 1 osc, 2 env, 3 filter, 4 delay */
+    int32_t src = MXB_NONE;
+    int stage = 0;                      /* 1 osc, 2 env, 3 filter, 4 delay, 0 anything else */
 };
 struct maxiBus { maxiVoices* voices = nullptr; };
 
-/* The bank of voices behind one play(): owns the mxb_ctx / mxb_bank handles. */
+/* The voices behind one play(). The calls made inside play() do not compute anything on the host: they RECORD the patch -- a
+ * stage per call, `+ - * /` between signals included -- and hand over parameters; render() runs the block on the GPU. A patch of the
+ * shape oscillator -> [maxiEnv] -> [filter] -> [maxiDelayline] -> maxiMix::stereo / per-voice output with block-constant arguments
+ * runs on the fused bank kernels (mxb_bank, the HBM-roofline path); any other graph -- sums of oscillators, an LFO on a cutoff,
+ * the envelope applied after the filter (maximilian_examples/15.polysynth/main.cpp:54-70), per-sample triggers -- runs on the patch
+ * interpreter (mxb_patch). The patch must be the same on every block (the reference's play() is, too). */
 class maxiVoices {
 public:
-    explicit maxiVoices(int voices, int device = 0) : V_(voices), device_(device) {
-        for (auto& d : dirty_) d = false;
-        std::memset(&desc_, 0, sizeof(desc_));
-        desc_.voices = voices; desc_.osc_kind = -1;
-    }
-    ~maxiVoices() { if (bank_) mxb_bank_destroy(bank_); if (ctx_) mxb_ctx_destroy(ctx_); }
+    explicit maxiVoices(int voices, int device = 0) : V_(voices), device_(device) {}
+    ~maxiVoices() { if (bank_) mxb_bank_destroy(bank_); if (patch_) mxb_patch_destroy(patch_); if (ctx_) mxb_ctx_destroy(ctx_); }
     maxiVoices(const maxiVoices&) = delete;
     maxiVoices& operator=(const maxiVoices&) = delete;
 
     int size() const { return V_; }
     maxiBus bus() { return maxiBus{this}; }
+    /* sineBuffer / transition of the reference (src/maximilian.cpp:63, 67) for sinebuf / sinebuf4 / sawn: see mxb_ctx_set_tables */
+    void setTables(const double* sine514, const double* transition1001, double sineBefore) {
+        sine_.assign(sine514, sine514 + 514); trans_.assign(transition1001, transition1001 + 1001); sineBefore_ = sineBefore; haveTables_ = true;
+    }
+    /* ring slots per voice for maxiDelayline / maxiFlanger stages of an interpreted patch (a fused chain takes it from the object) */
+    void setDelayCapacity(int taps) { taps_ = taps; }
+    /* the sum over voices of `x` goes to bus channel 0 (what `mix += x` does in a reference play()) */
+    void sum(maxiSignal x) { check(x, "maxiVoices::sum"); emit(MXB_OP_MIX_STEREO, 0, {x.src, constOp(0.0)}, false); }
+    /* per-voice output: out[t][v] = x */
+    void out(maxiSignal x) { check(x, "maxiVoices::out"); emit(MXB_OP_OUT, 0, {x.src}, false); outSrc_ = x.src; }
 
-    /* Run the chain described since the last render for nFrames frames.
-     * out:  per-voice samples [nFrames][V] (host memory) or nullptr;
+    /* Run the patch recorded since the last render for nFrames frames.
+     * out:  per-voice samples [nFrames][V] (host memory) or nullptr (the last signal of the chain unless out() named one);
      * mix:  stereo bus [nFrames][2] (host memory, interleaved like RTAUDIO_FLOAT64) or nullptr. */
     void render(int nFrames, double* out, double* mix) {
         using maxib200_detail::check;
-        if (desc_.osc_kind < 0) throw maxiError(MXB_ERR_STATE, "maxiVoices::render: play() described no oscillator");
-        if (!bank_) {
-            check(mxb_ctx_create(device_, (int32_t)maxiSettings::sampleRate, &ctx_), "mxb_ctx_create");
-            desc_.max_frames = (int32_t)(nFrames > (int)maxiSettings::bufferSize ? nFrames : (int)maxiSettings::bufferSize);
-            check(mxb_bank_create(ctx_, &desc_, &bank_), "mxb_bank_create");
-            built_ = desc_;
-        } else if (std::memcmp(&built_, &desc_, sizeof(desc_)) != 0 && !sameChain()) {
-            throw maxiError(MXB_ERR_UNSUPPORTED, "maxiVoices: play() changed the chain after the first block");
-        }
-        for (int id = 0; id < MXB_P_COUNT; ++id) {
-            if (!dirty_[id]) continue;
-            check(mxb_bank_set_param(bank_, id, params_[id].data(), MXB_MEM_HOST), "mxb_bank_set_param");
-            dirty_[id] = false;
-        }
-        const int32_t* on = gate_.on ? gate_.on->data() : nullptr;
-        const int32_t* off = gate_.off ? gate_.off->data() : nullptr;
-        check(mxb_bank_process(bank_, nFrames, on, off, out, MXB_F64, (wantMix_ ? mix : nullptr), MXB_MEM_HOST, nullptr), "mxb_bank_process");
-        gate_ = maxiGate();
+        if (prog_.empty()) throw maxiError(MXB_ERR_STATE, "maxiVoices::render: play() described nothing");
+        if (!ctx_) check(mxb_ctx_create(device_, (int32_t)maxiSettings::sampleRate, &ctx_), "mxb_ctx_create");
+        if (outSrc_ == MXB_NONE && lastSrc_ != MXB_NONE) { emit(MXB_OP_OUT, 0, {lastSrc_}, false); outSrc_ = lastSrc_; }   /* the chain's last signal */
+        wantMix_ = false;
+        for (const mxb_stage& g : prog_) wantMix_ = wantMix_ || g.op == MXB_OP_MIX_STEREO;
+        if (!bank_ && !patch_) build(nFrames);
+        else if (!sameProgram()) throw maxiError(MXB_ERR_UNSUPPORTED, "maxiVoices: play() recorded a different patch than on the first block");
+        if (bank_) runBank(nFrames, out, mix); else runPatch(nFrames, out, mix);
+        prog_.clear(); consts_.clear(); nParams_ = 0; nInputs_ = 0; nextReg_ = 0; gate_ = maxiGate(); gateInput_ = -1; outSrc_ = MXB_NONE; lastSrc_ = MXB_NONE;
+        pendingPhase_.clear();
     }
 
-    /* state read-back (checkpointing / tests): MXB_P_PHASE, MXB_S_* */
+    /* state read-back of a fused chain (checkpointing / tests): MXB_P_PHASE, MXB_S_* */
     std::vector<double> state(int id) {
+        if (!bank_) throw maxiError(MXB_ERR_STATE, "maxiVoices::state: the patch runs on the interpreter (use patchHandle())");
         std::vector<double> v((size_t)V_);
         maxib200_detail::check(mxb_bank_get_state(bank_, id, v.data(), MXB_MEM_HOST), "mxb_bank_get_state");
         return v;
     }
     mxb_bank* handle() { return bank_; }
+    mxb_patch* patchHandle() { return patch_; }
+    bool fused() const { return bank_ != nullptr; }
+
+    /* ---- recording interface (used by the maxi* classes and the operators below) ---- */
+    int32_t constOp(double v) {
+        for (size_t i = 0; i < consts_.size(); ++i) if (std::memcmp(&consts_[i], &v, sizeof(double)) == 0) return MXB_CONST((int32_t)i);
+        consts_.push_back(v);
+        return MXB_CONST((int32_t)consts_.size() - 1);
+    }
+    int32_t operand(const maxiParam& p) {
+        if (p.isScalar()) return constOp(p.scalar());
+        if (p.vec().size() != (size_t)V_) throw maxiError(MXB_ERR_INVALID, "maxiParam: per-voice vector has the wrong length");
+        if ((size_t)nParams_ >= paramVals_.size()) { paramVals_.emplace_back(); paramDirty_.push_back(true); }
+        std::vector<double>& dst = paramVals_[(size_t)nParams_];
+        if (dst.size() != (size_t)V_ || std::memcmp(dst.data(), p.vec().data(), sizeof(double) * (size_t)V_) != 0) { dst = p.vec(); paramDirty_[(size_t)nParams_] = true; }
+        return MXB_PARAM(nParams_++);
+    }
+    int32_t operand(const maxiSignal& x) { check(x, "operand"); return x.src; }
+    int32_t operand(const maxiStream& st) {
+        if ((size_t)nInputs_ >= inputPtr_.size()) inputPtr_.push_back(nullptr);
+        inputPtr_[(size_t)nInputs_] = st.values;
+        return MXB_INPUT(nInputs_++);
+    }
+    int32_t operand(const maxiGate& g) {          /* an interval gate: a trigger stream built at render time (or the bank's own gate) */
+        gate_ = g;
+        if ((size_t)nInputs_ >= inputPtr_.size()) inputPtr_.push_back(nullptr);
+        gateInput_ = nInputs_;
+        inputPtr_[(size_t)nInputs_] = nullptr;
+        return MXB_INPUT(nInputs_++);
+    }
+    maxiSignal emit(int32_t op, int32_t kind, std::initializer_list<int32_t> srcs, bool wantDst = true, int stageTag = 0) {
+        mxb_stage g;
+        g.op = op; g.kind = kind; g.reserved = 0; g.dst = MXB_NONE;
+        int k = 0;
+        for (int32_t x : srcs) g.src[k++] = x;
+        for (; k < MXB_STAGE_SRCS; ++k) g.src[k] = MXB_NONE;
+        if (wantDst) {
+            if (nextReg_ >= 16) throw maxiError(MXB_ERR_UNSUPPORTED, "maxiVoices: more than 16 values in one play()");
+            g.dst = MXB_REG(nextReg_++);
+        }
+        prog_.push_back(g);
+        if (wantDst) lastSrc_ = g.dst;
+        return maxiSignal{this, g.dst, stageTag};
+    }
+    void check(const maxiSignal& x, const char* who) const {
+        if (x.voices != this) throw maxiError(MXB_ERR_UNSUPPORTED, std::string(who) + ": the signal belongs to another maxiVoices");
+    }
+    int delayCapacity_ = 0;             /* of the maxiDelayline object of a fused chain */
+    int biquadType_ = 0;
 
 private:
-    friend class maxiOsc; friend class maxiFilter; friend class maxiSVF; friend class maxiBiquad;
-    friend class maxiEnv; friend class maxiDelayline; friend class maxiMix;
-
-    bool sameChain() const {
-        return built_.osc_kind == desc_.osc_kind && built_.filt_kind == desc_.filt_kind && built_.env_kind == desc_.env_kind &&
-               built_.biquad_type == desc_.biquad_type && built_.delay_taps == desc_.delay_taps && built_.delay_mode == desc_.delay_mode &&
-               std::memcmp(built_.svf_mix, desc_.svf_mix, sizeof(desc_.svf_mix)) == 0;
+    static bool blockConstant(int32_t s) { return s == MXB_NONE || (s >> 8) == 1 || (s >> 8) == 2; }   /* parameter or constant */
+    bool sameProgram() const {
+        return built_.size() == prog_.size() && std::memcmp(built_.data(), prog_.data(), sizeof(mxb_stage) * prog_.size()) == 0 &&
+               builtConsts_.size() == consts_.size() && std::memcmp(builtConsts_.data(), consts_.data(), sizeof(double) * consts_.size()) == 0;
     }
-    void setParam(int id, const maxiParam& p) {
-        std::vector<double>& dst = params_[id];
-        if (p.isScalar()) {
-            if (dst.size() == (size_t)V_ && scalarSet_[id] && scalarVal_[id] == p.scalar()) return;   /* unchanged since last block */
-            dst.assign((size_t)V_, p.scalar());
-            scalarSet_[id] = true; scalarVal_[id] = p.scalar();
-        } else {
-            if (p.vec().size() != (size_t)V_) throw maxiError(MXB_ERR_INVALID, "maxiParam: per-voice vector has the wrong length");
-            if (dst.size() == (size_t)V_ && !scalarSet_[id] && std::memcmp(dst.data(), p.vec().data(), sizeof(double) * (size_t)V_) == 0) return;
-            dst = p.vec();
-            scalarSet_[id] = false;
+    std::vector<double> values(int32_t s) const {       /* a block-constant operand as a per-voice array */
+        if ((s >> 8) == 1) return paramVals_[(size_t)(s & 0xff)];
+        return std::vector<double>((size_t)V_, s == MXB_NONE ? 0.0 : consts_[(size_t)(s & 0xff)]);
+    }
+
+    /* Does the recorded program have the shape of the fused kernels? osc -> [env(interval gate)] -> [filter] -> [delay] -> stereo / out,
+     * every argument block-constant. Fills chain_ (which stage plays which role). */
+    struct Chain { int osc = -1, env = -1, filt = -1, dly = -1, mix = -1, out = -1; };
+    bool matchChain(Chain& c) const {
+        size_t i = 0;
+        const size_t n = prog_.size();
+        auto args_const = [&](const mxb_stage& g, int from) { for (int k = from; k < MXB_STAGE_SRCS; ++k) if (!blockConstant(g.src[k])) return false; return true; };
+        if (i >= n || prog_[i].op != MXB_OP_OSC || prog_[i].kind > MXB_OSC_PHASORBETWEEN || !args_const(prog_[i], 0)) return false;
+        c.osc = (int)i; int32_t cur = prog_[i].dst; ++i;
+        if (i < n && (prog_[i].op == MXB_OP_ENV_ADSR || prog_[i].op == MXB_OP_ENV_AR)) {
+            const mxb_stage& g = prog_[i];
+            if (g.src[0] != cur || gateInput_ < 0 || g.src[1] != MXB_INPUT(gateInput_) || !args_const(g, 2)) return false;
+            c.env = (int)i; cur = g.dst; ++i;
         }
-        dirty_[id] = true;
+        if (i < n && (prog_[i].op == MXB_OP_FILTER || prog_[i].op == MXB_OP_SVF || prog_[i].op == MXB_OP_BIQUAD)) {
+            const mxb_stage& g = prog_[i];
+            if (g.src[0] != cur || !args_const(g, 1)) return false;
+            if (g.op == MXB_OP_FILTER && g.kind != MXB_FILT_LORES && g.kind != MXB_FILT_HIRES) return false;
+            if (g.op == MXB_OP_SVF) for (int k = 3; k < 7; ++k) if ((g.src[k] >> 8) != 2) return false;      /* mix weights: constants */
+            c.filt = (int)i; cur = g.dst; ++i;
+        }
+        if (i < n && prog_[i].op == MXB_OP_DELAY) {
+            const mxb_stage& g = prog_[i];
+            if (g.src[0] != cur || !args_const(g, 1)) return false;
+            c.dly = (int)i; cur = g.dst; ++i;
+        }
+        for (; i < n; ++i) {
+            const mxb_stage& g = prog_[i];
+            if (g.op == MXB_OP_MIX_STEREO && c.mix < 0 && g.src[0] == cur && blockConstant(g.src[1])) c.mix = (int)i;
+            else if (g.op == MXB_OP_OUT && c.out < 0 && g.src[0] == cur) c.out = (int)i;
+            else return false;
+        }
+        return nInputs_ == (c.env >= 0 ? 1 : 0);
     }
 
-    int V_, device_;
+    void build(int nFrames) {
+        using maxib200_detail::check;
+        const int maxFrames = nFrames > (int)maxiSettings::bufferSize ? nFrames : (int)maxiSettings::bufferSize;
+        Chain c;
+        if (matchChain(c)) {
+            mxb_bank_desc d;
+            std::memset(&d, 0, sizeof(d));
+            d.voices = V_; d.max_frames = maxFrames; d.osc_kind = prog_[(size_t)c.osc].kind;
+            if (c.env >= 0) d.env_kind = prog_[(size_t)c.env].op == MXB_OP_ENV_ADSR ? MXB_ENV_ADSR : MXB_ENV_AR;
+            if (c.filt >= 0) {
+                const mxb_stage& g = prog_[(size_t)c.filt];
+                d.filt_kind = g.op == MXB_OP_SVF ? MXB_FILT_SVF : g.op == MXB_OP_BIQUAD ? MXB_FILT_BIQUAD : g.kind;
+                if (g.op == MXB_OP_BIQUAD) d.biquad_type = g.kind;
+                if (g.op == MXB_OP_SVF) for (int k = 0; k < 4; ++k) d.svf_mix[k] = consts_[(size_t)(g.src[3 + k] & 0xff)];
+            }
+            if (c.dly >= 0) { d.delay_taps = delayCapacity_ > 0 ? delayCapacity_ : taps_; d.delay_mode = prog_[(size_t)c.dly].kind; }
+            check(mxb_bank_create(ctx_, &d, &bank_), "mxb_bank_create");
+            chain_ = c;
+        } else {
+            if (haveTables_) check(mxb_ctx_set_tables(ctx_, sine_.data(), trans_.data(), sineBefore_), "mxb_ctx_set_tables");
+            mxb_patch_desc d;
+            std::memset(&d, 0, sizeof(d));
+            d.voices = V_; d.n_stages = (int32_t)prog_.size(); d.n_params = nParams_; d.n_consts = (int32_t)consts_.size(); d.n_inputs = nInputs_;
+            d.max_frames = maxFrames; d.delay_taps = delayCapacity_ > 0 ? delayCapacity_ : taps_;
+            d.stages = prog_.data(); d.consts = consts_.data();
+            d.eg_stages = (int32_t)egTimes_.size(); d.eg_loop = egLoop_; d.eg_retrigger = egRetrigger_;
+            d.eg_levels = egLevels_.data(); d.eg_times = egTimes_.data(); d.eg_curves = egCurves_.data();
+            check(mxb_patch_create(ctx_, &d, &patch_), "mxb_patch_create");
+        }
+        built_ = prog_; builtConsts_ = consts_;
+        for (size_t j = 0; j < paramDirty_.size(); ++j) paramDirty_[j] = true;
+    }
+
+    void setBank(int id, int32_t s) {
+        if (s == MXB_NONE) return;
+        const bool isParam = (s >> 8) == 1;
+        if (isParam && !paramDirty_[(size_t)(s & 0xff)] && bankSet_[id]) return;
+        if (!isParam && bankSet_[id]) return;                         /* constants never change (sameProgram) */
+        const std::vector<double> v = values(s);
+        maxib200_detail::check(mxb_bank_set_param(bank_, id, v.data(), MXB_MEM_HOST), "mxb_bank_set_param");
+        bankSet_[id] = true;
+    }
+    void runBank(int nFrames, double* out, double* mix) {
+        const Chain& c = chain_;
+        const mxb_stage& o = prog_[(size_t)c.osc];
+        if (o.kind == MXB_OSC_PULSE) setBank(MXB_P_DUTY, o.src[1]);
+        if (o.kind == MXB_OSC_PHASORBETWEEN) { setBank(MXB_P_PHASOR_START, o.src[1]); setBank(MXB_P_PHASOR_END, o.src[2]); }
+        setBank(MXB_P_FREQ, o.src[0]);
+        for (const auto& ph : pendingPhase_) maxib200_detail::check(mxb_bank_set_param(bank_, MXB_P_PHASE, ph.second.data(), MXB_MEM_HOST), "mxb_bank_set_param");
+        if (c.env >= 0) {
+            const mxb_stage& g = prog_[(size_t)c.env];
+            if (g.op == MXB_OP_ENV_ADSR) { setBank(MXB_P_ENV_ATTACK, g.src[2]); setBank(MXB_P_ENV_DECAY, g.src[3]); setBank(MXB_P_ENV_SUSTAIN, g.src[4]);
+                                           setBank(MXB_P_ENV_RELEASE, g.src[5]); setBank(MXB_P_ENV_HOLDTIME, g.src[6]); }
+            else { setBank(MXB_P_ENV_ATTACK, g.src[2]); setBank(MXB_P_ENV_RELEASE, g.src[3]); setBank(MXB_P_ENV_HOLDTIME, g.src[4]); }
+        }
+        if (c.filt >= 0) {
+            const mxb_stage& g = prog_[(size_t)c.filt];
+            if (g.op == MXB_OP_BIQUAD) setBank(MXB_P_GAIN, g.src[3]);
+            setBank(MXB_P_CUTOFF, g.src[1]); setBank(MXB_P_RESONANCE, g.src[2]);
+        }
+        if (c.dly >= 0) {
+            const mxb_stage& g = prog_[(size_t)c.dly];
+            setBank(MXB_P_DELAY_SIZE, g.src[1]); setBank(MXB_P_DELAY_FEEDBACK, g.src[2]);
+            if (g.kind == MXB_DELAY_FROM_POSITION) setBank(MXB_P_DELAY_POSITION, g.src[3]);
+        }
+        if (c.mix >= 0) setBank(MXB_P_PAN, prog_[(size_t)c.mix].src[1]);
+        for (size_t j = 0; j < paramDirty_.size(); ++j) paramDirty_[j] = false;
+        const int32_t* on = gate_.on ? gate_.on->data() : nullptr;
+        const int32_t* off = gate_.off ? gate_.off->data() : nullptr;
+        maxib200_detail::check(mxb_bank_process(bank_, nFrames, on, off, c.out >= 0 ? out : nullptr, MXB_F64, c.mix >= 0 ? mix : nullptr, MXB_MEM_HOST, nullptr),
+                               "mxb_bank_process");
+    }
+    void runPatch(int nFrames, double* out, double* mix) {
+        using maxib200_detail::check;
+        for (int j = 0; j < nParams_; ++j) {
+            if (!paramDirty_[(size_t)j]) continue;
+            check(mxb_patch_set_param(patch_, j, paramVals_[(size_t)j].data(), MXB_MEM_HOST), "mxb_patch_set_param");
+            paramDirty_[(size_t)j] = false;
+        }
+        for (const auto& ph : pendingPhase_) check(mxb_patch_set_state(patch_, ph.first, 0, ph.second.data(), MXB_MEM_HOST), "mxb_patch_set_state");
+        if (gateInput_ >= 0) {        /* the interval gate as a per-sample trigger stream */
+            gateStream_.assign((size_t)nFrames * (size_t)V_, 0.0);
+            if (gate_.on && gate_.off)
+                for (int v = 0; v < V_; ++v)
+                    for (int t = (*gate_.on)[(size_t)v] < 0 ? 0 : (*gate_.on)[(size_t)v]; t < (*gate_.off)[(size_t)v] && t < nFrames; ++t) gateStream_[(size_t)t * (size_t)V_ + (size_t)v] = 1.0;
+            inputPtr_[(size_t)gateInput_] = gateStream_.data();
+        }
+        check(mxb_patch_process(patch_, nFrames, nInputs_ ? inputPtr_.data() : nullptr, outSrc_ != MXB_NONE ? out : nullptr, wantMix_ ? mix : nullptr,
+                                MXB_MEM_HOST, nullptr), "mxb_patch_process");
+    }
+
+    friend class maxiOsc; friend class maxiEnvGen;
+    int V_, device_, taps_ = 0;
     mxb_ctx* ctx_ = nullptr;
     mxb_bank* bank_ = nullptr;
-    mxb_bank_desc desc_, built_;
-    std::vector<double> params_[MXB_P_COUNT];
-    bool dirty_[MXB_P_COUNT];
-    bool scalarSet_[MXB_P_COUNT] = {};
-    double scalarVal_[MXB_P_COUNT] = {};
-    maxiGate gate_;
+    mxb_patch* patch_ = nullptr;
+    std::vector<mxb_stage> prog_, built_;
+    std::vector<double> consts_, builtConsts_;
+    std::vector<std::vector<double>> paramVals_;
+    std::vector<bool> paramDirty_;
+    std::vector<const double*> inputPtr_;
+    std::vector<double> gateStream_;
+    std::vector<std::pair<int, std::vector<double>>> pendingPhase_;      /* maxiOsc::phaseReset: (stage, per-voice phase), applied before the block */
+    std::vector<double> egLevels_{0.0}, egTimes_, egCurves_;
+    int egLoop_ = 0, egRetrigger_ = 0;
+    std::vector<double> sine_, trans_; double sineBefore_ = 0.0; bool haveTables_ = false;
+    int nParams_ = 0, nInputs_ = 0, nextReg_ = 0, gateInput_ = -1;
+    int32_t outSrc_ = MXB_NONE, lastSrc_ = MXB_NONE;
     bool wantMix_ = false;
+    bool bankSet_[MXB_P_COUNT] = {};
+    maxiGate gate_;
+    Chain chain_;
+};
+
+/* the arithmetic a play() does between the calls: recorded like everything else */
+namespace maxib200_detail {
+inline maxiSignal bin(int32_t op, maxiVoices* v, int32_t a, int32_t b) { return v->emit(op, 0, {a, b}); }
+}
+inline maxiSignal operator+(maxiSignal a, maxiSignal b) { a.voices->check(b, "operator+"); return maxib200_detail::bin(MXB_OP_ADD, a.voices, a.src, b.src); }
+inline maxiSignal operator-(maxiSignal a, maxiSignal b) { a.voices->check(b, "operator-"); return maxib200_detail::bin(MXB_OP_SUB, a.voices, a.src, b.src); }
+inline maxiSignal operator*(maxiSignal a, maxiSignal b) { a.voices->check(b, "operator*"); return maxib200_detail::bin(MXB_OP_MUL, a.voices, a.src, b.src); }
+inline maxiSignal operator/(maxiSignal a, maxiSignal b) { a.voices->check(b, "operator/"); return maxib200_detail::bin(MXB_OP_DIV, a.voices, a.src, b.src); }
+inline maxiSignal operator+(maxiSignal a, const maxiParam& b) { return maxib200_detail::bin(MXB_OP_ADD, a.voices, a.src, a.voices->operand(b)); }
+inline maxiSignal operator-(maxiSignal a, const maxiParam& b) { return maxib200_detail::bin(MXB_OP_SUB, a.voices, a.src, a.voices->operand(b)); }
+inline maxiSignal operator*(maxiSignal a, const maxiParam& b) { return maxib200_detail::bin(MXB_OP_MUL, a.voices, a.src, a.voices->operand(b)); }
+inline maxiSignal operator/(maxiSignal a, const maxiParam& b) { return maxib200_detail::bin(MXB_OP_DIV, a.voices, a.src, a.voices->operand(b)); }
+inline maxiSignal operator+(const maxiParam& a, maxiSignal b) { return maxib200_detail::bin(MXB_OP_ADD, b.voices, b.voices->operand(a), b.src); }
+inline maxiSignal operator-(const maxiParam& a, maxiSignal b) { return maxib200_detail::bin(MXB_OP_SUB, b.voices, b.voices->operand(a), b.src); }
+inline maxiSignal operator*(const maxiParam& a, maxiSignal b) { return maxib200_detail::bin(MXB_OP_MUL, b.voices, b.voices->operand(a), b.src); }
+inline maxiSignal operator/(const maxiParam& a, maxiSignal b) { return maxib200_detail::bin(MXB_OP_DIV, b.voices, b.voices->operand(a), b.src); }
+
+/* An argument of a stage: a signal computed earlier in play(), or a parameter. */
+class maxiArg {
+public:
+    maxiArg(maxiSignal s) : sig_(s), isSig_(true) {}
+    maxiArg(double v) : par_(v) {}
+    maxiArg(int v) : par_((double)v) {}
+    maxiArg(const std::vector<double>& v) : par_(v) {}
+    maxiArg(const maxiParam& p) : par_(p) {}
+    int32_t op(maxiVoices* v) const { if (isSig_) { v->check(sig_, "argument"); return sig_.src; } return v->operand(par_); }
+private:
+    maxiSignal sig_; maxiParam par_; bool isSig_ = false;
 };
 
 /* maxiOsc, src/maximilian.h:169-215 / src/maximilian.cpp:209-373 */
 class maxiOsc {
 public:
     explicit maxiOsc(maxiVoices& v) : v_(&v) {}
-    maxiSignal sinewave(const maxiParam& frequency) { return osc(MXB_OSC_SINEWAVE, frequency); }
-    maxiSignal coswave(const maxiParam& frequency) { return osc(MXB_OSC_COSWAVE, frequency); }
-    maxiSignal phasor(const maxiParam& frequency) { return osc(MXB_OSC_PHASOR, frequency); }
-    maxiSignal saw(const maxiParam& frequency) { return osc(MXB_OSC_SAW, frequency); }
-    maxiSignal square(const maxiParam& frequency) { return osc(MXB_OSC_SQUARE, frequency); }
-    maxiSignal triangle(const maxiParam& frequency) { return osc(MXB_OSC_TRIANGLE, frequency); }
-    maxiSignal impulse(const maxiParam& frequency) { return osc(MXB_OSC_IMPULSE, frequency); }
-    maxiSignal pulse(const maxiParam& frequency, const maxiParam& duty) { v_->setParam(MXB_P_DUTY, duty); return osc(MXB_OSC_PULSE, frequency); }
-    maxiSignal phasorBetween(const maxiParam& frequency, const maxiParam& startphase, const maxiParam& endphase) {
-        v_->setParam(MXB_P_PHASOR_START, startphase); v_->setParam(MXB_P_PHASOR_END, endphase);
-        return osc(MXB_OSC_PHASORBETWEEN, frequency);
+    maxiSignal sinewave(const maxiArg& frequency) { return osc(MXB_OSC_SINEWAVE, frequency); }
+    maxiSignal coswave(const maxiArg& frequency) { return osc(MXB_OSC_COSWAVE, frequency); }
+    maxiSignal phasor(const maxiArg& frequency) { return osc(MXB_OSC_PHASOR, frequency); }
+    maxiSignal saw(const maxiArg& frequency) { return osc(MXB_OSC_SAW, frequency); }
+    maxiSignal square(const maxiArg& frequency) { return osc(MXB_OSC_SQUARE, frequency); }
+    maxiSignal triangle(const maxiArg& frequency) { return osc(MXB_OSC_TRIANGLE, frequency); }
+    maxiSignal impulse(const maxiArg& frequency) { return osc(MXB_OSC_IMPULSE, frequency); }
+    maxiSignal sinebuf(const maxiArg& frequency) { return osc(MXB_OSC_SINEBUF, frequency); }
+    maxiSignal sinebuf4(const maxiArg& frequency) { return osc(MXB_OSC_SINEBUF4, frequency); }
+    maxiSignal sawn(const maxiArg& frequency) { return osc(MXB_OSC_SAWN, frequency); }
+    maxiSignal pulse(const maxiArg& frequency, const maxiArg& duty) { return emitOsc(MXB_OSC_PULSE, {frequency.op(v_), duty.op(v_)}); }
+    maxiSignal phasorBetween(const maxiArg& frequency, const maxiArg& startphase, const maxiArg& endphase) {
+        return emitOsc(MXB_OSC_PHASORBETWEEN, {frequency.op(v_), startphase.op(v_), endphase.op(v_)});
     }
-    void phaseReset(const maxiParam& phaseIn) { v_->setParam(MXB_P_PHASE, phaseIn); }
+    /* maxiOsc::phaseReset (src/maximilian.cpp:222-226): takes effect before the next block this oscillator plays in */
+    void phaseReset(const maxiParam& phaseIn) { pending_ = phaseIn.isScalar() ? std::vector<double>((size_t)v_->size(), phaseIn.scalar()) : phaseIn.vec(); }
 private:
-    maxiSignal osc(int kind, const maxiParam& f) { v_->desc_.osc_kind = kind; v_->setParam(MXB_P_FREQ, f); return maxiSignal{v_, 1}; }
+    maxiSignal osc(int kind, const maxiArg& f) { return emitOsc(kind, {f.op(v_)}); }
+    maxiSignal emitOsc(int kind, std::initializer_list<int32_t> srcs) {
+        if (!pending_.empty()) { v_->pendingPhase_.emplace_back((int)v_->prog_.size(), pending_); pending_.clear(); }
+        return v_->emit(MXB_OP_OSC, kind, srcs, true, 1);
+    }
     maxiVoices* v_;
+    std::vector<double> pending_;
 };
 
-/* maxiFilter::lores / hires, src/maximilian.cpp:455-484 */
+/* maxiFilter, src/maximilian.cpp:442-500 */
 class maxiFilter {
 public:
     explicit maxiFilter(maxiVoices& v) : v_(&v) {}
-    maxiSignal lores(maxiSignal input, const maxiParam& cutoff1, const maxiParam& resonance) { return f(MXB_FILT_LORES, input, cutoff1, resonance); }
-    maxiSignal hires(maxiSignal input, const maxiParam& cutoff1, const maxiParam& resonance) { return f(MXB_FILT_HIRES, input, cutoff1, resonance); }
+    maxiSignal lores(maxiSignal input, const maxiArg& cutoff1, const maxiArg& resonance) { return f(MXB_FILT_LORES, input, cutoff1, resonance); }
+    maxiSignal hires(maxiSignal input, const maxiArg& cutoff1, const maxiArg& resonance) { return f(MXB_FILT_HIRES, input, cutoff1, resonance); }
+    maxiSignal bandpass(maxiSignal input, const maxiArg& cutoff1, const maxiArg& resonance) { return f(MXB_FILT_BANDPASS, input, cutoff1, resonance); }
+    maxiSignal lopass(maxiSignal input, const maxiArg& cutoff) { v_->check(input, "maxiFilter::lopass"); return v_->emit(MXB_OP_FILTER, MXB_FILT_LOPASS, {input.src, cutoff.op(v_)}, true, 3); }
+    maxiSignal hipass(maxiSignal input, const maxiArg& cutoff) { v_->check(input, "maxiFilter::hipass"); return v_->emit(MXB_OP_FILTER, MXB_FILT_HIPASS, {input.src, cutoff.op(v_)}, true, 3); }
 private:
-    maxiSignal f(int kind, maxiSignal in, const maxiParam& c, const maxiParam& r) {
-        if (in.voices != v_ || in.stage < 1 || in.stage > 2) throw maxiError(MXB_ERR_UNSUPPORTED, "maxiFilter: input must be an oscillator or envelope of the same maxiVoices");
-        v_->desc_.filt_kind = kind; v_->setParam(MXB_P_CUTOFF, c); v_->setParam(MXB_P_RESONANCE, r);
-        return maxiSignal{v_, 3};
+    maxiSignal f(int kind, maxiSignal in, const maxiArg& c, const maxiArg& r) {
+        v_->check(in, "maxiFilter");
+        return v_->emit(MXB_OP_FILTER, kind, {in.src, c.op(v_), r.op(v_)}, true, 3);
     }
     maxiVoices* v_;
 };
@@ -231,16 +460,15 @@ private:
 class maxiSVF {
 public:
     explicit maxiSVF(maxiVoices& v) : v_(&v) {}
-    void setCutoff(const maxiParam& cutoff) { v_->setParam(MXB_P_CUTOFF, cutoff); }
-    void setResonance(const maxiParam& q) { v_->setParam(MXB_P_RESONANCE, q); }
+    void setCutoff(const maxiArg& cutoff) { cutoff_ = cutoff; }
+    void setResonance(const maxiArg& q) { res_ = q; }
     maxiSignal play(maxiSignal w, double lpmix, double bpmix, double hpmix, double notchmix) {
-        if (w.voices != v_ || w.stage < 1 || w.stage > 2) throw maxiError(MXB_ERR_UNSUPPORTED, "maxiSVF::play: input must be an oscillator or envelope of the same maxiVoices");
-        v_->desc_.filt_kind = MXB_FILT_SVF;
-        v_->desc_.svf_mix[0] = lpmix; v_->desc_.svf_mix[1] = bpmix; v_->desc_.svf_mix[2] = hpmix; v_->desc_.svf_mix[3] = notchmix;
-        return maxiSignal{v_, 3};
+        v_->check(w, "maxiSVF::play");
+        return v_->emit(MXB_OP_SVF, 0, {w.src, cutoff_.op(v_), res_.op(v_), v_->constOp(lpmix), v_->constOp(bpmix), v_->constOp(hpmix), v_->constOp(notchmix)}, true, 3);
     }
 private:
     maxiVoices* v_;
+    maxiArg cutoff_{1000.0}, res_{1.0};        /* maxiSVF ctor: setParams(1000, 1), src/maximilian.h:1284 */
 };
 
 /* maxiBiquad, src/maximilian.h:1343-1486 */
@@ -248,89 +476,141 @@ class maxiBiquad {
 public:
     enum filterTypes { LOWPASS, HIGHPASS, BANDPASS, NOTCH, PEAK, LOWSHELF, HIGHSHELF };
     explicit maxiBiquad(maxiVoices& v) : v_(&v) {}
-    void set(filterTypes filtType, const maxiParam& cutoff, const maxiParam& Q, const maxiParam& peakGain) {
-        v_->desc_.biquad_type = (int)filtType;
-        v_->setParam(MXB_P_GAIN, peakGain); v_->setParam(MXB_P_CUTOFF, cutoff); v_->setParam(MXB_P_RESONANCE, Q);
-    }
+    void set(filterTypes filtType, const maxiArg& cutoff, const maxiArg& Q, const maxiArg& peakGain) { type_ = (int)filtType; cutoff_ = cutoff; q_ = Q; gain_ = peakGain; }
     maxiSignal play(maxiSignal input) {
-        if (input.voices != v_ || input.stage < 1 || input.stage > 2) throw maxiError(MXB_ERR_UNSUPPORTED, "maxiBiquad::play: input must be an oscillator or envelope of the same maxiVoices");
-        v_->desc_.filt_kind = MXB_FILT_BIQUAD;
-        return maxiSignal{v_, 3};
+        v_->check(input, "maxiBiquad::play");
+        return v_->emit(MXB_OP_BIQUAD, type_, {input.src, cutoff_.op(v_), q_.op(v_), gain_.op(v_)}, true, 3);
     }
 private:
     maxiVoices* v_;
+    int type_ = 0;
+    maxiArg cutoff_{1000.0}, q_{1.0}, gain_{0.0};
 };
 
-/* maxiEnv (ADSR), src/maximilian.h:888-932 / src/maximilian.cpp:1415-1494 */
+/* maxiEnv (ADSR / AR), src/maximilian.h:888-932 / src/maximilian.cpp:1319-1494. The trigger is an argument here (the reference's
+ * public member `trigger`, written by the patch on any sample): a maxiGate interval or a maxiStream of per-sample values. */
 class maxiEnv {
 public:
     explicit maxiEnv(maxiVoices& v) : v_(&v) {}
-    void setAttack(const maxiParam& attackMS) { coeff(MXB_P_ENV_ATTACK, 0, attackMS); }
-    void setAttackMS(const maxiParam& attackMS) { coeff(MXB_P_ENV_ATTACK, 1, attackMS); }
-    void setDecay(const maxiParam& decayMS) { coeff(MXB_P_ENV_DECAY, 2, decayMS); }
-    void setRelease(const maxiParam& releaseMS) { coeff(MXB_P_ENV_RELEASE, 2, releaseMS); }
-    void setSustain(const maxiParam& sustainL) { v_->setParam(MXB_P_ENV_SUSTAIN, sustainL); }
-    void setHoldtime(const maxiParam& holdtime) { v_->setParam(MXB_P_ENV_HOLDTIME, holdtime); }   /* the public member `holdtime` */
-    maxiSignal adsr(maxiSignal input, const maxiGate& trigger) {
-        if (input.voices != v_ || input.stage != 1) throw maxiError(MXB_ERR_UNSUPPORTED, "maxiEnv::adsr: input must be the oscillator of the same maxiVoices");
-        v_->desc_.env_kind = MXB_ENV_ADSR; v_->gate_ = trigger;
-        return maxiSignal{v_, 2};
+    void setAttack(const maxiParam& attackMS) { coeff(0, 0, attackMS); }
+    void setAttackMS(const maxiParam& attackMS) { coeff(0, 1, attackMS); }
+    void setDecay(const maxiParam& decayMS) { coeff(1, 2, decayMS); }
+    void setRelease(const maxiParam& releaseMS) { coeff(3, 2, releaseMS); }
+    void setSustain(const maxiParam& sustainL) { set(2, sustainL); }
+    void setHoldtime(const maxiParam& holdtime) { set(4, holdtime); }          /* the public member `holdtime` (default 1) */
+    template <class Trig> maxiSignal adsr(const maxiArg& input, const Trig& trigger) {
+        return v_->emit(MXB_OP_ENV_ADSR, 0, {input.op(v_), v_->operand(trigger), arg(0), arg(1), arg(2), arg(3), arg(4)}, true, 2);
     }
     /* the overload that takes the raw coefficients as arguments (src/maximilian.cpp:1362-1413): the same state machine */
-    maxiSignal adsr(maxiSignal input, const maxiParam& attack, const maxiParam& decay, const maxiParam& sustain, const maxiParam& release,
-                    const maxiParam& holdtime, const maxiGate& trigger) {
-        v_->setParam(MXB_P_ENV_ATTACK, attack); v_->setParam(MXB_P_ENV_DECAY, decay); v_->setParam(MXB_P_ENV_SUSTAIN, sustain);
-        v_->setParam(MXB_P_ENV_RELEASE, release); v_->setParam(MXB_P_ENV_HOLDTIME, holdtime);
+    template <class Trig> maxiSignal adsr(const maxiArg& input, const maxiParam& attack, const maxiParam& decay, const maxiParam& sustain, const maxiParam& release,
+                                         const maxiParam& holdtime, const Trig& trigger) {
+        set(0, attack); set(1, decay); set(2, sustain); set(3, release); set(4, holdtime);
         return adsr(input, trigger);
     }
-    /* maxiEnv::ar(input, attack, release, holdtime, trigger): attack/release are the raw per-sample coefficients the
-     * reference takes as arguments (defaults 1, 0.9, holdtime 1) */
-    maxiSignal ar(maxiSignal input, const maxiParam& attack, const maxiParam& release, const maxiParam& holdtime, const maxiGate& trigger) {
-        if (input.voices != v_ || input.stage != 1) throw maxiError(MXB_ERR_UNSUPPORTED, "maxiEnv::ar: input must be the oscillator of the same maxiVoices");
-        v_->desc_.env_kind = MXB_ENV_AR; v_->gate_ = trigger;
-        v_->setParam(MXB_P_ENV_ATTACK, attack); v_->setParam(MXB_P_ENV_RELEASE, release); v_->setParam(MXB_P_ENV_HOLDTIME, holdtime);
-        return maxiSignal{v_, 2};
+    /* maxiEnv::ar(input, attack, release, holdtime, trigger): attack / release are the raw per-sample coefficients */
+    template <class Trig> maxiSignal ar(const maxiArg& input, const maxiParam& attack, const maxiParam& release, const maxiParam& holdtime, const Trig& trigger) {
+        return v_->emit(MXB_OP_ENV_AR, 0, {input.op(v_), v_->operand(trigger), v_->operand(attack), v_->operand(release), v_->operand(holdtime)}, true, 2);
     }
 private:
-    void coeff(int id, int kind, const maxiParam& ms) {
+    void set(int k, const maxiParam& p) { scalar_[k] = p.isScalar(); if (p.isScalar()) val_[k] = p.scalar(); else vec_[k] = p.vec(); }
+    int32_t arg(int k) { return scalar_[k] ? v_->constOp(val_[k]) : v_->operand(maxiParam(vec_[k])); }
+    void coeff(int k, int kind, const maxiParam& ms) {
         std::vector<double> in = ms.isScalar() ? std::vector<double>(1, ms.scalar()) : ms.vec();
         std::vector<double> out(in.size());
         maxib200_detail::check(mxb_env_coeffs(kind, in.data(), (int64_t)in.size(), (int32_t)maxiSettings::sampleRate, out.data()), "mxb_env_coeffs");
-        if (ms.isScalar()) v_->setParam(id, maxiParam(out[0])); else { tmp_[id - MXB_P_ENV_ATTACK] = out; v_->setParam(id, maxiParam(tmp_[id - MXB_P_ENV_ATTACK])); }
+        if (ms.isScalar()) set(k, maxiParam(out[0])); else set(k, maxiParam(out));
     }
     maxiVoices* v_;
-    std::vector<double> tmp_[4];
+    bool scalar_[5] = {true, true, true, true, true};
+    double val_[5] = {0, 0, 0, 0, 1.0};          /* maxiEnv: zero-filled but holdtime = 1, src/maximilian.h:913 */
+    std::vector<double> vec_[5];
 };
 
-/* maxiDelayline, src/maximilian.h:266-284 / src/maximilian.cpp:415-429 */
+/* maxiEnvGen, src/maximilian.h:2268-2547: one envelope shape for all voices, each with its own state */
+class maxiEnvGen {
+public:
+    static constexpr double HOLD = MXB_ENVGEN_HOLD;
+    explicit maxiEnvGen(maxiVoices& v) : v_(&v) {}
+    bool setup(const std::vector<double>& levels, const std::vector<double>& times, const std::vector<double>& curves, bool looping, bool allowRetrigger = false) {
+        if (levels.size() != times.size() + 1 || levels.size() != curves.size() + 1) return false;
+        v_->egLevels_ = levels; v_->egTimes_ = times; v_->egCurves_ = curves; v_->egLoop_ = looping; v_->egRetrigger_ = allowRetrigger;
+        return true;
+    }
+    void setupAR(double attack, double release) { setup({0, 1, 0}, {attack, release}, {1, 1}, false, false); }
+    void setupASR(double attack, double release) { setup({0, 1, 1, 0}, {attack, HOLD, release}, {1, 1, 1}, false, false); }
+    void setupADSR(double attack, double decay, double sustain, double release) { setup({0, 1, sustain, sustain, 0}, {attack, decay, HOLD, release}, {1, 1, 1, 1}, false, false); }
+    template <class Trig> maxiSignal play(const Trig& trigger) { return v_->emit(MXB_OP_ENVGEN, 0, {trig(trigger)}); }
+private:
+    int32_t trig(const maxiSignal& s) { v_->check(s, "maxiEnvGen::play"); return s.src; }
+    int32_t trig(const maxiStream& s) { return v_->operand(s); }
+    int32_t trig(const maxiParam& p) { return v_->operand(p); }
+    maxiVoices* v_;
+};
+
+/* maxiDelayline, src/maximilian.h:266-284 / src/maximilian.cpp:415-439 */
 class maxiDelayline {
 public:
     /* capacity: ring slots per voice (the reference allocates 705600 for every object) */
     maxiDelayline(maxiVoices& v, int capacity) : v_(&v), capacity_(capacity) {}
-    maxiSignal dl(maxiSignal input, const maxiParam& size, const maxiParam& feedback) {
-        if (input.voices != v_ || input.stage < 1 || input.stage > 3) throw maxiError(MXB_ERR_UNSUPPORTED, "maxiDelayline::dl: input must come from the same maxiVoices");
-        v_->desc_.delay_taps = capacity_; v_->desc_.delay_mode = MXB_DELAY_DL;
-        v_->setParam(MXB_P_DELAY_SIZE, size); v_->setParam(MXB_P_DELAY_FEEDBACK, feedback);
-        return maxiSignal{v_, 4};
+    maxiSignal dl(maxiSignal input, const maxiArg& size, const maxiArg& feedback) {
+        v_->check(input, "maxiDelayline::dl"); v_->delayCapacity_ = capacity_;
+        return v_->emit(MXB_OP_DELAY, MXB_DELAY_DL, {input.src, size.op(v_), feedback.op(v_)}, true, 4);
     }
-    maxiSignal dlFromPosition(maxiSignal input, const maxiParam& size, const maxiParam& feedback, const maxiParam& position) {
-        if (input.voices != v_ || input.stage < 1 || input.stage > 3) throw maxiError(MXB_ERR_UNSUPPORTED, "maxiDelayline::dlFromPosition: input must come from the same maxiVoices");
-        v_->desc_.delay_taps = capacity_; v_->desc_.delay_mode = MXB_DELAY_FROM_POSITION;
-        v_->setParam(MXB_P_DELAY_SIZE, size); v_->setParam(MXB_P_DELAY_FEEDBACK, feedback); v_->setParam(MXB_P_DELAY_POSITION, position);
-        return maxiSignal{v_, 4};
+    maxiSignal dlFromPosition(maxiSignal input, const maxiArg& size, const maxiArg& feedback, const maxiArg& position) {
+        v_->check(input, "maxiDelayline::dlFromPosition"); v_->delayCapacity_ = capacity_;
+        return v_->emit(MXB_OP_DELAY, MXB_DELAY_FROM_POSITION, {input.src, size.op(v_), feedback.op(v_), position.op(v_)}, true, 4);
     }
 private:
     maxiVoices* v_;
     int capacity_;
 };
 
+/* maxiFlanger, src/maximilian.h:1144-1180 (maxiChorus draws its LFO from rand(): not reproducible, not offered) */
+class maxiFlanger {
+public:
+    maxiFlanger(maxiVoices& v, int capacity) : v_(&v), capacity_(capacity) {}
+    maxiSignal flange(maxiSignal input, const maxiArg& delay, const maxiArg& feedback, const maxiArg& speed, const maxiArg& depth) {
+        v_->check(input, "maxiFlanger::flange"); v_->delayCapacity_ = capacity_;
+        return v_->emit(MXB_OP_FLANGER, 0, {input.src, delay.op(v_), feedback.op(v_), speed.op(v_), depth.op(v_)});
+    }
+private:
+    maxiVoices* v_;
+    int capacity_;
+};
+
+/* maxiDCBlocker, src/maximilian.h:1255-1267 */
+class maxiDCBlocker {
+public:
+    explicit maxiDCBlocker(maxiVoices& v) : v_(&v) {}
+    maxiSignal play(maxiSignal input, const maxiArg& R) { v_->check(input, "maxiDCBlocker::play"); return v_->emit(MXB_OP_DCBLOCK, 0, {input.src, R.op(v_)}); }
+private:
+    maxiVoices* v_;
+};
+
+/* maxiNonlinearity, src/maximilian.h:1046-1137 */
+class maxiNonlinearity {
+public:
+    explicit maxiNonlinearity(maxiVoices& v) : v_(&v) {}
+    maxiSignal atanDist(maxiSignal in, const maxiArg& shape) { return nl(MXB_NL_ATANDIST, in, shape.op(v_), MXB_NONE); }
+    maxiSignal fastAtanDist(maxiSignal in, const maxiArg& shape) { return nl(MXB_NL_FASTATANDIST, in, shape.op(v_), MXB_NONE); }
+    maxiSignal softclip(maxiSignal x) { return nl(MXB_NL_SOFTCLIP, x, MXB_NONE, MXB_NONE); }
+    maxiSignal hardclip(maxiSignal x) { return nl(MXB_NL_HARDCLIP, x, MXB_NONE, MXB_NONE); }
+    maxiSignal asymclip(maxiSignal x, const maxiArg& a, const maxiArg& b) { return nl(MXB_NL_ASYMCLIP, x, a.op(v_), b.op(v_)); }
+    maxiSignal fastatan(maxiSignal x) { return nl(MXB_NL_FASTATAN, x, MXB_NONE, MXB_NONE); }
+private:
+    maxiSignal nl(int kind, maxiSignal x, int32_t p1, int32_t p2) { v_->check(x, "maxiNonlinearity"); return v_->emit(MXB_OP_NONLIN, kind, {x.src, p1, p2}); }
+    maxiVoices* v_;
+};
+using maxiDistortion = maxiNonlinearity;       /* src/maximilian.h:1139 */
+
 /* maxiMix::stereo, src/maximilian.h:400 / src/maximilian.cpp:503-509; the per-voice results are summed into the bus */
 class maxiMix {
 public:
     explicit maxiMix(maxiVoices& v) : v_(&v) {}
-    void stereo(maxiSignal input, maxiBus two, const maxiParam& x) {
-        if (input.voices != v_ || two.voices != v_) throw maxiError(MXB_ERR_UNSUPPORTED, "maxiMix::stereo: signal and bus must belong to the same maxiVoices");
-        v_->setParam(MXB_P_PAN, x); v_->wantMix_ = true;
+    void stereo(maxiSignal input, maxiBus two, const maxiArg& x) {
+        if (two.voices != v_) throw maxiError(MXB_ERR_UNSUPPORTED, "maxiMix::stereo: signal and bus must belong to the same maxiVoices");
+        v_->check(input, "maxiMix::stereo");
+        v_->emit(MXB_OP_MIX_STEREO, 0, {input.src, x.op(v_)}, false);
     }
 private:
     maxiVoices* v_;
@@ -339,7 +619,7 @@ private:
 /* ---- block-dispatch shim: stands in for routing() of cpp/commandline/player.cpp:25-44 (RtAudio callback signature,
  * cpp/commandline/RtAudio.h:205-209). The user supplies  void play(maxiVoices&)  -- the block-rate twin of the
  * reference's  void play(double*)  -- and passes the maxiVoices as userData; the interleaved RTAUDIO_FLOAT64
- * stereo buffer is exactly the bank's mix bus. ---- */
+ * stereo buffer is exactly the patch's mix bus. ---- */
 void play(maxiVoices& voices);
 inline int maxiRouting(void* outputBuffer, void* /*inputBuffer*/, unsigned int nBufferFrames, double /*streamTime*/,
                        unsigned int /*status*/, void* userData) {

@@ -539,6 +539,7 @@ int32_t mxb_bank_process_fm(mxb_bank* b, int32_t n_frames, const double* freq_tv
 
 int32_t mxb_bank_process_mod(mxb_bank* b, int32_t n_frames, const mxb_modulation* mod, const int32_t* trig_on, const int32_t* trig_off,
                              void* out, int32_t out_dtype, double* mix, int32_t mem, void* stream_) {
+    NvtxRange nvtx_("mxb_bank_process_mod");
     MXB_REQUIRE(b, MXB_ERR_INVALID, "mxb_bank_process: NULL bank");
     const double* freq_tv = mod ? mod->freq_tv : nullptr;
     const double* cutoff_tv = mod ? mod->cutoff_tv : nullptr;

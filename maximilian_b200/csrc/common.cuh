@@ -11,6 +11,8 @@
 
 #include "../../include/maxib200.h"
 
+#include <nvtx3/nvToolsExt.h>      // header-only; ranges show up in nsys / ncu --nvtx timelines, cost nothing without a profiler
+
 namespace mxb {
 
 void set_error(const char* fmt, ...);
@@ -31,6 +33,11 @@ void set_error(const char* fmt, ...);
             return (code);                  \
         }                                   \
     } while (0)
+
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
 
 struct DeviceGuard {
     int prev = -1;

@@ -569,6 +569,7 @@ int32_t mxb_patch_get_ring(mxb_patch* p, int32_t stage, int32_t voice, double* d
 int64_t mxb_patch_launch_count(const mxb_patch* p) { return p ? p->launches : 0; }
 
 int32_t mxb_patch_process(mxb_patch* p, int32_t n_frames, const double* const* inputs, double* out, double* mix, int32_t mem, void* stream_) {
+    NvtxRange nvtx_("mxb_patch_process");
     MXB_REQUIRE(p, MXB_ERR_INVALID, "mxb_patch_process: NULL patch");
     MXB_REQUIRE(n_frames >= 0 && n_frames <= p->max_frames, MXB_ERR_INVALID, "mxb_patch_process: n_frames %d (max_frames %d)", n_frames, p->max_frames);
     MXB_REQUIRE(mem == MXB_MEM_HOST || mem == MXB_MEM_DEVICE, MXB_ERR_INVALID, "mxb_patch_process: mem %d", mem);

@@ -104,3 +104,48 @@ def test_patch_through_routing_matches_oracle(port, tmp_path):
         np.testing.assert_allclose(mix[k], mo, rtol=1e-9, atol=1e-11)
     oo, _ = o.process(B, gates[NB][0], gates[NB][1])
     assert np.array_equal(voices, oo)
+
+
+SRC_POLY = os.path.join(ROOT, "tests", "cpp", "patch_polysynth.cpp")
+EXE_POLY = os.path.join(ROOT, "tests", "cpp", "patch_polysynth")
+
+
+def test_polysynth_port_compiles_against_the_dropin_header():
+    """cpp/commandline/maximilian_examples/15.polysynth/main.cpp ported to the block-rate classes: same objects, same expressions."""
+    exe = compile_patch(SRC_POLY, EXE_POLY)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 2 and "usage" in r.stderr
+
+
+@pytest.mark.gpu
+def test_polysynth_port_matches_oracle(port, tmp_path):
+    """The polysynth example (two pulse VCOs summed into a lores VCF, sinebuf LFO on frequency and cutoff, ADSR applied after the filter,
+    notes triggered on single samples by a metronome) through the C++ layer -> patch interpreter, against the same graph
+    (tests/patch_cases.py) run by the C oracle with the trigger stream the C++ control code produced: 1e-9 relative (lores designs its
+    coefficients on every sample: libdevice cos / sqrt / pow)."""
+    import golden_checks as G
+    import patch_cases as PC
+    exe = compile_patch(SRC_POLY, EXE_POLY)
+    g = G.load("tables")
+    np.concatenate([g["sine"], g["transition"], [float(g["sine_before"])]]).astype(np.float64).tofile(tmp_path / "tables.bin")
+    NB, B, V = 12, 512, 6
+    r = subprocess.run([exe, str(tmp_path / "tables.bin"), str(tmp_path / "out.bin"), str(NB), str(B)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    raw = np.fromfile(tmp_path / "out.bin", dtype=np.float64)
+    trig = raw[:NB * B * V].reshape(NB, B, V); out = raw[NB * B * V:].reshape(NB, B, 2)
+    assert trig.sum() == round(NB * B / 44100 * 8 + 0.5) or abs(trig.sum() - NB * B * 8 / 44100) <= 1        # the 8 Hz metronome fired
+    name, d, params, inputs, exact, taps = PC.polysynth()
+    port.set_tables(g["sine"], g["transition"], float(g["sine_before"]), "port")
+    o = port.Patch(d, V, sample_rate=44100, kind="port")
+    pitch = np.arange(1.0, 7.0)
+    lib = port.load("port")
+    vals = dict(attack=lib.mxo_env_attack_coeff(0.0, 44100), decay=lib.mxo_env_decay_coeff(200.0, 44100), sustain=0.2,
+                release=lib.mxo_env_decay_coeff(2000.0, 44100), f1=55.0 * pitch, f2=110.0 * pitch, pitch=pitch, pan=0.5)
+    for k, v in vals.items():
+        o.set(k, v)
+    for blk in range(NB):
+        oo, _ = o.process(B, dict(trigger=trig[blk]))
+        ref = oo.sum(axis=1) * 0.5                                     # mix += VCFout*ADSRout/6 over the six voices; output = mix*0.5
+        np.testing.assert_allclose(out[blk, :, 0], ref, rtol=1e-9, atol=1e-12, err_msg=f"blk{blk}")
+        assert np.array_equal(out[blk, :, 0], out[blk, :, 1])
+    assert np.abs(out).max() > 1e-3
