@@ -13,25 +13,19 @@
 
 #include "maximilian_b200.hpp"
 
-//This shows how to use maximilian to build a polyphonic synth.
-
-//These are the synthesiser bits
+// six voices: two VCOs and an LFO each, one filter, one envelope
 maxiVoices voices(6);
 maxiOsc VCO1(voices), VCO2(voices), LFO1(voices), LFO2(voices);
 maxiFilter VCF(voices);
 maxiEnv ADSR(voices);
 
-//This is a bunch of control signals so that we can hear something
-
-double timerPhase = 0;//this is the metronome (the per-sample control code of the original: timer.phasor(8))
-int currentCount, lastCount, voice = 0;//these values are used to check if we have a new beat this sample
-
-//and these are some variables we can use to pass stuff around
+double timerPhase = 0;               // phase of the 8 Hz metronome (the original's timer.phasor(8))
+int currentCount, lastCount, voice = 0;   // beat detection and the round-robin voice index
 
 vector<double> pitch = {1, 2, 3, 4, 5, 6}, f1(6), f2(6);
-vector<double> trigger;//ADSR[i].trigger for every sample of the block: [frame][voice]
+vector<double> trigger;              // what the original writes into ADSR[i].trigger, for every sample of the block: [frame][voice]
 
-void setup() {//some inits
+void setup() {
     ADSR.setAttack(0);
     ADSR.setDecay(200);
     ADSR.setSustain(0.2);
@@ -39,31 +33,30 @@ void setup() {//some inits
     for (int i = 0; i < 6; i++) { f1[i] = 55 * pitch[i]; f2[i] = 110 * pitch[i]; }
 }
 
-//the control half of the original play(): a metronome that ticks 8 times a second; every tick triggers the next voice for one sample
+// The per-sample CONTROL half of the original play(): on every metronome tick the next voice is triggered for one sample.
 void control(int nFrames) {
     trigger.assign((size_t)nFrames * 6, 0.0);
     for (int t = 0; t < nFrames; t++) {
-        currentCount = (int)timerPhase;//maxiOsc::phasor(8), src/maximilian.cpp:285-291
+        currentCount = (int)timerPhase;                       // maxiOsc::phasor(8), src/maximilian.cpp:285-291
         if (timerPhase >= 1.0) timerPhase -= 1.0;
         timerPhase += (1. / (maxiSettings::sampleRate / (8.)));
-        if (lastCount != currentCount) {//if we have a new timer int this sample, play the sound
+        if (lastCount != currentCount) {                      // a tick
             if (voice == 6) {
                 voice = 0;
             }
-            trigger[(size_t)t * 6 + voice] = 1;//trigger the envelope from the start
+            trigger[(size_t)t * 6 + voice] = 1;
             voice++;
         }
     }
 }
 
 void play(maxiVoices& v) {
-    //and this is where we build the synth
-    maxiSignal ADSRout = ADSR.adsr(1., maxiStream(trigger));//our ADSR env is passed a constant signal of 1 to generate the transient.
-    maxiSignal LFO1out = LFO1.sinebuf(0.2);//this lfo is a sinewave at 0.2 hz
-    maxiSignal VCO1out = VCO1.pulse(f1, 0.6);//here's VCO1. it's a pulse wave at 55 hz, with a pulse width of 0.6
-    maxiSignal VCO2out = VCO2.pulse(f2 + LFO1out, 0.2);//here's VCO2. it's a pulse wave at 110hz with LFO modulation on the frequency, and width of 0.2
-    maxiSignal VCFout = VCF.lores((VCO1out + VCO2out) * 0.5, 250 + ((pitch + LFO1out) * 1000), 10);//now we stick the VCO's into the VCF, using the ADSR as the filter cutoff
-    v.sum(VCFout * ADSRout / 6);//finally we add the ADSR as an amplitude modulator
+    maxiSignal ADSRout = ADSR.adsr(1., maxiStream(trigger));      // envelope of a constant 1
+    maxiSignal LFO1out = LFO1.sinebuf(0.2);                        // 0.2 Hz LFO
+    maxiSignal VCO1out = VCO1.pulse(f1, 0.6);                      // 55 Hz * pitch
+    maxiSignal VCO2out = VCO2.pulse(f2 + LFO1out, 0.2);            // 110 Hz * pitch, LFO on the frequency
+    maxiSignal VCFout = VCF.lores((VCO1out + VCO2out) * 0.5, 250 + ((pitch + LFO1out) * 1000), 10);   // both VCOs into the VCF, LFO on the cutoff
+    v.sum(VCFout * ADSRout / 6);                               // envelope AFTER the filter; mix += ... over the voices
 }
 
 int main(int argc, char** argv) {
@@ -83,8 +76,8 @@ int main(int argc, char** argv) {
             maxiRouting(bus.data(), nullptr, (unsigned)B, 0.0, 0, &voices);      // what the audio driver would call
             for (int t = 0; t < B; ++t) {
                 const double mix = bus[(size_t)t * 2];
-                output.push_back(mix * 0.5);//left channel
-                output.push_back(mix * 0.5);//right channel
+                output.push_back(mix * 0.5);
+                output.push_back(mix * 0.5);
             }
             triggers.insert(triggers.end(), trigger.begin(), trigger.end());
         }
