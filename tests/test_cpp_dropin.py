@@ -128,12 +128,12 @@ def test_polysynth_port_matches_oracle(port, tmp_path):
     exe = compile_patch(SRC_POLY, EXE_POLY)
     g = G.load("tables")
     np.concatenate([g["sine"], g["transition"], [float(g["sine_before"])]]).astype(np.float64).tofile(tmp_path / "tables.bin")
-    NB, B, V = 12, 512, 6
+    NB, B, V = 40, 512, 6
     r = subprocess.run([exe, str(tmp_path / "tables.bin"), str(tmp_path / "out.bin"), str(NB), str(B)], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     raw = np.fromfile(tmp_path / "out.bin", dtype=np.float64)
     trig = raw[:NB * B * V].reshape(NB, B, V); out = raw[NB * B * V:].reshape(NB, B, 2)
-    assert trig.sum() == round(NB * B / 44100 * 8 + 0.5) or abs(trig.sum() - NB * B * 8 / 44100) <= 1        # the 8 Hz metronome fired
+    assert 2 <= trig.sum() <= 4 and abs(trig.sum() - NB * B * 8 / 44100) <= 1        # the 8 Hz metronome fired
     name, d, params, inputs, exact, taps = PC.polysynth()
     port.set_tables(g["sine"], g["transition"], float(g["sine_before"]), "port")
     o = port.Patch(d, V, sample_rate=44100, kind="port")
