@@ -16,9 +16,10 @@
 //     request), windowed and packed in registers -- no staging pass through shared memory.
 //   * the last radix-2 stage, the real-FFT untangling pass and the magnitudes run as ONE pass over shared memory: the
 //     lane that owns point p also owns 256 - p, so it holds all four inputs of bins p, 256 - p, 256 + p and 512 - p.
-//   * mel chains of both frames are spread over the lanes widest first (84 chains over 32 lanes in 3 passes); the DCT of
-//     the 8 frames a 4-warp group has in flight is one fp64 tensor-core row tile behind the group's own named barrier
-//     (one barrier per batch: the mel rows are double-buffered).
+//   * the whole MFCC stage runs on the fp64 tensor cores (mma.sync m8n8k4, SASS DMMA), 8 frames -- one 4-warp group -- at a time:
+//     mel bands = [8 frames x bins] . [bins x 8 filters] per filter tile, walking only the bins the tile's filters cover (the
+//     bank is banded: 377 non-zeros of 21 504), log on the accumulator fragment, then the DCT [8 x filters] . [filters x coeffs];
+//     two named barriers per batch and group (magnitudes ready / mel rows ready), mel rows double-buffered.
 #pragma once
 
 namespace {
@@ -65,16 +66,14 @@ constexpr int kStreamWarps = 8;                 // warps per CTA = channel pairs
 constexpr int kStreamN = 1024, kStreamHalf = 512;
 __device__ __forceinline__ int psi16(int p) { return p + (p >> 4); }          // padded index of a 16-byte point record
 
-struct StreamSmem { size_t off_tw, off_uw, off_win, off_w, off_lo, off_mel, off_work, total; int melstride; };
-__host__ __device__ inline StreamSmem stream_smem_layout(int nw, int nf) {
+struct StreamSmem { size_t off_tw, off_uw, off_win, off_mel, off_work, total; int melstride; };
+__host__ __device__ inline StreamSmem stream_smem_layout(int nf) {
     StreamSmem L;
     L.off_tw = 0;                                                          // float4[512]: (wx, wx, wy, wy) at (be - 1) + n
     L.off_uw = L.off_tw + sizeof(float4) * 512;                            // float4[256]: (wr, wr, wi, wi)
     L.off_win = L.off_uw + sizeof(float4) * 256;                           // float[1024]
-    L.off_w = align16(L.off_win + sizeof(float) * kStreamN);               // double[nw] band weights
-    L.off_lo = align16(L.off_w + sizeof(double) * (size_t)nw);             // int[3*nf]
     L.melstride = (nf + 3) & ~3;
-    L.off_mel = align16(L.off_lo + sizeof(int) * (size_t)(3 * nf));        // double[2][16][melstride]
+    L.off_mel = align16(L.off_win + sizeof(float) * kStreamN);             // double[2][16][melstride]
     L.off_work = align16(L.off_mel + sizeof(double) * 2 * 2 * kStreamWarps * (size_t)L.melstride);
     L.total = L.off_work + sizeof(ulonglong2) * (size_t)kStreamWarps * (kStreamHalf + kStreamHalf / 16);
     return L;
@@ -102,20 +101,16 @@ __global__ void __launch_bounds__(kStreamWarps * 32, 2) stft_stream_kernel(const
     extern __shared__ float4 smem4[];
     unsigned char* sm = (unsigned char*)smem4;
     constexpr int n = kStreamN, half = kStreamHalf;
-    const int nw = a.has_mfcc ? a.mf.nw : 0, nf = a.has_mfcc ? a.mf.filters : 0;
-    const StreamSmem L = stream_smem_layout(nw, nf);
+    const int nf = a.has_mfcc ? a.mf.filters : 0;
+    const StreamSmem L = stream_smem_layout(nf);
     ulonglong2* s_tw = (ulonglong2*)(sm + L.off_tw);
     ulonglong2* s_uw = (ulonglong2*)(sm + L.off_uw);
     float* s_win = (float*)(sm + L.off_win);
-    double* s_w = (double*)(sm + L.off_w);
-    int* s_lo = (int*)(sm + L.off_lo);
     double* s_mel = (double*)(sm + L.off_mel);
     const int melstride = L.melstride;
     for (int i = threadIdx.x; i < half - 1; i += blockDim.x) ((float4*)s_tw)[i] = sa.tw4[i];
     for (int i = threadIdx.x; i < half / 2; i += blockDim.x) ((float4*)s_uw)[i] = sa.uw4[i];
     for (int i = threadIdx.x; i < n; i += blockDim.x) s_win[i] = a.window[i];
-    for (int i = threadIdx.x; i < nw; i += blockDim.x) s_w[i] = a.mf.w[i];
-    for (int i = threadIdx.x; i < nf; i += blockDim.x) { s_lo[i] = a.mf.lo[i]; s_lo[nf + i] = a.mf.cnt[i]; s_lo[2 * nf + i] = a.mf.off[i]; }
     for (int i = threadIdx.x; i < 2 * 2 * kStreamWarps * melstride; i += blockDim.x) s_mel[i] = 0.0;     // K padding stays zero
     __syncthreads();
 
@@ -124,7 +119,9 @@ __global__ void __launch_bounds__(kStreamWarps * 32, 2) stft_stream_kernel(const
     const int Lr = (int)(__brev((unsigned)lane) >> 27);          // bit-reversed lane: the frame samples this lane loads
     const int low4 = lane & 15, b8 = lane >> 4;
     ulonglong2* sW = (ulonglong2*)(sm + L.off_work) + (size_t)warp * (half + half / 16);
-    float* s_mag = (float*)sW;                                   // [2][512] magnitudes, after the spectrum has been consumed
+    // after the spectrum has been consumed the area holds the two frames' magnitudes as doubles, [2][512] (+ a skew of 4 doubles per
+    // warp of the group: the 8 frame rows a tensor-core A fragment touches then fall into different banks)
+    double* d_mag = (double*)sW + 4 * (warp & 3);
 
     const int C = a.C, frames = a.frames, hop = a.hop;
     const int npairs = (C + 1) >> 1;
@@ -139,7 +136,6 @@ __global__ void __launch_bounds__(kStreamWarps * 32, 2) stft_stream_kernel(const
         const int cBs = vB ? cB : cA;                            // a missing second channel re-reads the first (its results are dropped)
 #pragma unroll 1
         for (int f = 0; f < frames; ++f, ++bc) {
-            double* melrow = s_mel + ((size_t)(bc & 1) * 2 * kStreamWarps + 2 * warp) * melstride;     // rows 2w (A), 2w + 1 (B)
             if (vA) {
                 // ---- fft::calcFFT windowing (fft.cpp:499-505) + RealFFT even/odd packing (:238-241) + bit-reversed copy (:146-150):
                 // register r <- complex sample rev4(r)*32 + rev5(lane), i.e. real samples 64*rev4(r) + 2*Lr and the next one
@@ -305,19 +301,19 @@ __global__ void __launch_bounds__(kStreamWarps * 32, 2) stft_stream_kernel(const
                         R[it] = Ak.x; I[it] = Ak.y;
                     }
                 }
-                __syncwarp();                                    // every lane has read its points: the area becomes s_mag[2][512]
+                __syncwarp();                                    // every lane has read its points: the area becomes d_mag[2][512]
 #pragma unroll
                 for (int it = 0; it < 4; ++it) {
                     const int p = it * 32 + lane;
                     const bool special = it == 0 && lane == 0;
                     const int b1 = special ? 128 : p, b3 = special ? 0 : 256 - p;
-                    s_mag[b1] = mg[it][0]; s_mag[half + b1] = mg[it][1];
-                    s_mag[b3] = mg[it][2]; s_mag[half + b3] = mg[it][3];
+                    d_mag[b1] = (double)mg[it][0]; d_mag[half + b1] = (double)mg[it][1];
+                    d_mag[b3] = (double)mg[it][2]; d_mag[half + b3] = (double)mg[it][3];
                     if (FULL) {
                         const int b2 = special ? 384 : 512 - p, b4 = special ? 256 : 256 + p;
                         float x, y;
-                        upk2(R[it], x, y); s_mag[b2] = x; s_mag[half + b2] = y;
-                        upk2(I[it], x, y); s_mag[b4] = x; s_mag[half + b4] = y;
+                        upk2(R[it], x, y); d_mag[b2] = (double)x; d_mag[half + b2] = (double)y;
+                        upk2(I[it], x, y); d_mag[b4] = (double)x; d_mag[half + b4] = (double)y;
                     }
                 }
                 if (feat) {
@@ -341,36 +337,18 @@ __global__ void __launch_bounds__(kStreamWarps * 32, 2) stft_stream_kernel(const
                     }
                 }
                 __syncwarp();
-                // ---- mel stage of maxiMFCC::mfcc (maxiMFCC.cpp:48-66) for both frames: chain g = (filter nf-1-g/2, frame g&1),
-                // widest filters first, ascending-bin fp64 sums exactly like the reference's dense loop ----
-                if (a.has_mfcc) {
-                    for (int g0 = 0; g0 < 2 * nf; g0 += 32) {
-                        const int g = g0 + lane;
-                        const bool act = g < 2 * nf;
-                        const int fl = act ? nf - 1 - (g >> 1) : 0, fr = g & 1;
-                        const int cnt = act ? s_lo[nf + fl] : 0;
-                        const int maxc = __reduce_max_sync(0xffffffffu, cnt);     // warp-uniform trip count, predicated body
-                        const double* w = s_w + s_lo[2 * nf + fl];
-                        const float* mag = s_mag + fr * half + s_lo[fl];
-                        double acc = 0.0;
-#pragma unroll 4
-                        for (int q = 0; q < maxc; ++q)
-                            if (q < cnt) acc = __dadd_rn(acc, __dmul_rn(w[q], (double)mag[q]));
-                        if (act) melrow[fr * melstride + fl] = acc > 0.000001 ? log(__dmul_rn(acc, acc)) : 0.0;
-                    }
-                }
                 if (FULL && (a.oct_nruns > 0 || a.bark_lim != nullptr)) {
                     // ---- maxiFFTOctaveAnalyzer::calculate (maxiFFT.cpp:264-300) and maxiBark (maxiBark.h:63-113) on the magnitudes
                     // still in shared memory. Octave: one lane per run of bins (the reference's running float sum closes a run ON the
                     // first bin of the next averaging band), then one lane per averaging band for the peak-hold logic; the bands'
                     // averages / peaks / hold counters are per-channel state carried from frame to frame in HBM (this warp walks
                     // the channel's frames in order). Bark: one lane per band, double sums in bin order, pow, max, total.
-                    double* bsc = (double*)sW + 512;                          // 24 doubles of scratch behind s_mag[2][512]
+                    double* bsc = (double*)sW + 1040;                         // 24 doubles of scratch behind d_mag[2][512] (+ skew)
 #pragma unroll 1
                     for (int fr = 0; fr < 2; ++fr) {
                         const int c = fr ? cB : cA;
                         if (c >= C) break;
-                        const float* mag = s_mag + fr * half;
+                        const double* mag = d_mag + fr * half;                // floats stored as doubles: the conversions back are exact
                         const size_t of = (size_t)c * a.max_frames + f;
                         if (a.oct_nruns > 0) {
                             const int nA = a.oct_navg;
@@ -379,7 +357,7 @@ __global__ void __launch_bounds__(kStreamWarps * 32, 2) stft_stream_kernel(const
                                 const int4 run = ((const int4*)a.oct_runs)[r];          // first bin, last bin, first band, one past the last band
                                 float sum = 0.f;
                                 for (int b = run.x; b <= run.y; ++b)
-                                    sum = __fadd_rn(sum, __fmul_rn(mag[b], __fadd_rn(a.oct_icpt, __fmul_rn((float)b, a.oct_slope))));
+                                    sum = __fadd_rn(sum, __fmul_rn((float)mag[b], __fadd_rn(a.oct_icpt, __fmul_rn((float)b, a.oct_slope))));
                                 const float av = __fdiv_rn(sum, (float)(run.y - run.x + 1));
                                 for (int j = run.z; j < run.w; ++j) avs[j] = av;
                             }
@@ -399,7 +377,7 @@ __global__ void __launch_bounds__(kStreamWarps * 32, 2) stft_stream_kernel(const
                             double spec = 0.0;
                             if (lane < 24) {
                                 double sum = 0.0;
-                                for (int j = a.bark_lim[lane]; j < a.bark_lim[lane + 1]; ++j) sum = __dadd_rn(sum, (double)mag[j]);
+                                for (int j = a.bark_lim[lane]; j < a.bark_lim[lane + 1]; ++j) sum = __dadd_rn(sum, mag[j]);
                                 spec = pow(sum, 0.23);
                                 bsc[lane] = spec;
                             }
@@ -422,20 +400,50 @@ __global__ void __launch_bounds__(kStreamWarps * 32, 2) stft_stream_kernel(const
                 }
                 __syncwarp();
             } else if (a.has_mfcc) {
-                for (int k = lane; k < 2 * melstride; k += 32) melrow[k] = 0.0;
+                for (int k = lane; k < 2 * half; k += 32) d_mag[k] = 0.0;     // a warp without a channel pair contributes silent frames
+                __syncwarp();
             }
             if (a.has_mfcc) {
-                // ---- maxiMFCC::dct (maxiMFCC.h:98-111): the 8 frames of a 4-warp group are one row tile of a fp64 tensor-core
-                // contraction [8 x filters] . [filters x coeffs] (mma.sync m8n8k4, SASS DMMA); the group meets at its own named
-                // barrier once per batch (mel rows double-buffered), the column tiles are dealt over its 4 warps. The B
-                // fragments come pre-arranged per (tile, k-step, lane) from global memory (L1-resident, one coalesced request). ----
+                // ---- maxiMFCC::mfcc (maxiMFCC.h:77-111, maxiMFCC.cpp:48-66) for the 8 frames of this 4-warp group, on the fp64 tensor
+                // cores (mma.sync m8n8k4, SASS DMMA). Frame row r of the group = warp r/2, channel A / B = r%2.
+                //   mel:  per tile of 8 filters  C[8 x 8] = mags[8 x bins] . W[bins x 8]  over the bins the tile's filters cover
+                //         (k-steps of 4 bins; B fragments pre-arranged per (tile, k-step, lane), zero outside the bands), then the
+                //         gate and log on the accumulator fragment: melBands = sum > 1e-6 ? log(sum^2) : 0
+                //   DCT:  per tile of 8 coefficients  C[8 x 8] = melBands[8 x filters] . D[filters x 8], / numCoeffs
+                // The tensor core adds in its own order: results agree with the reference's sequential sums to fp64 reassociation
+                // (~1e-15 relative; asserted at 1e-9). Two named barriers per batch and group; the mel rows are double-buffered.
                 const int grp = warp >> 2, wg = warp & 3;
+                const int row = lane >> 2, kk = lane & 3;
                 if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory");       // literal ids: a register id would reserve all 16 barriers
-                else asm volatile("bar.sync 2, 128;" ::: "memory");
-                const double* arow = s_mel + ((size_t)(bc & 1) * 2 * kStreamWarps + 8 * grp + (lane >> 2)) * melstride + (lane & 3);
+                else asm volatile("bar.sync 2, 128;" ::: "memory");                // the group's 8 magnitude rows are in shared memory
+                double* melbuf = s_mel + (size_t)(bc & 1) * 2 * kStreamWarps * melstride;
+                {
+                    const double* amag = (const double*)((ulonglong2*)(sm + L.off_work) + (size_t)(4 * grp + (row >> 1)) * (half + half / 16)) +
+                                         4 * (row >> 1) + (row & 1) * half + kk;      // row r: warp 4*grp + r/2 (skew 4*(r/2)), frame r%2
+                    double* mr = melbuf + (size_t)(8 * grp + row) * melstride;
+                    for (int nt = wg; nt < a.mf.mel_ntiles; nt += 4) {
+                        const int4 tile = __ldg((const int4*)a.mf.mel_tiles + nt);       // fragment offset, first bin, k-steps
+                        const double* bfrag = a.mf.melf + (size_t)tile.x * 32 + lane;
+                        const double* ap = amag + tile.y;
+                        double c0 = 0.0, c1 = 0.0;
+#pragma unroll 4
+                        for (int ks = 0; ks < tile.z; ++ks) {
+                            const double av = ap[4 * ks];
+                            const double bv = __ldg(bfrag + 32 * ks);
+                            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};\n"
+                                         : "+d"(c0), "+d"(c1) : "d"(av), "d"(bv));
+                        }
+                        const int f0 = nt * 8 + 2 * kk;
+                        if (f0 < nf) mr[f0] = c0 > 0.000001 ? log(__dmul_rn(c0, c0)) : 0.0;
+                        if (f0 + 1 < nf) mr[f0 + 1] = c1 > 0.000001 ? log(__dmul_rn(c1, c1)) : 0.0;
+                    }
+                }
+                if (grp == 0) asm volatile("bar.sync 3, 128;" ::: "memory");
+                else asm volatile("bar.sync 4, 128;" ::: "memory");                // the group's 8 mel rows are complete, its magnitudes consumed
+                const double* arow = melbuf + (size_t)(8 * grp + row) * melstride + kk;
                 const int ntiles = (a.mf.coeffs + 7) >> 3, ksteps = melstride >> 2;
                 const double ncf = (double)(unsigned)a.mf.coeffs;
-                for (int nt = wg; nt < ntiles; nt += 4) {
+                for (int nt = (wg + 2) & 3; nt < ntiles; nt += 4) {                 // warps 2, 3 first: warps 0, 1 had two mel tiles
                     const double* bfrag = a.mf.dctf + (size_t)nt * ksteps * 32 + lane;
                     double c0 = 0.0, c1 = 0.0;
 #pragma unroll 4
@@ -445,11 +453,11 @@ __global__ void __launch_bounds__(kStreamWarps * 32, 2) stft_stream_kernel(const
                         asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};\n"
                                      : "+d"(c0), "+d"(c1) : "d"(av), "d"(bv));
                     }
-                    const int fi = 8 * grp + (lane >> 2);        // frame of the CTA's batch: warp fi >> 1, channel A / B = fi & 1
+                    const int fi = 8 * grp + row;                // frame of the CTA's batch: warp fi >> 1, channel A / B = fi & 1
                     const int ch = 2 * (pb * kStreamWarps + (fi >> 1)) + (fi & 1);
                     if (ch < C) {
                         double* o = a.coeffs + ((size_t)ch * a.max_frames + f) * a.mf.coeffs;
-                        const int cc = nt * 8 + 2 * (lane & 3);
+                        const int cc = nt * 8 + 2 * kk;
                         if (cc < a.mf.coeffs) o[cc] = c0 / ncf;
                         if (cc + 1 < a.mf.coeffs) o[cc + 1] = c1 / ncf;
                     }

@@ -6,3 +6,7 @@ timeout 300 python bench.py --workload delay --steps 40 --warmup 5 --no-cpu > gp
 python -c "
 import json; d=json.loads(open('gpurun_out/d_bench_delay.json').read().strip().splitlines()[-1]); print('delay', d['value'], d['roofline']['frac'], 'e2e', d['e2e']['value'])"
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:delay_bank_kernel -s 3 -c 1 -f -o gpurun_out/prof_r02_delay_bulk_v2 python bench.py --workload delay --steps 3 --warmup 3 --no-cpu > /dev/null 2>&1; echo ncu-delay rc=$?
+timeout 300 python bench.py --workload mfcc --steps 30 --warmup 5 --no-cpu > gpurun_out/d_bench_mfcc.json 2> gpurun_out/d_bench_mfcc.err; echo "mfcc rc=$?"; tail -c 300 gpurun_out/d_bench_mfcc.err
+python -c "
+import json; d=json.loads(open('gpurun_out/d_bench_mfcc.json').read().strip().splitlines()[-1]); print('mfcc', d['value'], d['roofline']['frac'], 'e2e', d['e2e']['value'])"
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:stft_stream -s 3 -c 1 -f -o gpurun_out/prof_r02_stft_stream_v3 python bench.py --workload mfcc --steps 3 --warmup 3 --no-cpu > /dev/null 2>&1; echo ncu-stft rc=$?
