@@ -21,6 +21,7 @@
 //     bank is banded: 377 non-zeros of 21 504), log on the accumulator fragment, then the DCT [8 x filters] . [filters x coeffs];
 //     two named barriers per batch and group (magnitudes ready / mel rows ready), mel rows double-buffered.
 #pragma once
+#include <type_traits>
 
 namespace {
 
@@ -154,23 +155,34 @@ __global__ void __launch_bounds__(kStreamWarps * 32, 2) stft_stream_kernel(const
                 if (vec) {
                     const float* wl = s_win + 2 * Lr;
                     const float *hA = hpA + 2 * Lr, *hB = hpB + 2 * Lr, *iA = ipA + 2 * Lr, *iB = ipB + 2 * Lr;
+                    // QS = split / 64 known at compile time (8: the steady state of hop 512; 0: all new; 16: all history) turns the
+                    // choice of source into straight-line code; any other boundary selects per request (warp-uniform predicate)
+                    auto load = [&](auto QS) {
+                        constexpr int qs = decltype(QS)::value;
 #pragma unroll
-                    for (int g = 0; g < 2; ++g) {          // two groups of eight requests per channel: 32 raw values in flight
-                        float2 xa[8], xb[8];
+                        for (int g = 0; g < 2; ++g) {          // two groups of eight requests per channel: 32 raw values in flight
+                            float2 xa[8], xb[8];
 #pragma unroll
-                        for (int k = 0; k < 8; ++k) {
-                            const int r = 8 * g + k;
-                            const bool fromhist = 64 * brev4c(r) < split;      // warp-uniform
-                            xa[k] = *(const float2*)((fromhist ? hA : iA) + 64 * brev4c(r));
-                            xb[k] = *(const float2*)((fromhist ? hB : iB) + 64 * brev4c(r));
+                            for (int k = 0; k < 8; ++k) {
+                                const int r = 8 * g + k;
+                                const bool fromhist = qs >= 0 ? brev4c(r) < qs : 64 * brev4c(r) < split;
+                                xa[k] = *(const float2*)((fromhist ? hA : iA) + 64 * brev4c(r));
+                                xb[k] = *(const float2*)((fromhist ? hB : iB) + 64 * brev4c(r));
+                            }
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) {
+                                const int r = 8 * g + k;
+                                const float2 w = *(const float2*)(wl + 64 * brev4c(r));
+                                R[r] = pk2(__fmul_rn(xa[k].x, w.x), __fmul_rn(xb[k].x, w.x));
+                                I[r] = pk2(__fmul_rn(xa[k].y, w.y), __fmul_rn(xb[k].y, w.y));
+                            }
                         }
-#pragma unroll
-                        for (int k = 0; k < 8; ++k) {
-                            const int r = 8 * g + k;
-                            const float2 w = *(const float2*)(wl + 64 * brev4c(r));
-                            R[r] = pk2(__fmul_rn(xa[k].x, w.x), __fmul_rn(xb[k].x, w.x));
-                            I[r] = pk2(__fmul_rn(xa[k].y, w.y), __fmul_rn(xb[k].y, w.y));
-                        }
+                    };
+                    switch (split >> 6) {
+                        case 8: load(std::integral_constant<int, 8>()); break;
+                        case 0: load(std::integral_constant<int, 0>()); break;
+                        case 16: load(std::integral_constant<int, 16>()); break;
+                        default: load(std::integral_constant<int, -1>()); break;
                     }
                 } else {
 #pragma unroll
