@@ -40,8 +40,15 @@ constexpr int kDlRow = kDlT;                      // tile row stride in doubles:
 constexpr int kStageDoubles = 32 * kDlRow;        // one staged window tile per warp (4 KB: the image one bulk copy moves)
 // CTA shape of K2. Without a mix tile a warp needs 8 KB of staging: 14 warps per CTA, 2 CTAs per SM = 28 warps/SM, and 256 Ki
 // voices (8192 voice-warps over 148 SMs) run as two full waves. With the mix tile (12.9 KB per warp): 4 warps per CTA.
-template <bool MIX> struct DelayShape { static constexpr int kThreads = MIX ? 128 : 448; };
-constexpr int kDlStages = 2;                      // double buffer
+#ifndef MXB_DL_THREADS
+#define MXB_DL_THREADS 128
+#endif
+#ifndef MXB_DL_STAGES
+#define MXB_DL_STAGES 2
+#endif
+template <bool MIX> struct DelayShape { static constexpr int kThreads = MIX ? 128 : MXB_DL_THREADS; };
+constexpr int kDlStages = MXB_DL_STAGES;          // staged windows per warp: the bulk path requests kDlStages - 1 windows ahead
+static_assert(kDlStages >= 2 && kDlStages <= 8, "stages");
 constexpr int kDlVoicesPerReq = 32 / kDlT;        // voices covered by one cooperative request (2)
 constexpr int kMixDoubles = 2 * kMixTT * 33;
 constexpr int kFastMinSize = 2 * kDlT;
@@ -75,6 +82,7 @@ __device__ __forceinline__ void bulk_s2g(void* gdst, const void* smem_src, unsig
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }   // sources read: smem reusable
+__device__ __forceinline__ void bulk_wait_but1() { asm volatile("cp.async.bulk.wait_group 1;" ::: "memory"); }         // all but the latest group performed
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }           // writes performed
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
@@ -246,31 +254,49 @@ __global__ void __launch_bounds__(DelayShape<MIX>::kThreads) delay_bank_kernel(c
         const unsigned bytes = (unsigned)nlive * (kDlChunk * 8u);
         unsigned long long* bar = s_bar[threadIdx.x >> 5];
         double* run = d.ring + (size_t)v0 * kDlChunk;                      // chunk c of this warp's voices starts at run + c * V * 16
-        if (lane == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); }
+        if (lane == 0) {
+#pragma unroll
+            for (int i = 0; i < kDlStages; ++i) mbar_init(&bar[i], 1);
+        }
         fence_proxy_async();                                                // the initialised barriers become visible to the copy engine
         __syncwarp();
-        if (lane == 0) { mbar_expect_tx(&bar[0], bytes); bulk_g2s(wsm, run + (size_t)chunk * V * kDlChunk, bytes, &bar[0]); }
+        // Window k lives in stage k % kDlStages and is requested `ahead` windows early. The windows in flight must be distinct chunks
+        // of the ring (a short ring falls back to one window ahead), and the chunk a request reads must not be the target of a
+        // write-back still under way: the write-back of window k - j hits the chunk of window k + ahead when ahead + j is a multiple
+        // of nchunks, first at j = nchunks - ahead. j = 1 is the group committed last: then every write-back has to be performed
+        // before the request; otherwise all but the latest (cp.async.bulk.wait_group 1).
+        const int ahead = nchunks >= kDlStages ? kDlStages - 1 : 1;
+        const bool tight = nchunks - ahead < 2;
+        auto chunk_of = [&](int kk) { return (int)(((long long)(base0 >> kDlShift) + kk) % nchunks); };
+        if (lane == 0) {
+            for (int j = 0; j < ahead && j < nstages; ++j) {
+                mbar_expect_tx(&bar[j], bytes);
+                bulk_g2s(wsm + j * kStageDoubles, run + (size_t)chunk_of(j) * V * kDlChunk, bytes, &bar[j]);
+            }
+        }
         const int swz = lane & (kDlChunk - 1);
+        int sidx = 0, nidx = ahead % kDlStages;                            // stage of window k / of window k + ahead
+        unsigned par = 0;                                                   // parity of stage sidx's barrier: flips every kDlStages windows
+        int nchunk = chunk_of(ahead);
         for (int k = 0; k < nstages; ++k) {
-            const int sidx = k & 1;
             double* buf = wsm + sidx * kStageDoubles;
             const int t0 = k * kDlT;
             const int tn = min(kDlT, a.n_frames - t0);
-            int next_chunk = chunk + 1;
-            if (next_chunk >= nchunks) next_chunk = 0;
-            if (k + 1 < nstages && lane == 0) {
-                // the other stage still feeds the write-back of window k-1: wait until the engine has READ it (a ring of two chunks
-                // also needs that write-back performed: the next window is the very chunk it writes)
-                if (nchunks < 3) bulk_wait_all(); else bulk_wait_read0();
-                mbar_expect_tx(&bar[sidx ^ 1], bytes);
-                bulk_g2s(wsm + (sidx ^ 1) * kStageDoubles, run + (size_t)next_chunk * V * kDlChunk, bytes, &bar[sidx ^ 1]);
+            if (k + ahead < nstages && lane == 0) {
+                // stage nidx last held window k + ahead - kDlStages (<= k - 1), source of a write-back: wait until the engine has READ it
+                if (tight) bulk_wait_all(); else { bulk_wait_read0(); bulk_wait_but1(); }
+                mbar_expect_tx(&bar[nidx], bytes);
+                bulk_g2s(wsm + nidx * kStageDoubles, run + (size_t)nchunk * V * kDlChunk, bytes, &bar[nidx]);
             }
-            mbar_wait(&bar[sidx], (unsigned)(k >> 1) & 1u);                 // window k has landed
+            mbar_wait(&bar[sidx], par);                                     // window k has landed
             dl_window<OSC, FILT, ENV, true, OUTMODE, MIX>(s, buf + lane * kDlChunk, tn, t0, a, d, V, (size_t)vv, lane, gwarp, mixtile, swz);
             fence_proxy_async();                                            // this lane's updates of the window, ordered before the engine reads them
             __syncwarp();
             if (lane == 0) { bulk_s2g(run + (size_t)chunk * V * kDlChunk, buf, bytes); bulk_commit(); }
-            chunk = next_chunk;
+            if (++chunk >= nchunks) chunk = 0;
+            if (++nchunk >= nchunks) nchunk = 0;
+            if (++sidx == kDlStages) { sidx = 0; par ^= 1u; }
+            if (++nidx == kDlStages) nidx = 0;
         }
         if (lane == 0) bulk_wait_all();
         // phase += 1 after the last access: the window of the last stage started at slot 16*last_chunk

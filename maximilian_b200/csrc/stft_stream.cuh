@@ -27,6 +27,36 @@ namespace {
 
 typedef unsigned long long u64;
 
+// One m8n8k4 fp64 tensor-core step (SASS DMMA): C[8 x 8] += A[8 x 4] . B[4 x 8]; lane holds A[lane / 4][lane % 4], B[lane % 4][lane / 4],
+// C[lane / 4][2 * (lane % 4) + {0, 1}].
+__device__ __forceinline__ void dmma884(double& c0, double& c1, const double av, const double bv) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};\n" : "+d"(c0), "+d"(c1) : "d"(av), "d"(bv));
+}
+// C = A . B over `ksteps` k-steps: A from shared memory (this lane's element of k-step ks at ap[4 * ks]), B pre-arranged fragments in
+// global memory (bfrag[32 * ks]). A single accumulator would make every step wait for the one before it AND for its own loads; here four
+// accumulators take the k-steps round robin and the operands of four steps are requested together.
+// The order of the fp64 additions is fixed (by k-step mod 4, then ((0 + 1) + (2 + 3))): results are reproducible from run to run.
+__device__ __forceinline__ void dmma_tile(const double* __restrict__ ap, const double* __restrict__ bfrag, const int ksteps, double& c0, double& c1) {
+    double acc[4][2] = {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}};
+    const int groups = ksteps >> 2;
+#pragma unroll 1
+    for (int g = 0; g < groups; ++g) {
+        double av[4], bv[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { av[i] = ap[16 * g + 4 * i]; bv[i] = __ldg(bfrag + 128 * g + 32 * i); }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) dmma884(acc[i][0], acc[i][1], av[i], bv[i]);
+    }
+    for (int ks = 4 * groups, i = 0; ks < ksteps; ++ks, ++i) {
+        const double x = ap[4 * ks], y = __ldg(bfrag + 32 * ks);
+        if (i == 0) dmma884(acc[0][0], acc[0][1], x, y);
+        else if (i == 1) dmma884(acc[1][0], acc[1][1], x, y);
+        else dmma884(acc[2][0], acc[2][1], x, y);
+    }
+    c0 = __dadd_rn(__dadd_rn(acc[0][0], acc[1][0]), __dadd_rn(acc[2][0], acc[3][0]));
+    c1 = __dadd_rn(__dadd_rn(acc[0][1], acc[1][1]), __dadd_rn(acc[2][1], acc[3][1]));
+}
+
 __device__ __forceinline__ u64 pk2(float lo, float hi) { u64 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
 __device__ __forceinline__ void upk2(u64 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
 __device__ __forceinline__ u64 add2(u64 a, u64 b) { u64 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
@@ -426,6 +456,9 @@ __global__ void __launch_bounds__(kStreamWarps * 32, 2) stft_stream_kernel(const
                 // (~1e-15 relative; asserted at 1e-9). Two named barriers per batch and group; the mel rows are double-buffered.
                 const int grp = warp >> 2, wg = warp & 3;
                 const int row = lane >> 2, kk = lane & 3;
+                int nt = a.mf.mel_ntiles - 1 - wg;                                  // this warp's first mel tile: its descriptor (fragment
+                int4 tile = make_int4(0, 0, 0, 0);                                  // offset, first bin, k-steps) is requested before the wait
+                if (nt >= 0) tile = __ldg((const int4*)a.mf.mel_tiles + nt);
                 if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory");       // literal ids: a register id would reserve all 16 barriers
                 else asm volatile("bar.sync 2, 128;" ::: "memory");                // the group's 8 magnitude rows are in shared memory
                 double* melbuf = s_mel + (size_t)(bc & 1) * 2 * kStreamWarps * melstride;
@@ -433,21 +466,17 @@ __global__ void __launch_bounds__(kStreamWarps * 32, 2) stft_stream_kernel(const
                     const double* amag = (const double*)((ulonglong2*)(sm + L.off_work) + (size_t)(4 * grp + (row >> 1)) * (half + half / 16)) +
                                          4 * (row >> 1) + (row & 1) * half + kk;      // row r: warp 4*grp + r/2 (skew 4*(r/2)), frame r%2
                     double* mr = melbuf + (size_t)(8 * grp + row) * melstride;
-                    for (int nt = wg; nt < a.mf.mel_ntiles; nt += 4) {
-                        const int4 tile = __ldg((const int4*)a.mf.mel_tiles + nt);       // fragment offset, first bin, k-steps
-                        const double* bfrag = a.mf.melf + (size_t)tile.x * 32 + lane;
-                        const double* ap = amag + tile.y;
-                        double c0 = 0.0, c1 = 0.0;
-#pragma unroll 4
-                        for (int ks = 0; ks < tile.z; ++ks) {
-                            const double av = ap[4 * ks];
-                            const double bv = __ldg(bfrag + 32 * ks);
-                            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};\n"
-                                         : "+d"(c0), "+d"(c1) : "d"(av), "d"(bv));
-                        }
+                    // tiles from the top down: the widest bands (most k-steps) go to four different warps
+                    while (nt >= 0) {
+                        const int ntn = nt - 4;
+                        int4 tilen = tile;
+                        if (ntn >= 0) tilen = __ldg((const int4*)a.mf.mel_tiles + ntn);   // the next descriptor travels during this tile
+                        double c0, c1;
+                        dmma_tile(amag + tile.y, a.mf.melf + (size_t)tile.x * 32 + lane, tile.z, c0, c1);
                         const int f0 = nt * 8 + 2 * kk;
                         if (f0 < nf) mr[f0] = c0 > 0.000001 ? log(__dmul_rn(c0, c0)) : 0.0;
                         if (f0 + 1 < nf) mr[f0 + 1] = c1 > 0.000001 ? log(__dmul_rn(c1, c1)) : 0.0;
+                        nt = ntn; tile = tilen;
                     }
                 }
                 if (grp == 0) asm volatile("bar.sync 3, 128;" ::: "memory");
@@ -455,16 +484,9 @@ __global__ void __launch_bounds__(kStreamWarps * 32, 2) stft_stream_kernel(const
                 const double* arow = melbuf + (size_t)(8 * grp + row) * melstride + kk;
                 const int ntiles = (a.mf.coeffs + 7) >> 3, ksteps = melstride >> 2;
                 const double ncf = (double)(unsigned)a.mf.coeffs;
-                for (int nt = (wg + 2) & 3; nt < ntiles; nt += 4) {                 // warps 2, 3 first: warps 0, 1 had two mel tiles
-                    const double* bfrag = a.mf.dctf + (size_t)nt * ksteps * 32 + lane;
-                    double c0 = 0.0, c1 = 0.0;
-#pragma unroll 4
-                    for (int ks = 0; ks < ksteps; ++ks) {
-                        const double av = arow[4 * ks];                                   // columns >= filters are zero
-                        const double bv = __ldg(bfrag + 32 * ks);
-                        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};\n"
-                                     : "+d"(c0), "+d"(c1) : "d"(av), "d"(bv));
-                    }
+                for (int nt = 3 - wg; nt < ntiles; nt += 4) {                       // warps 3, 2 first: they had the narrowest mel tiles
+                    double c0, c1;
+                    dmma_tile(arow, a.mf.dctf + (size_t)nt * ksteps * 32 + lane, ksteps, c0, c1);   // columns >= filters are zero
                     const int fi = 8 * grp + row;                // frame of the CTA's batch: warp fi >> 1, channel A / B = fi & 1
                     const int ch = 2 * (pb * kStreamWarps + (fi >> 1)) + (fi & 1);
                     if (ch < C) {

@@ -17,6 +17,7 @@ from collections import defaultdict
 rep, obj, sym = sys.argv[1], sys.argv[2], sys.argv[3]
 units = float(sys.argv[4]) if len(sys.argv) > 4 else 1.0
 top = int(sys.argv[5]) if len(sys.argv) > 5 else 40
+by_stall = os.environ.get("BY_STALL") == "1"      # order by stall samples instead of executed instructions
 
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass"], capture_output=True, text=True).stdout
 rows = list(csv.reader(src.splitlines()))
@@ -49,10 +50,10 @@ for (loc, _), (_, e, s) in zip(lines, prof):
     agg[loc][0] += e; agg[loc][1] += s
 srcs = {}
 print(f"{tot / units:.1f} warp instructions per unit; top {top} source lines")
-for loc, (e, s) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:top]:
+for loc, (e, s) in sorted(agg.items(), key=lambda kv: -kv[1][1 if by_stall else 0])[:top]:
     f, n = loc if loc else ("?", 0)
     if f not in srcs:
-        p = os.path.join(os.path.dirname(os.path.abspath(obj)), "..", "csrc", f)
+        p = os.path.join(os.environ.get("CSRC", os.path.join(os.path.dirname(os.path.abspath(obj)), "..", "csrc")), f)
         srcs[f] = open(p).read().splitlines() if os.path.exists(p) else []
     text = srcs[f][n - 1].strip()[:100] if 0 < n <= len(srcs[f]) else ""
     print(f"{e / units:9.1f} ({e / tot * 100:5.1f}%)  stall {s / ts * 100:5.1f}%  {f}:{n}  {text}")
