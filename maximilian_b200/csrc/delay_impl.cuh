@@ -50,7 +50,8 @@ template <bool MIX> struct DelayShape { static constexpr int kThreads = MIX ? 12
 constexpr int kDlStages = MXB_DL_STAGES;          // staged windows per warp: the bulk path requests kDlStages - 1 windows ahead
 static_assert(kDlStages >= 2 && kDlStages <= 8, "stages");
 constexpr int kDlVoicesPerReq = 32 / kDlT;        // voices covered by one cooperative request (2)
-constexpr int kMixDoubles = 2 * kMixTT * 33;
+constexpr int kDlMixStride = 32 + 4;                // K2 mix tile: [kMixTT][36] raw samples ++ gains[32][2] (bank_kernels.cuh: mix_tile_dmma)
+constexpr int kMixDoubles = kMixTT * kDlMixStride + 64;
 constexpr int kFastMinSize = 2 * kDlT;
 constexpr unsigned kFull = 0xffffffffu;
 enum { DL_OUT_NONE = 0, DL_OUT_F64 = 1, DL_OUT_F32 = 2 };
@@ -73,6 +74,21 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* b, unsigned parity
     asm volatile("{\n.reg .pred p;\nMXB_WAIT_%=:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra MXB_DONE_%=;\nbra MXB_WAIT_%=;\nMXB_DONE_%=:\n}"
                  ::"r"(smem_u32(b)), "r"(parity) : "memory");
 }
+#ifdef MXB_DL_L2HINT      // A/B: ring chunks pass through L2 as evict-first (each is touched once per trip round the ring)
+__device__ __forceinline__ unsigned long long l2_evict_first() {
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, unsigned bytes, unsigned long long* b) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(b)), "l"(l2_evict_first()) : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void* gdst, const void* smem_src, unsigned bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;"
+                 ::"l"(gdst), "r"(smem_u32(smem_src)), "r"(bytes), "l"(l2_evict_first()) : "memory");
+}
+#else
 __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, unsigned bytes, unsigned long long* b) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(b)) : "memory");
@@ -80,9 +96,10 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, unsig
 __device__ __forceinline__ void bulk_s2g(void* gdst, const void* smem_src, unsigned bytes) {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(smem_src)), "r"(bytes) : "memory");
 }
+#endif
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }   // sources read: smem reusable
-__device__ __forceinline__ void bulk_wait_but1() { asm volatile("cp.async.bulk.wait_group 1;" ::: "memory"); }         // all but the latest group performed
+__device__ __forceinline__ void bulk_wait_but7() { asm volatile("cp.async.bulk.wait_group 7;" ::: "memory"); }         // all but the latest 7 groups performed
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }           // writes performed
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
@@ -145,21 +162,11 @@ __device__ __forceinline__ void dl_stage(DlVoice& s, double* row, const int tn, 
         }
         if (OUTMODE == DL_OUT_F64) { if (s.live) __stcs(out64, y); out64 += V; }
         if (OUTMODE == DL_OUT_F32) { if (s.live) __stcs(out32, (float)y); out32 += V; }
-        if (MIX) {
-            mixtile[(0 * kMixTT + j) * 33 + lane] = y * s.gl;
-            mixtile[(1 * kMixTT + j) * 33 + lane] = y * s.gr;
-        }
+        if (MIX) mixtile[j * kDlMixStride + lane] = y;
     }
     if (MIX) {
         __syncwarp();
-        const int ch = lane >> 4, rw = lane & 15;
-        if (rw < tn) {
-            const double* r = mixtile + (ch * kMixTT + rw) * 33;
-            double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;       // fixed order: deterministic
-#pragma unroll
-            for (int q = 0; q < 32; q += 4) { s0 += r[q]; s1 += r[q + 1]; s2 += r[q + 2]; s3 += r[q + 3]; }
-            a.partials[((size_t)(t0 + rw) * 2 + ch) * (size_t)a.W + (size_t)gwarp] = (s0 + s1) + (s2 + s3);
-        }
+        mix_tile_dmma<32, kMixTT>(mixtile, mixtile + kMixTT * kDlMixStride, tn, t0, a.partials, (size_t)a.W, (size_t)gwarp, lane);
         __syncwarp();
     }
 }
@@ -231,6 +238,9 @@ __global__ void __launch_bounds__(DelayShape<MIX>::kThreads) delay_bank_kernel(c
         if (x < 0) x = 0;
         s.gl = s.live ? sqrt(1.0 - x) : 0.0;
         s.gr = s.live ? sqrt(x) : 0.0;
+        mixtile[kMixTT * kDlMixStride + lane * 2 + 0] = s.gl;          // the warp's gain table behind its tile
+        mixtile[kMixTT * kDlMixStride + lane * 2 + 1] = s.gr;
+        __syncwarp();
     }
     s.ph = d.phase[vv];
     s.size = d.size[vv];
@@ -263,10 +273,11 @@ __global__ void __launch_bounds__(DelayShape<MIX>::kThreads) delay_bank_kernel(c
         // Window k lives in stage k % kDlStages and is requested `ahead` windows early. The windows in flight must be distinct chunks
         // of the ring (a short ring falls back to one window ahead), and the chunk a request reads must not be the target of a
         // write-back still under way: the write-back of window k - j hits the chunk of window k + ahead when ahead + j is a multiple
-        // of nchunks, first at j = nchunks - ahead. j = 1 is the group committed last: then every write-back has to be performed
-        // before the request; otherwise all but the latest (cp.async.bulk.wait_group 1).
+        // of nchunks, first at j = nchunks - ahead. A ring of at least ahead + 8 chunks only needs the write-backs older than the
+        // latest seven performed (cp.async.bulk.wait_group 7: they were issued seven windows ago, the wait is free); a shorter
+        // ring waits for all of them.
         const int ahead = nchunks >= kDlStages ? kDlStages - 1 : 1;
-        const bool tight = nchunks - ahead < 2;
+        const bool tight = nchunks - ahead < 8;
         auto chunk_of = [&](int kk) { return (int)(((long long)(base0 >> kDlShift) + kk) % nchunks); };
         if (lane == 0) {
             for (int j = 0; j < ahead && j < nstages; ++j) {
@@ -284,7 +295,7 @@ __global__ void __launch_bounds__(DelayShape<MIX>::kThreads) delay_bank_kernel(c
             const int tn = min(kDlT, a.n_frames - t0);
             if (k + ahead < nstages && lane == 0) {
                 // stage nidx last held window k + ahead - kDlStages (<= k - 1), source of a write-back: wait until the engine has READ it
-                if (tight) bulk_wait_all(); else { bulk_wait_read0(); bulk_wait_but1(); }
+                if (tight) bulk_wait_all(); else { bulk_wait_read0(); bulk_wait_but7(); }
                 mbar_expect_tx(&bar[nidx], bytes);
                 bulk_g2s(wsm + nidx * kStageDoubles, run + (size_t)nchunk * V * kDlChunk, bytes, &bar[nidx]);
             }

@@ -57,6 +57,35 @@ __device__ __forceinline__ void dmma_tile(const double* __restrict__ ap, const d
     c1 = __dadd_rn(__dadd_rn(acc[0][1], acc[1][1]), __dadd_rn(acc[2][1], acc[3][1]));
 }
 
+// Natural logarithm of a normal, positive double, within 1 ulp of the correctly rounded value (checked against libm on 2e7
+// arguments between e^-40 and e^41 and around 1). The argument reduction and the degree-14 polynomial in s = f / (2 + f) are the
+// classic ones (x = 2^k (1 + f), sqrt(2)/2 < 1 + f < sqrt(2); log(1 + f) = f - f^2/2 + s (f^2/2 + R(s^2))); the quotient comes from a
+// single-precision reciprocal refined twice. About 40 straight-line instructions against libdevice's ~90 with branches: two calls next
+// to each other interleave. Only the mel stage uses it: its arguments are squares > 1e-12.
+__device__ __forceinline__ double log_pos(double x) {
+    int hx = __double2hiint(x);
+    const int lx = __double2loint(x);
+    int kexp = (hx >> 20) - 1023;
+    hx &= 0x000fffff;
+    const int up = (hx + 0x95f64) & 0x100000;                     // mantissa above sqrt(2): halve it, count the exponent up
+    x = __hiloint2double(hx | (up ^ 0x3ff00000), lx);
+    kexp += up >> 20;
+    const double f = __dadd_rn(x, -1.0), d = __dadd_rn(2.0, f);
+    float r0;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(__double2float_rn(d)));
+    double r = (double)r0;
+    r = __fma_rn(r, __fma_rn(-d, r, 1.0), r);
+    r = __fma_rn(r, __fma_rn(-d, r, 1.0), r);
+    const double s = __dmul_rn(f, r), dk = (double)kexp;
+    const double z = __dmul_rn(s, s), w = __dmul_rn(z, z);
+    const double t1 = __dmul_rn(w, __fma_rn(w, __fma_rn(w, 1.531383769920937332e-01, 2.222219843214978396e-01), 3.999999999940941908e-01));
+    const double t2 = __dmul_rn(z, __fma_rn(w, __fma_rn(w, __fma_rn(w, 1.479819860511658591e-01, 1.818357216161805012e-01), 2.857142874366239149e-01),
+                                            6.666666666666735130e-01));
+    const double R = __dadd_rn(t2, t1), hfsq = __dmul_rn(__dmul_rn(0.5, f), f);
+    const double lo = __fma_rn(s, __dadd_rn(hfsq, R), __dmul_rn(dk, 1.90821492927058770002e-10));
+    return __dsub_rn(__dmul_rn(dk, 6.93147180369123816490e-01), __dsub_rn(__dsub_rn(hfsq, lo), f));
+}
+
 __device__ __forceinline__ u64 pk2(float lo, float hi) { u64 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
 __device__ __forceinline__ void upk2(u64 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
 __device__ __forceinline__ u64 add2(u64 a, u64 b) { u64 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
@@ -456,8 +485,13 @@ __global__ void __launch_bounds__(kStreamWarps * 32, 2) stft_stream_kernel(const
                 // (~1e-15 relative; asserted at 1e-9). Two named barriers per batch and group; the mel rows are double-buffered.
                 const int grp = warp >> 2, wg = warp & 3;
                 const int row = lane >> 2, kk = lane & 3;
-                int nt = a.mf.mel_ntiles - 1 - wg;                                  // this warp's first mel tile: its descriptor (fragment
-                int4 tile = make_int4(0, 0, 0, 0);                                  // offset, first bin, k-steps) is requested before the wait
+                // Mel tiles of this warp. Whole tiles go round robin from the top (the widest bands first); each costs two logarithms
+                // per lane, the expensive part. A last round of one or two tiles is shared by halves -- two warps run the (narrow)
+                // tile and each takes the logarithm of one accumulator -- so that 42 filters (six tiles) cost every warp three.
+                const int mel_nt = a.mf.mel_ntiles, mel_rem = mel_nt & 3;
+                const bool halves = mel_rem == 1 || mel_rem == 2;
+                int nt = mel_nt - 1 - wg;                                           // first tile: its descriptor (fragment offset, first bin,
+                int4 tile = make_int4(0, 0, 0, 0);                                  // k-steps) is requested before the wait
                 if (nt >= 0) tile = __ldg((const int4*)a.mf.mel_tiles + nt);
                 if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory");       // literal ids: a register id would reserve all 16 barriers
                 else asm volatile("bar.sync 2, 128;" ::: "memory");                // the group's 8 magnitude rows are in shared memory
@@ -466,24 +500,38 @@ __global__ void __launch_bounds__(kStreamWarps * 32, 2) stft_stream_kernel(const
                     const double* amag = (const double*)((ulonglong2*)(sm + L.off_work) + (size_t)(4 * grp + (row >> 1)) * (half + half / 16)) +
                                          4 * (row >> 1) + (row & 1) * half + kk;      // row r: warp 4*grp + r/2 (skew 4*(r/2)), frame r%2
                     double* mr = melbuf + (size_t)(8 * grp + row) * melstride;
-                    // tiles from the top down: the widest bands (most k-steps) go to four different warps
-                    while (nt >= 0) {
+                    const int whole_lo = halves ? mel_rem : 0;                         // tiles below this index are shared by halves
+                    while (nt >= whole_lo) {
                         const int ntn = nt - 4;
                         int4 tilen = tile;
                         if (ntn >= 0) tilen = __ldg((const int4*)a.mf.mel_tiles + ntn);   // the next descriptor travels during this tile
                         double c0, c1;
                         dmma_tile(amag + tile.y, a.mf.melf + (size_t)tile.x * 32 + lane, tile.z, c0, c1);
+                        const double l0 = log_pos(__dmul_rn(c0, c0)), l1 = log_pos(__dmul_rn(c1, c1));
                         const int f0 = nt * 8 + 2 * kk;
-                        if (f0 < nf) mr[f0] = c0 > 0.000001 ? log(__dmul_rn(c0, c0)) : 0.0;
-                        if (f0 + 1 < nf) mr[f0 + 1] = c1 > 0.000001 ? log(__dmul_rn(c1, c1)) : 0.0;
+                        if (f0 < nf) mr[f0] = c0 > 0.000001 ? l0 : 0.0;                // melBands = sum > 1e-6 ? log(sum^2) : 0 (maxiMFCC.cpp:64)
+                        if (f0 + 1 < nf) mr[f0 + 1] = c1 > 0.000001 ? l1 : 0.0;
                         nt = ntn; tile = tilen;
+                    }
+                    if (halves) {
+                        // rem 2: tile 1 -> warps 0, 1; tile 0 -> warps 2, 3.  rem 1: tile 0 -> warps 0, 1
+                        const int ht = mel_rem == 2 ? 1 - (wg >> 1) : (wg < 2 ? 0 : -1);
+                        if (ht >= 0) {
+                            const int4 th = __ldg((const int4*)a.mf.mel_tiles + ht);
+                            double c0, c1;
+                            dmma_tile(amag + th.y, a.mf.melf + (size_t)th.x * 32 + lane, th.z, c0, c1);
+                            const double c = (wg & 1) ? c1 : c0;
+                            const double l = log_pos(__dmul_rn(c, c));
+                            const int fi = ht * 8 + 2 * kk + (wg & 1);
+                            if (fi < nf) mr[fi] = c > 0.000001 ? l : 0.0;
+                        }
                     }
                 }
                 if (grp == 0) asm volatile("bar.sync 3, 128;" ::: "memory");
                 else asm volatile("bar.sync 4, 128;" ::: "memory");                // the group's 8 mel rows are complete, its magnitudes consumed
                 const double* arow = melbuf + (size_t)(8 * grp + row) * melstride + kk;
                 const int ntiles = (a.mf.coeffs + 7) >> 3, ksteps = melstride >> 2;
-                const double ncf = (double)(unsigned)a.mf.coeffs;
+                const double ncinv = 1.0 / (double)(unsigned)a.mf.coeffs;          // dct(): `/ numCoeffs` (maxiMFCC.h:108-110) as one multiply, <= 1 ulp apart
                 for (int nt = 3 - wg; nt < ntiles; nt += 4) {                       // warps 3, 2 first: they had the narrowest mel tiles
                     double c0, c1;
                     dmma_tile(arow, a.mf.dctf + (size_t)nt * ksteps * 32 + lane, ksteps, c0, c1);   // columns >= filters are zero
@@ -492,8 +540,8 @@ __global__ void __launch_bounds__(kStreamWarps * 32, 2) stft_stream_kernel(const
                     if (ch < C) {
                         double* o = a.coeffs + ((size_t)ch * a.max_frames + f) * a.mf.coeffs;
                         const int cc = nt * 8 + 2 * kk;
-                        if (cc < a.mf.coeffs) o[cc] = c0 / ncf;
-                        if (cc + 1 < a.mf.coeffs) o[cc + 1] = c1 / ncf;
+                        if (cc < a.mf.coeffs) o[cc] = __dmul_rn(c0, ncinv);
+                        if (cc + 1 < a.mf.coeffs) o[cc + 1] = __dmul_rn(c1, ncinv);
                     }
                 }
             }
