@@ -50,8 +50,7 @@ template <bool MIX> struct DelayShape { static constexpr int kThreads = MIX ? 12
 constexpr int kDlStages = MXB_DL_STAGES;          // staged windows per warp: the bulk path requests kDlStages - 1 windows ahead
 static_assert(kDlStages >= 2 && kDlStages <= 8, "stages");
 constexpr int kDlVoicesPerReq = 32 / kDlT;        // voices covered by one cooperative request (2)
-constexpr int kDlMixStride = 32 + 4;                // K2 mix tile: [kMixTT][36] raw samples ++ gains[32][2] (bank_kernels.cuh: mix_tile_dmma)
-constexpr int kMixDoubles = kMixTT * kDlMixStride + 64;
+constexpr int kMixDoubles = 2 * kMixTT * 33;
 constexpr int kFastMinSize = 2 * kDlT;
 constexpr unsigned kFull = 0xffffffffu;
 enum { DL_OUT_NONE = 0, DL_OUT_F64 = 1, DL_OUT_F32 = 2 };
@@ -162,11 +161,21 @@ __device__ __forceinline__ void dl_stage(DlVoice& s, double* row, const int tn, 
         }
         if (OUTMODE == DL_OUT_F64) { if (s.live) __stcs(out64, y); out64 += V; }
         if (OUTMODE == DL_OUT_F32) { if (s.live) __stcs(out32, (float)y); out32 += V; }
-        if (MIX) mixtile[j * kDlMixStride + lane] = y;
+        if (MIX) {
+            mixtile[(0 * kMixTT + j) * 33 + lane] = y * s.gl;
+            mixtile[(1 * kMixTT + j) * 33 + lane] = y * s.gr;
+        }
     }
     if (MIX) {
         __syncwarp();
-        mix_tile_dmma<32, kMixTT>(mixtile, mixtile + kMixTT * kDlMixStride, tn, t0, a.partials, (size_t)a.W, (size_t)gwarp, lane);
+        const int ch = lane >> 4, rw = lane & 15;
+        if (rw < tn) {
+            const double* r = mixtile + (ch * kMixTT + rw) * 33;
+            double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;       // fixed order: deterministic
+#pragma unroll
+            for (int q = 0; q < 32; q += 4) { s0 += r[q]; s1 += r[q + 1]; s2 += r[q + 2]; s3 += r[q + 3]; }
+            a.partials[((size_t)(t0 + rw) * 2 + ch) * (size_t)a.W + (size_t)gwarp] = (s0 + s1) + (s2 + s3);
+        }
         __syncwarp();
     }
 }
@@ -238,9 +247,6 @@ __global__ void __launch_bounds__(DelayShape<MIX>::kThreads) delay_bank_kernel(c
         if (x < 0) x = 0;
         s.gl = s.live ? sqrt(1.0 - x) : 0.0;
         s.gr = s.live ? sqrt(x) : 0.0;
-        mixtile[kMixTT * kDlMixStride + lane * 2 + 0] = s.gl;          // the warp's gain table behind its tile
-        mixtile[kMixTT * kDlMixStride + lane * 2 + 1] = s.gr;
-        __syncwarp();
     }
     s.ph = d.phase[vv];
     s.size = d.size[vv];
