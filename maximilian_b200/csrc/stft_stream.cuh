@@ -27,6 +27,24 @@ namespace {
 
 typedef unsigned long long u64;
 
+// Cache steering. The frames stream through once (each sample is read by two consecutive frames, ~10 us apart): they bypass L1 so
+// that the few KB every frame re-reads -- the tensor-core B fragments of the mel bank and the DCT -- stay there.
+__device__ __forceinline__ float2 ld_stream_f2(const float* p) {
+    float2 v;
+    asm volatile("ld.global.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ float4 ld_stream_f4(const float* p) {
+    float4 v;
+    asm volatile("ld.global.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ double ld_keep_f64(const double* p) {
+    double v;
+    asm("ld.global.nc.L1::evict_last.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+}
+
 // One m8n8k4 fp64 tensor-core step (SASS DMMA): C[8 x 8] += A[8 x 4] . B[4 x 8]; lane holds A[lane / 4][lane % 4], B[lane % 4][lane / 4],
 // C[lane / 4][2 * (lane % 4) + {0, 1}].
 __device__ __forceinline__ void dmma884(double& c0, double& c1, const double av, const double bv) {
@@ -43,12 +61,12 @@ __device__ __forceinline__ void dmma_tile(const double* __restrict__ ap, const d
     for (int g = 0; g < groups; ++g) {
         double av[4], bv[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) { av[i] = ap[16 * g + 4 * i]; bv[i] = __ldg(bfrag + 128 * g + 32 * i); }
+        for (int i = 0; i < 4; ++i) { av[i] = ap[16 * g + 4 * i]; bv[i] = ld_keep_f64(bfrag + 128 * g + 32 * i); }
 #pragma unroll
         for (int i = 0; i < 4; ++i) dmma884(acc[i][0], acc[i][1], av[i], bv[i]);
     }
     for (int ks = 4 * groups, i = 0; ks < ksteps; ++ks, ++i) {
-        const double x = ap[4 * ks], y = __ldg(bfrag + 32 * ks);
+        const double x = ap[4 * ks], y = ld_keep_f64(bfrag + 32 * ks);
         if (i == 0) dmma884(acc[0][0], acc[0][1], x, y);
         else if (i == 1) dmma884(acc[1][0], acc[1][1], x, y);
         else dmma884(acc[2][0], acc[2][1], x, y);
@@ -126,13 +144,16 @@ constexpr int kStreamWarps = 8;                 // warps per CTA = channel pairs
 constexpr int kStreamN = 1024, kStreamHalf = 512;
 __device__ __forceinline__ int psi16(int p) { return p + (p >> 4); }          // padded index of a 16-byte point record
 
-struct StreamSmem { size_t off_tw, off_uw, off_win, off_mel, off_work, total; int melstride; };
+struct StreamSmem { size_t off_tw, off_uw, off_win, off_mel, off_work, total; int melstride, dct_ksteps; };
 __host__ __device__ inline StreamSmem stream_smem_layout(int nf) {
     StreamSmem L;
     L.off_tw = 0;                                                          // float4[512]: (wx, wx, wy, wy) at (be - 1) + n
     L.off_uw = L.off_tw + sizeof(float4) * 512;                            // float4[256]: (wr, wr, wi, wi)
     L.off_win = L.off_uw + sizeof(float4) * 256;                           // float[1024]
-    L.melstride = (nf + 3) & ~3;
+    // DCT k-steps in whole groups of four (dmma_tile), zero padded; row stride + 4 doubles: the rows of an A-fragment load fall on
+    // distinct banks
+    L.dct_ksteps = (((nf + 3) >> 2) + 3) & ~3;
+    L.melstride = 4 * L.dct_ksteps + 4;
     L.off_mel = align16(L.off_win + sizeof(float) * kStreamN);             // double[2][16][melstride]
     L.off_work = align16(L.off_mel + sizeof(double) * 2 * 2 * kStreamWarps * (size_t)L.melstride);
     L.total = L.off_work + sizeof(ulonglong2) * (size_t)kStreamWarps * (kStreamHalf + kStreamHalf / 16);
@@ -225,8 +246,8 @@ __global__ void __launch_bounds__(kStreamWarps * 32, 2) stft_stream_kernel(const
                             for (int k = 0; k < 8; ++k) {
                                 const int r = 8 * g + k;
                                 const bool fromhist = qs >= 0 ? brev4c(r) < qs : 64 * brev4c(r) < split;
-                                xa[k] = *(const float2*)((fromhist ? hA : iA) + 64 * brev4c(r));
-                                xb[k] = *(const float2*)((fromhist ? hB : iB) + 64 * brev4c(r));
+                                xa[k] = ld_stream_f2((fromhist ? hA : iA) + 64 * brev4c(r));
+                                xb[k] = ld_stream_f2((fromhist ? hB : iB) + 64 * brev4c(r));
                             }
 #pragma unroll
                             for (int k = 0; k < 8; ++k) {
@@ -530,7 +551,7 @@ __global__ void __launch_bounds__(kStreamWarps * 32, 2) stft_stream_kernel(const
                 if (grp == 0) asm volatile("bar.sync 3, 128;" ::: "memory");
                 else asm volatile("bar.sync 4, 128;" ::: "memory");                // the group's 8 mel rows are complete, its magnitudes consumed
                 const double* arow = melbuf + (size_t)(8 * grp + row) * melstride + kk;
-                const int ntiles = (a.mf.coeffs + 7) >> 3, ksteps = melstride >> 2;
+                const int ntiles = (a.mf.coeffs + 7) >> 3, ksteps = L.dct_ksteps;
                 const double ncinv = 1.0 / (double)(unsigned)a.mf.coeffs;          // dct(): `/ numCoeffs` (maxiMFCC.h:108-110) as one multiply, <= 1 ulp apart
                 for (int nt = 3 - wg; nt < ntiles; nt += 4) {                       // warps 3, 2 first: they had the narrowest mel tiles
                     double c0, c1;
@@ -559,7 +580,7 @@ __global__ void __launch_bounds__(kStreamWarps * 32, 2) stft_stream_kernel(const
                 float* nx = a.next + (size_t)c * n;
                 const long long fromin = consumed - a.pos0;               // first new-sample index of the tail when none of it is history
                 if (planar && fromin >= 0 && (a.newpos & 3) == 0 && ((((uintptr_t)(isrc + fromin)) | ((uintptr_t)nx)) & 15) == 0) {
-                    for (int i = 4 * lane; i < a.newpos; i += 128) *(float4*)(nx + i) = *(const float4*)(isrc + fromin + i);
+                    for (int i = 4 * lane; i < a.newpos; i += 128) __stcs((float4*)(nx + i), ld_stream_f4(isrc + fromin + i));
                 } else {
                     for (int i = lane; i < a.newpos; i += 32) {
                         const long long s = consumed + i;
