@@ -319,7 +319,7 @@ def onbox_peaks(torch, out):
         best_fill = best_copy = best_r1w2 = 0.0
         # one read : two writes, the traffic mix of the delay-line kernel (ring in, ring out, voice out): complex(x, x) reads 8 B
         # and writes 16 B per element
-        third = flat.numel() // 3
+        third = (flat.numel() // 3) & ~1          # even: view_as_complex wants an even storage offset
         x, z = flat[:third], torch.view_as_complex(flat[third:3 * third].view(third, 2)) if flat.dtype == torch.float64 else None
         for _ in range(5):
             e0, e1, e2, e3 = (torch.cuda.Event(enable_timing=True) for _ in range(4))

@@ -215,6 +215,7 @@ __global__ void __launch_bounds__(kStreamWarps * 32, 2) stft_stream_kernel(const
         const int cA = 2 * pair, cB = cA + 1;
         const bool vA = cA < C, vB = cB < C;
         const int cBs = vB ? cB : cA;                            // a missing second channel re-reads the first (its results are dropped)
+        bool tail_done = false;                                  // the next assembly buffer was written while loading the last frame
 #pragma unroll 1
         for (int f = 0; f < frames; ++f, ++bc) {
             if (vA) {
@@ -237,6 +238,9 @@ __global__ void __launch_bounds__(kStreamWarps * 32, 2) stft_stream_kernel(const
                     const float *hA = hpA + 2 * Lr, *hB = hpB + 2 * Lr, *iA = ipA + 2 * Lr, *iB = ipB + 2 * Lr;
                     // QS = split / 64 known at compile time (8: the steady state of hop 512; 0: all new; 16: all history) turns the
                     // choice of source into straight-line code; any other boundary selects per request (warp-uniform predicate)
+                    // warp-uniform: this is the last frame and the unconsumed tail lies inside it (whole hops were fed)
+                    const bool tail_here = f == frames - 1 && a.newpos > 0 && a.newpos <= n - hop && ((hop | a.newpos) & 1) == 0;
+                    tail_done = tail_here;
                     auto load = [&](auto QS) {
                         constexpr int qs = decltype(QS)::value;
 #pragma unroll
@@ -248,6 +252,18 @@ __global__ void __launch_bounds__(kStreamWarps * 32, 2) stft_stream_kernel(const
                                 const bool fromhist = qs >= 0 ? brev4c(r) < qs : 64 * brev4c(r) < split;
                                 xa[k] = ld_stream_f2((fromhist ? hA : iA) + 64 * brev4c(r));
                                 xb[k] = ld_stream_f2((fromhist ? hB : iB) + 64 * brev4c(r));
+                            }
+                            if (tail_here) {
+                                // the last frame's samples from `hop` on ARE the next assembly buffer (maxiFFT.cpp:85-87): stored from the
+                                // registers they were just loaded into, not read again after the transform
+#pragma unroll
+                                for (int k = 0; k < 8; ++k) {
+                                    const int idx = 64 * brev4c(8 * g + k) + 2 * Lr - hop;
+                                    if (idx >= 0 && idx < a.newpos) {
+                                        __stcs((float2*)(a.next + (size_t)cA * n + idx), xa[k]);
+                                        if (vB) __stcs((float2*)(a.next + (size_t)cB * n + idx), xb[k]);
+                                    }
+                                }
                             }
 #pragma unroll
                             for (int k = 0; k < 8; ++k) {
@@ -569,7 +585,7 @@ __global__ void __launch_bounds__(kStreamWarps * 32, 2) stft_stream_kernel(const
         }
         // ---- the channels' next assembly buffers: the unconsumed tail of (buffer ++ new samples), maxiFFT.cpp:85-87 applied
         // `frames` times. It goes to the OTHER buffer (double-buffered across calls). ----
-        if (vA && a.newpos > 0) {
+        if (vA && a.newpos > 0 && !tail_done) {
             const long long consumed = (long long)frames * hop;
 #pragma unroll 1
             for (int k = 0; k < 2; ++k) {
