@@ -703,7 +703,7 @@ int32_t mxb_bank_process_mod(mxb_bank* b, int32_t n_frames, const mxb_modulation
             case MXB_FILT_BIQUAD: fn = launch_bank_biquad; break;
             default: break;
         }
-        const size_t smem = mix ? sizeof(double) * (kBankBlock / 32) * 2 * kBankMixRows * 33 : 0;
+        const size_t smem = mix ? sizeof(double) * (kBankBlock / 32) * 2 * kMixTT * 33 : 0;
         rc = fn(a, osc_t, env, out != nullptr, mix != nullptr, grid, smem, s);
         if (rc != MXB_OK) return rc;
     }

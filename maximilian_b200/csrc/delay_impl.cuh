@@ -47,8 +47,16 @@ constexpr int kStageDoubles = 32 * kDlRow;        // one staged window tile per 
 #define MXB_DL_STAGES 2
 #endif
 template <bool MIX> struct DelayShape { static constexpr int kThreads = MIX ? 128 : MXB_DL_THREADS; };
-constexpr int kDlStages = MXB_DL_STAGES;          // staged windows per warp: the bulk path requests kDlStages - 1 windows ahead
-static_assert(kDlStages >= 2 && kDlStages <= 8, "stages");
+#ifndef MXB_DL_AHEAD
+#define MXB_DL_AHEAD (MXB_DL_STAGES - 1)
+#endif
+constexpr int kDlStages = MXB_DL_STAGES;          // staged windows per warp
+constexpr int kDlAhead = MXB_DL_AHEAD;            // the bulk path requests this many windows ahead
+// The stage a request refills last held window k + ahead - stages; its write-back was committed kDlSlack groups before the latest one.
+// With slack 0 the warp waits, every window, for the copy engine to have drained the write-back it issued a moment ago (and that
+// drains at the speed of the saturated memory system); with slack 1 the engine has a whole window of time.
+constexpr int kDlSlack = kDlStages - 1 - kDlAhead;
+static_assert(kDlStages >= 2 && kDlStages <= 8 && kDlAhead >= 1 && kDlSlack >= 0 && kDlSlack <= 2, "stages / ahead");
 constexpr int kDlVoicesPerReq = 32 / kDlT;        // voices covered by one cooperative request (2)
 constexpr int kMixDoubles = 2 * kMixTT * 33;
 constexpr int kFastMinSize = 2 * kDlT;
@@ -98,6 +106,11 @@ __device__ __forceinline__ void bulk_s2g(void* gdst, const void* smem_src, unsig
 #endif
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }   // sources read: smem reusable
+template <int PENDING> __device__ __forceinline__ void bulk_wait_read() {      // all but the latest PENDING groups have read their sources
+    if (PENDING == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    else if (PENDING == 1) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+    else asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory");
+}
 __device__ __forceinline__ void bulk_wait_but7() { asm volatile("cp.async.bulk.wait_group 7;" ::: "memory"); }         // all but the latest 7 groups performed
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }           // writes performed
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -282,7 +295,7 @@ __global__ void __launch_bounds__(DelayShape<MIX>::kThreads) delay_bank_kernel(c
         // of nchunks, first at j = nchunks - ahead. A ring of at least ahead + 8 chunks only needs the write-backs older than the
         // latest seven performed (cp.async.bulk.wait_group 7: they were issued seven windows ago, the wait is free); a shorter
         // ring waits for all of them.
-        const int ahead = nchunks >= kDlStages ? kDlStages - 1 : 1;
+        const int ahead = nchunks >= kDlStages ? kDlAhead : 1;
         const bool tight = nchunks - ahead < 8;
         auto chunk_of = [&](int kk) { return (int)(((long long)(base0 >> kDlShift) + kk) % nchunks); };
         if (lane == 0) {
@@ -301,7 +314,7 @@ __global__ void __launch_bounds__(DelayShape<MIX>::kThreads) delay_bank_kernel(c
             const int tn = min(kDlT, a.n_frames - t0);
             if (k + ahead < nstages && lane == 0) {
                 // stage nidx last held window k + ahead - kDlStages (<= k - 1), source of a write-back: wait until the engine has READ it
-                if (tight) bulk_wait_all(); else { bulk_wait_read0(); bulk_wait_but7(); }
+                if (tight) bulk_wait_all(); else { if (ahead == kDlAhead) bulk_wait_read<kDlSlack>(); else bulk_wait_read0(); bulk_wait_but7(); }
                 mbar_expect_tx(&bar[nidx], bytes);
                 bulk_g2s(wsm + nidx * kStageDoubles, run + (size_t)nchunk * V * kDlChunk, bytes, &bar[nidx]);
             }
