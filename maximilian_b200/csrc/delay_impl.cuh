@@ -314,15 +314,35 @@ __global__ void __launch_bounds__(DelayShape<MIX>::kThreads) delay_bank_kernel(c
             const int tn = min(kDlT, a.n_frames - t0);
             if (k + ahead < nstages && lane == 0) {
                 // stage nidx last held window k + ahead - kDlStages (<= k - 1), source of a write-back: wait until the engine has READ it
+#ifndef MXB_DL_WB_STG
                 if (tight) bulk_wait_all(); else { if (ahead == kDlAhead) bulk_wait_read<kDlSlack>(); else bulk_wait_read0(); bulk_wait_but7(); }
+#endif
                 mbar_expect_tx(&bar[nidx], bytes);
                 bulk_g2s(wsm + nidx * kStageDoubles, run + (size_t)nchunk * V * kDlChunk, bytes, &bar[nidx]);
             }
             mbar_wait(&bar[sidx], par);                                     // window k has landed
             dl_window<OSC, FILT, ENV, true, OUTMODE, MIX>(s, buf + lane * kDlChunk, tn, t0, a, d, V, (size_t)vv, lane, gwarp, mixtile, swz);
+#ifdef MXB_DL_WB_STG
+            // A/B: the write-back as a plain coalesced copy of the staged image (8 x 512 B per warp), the load side stays on the copy
+            // engine. The buffer is free as soon as every lane has read its part; a short ring (or every 64th window) orders the stores
+            // before the engine's next read of the chunk with a device-scope fence and a proxy fence.
+            __syncwarp();
+            {
+                double* g = run + (size_t)chunk * V * kDlChunk;
+                const int nd = nlive * kDlChunk;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int o = 64 * i + 2 * lane;
+                    if (o < nd) *(double2*)(g + o) = *(const double2*)(buf + o);
+                }
+            }
+            if (tight || (k & 63) == 63) { __threadfence(); asm volatile("fence.proxy.async;" ::: "memory"); }
+            __syncwarp();
+#else
             fence_proxy_async();                                            // this lane's updates of the window, ordered before the engine reads them
             __syncwarp();
             if (lane == 0) { bulk_s2g(run + (size_t)chunk * V * kDlChunk, buf, bytes); bulk_commit(); }
+#endif
             if (++chunk >= nchunks) chunk = 0;
             if (++nchunk >= nchunks) nchunk = 0;
             if (++sidx == kDlStages) { sidx = 0; par ^= 1u; }

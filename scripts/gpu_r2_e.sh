@@ -7,5 +7,5 @@ timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --mast
 python -c "
 import json; d=json.loads(open('gpurun_out/e_bench_n2.json').read().strip().splitlines()[-1]); print('n2', d['value'], d['roofline']['frac'], 'mixdown', d['mixdown']['value'], d['mixdown'].get('check'))"
 timeout 600 compute-sanitizer --tool racecheck --print-limit 5 python -m pytest tests/test_gpu_spectral.py -m gpu -q -k "stream_kernel_mfcc_only_whole_hops and 7-512" > gpurun_out/e_sanitizer_racecheck_stft.log 2>&1; tail -4 gpurun_out/e_sanitizer_racecheck_stft.log
-timeout 600 compute-sanitizer --tool memcheck --print-limit 5 python -m pytest tests/test_gpu_bank.py -m gpu -q -k "delayline_index_exact and False-1024" > gpurun_out/e_sanitizer_memcheck_delay.log 2>&1; tail -4 gpurun_out/e_sanitizer_memcheck_delay.log
-timeout 600 compute-sanitizer --tool synccheck --print-limit 5 python -m pytest tests/test_gpu_bank.py -m gpu -q -k "delayline_index_exact and False-1024" > gpurun_out/e_sanitizer_synccheck_delay.log 2>&1; tail -4 gpurun_out/e_sanitizer_synccheck_delay.log
+timeout 600 compute-sanitizer --tool memcheck --print-limit 5 python -m pytest tests/test_gpu_bank.py -m gpu -q -k "delayline_index_exact and 1024-False" > gpurun_out/e_sanitizer_memcheck_delay.log 2>&1; tail -4 gpurun_out/e_sanitizer_memcheck_delay.log
+timeout 600 compute-sanitizer --tool synccheck --print-limit 5 python -m pytest tests/test_gpu_bank.py -m gpu -q -k "delayline_index_exact and 1024-False" > gpurun_out/e_sanitizer_synccheck_delay.log 2>&1; tail -4 gpurun_out/e_sanitizer_synccheck_delay.log
