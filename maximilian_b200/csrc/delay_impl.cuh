@@ -68,6 +68,10 @@ __device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc) 
     const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d), "l"(gsrc) : "memory");
 }
+__device__ __forceinline__ void cp_async16(double* smem_dst, const double* gsrc) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait1() { asm volatile("cp.async.wait_group 1;\n" ::: "memory"); }
 
@@ -298,12 +302,29 @@ __global__ void __launch_bounds__(DelayShape<MIX>::kThreads) delay_bank_kernel(c
         const int ahead = nchunks >= kDlStages ? kDlAhead : 1;
         const bool tight = nchunks - ahead < 8;
         auto chunk_of = [&](int kk) { return (int)(((long long)(base0 >> kDlShift) + kk) % nchunks); };
+#ifdef MXB_DL_NO_TMA
+        // A/B: no copy engine at all -- the window image by 8 coalesced 16-byte cp.async per lane, cp.async groups for completion
+        const int nd = nlive * kDlChunk;
+        auto request = [&](double* stage, const double* g) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int o = 64 * i + 2 * lane;
+                if (o < nd) cp_async16(stage + o, g + o);
+            }
+            cp_async_commit();
+        };
+        for (int j = 0; j < ahead; ++j) {
+            if (j < nstages) request(wsm + j * kStageDoubles, run + (size_t)chunk_of(j) * V * kDlChunk);
+            else cp_async_commit();
+        }
+#else
         if (lane == 0) {
             for (int j = 0; j < ahead && j < nstages; ++j) {
                 mbar_expect_tx(&bar[j], bytes);
                 bulk_g2s(wsm + j * kStageDoubles, run + (size_t)chunk_of(j) * V * kDlChunk, bytes, &bar[j]);
             }
         }
+#endif
         const int swz = lane & (kDlChunk - 1);
         int sidx = 0, nidx = ahead % kDlStages;                            // stage of window k / of window k + ahead
         unsigned par = 0;                                                   // parity of stage sidx's barrier: flips every kDlStages windows
@@ -312,6 +333,13 @@ __global__ void __launch_bounds__(DelayShape<MIX>::kThreads) delay_bank_kernel(c
             double* buf = wsm + sidx * kStageDoubles;
             const int t0 = k * kDlT;
             const int tn = min(kDlT, a.n_frames - t0);
+#ifdef MXB_DL_NO_TMA
+            if (k + ahead < nstages) request(wsm + nidx * kStageDoubles, run + (size_t)nchunk * V * kDlChunk);
+            else cp_async_commit();                                         // an empty group keeps the count uniform
+            if (ahead == 1) asm volatile("cp.async.wait_group 1;\n" ::: "memory");
+            else asm volatile("cp.async.wait_group %0;\n" ::"n"(kDlAhead) : "memory");
+            __syncwarp();                                                   // every lane's part of window k has landed
+#else
             if (k + ahead < nstages && lane == 0) {
                 // stage nidx last held window k + ahead - kDlStages (<= k - 1), source of a write-back: wait until the engine has READ it
 #ifndef MXB_DL_WB_STG
@@ -321,8 +349,9 @@ __global__ void __launch_bounds__(DelayShape<MIX>::kThreads) delay_bank_kernel(c
                 bulk_g2s(wsm + nidx * kStageDoubles, run + (size_t)nchunk * V * kDlChunk, bytes, &bar[nidx]);
             }
             mbar_wait(&bar[sidx], par);                                     // window k has landed
+#endif
             dl_window<OSC, FILT, ENV, true, OUTMODE, MIX>(s, buf + lane * kDlChunk, tn, t0, a, d, V, (size_t)vv, lane, gwarp, mixtile, swz);
-#ifdef MXB_DL_WB_STG
+#if defined(MXB_DL_WB_STG) || defined(MXB_DL_NO_TMA)
             // A/B: the write-back as a plain coalesced copy of the staged image (8 x 512 B per warp), the load side stays on the copy
             // engine. The buffer is free as soon as every lane has read its part; a short ring (or every 64th window) orders the stores
             // before the engine's next read of the chunk with a device-scope fence and a proxy fence.
@@ -336,7 +365,7 @@ __global__ void __launch_bounds__(DelayShape<MIX>::kThreads) delay_bank_kernel(c
                     if (o < nd) *(double2*)(g + o) = *(const double2*)(buf + o);
                 }
             }
-            if (tight || (k & 63) == 63) { __threadfence(); asm volatile("fence.proxy.async;" ::: "memory"); }
+            if (tight || (k & 63) == 63) { __threadfence(); asm volatile("fence.proxy.async;" ::: "memory"); }      // (cp.async reads in the generic proxy: the device fence is what it needs)
             __syncwarp();
 #else
             fence_proxy_async();                                            // this lane's updates of the window, ordered before the engine reads them
