@@ -401,7 +401,7 @@ def bank_leg(E, args, wl_name, steps, warmup, want_mix=False, with_onbox=False, 
     """One bank workload: resident-throughput, roofline and the pipelined e2e number."""
     torch, capi, W = E.torch, E.capi, E.W
     wl = WORKLOADS[wl_name]
-    V = wl["voices"]
+    V = int(os.environ.get("MXB_BENCH_VOICES", wl["voices"]))      # experiment hook (wave-quantisation probes); the JSON states voices_per_gpu
     rank, world, dev, stream = E.rank, E.world, E.dev, E.stream
     p = W.voice_params(V, seed=W.SEED + rank, delay_size=wl["delay"] or 4096)
     bank = capi.Bank(V, osc=wl["osc"], filt=wl["filt"], env=wl["env"], delay=wl["delay"] > 0,

@@ -85,21 +85,6 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* b, unsigned parity
     asm volatile("{\n.reg .pred p;\nMXB_WAIT_%=:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra MXB_DONE_%=;\nbra MXB_WAIT_%=;\nMXB_DONE_%=:\n}"
                  ::"r"(smem_u32(b)), "r"(parity) : "memory");
 }
-#ifdef MXB_DL_L2HINT      // A/B: ring chunks pass through L2 as evict-first (each is touched once per trip round the ring)
-__device__ __forceinline__ unsigned long long l2_evict_first() {
-    unsigned long long pol;
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-    return pol;
-}
-__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, unsigned bytes, unsigned long long* b) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
-                 ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(b)), "l"(l2_evict_first()) : "memory");
-}
-__device__ __forceinline__ void bulk_s2g(void* gdst, const void* smem_src, unsigned bytes) {
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;"
-                 ::"l"(gdst), "r"(smem_u32(smem_src)), "r"(bytes), "l"(l2_evict_first()) : "memory");
-}
-#else
 __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, unsigned bytes, unsigned long long* b) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(b)) : "memory");
@@ -107,7 +92,6 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, unsig
 __device__ __forceinline__ void bulk_s2g(void* gdst, const void* smem_src, unsigned bytes) {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(smem_src)), "r"(bytes) : "memory");
 }
-#endif
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }   // sources read: smem reusable
 template <int PENDING> __device__ __forceinline__ void bulk_wait_read() {      // all but the latest PENDING groups have read their sources
@@ -303,7 +287,8 @@ __global__ void __launch_bounds__(DelayShape<MIX>::kThreads) delay_bank_kernel(c
         const bool tight = nchunks - ahead < 8;
         auto chunk_of = [&](int kk) { return (int)(((long long)(base0 >> kDlShift) + kk) % nchunks); };
 #ifdef MXB_DL_NO_TMA
-        // A/B: no copy engine at all -- the window image by 8 coalesced 16-byte cp.async per lane, cp.async groups for completion
+        // A/B build (scripts/build_variant_one.sh): no copy engine at all -- the window image by 8 coalesced 16-byte cp.async per lane,
+        // cp.async groups for completion. Measured within 0.5 % of the copy-engine pipeline (profiles/bench_lines/r02_k2_variants.txt).
         const int nd = nlive * kDlChunk;
         auto request = [&](double* stage, const double* g) {
 #pragma unroll
@@ -342,19 +327,16 @@ __global__ void __launch_bounds__(DelayShape<MIX>::kThreads) delay_bank_kernel(c
 #else
             if (k + ahead < nstages && lane == 0) {
                 // stage nidx last held window k + ahead - kDlStages (<= k - 1), source of a write-back: wait until the engine has READ it
-#ifndef MXB_DL_WB_STG
                 if (tight) bulk_wait_all(); else { if (ahead == kDlAhead) bulk_wait_read<kDlSlack>(); else bulk_wait_read0(); bulk_wait_but7(); }
-#endif
                 mbar_expect_tx(&bar[nidx], bytes);
                 bulk_g2s(wsm + nidx * kStageDoubles, run + (size_t)nchunk * V * kDlChunk, bytes, &bar[nidx]);
             }
             mbar_wait(&bar[sidx], par);                                     // window k has landed
 #endif
             dl_window<OSC, FILT, ENV, true, OUTMODE, MIX>(s, buf + lane * kDlChunk, tn, t0, a, d, V, (size_t)vv, lane, gwarp, mixtile, swz);
-#if defined(MXB_DL_WB_STG) || defined(MXB_DL_NO_TMA)
-            // A/B: the write-back as a plain coalesced copy of the staged image (8 x 512 B per warp), the load side stays on the copy
-            // engine. The buffer is free as soon as every lane has read its part; a short ring (or every 64th window) orders the stores
-            // before the engine's next read of the chunk with a device-scope fence and a proxy fence.
+#ifdef MXB_DL_NO_TMA
+            // ... and the write-back as a plain coalesced copy of the staged image (8 x 512 B per warp). The buffer is free as soon as
+            // every lane has read its part; every lane later re-reads (cp.async) exactly the bytes it stored: program order is enough.
             __syncwarp();
             {
                 double* g = run + (size_t)chunk * V * kDlChunk;
@@ -365,7 +347,6 @@ __global__ void __launch_bounds__(DelayShape<MIX>::kThreads) delay_bank_kernel(c
                     if (o < nd) *(double2*)(g + o) = *(const double2*)(buf + o);
                 }
             }
-            if (tight || (k & 63) == 63) { __threadfence(); asm volatile("fence.proxy.async;" ::: "memory"); }      // (cp.async reads in the generic proxy: the device fence is what it needs)
             __syncwarp();
 #else
             fence_proxy_async();                                            // this lane's updates of the window, ordered before the engine reads them
