@@ -141,7 +141,21 @@ __device__ __forceinline__ void untangle2(u64& Ri, u64& Ii, u64& R3, u64& I3, co
     }
 }
 
-constexpr int kStreamWarps = 8;                 // warps per CTA = channel pairs in flight per CTA (16 frames per DCT batch)
+#ifndef MXB_STREAM_WARPS
+#define MXB_STREAM_WARPS 8
+#endif
+constexpr int kStreamWarps = MXB_STREAM_WARPS;  // warps per CTA = channel pairs in flight per CTA (groups of 4 warps = 8 frames per MFCC batch)
+constexpr int kStreamCtasPerSm = kStreamWarps <= 8 ? 2 : 1;
+static_assert(kStreamWarps % 4 == 0 && kStreamWarps <= 28, "4-warp groups, two named barriers each");
+// named barrier `id` for the 128 threads of a group; literal ids: a register id would reserve all 16 barriers
+__device__ __forceinline__ void group_barrier(const int id) {
+    switch (id) {
+#define MXB_BAR(I) case I: asm volatile("bar.sync " #I ", 128;" ::: "memory"); break;
+        MXB_BAR(1) MXB_BAR(2) MXB_BAR(3) MXB_BAR(4) MXB_BAR(5) MXB_BAR(6) MXB_BAR(7) MXB_BAR(8) MXB_BAR(9) MXB_BAR(10) MXB_BAR(11) MXB_BAR(12) MXB_BAR(13) MXB_BAR(14)
+#undef MXB_BAR
+        default: break;
+    }
+}
 constexpr int kStreamN = 1024, kStreamHalf = 512;
 __device__ __forceinline__ int psi16(int p) { return p + (p >> 4); }          // padded index of a 16-byte point record
 
@@ -178,7 +192,7 @@ __device__ __forceinline__ float frame_sample(const float* hp, const float* ip, 
 // FULL = false: nothing but MFCCs leaves the kernel and the mel bank reads bins < 256 only: the upper-half outputs of the
 // untangling pass and their magnitudes are never formed.
 template <bool FULL>
-__global__ void __launch_bounds__(kStreamWarps * 32, 2) stft_stream_kernel(const StreamArgs sa) {
+__global__ void __launch_bounds__(kStreamWarps * 32, kStreamCtasPerSm) stft_stream_kernel(const StreamArgs sa) {
     const StftArgs& a = sa.a;
     extern __shared__ float4 smem4[];
     unsigned char* sm = (unsigned char*)smem4;
@@ -538,8 +552,7 @@ __global__ void __launch_bounds__(kStreamWarps * 32, 2) stft_stream_kernel(const
                 int nt = mel_nt - 1 - wg;                                           // first tile: its descriptor (fragment offset, first bin,
                 int4 tile = make_int4(0, 0, 0, 0);                                  // k-steps) is requested before the wait
                 if (nt >= 0) tile = __ldg((const int4*)a.mf.mel_tiles + nt);
-                if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory");       // literal ids: a register id would reserve all 16 barriers
-                else asm volatile("bar.sync 2, 128;" ::: "memory");                // the group's 8 magnitude rows are in shared memory
+                group_barrier(1 + grp);                                             // the group's 8 magnitude rows are in shared memory
                 double* melbuf = s_mel + (size_t)(bc & 1) * 2 * kStreamWarps * melstride;
                 {
                     const double* amag = (const double*)((ulonglong2*)(sm + L.off_work) + (size_t)(4 * grp + (row >> 1)) * (half + half / 16)) +
@@ -572,8 +585,7 @@ __global__ void __launch_bounds__(kStreamWarps * 32, 2) stft_stream_kernel(const
                         }
                     }
                 }
-                if (grp == 0) asm volatile("bar.sync 3, 128;" ::: "memory");
-                else asm volatile("bar.sync 4, 128;" ::: "memory");                // the group's 8 mel rows are complete, its magnitudes consumed
+                group_barrier(1 + kStreamWarps / 4 + grp);                          // the group's 8 mel rows are complete, its magnitudes consumed
                 const double* arow = melbuf + (size_t)(8 * grp + row) * melstride + kk;
                 const int ntiles = (a.mf.coeffs + 7) >> 3, ksteps = L.dct_ksteps;
                 const double ncinv = 1.0 / (double)(unsigned)a.mf.coeffs;          // dct(): `/ numCoeffs` (maxiMFCC.h:108-110) as one multiply, <= 1 ulp apart
