@@ -243,8 +243,15 @@ int64_t mxb_bank_launch_count(const mxb_bank* bank);
  * oscillators summed into one filter, an LFO added to a frequency or a cutoff, the envelope multiplying the FILTER OUTPUT
  * (cpp/commandline/maximilian_examples/15.polysynth/main.cpp:54-70), a trigger that changes on any sample
  * (10.Filters/main.cpp:27-36), and the rest of the family: table oscillators, one-pole filters, maxiDCBlocker,
- * maxiNonlinearity, maxiEnvGen, maxiFlanger. One interpreting kernel runs the stage list (warp-uniform dispatch: every
- * voice runs the same program); state lives on the device between calls like a bank's.
+ * maxiNonlinearity, maxiEnvGen, maxiFlanger. State lives on the device between calls like a bank's. A patch runs in one
+ * of two ways (mxb_patch_set_mode), with identical state layout and results:
+ *   MXB_PATCH_FUSED (default)  the library writes the CUDA source of ONE kernel for exactly this stage list -- stage state and
+ *                              parameters in registers, constants as literals, coefficient designs whose arguments do not
+ *                              change within a block hoisted out of the sample loop -- compiles it for sm_100a with NVRTC on
+ *                              first use (about a second, once per patch) and launches it like the built-in kernels;
+ *   MXB_PATCH_INTERPRET        one interpreting kernel walks the stage list (warp-uniform dispatch: every voice runs the same
+ *                              program), registers / parameters / state in shared memory. No run-time compiler needed.
+ * Neither is a CPU path; a fused patch on a box without libnvrtc.so.12 fails with MXB_ERR_UNSUPPORTED and says so.
  *
  * A stage computes dst = op(src...) on 16 per-voice registers that read 0 until written within the sample. Operands: */
 #define MXB_STAGE_SRCS 8
@@ -252,7 +259,9 @@ int64_t mxb_bank_launch_count(const mxb_bank* bank);
 #define MXB_REG(i)   (i)             /* register i, 0..15 */
 #define MXB_PARAM(j) (0x100 + (j))   /* per-voice parameter array j (mxb_patch_set_param), 0..31 */
 #define MXB_CONST(k) (0x200 + (k))   /* scalar k of mxb_patch_desc.consts, 0..63 */
-#define MXB_INPUT(m) (0x300 + (m))   /* per-sample input stream m of mxb_patch_process: double [n_frames][voices], 0..7 */
+#define MXB_INPUT(m) (0x300 + (m))   /* per-sample input stream m of mxb_patch_process: [n_frames][voices] doubles (or bytes, input_types), 0..7 */
+#define MXB_IN_F64 0                 /* input stream element types (mxb_patch_desc.input_types) */
+#define MXB_IN_U8 1                  /* unsigned bytes, read as (double)byte: triggers and gates (maxiEnv::trigger is an int) at 1 B / voice-sample */
 /* oscillator kinds of MXB_OP_OSC beyond MXB_OSC_*: the table oscillators (tables: mxb_ctx_set_tables) */
 enum { MXB_OSC_SINEBUF = 9 /* maxiOsc::sinebuf src/maximilian.cpp:266-274 */, MXB_OSC_SINEBUF4 = 10 /* :237-264 */, MXB_OSC_SAWN = 11 /* :342-359 */ };
 /* filter kinds of MXB_OP_FILTER beyond MXB_FILT_LORES / HIRES */
@@ -285,6 +294,7 @@ typedef struct {
     const mxb_stage* stages;
     const double* consts;
     const double *eg_levels, *eg_times /* ms or MXB_ENVGEN_HOLD */, *eg_curves;
+    const int32_t* input_types;   /* n_inputs x MXB_IN_*, or NULL: every stream is doubles */
 } mxb_patch_desc;
 typedef struct mxb_patch mxb_patch;
 /* The reference's lookup tables sineBuffer[514] and transition[1001] (src/maximilian.cpp:63, 67-200) are DATA of the
@@ -300,9 +310,18 @@ int32_t mxb_patch_set_param(mxb_patch* patch, int32_t j, const double* values, i
 int32_t mxb_patch_set_state(mxb_patch* patch, int32_t stage, int32_t slot, const double* values, int32_t mem);
 int32_t mxb_patch_get_state(mxb_patch* patch, int32_t stage, int32_t slot, double* values, int32_t mem);
 int32_t mxb_patch_get_ring(mxb_patch* patch, int32_t stage, int32_t voice, double* dst, int32_t n, int32_t mem);
-/* inputs: n_inputs pointers to double [n_frames][voices]; out: [n_frames][voices] or NULL; mix: [n_frames][2] or NULL */
-int32_t mxb_patch_process(mxb_patch* patch, int32_t n_frames, const double* const* inputs, double* out, double* mix, int32_t mem, void* stream);
+/* inputs: n_inputs pointers to [n_frames][voices] of each stream's element type; out: [n_frames][voices] or NULL; mix: [n_frames][2] or NULL */
+int32_t mxb_patch_process(mxb_patch* patch, int32_t n_frames, const void* const* inputs, double* out, double* mix, int32_t mem, void* stream);
 int64_t mxb_patch_launch_count(const mxb_patch* patch);
+#define MXB_PATCH_INTERPRET 0
+#define MXB_PATCH_FUSED 1
+/* FUSED compiles at once (so that a patch the compiler rejects fails here and not in the audio loop). Patches start FUSED unless
+ * the environment says MXB_PATCH_MODE=interpret. */
+int32_t mxb_patch_set_mode(mxb_patch* patch, int32_t mode);
+int32_t mxb_patch_get_mode(const mxb_patch* patch);
+/* The CUDA source the library generates for a descriptor (voices / max_frames are not looked at), NUL-terminated into buf[cap]
+ * (may be NULL / 0); *needed = its size with the terminator. compile != 0 also runs it through NVRTC for sm_100a. Needs no device. */
+int32_t mxb_patch_codegen(const mxb_patch_desc* desc, char* buf, int64_t cap, int64_t* needed, int32_t compile);
 
 /* ------------------------------------------------------------------------------------------------
  * Multi-GPU mix-down: one process per GPU, voices sharded, every rank ends each block with the SAME stereo bus

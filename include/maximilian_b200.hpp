@@ -352,7 +352,7 @@ private:
                     for (int t = (*gate_.on)[(size_t)v] < 0 ? 0 : (*gate_.on)[(size_t)v]; t < (*gate_.off)[(size_t)v] && t < nFrames; ++t) gateStream_[(size_t)t * (size_t)V_ + (size_t)v] = 1.0;
             inputPtr_[(size_t)gateInput_] = gateStream_.data();
         }
-        check(mxb_patch_process(patch_, nFrames, nInputs_ ? inputPtr_.data() : nullptr, outSrc_ != MXB_NONE ? out : nullptr, wantMix_ ? mix : nullptr,
+        check(mxb_patch_process(patch_, nFrames, nInputs_ ? (const void* const*)inputPtr_.data() : nullptr, outSrc_ != MXB_NONE ? out : nullptr, wantMix_ ? mix : nullptr,
                                 MXB_MEM_HOST, nullptr), "mxb_patch_process");
     }
 

@@ -32,7 +32,7 @@ EXPORTS = [
     "mxb_istft_create", "mxb_istft_destroy", "mxb_istft_process",
     "mxb_octave_create", "mxb_octave_destroy", "mxb_octave_n_averages", "mxb_octave_config", "mxb_stft_process3",
     "mxb_ctx_set_tables", "mxb_patch_create", "mxb_patch_destroy", "mxb_patch_set_param", "mxb_patch_set_state", "mxb_patch_get_state",
-    "mxb_patch_get_ring", "mxb_patch_process", "mxb_patch_launch_count",
+    "mxb_patch_get_ring", "mxb_patch_process", "mxb_patch_launch_count", "mxb_patch_set_mode", "mxb_patch_get_mode", "mxb_patch_codegen",
 ]
 
 
@@ -129,6 +129,9 @@ def lib():
         "mxb_patch_get_ring": (i32, [vp, i32, i32, vp, i32, i32]),
         "mxb_patch_process": (i32, [vp, i32, vp, vp, vp, i32, vp]),
         "mxb_patch_launch_count": (i64, [vp]),
+        "mxb_patch_set_mode": (i32, [vp, i32]),
+        "mxb_patch_get_mode": (i32, [vp]),
+        "mxb_patch_codegen": (i32, [vp, vp, i64, vp, i32]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)          # AttributeError here = the library does not export a declared symbol
@@ -559,7 +562,8 @@ class PatchDesc(C.Structure):
     _fields_ = [("voices", C.c_int32), ("n_stages", C.c_int32), ("n_params", C.c_int32), ("n_consts", C.c_int32), ("n_inputs", C.c_int32),
                 ("max_frames", C.c_int32), ("delay_taps", C.c_int32), ("eg_stages", C.c_int32), ("eg_loop", C.c_int32), ("eg_retrigger", C.c_int32),
                 ("stages", C.POINTER(Stage)), ("consts", C.POINTER(C.c_double)),
-                ("eg_levels", C.POINTER(C.c_double)), ("eg_times", C.POINTER(C.c_double)), ("eg_curves", C.POINTER(C.c_double))]
+                ("eg_levels", C.POINTER(C.c_double)), ("eg_times", C.POINTER(C.c_double)), ("eg_curves", C.POINTER(C.c_double)),
+                ("input_types", C.POINTER(C.c_int32))]
 
 
 def set_tables(sine514, transition1001, sine_before, ctx=None, device=0, sample_rate=48000):
@@ -570,24 +574,62 @@ def set_tables(sine514, transition1001, sine_before, ctx=None, device=0, sample_
     check(lib().mxb_ctx_set_tables(ctx.h, _np_ptr(s), _np_ptr(t), float(sine_before)), "mxb_ctx_set_tables")
 
 
-class Patch:
-    """mxb_patch: a per-voice signal graph (maximilian_b200.patchdef.PatchDef) run by the interpreting kernel."""
+PATCH_INTERPRET, PATCH_FUSED = 0, 1
 
-    def __init__(self, defn, voices, max_frames=1024, delay_taps=0, ctx=None, device=0, sample_rate=48000):
+
+def _patch_desc(defn, voices, max_frames, delay_taps):
+    """mxb_patch_desc of a PatchDef; the second value keeps the ctypes arrays it points into alive."""
+    st = (Stage * len(defn.stages))()
+    for i, (op, kind, dst, src) in enumerate(defn.stages):
+        st[i].op, st[i].kind, st[i].dst, st[i].reserved = op, kind, dst, 0
+        for k in range(8):
+            st[i].src[k] = src[k]
+    consts = (C.c_double * max(1, len(defn.consts)))(*defn.consts)
+    eg = defn.eg or ([0.0], [], [], False, False)
+    lv = (C.c_double * max(1, len(eg[0])))(*eg[0]); tm = (C.c_double * max(1, len(eg[1])))(*eg[1]); cv = (C.c_double * max(1, len(eg[2])))(*eg[2])
+    ty = (C.c_int32 * max(1, len(defn.inputs)))(*[1 if defn.input_types.get(n) == "u8" else 0 for n in defn.inputs])
+    d = PatchDesc(int(voices), len(defn.stages), len(defn.params), len(defn.consts), len(defn.inputs), int(max_frames), int(delay_taps),
+                  len(eg[1]), int(eg[3]), int(eg[4]), st, consts, lv, tm, cv, ty)
+    return d, (st, consts, lv, tm, cv, ty)
+
+
+def patch_codegen(defn, compile=False):
+    """mxb_patch_codegen: the CUDA source the library generates for this stage list (compile=True: also through NVRTC for
+    sm_100a). Needs no device."""
+    d, keep = _patch_desc(defn, 1, 1, 1)
+    need = C.c_int64(0)
+    check(lib().mxb_patch_codegen(C.byref(d), None, 0, C.byref(need), 0), "mxb_patch_codegen")
+    buf = C.create_string_buffer(need.value)
+    check(lib().mxb_patch_codegen(C.byref(d), buf, need.value, C.byref(need), 1 if compile else 0), "mxb_patch_codegen")
+    return buf.value.decode()
+
+
+class Patch:
+    """mxb_patch: a per-voice signal graph (maximilian_b200.patchdef.PatchDef), run by the kernel the library generates and
+    compiles for it (mode "fused", the default) or by the interpreting kernel (mode "interpret")."""
+
+    def __init__(self, defn, voices, max_frames=1024, delay_taps=0, ctx=None, device=0, sample_rate=48000, mode=None):
         self.ctx = ctx or default_context(device, sample_rate)
         self.defn, self.V, self.max_frames = defn, int(voices), int(max_frames)
-        st = (Stage * len(defn.stages))()
-        for i, (op, kind, dst, src) in enumerate(defn.stages):
-            st[i].op, st[i].kind, st[i].dst, st[i].reserved = op, kind, dst, 0
-            for k in range(8):
-                st[i].src[k] = src[k]
-        consts = (C.c_double * max(1, len(defn.consts)))(*defn.consts)
-        eg = defn.eg or ([0.0], [], [], False, False)
-        lv = (C.c_double * max(1, len(eg[0])))(*eg[0]); tm = (C.c_double * max(1, len(eg[1])))(*eg[1]); cv = (C.c_double * max(1, len(eg[2])))(*eg[2])
-        d = PatchDesc(self.V, len(defn.stages), len(defn.params), len(defn.consts), len(defn.inputs), self.max_frames, int(delay_taps),
-                      len(eg[1]), int(eg[3]), int(eg[4]), st, consts, lv, tm, cv)
+        d, keep = _patch_desc(defn, self.V, self.max_frames, delay_taps)
         self.h = C.c_void_p()
         check(lib().mxb_patch_create(self.ctx.h, C.byref(d), C.byref(self.h)), "mxb_patch_create")
+        if mode is not None:
+            self.set_mode(mode)
+
+    def set_mode(self, mode):
+        m = {"interpret": PATCH_INTERPRET, "fused": PATCH_FUSED}.get(mode, mode)
+        check(lib().mxb_patch_set_mode(self.h, int(m)), "mxb_patch_set_mode")
+
+    @property
+    def mode(self):
+        return {PATCH_INTERPRET: "interpret", PATCH_FUSED: "fused"}[int(lib().mxb_patch_get_mode(self.h))]
+
+    def process_device(self, nframes, input_ptrs, out_ptr, mix_ptr, stream=None):
+        """device pointers in and out, asynchronous on `stream` (bench.py)"""
+        ptrs = (C.c_void_p * max(1, len(input_ptrs)))(*input_ptrs)
+        check(lib().mxb_patch_process(self.h, nframes, ptrs, C.c_void_p(out_ptr) if out_ptr else None, C.c_void_p(mix_ptr) if mix_ptr else None, MEM_DEVICE,
+                                      C.c_void_p(stream) if stream else None), "mxb_patch_process")
 
     def close(self):
         if getattr(self, "h", None):
@@ -625,7 +667,7 @@ class Patch:
     def process(self, nframes, inputs=None, want_out=True, want_mix=False):
         """inputs: dict name -> float64 [nframes][V]. Returns (out[nframes][V] | None, mix[nframes][2] | None)."""
         inputs = inputs or {}
-        arrs = [np.ascontiguousarray(inputs[n], dtype=np.float64) for n in self.defn.inputs]
+        arrs = [np.ascontiguousarray(inputs[n], dtype=np.uint8 if self.defn.input_types.get(n) == "u8" else np.float64) for n in self.defn.inputs]
         for a in arrs:
             assert a.shape == (nframes, self.V)
         ptrs = (C.c_void_p * max(1, len(arrs)))(*[a.ctypes.data for a in arrs])

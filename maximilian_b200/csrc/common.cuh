@@ -1,6 +1,11 @@
 // Internal definitions shared by the translation units of libmaxib200.so (not installed).
 #pragma once
 
+#ifdef __CUDACC_RTC__
+// Compiled at run time (NVRTC, patch_fuse.cu): only the device-side definitions of the headers are wanted; the host half of
+// this file is skipped and maxib200.h arrives as an embedded header.
+#include "maxib200.h"
+#else
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -73,3 +78,4 @@ struct mxb_ctx {
     double* d_sine;          // sineBuffer[514] ++ transition[1001] of the reference (mxb_ctx_set_tables), or NULL
     double sine_before;
 };
+#endif  // __CUDACC_RTC__

@@ -18,84 +18,11 @@
 
 #include <new>
 
-#include "bank_kernels.cuh"
-#include "filter_design.cuh"
+#include "patch_impl.cuh"
 
 using namespace mxb;
 
 namespace {
-
-constexpr int kPatchThreads = 128;
-constexpr int kMaxStages = 64, kMaxParams = 32, kMaxConsts = 64, kMaxInputs = 8, kMaxRegs = 16, kMaxEg = 16;
-
-struct EgStage { double startlevel, endlevel, gradient, curve; long long length; int hold; int pad; };
-
-struct PatchArgs {
-    int V, n_frames, n_stages, n_params, n_state, W, taps;
-    double sr;
-    const mxb_stage* stages;         // device, n_stages
-    const int* state_base;           // device, n_stages: first state slot of each stage
-    const int* ring_of;              // device, n_stages: ring index of a delay-like stage, else -1
-    const double* consts;            // device, kMaxConsts
-    const double* params;            // [n_params][V]
-    double* state;                   // [n_state][V]
-    const double* inputs[kMaxInputs];// [n_frames][V] each
-    double* out;                     // [n_frames][V] or NULL
-    double* partials;                // [n_frames][2][W] or NULL
-    double* rings;                   // [n_rings][taps][V]
-    const double* sine;              // sineBuffer[514], src/maximilian.cpp:63
-    const double* transition;        // transition[1001], src/maximilian.cpp:67-200
-    double sine_before;              // what sinebuf4 reads at sineBuffer[-1] on its wrap sample (out of bounds in the reference)
-    int eg_n, eg_loop, eg_retrigger;
-    EgStage eg[kMaxEg];
-};
-
-// table oscillators, src/maximilian.cpp:237-274, 342-359
-__device__ __forceinline__ double osc_table_tick(const int kind, double& phase, double& output, const double frequency, const double sr,
-                                                 const double* __restrict__ sine, const double* __restrict__ transition, const double sine_before) {
-    if (kind == MXB_OSC_SINEBUF4) {          // :237-264
-        phase += 512. / (sr / (frequency));
-        if (phase >= 511) phase -= 512;
-        const double remainder = phase - floor(phase);
-        double a, b, c, d;
-        const long long ip = (long long)phase;
-        if (phase == 0) { a = sine[512]; b = sine[ip]; c = sine[ip + 1]; d = sine[ip + 2]; }
-        else { a = ip - 1 < 0 ? sine_before : sine[ip - 1]; b = sine[ip]; c = sine[ip + 1]; d = sine[ip + 2]; }
-        const double a1 = 0.5 * (c - a);
-        const double a2 = a - 2.5 * b + 2.0 * c - 0.5 * d;
-        const double a3 = 0.5 * (d - a) + 1.5 * (b - c);
-        output = ((a3 * remainder + a2) * remainder + a1) * remainder + b;
-    } else if (kind == MXB_OSC_SINEBUF) {    // :266-274 (chandiv == 1)
-        phase += 512. / (sr / (frequency * 1.0));
-        if (phase >= 511) phase -= 512;
-        const double remainder = phase - floor(phase);
-        const long long ip = (long long)phase;
-        output = (1 - remainder) * sine[1 + ip] + remainder * sine[2 + ip];
-    } else {                                 // sawn, :342-359
-        if (phase >= 0.5) phase -= 1.0;
-        phase += (1. / (sr / (frequency)));
-        double temp = (8820.22 / frequency) * phase;
-        if (temp < -0.5) temp = -0.5;
-        if (temp > 0.5) temp = 0.5;
-        temp *= 1000.0;
-        temp += 500.0;
-        const double remainder = temp - floor(temp);
-        const long long it = (long long)temp;
-        // transition[1 + it] with it == 1000 is one past the table in the reference, multiplied by remainder == 0
-        const double t1 = it + 1 <= 1000 ? transition[it + 1] : 0.0;
-        output = ((1.0 - remainder) * transition[it] + remainder * t1) - phase;
-    }
-    return output;
-}
-
-// maxiTrigger::onZX, src/maximilian.h:564-585
-__device__ __forceinline__ double on_zx(double& previousValue, double& firstTrigger, const double input) {
-    double isZX = 0.0;
-    if ((previousValue <= 0.0 || firstTrigger != 0.0) && input > 0) isZX = 1.0;
-    previousValue = input;
-    firstTrigger = 0.0;
-    return isZX;
-}
 
 // state / register file of one thread in shared memory: slot-major, thread-minor
 struct Lane {
@@ -134,7 +61,7 @@ __global__ void __launch_bounds__(kPatchThreads) patch_kernel(const PatchArgs a)
                 case 0: return reg[k];
                 case 1: return par[k];
                 case 2: return s_const[k];
-                default: return live ? a.inputs[k][(size_t)t * V + vv] : 0.0;
+                default: return live ? patch_input(a, k, (size_t)t * V + vv) : 0.0;
             }
         };
         for (int si = 0; si < a.n_stages; ++si) {
@@ -144,13 +71,7 @@ __global__ void __launch_bounds__(kPatchThreads) patch_kernel(const PatchArgs a)
             switch (g.op) {
                 case MXB_OP_OSC: {
                     double phase = st[sb], oout = st[sb + 1];
-                    const double f = fetch(g.src[0]);
-                    if (g.kind >= MXB_OSC_SINEBUF) y = osc_table_tick(g.kind, phase, oout, f, sr, a.sine, a.transition, a.sine_before);
-                    else {
-                        const double d0 = fetch(g.src[1]), d1 = fetch(g.src[2]);
-                        const double inc = g.kind == MXB_OSC_PHASORBETWEEN ? ((d1 - d0) / (sr / (f))) : (1. / (sr / (f)));
-                        y = osc_tick<OSC_T_GENERIC>(phase, oout, inc, d0, g.kind, d1);
-                    }
+                    y = stage_osc(g.kind, phase, oout, fetch(g.src[0]), fetch(g.src[1]), fetch(g.src[2]), sr, a.sine, a.transition, a.sine_before);
                     st[sb] = phase; st[sb + 1] = oout;
                     break;
                 }
@@ -173,44 +94,16 @@ __global__ void __launch_bounds__(kPatchThreads) patch_kernel(const PatchArgs a)
                     break;
                 }
                 case MXB_OP_ENVGEN: {
-                    // maxiEnvGen::play, src/maximilian.h:2276-2357. Slots: 0 envval, 1 phase, 2 state (0 WAITING, 1 TRIGGERED, 2 HOLDING),
-                    // 3 nxcHappened, 4 counter, 5 currentlevel (of the current segment: every other segment's are 0), 6/7 trigDetector,
-                    // 8/9 holdDetector, 10/11 retriggerDetector (previousValue, firstTrigger)
-                    const double trigger = fetch(g.src[0]);
-                    double envval = st[sb]; int phase = (int)st[sb + 1], state = (int)st[sb + 2]; bool nxc = st[sb + 3] != 0.0;
-                    long long counter = (long long)st[sb + 4]; double currentlevel = st[sb + 5];
-                    double tp = st[sb + 6], tf = st[sb + 7], hp = st[sb + 8], hf = st[sb + 9], rp = st[sb + 10], rf = st[sb + 11];
-                    auto reset = [&]() { counter = 0; currentlevel = 0; phase = 0; state = 1; };
-                    bool run = true;
-                    if (state == 0) {
-                        if (on_zx(tp, tf, trigger) != 0.0) { if (a.eg_n > 0) { state = 1; nxc = false; } else run = false; }
-                        else run = false;
-                    }
-                    if (run && state == 1) {
-                        const EgStage& cs = a.eg[phase < a.eg_n ? phase : 0];
-                        if (on_zx(hp, hf, -trigger) != 0.0) nxc = true;
-                        if (cs.hold) state = 2;
-                        else {
-                            double val = pow(currentlevel, cs.curve);
-                            val = fmax(fmin(val, 1.0), 0.0);                                   // maxiMap::linlin, src/maximilian.h:801-805
-                            envval = ((val - 0.0) / (1.0 - 0.0) * (cs.endlevel - cs.startlevel)) + cs.startlevel;
-                            counter++;
-                            if (counter == cs.length) { counter = 0; currentlevel = 0; phase++; }
-                            else currentlevel += cs.gradient;
-                            if (a.eg_retrigger) { if (on_zx(rp, rf, trigger) != 0.0) { nxc = false; reset(); } }
-                            run = false;
-                        }
-                    }
-                    if (run && state == 2) {
-                        if (on_zx(hp, hf, -trigger) != 0.0) nxc = true;
-                        if (nxc) { state = 1; phase++; }
-                        if (a.eg_retrigger) { if (on_zx(rp, rf, trigger) != 0.0) { nxc = false; reset(); } }
-                    }
-                    if (phase == a.eg_n) { reset(); if (!a.eg_loop) state = 0; }
-                    y = envval;
-                    st[sb] = envval; st[sb + 1] = (double)phase; st[sb + 2] = (double)state; st[sb + 3] = nxc ? 1.0 : 0.0;
-                    st[sb + 4] = (double)counter; st[sb + 5] = currentlevel;
-                    st[sb + 6] = tp; st[sb + 7] = tf; st[sb + 8] = hp; st[sb + 9] = hf; st[sb + 10] = rp; st[sb + 11] = rf;
+                    // slots: 0 envval, 1 phase, 2 state, 3 nxcHappened, 4 counter, 5 currentlevel, 6/7 trigDetector, 8/9 holdDetector,
+                    // 10/11 retriggerDetector (previousValue, firstTrigger)
+                    EgRegs q;
+                    q.envval = st[sb]; q.phase = (int)st[sb + 1]; q.state = (int)st[sb + 2]; q.nxc = st[sb + 3] != 0.0;
+                    q.counter = (long long)st[sb + 4]; q.currentlevel = st[sb + 5];
+                    q.tp = st[sb + 6]; q.tf = st[sb + 7]; q.hp = st[sb + 8]; q.hf = st[sb + 9]; q.rp = st[sb + 10]; q.rf = st[sb + 11];
+                    y = envgen_tick(q, fetch(g.src[0]), a.eg, a.eg_n, a.eg_loop, a.eg_retrigger);
+                    st[sb] = q.envval; st[sb + 1] = (double)q.phase; st[sb + 2] = (double)q.state; st[sb + 3] = q.nxc ? 1.0 : 0.0;
+                    st[sb + 4] = (double)q.counter; st[sb + 5] = q.currentlevel;
+                    st[sb + 6] = q.tp; st[sb + 7] = q.tf; st[sb + 8] = q.hp; st[sb + 9] = q.hf; st[sb + 10] = q.rp; st[sb + 11] = q.rf;
                     break;
                 }
                 case MXB_OP_FILTER: {
@@ -220,20 +113,15 @@ __global__ void __launch_bounds__(kPatchThreads) patch_kernel(const PatchArgs a)
                         filt_design<FILT_T_LORES>(f, fetch(g.src[1]), fetch(g.src[2]), sr);
                         y = g.kind == MXB_FILT_LORES ? filt_tick<FILT_T_LORES>(f, in, nullptr) : filt_tick<FILT_T_HIRES>(f, in, nullptr);
                         st[sb] = f.s0; st[sb + 1] = f.s1;
-                    } else if (g.kind == MXB_FILT_LOPASS) {      // src/maximilian.cpp:442-446
-                        const double c = fetch(g.src[1]);
-                        y = st[sb] + c * (in - st[sb]);
-                        st[sb] = y;
-                    } else if (g.kind == MXB_FILT_HIPASS) {      // :449-453
-                        const double c = fetch(g.src[1]);
-                        y = in - (st[sb] + c * (in - st[sb]));
-                        st[sb] = y;
-                    } else {                                      // bandpass, :487-500
-                        double c0, c1, c2;
+                    } else if (g.kind == MXB_FILT_LOPASS || g.kind == MXB_FILT_HIPASS) {
+                        double z0 = st[sb];
+                        y = onepole_tick(g.kind, z0, in, fetch(g.src[1]));
+                        st[sb] = z0;
+                    } else {
+                        double c0, c1, c2, z0 = st[sb], z1 = st[sb + 1];
                         design_bandpass(fetch(g.src[1]), fetch(g.src[2]), sr, c0, c1, c2);
-                        y = c0 * in + c1 * st[sb] + c2 * st[sb + 1];
-                        st[sb + 1] = st[sb];
-                        st[sb] = y;
+                        y = bandpass_tick(z0, z1, in, c0, c1, c2);
+                        st[sb] = z0; st[sb + 1] = z1;
                     }
                     break;
                 }
@@ -254,66 +142,31 @@ __global__ void __launch_bounds__(kPatchThreads) patch_kernel(const PatchArgs a)
                     st[sb] = f.s0; st[sb + 1] = f.s1;
                     break;
                 }
-                case MXB_OP_DCBLOCK: {           // maxiDCBlocker::play, src/maximilian.h:1261-1266
-                    const double in = fetch(g.src[0]), R = fetch(g.src[1]);
-                    const double ym1 = in - st[sb] + R * st[sb + 1];
-                    st[sb + 1] = ym1; st[sb] = in;
-                    y = ym1;
+                case MXB_OP_DCBLOCK: {
+                    double xm1 = st[sb], ym1 = st[sb + 1];
+                    y = dcblock_tick(xm1, ym1, fetch(g.src[0]), fetch(g.src[1]));
+                    st[sb] = xm1; st[sb + 1] = ym1;
                     break;
                 }
-                case MXB_OP_NONLIN: {            // maxiNonlinearity, src/maximilian.h:1076-1137
-                    double x = fetch(g.src[0]);
-                    const double p1 = fetch(g.src[1]), p2 = fetch(g.src[2]);
-                    switch (g.kind) {
-                        case MXB_NL_ATANDIST: x = (1.0 / atan(p1)) * atan(x * p1); break;
-                        case MXB_NL_FASTATANDIST: x = (1.0 / (p1 / (1.0 + 0.28 * (p1 * p1)))) * ((x * p1) / (1.0 + 0.28 * ((x * p1) * (x * p1)))); break;
-                        case MXB_NL_SOFTCLIP: if (x >= 1) x = 1; else if (x <= -1) x = -1; else x = (2 / 3.0) * (x - pow(x, 3.0) / 3.0); break;
-                        case MXB_NL_HARDCLIP: x = x >= 1 ? 1 : (x <= -1 ? -1 : x); break;
-                        case MXB_NL_ASYMCLIP: if (x >= 1) x = 1; else if (x <= -1) x = -1; else if (x < 0) x = -(pow(-x, p1)); else x = pow(x, p2); break;
-                        default: x = (x / (1.0 + 0.28 * (x * x))); break;       // fastatan
-                    }
-                    y = x;
-                    break;
-                }
+                case MXB_OP_NONLIN: y = nonlin_eval(g.kind, fetch(g.src[0]), fetch(g.src[1]), fetch(g.src[2])); break;
                 case MXB_OP_DELAY:
                 case MXB_OP_FLANGER: {
                     double* ring = a.rings + (size_t)s_ring[si] * (size_t)a.taps * V + vv;      // slot r of this voice at ring[r * V]
                     const double in = fetch(g.src[0]);
-                    int size; double fb;
-                    if (g.op == MXB_OP_DELAY) { size = (int)fetch(g.src[1]); fb = fetch(g.src[2]); }
-                    else {
-                        // maxiFlanger::flange, src/maximilian.h:1167-1175: lfo.triangle(speed), size = delay + lfo*depth*delay + 1 (-> int)
-                        const unsigned int delay = (unsigned int)fetch(g.src[1]);
-                        fb = fetch(g.src[2]);
-                        const double speed = fetch(g.src[3]), depth = fetch(g.src[4]);
-                        double lph = st[sb + 1], lout = st[sb + 2];
-                        const double lfoVal = osc_tick<OSC_T_GENERIC>(lph, lout, 1. / (sr / (speed)), 0.0, MXB_OSC_TRIANGLE, 0.0);
-                        st[sb + 1] = lph; st[sb + 2] = lout;
-                        size = (int)(delay + (lfoVal * depth * delay) + 1);
-                    }
                     int ph = (int)st[sb];
-                    if (ph >= size) ph = 0;                                   // maxiDelayline::dl, src/maximilian.cpp:420-429
-                    const int idx = min(max(ph, 0), a.taps - 1);
-                    double outv = 0.0;
-                    if (live) {
-                        const double m = ring[(size_t)idx * V];
-                        if (g.op == MXB_OP_DELAY && g.kind == MXB_DELAY_FROM_POSITION) {   // dlFromPosition, :431-439
-                            int pos = (int)fetch(g.src[3]);
-                            if (pos >= size) pos = 0;
-                            outv = ring[(size_t)min(max(pos, 0), a.taps - 1) * V];
-                            ring[(size_t)idx * V] = (m * fb) + (in * fb) * 1.0;
-                        } else {
-                            outv = m;
-                            ring[(size_t)idx * V] = (m * fb) + (in * fb) * 0.5;
-                        }
+                    if (g.op == MXB_OP_DELAY) {
+                        const int size = (int)fetch(g.src[1]);
+                        const double fb = fetch(g.src[2]);
+                        const bool fp = g.kind == MXB_DELAY_FROM_POSITION;
+                        y = delay_tick(fp, ring, V, a.taps, live, ph, in, size, fb, fp ? (int)fetch(g.src[3]) : 0);
+                    } else {
+                        double lph = st[sb + 1], lout = st[sb + 2];
+                        const unsigned int delay = (unsigned int)fetch(g.src[1]);
+                        const double fb = fetch(g.src[2]);
+                        y = flanger_tick(ring, V, a.taps, live, ph, lph, lout, in, delay, fb, fetch(g.src[3]), fetch(g.src[4]), sr);
+                        st[sb + 1] = lph; st[sb + 2] = lout;
                     }
-                    ph += 1;
                     st[sb] = (double)ph;
-                    if (g.op == MXB_OP_FLANGER) {
-                        const double normalise = (1 - fabs(outv));
-                        outv *= normalise;
-                        y = (outv + in) / 2.0;
-                    } else y = outv;
                     break;
                 }
                 case MXB_OP_ADD: y = fetch(g.src[0]) + fetch(g.src[1]); break;
@@ -321,11 +174,8 @@ __global__ void __launch_bounds__(kPatchThreads) patch_kernel(const PatchArgs a)
                 case MXB_OP_MUL: y = fetch(g.src[0]) * fetch(g.src[1]); break;
                 case MXB_OP_DIV: y = fetch(g.src[0]) / fetch(g.src[1]); break;
                 case MXB_OP_MIX_STEREO: {        // maxiMix::stereo, src/maximilian.cpp:503-509, accumulated over the stages of this sample
-                    const double in = fetch(g.src[0]);
-                    double x = fetch(g.src[1]);
-                    if (x > 1) x = 1;
-                    if (x < 0) x = 0;
-                    if (live) { ml += in * sqrt(1.0 - x); mr += in * sqrt(x); }
+                    const double in = fetch(g.src[0]), x = fetch(g.src[1]);
+                    if (live) mix_stereo_acc(ml, mr, in, x);
                     break;
                 }
                 case MXB_OP_OUT:
@@ -361,19 +211,13 @@ __global__ void patch_mix_reduce_kernel(const double* __restrict__ partials, dou
     if (threadIdx.x == 0) mix[blockIdx.x] = (sm[0] + sm[1]) + (sm[2] + sm[3]);
 }
 
-int state_slots(const mxb_stage& g) {
-    switch (g.op) {
-        case MXB_OP_OSC: return 2;
-        case MXB_OP_ENV_ADSR: case MXB_OP_ENV_AR: return 4;
-        case MXB_OP_ENVGEN: return 12;
-        case MXB_OP_FILTER: return 2;
-        case MXB_OP_SVF: return 3;
-        case MXB_OP_BIQUAD: return 2;
-        case MXB_OP_DCBLOCK: return 2;
-        case MXB_OP_DELAY: return 1;
-        case MXB_OP_FLANGER: return 3;
-        default: return 0;
-    }
+int state_slots(const mxb_stage& g) { return patch_state_slots(g.op); }
+
+// MXB_PATCH_MODE=interpret | fused overrides the default (fused) for patches created afterwards: an A/B and debugging hook
+int patch_default_mode() {
+    const char* e = getenv("MXB_PATCH_MODE");
+    if (e && strcmp(e, "interpret") == 0) return MXB_PATCH_INTERPRET;
+    return MXB_PATCH_FUSED;
 }
 
 bool src_ok(int s, const mxb_patch_desc* d) {
@@ -390,20 +234,6 @@ bool src_ok(int s, const mxb_patch_desc* d) {
 }
 
 }  // namespace
-
-struct mxb_patch {
-    mxb_ctx* ctx;
-    int V, n_stages, n_params, n_consts, n_inputs, max_frames, taps, n_state, n_rings;
-    std::vector<mxb_stage> stages;
-    std::vector<int> state_base, ring_of;
-    mxb_stage* d_stages; int* d_state_base; int* d_ring_of; double* d_consts;
-    double* params; double* state; double* rings;
-    double* in_stage[kMaxInputs]; size_t in_stage_len[kMaxInputs];
-    double* out_stage; size_t out_stage_len;
-    double* partials; double* mix_dev;
-    int eg_n, eg_loop, eg_retrigger; EgStage eg[kMaxEg];
-    int64_t launches;
-};
 
 extern "C" {
 
@@ -427,6 +257,8 @@ int32_t mxb_patch_create(mxb_ctx* ctx, const mxb_patch_desc* d, mxb_patch** out)
     MXB_REQUIRE(d->n_consts == 0 || d->consts, MXB_ERR_INVALID, "mxb_patch_create: consts is NULL");
     MXB_REQUIRE(d->delay_taps >= 0, MXB_ERR_INVALID, "mxb_patch_create: delay_taps %d", d->delay_taps);
     MXB_REQUIRE(d->eg_stages >= 0 && d->eg_stages <= kMaxEg, MXB_ERR_INVALID, "mxb_patch_create: eg_stages %d (0..%d)", d->eg_stages, kMaxEg);
+    for (int i = 0; d->input_types && i < d->n_inputs; ++i)
+        MXB_REQUIRE(d->input_types[i] == MXB_IN_F64 || d->input_types[i] == MXB_IN_U8, MXB_ERR_INVALID, "mxb_patch_create: input_types[%d] = %d", i, d->input_types[i]);
     int n_state = 0, n_rings = 0;
     bool tables = false, eg = false;
     for (int i = 0; i < d->n_stages; ++i) {
@@ -456,6 +288,9 @@ int32_t mxb_patch_create(mxb_ctx* ctx, const mxb_patch_desc* d, mxb_patch** out)
     p->ctx = ctx; p->V = d->voices; p->n_stages = d->n_stages; p->n_params = d->n_params; p->n_consts = d->n_consts; p->n_inputs = d->n_inputs;
     p->max_frames = d->max_frames; p->taps = d->delay_taps; p->n_state = n_state; p->n_rings = n_rings;
     p->stages.assign(d->stages, d->stages + d->n_stages);
+    if (d->n_consts) p->consts.assign(d->consts, d->consts + d->n_consts);
+    p->mode = patch_default_mode(); p->fused = nullptr;
+    for (int i = 0; i < d->n_inputs; ++i) p->in_type[i] = d->input_types ? d->input_types[i] : MXB_IN_F64;
     int sb = 0, ri = 0;
     for (int i = 0; i < d->n_stages; ++i) {
         p->state_base.push_back(sb); sb += state_slots(p->stages[i]);
@@ -511,6 +346,7 @@ int32_t mxb_patch_destroy(mxb_patch* p) {
     if (!p) return MXB_OK;
     DeviceGuard g(p->ctx->device);
     cudaDeviceSynchronize();
+    patch_fused_free(p);
     cudaFree(p->d_stages); cudaFree(p->d_state_base); cudaFree(p->d_ring_of); cudaFree(p->d_consts);
     cudaFree(p->params); cudaFree(p->state); cudaFree(p->rings); cudaFree(p->out_stage); cudaFree(p->partials); cudaFree(p->mix_dev);
     for (auto q : p->in_stage) cudaFree(q);
@@ -568,7 +404,47 @@ int32_t mxb_patch_get_ring(mxb_patch* p, int32_t stage, int32_t voice, double* d
 
 int64_t mxb_patch_launch_count(const mxb_patch* p) { return p ? p->launches : 0; }
 
-int32_t mxb_patch_process(mxb_patch* p, int32_t n_frames, const double* const* inputs, double* out, double* mix, int32_t mem, void* stream_) {
+int32_t mxb_patch_set_mode(mxb_patch* p, int32_t mode) {
+    MXB_REQUIRE(p, MXB_ERR_INVALID, "mxb_patch_set_mode: NULL patch");
+    MXB_REQUIRE(mode == MXB_PATCH_INTERPRET || mode == MXB_PATCH_FUSED, MXB_ERR_INVALID, "mxb_patch_set_mode: mode %d", mode);
+    if (mode == MXB_PATCH_FUSED) {          // compile now: a patch that cannot be compiled says so here, not in the audio loop
+        DeviceGuard g(p->ctx->device);
+        const int rc = patch_fused_load(p);
+        if (rc != MXB_OK) return rc;
+    }
+    p->mode = mode;
+    return MXB_OK;
+}
+
+int32_t mxb_patch_get_mode(const mxb_patch* p) { return p ? p->mode : MXB_ERR_INVALID; }
+
+int32_t mxb_patch_codegen(const mxb_patch_desc* d, char* buf, int64_t cap, int64_t* needed, int32_t compile) {
+    MXB_REQUIRE(d && d->stages && needed, MXB_ERR_INVALID, "mxb_patch_codegen: NULL argument");
+    MXB_REQUIRE(d->n_stages > 0 && d->n_stages <= kMaxStages && d->n_params >= 0 && d->n_params <= kMaxParams && d->n_consts >= 0 && d->n_consts <= kMaxConsts &&
+                d->n_inputs >= 0 && d->n_inputs <= kMaxInputs && (d->n_consts == 0 || d->consts), MXB_ERR_INVALID, "mxb_patch_codegen: bad descriptor");
+    for (int i = 0; i < d->n_stages; ++i) {
+        const mxb_stage& g = d->stages[i];
+        MXB_REQUIRE(g.op >= MXB_OP_OSC && g.op <= MXB_OP_OUT && (g.dst == MXB_NONE || (g.dst >= 0 && g.dst < kMaxRegs)), MXB_ERR_INVALID, "mxb_patch_codegen: stage %d", i);
+        for (int k = 0; k < MXB_STAGE_SRCS; ++k) MXB_REQUIRE(src_ok(g.src[k], d), MXB_ERR_INVALID, "mxb_patch_codegen: stage %d: operand %d = 0x%x", i, k, g.src[k]);
+    }
+    int types[kMaxInputs] = {};
+    for (int i = 0; d->input_types && i < d->n_inputs; ++i) {
+        MXB_REQUIRE(d->input_types[i] == MXB_IN_F64 || d->input_types[i] == MXB_IN_U8, MXB_ERR_INVALID, "mxb_patch_codegen: input_types[%d] = %d", i, d->input_types[i]);
+        types[i] = d->input_types[i];
+    }
+    const std::string src = patch_generate_source(d->stages, d->n_stages, d->n_params, d->consts, d->n_consts, d->n_inputs, types);
+    *needed = (int64_t)src.size() + 1;
+    if (buf && cap > 0) { const size_t n = src.size() + 1 <= (size_t)cap ? src.size() : (size_t)cap - 1; memcpy(buf, src.data(), n); buf[n] = 0; }
+    if (compile) {
+        std::vector<char> cubin;
+        const int rc = patch_compile(src, cubin);
+        if (rc != MXB_OK) return rc;
+        MXB_REQUIRE(!cubin.empty(), MXB_ERR_STATE, "mxb_patch_codegen: the compiler returned no code");
+    }
+    return MXB_OK;
+}
+
+int32_t mxb_patch_process(mxb_patch* p, int32_t n_frames, const void* const* inputs, double* out, double* mix, int32_t mem, void* stream_) {
     NvtxRange nvtx_("mxb_patch_process");
     MXB_REQUIRE(p, MXB_ERR_INVALID, "mxb_patch_process: NULL patch");
     MXB_REQUIRE(n_frames >= 0 && n_frames <= p->max_frames, MXB_ERR_INVALID, "mxb_patch_process: n_frames %d (max_frames %d)", n_frames, p->max_frames);
@@ -584,11 +460,13 @@ int32_t mxb_patch_process(mxb_patch* p, int32_t n_frames, const double* const* i
     double* d_out = out; double* d_mix = mix;
     for (int i = 0; i < p->n_inputs; ++i) {
         a.inputs[i] = inputs[i];
+        a.in_u8[i] = p->in_type[i] == MXB_IN_U8;
         if (mem == MXB_MEM_HOST) {
+            const size_t nb = (a.in_u8[i] ? 1 : sizeof(double)) * (size_t)n_frames * V;
             if (nb > p->in_stage_len[i]) {
                 MXB_CUDA(cudaStreamSynchronize(s));
                 cudaFree(p->in_stage[i]); p->in_stage[i] = nullptr; p->in_stage_len[i] = 0;
-                cudaError_t e = cudaMalloc((void**)&p->in_stage[i], nb);
+                cudaError_t e = cudaMalloc(&p->in_stage[i], nb);
                 if (e != cudaSuccess) { set_error("mxb_patch_process: staging cudaMalloc(%zu): %s", nb, cudaGetErrorString(e)); return MXB_ERR_ALLOC; }
                 p->in_stage_len[i] = nb;
             }
@@ -619,10 +497,17 @@ int32_t mxb_patch_process(mxb_patch* p, int32_t n_frames, const double* const* i
     a.sine = p->ctx->d_sine; a.transition = p->ctx->d_sine ? p->ctx->d_sine + 514 : nullptr; a.sine_before = p->ctx->sine_before;
     a.eg_n = p->eg_n; a.eg_loop = p->eg_loop; a.eg_retrigger = p->eg_retrigger;
     for (int i = 0; i < p->eg_n; ++i) a.eg[i] = p->eg[i];
-    const size_t smem = sizeof(double) * (size_t)(kMaxRegs + p->n_params + p->n_state) * kPatchThreads;
-    MXB_CUDA(cudaFuncSetAttribute(patch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    patch_kernel<<<grid, kPatchThreads, smem, s>>>(a);
-    MXB_CUDA(cudaGetLastError());
+    if (p->mode == MXB_PATCH_FUSED) {
+        // the kernel generated for this stage list (patch_fuse.cu): compiled on first use, then launched like any other
+        int rc = patch_fused_load(p);
+        if (rc == MXB_OK) rc = patch_fused_launch(p, a, grid, s);
+        if (rc != MXB_OK) return rc;
+    } else {
+        const size_t smem = sizeof(double) * (size_t)(kMaxRegs + p->n_params + p->n_state) * kPatchThreads;
+        MXB_CUDA(cudaFuncSetAttribute(patch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        patch_kernel<<<grid, kPatchThreads, smem, s>>>(a);
+        MXB_CUDA(cudaGetLastError());
+    }
     p->launches += 1;
     if (mix) {
         patch_mix_reduce_kernel<<<n_frames * 2, 128, 0, s>>>(p->partials, d_mix, W);

@@ -28,6 +28,7 @@ class PatchDef:
         self.consts = []
         self.params = []          # names, index = parameter slot
         self.inputs = []          # names, index = input stream
+        self.input_types = {}     # name -> "u8" for byte streams (triggers / gates); doubles otherwise
         self.eg = None            # (levels, times, curves, loop, retrigger)
 
     def K(self, value):
@@ -48,11 +49,13 @@ class PatchDef:
             assert len(self.params) <= 32
         return 0x100 + self.params.index(name)
 
-    def IN(self, name):
-        """per-sample input stream operand"""
+    def IN(self, name, dtype="f64"):
+        """per-sample input stream operand; dtype "u8": the caller passes unsigned bytes (read as doubles by the stages)"""
         if name not in self.inputs:
             self.inputs.append(name)
             assert len(self.inputs) <= 8
+            if dtype == "u8":
+                self.input_types[name] = "u8"
         return 0x300 + self.inputs.index(name)
 
     def stage(self, op, *src, kind=0, dst=NONE):

@@ -1,5 +1,7 @@
-"""GPU parity of the patch interpreter (K8, maximilian_b200/csrc/patch.cu) through the C ABI against the plain-C oracle and the
-golden fixture made by the compiled reference.
+"""GPU parity of voice patches through the C ABI against the plain-C oracle and the golden fixture made by the compiled reference,
+both ways a patch runs: the kernel generated and compiled for its stage list (K8f, maximilian_b200/csrc/patch_fuse.cu) and the
+interpreting kernel (K8, patch.cu). The two must also agree with each other BIT FOR BIT on every patch (same stage bodies, same
+libdevice routines, same arguments: hoisting a coefficient design out of the sample loop does not change its result).
 
 Bars: patches whose stages are table look-ups and + - * / only are BIT-IDENTICAL; a patch with a stage that designs
 coefficients or calls pow / atan / tan / cos on every sample (libdevice where the reference calls glibc) is asserted at
@@ -31,12 +33,17 @@ def _cmp(got, ref, exact, what):
         np.testing.assert_allclose(got, ref, rtol=1e-9, atol=1e-12, err_msg=what)
 
 
+MODES = ["fused", "interpret"]
+
+
+@pytest.mark.parametrize("mode", MODES)
 @pytest.mark.parametrize("V,B", [(333, 257), (4100, 64)])
 @pytest.mark.parametrize("case", PC.cases(), ids=lambda c: c[0])
-def test_patch_vs_oracle(port, case, V, B):
+def test_patch_vs_oracle(port, case, V, B, mode):
     name, d, params, inputs, exact, taps = case
     _tables(port)
-    g = capi.Patch(d, V, max_frames=B, delay_taps=taps); o = port.Patch(d, V, delay_taps=taps, kind="port")
+    g = capi.Patch(d, V, max_frames=B, delay_taps=taps, mode=mode); o = port.Patch(d, V, delay_taps=taps, kind="port")
+    assert g.mode == mode
     for k, v in params(V, 21).items():
         g.set(k, v); o.set(k, v)
     for blk in range(3):
@@ -55,12 +62,65 @@ def test_patch_vs_oracle(port, case, V, B):
 
 
 @pytest.mark.parametrize("case", PC.cases(), ids=lambda c: c[0])
-def test_patch_golden(port, case):
+def test_fused_equals_interpreted_bit_for_bit(port, case):
+    """the generated kernel against the interpreter: outputs, bus, every state word and the rings, three blocks, switching the
+    SAME patch object between the modes in the last block (identical state layout)"""
+    name, d, params, inputs, exact, taps = case
+    _tables(port)
+    V, B = 1500, 200
+    a = capi.Patch(d, V, max_frames=B, delay_taps=taps, mode="fused"); b = capi.Patch(d, V, max_frames=B, delay_taps=taps, mode="interpret")
+    for k, v in params(V, 5).items():
+        a.set(k, v); b.set(k, v)
+    for blk in range(3):
+        if blk == 2:
+            a.set_mode("interpret"); b.set_mode("fused")
+        ins = inputs(V, B, blk, 4)
+        oa, ma = a.process(B, ins, want_mix=True); ob, mb = b.process(B, ins, want_mix=True)
+        assert np.array_equal(oa, ob, equal_nan=True), f"{name} blk{blk}: fused and interpreted outputs differ"
+        assert np.array_equal(ma, mb, equal_nan=True), f"{name} blk{blk}: fused and interpreted buses differ"
+    for si, (op, kind, dst, src) in enumerate(d.stages):
+        for sl in range(SLOTS.get(op, 0)):
+            assert np.array_equal(a.get_state(si, sl), b.get_state(si, sl), equal_nan=True), f"{name} stage {si} slot {sl}"
+        if op in (10, 11):
+            for v in range(0, V, 101):
+                assert np.array_equal(a.ring(si, v, taps), b.ring(si, v, taps), equal_nan=True)
+
+
+def test_fused_hoists_block_constant_designs(port):
+    """a patch whose filter / oscillator arguments are parameters and constants only (designs emitted before the sample loop)
+    against the oracle, which designs on every sample like the reference"""
+    from maximilian_b200.patchdef import PatchDef, R
+    d = PatchDef()
+    d.stage("osc", d.P("f"), kind="saw", dst=R(0))
+    d.stage("filter", R(0), d.P("cut"), d.K(3.0), kind="lores", dst=R(1))
+    d.stage("svf", R(1), d.P("cut"), d.K(2.0), d.K(1.0), d.K(0.25), d.K(0.0), d.K(0.5), dst=R(2))
+    d.stage("biquad", R(2), d.P("cut"), d.K(0.9), d.K(3.0), kind="peak", dst=R(3))
+    d.stage("filter", R(3), d.P("cut"), d.K(0.4), kind="bandpass", dst=R(4))
+    d.stage("out", R(4)); d.stage("mix_stereo", R(4), d.K(0.3))
+    src = capi.patch_codegen(d)
+    head = src[:src.index("for (int t = 0")]
+    for fn in ("filt_design<FILT_T_LORES>", "filt_design<FILT_T_SVF>", "design_biquad_one", "design_bandpass", "const double inc0"):
+        assert fn in head, f"{fn} was not hoisted out of the sample loop"
+    V, B = 777, 300
+    rng = np.random.default_rng(3)
+    prm = dict(f=rng.uniform(30, 2000, V), cut=rng.uniform(100, 8000, V))
+    g = capi.Patch(d, V, max_frames=B, mode="fused"); o = port.Patch(d, V, kind="port")
+    for k, v in prm.items():
+        g.set(k, v); o.set(k, v)
+    for blk in range(2):
+        og, mg = g.process(B, want_mix=True); oo, mo = o.process(B, want_mix=True)
+        _cmp(og, oo, False, f"hoisted blk{blk}")
+        np.testing.assert_allclose(mg, mo, rtol=1e-9, atol=1e-10)
+
+
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("case", PC.cases(), ids=lambda c: c[0])
+def test_patch_golden(port, case, mode):
     name, d, params, inputs, exact, taps = case
     _tables(port)
     gl = G.load("patches")
     V, B, NB = int(gl["V"]), int(gl["B"]), int(gl["NB"])
-    p = capi.Patch(d, V, max_frames=B, delay_taps=taps)
+    p = capi.Patch(d, V, max_frames=B, delay_taps=taps, mode=mode)
     for k, v in params(V, 2468).items():
         p.set(k, v)
     for blk in range(NB):

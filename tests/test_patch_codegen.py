@@ -1,0 +1,41 @@
+"""Host-side checks of the patch code generator (maximilian_b200/csrc/patch_fuse.cu): no device needed -- the source is generated
+and compiled for sm_100a by NVRTC exactly as a fused patch's first launch does, only the loading step is left out."""
+import re
+
+import pytest
+
+import patch_cases as PC
+from maximilian_b200 import capi
+from maximilian_b200.patchdef import PatchDef, R
+
+
+@pytest.mark.parametrize("case", PC.cases(), ids=lambda c: c[0])
+def test_generated_kernel_compiles_for_sm100a(case):
+    name, d, params, inputs, exact, taps = case
+    src = capi.patch_codegen(d, compile=True)
+    assert 'extern "C" __global__' in src and "mxb_fused_patch" in src
+    # one body per stage, in order
+    assert [int(x) for x in re.findall(r"// stage (\d+):", src)] == list(range(len(d.stages)))
+    # every constant arrives as a bit-exact literal
+    assert len(re.findall(r"__longlong_as_double\(0x[0-9a-f]{16}LL\)", src)) == len(d.consts)
+
+
+def test_block_constant_arguments_are_designed_once():
+    d = PatchDef()
+    d.stage("osc", d.P("f"), kind="saw", dst=R(0))
+    d.stage("filter", R(0), d.P("cut"), d.K(3.0), kind="lores", dst=R(1))
+    d.stage("filter", R(1), R(0), d.K(3.0), kind="hires", dst=R(2))              # cutoff from a register: per sample
+    d.stage("out", R(2))
+    src = capi.patch_codegen(d, compile=True)
+    head, loop = src.split("for (int t = 0", 1)
+    assert "filt_design<FILT_T_LORES>(f1, p1, c0, sr);" in head and "const double inc0" in head
+    assert "filt_design<FILT_T_LORES>(f2, r0, c0, sr);" in loop
+
+
+def test_a_program_the_generator_rejects_is_an_error_not_a_crash():
+    d = PatchDef(); d.stages.append((99, 0, -1, [-1] * 8))
+    with pytest.raises(capi.MxbError):
+        capi.patch_codegen(d)
+    d = PatchDef(); d.stage("add", 0x100 + 5, 0x200 + 7, dst=R(0))                 # parameter / constant that do not exist
+    with pytest.raises(capi.MxbError):
+        capi.patch_codegen(d)
