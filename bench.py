@@ -790,6 +790,259 @@ def mfcc_leg(E, args, steps, warmup):
     return res
 
 
+# ------------------------------------------------------------------------------------------------ voice patch
+
+PATCH_WL = dict(voices=1 << 18, bytes_per=8.0 + 1.0 + (12 * 16 + 8 * 8) / BLOCK,
+                desc="15.polysynth voice patch x 256Ki voices: 2 pulse VCOs (one detuned by a sinebuf LFO) -> lores VCF with per-sample cutoff "
+                     "(coefficients designed every sample: cos, pow, sqrt) -> x ADSR (per-sample trigger bytes), fp64 out[1024][V] materialised + stereo bus")
+
+
+def _tables():
+    g = np.load(os.path.join(ROOT, "tests", "golden", "tables.npz"))      # the reference's sineBuffer / transition DATA (extracted by make_golden.py)
+    return g["sine"], g["transition"], float(g["sine_before"])
+
+
+def cpu_patch_rate(kind, budget_s, voices=4096):
+    """the reference's own objects run the same stage list per sample (oracle/ref_shim.cpp), voices partitioned over pinned threads"""
+    from maximilian_b200 import workloads as W
+    from oracle import oracle_py as O
+    O.load(kind)
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    threads = max(1, min(cores, voices // 8))
+    bounds = np.linspace(0, voices, threads + 1).astype(int)
+    prm = W.polysynth_params(voices)
+    pat = W.note_pattern(voices)
+    d = W.polysynth_patch()
+
+    def make(i):
+        lo, hi = int(bounds[i]), int(bounds[i + 1])
+        q = O.Patch(d, hi - lo, sample_rate=SR, kind=kind)
+        for k, v in prm.items():
+            q.set(k, v[lo:hi])
+        trig = [W.note_triggers(pat, BLOCK, b, lo, hi, dtype=np.float64) for b in range(2)]
+        return q, trig
+
+    farm = CpuFarm(threads, make)
+
+    def job_n(n, b0):
+        def job(i, part):
+            q, trig = part
+            for b in range(n):
+                q.process(BLOCK, {"trigger": trig[(b0 + b) & 1]}, want_out=True, want_mix=False)
+        return job
+    farm.run(job_n(1, 0))
+    n, total, per = 0, 0.0, 2
+    while total < budget_s and n < 1024:
+        dt = farm.run(job_n(per, n))
+        total += dt; n += per
+        if dt < budget_s / 4:
+            per *= 2
+    farm.close()
+    return voices * BLOCK * n / total, voices, threads, n, total
+
+
+def cpu_baseline_patch(budget_s=3.0):
+    kinds = cpu_kinds()
+    res = {}
+    for k in kinds:
+        v, voices, threads, n, total = cpu_patch_rate(k, budget_s)
+        res[k] = dict(value=v, flags=CPU_FLAGS[k], blocks=n, seconds=total)
+    main = kinds[0]
+    out = {"value": res[main]["value"], "unit": "samples/s", "cores": threads, "kind": "reference" if main.startswith("reference") else "port",
+           "flags": res[main]["flags"], "timed_seconds": res[main]["seconds"],
+           "sample": f"{voices} voices x {BLOCK} frames x {res[main]['blocks']} blocks of the same patch run by the reference's own objects, per sample, "
+                     f"voices partitioned over {threads} pinned host threads"}
+    if len(kinds) > 1:
+        out["best_effort"] = {"value": res[kinds[1]]["value"], "flags": res[kinds[1]]["flags"], "timed_seconds": res[kinds[1]]["seconds"]}
+    return out
+
+
+def patch_leg(E, args, steps, warmup):
+    """The reference's polysynth example as a voice patch: the kernel generated + NVRTC-compiled for its stage list (K8f), the
+    interpreting kernel (K8) beside it, and the e2e loop with the trigger bytes coming from the host every block."""
+    torch, capi, W = E.torch, E.capi, E.W
+    rank, world, dev, stream = E.rank, E.world, E.dev, E.stream
+    wl = PATCH_WL
+    V = int(os.environ.get("MXB_BENCH_PATCH_VOICES", wl["voices"]))
+    capi.set_tables(*_tables(), ctx=E.ctx)
+    d = W.polysynth_patch("u8")
+    prm = W.polysynth_params(V, seed=W.SEED + rank)
+    pat = tuple(torch.from_numpy(a).to(dev) for a in W.note_pattern(V, seed=W.SEED + rank))
+
+    def triggers(block_index):          # the same formula as workloads.note_triggers, evaluated on the device for 256 Ki voices
+        t = (torch.arange(BLOCK, dtype=torch.int64, device=dev) + BLOCK * block_index)[:, None]
+        return (((t + pat[1][None, :]) % pat[0][None, :]) < pat[2][None, :]).to(torch.uint8).contiguous()
+    trig = [triggers(b) for b in range(2)]
+    out = torch.empty((BLOCK, V), dtype=torch.float64, device=dev)
+    mix = [torch.zeros((BLOCK, 2), dtype=torch.float64, device=dev) for _ in range(2)]
+    res_modes = {}
+    t_wall = [0.0, 0.0]
+    patches = {}
+    for mode in ("fused", "interpret"):
+        t_c0 = time.perf_counter()
+        pt = capi.Patch(d, V, max_frames=BLOCK, ctx=E.ctx, sample_rate=SR, mode=mode)
+        compile_s = time.perf_counter() - t_c0
+        for k, v in prm.items():
+            pt.set(k, v)
+        patches[mode] = pt
+        n = steps if mode == "fused" else max(3, min(steps, 5))
+
+        def step(k):
+            pt.process_device(BLOCK, [trig[k & 1].data_ptr()], out.data_ptr(), mix[k & 1].data_ptr(), stream=stream.cuda_stream)
+        for k in range(warmup):
+            step(k)
+        barrier(E)
+        l0 = pt.launches
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        tw0 = time.perf_counter()
+        e0.record(stream)
+        for k in range(n):
+            step(warmup + k)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        tw1 = time.perf_counter()
+        barrier(E)
+        ms = e0.elapsed_time(e1)
+        ms_max = max_over_ranks(E, ms)
+        res_modes[mode] = dict(value=world * V * BLOCK * n / (ms_max * 1e-3), ms_per_step=ms_max / n, steps=n, launches=pt.launches - l0, ms_local=ms / n,
+                               create_seconds=compile_s)
+        if mode == "fused":
+            t_wall = [tw0, tw1]
+    # ---- e2e: per step this block's trigger bytes go up from pinned memory on a copy stream (double-buffered on the device), the
+    # fused patch runs, the stereo bus comes back into one of two pinned buffers; one synchronisation at the end
+    pt = patches["fused"]
+    trig_host = [t.cpu().pin_memory() for t in trig]
+    trig_dev = [torch.empty_like(trig[0]) for _ in range(2)]
+    mix_host = [torch.zeros((BLOCK, 2), dtype=torch.float64).pin_memory() for _ in range(2)]
+    copy_stream = torch.cuda.Stream(device=dev)
+    ev_up = [torch.cuda.Event() for _ in range(2)]
+    ev_done = [torch.cuda.Event() for _ in range(2)]
+
+    def e2e_step(k):
+        b = k & 1
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(ev_done[b])
+            trig_dev[b].copy_(trig_host[b], non_blocking=True)
+            ev_up[b].record(copy_stream)
+        stream.wait_event(ev_up[b])
+        pt.process_device(BLOCK, [trig_dev[b].data_ptr()], out.data_ptr(), mix[b].data_ptr(), stream=stream.cuda_stream)
+        ev_done[b].record(stream)
+        mix_host[b].copy_(mix[b], non_blocking=True)
+    e2e_steps = max(3, min(steps, 30))
+    for k in range(3):
+        e2e_step(k)
+    barrier(E)
+    t0 = time.perf_counter()
+    for k in range(e2e_steps):
+        e2e_step(k)
+    torch.cuda.synchronize()
+    dt = max_over_ranks(E, time.perf_counter() - t0)
+    f = res_modes["fused"]
+    res = {"metric": "voice_samples_per_sec", "value": f["value"], "unit": "samples/s", "ms_per_step": f["ms_per_step"], "steps": f["steps"], "warmup": warmup,
+           "gpu_launches": f["launches"]}
+    if rank == 0:
+        peak, peak_src = load_peaks()
+        achieved = wl["bytes_per"] * V * BLOCK / (f["ms_local"] * 1e-3) / 1e9
+        res["config"] = {"workload": wl["desc"], "voices_per_gpu": V, "block": BLOCK, "sample_rate": SR, "parallelism": f"voices sharded x{world}", "collective": "none",
+                         "l2": "no flush needed: each step reads %.2f GB of trigger bytes and writes %.1f GB" % (V * BLOCK / 1e9, V * BLOCK * 8 / 1e9)}
+        res["roofline"] = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, **load_traffic("patch"),
+                           "algorithmic_bytes_per_launch": wl["bytes_per"] * V * BLOCK, "algorithmic_bytes_per_voice_sample": wl["bytes_per"],
+                           "peak_source": peak_src, "kernel": "mxb_fused_patch (generated per patch, NVRTC)", "launch_ms_avg": f["ms_local"],
+                           "note": "fp64-arithmetic bound, not HBM bound: the per-sample lores design (cos + pow + sqrt + 3 divisions) and two oscillator "
+                                   "increments (2 divisions each) are ~1000 instructions per voice-sample; the HBM fraction is reported as north_star asks"}
+        res["interpreter"] = {"value": res_modes["interpret"]["value"], "unit": "samples/s", "ms_per_step": res_modes["interpret"]["ms_per_step"],
+                              "steps": res_modes["interpret"]["steps"], "fused_speedup": f["value"] / res_modes["interpret"]["value"],
+                              "what": "the same patch on the interpreting kernel (MXB_PATCH_INTERPRET): identical results bit for bit"}
+        res["compile_seconds"] = f["create_seconds"]
+        res["e2e"] = {"value": world * V * BLOCK * e2e_steps / dt, "unit": "samples/s", "h2d_bytes_per_step": int(trig_host[0].numel()),
+                      "d2h_bytes_per_step": int(mix_host[0].numel() * 8), "steps": e2e_steps, "frac_of_resident": world * V * BLOCK * e2e_steps / dt / f["value"],
+                      "what": "per step: trigger bytes [1024][V] from pinned host memory (copy stream, double-buffered), mxb_patch_process(MXB_MEM_DEVICE) "
+                              "of the fused patch, stereo bus back to pinned host memory; voice signals materialised on the device"}
+        res["clocks"] = E.sampler.summary(t_wall[0], t_wall[1])
+    del patches, pt, out, trig, trig_dev
+    torch.cuda.empty_cache()
+    return res
+
+
+
+# ------------------------------------------------------------------------------------------------ spectral round trip + analysers (SURVEY.md 8(f))
+
+SPEC_WL = dict(channels=1 << 14, fft=1024, hop=512, hops_per_step=8,
+               desc="16Ki channels, 8 hops per step: maxiFFT 1024/512 (magnitudes + phases written) -> maxiIFFT SPECTRUM resynthesis; and the same "
+                    "analysis with maxiFFTOctaveAnalyzer (averages + peaks) and maxiBark (specific / relative / total loudness) fused in")
+
+
+def spectral_extra_leg(E, args, steps, warmup):
+    """The rows of SURVEY.md 8(f) around the transform that the MFCC leg does not touch: the full-spectrum analysis (cartToPol incl.
+    atan2), the octave-analyser / Bark epilogues, and maxiIFFT. Each sub-leg: CUDA events over `steps` steps, algorithmic bytes."""
+    import ctypes as C_
+    torch, capi, W = E.torch, E.capi, E.W
+    dev, stream, world = E.dev, E.stream, E.world
+    wl = SPEC_WL
+    C, n, hop, H = wl["channels"], wl["fft"], wl["hop"], wl["hops_per_step"]
+    bins = n // 2
+    base = W.channel_streams(1024, H * hop, seed=11 + E.rank)
+    x = torch.from_numpy(np.tile(base, (C // 1024, 1))).to(dev)                  # [C][H*hop] planar fp32
+    mags = torch.empty((C, H, bins), dtype=torch.float32, device=dev); phases = torch.empty_like(mags)
+    y = torch.empty((C, H * hop), dtype=torch.float32, device=dev)
+    L = capi.lib()
+    sp = C_.c_void_p(stream.cuda_stream)
+    nf = C_.c_int32(0)
+    peak, peak_src = load_peaks()
+    out = {}
+
+    def timed(fn, n_steps):
+        for _ in range(warmup):
+            fn()
+        barrier(E)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(n_steps):
+            fn()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        barrier(E)
+        return max_over_ranks(E, e0.elapsed_time(e1)) / n_steps
+
+    def entry(ms, bytes_per_frame, kernel, what):
+        frames = C * H
+        ach = bytes_per_frame * frames / (ms * 1e-3) / 1e9
+        return {"value": world * frames / (ms * 1e-3), "unit": "frames/s", "ms_per_step": ms, "steps": steps,
+                "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                             "kernel": kernel, "algorithmic_bytes_per_frame": bytes_per_frame}, "what": what}
+
+    # (1) analysis with the whole spectrum leaving the chip: magnitudes + phases (atan2f per bin)
+    st = capi.Stft(C, n, hop, ctx=E.ctx)
+    ms = timed(lambda: st.process_device(x.data_ptr(), H * hop, 1, H * hop, H, mags=mags.data_ptr(), phases=phases.data_ptr(), stream=stream.cuda_stream), steps)
+    out["analysis_mags_phases"] = entry(ms, hop * 4 + 2 * bins * 4, "stft_stream_kernel<FULL>", "maxiFFT::process + cartToPol, magnitudes and phases written")
+    # (2) resynthesis: maxiIFFT SPECTRUM from those magnitudes / phases
+    ist = capi.Istft(C, n, hop, ctx=E.ctx)
+
+    def resyn():
+        capi.check(L.mxb_istft_process(ist.h, C_.c_void_p(mags.data_ptr()), C_.c_void_p(phases.data_ptr()), H, C_.c_void_p(y.data_ptr()), capi.MEM_DEVICE, sp), "mxb_istft_process")
+    ms = timed(resyn, steps)
+    out["resynthesis"] = entry(ms, 2 * bins * 4 + hop * 4, "istft_frame_kernel + istft_ola_kernel", "maxiIFFT::process(SPECTRUM): polToCart, inverse transform, window, overlap-add")
+    del ist, y, phases
+    # (3) analysis with the octave analyser and Bark loudness fused in (magnitudes written too)
+    oc = capi.Octave(C, float(SR), bins, 3, ctx=E.ctx)
+    nA = oc.n_averages
+    av = torch.empty((C, H, nA), dtype=torch.float32, device=dev); pk = torch.empty_like(av)
+    bs = torch.empty((C, H, 24), dtype=torch.float64, device=dev); br = torch.empty_like(bs); bt = torch.empty((C, H), dtype=torch.float64, device=dev)
+    o = capi.StftOutputs(mags.data_ptr(), None, None, None, None, None, None, None)
+    post = capi.StftPost(oc.h, av.data_ptr(), pk.data_ptr(), 1, bs.data_ptr(), br.data_ptr(), bt.data_ptr())
+
+    def analyse():
+        capi.check(L.mxb_stft_process3(st.h, C_.c_void_p(x.data_ptr()), H * hop, 1, H * hop, H, C_.byref(o), C_.byref(post), None, C_.byref(nf), capi.MEM_DEVICE, sp), "mxb_stft_process3")
+    ms = timed(analyse, steps)
+    out["analysis_octave_bark"] = entry(ms, hop * 4 + bins * 4 + 2 * nA * 4 + (48 + 1) * 8, "stft_stream_kernel<FULL> + octave / Bark epilogues",
+                                        f"maxiFFT::process + maxiFFTOctaveAnalyzer::calculate ({nA} averages, peaks) + maxiBark, magnitudes written")
+    out["config"] = {"workload": wl["desc"], "channels_per_gpu": C, "hops_per_step": H}
+    del st, oc, x, mags, av, pk, bs, br, bt
+    torch.cuda.empty_cache()
+    return out
+
+
+
 def finish(E):
     if E.rank == 0:
         time.sleep(0.06)
@@ -804,7 +1057,7 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200")
-    ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS) + ["mfcc"],
+    ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS) + ["mfcc", "patch", "spectral"],
                     help="headline workload (default svf = BASELINE.json configs[1]; without this flag and with one GPU the other "
                          "configurations are measured too and reported under 'workloads')")
     ap.add_argument("--mix", type=int, default=-1,
@@ -822,9 +1075,28 @@ def main():
     if args.impl == "reference":
         if wl_name == "mfcc":
             return reference_arm_mfcc(args)
+        if wl_name == "patch":
+            return reference_arm_patch(args)
         return reference_arm(args, wl_name, WORKLOADS[wl_name])
     assert args.warmup >= 3, "timing rules: at least 3 warm-up steps"
     E = setup_env(args)
+
+    if wl_name == "spectral":
+        r = spectral_extra_leg(E, args, max(3, min(args.steps, 20)), args.warmup)
+        if E.rank == 0:
+            print(json.dumps({"metric": "fft_frames_per_sec", "unit": "frames/s", "n_gpus": E.world, "higher_is_better": True, "data": "synthetic", **r}), flush=True)
+        return finish(E)
+
+    if wl_name == "patch":
+        head = patch_leg(E, args, args.steps, args.warmup)
+        if E.rank == 0:
+            line = {"metric": "voice_samples_per_sec", "value": head["value"], "unit": "samples/s", "n_gpus": E.world, "steps": args.steps,
+                    "warmup": args.warmup, "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                    "dtype": "f64", "data": "synthetic", **{k: head[k] for k in ("config", "roofline", "e2e", "gpu_launches", "clocks", "interpreter", "compile_seconds")}}
+            if not args.no_cpu and E.world == 1:
+                line["cpu_baseline"] = cpu_baseline_patch()
+            print(json.dumps(line), flush=True)
+        return finish(E)
 
     if wl_name == "mfcc":
         head = mfcc_leg(E, args, args.steps, args.warmup)
@@ -859,6 +1131,11 @@ def main():
         if not args.no_cpu:
             r["cpu_baseline"] = cpu_baseline_mfcc(3.0)
         extras["mfcc"] = r
+        r = patch_leg(E, args, max(3, min(args.steps, 20)), xw)
+        if not args.no_cpu:
+            r["cpu_baseline"] = cpu_baseline_patch(3.0)
+        extras["patch"] = r
+        extras["spectral_extras"] = spectral_extra_leg(E, args, 5, 3)
     if E.rank == 0:
         line = {"metric": "voice_samples_per_sec", "value": head["value"], "unit": "samples/s", "n_gpus": E.world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "weak",
@@ -889,6 +1166,19 @@ def reference_arm_mfcc(args):
                                        "flags": CPU_FLAGS[kind], "timed_seconds": dt,
                                        "sample": f"each step = 64 hops of {ch} channels on {threads} pinned host threads"},
                       "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
+
+
+def reference_arm_patch(args):
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    kind = cpu_kinds()[-1]
+    v, voices, threads, n, dt = cpu_patch_rate(kind, 3.0 * max(1, min(args.steps, 10)) / 3.0)
+    print(json.dumps({"impl": "reference", "metric": "voice_samples_per_sec", "value": v, "unit": "samples/s", "n_gpus": args.gpus, "steps": args.steps,
+                      "warmup": 1, "ms_per_step": 1e3 * dt / max(1, n), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                      "data": "synthetic", "config": {"workload": PATCH_WL["desc"], "cpu_sample_voices": voices, "block": BLOCK, "sample_rate": SR},
+                      "cpu_baseline": {"value": v, "unit": "samples/s", "cores": threads, "kind": "reference" if kind.startswith("reference") else "port",
+                                       "flags": CPU_FLAGS[kind], "timed_seconds": dt, "sample": f"{voices} voices x {BLOCK} frames x {n} blocks on {threads} pinned host threads"},
+                      "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
 
 
 if __name__ == "__main__":

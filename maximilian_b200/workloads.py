@@ -96,3 +96,53 @@ def configure_bank(bank, filt, p, env=False, delay=False, sample_rate=SAMPLE_RAT
     if delay:
         bank.set("delay_size", p["delay_size"]); bank.set("delay_feedback", p["delay_feedback"])
     bank.set("pan", p["pan"])
+
+
+def polysynth_patch(trigger_dtype="f64"):
+    """One voice of cpp/commandline/maximilian_examples/15.polysynth/main.cpp:54-70 as a PatchDef: two pulse VCOs (the second
+    detuned by a sinebuf LFO) summed into a lores VCF whose cutoff follows pitch + LFO, multiplied by the ADSR AFTER the filter.
+    trigger_dtype "u8": the per-sample trigger stream arrives as bytes (maxiEnv::trigger is an int)."""
+    from .patchdef import PatchDef, R
+    d = PatchDef()
+    one = d.K(1.0)
+    d.stage("env_adsr", one, d.IN("trigger", trigger_dtype), d.P("attack"), d.P("decay"), d.P("sustain"), d.P("release"), d.K(1.0), dst=R(0))   # ADSRout
+    d.stage("osc", d.K(0.2), kind="sinebuf", dst=R(1))                                   # LFO1out
+    d.stage("osc", d.P("f1"), d.K(0.6), kind="pulse", dst=R(2))                          # VCO1out = pulse(55*pitch, 0.6)
+    d.stage("add", d.P("f2"), R(1), dst=R(3))                                             # (110*pitch) + LFO1out
+    d.stage("osc", R(3), d.K(0.2), kind="pulse", dst=R(3))                               # VCO2out
+    d.stage("add", R(2), R(3), dst=R(4))
+    d.stage("mul", R(4), d.K(0.5), dst=R(4))                                              # (VCO1out + VCO2out) * 0.5
+    d.stage("add", d.P("pitch"), R(1), dst=R(5))
+    d.stage("mul", R(5), d.K(1000.0), dst=R(5))
+    d.stage("add", d.K(250.0), R(5), dst=R(5))                                            # 250 + ((pitch + LFO1out) * 1000)
+    d.stage("filter", R(4), R(5), d.K(10.0), kind="lores", dst=R(6))                     # VCFout
+    d.stage("mul", R(6), R(0), dst=R(7))
+    d.stage("div", R(7), d.K(6.0), dst=R(7))                                              # VCFout * ADSRout / 6
+    d.stage("out", R(7))
+    d.stage("mix_stereo", R(7), d.P("pan"))
+    return d
+
+
+def polysynth_params(voices, seed=SEED):
+    p = voice_params(voices, seed=seed)
+    att, dec, rel = env_coeffs(p)
+    pitch = 1.0 + (np.arange(voices) % 6)
+    return dict(attack=att, decay=dec, sustain=p["env_sustain"], release=rel, f1=55.0 * pitch, f2=110.0 * pitch, pitch=pitch, pan=p["pan"])
+
+
+def note_pattern(voices, seed=SEED):
+    """(period, offset, length) per voice, samples: trigger(t, v) = ((t + offset_v) mod period_v) < length_v -- every voice plays
+    notes of its own length at its own rate, several per 1024-frame block for the fast ones (10.Filters/main.cpp:27-36 writes
+    maxiEnv::trigger on any sample)."""
+    rng = np.random.default_rng(seed + 404)
+    period = rng.integers(300, 4000, voices)
+    offset = rng.integers(0, 4000, voices)
+    length = (period * (0.1 + 0.6 * rng.random(voices))).astype(np.int64)
+    return period.astype(np.int64), offset.astype(np.int64), length
+
+
+def note_triggers(pattern, block, block_index, lo=0, hi=None, dtype=np.uint8):
+    """trigger[block][hi - lo] of block `block_index` from note_pattern()"""
+    period, offset, length = (a[lo:hi] for a in pattern)
+    t = (np.arange(block, dtype=np.int64) + block * block_index)[:, None]
+    return (((t + offset[None, :]) % period[None, :]) < length[None, :]).astype(dtype)

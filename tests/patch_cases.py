@@ -27,29 +27,10 @@ def _trig_stream(V, B, blk, seed, density=0.004, hold=(5, 300)):
 def polysynth():
     """One voice of cpp/commandline/maximilian_examples/15.polysynth/main.cpp:54-70: two pulse VCOs (the second detuned by a
     sinebuf LFO) summed into a lores VCF whose cutoff follows pitch + LFO, multiplied by the ADSR AFTER the filter."""
-    d = PatchDef()
-    one = d.K(1.0)
-    d.stage("env_adsr", one, d.IN("trigger"), d.P("attack"), d.P("decay"), d.P("sustain"), d.P("release"), d.K(1.0), dst=R(0))   # ADSRout
-    d.stage("osc", d.K(0.2), kind="sinebuf", dst=R(1))                                   # LFO1out
-    d.stage("osc", d.P("f1"), d.K(0.6), kind="pulse", dst=R(2))                          # VCO1out = pulse(55*pitch, 0.6)
-    d.stage("add", d.P("f2"), R(1), dst=R(3))                                             # (110*pitch) + LFO1out
-    d.stage("osc", R(3), d.K(0.2), kind="pulse", dst=R(3))                               # VCO2out
-    d.stage("add", R(2), R(3), dst=R(4))
-    d.stage("mul", R(4), d.K(0.5), dst=R(4))                                              # (VCO1out + VCO2out) * 0.5
-    d.stage("add", d.P("pitch"), R(1), dst=R(5))
-    d.stage("mul", R(5), d.K(1000.0), dst=R(5))
-    d.stage("add", d.K(250.0), R(5), dst=R(5))                                            # 250 + ((pitch + LFO1out) * 1000)
-    d.stage("filter", R(4), R(5), d.K(10.0), kind="lores", dst=R(6))                     # VCFout
-    d.stage("mul", R(6), R(0), dst=R(7))
-    d.stage("div", R(7), d.K(6.0), dst=R(7))                                              # VCFout * ADSRout / 6
-    d.stage("out", R(7))
-    d.stage("mix_stereo", R(7), d.P("pan"))
+    d = W.polysynth_patch()
 
     def params(V, seed):
-        p = W.voice_params(V, seed=seed)
-        att, dec, rel = W.env_coeffs(p)
-        pitch = 1.0 + (np.arange(V) % 6)
-        return dict(attack=att, decay=dec, sustain=p["env_sustain"], release=rel, f1=55.0 * pitch, f2=110.0 * pitch, pitch=pitch, pan=p["pan"])
+        return W.polysynth_params(V, seed)
 
     def inputs(V, B, blk, seed):
         return dict(trigger=_trig_stream(V, B, blk, seed))
