@@ -185,15 +185,7 @@ __global__ void __launch_bounds__(kPatchThreads) patch_kernel(const PatchArgs a)
             }
             if (g.dst >= 0) reg[g.dst] = y;
         }
-        if (a.partials) {
-            // per-warp sum in a fixed xor tree: deterministic; the second kernel adds the warps in order
-#pragma unroll
-            for (int m = 16; m >= 1; m >>= 1) { ml += __shfl_xor_sync(0xffffffffu, ml, m); mr += __shfl_xor_sync(0xffffffffu, mr, m); }
-            if (lane == 0) {
-                a.partials[((size_t)t * 2 + 0) * (size_t)a.W + (size_t)gwarp] = ml;
-                a.partials[((size_t)t * 2 + 1) * (size_t)a.W + (size_t)gwarp] = mr;
-            }
-        }
+        if (a.partials) mix_warp_store(ml, mr, lane, a.partials, (size_t)t, (size_t)a.W, (size_t)gwarp);      // the second kernel adds the warps in order
     }
     if (live) for (int i = 0; i < a.n_state; ++i) a.state[(size_t)i * V + (size_t)v] = st[i];
 }

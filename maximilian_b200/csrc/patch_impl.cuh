@@ -204,6 +204,17 @@ __device__ __forceinline__ void mix_stereo_acc(double& ml, double& mr, const dou
     mr += in * sqrt(x);
 }
 
+// The warp's two bus sums of one sample in five exchange steps instead of ten: in the first step the lower half-warp keeps the left
+// sums and hands its right sums to the upper half (and the other way round), then each half reduces ONE value. Fixed tree, so the
+// result is the same from run to run and in both ways a patch runs; lanes 0 and 16 end up with the left / right sum.
+__device__ __forceinline__ void mix_warp_store(double ml, double mr, const int lane, double* __restrict__ partials, const size_t t, const size_t W, const size_t gwarp) {
+    const bool up = (lane & 16) != 0;
+    double v = (up ? mr : ml) + __shfl_xor_sync(0xffffffffu, up ? ml : mr, 16);
+#pragma unroll
+    for (int m = 8; m >= 1; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
+    if ((lane & 15) == 0) partials[(t * 2 + (up ? 1 : 0)) * W + gwarp] = v;
+}
+
 // number of state words of a stage (the order documented with the ops in maxib200.h)
 __host__ __device__ inline int patch_state_slots(const int op) {
     switch (op) {

@@ -13,6 +13,7 @@ import pytest
 import golden_checks as G
 import patch_cases as PC
 from maximilian_b200 import capi
+from maximilian_b200 import workloads as W
 
 pytestmark = pytest.mark.gpu
 
@@ -128,6 +129,33 @@ def test_patch_golden(port, case, mode):
         o, m = p.process(B, ins, want_mix=True)
         _cmp(o, gl[name + "/out"][blk], exact, f"{name} blk{blk}")
         np.testing.assert_allclose(m, gl[name + "/mix"][blk], rtol=1e-9, atol=1e-12)
+
+
+def test_full_size_polysynth_256k_voices_vs_oracle_slices(port):
+    """The bench's patch leg at its own size (262 144 voices x 1024 frames, trigger bytes, the generated kernel), two blocks: a
+    1536-voice slice -- first, middle and last warps -- against the oracle run on those voices (outputs 1e-9, envelope flags / hold
+    counts exact), the bus against the pan-weighted sum of the GPU's own output, and the interpreter on the slice bit for bit."""
+    V, B = 262144, 1024
+    _tables(port)
+    d = W.polysynth_patch("u8")
+    prm = W.polysynth_params(V, seed=31); pat = W.note_pattern(V, seed=31)
+    sl = np.concatenate([np.arange(0, 512), np.arange(V // 2 - 256, V // 2 + 256), np.arange(V - 512, V)])
+    g = capi.Patch(d, V, max_frames=B, mode="fused")
+    o = port.Patch(d, sl.size, kind="port"); gi = capi.Patch(d, sl.size, max_frames=B, mode="interpret")
+    for k, v in prm.items():
+        g.set(k, v); o.set(k, v[sl]); gi.set(k, v[sl])
+    pan = np.clip(prm["pan"], 0.0, 1.0)
+    for blk in range(2):
+        tr = W.note_triggers(pat, B, blk)
+        og, mg = g.process(B, {"trigger": tr}, want_mix=True)
+        oo, _ = o.process(B, {"trigger": tr[:, sl].astype(np.float64)})
+        oi, _ = gi.process(B, {"trigger": np.ascontiguousarray(tr[:, sl])})
+        np.testing.assert_allclose(og[:, sl], oo, rtol=1e-9, atol=1e-12)
+        assert np.array_equal(og[:, sl], oi)
+        bus = np.stack([og @ np.sqrt(1.0 - pan), og @ np.sqrt(pan)], axis=1)
+        np.testing.assert_allclose(mg, bus, rtol=1e-9, atol=1e-9)
+    for slot in (2, 3):                                        # holdcount, flags of the ADSR (stage 0)
+        assert np.array_equal(g.get_state(0, slot)[sl], o.get_state(0, slot))
 
 
 def test_patch_rejects_bad_programs():
