@@ -1004,12 +1004,12 @@ def spectral_extra_leg(E, args, steps, warmup):
         barrier(E)
         return max_over_ranks(E, e0.elapsed_time(e1)) / n_steps
 
-    def entry(ms, bytes_per_frame, kernel, what):
+    def entry(ms, bytes_per_frame, kernel, what, traffic_key=None):
         frames = C * H
         ach = bytes_per_frame * frames / (ms * 1e-3) / 1e9
         return {"value": world * frames / (ms * 1e-3), "unit": "frames/s", "ms_per_step": ms, "steps": steps,
-                "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None, "peak_source": peak_src,
-                             "kernel": kernel, "algorithmic_bytes_per_frame": bytes_per_frame}, "what": what}
+                "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, **load_traffic(traffic_key), "peak_source": peak_src,
+                             "kernel": kernel, "algorithmic_bytes_per_frame": bytes_per_frame, "algorithmic_bytes_per_launch": bytes_per_frame * frames}, "what": what}
 
     # (1) analysis with the whole spectrum leaving the chip: magnitudes + phases (atan2f per bin)
     st = capi.Stft(C, n, hop, ctx=E.ctx)
@@ -1021,7 +1021,7 @@ def spectral_extra_leg(E, args, steps, warmup):
     def resyn():
         capi.check(L.mxb_istft_process(ist.h, C_.c_void_p(mags.data_ptr()), C_.c_void_p(phases.data_ptr()), H, C_.c_void_p(y.data_ptr()), capi.MEM_DEVICE, sp), "mxb_istft_process")
     ms = timed(resyn, steps)
-    out["resynthesis"] = entry(ms, 2 * bins * 4 + hop * 4, "istft_frame_kernel + istft_ola_kernel", "maxiIFFT::process(SPECTRUM): polToCart, inverse transform, window, overlap-add")
+    out["resynthesis"] = entry(ms, 2 * bins * 4 + hop * 4, "istft1024_kernel", "maxiIFFT::process(SPECTRUM): polToCart, inverse transform, window, overlap-add", "istft")
     del ist, y, phases
     # (3) analysis with the octave analyser and Bark loudness fused in (magnitudes written too)
     oc = capi.Octave(C, float(SR), bins, 3, ctx=E.ctx)
