@@ -62,7 +62,7 @@ constexpr int kMixDoubles = 2 * kMixTT * 33;
 constexpr int kFastMinSize = 2 * kDlT;
 constexpr unsigned kFull = 0xffffffffu;
 enum { DL_OUT_NONE = 0, DL_OUT_F64 = 1, DL_OUT_F32 = 2 };
-static_assert(kDlT == kMixTT, "one staged window = one mix tile");
+static_assert(kDlT <= kMixTT, "one staged window fits one mix tile");
 
 __device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc) {
     const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -287,6 +287,7 @@ __global__ void __launch_bounds__(DelayShape<MIX>::kThreads) delay_bank_kernel(c
         const bool tight = nchunks - ahead < 8;
         auto chunk_of = [&](int kk) { return (int)(((long long)(base0 >> kDlShift) + kk) % nchunks); };
 #ifdef MXB_DL_NO_TMA
+        static_assert(kDlChunk == 16, "the no-copy-engine A/B path is written for 16-slot windows");
         // A/B build (scripts/build_variant_one.sh): no copy engine at all -- the window image by 8 coalesced 16-byte cp.async per lane,
         // cp.async groups for completion. Measured within 0.5 % of the copy-engine pipeline (profiles/bench_lines/r02_k2_variants.txt).
         const int nd = nlive * kDlChunk;
@@ -310,7 +311,7 @@ __global__ void __launch_bounds__(DelayShape<MIX>::kThreads) delay_bank_kernel(c
             }
         }
 #endif
-        const int swz = lane & (kDlChunk - 1);
+        const int swz = dl_swz((size_t)lane);
         int sidx = 0, nidx = ahead % kDlStages;                            // stage of window k / of window k + ahead
         unsigned par = 0;                                                   // parity of stage sidx's barrier: flips every kDlStages windows
         int nchunk = chunk_of(ahead);
@@ -378,7 +379,7 @@ __global__ void __launch_bounds__(DelayShape<MIX>::kThreads) delay_bank_kernel(c
                 if (!f_i) continue;
                 int r = b_i + sl;
                 if (r >= s_i) r -= s_i;
-                cp_async8(buf + i * kDlRow + (sl ^ (i & (kDlT - 1))), d.ring + dl_slot(V, (size_t)(v0 + i), r));
+                cp_async8(buf + i * kDlRow + (sl ^ dl_swz((size_t)i)), d.ring + dl_slot(V, (size_t)(v0 + i), r));
             }
         };
         issue_loads(wsm, base);
@@ -393,7 +394,7 @@ __global__ void __launch_bounds__(DelayShape<MIX>::kThreads) delay_bank_kernel(c
             cp_async_commit();
             cp_async_wait1();
             __syncwarp();
-            dl_window<OSC, FILT, ENV, false, OUTMODE, MIX>(s, buf + lane * kDlRow, tn, t0, a, d, V, (size_t)vv, lane, gwarp, mixtile, lane & (kDlT - 1));
+            dl_window<OSC, FILT, ENV, false, OUTMODE, MIX>(s, buf + lane * kDlRow, tn, t0, a, d, V, (size_t)vv, lane, gwarp, mixtile, dl_swz((size_t)lane));
             __syncwarp();
 #pragma unroll 4
             for (int q = 0; q < 32 / kDlVoicesPerReq; ++q) {
@@ -404,7 +405,7 @@ __global__ void __launch_bounds__(DelayShape<MIX>::kThreads) delay_bank_kernel(c
                 if (f_i && sl < tn) {
                     int r = b_i + sl;
                     if (r >= s_i) r -= s_i;
-                    d.ring[dl_slot(V, (size_t)(v0 + i), r)] = buf[i * kDlRow + (sl ^ (i & (kDlT - 1)))];
+                    d.ring[dl_slot(V, (size_t)(v0 + i), r)] = buf[i * kDlRow + (sl ^ dl_swz((size_t)i))];
                 }
             }
             __syncwarp();

@@ -5,8 +5,15 @@
 
 namespace mxb {
 
-constexpr int kDlShift = 4;
+#ifndef MXB_DL_SHIFT
+#define MXB_DL_SHIFT 4
+#endif
+constexpr int kDlShift = MXB_DL_SHIFT;      // 4, or 3 for an A/B build with 8-slot chunks (half the staging per warp)
 constexpr int kDlChunk = 1 << kDlShift;     // ring slots per chunk = time steps per staged window (16)
+static_assert(kDlShift == 3 || kDlShift == 4, "chunks of 8 or 16 slots");
+// the swizzle of voice v's chunk: v % 16 for 16-slot chunks; (v / 2) % 8 for 8-slot chunks (rows of 64 bytes: two lanes share a
+// 128-byte bank row, the 8 even lanes of a half-warp must differ in the low half of it and the 8 odd ones in the high half)
+__host__ __device__ inline int dl_swz(size_t v) { return (int)((v >> (4 - kDlShift)) & (size_t)(kDlChunk - 1)); }
 
 // Ring storage is chunk-interleaved and swizzled: slot r of voice v lives at ((r / 16) * V + v) * 16 + ((r % 16) ^ (v % 16)).
 // A voice's 16-slot chunk is 128 contiguous bytes (4 full sectors whatever its phase), and voices whose
@@ -16,7 +23,7 @@ constexpr int kDlChunk = 1 << kDlShift;     // ring slots per chunk = time steps
 // memory usable as it is: lane v reads slot j of its row at position j ^ (v % 16), so the 16 lanes of a half-warp hit 16
 // different 8-byte bank pairs -- conflict-free without padding, which a bulk copy could not produce.
 __host__ __device__ inline size_t dl_slot(size_t V, size_t v, int r) {
-    return (((size_t)(r >> kDlShift)) * V + v) * kDlChunk + (size_t)((r ^ (int)v) & (kDlChunk - 1));
+    return (((size_t)(r >> kDlShift)) * V + v) * kDlChunk + (size_t)((r ^ dl_swz(v)) & (kDlChunk - 1));
 }
 inline size_t dl_ring_doubles(size_t V, int taps) { return (size_t)((taps + kDlChunk - 1) / kDlChunk) * kDlChunk * V; }
 
