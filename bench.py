@@ -792,9 +792,9 @@ def mfcc_leg(E, args, steps, warmup):
 
 # ------------------------------------------------------------------------------------------------ voice patch
 
-PATCH_WL = dict(voices=1 << 18, bytes_per=8.0 + 1.0 + (12 * 16 + 8 * 8) / BLOCK,
+PATCH_WL = dict(voices=1 << 18, bytes_per=8.0 + 1.0 / 8 + (12 * 16 + 8 * 8) / BLOCK,
                 desc="15.polysynth voice patch x 256Ki voices: 2 pulse VCOs (one detuned by a sinebuf LFO) -> lores VCF with per-sample cutoff "
-                     "(coefficients designed every sample: cos, pow, sqrt) -> x ADSR (per-sample trigger bytes), fp64 out[1024][V] materialised + stereo bus")
+                     "(coefficients designed every sample: cos, pow, sqrt) -> x ADSR (per-sample trigger, one bit per voice-sample), fp64 out[1024][V] materialised + stereo bus")
 
 
 def _tables():
@@ -865,13 +865,16 @@ def patch_leg(E, args, steps, warmup):
     wl = PATCH_WL
     V = int(os.environ.get("MXB_BENCH_PATCH_VOICES", wl["voices"]))
     capi.set_tables(*_tables(), ctx=E.ctx)
-    d = W.polysynth_patch("u8")
+    assert V % 32 == 0
+    d = W.polysynth_patch("bits")
     prm = W.polysynth_params(V, seed=W.SEED + rank)
     pat = tuple(torch.from_numpy(a).to(dev) for a in W.note_pattern(V, seed=W.SEED + rank))
+    weights = (torch.ones(32, dtype=torch.int64, device=dev) << torch.arange(32, dtype=torch.int64, device=dev))
 
-    def triggers(block_index):          # the same formula as workloads.note_triggers, evaluated on the device for 256 Ki voices
-        t = (torch.arange(BLOCK, dtype=torch.int64, device=dev) + BLOCK * block_index)[:, None]
-        return (((t + pat[1][None, :]) % pat[0][None, :]) < pat[2][None, :]).to(torch.uint8).contiguous()
+    def triggers(block_index):          # the same formula as workloads.note_triggers, evaluated on the device for 256 Ki voices, then
+        t = (torch.arange(BLOCK, dtype=torch.int64, device=dev) + BLOCK * block_index)[:, None]      # packed: voice v = bit v % 32 of word v / 32
+        on = (((t + pat[1][None, :]) % pat[0][None, :]) < pat[2][None, :]).to(torch.int64)
+        return (on.view(BLOCK, V // 32, 32) * weights).sum(-1).to(torch.int32).contiguous()
     trig = [triggers(b) for b in range(2)]
     out = torch.empty((BLOCK, V), dtype=torch.float64, device=dev)
     mix = [torch.zeros((BLOCK, 2), dtype=torch.float64, device=dev) for _ in range(2)]
@@ -944,7 +947,7 @@ def patch_leg(E, args, steps, warmup):
         peak, peak_src = load_peaks()
         achieved = wl["bytes_per"] * V * BLOCK / (f["ms_local"] * 1e-3) / 1e9
         res["config"] = {"workload": wl["desc"], "voices_per_gpu": V, "block": BLOCK, "sample_rate": SR, "parallelism": f"voices sharded x{world}", "collective": "none",
-                         "l2": "no flush needed: each step reads %.2f GB of trigger bytes and writes %.1f GB" % (V * BLOCK / 1e9, V * BLOCK * 8 / 1e9)}
+                         "l2": "no flush needed: each step writes %.1f GB (and reads %.0f MB of packed trigger bits)" % (V * BLOCK * 8 / 1e9, V * BLOCK / 8e6)}
         res["roofline"] = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, **load_traffic("patch"),
                            "algorithmic_bytes_per_launch": wl["bytes_per"] * V * BLOCK, "algorithmic_bytes_per_voice_sample": wl["bytes_per"],
                            "peak_source": peak_src, "kernel": "mxb_fused_patch (generated per patch, NVRTC)", "launch_ms_avg": f["ms_local"],
@@ -954,9 +957,9 @@ def patch_leg(E, args, steps, warmup):
                               "steps": res_modes["interpret"]["steps"], "fused_speedup": f["value"] / res_modes["interpret"]["value"],
                               "what": "the same patch on the interpreting kernel (MXB_PATCH_INTERPRET): identical results bit for bit"}
         res["compile_seconds"] = f["create_seconds"]
-        res["e2e"] = {"value": world * V * BLOCK * e2e_steps / dt, "unit": "samples/s", "h2d_bytes_per_step": int(trig_host[0].numel()),
+        res["e2e"] = {"value": world * V * BLOCK * e2e_steps / dt, "unit": "samples/s", "h2d_bytes_per_step": int(trig_host[0].numel() * trig_host[0].element_size()),
                       "d2h_bytes_per_step": int(mix_host[0].numel() * 8), "steps": e2e_steps, "frac_of_resident": world * V * BLOCK * e2e_steps / dt / f["value"],
-                      "what": "per step: trigger bytes [1024][V] from pinned host memory (copy stream, double-buffered), mxb_patch_process(MXB_MEM_DEVICE) "
+                      "what": "per step: packed trigger bits [1024][V/32] words from pinned host memory (copy stream, double-buffered), mxb_patch_process(MXB_MEM_DEVICE) "
                               "of the fused patch, stereo bus back to pinned host memory; voice signals materialised on the device"}
         res["clocks"] = E.sampler.summary(t_wall[0], t_wall[1])
     del patches, pt, out, trig, trig_dev

@@ -262,6 +262,7 @@ int64_t mxb_bank_launch_count(const mxb_bank* bank);
 #define MXB_INPUT(m) (0x300 + (m))   /* per-sample input stream m of mxb_patch_process: [n_frames][voices] doubles (or bytes, input_types), 0..7 */
 #define MXB_IN_F64 0                 /* input stream element types (mxb_patch_desc.input_types) */
 #define MXB_IN_U8 1                  /* unsigned bytes, read as (double)byte: triggers and gates (maxiEnv::trigger is an int) at 1 B / voice-sample */
+#define MXB_IN_BITS 2                /* one bit per voice-sample, read as 0.0 / 1.0: uint32 words [n_frames][(voices + 31) / 32], voice v = bit v % 32 of word v / 32 */
 /* oscillator kinds of MXB_OP_OSC beyond MXB_OSC_*: the table oscillators (tables: mxb_ctx_set_tables) */
 enum { MXB_OSC_SINEBUF = 9 /* maxiOsc::sinebuf src/maximilian.cpp:266-274 */, MXB_OSC_SINEBUF4 = 10 /* :237-264 */, MXB_OSC_SAWN = 11 /* :342-359 */ };
 /* filter kinds of MXB_OP_FILTER beyond MXB_FILT_LORES / HIRES */
@@ -310,7 +311,7 @@ int32_t mxb_patch_set_param(mxb_patch* patch, int32_t j, const double* values, i
 int32_t mxb_patch_set_state(mxb_patch* patch, int32_t stage, int32_t slot, const double* values, int32_t mem);
 int32_t mxb_patch_get_state(mxb_patch* patch, int32_t stage, int32_t slot, double* values, int32_t mem);
 int32_t mxb_patch_get_ring(mxb_patch* patch, int32_t stage, int32_t voice, double* dst, int32_t n, int32_t mem);
-/* inputs: n_inputs pointers to [n_frames][voices] of each stream's element type; out: [n_frames][voices] or NULL; mix: [n_frames][2] or NULL */
+/* inputs: n_inputs pointers to [n_frames][voices] of each stream's element type (MXB_IN_BITS: [n_frames][(voices + 31) / 32] words); out: [n_frames][voices] or NULL; mix: [n_frames][2] or NULL */
 int32_t mxb_patch_process(mxb_patch* patch, int32_t n_frames, const void* const* inputs, double* out, double* mix, int32_t mem, void* stream);
 int64_t mxb_patch_launch_count(const mxb_patch* patch);
 #define MXB_PATCH_INTERPRET 0

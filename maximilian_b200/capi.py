@@ -577,6 +577,16 @@ def set_tables(sine514, transition1001, sine_before, ctx=None, device=0, sample_
 PATCH_INTERPRET, PATCH_FUSED = 0, 1
 
 
+def pack_bits(x):
+    """[n][V] of 0 / 1 -> uint32 [n][(V + 31) / 32] (MXB_IN_BITS: voice v = bit v % 32 of word v / 32)"""
+    x = np.asarray(x) != 0
+    n, V = x.shape
+    W = (V + 31) // 32
+    pad = np.zeros((n, W * 32), dtype=np.uint8)
+    pad[:, :V] = x
+    return np.ascontiguousarray(np.packbits(pad, axis=1, bitorder="little")).view(np.uint32).reshape(n, W)
+
+
 def _patch_desc(defn, voices, max_frames, delay_taps):
     """mxb_patch_desc of a PatchDef; the second value keeps the ctypes arrays it points into alive."""
     st = (Stage * len(defn.stages))()
@@ -587,7 +597,7 @@ def _patch_desc(defn, voices, max_frames, delay_taps):
     consts = (C.c_double * max(1, len(defn.consts)))(*defn.consts)
     eg = defn.eg or ([0.0], [], [], False, False)
     lv = (C.c_double * max(1, len(eg[0])))(*eg[0]); tm = (C.c_double * max(1, len(eg[1])))(*eg[1]); cv = (C.c_double * max(1, len(eg[2])))(*eg[2])
-    ty = (C.c_int32 * max(1, len(defn.inputs)))(*[1 if defn.input_types.get(n) == "u8" else 0 for n in defn.inputs])
+    ty = (C.c_int32 * max(1, len(defn.inputs)))(*[{"u8": 1, "bits": 2}.get(defn.input_types.get(n), 0) for n in defn.inputs])
     d = PatchDesc(int(voices), len(defn.stages), len(defn.params), len(defn.consts), len(defn.inputs), int(max_frames), int(delay_taps),
                   len(eg[1]), int(eg[3]), int(eg[4]), st, consts, lv, tm, cv, ty)
     return d, (st, consts, lv, tm, cv, ty)
@@ -667,9 +677,16 @@ class Patch:
     def process(self, nframes, inputs=None, want_out=True, want_mix=False):
         """inputs: dict name -> float64 [nframes][V]. Returns (out[nframes][V] | None, mix[nframes][2] | None)."""
         inputs = inputs or {}
-        arrs = [np.ascontiguousarray(inputs[n], dtype=np.uint8 if self.defn.input_types.get(n) == "u8" else np.float64) for n in self.defn.inputs]
-        for a in arrs:
-            assert a.shape == (nframes, self.V)
+        arrs = []
+        for n in self.defn.inputs:
+            ty = self.defn.input_types.get(n)
+            if ty == "bits":                 # [nframes][V] of 0 / 1 -> uint32 words [nframes][(V + 31) / 32], voice v = bit v % 32 of word v / 32
+                a = pack_bits(inputs[n])
+                assert a.shape == (nframes, (self.V + 31) // 32)
+            else:
+                a = np.ascontiguousarray(inputs[n], dtype=np.uint8 if ty == "u8" else np.float64)
+                assert a.shape == (nframes, self.V)
+            arrs.append(a)
         ptrs = (C.c_void_p * max(1, len(arrs)))(*[a.ctypes.data for a in arrs])
         out = np.empty((nframes, self.V), dtype=np.float64) if want_out else None
         mix = np.empty((nframes, 2), dtype=np.float64) if want_mix else None

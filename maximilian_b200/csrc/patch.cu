@@ -61,7 +61,7 @@ __global__ void __launch_bounds__(kPatchThreads) patch_kernel(const PatchArgs a)
                 case 0: return reg[k];
                 case 1: return par[k];
                 case 2: return s_const[k];
-                default: return live ? patch_input(a, k, (size_t)t * V + vv) : 0.0;
+                default: return live ? patch_input(a, k, (size_t)t, vv, V) : 0.0;
             }
         };
         for (int si = 0; si < a.n_stages; ++si) {
@@ -250,7 +250,7 @@ int32_t mxb_patch_create(mxb_ctx* ctx, const mxb_patch_desc* d, mxb_patch** out)
     MXB_REQUIRE(d->delay_taps >= 0, MXB_ERR_INVALID, "mxb_patch_create: delay_taps %d", d->delay_taps);
     MXB_REQUIRE(d->eg_stages >= 0 && d->eg_stages <= kMaxEg, MXB_ERR_INVALID, "mxb_patch_create: eg_stages %d (0..%d)", d->eg_stages, kMaxEg);
     for (int i = 0; d->input_types && i < d->n_inputs; ++i)
-        MXB_REQUIRE(d->input_types[i] == MXB_IN_F64 || d->input_types[i] == MXB_IN_U8, MXB_ERR_INVALID, "mxb_patch_create: input_types[%d] = %d", i, d->input_types[i]);
+        MXB_REQUIRE(d->input_types[i] >= MXB_IN_F64 && d->input_types[i] <= MXB_IN_BITS, MXB_ERR_INVALID, "mxb_patch_create: input_types[%d] = %d", i, d->input_types[i]);
     int n_state = 0, n_rings = 0;
     bool tables = false, eg = false;
     for (int i = 0; i < d->n_stages; ++i) {
@@ -421,7 +421,7 @@ int32_t mxb_patch_codegen(const mxb_patch_desc* d, char* buf, int64_t cap, int64
     }
     int types[kMaxInputs] = {};
     for (int i = 0; d->input_types && i < d->n_inputs; ++i) {
-        MXB_REQUIRE(d->input_types[i] == MXB_IN_F64 || d->input_types[i] == MXB_IN_U8, MXB_ERR_INVALID, "mxb_patch_codegen: input_types[%d] = %d", i, d->input_types[i]);
+        MXB_REQUIRE(d->input_types[i] >= MXB_IN_F64 && d->input_types[i] <= MXB_IN_BITS, MXB_ERR_INVALID, "mxb_patch_codegen: input_types[%d] = %d", i, d->input_types[i]);
         types[i] = d->input_types[i];
     }
     const std::string src = patch_generate_source(d->stages, d->n_stages, d->n_params, d->consts, d->n_consts, d->n_inputs, types);
@@ -452,9 +452,9 @@ int32_t mxb_patch_process(mxb_patch* p, int32_t n_frames, const void* const* inp
     double* d_out = out; double* d_mix = mix;
     for (int i = 0; i < p->n_inputs; ++i) {
         a.inputs[i] = inputs[i];
-        a.in_u8[i] = p->in_type[i] == MXB_IN_U8;
+        a.in_kind[i] = (unsigned char)p->in_type[i];
         if (mem == MXB_MEM_HOST) {
-            const size_t nb = (a.in_u8[i] ? 1 : sizeof(double)) * (size_t)n_frames * V;
+            const size_t nb = patch_input_bytes(p->in_type[i], (size_t)n_frames, V);
             if (nb > p->in_stage_len[i]) {
                 MXB_CUDA(cudaStreamSynchronize(s));
                 cudaFree(p->in_stage[i]); p->in_stage[i] = nullptr; p->in_stage_len[i] = 0;

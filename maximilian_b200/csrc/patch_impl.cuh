@@ -25,8 +25,8 @@ struct PatchArgs {
     const double* consts;            // device, kMaxConsts                              (interpreter only: generated kernels hold them as literals)
     const double* params;            // [n_params][V]
     double* state;                   // [n_state][V]
-    const void* inputs[kMaxInputs];  // [n_frames][V] each: doubles, or bytes where in_u8[k]
-    unsigned char in_u8[kMaxInputs];
+    const void* inputs[kMaxInputs];  // [n_frames][V] each: doubles, bytes or packed bits (in_kind[k] = MXB_IN_*)
+    unsigned char in_kind[kMaxInputs];
     double* out;                     // [n_frames][V] or NULL
     double* partials;                // [n_frames][2][W] or NULL
     double* rings;                   // [n_rings][taps][V]
@@ -232,8 +232,13 @@ __host__ __device__ inline int patch_state_slots(const int op) {
 }
 
 // sample t of input stream k for voice v
-__device__ __forceinline__ double patch_input(const PatchArgs& a, const int k, const size_t idx) {
-    return a.in_u8[k] ? (double)((const unsigned char*)a.inputs[k])[idx] : ((const double*)a.inputs[k])[idx];
+__device__ __forceinline__ double patch_input(const PatchArgs& a, const int k, const size_t t, const size_t v, const size_t V) {
+    if (a.in_kind[k] == MXB_IN_BITS) return (double)((((const unsigned*)a.inputs[k])[t * ((V + 31) >> 5) + (v >> 5)] >> (v & 31)) & 1u);   // one word per warp
+    return a.in_kind[k] == MXB_IN_U8 ? (double)((const unsigned char*)a.inputs[k])[t * V + v] : ((const double*)a.inputs[k])[t * V + v];
+}
+// bytes of one block of an input stream
+__host__ __device__ inline size_t patch_input_bytes(const int kind, const size_t n_frames, const size_t V) {
+    return kind == MXB_IN_BITS ? n_frames * ((V + 31) >> 5) * 4 : n_frames * V * (kind == MXB_IN_U8 ? 1 : 8);
 }
 
 }  // namespace mxb

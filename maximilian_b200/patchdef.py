@@ -28,7 +28,7 @@ class PatchDef:
         self.consts = []
         self.params = []          # names, index = parameter slot
         self.inputs = []          # names, index = input stream
-        self.input_types = {}     # name -> "u8" for byte streams (triggers / gates); doubles otherwise
+        self.input_types = {}     # name -> "u8" | "bits" for byte / packed-bit streams (triggers, gates); doubles otherwise
         self.eg = None            # (levels, times, curves, loop, retrigger)
 
     def K(self, value):
@@ -50,12 +50,13 @@ class PatchDef:
         return 0x100 + self.params.index(name)
 
     def IN(self, name, dtype="f64"):
-        """per-sample input stream operand; dtype "u8": the caller passes unsigned bytes (read as doubles by the stages)"""
+        """per-sample input stream operand; dtype "u8": the caller passes unsigned bytes, "bits": one bit per voice-sample packed into
+        uint32 words (both read as doubles by the stages)"""
         if name not in self.inputs:
             self.inputs.append(name)
             assert len(self.inputs) <= 8
-            if dtype == "u8":
-                self.input_types[name] = "u8"
+            if dtype in ("u8", "bits"):
+                self.input_types[name] = dtype
         return 0x300 + self.inputs.index(name)
 
     def stage(self, op, *src, kind=0, dst=NONE):

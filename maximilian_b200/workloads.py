@@ -101,7 +101,8 @@ def configure_bank(bank, filt, p, env=False, delay=False, sample_rate=SAMPLE_RAT
 def polysynth_patch(trigger_dtype="f64"):
     """One voice of cpp/commandline/maximilian_examples/15.polysynth/main.cpp:54-70 as a PatchDef: two pulse VCOs (the second
     detuned by a sinebuf LFO) summed into a lores VCF whose cutoff follows pitch + LFO, multiplied by the ADSR AFTER the filter.
-    trigger_dtype "u8": the per-sample trigger stream arrives as bytes (maxiEnv::trigger is an int)."""
+    trigger_dtype "u8" / "bits": the per-sample trigger stream arrives as bytes / as one bit per voice-sample (maxiEnv::trigger is an
+    int that a patch sets to 0 or 1)."""
     from .patchdef import PatchDef, R
     d = PatchDef()
     one = d.K(1.0)

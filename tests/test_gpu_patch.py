@@ -158,6 +158,28 @@ def test_full_size_polysynth_256k_voices_vs_oracle_slices(port):
         assert np.array_equal(g.get_state(0, slot)[sl], o.get_state(0, slot))
 
 
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("V", [96, 1000, 4099])
+def test_trigger_streams_as_bytes_and_as_packed_bits(mode, V):
+    """the three element types of an input stream (doubles, bytes, one bit per voice-sample) give the same bits out; voice counts that
+    are not multiples of 32 end in a partly used word"""
+    B = 160
+    prm = W.polysynth_params(V, seed=9); pat = W.note_pattern(V, seed=9)
+    ps = {ty: capi.Patch(W.polysynth_patch(ty), V, max_frames=B, mode=mode) for ty in ("f64", "u8", "bits")}
+    for p in ps.values():
+        for k, v in prm.items():
+            p.set(k, v)
+    for blk in range(2):
+        tr = W.note_triggers(pat, B, blk)
+        ref = None
+        for ty, p in ps.items():
+            o, m = p.process(B, {"trigger": tr.astype(np.float64) if ty == "f64" else tr}, want_mix=True)
+            if ref is None:
+                ref = (o, m)
+            else:
+                assert np.array_equal(o, ref[0]) and np.array_equal(m, ref[1]), (ty, blk)
+
+
 def test_patch_rejects_bad_programs():
     from maximilian_b200.patchdef import PatchDef, R
     d = PatchDef(); d.stage("osc", d.K(100.0), kind="sinebuf", dst=R(0)); d.stage("out", R(0))

@@ -2,6 +2,8 @@
 and compiled for sm_100a by NVRTC exactly as a fused patch's first launch does, only the loading step is left out."""
 import re
 
+import numpy as np
+
 import pytest
 
 import patch_cases as PC
@@ -30,6 +32,18 @@ def test_block_constant_arguments_are_designed_once():
     head, loop = src.split("for (int t = 0", 1)
     assert "filt_design<FILT_T_LORES>(f1, p1, c0, sr);" in head and "const double inc0" in head
     assert "filt_design<FILT_T_LORES>(f2, r0, c0, sr);" in loop
+
+
+def test_input_element_types_are_part_of_the_program():
+    from maximilian_b200 import workloads as W
+    srcs = {ty: capi.patch_codegen(W.polysynth_patch(ty), compile=True) for ty in ("f64", "u8", "bits")}
+    assert "(const double*)a.inputs[0]" in srcs["f64"] and "(const unsigned char*)a.inputs[0]" in srcs["u8"] and "(const unsigned*)a.inputs[0]" in srcs["bits"]
+    assert len({*srcs.values()}) == 3
+    x = (np.arange(3 * 70).reshape(3, 70) % 3 == 0)
+    w = capi.pack_bits(x)
+    assert w.shape == (3, 3) and w.dtype == np.uint32
+    for v in range(70):
+        assert np.array_equal((w[:, v // 32] >> np.uint32(v % 32)) & 1, x[:, v].astype(np.uint32))
 
 
 def test_a_program_the_generator_rejects_is_an_error_not_a_crash():
