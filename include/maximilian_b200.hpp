@@ -123,7 +123,7 @@ struct maxiBus { maxiVoices* voices = nullptr; };
  * shape oscillator -> [maxiEnv] -> [filter] -> [maxiDelayline] -> maxiMix::stereo / per-voice output with block-constant arguments
  * runs on the fused bank kernels (mxb_bank, the HBM-roofline path); any other graph -- sums of oscillators, an LFO on a cutoff,
  * the envelope applied after the filter (maximilian_examples/15.polysynth/main.cpp:54-70), per-sample triggers -- runs on the patch
- * interpreter (mxb_patch). The patch must be the same on every block (the reference's play() is, too). */
+ * voice patch (mxb_patch: a kernel generated and compiled for the recorded graph, or the interpreting kernel). The patch must be the same on every block (the reference's play() is, too). */
 class maxiVoices {
 public:
     explicit maxiVoices(int voices, int device = 0) : V_(voices), device_(device) {}
@@ -163,7 +163,7 @@ public:
 
     /* state read-back of a fused chain (checkpointing / tests): MXB_P_PHASE, MXB_S_* */
     std::vector<double> state(int id) {
-        if (!bank_) throw maxiError(MXB_ERR_STATE, "maxiVoices::state: the patch runs on the interpreter (use patchHandle())");
+        if (!bank_) throw maxiError(MXB_ERR_STATE, "maxiVoices::state: the graph runs as a voice patch (use patchHandle())");
         std::vector<double> v((size_t)V_);
         maxib200_detail::check(mxb_bank_get_state(bank_, id, v.data(), MXB_MEM_HOST), "mxb_bank_get_state");
         return v;

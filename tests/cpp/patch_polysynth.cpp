@@ -3,7 +3,8 @@
 // the per-voice arrays become per-voice vectors, and the per-SAMPLE control code of the original play() (the metronome that writes
 // ADSR[voice].trigger) runs once per block over all of its samples and hands the triggers over as a stream. Two oscillators summed
 // into the filter, an LFO on the second oscillator's frequency and on the cutoff, the envelope applied AFTER the filter: a graph the
-// fused bank kernels cannot express -- maxiVoices runs it on the patch interpreter.
+// fused bank kernels cannot express -- maxiVoices runs it as a voice patch: the kernel the library generates and compiles for this graph
+// (MXB_PATCH_MODE=interpret: the interpreting kernel).
 //
 //   patch_polysynth <tables.bin> <out.bin> NBLOCKS B      tables.bin: sineBuffer[514] ++ transition[1001] ++ sine_before (doubles)
 // out.bin: the trigger stream [NBLOCKS][B][6] (doubles), then the interleaved stereo output [NBLOCKS][B][2] the audio callback filled.
@@ -81,7 +82,7 @@ int main(int argc, char** argv) {
             }
             triggers.insert(triggers.end(), trigger.begin(), trigger.end());
         }
-        if (voices.fused()) { fprintf(stderr, "expected the interpreter, got the fused bank\n"); return 1; }
+        if (voices.fused()) { fprintf(stderr, "expected a voice patch, got the fused bank\n"); return 1; }
         FILE* g = fopen(argv[2], "wb");
         fwrite(triggers.data(), sizeof(double), triggers.size(), g);
         fwrite(output.data(), sizeof(double), output.size(), g);
