@@ -122,8 +122,9 @@ struct maxiBus { maxiVoices* voices = nullptr; };
  * stage per call, `+ - * /` between signals included -- and hand over parameters; render() runs the block on the GPU. A patch of the
  * shape oscillator -> [maxiEnv] -> [filter] -> [maxiDelayline] -> maxiMix::stereo / per-voice output with block-constant arguments
  * runs on the fused bank kernels (mxb_bank, the HBM-roofline path); any other graph -- sums of oscillators, an LFO on a cutoff,
- * the envelope applied after the filter (maximilian_examples/15.polysynth/main.cpp:54-70), per-sample triggers -- runs on the patch
- * voice patch (mxb_patch: a kernel generated and compiled for the recorded graph, or the interpreting kernel). The patch must be the same on every block (the reference's play() is, too). */
+ * the envelope applied after the filter (maximilian_examples/15.polysynth/main.cpp:54-70), per-sample triggers -- runs as a voice
+ * patch (mxb_patch: a kernel generated and compiled for the recorded graph, or the interpreting kernel). The patch must be the same on
+ * every block (the reference's play() is, too). */
 class maxiVoices {
 public:
     explicit maxiVoices(int voices, int device = 0) : V_(voices), device_(device) {}
