@@ -243,7 +243,7 @@ int64_t mxb_bank_launch_count(const mxb_bank* bank);
  * oscillators summed into one filter, an LFO added to a frequency or a cutoff, the envelope multiplying the FILTER OUTPUT
  * (cpp/commandline/maximilian_examples/15.polysynth/main.cpp:54-70), a trigger that changes on any sample
  * (10.Filters/main.cpp:27-36), and the rest of the family: table oscillators, one-pole filters, maxiDCBlocker,
- * maxiNonlinearity, maxiEnvGen, maxiFlanger. State lives on the device between calls like a bank's. A patch runs in one
+ * maxiNonlinearity, maxiEnvGen, maxiFlanger, maxiChorus. State lives on the device between calls like a bank's. A patch runs in one
  * of two ways (mxb_patch_set_mode), with identical state layout and results:
  *   MXB_PATCH_FUSED (default)  the library writes the CUDA source of ONE kernel for exactly this stage list -- stage state and
  *                              parameters in registers, constants as literals, coefficient designs whose arguments do not
@@ -285,12 +285,16 @@ enum {
     MXB_OP_FLANGER,      /* maxiFlanger::flange src/maximilian.h:1144-1180: src0 input, src1 delay, src2 feedback, src3 speed, src4 depth. state: dl phase, lfo phase, lfo output */
     MXB_OP_ADD, MXB_OP_SUB, MXB_OP_MUL, MXB_OP_DIV,   /* src0 (+ - * /) src1: the arithmetic a play() does between the calls */
     MXB_OP_MIX_STEREO,   /* maxiMix::stereo(src0, two, src1 = pan) summed into the bus (src/maximilian.cpp:503-509) */
-    MXB_OP_OUT           /* out[t][voice] = src0 */
+    MXB_OP_OUT,          /* out[t][voice] = src0 */
+    MXB_OP_CHORUS        /* maxiChorus::chorus src/maximilian.h:1180-1212: src0 input, src1 delay, src2 feedback, src3 speed, src4 depth, src5 noise -- the
+                            value maxiOsc::noise() returns for this sample (libc rand() scaled to [-1, 1], src/maximilian.cpp:214-220): the caller
+                            owns the random stream, the stage is everything after it (lores(noise, speed, 1) * 2 sweeping two delay lines).
+                            state: dl phase, dl2 phase, lopass x, lopass y; two rings (mxb_patch_get_ring returns them back to back) */
 };
 typedef struct { int32_t op, kind, dst, reserved; int32_t src[MXB_STAGE_SRCS]; } mxb_stage;
 typedef struct {
     int32_t voices, n_stages, n_params, n_consts, n_inputs, max_frames;
-    int32_t delay_taps;           /* ring slots per voice of every DELAY / FLANGER stage */
+    int32_t delay_taps;           /* ring slots per voice of every DELAY / FLANGER stage and of each of a CHORUS stage's two lines */
     int32_t eg_stages, eg_loop, eg_retrigger;     /* maxiEnvGen::setup(levels, times, curves, looping, allowRetrigger): eg_stages + 1 levels */
     const mxb_stage* stages;
     const double* consts;

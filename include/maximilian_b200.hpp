@@ -566,13 +566,29 @@ private:
     int capacity_;
 };
 
-/* maxiFlanger, src/maximilian.h:1144-1180 (maxiChorus draws its LFO from rand(): not reproducible, not offered) */
+/* maxiFlanger, src/maximilian.h:1144-1180 */
 class maxiFlanger {
 public:
     maxiFlanger(maxiVoices& v, int capacity) : v_(&v), capacity_(capacity) {}
     maxiSignal flange(maxiSignal input, const maxiArg& delay, const maxiArg& feedback, const maxiArg& speed, const maxiArg& depth) {
         v_->check(input, "maxiFlanger::flange"); v_->delayCapacity_ = capacity_;
         return v_->emit(MXB_OP_FLANGER, 0, {input.src, delay.op(v_), feedback.op(v_), speed.op(v_), depth.op(v_)});
+    }
+private:
+    maxiVoices* v_;
+    int capacity_;
+};
+
+/* maxiChorus, src/maximilian.h:1180-1212. The reference draws its modulator from libc rand() inside the call (lfo.noise()); here the caller
+ * owns the random stream and hands over what noise() would have returned for every sample of the block -- maxiStream of
+ * [frame][voice] values in [-1, 1], e.g. `float r = rand() / (float)RAND_MAX; x = r * 2 - 1;` in frame-major order to replay the
+ * reference exactly. Everything after the draw (the lores-filtered modulator, both swept delay lines, the normalisation) is the stage. */
+class maxiChorus {
+public:
+    maxiChorus(maxiVoices& v, int capacity) : v_(&v), capacity_(capacity) {}
+    maxiSignal chorus(maxiSignal input, const maxiArg& delay, const maxiArg& feedback, const maxiArg& speed, const maxiArg& depth, const maxiStream& noise) {
+        v_->check(input, "maxiChorus::chorus"); v_->delayCapacity_ = capacity_;
+        return v_->emit(MXB_OP_CHORUS, 0, {input.src, delay.op(v_), feedback.op(v_), speed.op(v_), depth.op(v_), v_->operand(noise)});
     }
 private:
     maxiVoices* v_;

@@ -169,6 +169,16 @@ __global__ void __launch_bounds__(kPatchThreads) patch_kernel(const PatchArgs a)
                     st[sb] = (double)ph;
                     break;
                 }
+                case MXB_OP_CHORUS: {
+                    double* ring = a.rings + (size_t)s_ring[si] * (size_t)a.taps * V + vv;      // this voice's two lines: ring index s_ring[si], + 1
+                    int ph1 = (int)st[sb], ph2 = (int)st[sb + 1];
+                    FiltRegs lp; lp.s0 = st[sb + 2]; lp.s1 = st[sb + 3];
+                    filt_design<FILT_T_LORES>(lp, fetch(g.src[3]), 1.0, sr);
+                    y = chorus_tick(ring, ring + (size_t)a.taps * V, V, a.taps, live, ph1, ph2, lp, fetch(g.src[0]), (unsigned int)fetch(g.src[1]), fetch(g.src[2]),
+                                    fetch(g.src[4]), fetch(g.src[5]));
+                    st[sb] = (double)ph1; st[sb + 1] = (double)ph2; st[sb + 2] = lp.s0; st[sb + 3] = lp.s1;
+                    break;
+                }
                 case MXB_OP_ADD: y = fetch(g.src[0]) + fetch(g.src[1]); break;
                 case MXB_OP_SUB: y = fetch(g.src[0]) - fetch(g.src[1]); break;
                 case MXB_OP_MUL: y = fetch(g.src[0]) * fetch(g.src[1]); break;
@@ -255,7 +265,7 @@ int32_t mxb_patch_create(mxb_ctx* ctx, const mxb_patch_desc* d, mxb_patch** out)
     bool tables = false, eg = false;
     for (int i = 0; i < d->n_stages; ++i) {
         const mxb_stage& g = d->stages[i];
-        MXB_REQUIRE(g.op >= MXB_OP_OSC && g.op <= MXB_OP_OUT, MXB_ERR_INVALID, "mxb_patch_create: stage %d: unknown op %d", i, g.op);
+        MXB_REQUIRE(g.op >= MXB_OP_OSC && g.op <= MXB_OP_CHORUS, MXB_ERR_INVALID, "mxb_patch_create: stage %d: unknown op %d", i, g.op);
         MXB_REQUIRE(g.dst == MXB_NONE || (g.dst >= 0 && g.dst < kMaxRegs), MXB_ERR_INVALID, "mxb_patch_create: stage %d: dst %d", i, g.dst);
         for (int k = 0; k < MXB_STAGE_SRCS; ++k) MXB_REQUIRE(src_ok(g.src[k], d), MXB_ERR_INVALID, "mxb_patch_create: stage %d: operand %d = 0x%x", i, k, g.src[k]);
         if (g.op == MXB_OP_OSC) {
@@ -266,7 +276,7 @@ int32_t mxb_patch_create(mxb_ctx* ctx, const mxb_patch_desc* d, mxb_patch** out)
                                                MXB_ERR_INVALID, "mxb_patch_create: stage %d: filter kind %d", i, g.kind);
         if (g.op == MXB_OP_BIQUAD) MXB_REQUIRE(g.kind >= MXB_BQ_LOWPASS && g.kind <= MXB_BQ_HIGHSHELF, MXB_ERR_INVALID, "mxb_patch_create: stage %d: biquad type %d", i, g.kind);
         if (g.op == MXB_OP_NONLIN) MXB_REQUIRE(g.kind >= MXB_NL_ATANDIST && g.kind <= MXB_NL_FASTATAN, MXB_ERR_INVALID, "mxb_patch_create: stage %d: nonlinearity %d", i, g.kind);
-        if (g.op == MXB_OP_DELAY || g.op == MXB_OP_FLANGER) { MXB_REQUIRE(d->delay_taps > 0, MXB_ERR_INVALID, "mxb_patch_create: stage %d needs delay_taps > 0", i); ++n_rings; }
+        if (patch_stage_rings(g.op)) { MXB_REQUIRE(d->delay_taps > 0, MXB_ERR_INVALID, "mxb_patch_create: stage %d needs delay_taps > 0", i); n_rings += patch_stage_rings(g.op); }
         if (g.op == MXB_OP_ENVGEN) eg = true;
         n_state += state_slots(g);
     }
@@ -286,8 +296,9 @@ int32_t mxb_patch_create(mxb_ctx* ctx, const mxb_patch_desc* d, mxb_patch** out)
     int sb = 0, ri = 0;
     for (int i = 0; i < d->n_stages; ++i) {
         p->state_base.push_back(sb); sb += state_slots(p->stages[i]);
-        const bool ring = p->stages[i].op == MXB_OP_DELAY || p->stages[i].op == MXB_OP_FLANGER;
-        p->ring_of.push_back(ring ? ri++ : -1);
+        const int nr = patch_stage_rings(p->stages[i].op);
+        p->ring_of.push_back(nr ? ri : -1);
+        ri += nr;
     }
     // maxiEnvGen::setup + setupSegmentTime, src/maximilian.h:2371-2402, 2524-2538: segment table from levels / times / curves
     p->eg_n = d->eg_stages; p->eg_loop = d->eg_loop; p->eg_retrigger = d->eg_retrigger;
@@ -386,7 +397,7 @@ int32_t mxb_patch_get_state(mxb_patch* p, int32_t stage, int32_t slot, double* v
 int32_t mxb_patch_get_ring(mxb_patch* p, int32_t stage, int32_t voice, double* dst, int32_t n, int32_t mem) {
     MXB_REQUIRE(p && dst, MXB_ERR_INVALID, "mxb_patch_get_ring: NULL argument");
     MXB_REQUIRE(stage >= 0 && stage < p->n_stages && p->ring_of[stage] >= 0, MXB_ERR_INVALID, "mxb_patch_get_ring: stage %d has no delay line", stage);
-    MXB_REQUIRE(voice >= 0 && voice < p->V && n >= 0 && n <= p->taps, MXB_ERR_INVALID, "mxb_patch_get_ring: voice %d n %d", voice, n);
+    MXB_REQUIRE(voice >= 0 && voice < p->V && n >= 0 && n <= p->taps * patch_stage_rings(p->stages[stage].op), MXB_ERR_INVALID, "mxb_patch_get_ring: voice %d n %d", voice, n);
     DeviceGuard g(p->ctx->device);
     const double* src = p->rings + (size_t)p->ring_of[stage] * (size_t)p->taps * (size_t)p->V + (size_t)voice;
     if (n) MXB_CUDA(cudaMemcpy2D(dst, sizeof(double), src, sizeof(double) * (size_t)p->V, sizeof(double), (size_t)n,
@@ -416,7 +427,7 @@ int32_t mxb_patch_codegen(const mxb_patch_desc* d, char* buf, int64_t cap, int64
                 d->n_inputs >= 0 && d->n_inputs <= kMaxInputs && (d->n_consts == 0 || d->consts), MXB_ERR_INVALID, "mxb_patch_codegen: bad descriptor");
     for (int i = 0; i < d->n_stages; ++i) {
         const mxb_stage& g = d->stages[i];
-        MXB_REQUIRE(g.op >= MXB_OP_OSC && g.op <= MXB_OP_OUT && (g.dst == MXB_NONE || (g.dst >= 0 && g.dst < kMaxRegs)), MXB_ERR_INVALID, "mxb_patch_codegen: stage %d", i);
+        MXB_REQUIRE(g.op >= MXB_OP_OSC && g.op <= MXB_OP_CHORUS && (g.dst == MXB_NONE || (g.dst >= 0 && g.dst < kMaxRegs)), MXB_ERR_INVALID, "mxb_patch_codegen: stage %d", i);
         for (int k = 0; k < MXB_STAGE_SRCS; ++k) MXB_REQUIRE(src_ok(g.src[k], d), MXB_ERR_INVALID, "mxb_patch_codegen: stage %d: operand %d = 0x%x", i, k, g.src[k]);
     }
     int types[kMaxInputs] = {};

@@ -196,6 +196,18 @@ __device__ __forceinline__ double flanger_tick(double* __restrict__ ring, const 
     return (outv + in) / 2.0;
 }
 
+// maxiChorus::chorus, src/maximilian.h:1200-1212, from the noise value on: lfoVal = lopass.lores(noise, speed, 1.0) * 2.0 (the design is
+// the caller's: it is block-constant when `speed` is), two delay lines swept by it, normalise, average
+__device__ __forceinline__ double chorus_tick(double* __restrict__ ringA, double* __restrict__ ringB, const size_t V, const int taps, const bool live, int& ph1, int& ph2,
+                                              FiltRegs& lp, const double in, const unsigned int delay, const double fb, const double depth, const double noise) {
+    const double lfoVal = filt_tick<FILT_T_LORES>(lp, noise, nullptr) * 2.0;
+    double output1 = delay_tick(false, ringA, V, taps, live, ph1, in, (int)(delay + (lfoVal * depth * delay) + 1), fb, 0);
+    double output2 = delay_tick(false, ringB, V, taps, live, ph2, in, (int)((delay + (lfoVal * depth * delay * 1.02) + 1) * 0.98), fb * 0.99, 0);
+    output1 *= (1.0 - fabs(output1));
+    output2 *= (1.0 - fabs(output2));
+    return (output1 + output2 + in) / 3.0;
+}
+
 // maxiMix::stereo (src/maximilian.cpp:503-509) of one voice, accumulated into the bus sums of this sample
 __device__ __forceinline__ void mix_stereo_acc(double& ml, double& mr, const double in, double x) {
     if (x > 1) x = 1;
@@ -227,9 +239,12 @@ __host__ __device__ inline int patch_state_slots(const int op) {
         case MXB_OP_DCBLOCK: return 2;
         case MXB_OP_DELAY: return 1;
         case MXB_OP_FLANGER: return 3;
+        case MXB_OP_CHORUS: return 4;
         default: return 0;
     }
 }
+// delay lines (rings of delay_taps slots) a stage owns
+__host__ __device__ inline int patch_stage_rings(const int op) { return op == MXB_OP_CHORUS ? 2 : (op == MXB_OP_DELAY || op == MXB_OP_FLANGER) ? 1 : 0; }
 
 // sample t of input stream k for voice v
 __device__ __forceinline__ double patch_input(const PatchArgs& a, const int k, const size_t t, const size_t v, const size_t V) {

@@ -5,7 +5,7 @@ operands that are registers, per-voice parameters, scalar constants or per-sampl
 the GPU (capi.Patch) and, in the tests, both CPU oracles (oracle_py.Patch): one description, three executors.
 """
 OP = dict(osc=1, env_adsr=2, env_ar=3, envgen=4, filter=5, svf=6, biquad=7, dcblock=8, nonlin=9, delay=10, flanger=11,
-          add=12, sub=13, mul=14, div=15, mix_stereo=16, out=17)
+          add=12, sub=13, mul=14, div=15, mix_stereo=16, out=17, chorus=18)
 OSC = dict(sinewave=0, coswave=1, phasor=2, saw=3, square=4, pulse=5, impulse=6, triangle=7, phasorbetween=8, sinebuf=9, sinebuf4=10, sawn=11)
 FILT = dict(lores=1, hires=2, lopass=5, hipass=6, bandpass=7)
 BIQUAD = dict(lowpass=0, highpass=1, bandpass=2, notch=3, peak=4, lowshelf=5, highshelf=6)

@@ -542,8 +542,17 @@ static int p_state_slots(const mxo_stage* g) {
         case MXO_OP_DCBLOCK: return 2;
         case MXO_OP_DELAY: return 1;
         case MXO_OP_FLANGER: return 3;
+        case MXO_OP_CHORUS: return 4;
         default: return 0;
     }
+}
+static int p_stage_rings(const mxo_stage* g) { return g->op == MXO_OP_CHORUS ? 2 : (g->op == MXO_OP_DELAY || g->op == MXO_OP_FLANGER) ? 1 : 0; }
+
+/* maxiOsc::noise, src/maximilian.cpp:214-220, on libc rand() */
+void mxo_srand(uint32_t seed) { srand(seed); }
+void mxo_noise_fill(uint32_t seed, int64_t n, double* out) {
+    srand(seed);
+    for (int64_t i = 0; i < n; ++i) { float r = rand() / (float)RAND_MAX; out[i] = r * 2 - 1; }
 }
 
 void* mxo_patch_create(const mxo_patch_desc* d) {
@@ -557,8 +566,9 @@ void* mxo_patch_create(const mxo_patch_desc* d) {
     p->sbase = (int*)calloc((size_t)d->n_stages, sizeof(int)); p->ringof = (int*)calloc((size_t)d->n_stages, sizeof(int));
     for (int i = 0; i < d->n_stages; ++i) {
         p->sbase[i] = p->n_state; p->n_state += p_state_slots(&p->stages[i]);
-        const int ring = p->stages[i].op == MXO_OP_DELAY || p->stages[i].op == MXO_OP_FLANGER;
-        p->ringof[i] = ring ? p->n_rings++ : -1;
+        const int nr = p_stage_rings(&p->stages[i]);
+        p->ringof[i] = nr ? p->n_rings : -1;
+        p->n_rings += nr;
     }
     const size_t V = (size_t)d->voices;
     p->params = (double*)calloc((size_t)(d->n_params ? d->n_params : 1) * V, sizeof(double));
@@ -612,8 +622,13 @@ int32_t mxo_patch_get_state(void* h, int32_t stage, int32_t slot, double* x) {
 }
 int32_t mxo_patch_get_ring(void* h, int32_t stage, int32_t v, double* dst, int32_t n) {
     patch_t* p = (patch_t*)h;
-    if (!p || !dst || stage < 0 || stage >= p->d.n_stages || p->ringof[stage] < 0 || v < 0 || v >= p->d.voices || n < 0 || n > p->d.delay_taps) return -1;
-    memcpy(dst, p->rings + ((size_t)p->ringof[stage] * (size_t)p->d.voices + (size_t)v) * (size_t)p->d.delay_taps, sizeof(double) * (size_t)n);
+    if (!p || !dst || stage < 0 || stage >= p->d.n_stages || p->ringof[stage] < 0 || v < 0 || v >= p->d.voices || n < 0) return -1;
+    const int taps = p->d.delay_taps, nr = p_stage_rings(&p->stages[stage]);
+    if (n > taps * nr) return -1;
+    for (int k = 0; k < nr && k * taps < n; ++k) {          /* a chorus stage's two lines back to back */
+        const int m = n - k * taps < taps ? n - k * taps : taps;
+        memcpy(dst + (size_t)k * taps, p->rings + ((size_t)(p->ringof[stage] + k) * (size_t)p->d.voices + (size_t)v) * (size_t)taps, sizeof(double) * (size_t)m);
+    }
     return 0;
 }
 
@@ -917,6 +932,44 @@ int32_t mxo_patch_process(void* h, int32_t nframes, const double* const* inputs,
                             output *= normalise;
                             y = (output + input) / 2.0;
                         } else y = output;
+                        break;
+                    }
+                    case MXO_OP_CHORUS: {           /* maxiChorus::chorus, src/maximilian.h:1200-1212; slots: dl.phase, dl2.phase, lopass.x, lopass.y */
+                        const double input = FETCH(g->src[0]);
+                        const unsigned int delay = (unsigned int)FETCH(g->src[1]);
+                        const double feedback = FETCH(g->src[2]), speed = FETCH(g->src[3]), depth = FETCH(g->src[4]);
+                        double lfoVal = FETCH(g->src[5]);                 /* lfo.noise() */
+                        {   /* lopass.lores(lfoVal, speed, 1.0), src/maximilian.cpp:455-468 */
+                            double cutoff = speed, resonance = 1.0;
+                            double fx = st[2 * V], fy = st[3 * V];
+                            if (cutoff < 10) cutoff = 10;
+                            if (cutoff > sr) cutoff = sr;
+                            if (resonance < 1.) resonance = 1.;
+                            double z = cos(MAXI_TWOPI * cutoff / sr);
+                            double cc = 2 - 2 * z;
+                            double r = (sqrt(2.0) * sqrt(-pow((z - 1.0), 3.0)) + resonance * (z - 1)) / (resonance * (z - 1));
+                            fx = fx + (lfoVal - fy) * cc;
+                            fy = fy + fx;
+                            fx = fx * r;
+                            st[2 * V] = fx; st[3 * V] = fy;
+                            lfoVal = fy * 2.0;
+                        }
+                        double outs[2];
+                        for (int k = 0; k < 2; ++k) {                     /* dl.dl(input, size, feedback) / dl2.dl(...), src/maximilian.cpp:420-429 */
+                            double* memory = p->rings + ((size_t)(p->ringof[si] + k) * V + v) * (size_t)taps;
+                            const int size = k == 0 ? (int)(delay + (lfoVal * depth * delay) + 1) : (int)((delay + (lfoVal * depth * delay * 1.02) + 1) * 0.98);
+                            const double fbk = k == 0 ? feedback : feedback * 0.99;
+                            int phase = (int)st[(size_t)k * V];
+                            if (phase >= size) phase = 0;
+                            if (phase < 0 || phase >= taps) return -4;
+                            outs[k] = memory[phase];
+                            memory[phase] = (memory[phase] * fbk) + (input * fbk) * 0.5;
+                            phase += 1;
+                            st[(size_t)k * V] = (double)phase;
+                        }
+                        outs[0] *= (1.0 - fabs(outs[0]));
+                        outs[1] *= (1.0 - fabs(outs[1]));
+                        y = (outs[0] + outs[1] + input) / 3.0;
                         break;
                     }
                     case MXO_OP_ADD: y = FETCH(g->src[0]) + FETCH(g->src[1]); break;

@@ -152,7 +152,8 @@ enum { MXO_FILT_LOPASS = 5, MXO_FILT_HIPASS = 6, MXO_FILT_BANDPASS = 7 };       
 enum { MXO_NL_ATANDIST = 0, MXO_NL_FASTATANDIST, MXO_NL_SOFTCLIP, MXO_NL_HARDCLIP, MXO_NL_ASYMCLIP, MXO_NL_FASTATAN };   /* src/maximilian.h:1046-1137 */
 #define MXO_ENVGEN_HOLD (-46692.0)                                                       /* maxiEnvGen::HOLD, src/maximilian.h:2271 */
 enum { MXO_OP_OSC = 1, MXO_OP_ENV_ADSR, MXO_OP_ENV_AR, MXO_OP_ENVGEN, MXO_OP_FILTER, MXO_OP_SVF, MXO_OP_BIQUAD, MXO_OP_DCBLOCK, MXO_OP_NONLIN,
-       MXO_OP_DELAY, MXO_OP_FLANGER, MXO_OP_ADD, MXO_OP_SUB, MXO_OP_MUL, MXO_OP_DIV, MXO_OP_MIX_STEREO, MXO_OP_OUT };
+       MXO_OP_DELAY, MXO_OP_FLANGER, MXO_OP_ADD, MXO_OP_SUB, MXO_OP_MUL, MXO_OP_DIV, MXO_OP_MIX_STEREO, MXO_OP_OUT,
+       MXO_OP_CHORUS /* maxiChorus::chorus, src/maximilian.h:1200-1212: src5 = the value maxiOsc::noise() returns this sample */ };
 typedef struct { int32_t op, kind, dst, reserved; int32_t src[8]; } mxo_stage;      /* operands: 0..15 register, 0x100+j parameter, 0x200+k constant, 0x300+m input, -1 none */
 typedef struct {
     int32_t voices, n_stages, n_params, n_consts, n_inputs, sample_rate;
@@ -173,6 +174,11 @@ int32_t mxo_patch_set_state(void* patch, int32_t stage, int32_t slot, const doub
 int32_t mxo_patch_get_state(void* patch, int32_t stage, int32_t slot, double* values);
 int32_t mxo_patch_get_ring(void* patch, int32_t stage, int32_t voice, double* dst, int32_t n);
 int32_t mxo_patch_process(void* patch, int32_t nframes, const double* const* inputs, double* out, double* mix);
+/* maxiChorus draws its modulator from libc rand() through maxiOsc::noise() (src/maximilian.cpp:214-220). mxo_noise_fill: srand(seed), then n
+ * values exactly as noise() produces them (both libraries: the same libc); mxo_srand: re-seed before the compiled reference runs a patch
+ * with ONE chorus stage and no other noise source, so that it draws the sequence mxo_noise_fill returned, in (frame, voice) order. */
+void    mxo_noise_fill(uint32_t seed, int64_t n, double* out);
+void    mxo_srand(uint32_t seed);
 
 /* maxiFFTOctaveAnalyzer (src/libs/maxiFFT.h:162-205, maxiFFT.cpp:201-300), one analyser per channel, fed magnitude frames:
  * mags[C][frames][n_bands] -> averages / peaks [C][frames][nAverages] (the values after each calculate()). averages[], peaks[]

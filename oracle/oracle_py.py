@@ -373,7 +373,23 @@ def _patch_sigs(lib):
     lib.mxo_patch_get_state.restype, lib.mxo_patch_get_state.argtypes = i32, [vp, i32, i32, dp]
     lib.mxo_patch_get_ring.restype, lib.mxo_patch_get_ring.argtypes = i32, [vp, i32, i32, dp, i32]
     lib.mxo_patch_process.restype, lib.mxo_patch_process.argtypes = i32, [vp, i32, C.POINTER(C.c_void_p), dp, dp]
+    lib.mxo_noise_fill.restype, lib.mxo_noise_fill.argtypes = None, [C.c_uint32, C.c_int64, dp]
+    lib.mxo_srand.restype, lib.mxo_srand.argtypes = None, [C.c_uint32]
     lib._patch_sigs_done = True
+
+
+def noise_fill(seed, n, kind="port"):
+    """srand(seed), then n values of maxiOsc::noise() (src/maximilian.cpp:214-220) from this process's libc rand()."""
+    lib = load(kind); _patch_sigs(lib)
+    a = np.empty(int(n), dtype=np.float64)
+    lib.mxo_noise_fill(int(seed), int(n), _dp(a))
+    return a
+
+
+def srand(seed, kind="reference"):
+    """Re-seed libc rand() (process-wide) before the compiled reference runs a patch whose chorus stage draws from it."""
+    lib = load(kind); _patch_sigs(lib)
+    lib.mxo_srand(int(seed))
 
 
 def get_tables(kind="reference"):

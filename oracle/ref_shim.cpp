@@ -421,6 +421,7 @@ struct RefPatch {
     std::vector<RefStageObj*> objs;            /* [stage] -> calloc'ed array of V objects (light stages) */
     std::vector<maxiDelayline**> delays;       /* [stage] -> V delay lines (5.6 MB each) or null */
     std::vector<maxiFlanger**> flangers;
+    std::vector<maxiChorus**> choruses;        /* two delay lines each */
     std::vector<maxiEnvGen*> envgens;          /* [stage] -> array of V */
 };
 
@@ -435,6 +436,7 @@ int ref_state_slots(const mxo_stage& g) {
         case MXO_OP_DCBLOCK: return 2;
         case MXO_OP_DELAY: return 1;
         case MXO_OP_FLANGER: return 3;
+        case MXO_OP_CHORUS: return 4;
         default: return 0;
     }
 }
@@ -454,6 +456,7 @@ double* ref_slot_ptr(RefPatch* p, int si, int slot, int v) {
         case MXO_OP_BIQUAD: return slot == 0 ? &o->bq.v[1] : &o->bq.v[2];
         case MXO_OP_DCBLOCK: return slot == 0 ? &o->dc.xm1 : &o->dc.ym1;
         case MXO_OP_FLANGER: return slot == 1 ? &p->flangers[si][v]->lfo.phase : slot == 2 ? &p->flangers[si][v]->lfo.output : nullptr;
+        case MXO_OP_CHORUS: return slot == 2 ? &p->choruses[si][v]->lopass.x : slot == 3 ? &p->choruses[si][v]->lopass.y : nullptr;
         default: return nullptr;
     }
 }
@@ -485,7 +488,8 @@ void* mxo_patch_create(const mxo_patch_desc* d) {
         RefStageObj* o = (RefStageObj*)calloc((size_t)V, sizeof(RefStageObj));
         for (int v = 0; v < V; ++v) new (&o[v]) RefStageObj();
         p->objs.push_back(o);
-        maxiDelayline** dl = nullptr; maxiFlanger** fl = nullptr; maxiEnvGen* eg = nullptr;
+        maxiDelayline** dl = nullptr; maxiFlanger** fl = nullptr; maxiChorus** ch = nullptr; maxiEnvGen* eg = nullptr;
+        if (g.op == MXO_OP_CHORUS) { ch = (maxiChorus**)calloc((size_t)V, sizeof(void*)); for (int v = 0; v < V; ++v) ch[v] = zeroed_new<maxiChorus>(); }
         if (g.op == MXO_OP_DELAY) { dl = (maxiDelayline**)calloc((size_t)V, sizeof(void*)); for (int v = 0; v < V; ++v) dl[v] = zeroed_new<maxiDelayline>(); }
         if (g.op == MXO_OP_FLANGER) { fl = (maxiFlanger**)calloc((size_t)V, sizeof(void*)); for (int v = 0; v < V; ++v) fl[v] = zeroed_new<maxiFlanger>(); }
         if (g.op == MXO_OP_ENVGEN) {
@@ -496,7 +500,7 @@ void* mxo_patch_create(const mxo_patch_desc* d) {
             for (int v = 0; v < V; ++v) eg[v].setup(levels, times, curves, d->eg_loop != 0, d->eg_retrigger != 0);
             std::cout.rdbuf(old);
         }
-        p->delays.push_back(dl); p->flangers.push_back(fl); p->envgens.push_back(eg);
+        p->delays.push_back(dl); p->flangers.push_back(fl); p->choruses.push_back(ch); p->envgens.push_back(eg);
     }
     return p;
 }
@@ -507,6 +511,7 @@ void mxo_patch_destroy(void* h) {
         free(p->objs[si]);
         if (p->delays[si]) { for (int v = 0; v < p->d.voices; ++v) free(p->delays[si][v]); free(p->delays[si]); }
         if (p->flangers[si]) { for (int v = 0; v < p->d.voices; ++v) free(p->flangers[si][v]); free(p->flangers[si]); }
+        if (p->choruses[si]) { for (int v = 0; v < p->d.voices; ++v) free(p->choruses[si][v]); free(p->choruses[si]); }
         delete[] p->envgens[si];
     }
     delete p;
@@ -538,6 +543,7 @@ int32_t mxo_patch_get_state(void* h, int32_t stage, int32_t slot, double* x) {
                              : (double)((e.attackphase & 1) | (e.decayphase & 1) << 1 | (e.sustainphase & 1) << 2 | (e.holdphase & 1) << 3 | (e.releasephase & 1) << 4);
         } else if (g.op == MXO_OP_DELAY) x[v] = (double)p->delays[stage][v]->phase;
         else if (g.op == MXO_OP_FLANGER) x[v] = (double)p->flangers[stage][v]->dl.phase;
+        else if (g.op == MXO_OP_CHORUS) x[v] = (double)(slot == 0 ? p->choruses[stage][v]->dl.phase : p->choruses[stage][v]->dl2.phase);
         else if (g.op == MXO_OP_ENVGEN) {
             maxiEnvGen& e = p->envgens[stage][v];
             switch (slot) {
@@ -564,8 +570,22 @@ int32_t mxo_patch_get_ring(void* h, int32_t stage, int32_t v, double* dst, int32
     if (!p || !dst || stage < 0 || stage >= p->d.n_stages || v < 0 || v >= p->d.voices || n < 0 || n > 88200 * 8) return -1;
     if (p->delays[stage]) memcpy(dst, p->delays[stage][v]->memory, sizeof(double) * (size_t)n);
     else if (p->flangers[stage]) memcpy(dst, p->flangers[stage][v]->dl.memory, sizeof(double) * (size_t)n);
+    else if (p->choruses[stage]) {          /* the two lines back to back, delay_taps slots of each */
+        const int taps = p->d.delay_taps;
+        if (n > 2 * taps) return -1;
+        memcpy(dst, p->choruses[stage][v]->dl.memory, sizeof(double) * (size_t)(n < taps ? n : taps));
+        if (n > taps) memcpy(dst + taps, p->choruses[stage][v]->dl2.memory, sizeof(double) * (size_t)(n - taps));
+    }
     else return -1;
     return 0;
+}
+
+/* maxiOsc::noise() as the reference's own object produces it, after srand(seed) */
+void mxo_srand(uint32_t seed) { srand(seed); }
+void mxo_noise_fill(uint32_t seed, int64_t n, double* out) {
+    srand(seed);
+    maxiOsc o;
+    for (int64_t i = 0; i < n; ++i) out[i] = o.noise();
 }
 
 int32_t mxo_patch_process(void* h, int32_t nframes, const double* const* inputs, double* out, double* mix) {
@@ -643,6 +663,9 @@ int32_t mxo_patch_process(void* h, int32_t nframes, const double* const* inputs,
                         break;
                     case MXO_OP_FLANGER:
                         y = p->flangers[si][v]->flange(F(g.src[0]), (unsigned int)F(g.src[1]), F(g.src[2]), F(g.src[3]), F(g.src[4]));
+                        break;
+                    case MXO_OP_CHORUS:      /* the reference draws its own noise (rand()): src5 is what the caller predicted it to be (mxo_noise_fill / mxo_srand) */
+                        y = p->choruses[si][v]->chorus(F(g.src[0]), (unsigned int)F(g.src[1]), F(g.src[2]), F(g.src[3]), F(g.src[4]));
                         break;
                     case MXO_OP_ADD: y = F(g.src[0]) + F(g.src[1]); break;
                     case MXO_OP_SUB: y = F(g.src[0]) - F(g.src[1]); break;

@@ -177,9 +177,31 @@ def patches():
     np.savez_compressed(os.path.join(HERE, "patches.npz"), **out)
 
 
+def chorus():
+    """maxiChorus run by the reference's own objects, drawing its noise from libc rand() after srand(seed); the fixture keeps the noise
+    stream (what maxiOsc::noise() returned, in frame-major / voice-minor order) next to the outputs, so that the replay needs no rand()."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import patch_cases as PC
+    V, B, NB, seed = 10, 200, 3, 4242
+    name, d, params, _, exact, taps = PC.chorus()
+    noise = O.noise_fill(seed, NB * B * V, KIND).reshape(NB, B, V)
+    p = O.Patch(d, V, delay_taps=taps, kind=KIND)
+    for k, v in params(V, 99).items():
+        p.set(k, v)
+    O.srand(seed, KIND)
+    outs, mixes = [], []
+    for blk in range(NB):
+        o, m = p.process(B, {"noise": noise[blk]}, want_mix=True)       # the reference ignores the stream: it draws the same values itself
+        outs.append(o); mixes.append(m)
+    np.savez_compressed(os.path.join(HERE, "chorus.npz"), V=V, B=B, NB=NB, taps=taps, noise=noise, out=np.stack(outs), mix=np.stack(mixes))
+
+
 if __name__ == "__main__":
     O.build("reference")
-    chains(); seeds(); spectral(); mods(); tables(); patches()
+    if len(sys.argv) > 1 and sys.argv[1] == "chorus":      # add this fixture without rewriting the others
+        chorus()
+    else:
+        chains(); seeds(); spectral(); mods(); tables(); patches(); chorus()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)), "bytes")

@@ -118,5 +118,31 @@ def envgen_flanger():
     return ("envgen_flanger", d, params, inputs, False, 512)        # pow(level, curve) per sample: libdevice vs glibc
 
 
+def chorus(modulated_speed=False):
+    """maxiChorus (src/maximilian.h:1180-1212) on a saw: lores-filtered noise sweeps two delay lines. The noise is an input stream -- what
+    maxiOsc::noise() returns, sample by sample, in (frame, voice) order; the compiled reference draws it itself from libc rand()
+    (oracle_py.noise_fill / srand keep the two in step). modulated_speed: the chorus speed follows a slow LFO (the lores design then
+    runs per sample instead of once per block)."""
+    d = PatchDef()
+    d.stage("osc", d.P("freq"), kind="saw", dst=R(0))
+    d.stage("mul", R(0), d.K(0.5), dst=R(0))
+    if modulated_speed:
+        d.stage("osc", d.K(2.0), kind="triangle", dst=R(2))
+        d.stage("mul", R(2), d.K(15.0), dst=R(2))
+        d.stage("add", R(2), d.K(40.0), dst=R(2))                                     # 25 .. 55 Hz
+        speed = R(2)
+    else:
+        speed = d.K(35.0)
+    d.stage("chorus", R(0), d.K(120.0), d.P("fb"), speed, d.P("depth"), d.IN("noise"), dst=R(1))
+    d.stage("out", R(1))
+    d.stage("mix_stereo", R(1), d.P("pan"))
+
+    def params(V, seed):
+        p = W.voice_params(V, seed=seed)
+        rng = np.random.default_rng(seed + 1)
+        return dict(freq=p["freq"], fb=p["delay_feedback"], depth=0.2 + 0.6 * rng.random(V), pan=p["pan"])
+    return ("chorus_lfo" if modulated_speed else "chorus", d, params, None, False, 512)        # inputs: the noise stream, made by the test
+
+
 def cases():
     return [polysynth(), family_exact(), family_libm(), envgen_flanger()]

@@ -17,8 +17,8 @@ from maximilian_b200 import workloads as W
 
 pytestmark = pytest.mark.gpu
 
-SLOTS = {1: 2, 2: 4, 3: 4, 4: 12, 5: 2, 6: 3, 7: 2, 8: 2, 10: 1, 11: 3}
-INT_SLOTS = {2: (2, 3), 3: (2, 3), 4: (1, 2, 4), 10: (0,), 11: (0,)}          # integral members: exact whatever the patch
+SLOTS = {1: 2, 2: 4, 3: 4, 4: 12, 5: 2, 6: 3, 7: 2, 8: 2, 10: 1, 11: 3, 18: 4}
+INT_SLOTS = {2: (2, 3), 3: (2, 3), 4: (1, 2, 4), 10: (0,), 11: (0,), 18: (0, 1)}          # integral members: exact whatever the patch
 
 
 def _tables(port):
@@ -178,6 +178,47 @@ def test_trigger_streams_as_bytes_and_as_packed_bits(mode, V):
                 ref = (o, m)
             else:
                 assert np.array_equal(o, ref[0]) and np.array_equal(m, ref[1]), (ty, blk)
+
+
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("modulated", [False, True])
+def test_chorus_vs_oracle(port, mode, modulated):
+    """maxiChorus as a stage (the noise it draws is an input stream): outputs 1e-9 (cos / sqrt of the per-sample or hoisted lores design
+    are libdevice's), both delay-line indices exact, both rings and the lores state 1e-9; three blocks, odd voice count."""
+    name, d, params, _, exact, taps = PC.chorus(modulated)
+    V, B, NB = 333, 180, 3
+    noise = port.noise_fill(31, NB * B * V, "port").reshape(NB, B, V)
+    g = capi.Patch(d, V, max_frames=B, delay_taps=taps, mode=mode); o = port.Patch(d, V, delay_taps=taps, kind="port")
+    if not modulated and mode == "fused":
+        src = capi.patch_codegen(d)
+        assert "filt_design<FILT_T_LORES>" in src[:src.index("for (int t = 0")]           # constant speed: designed once per block
+    for k, v in params(V, 6).items():
+        g.set(k, v); o.set(k, v)
+    for blk in range(NB):
+        og, mg = g.process(B, {"noise": noise[blk]}, want_mix=True); oo, mo = o.process(B, {"noise": noise[blk]}, want_mix=True)
+        _cmp(og, oo, False, f"{name} blk{blk}")
+        np.testing.assert_allclose(mg, mo, rtol=1e-9, atol=1e-10)
+    si = [i for i, st in enumerate(d.stages) if st[0] == 18][0]
+    for sl in range(4):
+        _cmp(g.get_state(si, sl), o.get_state(si, sl), sl < 2, f"{name} slot {sl}")
+    for v in range(0, V, 41):
+        _cmp(g.ring(si, v, 2 * taps), o.ring(si, v, 2 * taps), False, f"{name} rings of voice {v}")
+
+
+def test_chorus_golden_and_modes_agree(port):
+    """tests/golden/chorus.npz (the compiled reference drawing its own rand()) replayed on the GPU both ways; fused == interpreted bit for bit"""
+    gl = G.load("chorus")
+    name, d, params, _, exact, taps = PC.chorus()
+    V, B, NB = int(gl["V"]), int(gl["B"]), int(gl["NB"])
+    ps = {m: capi.Patch(d, V, max_frames=B, delay_taps=taps, mode=m) for m in MODES}
+    for p in ps.values():
+        for k, v in params(V, 99).items():
+            p.set(k, v)
+    for blk in range(NB):
+        res = {m: p.process(B, {"noise": gl["noise"][blk]}, want_mix=True) for m, p in ps.items()}
+        _cmp(res["fused"][0], gl["out"][blk], False, f"chorus golden blk{blk}")
+        np.testing.assert_allclose(res["fused"][1], gl["mix"][blk], rtol=1e-9, atol=1e-12)
+        assert np.array_equal(res["fused"][0], res["interpret"][0]) and np.array_equal(res["fused"][1], res["interpret"][1])
 
 
 def test_patch_rejects_bad_programs():

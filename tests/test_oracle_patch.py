@@ -66,6 +66,46 @@ def test_patch_golden_exact(port, case):
         assert np.array_equal(m, g[name + "/mix"][blk], equal_nan=True), (name, blk)
 
 
+def test_chorus_port_equals_reference(port, reference):
+    """maxiChorus: the reference draws its noise from libc rand(); the port is fed the sequence the same libc produces after the same
+    srand (oracle_py.noise_fill), in the (frame, voice) order the reference's loop draws it. Outputs, buses, both delay lines' indices
+    and contents, the lores state: bit for bit."""
+    name, d, params, _, exact, taps = PC.chorus()
+    V, B, NB, seed = 9, 150, 3, 777
+    noise = port.noise_fill(seed, NB * B * V, "port").reshape(NB, B, V)
+    assert np.array_equal(noise, reference.noise_fill(seed, NB * B * V, "reference").reshape(NB, B, V))
+    assert np.abs(noise).max() <= 1.0 and noise.std() > 0.5
+    po = port.Patch(d, V, delay_taps=taps, kind="port"); pr = reference.Patch(d, V, delay_taps=taps, kind="reference")
+    for k, v in params(V, 3).items():
+        po.set(k, v); pr.set(k, v)
+    reference.srand(seed, "reference")
+    si = [i for i, st in enumerate(d.stages) if st[0] == 18][0]
+    for blk in range(NB):
+        orr, mr = pr.process(B, {"noise": noise[blk]}, want_mix=True)          # draws from rand() itself
+        oo, mo = po.process(B, {"noise": noise[blk]}, want_mix=True)
+        assert np.array_equal(oo, orr), blk
+        assert np.array_equal(mo, mr), blk
+        assert np.isfinite(orr).all() and np.abs(orr).max() > 1e-3
+    for sl in range(4):
+        assert np.array_equal(po.get_state(si, sl), pr.get_state(si, sl)), sl
+    for v in range(V):
+        assert np.array_equal(po.ring(si, v, 2 * taps), pr.ring(si, v, 2 * taps)), v
+    assert len({int(x) for x in po.get_state(si, 0)} | {int(x) for x in po.get_state(si, 1)}) > 2      # the lines are swept: indices diverged
+
+
+def test_chorus_golden_exact(port):
+    g = G.load("chorus")
+    name, d, params, _, exact, taps = PC.chorus()
+    V, B, NB = int(g["V"]), int(g["B"]), int(g["NB"])
+    assert int(g["taps"]) == taps
+    p = port.Patch(d, V, delay_taps=taps, kind="port")
+    for k, v in params(V, 99).items():
+        p.set(k, v)
+    for blk in range(NB):
+        o, m = p.process(B, {"noise": g["noise"][blk]}, want_mix=True)
+        assert np.array_equal(o, g["out"][blk]) and np.array_equal(m, g["mix"][blk]), blk
+
+
 def test_registers_read_zero_until_written(port):
     from maximilian_b200.patchdef import PatchDef, R
     d = PatchDef()

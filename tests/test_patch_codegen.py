@@ -11,7 +11,7 @@ from maximilian_b200 import capi
 from maximilian_b200.patchdef import PatchDef, R
 
 
-@pytest.mark.parametrize("case", PC.cases(), ids=lambda c: c[0])
+@pytest.mark.parametrize("case", PC.cases() + [PC.chorus(False), PC.chorus(True)], ids=lambda c: c[0])
 def test_generated_kernel_compiles_for_sm100a(case):
     name, d, params, inputs, exact, taps = case
     src = capi.patch_codegen(d, compile=True)
