@@ -40,6 +40,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+os.environ.setdefault("MXB_PATCH_CACHE", os.path.join(ROOT, ".mxb_cache"))      # compiled patch kernels stay inside the repository
 
 BLOCK = 1024
 SR = 48000

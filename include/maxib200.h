@@ -248,7 +248,9 @@ int64_t mxb_bank_launch_count(const mxb_bank* bank);
  *   MXB_PATCH_FUSED (default)  the library writes the CUDA source of ONE kernel for exactly this stage list -- stage state and
  *                              parameters in registers, constants as literals, coefficient designs whose arguments do not
  *                              change within a block hoisted out of the sample loop -- compiles it for sm_100a with NVRTC on
- *                              first use (about a second, once per patch) and launches it like the built-in kernels;
+ *                              first use (about a second, once per distinct program: compiled kernels are kept in the process and, as cubin
+ *                              files, under $MXB_PATCH_CACHE | $XDG_CACHE_HOME/maxib200 | ~/.cache/maxib200; MXB_PATCH_CACHE=0: no files) and
+ *                              launches it like the built-in kernels;
  *   MXB_PATCH_INTERPRET        one interpreting kernel walks the stage list (warp-uniform dispatch: every voice runs the same
  *                              program), registers / parameters / state in shared memory. No run-time compiler needed.
  * Neither is a CPU path; a fused patch on a box without libnvrtc.so.12 fails with MXB_ERR_UNSUPPORTED and says so.

@@ -6,6 +6,9 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
+# compiled patch kernels of the test runs stay inside the repository (the library's default is ~/.cache/maxib200); the directory does not
+# travel to the GPU box (.gpurunignore), so the run-time compiler is exercised there
+os.environ.setdefault("MXB_PATCH_CACHE", os.path.join(ROOT, ".mxb_cache"))
 
 
 def pytest_configure(config):

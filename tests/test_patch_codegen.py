@@ -46,6 +46,28 @@ def test_input_element_types_are_part_of_the_program():
         assert np.array_equal((w[:, v // 32] >> np.uint32(v % 32)) & 1, x[:, v].astype(np.uint32))
 
 
+def test_compiled_kernels_are_cached_on_disk(tmp_path, monkeypatch):
+    """the second compilation of a program (here: in the same process; in practice: the next process) reads the cubin file"""
+    import os
+    import time
+    monkeypatch.setenv("MXB_PATCH_CACHE", str(tmp_path / "cache" / "nested"))
+    d = PatchDef()
+    d.stage("osc", d.P("f"), kind="triangle", dst=R(0))
+    d.stage("filter", R(0), d.K(1234.5 + (os.getpid() % 97)), d.K(2.0), kind="hires", dst=R(1))     # a program no earlier run compiled
+    d.stage("out", R(1))
+    t0 = time.perf_counter(); capi.patch_codegen(d, compile=True); t_cold = time.perf_counter() - t0
+    files = list((tmp_path / "cache" / "nested").glob("patch_*.cubin"))
+    assert len(files) == 1 and files[0].read_bytes()[:4] == b"\x7fELF"
+    stamp = files[0].stat().st_mtime_ns
+    t0 = time.perf_counter(); capi.patch_codegen(d, compile=True); t_warm = time.perf_counter() - t0
+    assert files[0].stat().st_mtime_ns == stamp and t_warm < t_cold
+    files[0].write_bytes(b"garbage")                        # a damaged file is ignored and replaced
+    capi.patch_codegen(d, compile=True)
+    assert files[0].read_bytes()[:4] == b"\x7fELF"
+    monkeypatch.setenv("MXB_PATCH_CACHE", "0")
+    capi.patch_codegen(d, compile=True)                     # and the cache can be switched off
+
+
 def test_a_program_the_generator_rejects_is_an_error_not_a_crash():
     d = PatchDef(); d.stages.append((99, 0, -1, [-1] * 8))
     with pytest.raises(capi.MxbError):
