@@ -511,6 +511,25 @@ def bank_leg(E, args, wl_name, steps, warmup, want_mix=False, with_onbox=False, 
         res["clocks"] = E.sampler.summary(t_wall0, t_wall1)
         if with_onbox:
             onbox = onbox_peaks(torch, out)
+            # the same store pattern with next to no arithmetic: a bank of bare phasors (3 fp64 operations per voice-sample) writing the same
+            # time-major out[1024][V] -- what this box's memory system takes from V / 64 warps that each append 512 B to their own column
+            # block of one row after the other (a library fill_ is ONE linear stream)
+            try:
+                pb = capi.Bank(V, osc="phasor", filt="none", env=False, delay=False, delay_capacity=1, max_frames=BLOCK, ctx=E.ctx, sample_rate=SR)
+                pb.set("freq", p["freq"]); pb.set("phase", p["phase"])
+                for _ in range(3):
+                    pb.process_device(BLOCK, out_ptr=out.data_ptr(), mix_ptr=None, f32=args.f32_out, stream=stream.cuda_stream)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                for _ in range(10):
+                    pb.process_device(BLOCK, out_ptr=out.data_ptr(), mix_ptr=None, f32=args.f32_out, stream=stream.cuda_stream)
+                e1.record(stream)
+                torch.cuda.synchronize()
+                onbox["pattern_write_gbs"] = (4.0 if args.f32_out else 8.0) * samples_per_step * 10 / (e0.elapsed_time(e1) * 1e-3) / 1e9
+                res["roofline"]["frac_of_onbox_pattern_write"] = achieved / onbox["pattern_write_gbs"]
+                del pb
+            except Exception as e:      # a missing number must not take the bench line down
+                onbox["pattern_write_error"] = str(e)[:200]
             res["roofline"]["onbox_peaks"] = onbox
             if "fill_gbs" in onbox:
                 res["roofline"]["frac_of_onbox_fill"] = achieved / onbox["fill_gbs"]
