@@ -201,8 +201,9 @@ int32_t mxb_bank_process(mxb_bank* bank, int32_t n_frames,
 /* The same block with a per-sample oscillator frequency freq_tv[t][v] (n_frames x voices doubles, in the memory the
  * gates live in; NULL = the block-constant MXB_P_FREQ). The reference takes the frequency by argument on every
  * sample, so a patch may modulate it at audio rate -- FM: osc.sinewave(440 + lfo.sinewave(1)*100),
- * cpp/commandline/maximilian_examples/5.FM1/main.cpp:29. Costs one 8-byte read per voice-sample. Built for
- * oscillator -> [envelope] -> [filter] -> out / mix chains; with a delay stage it returns MXB_ERR_UNSUPPORTED (use a voice patch). */
+ * cpp/commandline/maximilian_examples/5.FM1/main.cpp:29. Costs one 8-byte read per voice-sample. Works on every bank
+ * chain, oscillator -> [envelope] -> [filter] -> [delay line] -> out / mix (with a delay stage the staged-window kernel runs a
+ * modulated instantiation of its window body). */
 int32_t mxb_bank_process_fm(mxb_bank* bank, int32_t n_frames, const double* freq_tv,
                             const int32_t* trig_on, const int32_t* trig_off,
                             void* out, int32_t out_dtype, double* mix,
@@ -212,10 +213,11 @@ int32_t mxb_bank_process_fm(mxb_bank* bank, int32_t n_frames, const double* freq
  * play() on every sample (src/maximilian.h:1287-1290): a swept filter. The coefficient design (cos/sqrt/pow, tan) then
  * runs per sample on the device -- libdevice instead of glibc, so results agree to rounding of those functions (asserted
  * at 1e-9 relative) instead of bit for bit. The modulation lasts for this call; MXB_P_CUTOFF is in force again afterwards.
- * maxiBiquad (whose set() is a design routine, not a per-sample argument) and delay stages: MXB_ERR_UNSUPPORTED (voice patches cover both).
+ * maxiBiquad (whose set() is a design routine, not a per-sample argument): MXB_ERR_UNSUPPORTED (a voice patch covers it). Chains with
+ * a delay stage take freq_tv / cutoff_tv like the others.
  * delay_size_tv[t][v] (integral values, 1 .. delay_taps): the `size` argument of maxiDelayline::dl / dlFromPosition, which a
  * flanger or chorus changes on every call (maxiFlanger::flange, src/maximilian.h:1144-1180). Works on any chain with a
- * delay stage (not together with freq_tv / cutoff_tv); the ring is then addressed slot by slot in HBM (the staged-window
+ * delay stage, also together with freq_tv / cutoff_tv; the ring is then addressed slot by slot in HBM (the staged-window
  * schedule needs a size that holds for a block), indices exactly as the reference computes them. */
 typedef struct {
     const double* freq_tv;        /* [n_frames][voices] or NULL */

@@ -673,7 +673,72 @@ private:
     std::vector<double> out_;
 };
 
-/* maxiFFT, src/libs/maxiFFT.h:46-120: process() takes one block of samples per channel instead of one sample */
+class maxiFFT;
+
+/* maxiFFTOctaveAnalyzer, src/libs/maxiFFT.h:162-205, maxiFFT.cpp:201-300. Here calculate() is an epilogue of the transform: the analyser is
+ * attached to a maxiFFT (fft.attach(oct), before or after setup()), whose process() then runs it for every frame it fires, on the device,
+ * while the magnitudes are on chip. The public members keep the reference's names: peakHoldTime, peakDecayRate, linearEQIntercept and
+ * linearEQSlope are read at every process(); `averages` / `peaks` point at the LAST fired frame of channel 0 (what a reference patch reads
+ * after calculate()), averagesOf(c, f) / peaksOf(c, f) at any frame of the last call. nAverages is known once both setup() and attach()
+ * have happened. calculate(fftData) is kept for source compatibility: it accepts the attached transform's own magnitudes (the values are
+ * already there) and rejects any other pointer -- there is no stand-alone analyser kernel. */
+class maxiFFTOctaveAnalyzer {
+public:
+    float samplingRate = 0.f;
+    int nSpectrum = 0, nAverages = 0, nAveragesPerOctave = 0;
+    float* averages = nullptr;
+    float* peaks = nullptr;
+    int peakHoldTime = 0;                                   /* setup()'s values, src/libs/maxiFFT.cpp:257-261 */
+    float peakDecayRate = 0.9f, linearEQIntercept = 1.0f, linearEQSlope = 0.0f;
+    maxiFFTOctaveAnalyzer() {}
+    ~maxiFFTOctaveAnalyzer() { if (h_) mxb_octave_destroy(h_); }
+    maxiFFTOctaveAnalyzer(const maxiFFTOctaveAnalyzer&) = delete;
+    void setup(float samplingRate_, int nBandsInTheFFT, int nAveragesPerOctave_) {
+        samplingRate = samplingRate_; nSpectrum = nBandsInTheFFT; nAveragesPerOctave = nAveragesPerOctave_ == 0 ? 1 : nAveragesPerOctave_;
+        peakHoldTime = 0; peakDecayRate = 0.9f; linearEQIntercept = 1.0f; linearEQSlope = 0.0f;
+        isSetup_ = true;
+        create();
+    }
+    inline void calculate(const float* fftData);
+    const float* averagesOf(int channel, int frame) const { return avg_.data() + ((size_t)channel * (size_t)maxf_ + (size_t)frame) * (size_t)nAverages; }
+    const float* peaksOf(int channel, int frame) const { return pk_.data() + ((size_t)channel * (size_t)maxf_ + (size_t)frame) * (size_t)nAverages; }
+private:
+    friend class maxiFFT;
+    inline void create();
+    maxiFFT* fft_ = nullptr;
+    mxb_octave* h_ = nullptr;
+    bool isSetup_ = false;
+    int maxf_ = 0;
+    std::vector<float> avg_, pk_;
+};
+
+/* maxiBarkScaleAnalyser / maxiBark, src/libs/maxiBark.h:36-128: likewise an epilogue of an attached maxiFFT (fft.attach(bark)); setup(sR, bS)
+ * must name the transform's own sample rate and size. specificLoudness / relativeLoudness / totalLoudness return the values of the LAST
+ * fired frame of channel 0 and accept the attached transform's magnitudes only (any other pointer is rejected); ...Of(c, f) reach the rest. */
+template <class T>
+class maxiBarkScaleAnalyser {
+public:
+    int NUM_BARK_BANDS = 24;
+    void setup(unsigned int sR, unsigned int bS) { sampleRate_ = sR; bufferSize_ = bS; isSetup_ = true; }
+    inline double* specificLoudness(const float* normalisedSpectrum);
+    inline double* relativeLoudness(const float* normalisedSpectrum);
+    inline double* totalLoudness(const float* normalisedSpectrum);
+    const double* specificLoudnessOf(int channel, int frame) const { return spec_.data() + ((size_t)channel * (size_t)maxf_ + (size_t)frame) * 24; }
+    const double* relativeLoudnessOf(int channel, int frame) const { return rel_.data() + ((size_t)channel * (size_t)maxf_ + (size_t)frame) * 24; }
+    double totalLoudnessOf(int channel, int frame) const { return tot_[(size_t)channel * (size_t)maxf_ + (size_t)frame]; }
+private:
+    friend class maxiFFT;
+    inline void own(const float* spectrum, const char* who) const;
+    maxiFFT* fft_ = nullptr;
+    unsigned int sampleRate_ = 0, bufferSize_ = 0;
+    bool isSetup_ = false;
+    int maxf_ = 0, last_ = -1;
+    std::vector<double> spec_, rel_, tot_;
+};
+typedef maxiBarkScaleAnalyser<double> maxiBark;
+
+/* maxiFFT, src/libs/maxiFFT.h:46-120: process() takes one block of samples per channel, or -- the reference's signature, for a
+ * single channel -- one sample */
 class maxiFFT {
 public:
     enum fftModes { NO_POLAR_CONVERSION = 0, WITH_POLAR_CONVERSION = 1 };
@@ -686,11 +751,37 @@ public:
         check(mxb_ctx_create(device_, (int32_t)maxiSettings::sampleRate, &ctx_), "mxb_ctx_create");
         check(mxb_stft_create(ctx_, C_, fftSize, hopSize, &h_), "mxb_stft_create");
         fftSize_ = fftSize; hop_ = hopSize; bins_ = fftSize / 2;
+        /* the reference's magnitudes / phases exist (as zeros) before the first frame: a patch may hand them to maxiIFFT at once */
+        mags_.assign((size_t)C_ * (size_t)bins_, 0.f); phases_.assign((size_t)C_ * (size_t)bins_, 0.f); maxf_ = 1;
+        hopbuf_.clear(); hopbuf_.reserve((size_t)hop_);
+        if (oct_) oct_->create();
     }
+    /* bool process(float value, fftModes mode), src/libs/maxiFFT.cpp:65-91 -- the reference's per-sample signature, for a transform of
+     * ONE channel: the samples of a hop are collected on the host (no arithmetic) and handed over together; true on the sample that
+     * completes a frame, exactly where the reference returns it (the first frame fires after hopSize samples, maxiFFT.cpp:55). Afterwards
+     * getMagnitudes() / getPhases() hold that frame's numBins values, as in the reference. */
+    bool process(float value, fftModes mode = WITH_POLAR_CONVERSION) {
+        if (C_ != 1) throw maxiError(MXB_ERR_INVALID, "maxiFFT::process(float): one sample per call feeds a transform of one channel; use process(values, nSamples)");
+        if (!h_) throw maxiError(MXB_ERR_STATE, "maxiFFT::process before setup()");
+        hopbuf_.push_back(value);
+        if ((int)hopbuf_.size() < hop_) return false;
+        const bool fired = process(hopbuf_.data(), hop_, mode, 1);
+        hopbuf_.clear();
+        return fired;
+    }
+    /* the spectral analysers of the reference as epilogues of this transform (computed by the same kernel, per fired frame) */
+    void attach(maxiFFTOctaveAnalyzer& o) { oct_ = &o; o.fft_ = this; if (h_) o.create(); }
+    void attach(maxiBark& b) { bark_ = &b; b.fft_ = this; }
+    /* magnitudes of frame f (of the last call) of channel c */
+    const float* magnitudesOf(int channel, int frame) const { return mags_.data() + ((size_t)channel * (size_t)maxf_ + (size_t)frame) * (size_t)bins_; }
+    mxb_ctx* context() { return ctx_; }
+    int channels() const { return C_; }
     /* values: planar [channels][nSamples] (host). Returns true when at least one new frame fired (the reference
-     * returns true on the sample that completes a frame); frames() tells how many per channel. */
-    bool process(const float* values, int nSamples, fftModes mode = WITH_POLAR_CONVERSION) {
-        const int maxf = nSamples / hop_ + 2;
+     * returns true on the sample that completes a frame); frames() tells how many per channel. maxFrames: rows per channel of the
+     * result arrays (0 = enough for any nSamples). */
+    bool process(const float* values, int nSamples, fftModes mode = WITH_POLAR_CONVERSION, int maxFrames = 0) {
+        if (!h_) throw maxiError(MXB_ERR_STATE, "maxiFFT::process before setup()");
+        const int maxf = maxFrames > 0 ? maxFrames : nSamples / hop_ + 2;
         const size_t len = (size_t)C_ * (size_t)maxf * (size_t)bins_;
         const bool polar = mode == WITH_POLAR_CONVERSION;
         re_.resize(len); im_.resize(len);
@@ -705,9 +796,36 @@ public:
         o.flatness = polar ? flatness_.data() : nullptr; o.centroid = polar ? centroid_.data() : nullptr;
         o.coeffs = nullptr;
         int32_t nf = 0;
-        maxib200_detail::check(mxb_stft_process2(h_, values, nSamples, 1, nSamples, maxf, &o, nullptr, &nf, MXB_MEM_HOST, nullptr),
-                               "mxb_stft_process2");
+        const bool post = polar && ((oct_ && oct_->h_) || bark_);
+        if (!polar && (oct_ || bark_)) throw maxiError(MXB_ERR_INVALID, "maxiFFT::process: the attached analysers read magnitudes (WITH_POLAR_CONVERSION)");
+        if (post) {
+            mxb_stft_post q;
+            std::memset(&q, 0, sizeof(q));
+            if (oct_ && oct_->h_) {
+                maxiFFTOctaveAnalyzer& a = *oct_;
+                maxib200_detail::check(mxb_octave_config(a.h_, a.peakHoldTime, a.peakDecayRate, a.linearEQIntercept, a.linearEQSlope), "mxb_octave_config");
+                const size_t na = (size_t)C_ * (size_t)maxf * (size_t)(a.nAverages > 0 ? a.nAverages : 1);
+                a.avg_.resize(na); a.pk_.resize(na); a.maxf_ = maxf;
+                q.octave = a.h_; q.octave_averages = a.avg_.data(); q.octave_peaks = a.pk_.data();
+            }
+            if (bark_) {
+                maxiBark& b = *bark_;
+                if (!b.isSetup_) throw maxiError(MXB_ERR_STATE, "maxiBark attached but never setup()");
+                if (b.sampleRate_ != (unsigned)maxiSettings::sampleRate || b.bufferSize_ != (unsigned)fftSize_)
+                    throw maxiError(MXB_ERR_UNSUPPORTED, "maxiBark::setup(sR, bS) must name the attached transform's sample rate and fft size");
+                const size_t nb = (size_t)C_ * (size_t)maxf;
+                b.spec_.resize(nb * 24); b.rel_.resize(nb * 24); b.tot_.resize(nb); b.maxf_ = maxf;
+                q.bark = 1; q.bark_specific = b.spec_.data(); q.bark_relative = b.rel_.data(); q.bark_total = b.tot_.data();
+            }
+            maxib200_detail::check(mxb_stft_process3(h_, values, nSamples, 1, nSamples, maxf, &o, &q, nullptr, &nf, MXB_MEM_HOST, nullptr),
+                                   "mxb_stft_process3");
+        } else {
+            maxib200_detail::check(mxb_stft_process2(h_, values, nSamples, 1, nSamples, maxf, &o, nullptr, &nf, MXB_MEM_HOST, nullptr),
+                                   "mxb_stft_process2");
+        }
         frames_ = nf; maxf_ = maxf;
+        if (oct_ && oct_->h_ && nf > 0) { oct_->averages = const_cast<float*>(oct_->averagesOf(0, nf - 1)); oct_->peaks = const_cast<float*>(oct_->peaksOf(0, nf - 1)); }
+        if (bark_) bark_->last_ = nf > 0 ? nf - 1 : -1;
         return nf > 0;
     }
     int frames() const { return frames_; }
@@ -729,8 +847,30 @@ private:
     int C_, device_;
     mxb_ctx* ctx_ = nullptr; mxb_stft* h_ = nullptr;
     int fftSize_ = 0, hop_ = 0, bins_ = 0, frames_ = 0, maxf_ = 0;
-    std::vector<float> mags_, phases_, re_, im_, magsdb_, flatness_, centroid_;
+    std::vector<float> mags_, phases_, re_, im_, magsdb_, flatness_, centroid_, hopbuf_;
+    maxiFFTOctaveAnalyzer* oct_ = nullptr;
+    maxiBark* bark_ = nullptr;
 };
+
+inline void maxiFFTOctaveAnalyzer::create() {
+    if (!isSetup_ || !fft_ || !fft_->context()) return;
+    if (h_) { mxb_octave_destroy(h_); h_ = nullptr; }
+    maxib200_detail::check(mxb_octave_create(fft_->context(), fft_->channels(), samplingRate, nSpectrum, nAveragesPerOctave, &h_), "mxb_octave_create");
+    nAverages = mxb_octave_n_averages(h_);
+}
+inline void maxiFFTOctaveAnalyzer::calculate(const float* fftData) {
+    if (!h_ || !fft_ || fft_->frames() <= 0) throw maxiError(MXB_ERR_STATE, "maxiFFTOctaveAnalyzer::calculate: attach the analyser to a maxiFFT; its process() runs it per frame");
+    if (fftData != fft_->magnitudesOf(0, fft_->frames() - 1) && fftData != fft_->magnitudesOf(0, 0))
+        throw maxiError(MXB_ERR_UNSUPPORTED, "maxiFFTOctaveAnalyzer::calculate: only the attached transform's own magnitudes can be analysed");
+}
+template <class T> inline void maxiBarkScaleAnalyser<T>::own(const float* spectrum, const char* who) const {
+    if (!fft_ || last_ < 0) throw maxiError(MXB_ERR_STATE, std::string(who) + ": attach the analyser to a maxiFFT; its process() runs it per frame");
+    if (spectrum != fft_->magnitudesOf(0, last_) && spectrum != fft_->magnitudesOf(0, 0))
+        throw maxiError(MXB_ERR_UNSUPPORTED, std::string(who) + ": only the attached transform's own magnitudes can be analysed");
+}
+template <class T> inline double* maxiBarkScaleAnalyser<T>::specificLoudness(const float* sp) { own(sp, "maxiBark::specificLoudness"); return const_cast<double*>(specificLoudnessOf(0, last_)); }
+template <class T> inline double* maxiBarkScaleAnalyser<T>::relativeLoudness(const float* sp) { own(sp, "maxiBark::relativeLoudness"); return const_cast<double*>(relativeLoudnessOf(0, last_)); }
+template <class T> inline double* maxiBarkScaleAnalyser<T>::totalLoudness(const float* sp) { own(sp, "maxiBark::totalLoudness"); return &tot_[(size_t)last_]; }
 
 /* maxiIFFT (SPECTRUM mode), src/libs/maxiFFT.h:125-156; COMPLEX mode yields zeros in the reference on Linux and is not offered */
 class maxiIFFT {
@@ -753,11 +893,26 @@ public:
         maxib200_detail::check(mxb_istft_process(h_, data1.data(), data2.data(), frames, out_.data(), MXB_MEM_HOST, nullptr), "mxb_istft_process");
         return out_;
     }
+    /* float process(mags, phases, mode), src/libs/maxiFFT.cpp:154-192 -- the reference's per-sample signature, for ONE channel: the spectrum is
+     * read on the first call of every hop (pos == 0, like the reference), that frame is resynthesised and overlap-added on the device, and its
+     * hop samples are handed out one per call. */
+    float process(std::vector<float>& mags, std::vector<float>& phases, fftModes = SPECTRUM) {
+        if (C_ != 1) throw maxiError(MXB_ERR_INVALID, "maxiIFFT::process per sample feeds one channel; use process(mags, phases, frames)");
+        if (!h_) throw maxiError(MXB_ERR_STATE, "maxiIFFT::process before setup()");
+        if (pos_ == 0) {
+            if ((int)mags.size() < bins_ || (int)phases.size() < bins_) throw maxiError(MXB_ERR_INVALID, "maxiIFFT::process: magnitudes / phases shorter than numBins");
+            cur_.resize((size_t)hop_);
+            maxib200_detail::check(mxb_istft_process(h_, mags.data(), phases.data(), 1, cur_.data(), MXB_MEM_HOST, nullptr), "mxb_istft_process");
+        }
+        const float v = cur_[(size_t)pos_];
+        if (++pos_ == hop_) pos_ = 0;
+        return v;
+    }
     int getNumBins() { return bins_; }
 private:
     int C_, device_;
-    mxb_ctx* ctx_ = nullptr; mxb_istft* h_ = nullptr; int hop_ = 0, bins_ = 0;
-    std::vector<float> out_;
+    mxb_ctx* ctx_ = nullptr; mxb_istft* h_ = nullptr; int hop_ = 0, bins_ = 0, pos_ = 0;
+    std::vector<float> out_, cur_;
 };
 
 #endif /* MAXIMILIAN_B200_HPP */

@@ -574,10 +574,6 @@ int32_t mxb_bank_process_mod(mxb_bank* b, int32_t n_frames, const mxb_modulation
 
     const int* d_on = trig_on; const int* d_off = trig_off;
     void* d_out = out; double* d_mix = mix;
-    if (freq_tv || cutoff_tv)
-        MXB_REQUIRE(b->desc.delay_taps == 0, MXB_ERR_UNSUPPORTED,
-                    "mxb_bank_process_mod: per-sample frequency / cutoff are built for oscillator -> [envelope] -> filter -> out/mix chains "
-                    "(a chain with a delay line: use a voice patch, mxb_patch_*)");
     if (cutoff_tv)
         MXB_REQUIRE(fk == MXB_FILT_LORES || fk == MXB_FILT_HIRES || fk == MXB_FILT_SVF, MXB_ERR_UNSUPPORTED,
                     "mxb_bank_process_mod: per-sample cutoff is built for lores / hires / maxiSVF");

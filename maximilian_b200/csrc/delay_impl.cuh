@@ -104,7 +104,7 @@ __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wa
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 struct DlVoice {
-    double phase, oout, inc, duty, pend, fb, gl, gr;
+    double phase, oout, inc, duty, pend, fb, gl, gr, res;
     FiltRegs fr;
     EnvRegs er;
     int ph, size, pos;
@@ -114,7 +114,11 @@ struct DlVoice {
 // one window (<= 16 steps) of one voice against its staged row (ALLFAST) or, for short rings, against global memory
 // ESTEADY: every voice of the warp spends this whole window in one of the two steady states of maxiEnv::adsr (see
 // dl_window); `relmode` tells which one this lane is in.
-template <int OSC, int FILT, int ENV, bool ALLFAST, int OUTMODE, bool MIX, bool ESTEADY>
+// MODW: the block carries a per-sample oscillator frequency (a.freq_tv) and / or filter cutoff (a.cutoff_tv): the reference takes both
+// by argument on every call (FM: maximilian_examples/5.FM1/main.cpp:29), so the increment / the filter design are redone each sample,
+// in the order the patch evaluates them (oscillator, envelope, design, filter). Its own instantiation of the window body: the
+// block-constant windows keep their instruction count.
+template <int OSC, int FILT, int ENV, bool ALLFAST, int OUTMODE, bool MIX, bool ESTEADY, bool MODW = false>
 __device__ __forceinline__ void dl_stage(DlVoice& s, double* row, const int tn, const int t0, const BankArgs& a, const DelayArgs& d,
                                          const size_t V, const size_t v, const int lane, const int gwarp, double* mixtile,
                                          const bool relmode, const int swz) {
@@ -123,6 +127,11 @@ __device__ __forceinline__ void dl_stage(DlVoice& s, double* row, const int tn, 
 #pragma unroll 4
     for (int j = 0; j < tn; ++j) {
         const int t = t0 + j;
+        if (MODW && a.freq_tv) {
+            const bool pb = OSC == OSC_T_GENERIC && a.osc_kind == MXB_OSC_PHASORBETWEEN;
+            const double fq = s.live ? a.freq_tv[(size_t)t * V + v] : 1.0;
+            s.inc = pb ? ((s.pend - s.duty) / (a.sr / fq)) : (1. / (a.sr / fq));
+        }
         double x = osc_tick<OSC>(s.phase, s.oout, s.inc, s.duty, a.osc_kind, s.pend);
         if (ENV && ESTEADY) {
             // what env_tick() reduces to in the steady states -- same operands, same roundings
@@ -132,6 +141,9 @@ __device__ __forceinline__ void dl_stage(DlVoice& s, double* row, const int tn, 
         } else if (ENV) {
             const bool trig = a.trig_tv ? (s.live && a.trig_tv[(size_t)t * V + v] == 1) : (t >= s.er.on && t < s.er.off);
             x = a.env_ar ? env_ar_tick(s.er, x, trig) : env_tick(s.er, x, trig);
+        }
+        if constexpr (MODW && (FILT == FILT_T_LORES || FILT == FILT_T_HIRES || FILT == FILT_T_SVF || FILT == FILT_T_SVF_LP)) {
+            if (a.cutoff_tv) filt_design<FILT>(s.fr, s.live ? a.cutoff_tv[(size_t)t * V + v] : 1000.0, s.res, a.sr);
         }
         x = filt_tick<FILT>(s.fr, x, a.svf_mix);
         // maxiDelayline::dl, src/maximilian.cpp:420-429
@@ -191,6 +203,10 @@ __device__ __forceinline__ void dl_stage(DlVoice& s, double* row, const int tn, 
 template <int OSC, int FILT, int ENV, bool ALLFAST, int OUTMODE, bool MIX>
 __device__ __forceinline__ void dl_window(DlVoice& s, double* row, const int tn, const int t0, const BankArgs& a, const DelayArgs& d,
                                           const size_t V, const size_t v, const int lane, const int gwarp, double* mixtile, const int swz) {
+    if (a.freq_tv || a.cutoff_tv) {       // warp-uniform (kernel arguments)
+        dl_stage<OSC, FILT, ENV, ALLFAST, OUTMODE, MIX, false, true>(s, row, tn, t0, a, d, V, v, lane, gwarp, mixtile, false, swz);
+        return;
+    }
     if (ENV) {
         const EnvRegs& e = s.er;
         const bool notrig = e.off <= t0 || e.on >= t0 + tn || e.on >= e.off;
@@ -235,6 +251,7 @@ __global__ void __launch_bounds__(DelayShape<MIX>::kThreads) delay_bank_kernel(c
         s.fr.c0 = a.cf[0][vv]; s.fr.c1 = a.cf[1][vv];
         if (FILT != FILT_T_LORES && FILT != FILT_T_HIRES) { s.fr.c2 = a.cf[2][vv]; s.fr.c3 = a.cf[3][vv]; s.fr.c4 = a.cf[4][vv]; }
     }
+    s.res = a.cutoff_tv ? a.res[vv] : 0.0;
     if (ENV) {
         s.er.amp = a.env_amp[vv]; s.er.output = a.env_output[vv];
         s.er.att = a.env_att[vv]; s.er.dec = a.env_dec[vv]; s.er.sus = a.env_sus[vv]; s.er.rel = a.env_rel[vv];

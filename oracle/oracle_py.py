@@ -167,8 +167,10 @@ class Bank:
             assert tv.shape == (nframes, self.V) and trig_on is None
             f = np.ascontiguousarray(freq_tv, dtype=np.float64) if freq_tv is not None else None
             cu = np.ascontiguousarray(cutoff_tv, dtype=np.float64) if cutoff_tv is not None else None
+            ds = np.ascontiguousarray(delay_size_tv, dtype=np.float64) if delay_size_tv is not None else None
+            assert ds is None or ds.shape == (nframes, self.V)
             mix = np.empty((nframes, 2), dtype=np.float64) if want_mix else None
-            rc = self.lib.mxo_bank_process_mod2(self.h, nframes, _dp(f), _dp(cu), None, tv.ctypes.data_as(C.POINTER(C.c_uint8)), None, None,
+            rc = self.lib.mxo_bank_process_mod2(self.h, nframes, _dp(f), _dp(cu), _dp(ds), tv.ctypes.data_as(C.POINTER(C.c_uint8)), None, None,
                                                 _dp(out), _dp(mix), 0, self.V)
             if rc:
                 raise RuntimeError(f"mxo_bank_process_mod2 -> {rc}")

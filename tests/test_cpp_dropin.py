@@ -149,3 +149,59 @@ def test_polysynth_port_matches_oracle(port, tmp_path):
         np.testing.assert_allclose(out[blk, :, 0], ref, rtol=1e-9, atol=1e-12, err_msg=f"blk{blk}")
         assert np.array_equal(out[blk, :, 0], out[blk, :, 1])
     assert np.abs(out).max() > 1e-3
+
+
+SRC_FX = os.path.join(ROOT, "tests", "cpp", "patch_featurex.cpp")
+EXE_FX = os.path.join(ROOT, "tests", "cpp", "patch_featurex")
+
+
+def test_per_sample_feature_extractor_compiles_against_the_dropin_header():
+    exe = compile_patch(SRC_FX, EXE_FX)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 2 and "usage" in r.stderr
+
+
+@pytest.mark.gpu
+def test_per_sample_feature_extractor_matches_oracle(port, tmp_path):
+    """The reference's per-sample idiom (`if (fft.process(x)) {...}`, `y = ifft.process(mags, phases)` every sample; maxiFFTOctaveAnalyzer /
+    maxiBark / maxiMFCC on the fired frame) through the C++ layer's scalar signatures, against the oracle: frame schedule exact, magnitudes
+    and octave averages / peaks bit-identical, Bark 1e-12, MFCC 1e-9, resynthesis 2e-5 of max (atan2f / cosf / sinf ulps)."""
+    exe = compile_patch(SRC_FX, EXE_FX)
+    N, bins, hop, nc = 6 * 1024 + 300, 512, 512, 13
+    x = W.channel_streams(1, N, seed=45)
+    x.tofile(tmp_path / "in.bin")
+    r = subprocess.run([exe, str(tmp_path / "in.bin"), str(tmp_path / "out.bin"), str(N)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    raw = open(tmp_path / "out.bin", "rb").read()
+    F, nA = (int(v) for v in np.frombuffer(raw, dtype=np.int32, count=2)); off = 8
+
+    def take(dtype, shape):
+        nonlocal off
+        n = int(np.prod(shape)); a = np.frombuffer(raw, dtype=dtype, count=n, offset=off).reshape(shape)
+        off += a.nbytes
+        return a
+    fired, mags = take(np.float32, (N,)), take(np.float32, (1, F, bins))
+    avs, pks = take(np.float32, (1, F, nA)), take(np.float32, (1, F, nA))
+    spec, rel, tot = take(np.float64, (1, F, 24)), take(np.float64, (1, F, 24)), take(np.float64, (1, F))
+    co, y = take(np.float64, (1, F, nc)), take(np.float32, (N,))
+    assert off == len(raw)
+
+    assert F == N // hop and np.array_equal(np.nonzero(fired)[0], hop * np.arange(1, F + 1) - 1)   # true on the sample that completes a frame
+    o = port.Stft(1, 1024, hop).process(x)
+    assert np.array_equal(mags, o["mags"][:, :F])
+    ooc = port.Octave(1, 48000, bins, 3); ooc.config(2, 0.8, 0.9, 0.01)
+    assert ooc.n_averages == nA
+    oav, opk = ooc.process(o["mags"][:, :F])
+    assert np.array_equal(avs, oav) and np.array_equal(pks, opk)
+    sp, rl, tt = port.bark(o["mags"][:, :F], 48000, 1024)
+    np.testing.assert_allclose(spec, sp, rtol=1e-12, atol=0)
+    np.testing.assert_allclose(rel, rl, rtol=1e-12, atol=0)
+    np.testing.assert_allclose(tot, tt, rtol=1e-12, atol=0)
+    oc, _ = port.Mfcc(bins, 42, nc, 20.0, 20000.0, 48000).process(o["mags"][:, :F])
+    np.testing.assert_allclose(co, oc, rtol=1e-9, atol=1e-12)
+    # maxiIFFT::process reads the spectrum on the first sample of every hop: zeros before the first frame, then frame k - 1 during hop k
+    K = (N + hop - 1) // hop
+    zm = np.zeros((1, 1, bins), dtype=np.float32)
+    oy = port.Istft(1, 1024, hop).process(np.concatenate([zm, o["mags"][:, :K - 1]], axis=1), np.concatenate([zm, o["phases"][:, :K - 1]], axis=1))
+    assert np.abs(y - oy[0, :N]).max() <= 2e-5 * np.abs(oy).max()
+    assert np.abs(y[hop:]).max() > 1e-3

@@ -270,11 +270,46 @@ def test_delay_with_filter_and_nonpositive_size(port, osc):
         assert np.array_equal(g.get("delay_phase"), o.get("delay_phase"))
 
 
-def test_per_sample_frequency_with_a_delay_line_is_refused():
-    g = gpu_bank(8, osc="saw", env=True, delay=True, delay_capacity=64, max_frames=16)
-    g.set("delay_size", 32.0)
-    with pytest.raises(capi.MxbError):
-        g.process(16, freq_tv=np.full((16, 8), 100.0))
+@pytest.mark.parametrize("osc,filt,env,ragged,cm,dsz", [("saw", "none", True, False, False, False), ("saw", "lores", True, True, True, False),
+                                                        ("pulse", "svf", False, False, True, False), ("phasorbetween", "biquad", True, True, False, False),
+                                                        ("sinewave", "hires", False, False, True, True)])
+def test_modulated_frequency_and_cutoff_with_a_delay_line(port, osc, filt, env, ragged, cm, dsz):
+    """per-sample frequency / cutoff on a chain WITH a delay line run on the staged-window kernel (K2), uniform and
+    generic schedules, with the envelope's per-sample trigger and (last case) a per-sample delay size on top. Ring contents and the
+    ring index are compared too."""
+    from test_oracle_vs_reference import cutoff_sweeps, fm_frequencies
+    V, B, cap = 173, 200, 128
+    p = W.voice_params(V, seed=61, delay_size=cap, ragged_delay=ragged)
+    g = gpu_bank(V, osc=osc, filt=filt, env=env, delay=True, delay_capacity=cap, max_frames=B)
+    o = port.Bank(V, osc=osc, filt=filt, env=env, delay=True, delay_capacity=cap)
+    W.configure_bank(g, filt, p, env, True); W.configure_bank(o, filt, p, env, True)
+    exact = not cm and osc not in TRIG
+    for blk in range(3):
+        f = fm_frequencies(V, B, blk); cu = cutoff_sweeps(V, B, blk) if cm else None
+        tv = trigger_bytes(V, B, blk, seed=7) if env else None
+        sz = None
+        if dsz:
+            sz = np.floor(1 + (cap - 1) * np.random.default_rng(90 + blk).random((B, V)))
+        og, mg = g.process(B, freq_tv=f, cutoff_tv=cu, trig_tv=tv, delay_size_tv=sz, want_mix=True)
+        oo, mo = o.process(B, freq_tv=f, cutoff_tv=cu, trig_tv=tv, delay_size_tv=sz, want_mix=True)
+        if exact:
+            assert np.array_equal(og, oo), f"blk{blk}"
+        else:
+            np.testing.assert_allclose(og, oo, rtol=1e-9, atol=1e-12, err_msg=f"blk{blk}")
+        np.testing.assert_allclose(mg, mo, rtol=1e-9, atol=1e-11)
+        assert np.array_equal(g.get("delay_phase"), o.get("delay_phase")), blk
+    on, off = (W.gate(V, B, 3) if env else (None, None))
+    og, _ = g.process(B, on, off); oo, _ = o.process(B, on, off)      # block-constant parameters are in force again
+    if exact:
+        assert np.array_equal(og, oo)
+    else:
+        np.testing.assert_allclose(og, oo, rtol=1e-9, atol=1e-12)
+    for v in (0, 1, 31, 32, V // 2, V - 1):
+        rg, ro = g.ring(v, cap), o.ring(v, cap)
+        if exact:
+            assert np.array_equal(rg, ro), v
+        else:
+            np.testing.assert_allclose(rg, ro, rtol=1e-9, atol=1e-12, err_msg=f"ring of voice {v}")
 
 
 def trigger_bytes(V, B, blk, seed=0):
@@ -387,8 +422,8 @@ def test_per_sample_cutoff_refused_where_not_built():
     g.set("cutoff", 500.0); g.set("resonance", 1.0); g.set("gain", 0.0)
     with pytest.raises(capi.MxbError):
         g.process(16, cutoff_tv=np.full((16, 8), 300.0))
-    g = gpu_bank(8, osc="saw", filt="svf", delay=True, delay_capacity=64, max_frames=16)
-    g.set("delay_size", 32.0)
+    g = gpu_bank(8, osc="saw", filt="biquad", delay=True, delay_capacity=64, max_frames=16)
+    g.set("cutoff", 500.0); g.set("resonance", 1.0); g.set("gain", 0.0); g.set("delay_size", 32.0)
     with pytest.raises(capi.MxbError):
         g.process(16, cutoff_tv=np.full((16, 8), 300.0))
 
