@@ -12,14 +12,26 @@ int launch_delay_bank(const BankArgs& a_in, DelayArgs& d, int filt_kind, bool sv
     d.W_out = a.W;
     const int saw = a.osc_kind == MXB_OSC_SAW;
     const int outmode = !out ? 0 : (a.out_f32 ? 2 : 1);      // DL_OUT_NONE / F64 / F32
-    switch (filt_kind) {
-        case MXB_FILT_NONE:   return launch_delay_none(a, d, saw, env, outmode, mix, grid, s);
-        case MXB_FILT_LORES:  return launch_delay_lores(a, d, saw, env, outmode, mix, grid, s);
-        case MXB_FILT_HIRES:  return launch_delay_hires(a, d, saw, env, outmode, mix, grid, s);
-        case MXB_FILT_SVF:    return svf_lp ? launch_delay_svf_lp(a, d, saw, env, outmode, mix, grid, s)
-                                            : launch_delay_svf(a, d, saw, env, outmode, mix, grid, s);
-        case MXB_FILT_BIQUAD: return launch_delay_biquad(a, d, saw, env, outmode, mix, grid, s);
-        default: break;
+    if (a.freq_tv || a.cutoff_tv) {      // per-sample frequency / cutoff: the modulated instantiations
+        switch (filt_kind) {
+            case MXB_FILT_NONE:   return launch_delay_none_mod(a, d, saw, env, outmode, mix, grid, s);
+            case MXB_FILT_LORES:  return launch_delay_lores_mod(a, d, saw, env, outmode, mix, grid, s);
+            case MXB_FILT_HIRES:  return launch_delay_hires_mod(a, d, saw, env, outmode, mix, grid, s);
+            case MXB_FILT_SVF:    return svf_lp ? launch_delay_svf_lp_mod(a, d, saw, env, outmode, mix, grid, s)
+                                                : launch_delay_svf_mod(a, d, saw, env, outmode, mix, grid, s);
+            case MXB_FILT_BIQUAD: return launch_delay_biquad_mod(a, d, saw, env, outmode, mix, grid, s);
+            default: break;
+        }
+    } else {
+        switch (filt_kind) {
+            case MXB_FILT_NONE:   return launch_delay_none(a, d, saw, env, outmode, mix, grid, s);
+            case MXB_FILT_LORES:  return launch_delay_lores(a, d, saw, env, outmode, mix, grid, s);
+            case MXB_FILT_HIRES:  return launch_delay_hires(a, d, saw, env, outmode, mix, grid, s);
+            case MXB_FILT_SVF:    return svf_lp ? launch_delay_svf_lp(a, d, saw, env, outmode, mix, grid, s)
+                                                : launch_delay_svf(a, d, saw, env, outmode, mix, grid, s);
+            case MXB_FILT_BIQUAD: return launch_delay_biquad(a, d, saw, env, outmode, mix, grid, s);
+            default: break;
+        }
     }
     set_error("launch_delay_bank: filt_kind %d", filt_kind);
     return MXB_ERR_UNSUPPORTED;

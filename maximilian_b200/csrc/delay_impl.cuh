@@ -58,11 +58,19 @@ constexpr int kDlAhead = MXB_DL_AHEAD;            // the bulk path requests this
 constexpr int kDlSlack = kDlStages - 1 - kDlAhead;
 static_assert(kDlStages >= 2 && kDlStages <= 8 && kDlAhead >= 1 && kDlSlack >= 0 && kDlSlack <= 2, "stages / ahead");
 constexpr int kDlVoicesPerReq = 32 / kDlT;        // voices covered by one cooperative request (2)
-constexpr int kMixDoubles = 2 * kMixTT * 33;
+// Rows (steps) of the per-warp mix tile of K2. The tile costs shared memory the window stages compete for: with 16 rows a 4-warp CTA
+// needs 65 KB (3 CTAs = 12 warps per SM), with 8 rows 48.5 KB (4 CTAs = 16 warps per SM) at twice the row-sum instructions -- K2 has
+// the fp64 slots for them (fp64 pipe 15 %), unlike K1.
+#ifndef MXB_DL_MIXROWS
+#define MXB_DL_MIXROWS 16
+#endif
+constexpr int kDlMixRows = MXB_DL_MIXROWS;
+static_assert(kDlMixRows == 8 || kDlMixRows == 16, "mix tile rows");
+constexpr int kMixDoubles = 2 * kDlMixRows * 33;
 constexpr int kFastMinSize = 2 * kDlT;
 constexpr unsigned kFull = 0xffffffffu;
 enum { DL_OUT_NONE = 0, DL_OUT_F64 = 1, DL_OUT_F32 = 2 };
-static_assert(kDlT <= kMixTT, "one staged window fits one mix tile");
+static_assert(kDlT % kDlMixRows == 0, "a staged window is a whole number of mix tiles");
 
 __device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc) {
     const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -116,16 +124,20 @@ struct DlVoice {
 // dl_window); `relmode` tells which one this lane is in.
 // MODW: the block carries a per-sample oscillator frequency (a.freq_tv) and / or filter cutoff (a.cutoff_tv): the reference takes both
 // by argument on every call (FM: maximilian_examples/5.FM1/main.cpp:29), so the increment / the filter design are redone each sample,
-// in the order the patch evaluates them (oscillator, envelope, design, filter). Its own instantiation of the window body: the
-// block-constant windows keep their instruction count.
+// in the order the patch evaluates them (oscillator, envelope, design, filter). Its own instantiation of the window body;
+// modulated blocks run their own instantiation of the KERNEL (MODK; delay_km_*.cu), so the block-constant kernels are compiled exactly
+// as before (with both bodies in one kernel the headline instantiation measured 3 % slower: 0.830 against 0.855, run Z).
 template <int OSC, int FILT, int ENV, bool ALLFAST, int OUTMODE, bool MIX, bool ESTEADY, bool MODW = false>
 __device__ __forceinline__ void dl_stage(DlVoice& s, double* row, const int tn, const int t0, const BankArgs& a, const DelayArgs& d,
                                          const size_t V, const size_t v, const int lane, const int gwarp, double* mixtile,
                                          const bool relmode, const int swz) {
     double* out64 = (double*)a.out + (size_t)t0 * V + v;
     float* out32 = (float*)a.out + (size_t)t0 * V + v;
+    for (int jb = 0; jb < tn; jb += kDlMixRows) {         // one mix tile (the whole window when the tile has 16 rows)
+    const int jn = min(kDlMixRows, tn - jb);
 #pragma unroll 4
-    for (int j = 0; j < tn; ++j) {
+    for (int jj = 0; jj < jn; ++jj) {
+        const int j = jb + jj;
         const int t = t0 + j;
         if (MODW && a.freq_tv) {
             const bool pb = OSC == OSC_T_GENERIC && a.osc_kind == MXB_OSC_PHASORBETWEEN;
@@ -175,21 +187,22 @@ __device__ __forceinline__ void dl_stage(DlVoice& s, double* row, const int tn, 
         if (OUTMODE == DL_OUT_F64) { if (s.live) __stcs(out64, y); out64 += V; }
         if (OUTMODE == DL_OUT_F32) { if (s.live) __stcs(out32, (float)y); out32 += V; }
         if (MIX) {
-            mixtile[(0 * kMixTT + j) * 33 + lane] = y * s.gl;
-            mixtile[(1 * kMixTT + j) * 33 + lane] = y * s.gr;
+            mixtile[(0 * kDlMixRows + jj) * 33 + lane] = y * s.gl;
+            mixtile[(1 * kDlMixRows + jj) * 33 + lane] = y * s.gr;
         }
     }
     if (MIX) {
         __syncwarp();
-        const int ch = lane >> 4, rw = lane & 15;
-        if (rw < tn) {
-            const double* r = mixtile + (ch * kMixTT + rw) * 33;
+        const int ch = lane / kDlMixRows, rw = lane % kDlMixRows;
+        if (ch < 2 && rw < jn) {
+            const double* r = mixtile + (ch * kDlMixRows + rw) * 33;
             double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;       // fixed order: deterministic
 #pragma unroll
             for (int q = 0; q < 32; q += 4) { s0 += r[q]; s1 += r[q + 1]; s2 += r[q + 2]; s3 += r[q + 3]; }
-            a.partials[((size_t)(t0 + rw) * 2 + ch) * (size_t)a.W + (size_t)gwarp] = (s0 + s1) + (s2 + s3);
+            a.partials[((size_t)(t0 + jb + rw) * 2 + ch) * (size_t)a.W + (size_t)gwarp] = (s0 + s1) + (s2 + s3);
         }
         __syncwarp();
+    }
     }
 }
 
@@ -200,10 +213,10 @@ __device__ __forceinline__ void dl_stage(DlVoice& s, double* row, const int tn, 
 // (every other statement of the function is a no-op there: the first four tests fail on the flags, `holdphase = false;
 // releasephase = true` re-assigns what is already set). When the gate does not change inside the window and every
 // voice of the warp is in one of the two, the window runs those statements alone; otherwise the full state machine.
-template <int OSC, int FILT, int ENV, bool ALLFAST, int OUTMODE, bool MIX>
+template <int OSC, int FILT, int ENV, bool ALLFAST, int OUTMODE, bool MIX, bool MODK>
 __device__ __forceinline__ void dl_window(DlVoice& s, double* row, const int tn, const int t0, const BankArgs& a, const DelayArgs& d,
                                           const size_t V, const size_t v, const int lane, const int gwarp, double* mixtile, const int swz) {
-    if (a.freq_tv || a.cutoff_tv) {       // warp-uniform (kernel arguments)
+    if (MODK) {
         dl_stage<OSC, FILT, ENV, ALLFAST, OUTMODE, MIX, false, true>(s, row, tn, t0, a, d, V, v, lane, gwarp, mixtile, false, swz);
         return;
     }
@@ -221,7 +234,7 @@ __device__ __forceinline__ void dl_window(DlVoice& s, double* row, const int tn,
     dl_stage<OSC, FILT, ENV, ALLFAST, OUTMODE, MIX, false>(s, row, tn, t0, a, d, V, v, lane, gwarp, mixtile, false, swz);
 }
 
-template <int OSC, int FILT, int ENV, int OUTMODE, bool MIX>
+template <int OSC, int FILT, int ENV, int OUTMODE, bool MIX, bool MODK = false>
 __global__ void __launch_bounds__(DelayShape<MIX>::kThreads) delay_bank_kernel(const BankArgs a, const DelayArgs d) {
     const int lane = threadIdx.x & 31;
     const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -251,7 +264,7 @@ __global__ void __launch_bounds__(DelayShape<MIX>::kThreads) delay_bank_kernel(c
         s.fr.c0 = a.cf[0][vv]; s.fr.c1 = a.cf[1][vv];
         if (FILT != FILT_T_LORES && FILT != FILT_T_HIRES) { s.fr.c2 = a.cf[2][vv]; s.fr.c3 = a.cf[3][vv]; s.fr.c4 = a.cf[4][vv]; }
     }
-    s.res = a.cutoff_tv ? a.res[vv] : 0.0;
+    s.res = (MODK && a.cutoff_tv) ? a.res[vv] : 0.0;
     if (ENV) {
         s.er.amp = a.env_amp[vv]; s.er.output = a.env_output[vv];
         s.er.att = a.env_att[vv]; s.er.dec = a.env_dec[vv]; s.er.sus = a.env_sus[vv]; s.er.rel = a.env_rel[vv];
@@ -351,7 +364,7 @@ __global__ void __launch_bounds__(DelayShape<MIX>::kThreads) delay_bank_kernel(c
             }
             mbar_wait(&bar[sidx], par);                                     // window k has landed
 #endif
-            dl_window<OSC, FILT, ENV, true, OUTMODE, MIX>(s, buf + lane * kDlChunk, tn, t0, a, d, V, (size_t)vv, lane, gwarp, mixtile, swz);
+            dl_window<OSC, FILT, ENV, true, OUTMODE, MIX, MODK>(s, buf + lane * kDlChunk, tn, t0, a, d, V, (size_t)vv, lane, gwarp, mixtile, swz);
 #ifdef MXB_DL_NO_TMA
             // ... and the write-back as a plain coalesced copy of the staged image (8 x 512 B per warp). The buffer is free as soon as
             // every lane has read its part; every lane later re-reads (cp.async) exactly the bytes it stored: program order is enough.
@@ -411,7 +424,7 @@ __global__ void __launch_bounds__(DelayShape<MIX>::kThreads) delay_bank_kernel(c
             cp_async_commit();
             cp_async_wait1();
             __syncwarp();
-            dl_window<OSC, FILT, ENV, false, OUTMODE, MIX>(s, buf + lane * kDlRow, tn, t0, a, d, V, (size_t)vv, lane, gwarp, mixtile, dl_swz((size_t)lane));
+            dl_window<OSC, FILT, ENV, false, OUTMODE, MIX, MODK>(s, buf + lane * kDlRow, tn, t0, a, d, V, (size_t)vv, lane, gwarp, mixtile, dl_swz((size_t)lane));
             __syncwarp();
 #pragma unroll 4
             for (int q = 0; q < 32 / kDlVoicesPerReq; ++q) {
@@ -447,12 +460,12 @@ __global__ void __launch_bounds__(DelayShape<MIX>::kThreads) delay_bank_kernel(c
     }
 }
 
-template <int OSC, int FILT, int ENV, int OUTMODE, bool MIX>
+template <int OSC, int FILT, int ENV, int OUTMODE, bool MIX, bool MODK>
 inline int launch_delay_one(const BankArgs& a, const DelayArgs& d, int grid, cudaStream_t s) {
     constexpr int threads = DelayShape<MIX>::kThreads;
     constexpr size_t smem = sizeof(double) * (threads / 32) * (kDlStages * kStageDoubles + (MIX ? kMixDoubles : 0));
     grid = (a.V + threads - 1) / threads;
-    auto kern = delay_bank_kernel<OSC, FILT, ENV, OUTMODE, MIX>;
+    auto kern = delay_bank_kernel<OSC, FILT, ENV, OUTMODE, MIX, MODK>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { set_error("delay_bank_kernel smem attribute (%zu B): %s", smem, cudaGetErrorString(e)); return MXB_ERR_CUDA; }
     kern<<<grid, threads, smem, s>>>(a, d);
@@ -461,16 +474,17 @@ inline int launch_delay_one(const BankArgs& a, const DelayArgs& d, int grid, cud
     return MXB_OK;
 }
 
-// outmode: DL_OUT_*; at least one of outmode / mix is set
-template <int FILT>
+// outmode: DL_OUT_*; at least one of outmode / mix is set. MODK: the instantiations for blocks with a per-sample frequency / cutoff
+// (their own translation units, delay_km_*.cu)
+template <int FILT, bool MODK = false>
 inline int launch_delay_filt(const BankArgs& a, const DelayArgs& d, int osc_saw, int env, int outmode, bool mix, int grid, cudaStream_t s) {
 #define MXB_D3(O, E)                                                                                       \
     do {                                                                                                   \
-        if (outmode == DL_OUT_F64)      return mix ? launch_delay_one<O, FILT, E, DL_OUT_F64, true>(a, d, grid, s)   \
-                                                   : launch_delay_one<O, FILT, E, DL_OUT_F64, false>(a, d, grid, s); \
-        else if (outmode == DL_OUT_F32) return mix ? launch_delay_one<O, FILT, E, DL_OUT_F32, true>(a, d, grid, s)   \
-                                                   : launch_delay_one<O, FILT, E, DL_OUT_F32, false>(a, d, grid, s); \
-        else                            return launch_delay_one<O, FILT, E, DL_OUT_NONE, true>(a, d, grid, s);       \
+        if (outmode == DL_OUT_F64)      return mix ? launch_delay_one<O, FILT, E, DL_OUT_F64, true, MODK>(a, d, grid, s)   \
+                                                   : launch_delay_one<O, FILT, E, DL_OUT_F64, false, MODK>(a, d, grid, s); \
+        else if (outmode == DL_OUT_F32) return mix ? launch_delay_one<O, FILT, E, DL_OUT_F32, true, MODK>(a, d, grid, s)   \
+                                                   : launch_delay_one<O, FILT, E, DL_OUT_F32, false, MODK>(a, d, grid, s); \
+        else                            return launch_delay_one<O, FILT, E, DL_OUT_NONE, true, MODK>(a, d, grid, s);       \
     } while (0)
     if (osc_saw) { if (env) MXB_D3(OSC_T_SAW, 1); else MXB_D3(OSC_T_SAW, 0); }
     else         { if (env) MXB_D3(OSC_T_GENERIC, 1); else MXB_D3(OSC_T_GENERIC, 0); }

@@ -52,5 +52,12 @@ int launch_delay_hires(const BankArgs& a, const DelayArgs& d, int osc_saw, int e
 int launch_delay_svf(const BankArgs& a, const DelayArgs& d, int osc_saw, int env, int outmode, bool mix, int grid, cudaStream_t s);
 int launch_delay_svf_lp(const BankArgs& a, const DelayArgs& d, int osc_saw, int env, int outmode, bool mix, int grid, cudaStream_t s);
 int launch_delay_biquad(const BankArgs& a, const DelayArgs& d, int osc_saw, int env, int outmode, bool mix, int grid, cudaStream_t s);
+// ... and for blocks with a per-sample oscillator frequency / filter cutoff (delay_km_*.cu)
+int launch_delay_none_mod(const BankArgs& a, const DelayArgs& d, int osc_saw, int env, int outmode, bool mix, int grid, cudaStream_t s);
+int launch_delay_lores_mod(const BankArgs& a, const DelayArgs& d, int osc_saw, int env, int outmode, bool mix, int grid, cudaStream_t s);
+int launch_delay_hires_mod(const BankArgs& a, const DelayArgs& d, int osc_saw, int env, int outmode, bool mix, int grid, cudaStream_t s);
+int launch_delay_svf_mod(const BankArgs& a, const DelayArgs& d, int osc_saw, int env, int outmode, bool mix, int grid, cudaStream_t s);
+int launch_delay_svf_lp_mod(const BankArgs& a, const DelayArgs& d, int osc_saw, int env, int outmode, bool mix, int grid, cudaStream_t s);
+int launch_delay_biquad_mod(const BankArgs& a, const DelayArgs& d, int osc_saw, int env, int outmode, bool mix, int grid, cudaStream_t s);
 
 }  // namespace mxb

@@ -1,0 +1,8 @@
+// Explicit instantiations of the K2 delay-line bank kernel for FILT_T_NONE, blocks with a per-sample frequency / cutoff (see delay_impl.cuh).
+#include "delay_impl.cuh"
+
+namespace mxb {
+int launch_delay_none_mod(const BankArgs& a, const DelayArgs& d, int osc_saw, int env, int outmode, bool mix, int grid, cudaStream_t s) {
+    return launch_delay_filt<FILT_T_NONE, true>(a, d, osc_saw, env, outmode, mix, grid, s);
+}
+}  // namespace mxb

@@ -1,7 +1,10 @@
-# round 2, run Z: trigger streams as packed bits (parity across the three element types, the patch leg with 32 MiB of triggers per block)
+# round 2, run Z: the modulated K2 window body and the C++ layer's per-sample signatures (new parity tests), and the delay leg again
+# (the block-constant windows must keep their time: 2.33e11 / 0.855 before the change)
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_patch.py -m gpu -q > gpurun_out/z_pytest.log 2>&1; grep -E "^(FAILED|ERROR)" gpurun_out/z_pytest.log | head; tail -3 gpurun_out/z_pytest.log
-timeout 300 python bench.py --workload patch --steps 20 --warmup 3 > gpurun_out/z_bench_patch.json 2>gpurun_out/z_bench_patch.err; tail -c 400 gpurun_out/z_bench_patch.err
-python -c "
-import json
-d=json.loads(open('gpurun_out/z_bench_patch.json').read().strip().splitlines()[-1]); print('patch', d['value'], round(d['roofline']['frac'],4), d['ms_per_step'], 'interp', d['interpreter']['value'], 'e2e', d['e2e']['value'], d['e2e']['frac_of_resident'], 'cpu', d['cpu_baseline']['value'])"
+timeout 400 python -m pytest tests/test_gpu_bank.py -m gpu -q -x -k "modulated or refused or delay or trigger or config2" > gpurun_out/z_pytest_bank.log 2>&1; tail -4 gpurun_out/z_pytest_bank.log
+timeout 300 python -m pytest tests/test_cpp_dropin.py -m gpu -q -x > gpurun_out/z_pytest_cpp.log 2>&1; tail -4 gpurun_out/z_pytest_cpp.log
+for i in 1 2; do
+timeout 300 python bench.py --workload delay --steps 40 --warmup 5 --no-cpu --no-extras 2>/dev/null | python -c "
+import sys,json
+d=json.loads([l for l in sys.stdin.read().splitlines() if l.startswith('{')][-1]); print('delay', d['value'], round(d['roofline']['frac'],4), d['roofline'].get('launch_ms_median'), 'e2e', d['e2e']['value'])"
+done
