@@ -12,7 +12,8 @@ voices are independent, so the headline block has no collective at any N.
   workloads  (N = 1, default run) the other BASELINE.json configurations measured the same way in the same run, each with
              its own value / roofline / e2e / cpu_baseline:  biquad_bank = configs[4]'s shard in bank mode (saw ->
              maxiBiquad, output materialised), delay = configs[2] (256 Ki voices saw -> ADSR -> 4096-tap delay line),
-             mfcc = configs[3] (64 Ki channels FFT-1024 / hop 512 + 40 MFCCs, frames/s)
+             mfcc = configs[3] (64 Ki channels FFT-1024 / hop 512 + 40 MFCCs, frames/s); modulated = configs[1]'s and configs[2]'s
+             banks with a per-sample frequency array (FM; SURVEY.md 8(f) rank 1: +8 B read per voice-sample)
   mixdown    BASELINE.json configs[4] in "mix mode" (SURVEY.md 8(d) config 5), timed separately in the same run:
              1 Mi voices/GPU saw -> maxiBiquad -> maxiMix::stereo -> sum over voices, only the stereo bus is
              written; for N > 1 the bus is summed over the GPUs -- the path's only exchange step (--collective
@@ -30,6 +31,7 @@ voices are independent, so the headline block has no collective at any N.
 """
 import argparse
 import json
+import math
 import os
 import subprocess
 import sys
@@ -995,6 +997,61 @@ SPEC_WL = dict(channels=1 << 14, fft=1024, hop=512, hops_per_step=8,
                     "analysis with maxiFFTOctaveAnalyzer (averages + peaks) and maxiBark (specific / relative / total loudness) fused in")
 
 
+def modulated_leg(E, args, steps, warmup):
+    """SURVEY.md 8(f) rank 1, timed: the banks with a per-sample oscillator frequency (FM: `osc.saw(f + lfo)`, the reference takes the
+    frequency by argument on every call) -- one more 8-byte stream READ per voice-sample, resident on the device like the output.
+    fm_svf: configs[1]'s bank (K1, MOD instantiation); fm_delay: configs[2]'s bank (K2, the modulated instantiation of its windows)."""
+    torch, capi, W = E.torch, E.capi, E.W
+    dev, stream, rank = E.dev, E.stream, E.rank
+    res = {}
+    for key, wl_name in (("fm_svf", "svf"), ("fm_delay", "delay")):
+        wl = WORKLOADS[wl_name]
+        V = wl["voices"]
+        p = W.voice_params(V, seed=W.SEED + rank, delay_size=wl["delay"] or 4096)
+        bank = capi.Bank(V, osc=wl["osc"], filt=wl["filt"], env=wl["env"], delay=wl["delay"] > 0,
+                         delay_capacity=max(wl["delay"], 1), max_frames=BLOCK, ctx=E.ctx, sample_rate=SR)
+        W.configure_bank(bank, wl["filt"], p, wl["env"], wl["delay"] > 0)
+        out = torch.empty((BLOCK, V), dtype=torch.float64, device=dev)
+        # freq_tv[t][v] = f_v * (1 + 0.02 sin(2 pi 5 t / sr + v)): a 5 Hz vibrato, built in place on the device (synthetic control data)
+        ft = torch.arange(BLOCK, dtype=torch.float64, device=dev).mul_(2.0 * math.pi * 5.0 / SR)[:, None].expand(BLOCK, V).contiguous()
+        ft.add_(torch.arange(V, dtype=torch.float64, device=dev)[None, :]).sin_().mul_(0.02).add_(1.0)
+        ft.mul_(torch.from_numpy(p["freq"]).to(dev)[None, :])
+        gates = None
+        if wl["env"]:
+            on, off = W.gate(V, BLOCK, 0, seed=W.SEED + rank)
+            gates = (torch.from_numpy(on).to(dev), torch.from_numpy(off).to(dev))
+        torch.cuda.synchronize()
+
+        def step():
+            bank.process_mod_device(BLOCK, out_ptr=out.data_ptr(), freq_tv_ptr=ft.data_ptr(),
+                                    trig_on_ptr=gates[0].data_ptr() if gates else None, trig_off_ptr=gates[1].data_ptr() if gates else None,
+                                    stream=stream.cuda_stream)
+        for _ in range(warmup):
+            step()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        l0 = bank.launches
+        e0.record(stream)
+        for _ in range(steps):
+            step()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        peak, peak_src = load_peaks()
+        bytes_per = wl["bytes_per"] + 8.0
+        achieved = bytes_per * V * BLOCK / (ms * 1e-3) / 1e9
+        res[key] = {"value": V * BLOCK / (ms * 1e-3), "unit": "samples/s", "ms_per_step": ms, "steps": steps, "warmup": warmup,
+                    "gpu_launches": bank.launches - l0,
+                    "config": {"workload": wl["desc"] + " + per-sample frequency freq_tv[1024][V] fp64 (device-resident)", "voices_per_gpu": V,
+                               "block": BLOCK, "l2": "no flush needed: each step streams far more than the 126 MB L2"},
+                    "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                                 "algorithmic_bytes_per_voice_sample": bytes_per, "peak_source": peak_src,
+                                 "kernel": "delay_bank_kernel<..., MODK>" if wl["delay"] else "bank_kernel<..., MOD = 1>"}}
+        del bank, out, ft
+        torch.cuda.empty_cache()
+    return res
+
+
 def spectral_extra_leg(E, args, steps, warmup):
     """The rows of SURVEY.md 8(f) around the transform that the MFCC leg does not touch: the full-spectrum analysis (cartToPol incl.
     atan2), the octave-analyser / Bark epilogues, and maxiIFFT. Each sub-leg: CUDA events over `steps` steps, algorithmic bytes."""
@@ -1080,7 +1137,7 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200")
-    ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS) + ["mfcc", "patch", "spectral"],
+    ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS) + ["mfcc", "patch", "spectral", "modulated"],
                     help="headline workload (default svf = BASELINE.json configs[1]; without this flag and with one GPU the other "
                          "configurations are measured too and reported under 'workloads')")
     ap.add_argument("--mix", type=int, default=-1,
@@ -1108,6 +1165,12 @@ def main():
         r = spectral_extra_leg(E, args, max(3, min(args.steps, 20)), args.warmup)
         if E.rank == 0:
             print(json.dumps({"metric": "fft_frames_per_sec", "unit": "frames/s", "n_gpus": E.world, "higher_is_better": True, "data": "synthetic", **r}), flush=True)
+        return finish(E)
+
+    if wl_name == "modulated":
+        r = modulated_leg(E, args, max(3, min(args.steps, 40)), args.warmup)
+        if E.rank == 0:
+            print(json.dumps({"metric": "voice_samples_per_sec", "unit": "samples/s", "n_gpus": E.world, "higher_is_better": True, "data": "synthetic", **r}), flush=True)
         return finish(E)
 
     if wl_name == "patch":
@@ -1159,6 +1222,7 @@ def main():
             r["cpu_baseline"] = cpu_baseline_patch(3.0)
         extras["patch"] = r
         extras["spectral_extras"] = spectral_extra_leg(E, args, 5, 3)
+        extras["modulated"] = modulated_leg(E, args, max(3, min(args.steps, 20)), xw)
     if E.rank == 0:
         line = {"metric": "voice_samples_per_sec", "value": head["value"], "unit": "samples/s", "n_gpus": E.world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "weak",

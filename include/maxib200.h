@@ -353,6 +353,9 @@ int32_t mxb_exchange_connect(mxb_exchange* ex, const void* all_handles /* world 
 int32_t mxb_exchange_status(mxb_exchange* ex, int32_t* timed_out_ranks);
 int32_t mxb_exchange_destroy(mxb_exchange* ex);
 int32_t mxb_bank_set_exchange(mxb_bank* bank, mxb_exchange* ex /* NULL detaches */);
+/* ... and a voice patch's bus likewise (the patch's mix-reduce kernel has the same exchange fused in): a sharded polysynth ends every block
+ * with the global stereo bus on every rank. One exchange serves one bank or patch at a time (its sequence numbers count the blocks). */
+int32_t mxb_patch_set_exchange(mxb_patch* patch, mxb_exchange* ex /* NULL detaches */);
 
 /* the reference's envelope setters, vectorised: kind 0 = setAttack (1 - pow(0.01, 1/(ms*sr*0.001))),
  * 1 = setAttackMS (1/(ms/1000*sr)), 2 = setDecay == setRelease (pow(0.01, 1/(ms*sr*0.001))).

@@ -26,7 +26,7 @@ EXPORTS = [
     "mxb_ctx_synchronize", "mxb_host_alloc", "mxb_host_free",
     "mxb_bank_create", "mxb_bank_destroy", "mxb_bank_voices", "mxb_bank_set_param", "mxb_bank_set_param_async", "mxb_bank_get_state",
     "mxb_bank_get_ring", "mxb_bank_set_state", "mxb_bank_set_ring", "mxb_bank_clone", "mxb_bank_process", "mxb_bank_process_fm", "mxb_bank_process_mod", "mxb_play_block", "mxb_bank_launch_count", "mxb_env_coeffs",
-    "mxb_exchange_create", "mxb_exchange_local_handle", "mxb_exchange_connect", "mxb_exchange_status", "mxb_exchange_destroy", "mxb_bank_set_exchange",
+    "mxb_exchange_create", "mxb_exchange_local_handle", "mxb_exchange_connect", "mxb_exchange_status", "mxb_exchange_destroy", "mxb_bank_set_exchange", "mxb_patch_set_exchange",
     "mxb_stft_create", "mxb_stft_destroy", "mxb_stft_process", "mxb_stft_process2", "mxb_stft_launch_count",
     "mxb_mfcc_create", "mxb_mfcc_destroy", "mxb_mfcc_process",
     "mxb_istft_create", "mxb_istft_destroy", "mxb_istft_process",
@@ -104,6 +104,7 @@ def lib():
         "mxb_exchange_status": (i32, [vp, C.POINTER(i32)]),
         "mxb_exchange_destroy": (i32, [vp]),
         "mxb_bank_set_exchange": (i32, [vp, vp]),
+        "mxb_patch_set_exchange": (i32, [vp, vp]),
         "mxb_stft_create": (i32, [vp, i32, i32, i32, pp]),
         "mxb_stft_destroy": (i32, [vp]),
         "mxb_stft_process": (i32, [vp, vp, i64, i64, i32, i32, vp, vp, vp, vp, vp, vp, C.POINTER(i32), i32, vp]),
@@ -304,6 +305,15 @@ class Bank:
               "mxb_bank_process")
 
 
+    def process_mod_device(self, nframes, out_ptr=None, mix_ptr=None, freq_tv_ptr=None, cutoff_tv_ptr=None, delay_size_tv_ptr=None,
+                           trig_tv_ptr=None, trig_on_ptr=None, trig_off_ptr=None, f32=False, stream=0):
+        """mxb_bank_process_mod with device pointers throughout (per-sample arrays [nframes][V] resident on the device), asynchronous
+        on `stream`."""
+        mod = Modulation(_ptr(freq_tv_ptr), _ptr(cutoff_tv_ptr), _ptr(delay_size_tv_ptr), _ptr(trig_tv_ptr))
+        check(lib().mxb_bank_process_mod(self.h, nframes, C.byref(mod), _ptr(trig_on_ptr), _ptr(trig_off_ptr), _ptr(out_ptr),
+                                         F32 if f32 else F64, _ptr(mix_ptr), MEM_DEVICE, C.c_void_p(int(stream)) if stream else None),
+              "mxb_bank_process_mod")
+
     def process_split(self, nframes, out_ptr, mix, trig_on=None, trig_off=None, f32=False, stream=0, wait=True):
         """MXB_MEM_SPLIT: gates / mix are host numpy arrays, `out_ptr` is a raw device pointer (or None).
         Returns when the mix is in host memory; with wait=False (MXB_MEM_ASYNC; page-locked host arrays) as soon as the
@@ -359,7 +369,11 @@ class Exchange:
         return m.value
 
     def attach(self, bank):
-        check(lib().mxb_bank_set_exchange(bank.h, self.h), "mxb_bank_set_exchange")
+        """bank: a Bank or a Patch (its mix bus then leaves every block as the sum over all ranks)."""
+        if isinstance(bank, Patch):
+            check(lib().mxb_patch_set_exchange(bank.h, self.h), "mxb_patch_set_exchange")
+        else:
+            check(lib().mxb_bank_set_exchange(bank.h, self.h), "mxb_bank_set_exchange")
         bank._exchange = self
 
     def close(self):

@@ -278,6 +278,7 @@ struct mxb_patch {
     int64_t launches;
     int mode;              // MXB_PATCH_INTERPRET | MXB_PATCH_FUSED
     mxb_fused* fused;      // compiled on the first fused launch
+    mxb_exchange* ex;      // peer-memory mix exchange (multi-GPU), or NULL
 };
 
 namespace mxb {

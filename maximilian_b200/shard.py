@@ -35,7 +35,7 @@ def max_over_ranks(value, device):
 
 # ---- one process per GPU without torch.distributed: the peer-memory mix exchange driven over multiprocessing queues ----
 
-def _exchange_rank(rank, world, V, B, nblk, seed, q_in, q_out, results, silent_rank):
+def _exchange_rank(rank, world, V, B, nblk, seed, q_in, q_out, results, silent_rank, what="bank", tables=None):
     import numpy as np
     torch.cuda.set_device(rank)
     from maximilian_b200 import capi
@@ -43,8 +43,15 @@ def _exchange_rank(rank, world, V, B, nblk, seed, q_in, q_out, results, silent_r
     ctx = capi.Context(rank, 48000)
     p = W.voice_params(V, seed=seed)
     lo, hi = shard_range(V, rank, world)
-    bank = capi.Bank(hi - lo, osc="saw", filt="biquad", max_frames=B, ctx=ctx)
-    W.configure_bank(bank, "biquad", {k: v[lo:hi] for k, v in p.items()})
+    if what == "patch":       # the polysynth voice patch (workloads.polysynth_patch), its bus exchanged like a bank's
+        capi.set_tables(*tables, ctx=ctx)
+        pat = W.note_pattern(V, seed=seed)
+        bank = capi.Patch(W.polysynth_patch("u8"), hi - lo, max_frames=B, ctx=ctx)
+        for k, v in W.polysynth_params(V, seed=seed).items():
+            bank.set(k, np.ascontiguousarray(v[lo:hi]))
+    else:
+        bank = capi.Bank(hi - lo, osc="saw", filt="biquad", max_frames=B, ctx=ctx)
+        W.configure_bank(bank, "biquad", {k: v[lo:hi] for k, v in p.items()})
     ex = capi.Exchange(ctx, rank, world, max_doubles=2 * B)
     q_out.put((rank, ex.local_handle()))
     ex.connect(q_in.get(timeout=120))
@@ -56,19 +63,23 @@ def _exchange_rank(rank, world, V, B, nblk, seed, q_in, q_out, results, silent_r
         return
     mixes, err = [], None
     try:
-        for _ in range(nblk):
-            _, m = bank.process(B, want_out=False, want_mix=True)
+        for blk in range(nblk):
+            if what == "patch":
+                _, m = bank.process(B, {"trigger": W.note_triggers(pat, B, blk, lo, hi)}, want_out=False, want_mix=True)
+            else:
+                _, m = bank.process(B, want_out=False, want_mix=True)
             mixes.append(m.copy())
     except capi.MxbError as e:
         err = str(e)
     results.put((rank, (np.stack(mixes) if mixes else None, err, ex.status())))
 
 
-def run_exchange_ranks(world, V, B, nblk, seed=3, silent_rank=-1, timeout_ms=None):
+def run_exchange_ranks(world, V, B, nblk, seed=3, silent_rank=-1, timeout_ms=None, what="bank", tables=None):
     """Spawns `world` processes, one per GPU, each owning a voice shard of a saw -> biquad bank with the peer-memory mix
     exchange attached (the IPC handles travel through multiprocessing queues; no NCCL anywhere). Returns
     {rank: (buses [nblk][B][2] | None, error text | None, exchange status mask)}. silent_rank: that rank connects and then
-    never processes (the others must come back with a time-out error instead of hanging)."""
+    never processes (the others must come back with a time-out error instead of hanging). what="patch": the polysynth voice patch instead
+    of the bank (tables = (sine514, transition1001, sine_before) for its sinebuf LFO)."""
     import os
     import torch.multiprocessing as mp
     if timeout_ms is not None:
@@ -76,7 +87,7 @@ def run_exchange_ranks(world, V, B, nblk, seed=3, silent_rank=-1, timeout_ms=Non
     ctx = mp.get_context("spawn")
     q_ins = [ctx.Queue() for _ in range(world)]
     q_out, results = ctx.Queue(), ctx.Queue()
-    procs = [ctx.Process(target=_exchange_rank, args=(r, world, V, B, nblk, seed, q_ins[r], q_out, results, silent_rank)) for r in range(world)]
+    procs = [ctx.Process(target=_exchange_rank, args=(r, world, V, B, nblk, seed, q_ins[r], q_out, results, silent_rank, what, tables)) for r in range(world)]
     [p.start() for p in procs]
     try:
         hs = dict(q_out.get(timeout=180) for _ in range(world))

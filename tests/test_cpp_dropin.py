@@ -15,7 +15,9 @@ EXE = os.path.join(ROOT, "tests", "cpp", "patch_poly")
 
 
 def compile_patch(src=SRC, exe=EXE):
-    lib = build.build()
+    # the library is built by __graft_entry__.build() / python -m maximilian_b200.build; a test session only links against it (on the GPU box
+    # the object directory does not travel: build.build() there would recompile every kernel, minutes of GPU-box time)
+    lib = build.LIB if os.path.exists(build.LIB) else build.build()
     libdir = os.path.dirname(lib)
     cmd = ["g++", "-std=c++17", "-O2", "-Wall", "-I", os.path.join(ROOT, "include"), src, "-o", exe,
            "-L", libdir, "-lmaxib200", "-Wl,-rpath," + libdir]
