@@ -1208,21 +1208,26 @@ def main():
     if extras_wanted and E.world == 1:
         xs = max(3, min(args.steps, 40)); xw = max(3, min(args.warmup, 5))
         extras = {}
-        for key, name in (("biquad_bank", "biquad"), ("delay", "delay")):
-            r = bank_leg(E, args, name, xs, xw)
-            if not args.no_cpu:
-                r["cpu_baseline"] = cpu_baseline(WORKLOADS[name], budget_s=3.0)
+
+        def extra(key, run, cpu=None):
+            # a leg that fails is reported as such under its key; it never takes the headline line with it
+            try:
+                r = run()
+                if cpu is not None and not args.no_cpu:
+                    r["cpu_baseline"] = cpu()
+            except Exception as e:       # noqa: BLE001
+                r = {"error": f"{type(e).__name__}: {e}"}
+                try:
+                    E.torch.cuda.synchronize(); E.torch.cuda.empty_cache()
+                except Exception:    # noqa: BLE001
+                    pass
             extras[key] = r
-        r = mfcc_leg(E, args, max(3, min(args.steps, 20)), xw)
-        if not args.no_cpu:
-            r["cpu_baseline"] = cpu_baseline_mfcc(3.0)
-        extras["mfcc"] = r
-        r = patch_leg(E, args, max(3, min(args.steps, 20)), xw)
-        if not args.no_cpu:
-            r["cpu_baseline"] = cpu_baseline_patch(3.0)
-        extras["patch"] = r
-        extras["spectral_extras"] = spectral_extra_leg(E, args, 5, 3)
-        extras["modulated"] = modulated_leg(E, args, max(3, min(args.steps, 20)), xw)
+        for key, name in (("biquad_bank", "biquad"), ("delay", "delay")):
+            extra(key, lambda name=name: bank_leg(E, args, name, xs, xw), lambda name=name: cpu_baseline(WORKLOADS[name], budget_s=3.0))
+        extra("mfcc", lambda: mfcc_leg(E, args, max(3, min(args.steps, 20)), xw), lambda: cpu_baseline_mfcc(3.0))
+        extra("patch", lambda: patch_leg(E, args, max(3, min(args.steps, 20)), xw), lambda: cpu_baseline_patch(3.0))
+        extra("spectral_extras", lambda: spectral_extra_leg(E, args, 5, 3))
+        extra("modulated", lambda: modulated_leg(E, args, max(3, min(args.steps, 20)), xw))
     if E.rank == 0:
         line = {"metric": "voice_samples_per_sec", "value": head["value"], "unit": "samples/s", "n_gpus": E.world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "weak",
