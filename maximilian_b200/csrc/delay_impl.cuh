@@ -60,9 +60,10 @@ static_assert(kDlStages >= 2 && kDlStages <= 8 && kDlAhead >= 1 && kDlSlack >= 0
 constexpr int kDlVoicesPerReq = 32 / kDlT;        // voices covered by one cooperative request (2)
 // Rows (steps) of the per-warp mix tile of K2. The tile costs shared memory the window stages compete for: with 16 rows a 4-warp CTA
 // needs 65 KB (3 CTAs = 12 warps per SM), with 8 rows 48.5 KB (4 CTAs = 16 warps per SM) at twice the row-sum instructions -- K2 has
-// the fp64 slots for them (fp64 pipe 15 %), unlike K1.
+// the fp64 slots for them (fp64 pipe 15 %), unlike K1. Measured (run "final", profiles/bench_lines/r02_k2_variants.txt): out + mix 1.557 ms against
+// 1.639 ms per 256 Ki x 1024 block (0.654 against 0.617 of the HBM peak), end to end + 10 %.
 #ifndef MXB_DL_MIXROWS
-#define MXB_DL_MIXROWS 16
+#define MXB_DL_MIXROWS 8
 #endif
 constexpr int kDlMixRows = MXB_DL_MIXROWS;
 static_assert(kDlMixRows == 8 || kDlMixRows == 16, "mix tile rows");
