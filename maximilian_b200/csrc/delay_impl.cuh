@@ -143,7 +143,7 @@ __device__ __forceinline__ void dl_stage(DlVoice& s, double* row, const int tn, 
         if (MODW && a.freq_tv) {
             const bool pb = OSC == OSC_T_GENERIC && a.osc_kind == MXB_OSC_PHASORBETWEEN;
             const double fq = s.live ? a.freq_tv[(size_t)t * V + v] : 1.0;
-            s.inc = pb ? ((s.pend - s.duty) / (a.sr / fq)) : (1. / (a.sr / fq));
+            s.inc = pb ? ((s.pend - s.duty) / (a.sr / fq)) : osc_increment(a.sr, fq);
         }
         double x = osc_tick<OSC>(s.phase, s.oout, s.inc, s.duty, a.osc_kind, s.pend);
         if (ENV && ESTEADY) {

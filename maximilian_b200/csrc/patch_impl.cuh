@@ -60,7 +60,7 @@ __device__ __forceinline__ double osc_table_tick(const int kind, double& phase, 
         output = (1 - remainder) * sine[1 + ip] + remainder * sine[2 + ip];
     } else {                                 // sawn, :342-359
         if (phase >= 0.5) phase -= 1.0;
-        phase += (1. / (sr / (frequency)));
+        phase += osc_increment(sr, frequency);
         double temp = (8820.22 / frequency) * phase;
         if (temp < -0.5) temp = -0.5;
         if (temp > 0.5) temp = 0.5;
@@ -79,7 +79,7 @@ __device__ __forceinline__ double osc_table_tick(const int kind, double& phase, 
 __device__ __forceinline__ double stage_osc(const int kind, double& phase, double& oout, const double f, const double d0, const double d1, const double sr,
                                             const double* __restrict__ sine, const double* __restrict__ transition, const double sine_before) {
     if (kind >= MXB_OSC_SINEBUF) return osc_table_tick(kind, phase, oout, f, sr, sine, transition, sine_before);
-    const double inc = kind == MXB_OSC_PHASORBETWEEN ? ((d1 - d0) / (sr / (f))) : (1. / (sr / (f)));
+    const double inc = kind == MXB_OSC_PHASORBETWEEN ? ((d1 - d0) / (sr / (f))) : osc_increment(sr, f);
     return osc_tick<OSC_T_GENERIC>(phase, oout, inc, d0, kind, d1);
 }
 
@@ -188,7 +188,7 @@ __device__ __forceinline__ double delay_tick(const bool from_position, double* _
 // maxiFlanger::flange, src/maximilian.h:1167-1175: lfo.triangle(speed), size = delay + lfo*depth*delay + 1 (-> int), dl, normalise
 __device__ __forceinline__ double flanger_tick(double* __restrict__ ring, const size_t V, const int taps, const bool live, int& ph, double& lph, double& lout,
                                                const double in, const unsigned int delay, const double fb, const double speed, const double depth, const double sr) {
-    const double lfoVal = osc_tick<OSC_T_GENERIC>(lph, lout, 1. / (sr / (speed)), 0.0, MXB_OSC_TRIANGLE, 0.0);
+    const double lfoVal = osc_tick<OSC_T_GENERIC>(lph, lout, osc_increment(sr, speed), 0.0, MXB_OSC_TRIANGLE, 0.0);
     const int size = (int)(delay + (lfoVal * depth * delay) + 1);
     double outv = delay_tick(false, ring, V, taps, live, ph, in, size, fb, 0);
     const double normalise = (1 - fabs(outv));
