@@ -1045,8 +1045,8 @@ def modulated_leg(E, args, steps, warmup):
                     "config": {"workload": wl["desc"] + " + per-sample frequency freq_tv[1024][V] fp64 (device-resident)", "voices_per_gpu": V,
                                "block": BLOCK, "l2": "no flush needed: each step streams far more than the 126 MB L2"},
                     "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                                 "note": "the reference recomputes the increment 1./(sampleRate/frequency) on every call: two IEEE fp64 divisions per "
-                                         "voice-sample (kept for bit parity) put these kernels on the fp64 pipe, not on HBM",
+                                 "note": "the reference recomputes the increment 1./(sampleRate/frequency) on every call: an IEEE fp64 division and a reciprocal "
+                                         "per voice-sample, kept for bit parity (straight-line sequences, csrc/bank_kernels.cuh osc_increment_unchecked)",
                                  "algorithmic_bytes_per_voice_sample": bytes_per, "peak_source": peak_src,
                                  "kernel": "delay_bank_kernel<..., MODK>" if wl["delay"] else "bank_kernel<..., MOD = 1>"}}
         del bank, out, ft

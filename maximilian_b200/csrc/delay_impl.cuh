@@ -142,6 +142,8 @@ __device__ __forceinline__ void dl_stage(DlVoice& s, double* row, const int tn, 
         const int t = t0 + j;
         if (MODW && a.freq_tv) {
             const bool pb = OSC == OSC_T_GENERIC && a.osc_kind == MXB_OSC_PHASORBETWEEN;
+            if (MXB_FM_PREFETCH > 0 && s.live && t + MXB_FM_PREFETCH < a.n_frames)          // look-ahead on the stream, as in K1
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(a.freq_tv + (size_t)(t + MXB_FM_PREFETCH) * V + v));
             const double fq = s.live ? a.freq_tv[(size_t)t * V + v] : 1.0;
             s.inc = pb ? ((s.pend - s.duty) / (a.sr / fq)) : osc_increment(a.sr, fq);
         }
