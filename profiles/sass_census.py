@@ -14,12 +14,14 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 BUILD = os.path.join(ROOT, "maximilian_b200", "build")
 KERNELS = [
     ("K1 bank_kernel<saw, svf_lp, no env, out, no mix> (headline)", "bank_k_svf_lp.o", "bank_kernelILi2ELi4ELi0ELb1ELb0ELi0E"),
-    ("K2 delay_bank_kernel<saw, none, env, f64 out, no mix> (configs[2])", "delay_k_none.o", "delay_bank_kernelILi2ELi0ELi1ELi1ELb0E"),
+    ("K1 bank_kernel<saw, svf_lp, no env, out, no mix, MOD = 1> (configs[1] with a per-sample frequency stream)", "bank_k_svf_lp.o", "bank_kernelILi2ELi4ELi0ELb1ELb0ELi1E"),
+    ("K2 delay_bank_kernel<saw, none, env, f64 out, no mix> (configs[2])", "delay_k_none.o", "delay_bank_kernelILi2ELi0ELi1ELi1ELb0ELb0E"),
+    ("K2 delay_bank_kernel<saw, none, env, f64 out, no mix, modulated> (configs[2] with a per-sample frequency stream)", "delay_km_none.o", "delay_bank_kernelILi2ELi0ELi1ELi1ELb0ELb1E"),
     ("K4s stft_stream_kernel<MFCC only> (configs[3])", "spectral.o", "stft_stream_kernelILb0E"),
     ("K4s stft_stream_kernel<all outputs>", "spectral.o", "stft_stream_kernelILb1E"),
     ("K8 patch_kernel (interpreter)", "patch.o", "patch_kernel"),
 ]
-WATCH = ["UBLKCP", "SYNCS", "FENCE", "FMUL2", "FADD2", "FFMA2", "DMMA", "HMMA", "LDGSTS", "DADD", "DMUL", "DFMA", "FADD", "FMUL", "FFMA",
+WATCH = ["UBLKCP", "SYNCS", "FENCE", "CCTL", "FMUL2", "FADD2", "FFMA2", "DMMA", "HMMA", "LDGSTS", "DADD", "DMUL", "DFMA", "FADD", "FMUL", "FFMA",
          "SHFL", "MUFU", "LDS", "STS", "LDG", "STG", "BAR", "BRA"]
 
 print("# SASS opcode census of the measured kernels (cuobjdump -sass of the sm_100a objects in maximilian_b200/build/, static counts).")
