@@ -397,3 +397,29 @@ def test_per_sample_trigger_port_equals_reference(port, reference, filt, delay, 
         assert np.array_equal(oa, ob) and np.array_equal(ma, mb), blk
         for s_ in ("env_holdcount", "env_flags", "env_amplitude", "env_output"):
             assert np.array_equal(a.get(s_), b.get(s_)), (blk, s_)
+
+
+@pytest.mark.parametrize("osc,filt,env,cm,dsz", [("saw", "none", True, False, False), ("saw", "lores", True, True, False), ("pulse", "svf", False, True, False),
+                                                 ("phasorbetween", "biquad", True, False, False), ("sinewave", "hires", False, True, True)])
+def test_modulated_chain_with_a_delay_line_port_equals_reference(port, reference, osc, filt, env, cm, dsz):
+    """Per-sample frequency / cutoff (/ delay size / trigger) on a chain that ends in maxiDelayline::dl -- the combinations the modulated
+    instantiation of K2 is tested against (tests/test_gpu_bank.py::test_modulated_frequency_and_cutoff_with_a_delay_line compares it
+    with the port): the port itself against the compiled reference, samples, ring index and ring contents bit for bit."""
+    V, B, cap = 23, 150, 96
+    p = W.voice_params(V, seed=61, delay_size=cap, ragged_delay=True)
+    a, b = _pair(port, reference, V, osc=osc, filt=filt, env=env, delay=True, delay_capacity=cap)
+    _configure(a, filt, p, env, True); _configure(b, filt, p, env, True)
+    rng = np.random.default_rng(8)
+    for blk in range(3):
+        f = fm_frequencies(V, B, blk); cu = cutoff_sweeps(V, B, blk) if cm else None
+        tv = (rng.random((B, V)) < 0.4).astype(np.uint8) if env else None
+        sz = np.floor(1 + (cap - 1) * rng.random((B, V))) if dsz else None
+        oa, ma = a.process(B, freq_tv=f, cutoff_tv=cu, trig_tv=tv, delay_size_tv=sz, want_mix=True)
+        ob, mb = b.process(B, freq_tv=f, cutoff_tv=cu, trig_tv=tv, delay_size_tv=sz, want_mix=True)
+        assert _same(oa, ob) and _same(ma, mb), blk
+        assert _same(a.get("delay_phase"), b.get("delay_phase")), blk
+    on, off = (W.gate(V, B, 3) if env else (None, None))
+    oa, _ = a.process(B, on, off); ob, _ = b.process(B, on, off)
+    assert _same(oa, ob)
+    for v in (0, V // 2, V - 1):
+        assert _same(a.ring(v, cap), b.ring(v, cap)), v
