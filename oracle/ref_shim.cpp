@@ -402,6 +402,24 @@ int32_t mxo_istft_process(void* h, const float* mags, const float* phases, int32
     return 0;
 }
 
+/* The reference's per-sample analysis / resynthesis idiom, literally (its feature-extractor examples): every sample goes into
+ * maxiFFT::process(); maxiIFFT::process() is called on EVERY sample with the transform's current magnitudes / phases (it reads them on the
+ * first sample of each hop). fired[i] = 1 where process() returned true. Pins what the per-sample signatures of include/maximilian_b200.hpp
+ * must deliver (tests/test_oracle_vs_reference.py composes the block functions the same way). Reference library only. */
+int32_t mxo_ref_per_sample_roundtrip(const float* in, int32_t n, int32_t fft_size, int32_t hop_size, float* out, uint8_t* fired) {
+    if (!in || !out || !fired || n < 0) return -1;
+    maxiFFT f; f.setup(fft_size, hop_size, fft_size);
+    maxiIFFT g; g.setup(fft_size, hop_size, fft_size);
+    int frames = 0;
+    for (int i = 0; i < n; ++i) {
+        const bool fr = f.process(in[i], maxiFFT::WITH_POLAR_CONVERSION);
+        fired[i] = fr ? 1 : 0;
+        frames += fr ? 1 : 0;
+        out[i] = g.process(f.getMagnitudes(), f.getPhases(), maxiIFFT::SPECTRUM);
+    }
+    return frames;
+}
+
 }  // extern "C"
 
 /* ------------------------------------------------------------------ patches

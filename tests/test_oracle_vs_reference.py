@@ -423,3 +423,25 @@ def test_modulated_chain_with_a_delay_line_port_equals_reference(port, reference
     assert _same(oa, ob)
     for v in (0, V // 2, V - 1):
         assert _same(a.ring(v, cap), b.ring(v, cap)), v
+
+
+def test_per_sample_analysis_resynthesis_idiom(port, reference):
+    """`if (fft.process(sample)) ...; out = ifft.process(fft.getMagnitudes(), fft.getPhases())` on every sample, run by the compiled
+    reference (ref_shim: mxo_ref_per_sample_roundtrip), equals the block functions composed the way the C++ layer's per-sample signatures
+    compose them (tests/test_cpp_dropin.py::test_per_sample_feature_extractor_matches_oracle): a frame fires on the last sample of every
+    hop; the resynthesis reads zeros during the first hop and frame k - 1 during hop k. Bit for bit."""
+    import ctypes as C
+    lib = reference.load("reference")
+    fn = lib.mxo_ref_per_sample_roundtrip
+    fn.restype = C.c_int32
+    fn.argtypes = [C.POINTER(C.c_float), C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_float), C.POINTER(C.c_uint8)]
+    N, n, hop, bins = 6 * 1024 + 300, 1024, 512, 512
+    x = W.channel_streams(1, N, seed=45)
+    y = np.empty(N, dtype=np.float32); fired = np.empty(N, dtype=np.uint8)
+    F = fn(x.ctypes.data_as(C.POINTER(C.c_float)), N, n, hop, y.ctypes.data_as(C.POINTER(C.c_float)), fired.ctypes.data_as(C.POINTER(C.c_uint8)))
+    assert F == N // hop and np.array_equal(np.nonzero(fired)[0], hop * np.arange(1, F + 1) - 1)
+    o = port.Stft(1, n, hop, kind="port").process(x)
+    K = (N + hop - 1) // hop
+    z = np.zeros((1, 1, bins), dtype=np.float32)
+    oy = port.Istft(1, n, hop, kind="port").process(np.concatenate([z, o["mags"][:, :K - 1]], axis=1), np.concatenate([z, o["phases"][:, :K - 1]], axis=1))
+    assert np.array_equal(y, oy[0, :N])
