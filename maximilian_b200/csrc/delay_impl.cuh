@@ -39,7 +39,7 @@ constexpr int kDlT = kDlChunk;                    // steps per staged window
 constexpr int kDlRow = kDlT;                      // tile row stride in doubles: unpadded, slot j of row i at position j ^ (i % 16)
 constexpr int kStageDoubles = 32 * kDlRow;        // one staged window tile per warp (4 KB: the image one bulk copy moves)
 // CTA shape of K2. Without a mix tile a warp needs 8 KB of staging: 14 warps per CTA, 2 CTAs per SM = 28 warps/SM, and 256 Ki
-// voices (8192 voice-warps over 148 SMs) run as two full waves. With the mix tile (12.9 KB per warp): 4 warps per CTA.
+// voices (8192 voice-warps over 148 SMs) run as two full waves. With the mix tile (8-row tile: 12.1 KB per warp with the two window stages): 4 warps per CTA.
 #ifndef MXB_DL_THREADS
 #define MXB_DL_THREADS 128
 #endif
