@@ -71,6 +71,9 @@ MODS = [  # (name, osc, filt, env, delay, which per-sample arrays)
     ("saw_svf_swept_cutoff", "saw", "svf", False, False, ("cutoff",)),
     ("phasor_lores_swept_cutoff_fm", "phasor", "lores", False, False, ("cutoff", "freq")),
     ("saw_env_lores_flanged_delay", "saw", "lores", True, True, ("delay_size",)),
+    # per-sample frequency / cutoff on chains that end in a delay line (the modulated instantiations of the delay kernel)
+    ("saw_env_delay_fm", "saw", "none", True, True, ("freq",)),
+    ("pulse_svf_delay_swept_cutoff_fm", "pulse", "svf", False, True, ("cutoff", "freq")),
 ]
 
 
@@ -200,6 +203,8 @@ if __name__ == "__main__":
     O.build("reference")
     if len(sys.argv) > 1 and sys.argv[1] == "chorus":      # add this fixture without rewriting the others
         chorus()
+    elif len(sys.argv) > 1 and sys.argv[1] == "mods":
+        mods()
     else:
         chains(); seeds(); spectral(); mods(); tables(); patches(); chorus()
     for f in sorted(os.listdir(HERE)):
